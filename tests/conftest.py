@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "slow: CPU test that takes more than ~20 s")
+
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CASES = ["quickstart", "uniform300", "powerlaw500_e3", "uniform200_l3e4"]
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
