@@ -1,0 +1,838 @@
+// gpe_api.cu -- the C ABI (include/gpe.h) and the host orchestration of the three kernel groups.
+// Product code: no CPU fallback, nothing from oracle/.
+#include <algorithm>
+#include <numeric>
+
+#include "gpe_internal.h"
+#include "host_ref.h"
+
+using namespace gpe;
+
+static std::string g_create_err;
+
+namespace {
+
+struct StageTimer {
+    gpe_ctx *c;
+    float *dst;
+    StageTimer(gpe_ctx *ctx, float *d) : c(ctx), dst(d) {
+        if (c->timing) cudaEventRecord(c->ev0, c->stream);
+    }
+    ~StageTimer() {
+        if (c->timing) {
+            cudaEventRecord(c->ev1, c->stream);
+            cudaEventSynchronize(c->ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+            *dst = ms;
+        }
+    }
+};
+
+GraphView graph_view(const gpe_ctx *c) {
+    GraphView g;
+    g.V = c->V;
+    g.off = c->d_off.as<u32>();
+    g.nbr = c->d_nbr.as<u32>();
+    g.label = c->d_label.as<u32>();
+    g.deg = c->d_deg.as<u32>();
+    g.rank = c->d_rank.as<u32>();
+    g.vde = c->d_vde.as<double>();
+    g.e = c->e;
+    return g;
+}
+
+u32 host_key(const TableView &t, const u32 *labels) {
+    u32 key = 0;
+    for (u32 k = 0; k < t.L; k++)
+        if (t.key_radix[k] > 1) key += (labels[k] % t.key_radix[k]) * t.key_stride[k];
+    return key;
+}
+
+// Host-side staging of the plan paths of the current batch.
+struct QPathSet {
+    u32 L = 0, D = 0;
+    std::vector<u32> slots, labels, degs;  // n x L
+    std::vector<double> pde;               // n x D
+    u32 n() const { return L ? (u32)(labels.size() / L) : 0; }
+};
+
+int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
+    const TableView &t = c->tv;
+    const u32 L = t.L, D = t.D, n = qp.n();
+    const bool prune = !(flags & GPE_FILTER_NO_PRUNE);
+    c->b_flags = flags;
+    c->b_slots = n_slots;
+    c->b_qpaths = n;
+
+    // group plan paths into blocks of <= kQB that read the same tiles
+    std::vector<u32> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::vector<u32> keys(n, 0);
+    if (prune) {
+        for (u32 i = 0; i < n; i++) keys[i] = host_key(t, &qp.labels[(size_t)i * L]);
+        std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return keys[a] < keys[b]; });
+    }
+    const size_t rec_bytes = qblock_rec_bytes(L, t.E);
+    std::vector<QBlockHost> blocks;
+    std::vector<unsigned char> recs;
+    std::vector<u32> ids(kQB), bl(kQB * kMaxL), bd(kQB * kMaxL), bs(kQB * kMaxL);
+    std::vector<double> bp((size_t)kQB * kMaxL * kMaxE);
+    for (u32 i = 0; i < n;) {
+        u32 j = i;
+        while (j < n && j - i < (u32)kQB && (!prune || keys[order[j]] == keys[order[i]])) j++;
+        QBlockHost hb;
+        hb.n = j - i;
+        hb.first_qpath = order[i];
+        if (prune) {
+            u64 r0 = c->h_bucket_start[keys[order[i]]], r1 = c->h_bucket_start[keys[order[i]] + 1];
+            hb.t0 = (u32)(r0 / kTileRows);
+            hb.t1 = r1 > r0 ? (u32)((r1 + kTileRows - 1) / kTileRows) : hb.t0;
+        } else {
+            hb.t0 = 0;
+            hb.t1 = (u32)t.n_tiles;
+        }
+        for (u32 m = 0; m < hb.n; m++) {
+            u32 q = order[i + m];
+            ids[m] = q;
+            for (u32 k = 0; k < L; k++) {
+                bl[m * L + k] = qp.labels[(size_t)q * L + k];
+                bd[m * L + k] = qp.degs[(size_t)q * L + k];
+                bs[m * L + k] = qp.slots[(size_t)q * L + k];
+            }
+            for (u32 d = 0; d < D; d++) bp[(size_t)m * D + d] = qp.pde[(size_t)q * D + d];
+        }
+        recs.resize(recs.size() + rec_bytes);
+        qblock_pack(L, t.E, recs.data() + recs.size() - rec_bytes, hb.n, hb.first_qpath, ids.data(), bl.data(),
+                    bd.data(), bs.data(), bp.data());
+        blocks.push_back(hb);
+        i = j;
+    }
+    const u32 nb = (u32)blocks.size();
+    c->b_qblocks = nb;
+    std::vector<u32> t0(nb + 1, 0);
+    std::vector<u64> prefix(nb + 1, 0);
+    for (u32 b = 0; b < nb; b++) {
+        t0[b] = blocks[b].t0;
+        prefix[b + 1] = prefix[b] + (blocks[b].t1 - blocks[b].t0);
+    }
+    c->b_items_unpruned = prefix[nb];
+    c->b_words = ((u64)(c->V + 31) / 32 + kChunkWords - 1) / kChunkWords * kChunkWords;
+    c->b_chunks_per_slot = c->b_words / kChunkWords;
+
+    GPE_CUDA(c, c->d_qblocks.reserve(std::max<size_t>(recs.size(), 16)));
+    GPE_CUDA(c, c->d_qb_t0.reserve((nb + 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_qb_prefix.reserve((nb + 1) * sizeof(u64)));
+    GPE_CUDA(c, c->d_worklist.reserve(std::max<u64>(prefix[nb], 1) * sizeof(u64)));
+    GPE_CUDA(c, c->d_counters.reserve(8 * sizeof(u64)));
+    GPE_CUDA(c, c->d_survivors.reserve(std::max<u32>(n, 1) * sizeof(u64)));
+    GPE_CUDA(c, c->d_bitmap.reserve(std::max<u64>((u64)n_slots * c->b_words, 1) * sizeof(u32)));
+    // stage through pinned memory so the copies are asynchronous
+    size_t need = recs.size() + (nb + 1) * sizeof(u32) + (nb + 1) * sizeof(u64) + 64;
+    GPE_CUDA(c, c->h_pin.reserve(need));
+    unsigned char *pin = c->h_pin.as<unsigned char>();
+    size_t o_rec = 0, o_t0 = (recs.size() + 15) / 16 * 16, o_pf = (o_t0 + (nb + 1) * sizeof(u32) + 15) / 16 * 16;
+    GPE_CUDA(c, c->h_pin.reserve(o_pf + (nb + 1) * sizeof(u64)));
+    pin = c->h_pin.as<unsigned char>();
+    memcpy(pin + o_rec, recs.data(), recs.size());
+    memcpy(pin + o_t0, t0.data(), (nb + 1) * sizeof(u32));
+    memcpy(pin + o_pf, prefix.data(), (nb + 1) * sizeof(u64));
+    if (!recs.empty())
+        GPE_CUDA(c, cudaMemcpyAsync(c->d_qblocks.p, pin + o_rec, recs.size(), cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(c->d_qb_t0.p, pin + o_t0, (nb + 1) * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(c->d_qb_prefix.p, pin + o_pf, (nb + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    c->b_filtered = false;
+    c->b_joined = false;
+    c->stats.n_qpaths = n;
+    c->stats.n_qblocks = nb;
+    c->stats.n_slots = n_slots;
+    c->stats.scan_items_unpruned = prefix[nb];
+    return GPE_OK;
+}
+
+// bitmap -> sorted candidate lists (d_cand, d_cand_off); one host sync for the total
+int compact_candidates(gpe_ctx *c) {
+    StageTimer tm(c, &c->stats.last_compact_ms);
+    const u64 n_chunks = c->b_chunks_per_slot * c->b_slots;
+    GPE_CUDA(c, c->d_chunk_off.reserve((n_chunks + 1) * sizeof(u64)));
+    GPE_CUDA(c, c->d_cand_off.reserve(((u64)c->b_slots + 1) * sizeof(u64)));
+    GPE_CUDA(c, c->d_counters.reserve(8 * sizeof(u64)));
+    GPE_CUDA(c, k3_chunk_count(c->d_bitmap.as<u32>(), c->b_words, c->b_chunks_per_slot, c->b_slots,
+                               c->d_chunk_off.as<u64>(), c->stream));
+    GPE_CUDA(c, exclusive_scan_u64(c->d_chunk_off.as<u64>(), n_chunks + 1, c->d_scan_tmp, c->stream));
+    GPE_CUDA(c, c->h_pin2.reserve(16 * sizeof(u64)));
+    u64 *pin = c->h_pin2.as<u64>();
+    GPE_CUDA(c, cudaMemcpyAsync(pin, c->d_chunk_off.as<u64>() + n_chunks, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(pin + 1, c->d_counters.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->b_n_cand = pin[0];
+    c->stats.n_candidates = pin[0];
+    c->stats.scan_items = pin[1];
+    c->stats.scan_rows = pin[1] * kTileRows;
+    GPE_CUDA(c, c->d_cand.reserve(std::max<u64>(c->b_n_cand, 1) * sizeof(u32)));
+    if (n_chunks == 0) {
+        GPE_CUDA(c, cudaMemsetAsync(c->d_cand_off.p, 0, sizeof(u64), c->stream));
+    } else {
+        GPE_CUDA(c, k3_compact(c->d_bitmap.as<u32>(), c->b_words, c->b_chunks_per_slot, c->b_slots,
+                               c->d_chunk_off.as<u64>(), c->d_cand.as<u32>(), c->d_cand_off.as<u64>(), c->stream));
+    }
+    c->stats.compact_launches += 3;
+    return GPE_OK;
+}
+
+int run_filter(gpe_ctx *c) {
+    const u64 n_items = c->b_items_unpruned;
+    GPE_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(u64), c->stream));
+    GPE_CUDA(c, cudaMemsetAsync(c->d_survivors.p, 0, std::max<u32>(c->b_qpaths, 1) * sizeof(u64), c->stream));
+    GPE_CUDA(c, cudaMemsetAsync(c->d_bitmap.p, 0, std::max<u64>((u64)c->b_slots * c->b_words, 1) * sizeof(u32), c->stream));
+    if (n_items > 0 && c->b_qblocks > 0) {
+        {
+            StageTimer tm(c, &c->stats.last_select_ms);
+            GPE_CUDA(c, k2_select(c->tv, c->d_qblocks.p, c->d_qb_t0.as<u32>(), c->d_qb_prefix.as<u64>(), c->b_qblocks,
+                                  n_items, !(c->b_flags & GPE_FILTER_NO_PRUNE), c->d_worklist.as<u64>(),
+                                  c->d_counters.as<u64>(), c->stream));
+            c->stats.select_launches++;
+        }
+        {
+            StageTimer tm(c, &c->stats.last_scan_ms);
+            GPE_CUDA(c, k2_scan(c->tv, c->d_qblocks.p, c->d_worklist.as<u64>(), c->d_counters.as<u64>(),
+                                c->d_bitmap.as<u32>(), c->b_words, c->d_survivors.as<u64>(), c->sm_count, c->stream));
+            c->stats.scan_launches++;
+        }
+    }
+    int rc = compact_candidates(c);
+    if (rc) return rc;
+    c->b_filtered = true;
+    c->b_cand_external = false;
+    return GPE_OK;
+}
+
+int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_ebase, const u32 *q_offsets,
+                   const u32 *q_nbrs, const u32 *q_labels, const u64 *limits) {
+    const u32 n_slots = q_vbase[n_queries], n_adj = q_ebase[n_queries];
+    c->b_nq = n_queries;
+    c->h_q_vbase.assign(q_vbase, q_vbase + n_queries + 1);
+    c->h_limits.assign(n_queries, GPE_LIMIT_MAX);
+    if (limits) c->h_limits.assign(limits, limits + n_queries);
+    size_t sz[6] = {(n_queries + 1) * sizeof(u32), (n_queries + 1) * sizeof(u32), ((size_t)n_slots + n_queries) * sizeof(u32),
+                    std::max<size_t>(n_adj, 1) * sizeof(u32), std::max<size_t>(n_slots, 1) * sizeof(u32),
+                    n_queries * sizeof(u64)};
+    GPE_CUDA(c, c->d_q_vbase.reserve(sz[0]));
+    GPE_CUDA(c, c->d_q_ebase.reserve(sz[1]));
+    GPE_CUDA(c, c->d_q_offsets.reserve(sz[2]));
+    GPE_CUDA(c, c->d_q_nbrs.reserve(sz[3]));
+    GPE_CUDA(c, c->d_q_labels.reserve(sz[4]));
+    GPE_CUDA(c, c->d_limits.reserve(std::max<size_t>(sz[5], 8)));
+    GPE_CUDA(c, cudaMemcpyAsync(c->d_q_vbase.p, q_vbase, sz[0], cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(c->d_q_ebase.p, q_ebase, sz[1], cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(c->d_q_offsets.p, q_offsets, sz[2], cudaMemcpyHostToDevice, c->stream));
+    if (n_adj) GPE_CUDA(c, cudaMemcpyAsync(c->d_q_nbrs.p, q_nbrs, n_adj * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    if (n_slots) GPE_CUDA(c, cudaMemcpyAsync(c->d_q_labels.p, q_labels, n_slots * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    if (n_queries) GPE_CUDA(c, cudaMemcpyAsync(c->d_limits.p, c->h_limits.data(), sz[5], cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, c->d_order.reserve(std::max<size_t>(n_slots, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_pivot.reserve(std::max<size_t>(n_slots, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_jplan.reserve(std::max<size_t>(n_slots, 1) * sizeof(JoinDepth)));
+    GPE_CUDA(c, c->d_item_base.reserve(((size_t)n_queries + 1) * sizeof(u64)));
+    GPE_CUDA(c, c->d_answers.reserve(((size_t)n_queries + 2) * sizeof(u64)));
+    GPE_CUDA(c, c->d_match_cursor.reserve(2 * sizeof(u64)));
+    // pageable sources: make sure the copies are done before the caller's buffers go away
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    return GPE_OK;
+}
+
+int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
+    StageTimer tm(c, &c->stats.last_join_ms);
+    const u32 nq = c->b_nq;
+    GPE_CUDA(c, cudaMemsetAsync(c->d_answers.p, 0, ((size_t)nq + 2) * sizeof(u64), c->stream));
+    GPE_CUDA(c, cudaMemsetAsync(c->d_match_cursor.p, 0, 2 * sizeof(u64), c->stream));
+    GPE_CUDA(c, k3_order(nq, c->V, c->d_q_vbase.as<u32>(), c->d_q_ebase.as<u32>(), c->d_q_offsets.as<u32>(),
+                         c->d_q_nbrs.as<u32>(), c->d_q_labels.as<u32>(), c->d_cand_off.as<u64>(), c->d_order.as<u32>(),
+                         c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_item_base.as<u64>(), rank, world,
+                         c->stream));
+    u64 *answers = c->d_answers.as<u64>();
+    GPE_CUDA(c, k3_join(graph_view(c), nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
+                        c->d_cand.as<u32>(), c->d_item_base.as<u64>(), c->d_limits.as<u64>(), answers, answers + nq + 1,
+                        rank, world, d_matches, matches_cap, c->d_match_cursor.as<u64>(), c->sm_count, c->stream));
+    c->stats.join_launches += 2;
+    c->b_joined = true;
+    return GPE_OK;
+}
+
+bool check_query(gpe_ctx *c, u32 nq, const u32 *off, const u32 *nbr, std::string &why) {
+    if (nq > GPE_MAX_QUERY_VERTICES) { why = "query has more than GPE_MAX_QUERY_VERTICES vertices"; return false; }
+    if (nq == 0) { why = "empty query graph"; return false; }
+    if (off[0] != 0) { why = "query offsets must start at 0"; return false; }
+    for (u32 u = 0; u < nq; u++) {
+        if (off[u + 1] < off[u]) { why = "query offsets not monotone"; return false; }
+        for (u32 j = off[u]; j < off[u + 1]; j++) {
+            if (nbr[j] >= nq) { why = "query neighbour id out of range"; return false; }
+            if (nbr[j] == u) { why = "self loop in query graph"; return false; }
+            if (j > off[u] && nbr[j - 1] >= nbr[j]) { why = "query adjacency must be strictly ascending (simple graph)"; return false; }
+        }
+    }
+    if (!query_connected(nq, off, nbr)) {
+        // custom.h:684-704 reads an uninitialised `next_vertex` for a disconnected query
+        why = "disconnected query graph (undefined behaviour in the reference)";
+        return false;
+    }
+    (void)c;
+    return true;
+}
+
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+int gpe_abi_version(void) { return 1; }
+
+const char *gpe_last_error(const gpe_ctx *ctx) {
+    if (ctx) return ctx->err.c_str();
+    return g_create_err.c_str();
+}
+
+int gpe_create(int device, gpe_ctx **out) {
+    if (!out) return GPE_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_err = std::string("no CUDA device available (libgpe has no CPU fallback): ") +
+                       (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return GPE_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_err = "device index out of range"; return GPE_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e);
+        return GPE_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_err = std::string("libgpe is built for sm_100a (B200) only; device is ") + prop.name;
+        return GPE_ERR_UNSUPPORTED;
+    }
+    gpe_ctx *c = new gpe_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e);
+        delete c;
+        return GPE_ERR_CUDA;
+    }
+    *out = c;
+    return GPE_OK;
+}
+
+void gpe_destroy(gpe_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
+                      &c->d_offr, &c->d_ebase, &c->d_start_rows, &c->d_scan_tmp, &c->d_tiles, &c->d_vids, &c->d_sum_u32, &c->d_sum_f64,
+                      &c->d_bucket, &c->d_cursor, &c->d_qblocks, &c->d_qb_t0, &c->d_qb_prefix, &c->d_worklist,
+                      &c->d_counters, &c->d_bitmap, &c->d_survivors, &c->d_chunk_cnt, &c->d_chunk_off, &c->d_cand,
+                      &c->d_cand_off, &c->d_q_vbase, &c->d_q_ebase, &c->d_q_offsets, &c->d_q_nbrs, &c->d_q_labels,
+                      &c->d_limits, &c->d_order, &c->d_pivot, &c->d_jplan, &c->d_item_base, &c->d_answers,
+                      &c->d_matches, &c->d_match_cursor};
+    for (DevBuf *b : bufs) b->release();
+    c->h_pin.release();
+    c->h_pin2.release();
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void *gpe_stream(gpe_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int gpe_sync(gpe_ctx *c) {
+    if (!c) return GPE_ERR_INVALID;
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    return GPE_OK;
+}
+
+int gpe_set_timing(gpe_ctx *c, int enabled) {
+    if (!c) return GPE_ERR_INVALID;
+    c->timing = enabled != 0;
+    return GPE_OK;
+}
+
+int gpe_get_stats(gpe_ctx *c, gpe_stats *out) {
+    if (!c || !out) return GPE_ERR_INVALID;
+    c->stats.table_rows = c->tv.n_rows;
+    c->stats.table_tiles = c->tv.n_tiles;
+    c->stats.tile_rows = kTileRows;
+    c->stats.row_bytes = c->tv.L ? (u64)c->tv.L * 8 + (u64)c->tv.D * 8 : 0;
+    *out = c->stats;
+    return GPE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int gpe_set_graph(gpe_ctx *c, uint32_t V, const uint32_t *offsets, const uint32_t *nbrs, const uint32_t *labels) {
+    if (!c || !offsets || !labels || (V && !nbrs && offsets[V])) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    if (offsets[0] != 0) return c->fail(GPE_ERR_INVALID, "offsets[0] must be 0");
+    const u32 n_adj = offsets[V];
+    std::vector<u32> deg(V);
+    u32 max_label = 0, max_deg = 0;
+    for (u32 v = 0; v < V; v++) {
+        if (offsets[v + 1] < offsets[v]) return c->fail(GPE_ERR_INVALID, "offsets not monotone at vertex %u", v);
+        deg[v] = offsets[v + 1] - offsets[v];
+        max_deg = std::max(max_deg, deg[v]);
+        max_label = std::max(max_label, labels[v]);
+        for (u32 j = offsets[v]; j < offsets[v + 1]; j++) {
+            if (nbrs[j] >= V) return c->fail(GPE_ERR_INVALID, "neighbour id out of range at vertex %u", v);
+            if (nbrs[j] == v) return c->fail(GPE_ERR_INVALID, "self loop at vertex %u (simple graphs only)", v);
+            if (j > offsets[v] && nbrs[j - 1] >= nbrs[j])
+                return c->fail(GPE_ERR_INVALID, "adjacency of vertex %u not strictly ascending (sorted, no duplicate edges)", v);
+        }
+    }
+    if (max_label >= 0x7fffffffu) return c->fail(GPE_ERR_INVALID, "labels must be < 2^31");
+    c->V = V;
+    c->n_adj = n_adj;
+    c->n_labels = V ? max_label + 1 : 0;
+    c->max_degree = max_deg;
+    GPE_CUDA(c, c->d_off.reserve(((size_t)V + 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_nbr.reserve(std::max<size_t>(n_adj, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_label.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_deg.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
+    GPE_CUDA(c, cudaMemcpyAsync(c->d_off.p, offsets, ((size_t)V + 1) * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    if (n_adj) GPE_CUDA(c, cudaMemcpyAsync(c->d_nbr.p, nbrs, (size_t)n_adj * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    if (V) GPE_CUDA(c, cudaMemcpyAsync(c->d_label.p, labels, (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    if (V) GPE_CUDA(c, cudaMemcpyAsync(c->d_deg.p, deg.data(), (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->have_graph = true;
+    c->have_emb = c->have_enum = c->have_table = false;
+    return GPE_OK;
+}
+
+int gpe_set_embeddings(gpe_ctx *c, uint32_t e, const double *vde) {
+    if (!c || !vde) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
+    if (!c->have_graph) return c->fail(GPE_ERR_INVALID, "gpe_set_graph first");
+    if (e == 0 || e > (u32)kMaxE) return c->fail(GPE_ERR_UNSUPPORTED, "embedding dimension %u not in 1..%d", e, kMaxE);
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    c->e = e;
+    GPE_CUDA(c, c->d_vde.reserve(std::max<size_t>((size_t)c->V * e, 1) * sizeof(double)));
+    if (c->V) GPE_CUDA(c, cudaMemcpyAsync(c->d_vde.p, vde, (size_t)c->V * e * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->have_emb = true;
+    c->have_table = false;
+    return GPE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int gpe_enumerate(gpe_ctx *c, uint32_t L, const uint32_t *sorted_nodes, const uint32_t *membership, uint32_t p,
+                  uint64_t *rows_per_partition, uint64_t *n_rows) {
+    if (!c || !sorted_nodes || !membership || p == 0) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
+    if (!c->have_graph) return c->fail(GPE_ERR_INVALID, "gpe_set_graph first");
+    if (L != 3 && L != 4)
+        return c->fail(GPE_ERR_UNSUPPORTED, "path length l=%u unsupported: kernels are built for l=2 and l=3 "
+                                            "(the reference itself only handles l=2, SURVEY.md F5)", L - 1);
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    const u32 V = c->V;
+    std::vector<u32> rank(V, 0xffffffffu), offr((size_t)V + 1, 0), h_off((size_t)V + 1);
+    GPE_CUDA(c, cudaMemcpy(h_off.data(), c->d_off.p, ((size_t)V + 1) * sizeof(u32), cudaMemcpyDeviceToHost));
+    for (u32 i = 0; i < V; i++) {
+        u32 v = sorted_nodes[i];
+        if (v >= V || rank[v] != 0xffffffffu) return c->fail(GPE_ERR_INVALID, "sorted_nodes is not a permutation of the vertices");
+        rank[v] = i;
+        if (membership[v] >= p) return c->fail(GPE_ERR_INVALID, "membership[%u]=%u outside [0,%u)", v, membership[v], p);
+        offr[i + 1] = offr[i] + (h_off[v + 1] - h_off[v]);
+    }
+    c->L = L;
+    c->p = p;
+    c->h_member.assign(membership, membership + V);
+    GPE_CUDA(c, c->d_rank.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_sorted.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_member.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_offr.reserve(((size_t)V + 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_ebase.reserve(((size_t)c->n_adj + 1) * sizeof(u64)));
+    GPE_CUDA(c, c->d_start_rows.reserve(((size_t)V + 1 + p) * sizeof(u64)));  // start_rows | part_rows
+    if (V) {
+        GPE_CUDA(c, cudaMemcpyAsync(c->d_rank.p, rank.data(), (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+        GPE_CUDA(c, cudaMemcpyAsync(c->d_sorted.p, sorted_nodes, (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+        GPE_CUDA(c, cudaMemcpyAsync(c->d_member.p, membership, (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    }
+    GPE_CUDA(c, cudaMemcpyAsync(c->d_offr.p, offr.data(), ((size_t)V + 1) * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+
+    u64 *ebase = c->d_ebase.as<u64>();
+    u64 *start_rows = c->d_start_rows.as<u64>();
+    u64 *part_rows = start_rows + V + 1;
+    {
+        StageTimer tm(c, &c->stats.last_enumerate_ms);
+        GPE_CUDA(c, cudaMemsetAsync(ebase + c->n_adj, 0, sizeof(u64), c->stream));
+        GPE_CUDA(c, cudaMemsetAsync(part_rows, 0, p * sizeof(u64), c->stream));
+        GPE_CUDA(c, k1_count(graph_view(c), L, c->d_sorted.as<u32>(), c->d_offr.as<u32>(), ebase, c->sm_count, c->stream));
+        GPE_CUDA(c, exclusive_scan_u64(ebase, (u64)c->n_adj + 1, c->d_scan_tmp, c->stream));
+        GPE_CUDA(c, k1_rows_per_partition(V, c->d_sorted.as<u32>(), c->d_offr.as<u32>(), ebase, c->d_member.as<u32>(),
+                                          part_rows, start_rows, c->stream));
+    }
+    c->stats.build_launches += 3;
+    std::vector<u64> host((size_t)V + 1 + p);
+    GPE_CUDA(c, cudaMemcpyAsync(host.data(), start_rows, host.size() * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->h_bucket_start.clear();
+    c->n_rows = host[V];
+    if (rows_per_partition) std::copy(host.begin() + V + 1, host.end(), rows_per_partition);
+    if (n_rows) *n_rows = c->n_rows;
+    c->have_enum = true;
+    c->have_table = false;
+    return GPE_OK;
+}
+
+int gpe_start_rows(gpe_ctx *c, uint64_t *start_row) {
+    if (!c || !start_row) return GPE_ERR_INVALID;
+    if (!c->have_enum) return c->fail(GPE_ERR_INVALID, "gpe_enumerate first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    GPE_CUDA(c, cudaMemcpy(start_row, c->d_start_rows.p, ((size_t)c->V + 1) * sizeof(u64), cudaMemcpyDeviceToHost));
+    return GPE_OK;
+}
+
+int gpe_dump_paths(gpe_ctx *c, uint64_t first, uint64_t n, uint32_t *vids) {
+    if (!c || (!vids && n)) return GPE_ERR_INVALID;
+    if (!c->have_enum) return c->fail(GPE_ERR_INVALID, "gpe_enumerate first");
+    if (first + n > c->n_rows) return c->fail(GPE_ERR_INVALID, "rows [%llu,%llu) outside the table of %llu rows",
+                                              (unsigned long long)first, (unsigned long long)(first + n), (unsigned long long)c->n_rows);
+    if (n == 0) return GPE_OK;
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    std::vector<u64> start((size_t)c->V + 1);
+    GPE_CUDA(c, cudaMemcpy(start.data(), c->d_start_rows.p, start.size() * sizeof(u64), cudaMemcpyDeviceToHost));
+    u32 lo = (u32)(std::upper_bound(start.begin(), start.end(), first) - start.begin() - 1);
+    u32 hi = (u32)(std::upper_bound(start.begin(), start.end(), first + n - 1) - start.begin() - 1);
+    if (hi >= c->V) hi = c->V - 1;
+    DevBuf out;
+    GPE_CUDA(c, out.reserve(n * c->L * sizeof(u32)));
+    cudaError_t e = k1_dump(graph_view(c), c->L, c->d_sorted.as<u32>(), c->d_offr.as<u32>(), c->d_ebase.as<u64>(), lo, hi,
+                            first, n, out.as<u32>(), c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(vids, out.p, n * c->L * sizeof(u32), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    out.release();
+    GPE_CUDA(c, e);
+    return GPE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int gpe_build_table(gpe_ctx *c, const uint8_t *part_select, uint64_t *n_table_rows) {
+    if (!c) return GPE_ERR_INVALID;
+    if (!c->have_enum || !c->have_emb) return c->fail(GPE_ERR_INVALID, "gpe_enumerate and gpe_set_embeddings first");
+    if (!k2_supported(c->L, c->e))
+        return c->fail(GPE_ERR_UNSUPPORTED, "no scan kernel compiled for L=%u, e=%u (L in {3,4}, e in {1,2,3,4,8})", c->L, c->e);
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    TableView t{};
+    t.L = c->L;
+    t.E = c->e;
+    t.D = c->L * c->e;
+    t.tile_bytes = kTileRows * (8 * t.L + 8 * t.D);
+    // label-sequence directory: mixed radix over the label alphabet, truncated to kKeyBudget buckets
+    u64 budget = kKeyBudget;
+    for (u32 k = 0; k < (u32)kMaxL; k++) t.key_radix[k] = 1;
+    for (u32 k = 0; k < t.L; k++) {
+        u64 r = std::min<u64>(std::max<u32>(c->n_labels, 1), budget);
+        t.key_radix[k] = (u32)std::max<u64>(r, 1);
+        budget = std::max<u64>(budget / t.key_radix[k], 1);
+    }
+    u64 stride = 1;
+    for (int k = (int)t.L - 1; k >= 0; k--) { t.key_stride[k] = (u32)stride; stride *= t.key_radix[k]; }
+    for (u32 k = t.L; k < (u32)kMaxL; k++) t.key_stride[k] = 0;
+    t.n_keys = (u32)stride;
+
+    DevBuf d_sel;
+    const unsigned char *sel = nullptr;
+    if (part_select) {
+        GPE_CUDA(c, d_sel.reserve(c->p));
+        GPE_CUDA(c, cudaMemcpy(d_sel.p, part_select, c->p, cudaMemcpyHostToDevice));
+        sel = d_sel.as<unsigned char>();
+    }
+    GPE_CUDA(c, c->d_bucket.reserve(((size_t)t.n_keys + 1) * sizeof(u64)));
+    GPE_CUDA(c, c->d_cursor.reserve(((size_t)t.n_keys + 1) * sizeof(u64)));
+    u64 *bucket = c->d_bucket.as<u64>();
+    GraphView g = graph_view(c);
+    cudaEvent_t b0, b1;
+    cudaEventCreate(&b0);
+    cudaEventCreate(&b1);
+    cudaEventRecord(b0, c->stream);
+    GPE_CUDA(c, cudaMemsetAsync(bucket, 0, ((size_t)t.n_keys + 1) * sizeof(u64), c->stream));
+    GPE_CUDA(c, k1_histogram(g, t, c->d_sorted.as<u32>(), c->d_member.as<u32>(), sel, bucket, c->sm_count, c->stream));
+    GPE_CUDA(c, exclusive_scan_u64(bucket, (u64)t.n_keys + 1, c->d_scan_tmp, c->stream));
+    c->h_bucket_start.resize((size_t)t.n_keys + 1);
+    GPE_CUDA(c, cudaMemcpyAsync(c->h_bucket_start.data(), bucket, ((size_t)t.n_keys + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    t.n_rows = c->h_bucket_start[t.n_keys];
+    t.n_tiles = (t.n_rows + kTileRows - 1) / kTileRows;
+    if (t.n_tiles >= 0xffffffffull) return c->fail(GPE_ERR_UNSUPPORTED, "table has more than 2^32 tiles");
+    const size_t tile_bytes_total = std::max<u64>(t.n_tiles, 1) * t.tile_bytes;
+    const size_t vids_bytes = std::max<u64>(t.n_tiles, 1) * t.L * kTileRows * sizeof(u32);
+    cudaError_t e1 = c->d_tiles.reserve(tile_bytes_total);
+    cudaError_t e2 = e1 == cudaSuccess ? c->d_vids.reserve(vids_bytes) : e1;
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        cudaGetLastError();
+        return c->fail(GPE_ERR_CUDA, "path table of %llu rows needs %.1f GB of HBM: %s", (unsigned long long)t.n_rows,
+                       (tile_bytes_total + vids_bytes) / 1e9, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    }
+    GPE_CUDA(c, c->d_sum_u32.reserve(std::max<u64>(t.n_tiles, 1) * 3 * t.L * sizeof(u32)));
+    GPE_CUDA(c, c->d_sum_f64.reserve(std::max<u64>(t.n_tiles, 1) * t.D * sizeof(double)));
+    t.tiles = c->d_tiles.as<unsigned char>();
+    t.vids = c->d_vids.as<u32>();
+    t.lab_min = c->d_sum_u32.as<u32>();
+    t.lab_max = t.lab_min + t.n_tiles * t.L;
+    t.deg_max = t.lab_max + t.n_tiles * t.L;
+    t.pde_max = c->d_sum_f64.as<double>();
+    t.bucket_start = bucket;
+    if (t.n_tiles) {
+        // only the tail of the last tile is never written
+        GPE_CUDA(c, cudaMemsetAsync(t.tiles + (t.n_tiles - 1) * t.tile_bytes, 0, t.tile_bytes, c->stream));
+        GPE_CUDA(c, cudaMemsetAsync(t.vids + (t.n_tiles - 1) * t.L * kTileRows, 0, t.L * kTileRows * sizeof(u32), c->stream));
+    }
+    GPE_CUDA(c, cudaMemcpyAsync(c->d_cursor.p, bucket, ((size_t)t.n_keys + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+    GPE_CUDA(c, k1_fill(g, t, c->d_sorted.as<u32>(), c->d_member.as<u32>(), sel, c->d_cursor.as<u64>(), c->sm_count, c->stream));
+    GPE_CUDA(c, k1_summaries(t, c->stream));
+    cudaEventRecord(b1, c->stream);
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->stats.last_build_ms, b0, b1);
+    cudaEventDestroy(b0);
+    cudaEventDestroy(b1);
+    d_sel.release();
+    c->stats.build_launches += 5;
+    c->tv = t;
+    c->have_table = true;
+    if (n_table_rows) *n_table_rows = t.n_rows;
+    return GPE_OK;
+}
+
+int gpe_dump_table(gpe_ctx *c, uint64_t first, uint64_t n, uint32_t *vids, uint32_t *labels, uint32_t *degs, double *pde) {
+    if (!c) return GPE_ERR_INVALID;
+    if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
+    if (first + n > c->tv.n_rows) return c->fail(GPE_ERR_INVALID, "row range outside the table");
+    if (n == 0) return GPE_OK;
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    const u32 L = c->tv.L, D = c->tv.D;
+    DevBuf dv, dl, dd, dp;
+    cudaError_t e = cudaSuccess;
+    if (vids && e == cudaSuccess) e = dv.reserve(n * L * sizeof(u32));
+    if (labels && e == cudaSuccess) e = dl.reserve(n * L * sizeof(u32));
+    if (degs && e == cudaSuccess) e = dd.reserve(n * L * sizeof(u32));
+    if (pde && e == cudaSuccess) e = dp.reserve(n * D * sizeof(double));
+    if (e == cudaSuccess)
+        e = k1_dump_table(c->tv, first, n, vids ? dv.as<u32>() : nullptr, labels ? dl.as<u32>() : nullptr,
+                          degs ? dd.as<u32>() : nullptr, pde ? dp.as<double>() : nullptr, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (vids && e == cudaSuccess) e = cudaMemcpy(vids, dv.p, n * L * sizeof(u32), cudaMemcpyDeviceToHost);
+    if (labels && e == cudaSuccess) e = cudaMemcpy(labels, dl.p, n * L * sizeof(u32), cudaMemcpyDeviceToHost);
+    if (degs && e == cudaSuccess) e = cudaMemcpy(degs, dd.p, n * L * sizeof(u32), cudaMemcpyDeviceToHost);
+    if (pde && e == cudaSuccess) e = cudaMemcpy(pde, dp.p, n * D * sizeof(double), cudaMemcpyDeviceToHost);
+    dv.release(); dl.release(); dd.release(); dp.release();
+    GPE_CUDA(c, e);
+    return GPE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int gpe_filter(gpe_ctx *c, uint32_t n_qpaths, const uint32_t *q_vids, const uint32_t *q_labels, const uint32_t *q_degs,
+               const double *q_pde, uint32_t nq, uint32_t flags, uint64_t *cand_offsets, uint64_t *survivors) {
+    if (!c) return GPE_ERR_INVALID;
+    if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
+    if (n_qpaths && (!q_vids || !q_labels || !q_degs || !q_pde)) return c->fail(GPE_ERR_INVALID, "null plan arrays");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    const u32 L = c->tv.L, D = c->tv.D;
+    QPathSet qp;
+    qp.L = L;
+    qp.D = D;
+    for (u32 i = 0; i < n_qpaths * L; i++)
+        if (q_vids[i] >= nq) return c->fail(GPE_ERR_INVALID, "plan path vertex %u outside the query (nq=%u)", q_vids[i], nq);
+    qp.slots.assign(q_vids, q_vids + (size_t)n_qpaths * L);
+    qp.labels.assign(q_labels, q_labels + (size_t)n_qpaths * L);
+    qp.degs.assign(q_degs, q_degs + (size_t)n_qpaths * L);
+    qp.pde.assign(q_pde, q_pde + (size_t)n_qpaths * D);
+    c->b_nq = 1;
+    int rc = setup_filter(c, qp, nq, flags);
+    if (rc) return rc;
+    rc = run_filter(c);
+    if (rc) return rc;
+    if (cand_offsets)
+        GPE_CUDA(c, cudaMemcpyAsync(cand_offsets, c->d_cand_off.p, ((size_t)nq + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    if (survivors && n_qpaths)
+        GPE_CUDA(c, cudaMemcpyAsync(survivors, c->d_survivors.p, (size_t)n_qpaths * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    return GPE_OK;
+}
+
+int gpe_get_candidates(gpe_ctx *c, uint32_t *cand) {
+    if (!c || !cand) return GPE_ERR_INVALID;
+    if (!c->b_filtered) return c->fail(GPE_ERR_INVALID, "no filter result");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    if (c->b_n_cand) GPE_CUDA(c, cudaMemcpy(cand, c->d_cand.p, c->b_n_cand * sizeof(u32), cudaMemcpyDeviceToHost));
+    return GPE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+uint64_t gpe_clamp_answer(uint64_t raw_total, uint64_t limit) {
+    // custom.h:846-855: the count stops growing once it reaches the limit, and the test comes after the
+    // increment, so a limit of 0 still reports one match.
+    if (limit == 0) limit = 1;
+    return raw_total < limit ? raw_total : limit;
+}
+
+int gpe_refine(gpe_ctx *c, uint32_t nq, const uint32_t *q_offsets, const uint32_t *q_nbrs, const uint32_t *q_labels,
+               const uint64_t *cand_offsets, const uint32_t *cand, uint64_t limit, uint64_t *n_matches,
+               uint32_t *order_out, uint32_t *pivot_out, uint32_t *matches, uint64_t matches_cap) {
+    if (!c || !q_offsets || !q_labels || !cand_offsets) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
+    if (!c->have_graph) return c->fail(GPE_ERR_INVALID, "gpe_set_graph first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    std::string why;
+    if (!check_query(c, nq, q_offsets, q_nbrs, why)) return c->fail(GPE_ERR_INVALID, "%s", why.c_str());
+    const u64 total = cand_offsets[nq];
+    for (u64 i = 0; i < total; i++)
+        if (cand[i] >= c->V) return c->fail(GPE_ERR_INVALID, "candidate id out of range");
+    u32 vbase[2] = {0, nq}, ebase[2] = {0, q_offsets[nq]};
+    int rc = upload_queries(c, 1, vbase, ebase, q_offsets, q_nbrs, q_labels, &limit);
+    if (rc) return rc;
+    if (!c->d_rank.p) {  // the join never reads rank/vde, but the view wants valid pointers
+        GPE_CUDA(c, c->d_rank.reserve(16));
+    }
+    c->b_slots = nq;
+    GPE_CUDA(c, c->d_cand.reserve(std::max<u64>(total, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_cand_off.reserve(((size_t)nq + 1) * sizeof(u64)));
+    if (total) GPE_CUDA(c, cudaMemcpyAsync(c->d_cand.p, cand, total * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(c->d_cand_off.p, cand_offsets, ((size_t)nq + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    u32 *d_matches = nullptr;
+    if (matches && matches_cap) {
+        GPE_CUDA(c, c->d_matches.reserve(matches_cap * nq * sizeof(u32)));
+        d_matches = c->d_matches.as<u32>();
+    }
+    rc = run_join(c, 0, 1, d_matches, d_matches ? matches_cap : 0);
+    if (rc) return rc;
+    u64 raw = 0, n_emitted = 0;
+    GPE_CUDA(c, cudaMemcpyAsync(&raw, c->d_answers.p, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(&n_emitted, c->d_match_cursor.p, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    if (order_out) GPE_CUDA(c, cudaMemcpyAsync(order_out, c->d_order.p, nq * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    if (pivot_out) GPE_CUDA(c, cudaMemcpyAsync(pivot_out, c->d_pivot.p, nq * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (d_matches) {
+        u64 n = std::min<u64>(n_emitted, matches_cap);
+        if (n) GPE_CUDA(c, cudaMemcpy(matches, d_matches, n * nq * sizeof(u32), cudaMemcpyDeviceToHost));
+    }
+    if (n_matches) *n_matches = gpe_clamp_answer(raw, limit);
+    c->b_filtered = false;
+    return GPE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int gpe_batch_upload(gpe_ctx *c, const gpe_batch *b, uint32_t flags) {
+    if (!c || !b || !b->q_vbase || !b->q_ebase || !b->q_offsets || !b->q_labels) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
+    if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    const u32 L = c->tv.L, E = c->tv.E, D = c->tv.D;
+    QPathSet qp;
+    qp.L = L;
+    qp.D = D;
+    QueryPlan plan;
+    std::string why;
+    for (u32 q = 0; q < b->n_queries; q++) {
+        const u32 vb = b->q_vbase[q], nq = b->q_vbase[q + 1] - vb;
+        const u32 *off = b->q_offsets + vb + q;
+        const u32 *nbr = b->q_nbrs + b->q_ebase[q];
+        if (!check_query(c, nq, off, nbr, why)) return c->fail(GPE_ERR_INVALID, "query %u: %s", q, why.c_str());
+        query_plan(nq, off, nbr, b->q_labels + vb, L, E, plan);
+        for (u32 i = 0; i < plan.n * L; i++) qp.slots.push_back(vb + plan.vids[i]);
+        qp.labels.insert(qp.labels.end(), plan.labels.begin(), plan.labels.end());
+        qp.degs.insert(qp.degs.end(), plan.degs.begin(), plan.degs.end());
+        qp.pde.insert(qp.pde.end(), plan.pde.begin(), plan.pde.end());
+    }
+    int rc = upload_queries(c, b->n_queries, b->q_vbase, b->q_ebase, b->q_offsets, b->q_nbrs, b->q_labels, b->limits);
+    if (rc) return rc;
+    return setup_filter(c, qp, b->q_vbase[b->n_queries], flags);
+}
+
+int gpe_batch_filter(gpe_ctx *c) {
+    if (!c) return GPE_ERR_INVALID;
+    if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    return run_filter(c);
+}
+
+int gpe_batch_join(gpe_ctx *c, uint32_t rank, uint32_t world) {
+    if (!c) return GPE_ERR_INVALID;
+    if (!c->b_filtered) return c->fail(GPE_ERR_INVALID, "gpe_batch_filter (or gpe_batch_cand_merge) first");
+    if (world == 0 || rank >= world) return c->fail(GPE_ERR_INVALID, "bad rank/world");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    return run_join(c, rank, world, nullptr, 0);
+}
+
+int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) {
+    if (!c || !raw_counts) return GPE_ERR_INVALID;
+    if (!c->b_joined) return c->fail(GPE_ERR_INVALID, "gpe_batch_join first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    GPE_CUDA(c, c->h_pin2.reserve(std::max<size_t>(c->b_nq, 16) * sizeof(u64)));
+    GPE_CUDA(c, cudaMemcpyAsync(c->h_pin2.p, c->d_answers.p, (size_t)c->b_nq * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(raw_counts, c->h_pin2.p, (size_t)c->b_nq * sizeof(u64));
+    return GPE_OK;
+}
+
+int gpe_query_batch(gpe_ctx *c, const gpe_batch *b, uint32_t flags, uint64_t *answers) {
+    if (!c || !answers) return GPE_ERR_INVALID;
+    int rc = gpe_batch_upload(c, b, flags);
+    if (rc) return rc;
+    if ((rc = run_filter(c))) return rc;
+    if ((rc = run_join(c, 0, 1, nullptr, 0))) return rc;
+    if ((rc = gpe_batch_download(c, answers))) return rc;
+    for (u32 q = 0; q < b->n_queries; q++) answers[q] = gpe_clamp_answer(answers[q], c->h_limits[q]);
+    return GPE_OK;
+}
+
+int gpe_batch_cand_info(gpe_ctx *c, uint64_t *n_slots, uint64_t *n_cand_total) {
+    if (!c) return GPE_ERR_INVALID;
+    if (!c->b_filtered) return c->fail(GPE_ERR_INVALID, "no filter result");
+    if (n_slots) *n_slots = c->b_slots;
+    if (n_cand_total) *n_cand_total = c->b_n_cand;
+    return GPE_OK;
+}
+
+int gpe_batch_cand_export(gpe_ctx *c, void *d_counts_u32, void *d_cand_u32) {
+    if (!c || !d_counts_u32) return GPE_ERR_INVALID;
+    if (!c->b_filtered) return c->fail(GPE_ERR_INVALID, "no filter result");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    GPE_CUDA(c, k3_counts_from_offsets(c->d_cand_off.as<u64>(), c->b_slots, (u32 *)d_counts_u32, c->stream));
+    if (c->b_n_cand && d_cand_u32)
+        GPE_CUDA(c, cudaMemcpyAsync(d_cand_u32, c->d_cand.p, c->b_n_cand * sizeof(u32), cudaMemcpyDeviceToDevice, c->stream));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    return GPE_OK;
+}
+
+int gpe_batch_cand_merge(gpe_ctx *c, uint32_t world, const void *d_counts, const void *d_cand, uint64_t stride) {
+    if (!c || !d_counts || world == 0) return GPE_ERR_INVALID;
+    if (!c->b_slots && !c->b_filtered) return c->fail(GPE_ERR_INVALID, "no batch");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    GPE_CUDA(c, cudaMemsetAsync(c->d_bitmap.p, 0, std::max<u64>((u64)c->b_slots * c->b_words, 1) * sizeof(u32), c->stream));
+    GPE_CUDA(c, c->d_chunk_cnt.reserve(std::max<size_t>((size_t)world * c->b_slots, 1) * sizeof(u64)));
+    GPE_CUDA(c, k3_scatter((const u32 *)d_counts, (const u32 *)d_cand, stride, world, c->b_slots, c->d_bitmap.as<u32>(),
+                           c->b_words, c->d_chunk_cnt.as<u64>(), c->stream));
+    int rc = compact_candidates(c);
+    if (rc) return rc;
+    c->b_filtered = true;
+    c->b_cand_external = true;
+    return GPE_OK;
+}
+
+int gpe_batch_get_candidates(gpe_ctx *c, uint64_t *cand_offsets, uint32_t *cand) {
+    if (!c || !cand_offsets) return GPE_ERR_INVALID;
+    if (!c->b_filtered) return c->fail(GPE_ERR_INVALID, "no filter result");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    GPE_CUDA(c, cudaMemcpy(cand_offsets, c->d_cand_off.p, ((size_t)c->b_slots + 1) * sizeof(u64), cudaMemcpyDeviceToHost));
+    if (cand && c->b_n_cand) GPE_CUDA(c, cudaMemcpy(cand, c->d_cand.p, c->b_n_cand * sizeof(u32), cudaMemcpyDeviceToHost));
+    return GPE_OK;
+}
+
+int gpe_batch_get_plan(gpe_ctx *c, uint32_t *order, uint32_t *pivot) {
+    if (!c) return GPE_ERR_INVALID;
+    if (!c->b_joined) return c->fail(GPE_ERR_INVALID, "gpe_batch_join first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (order) GPE_CUDA(c, cudaMemcpy(order, c->d_order.p, (size_t)c->b_slots * sizeof(u32), cudaMemcpyDeviceToHost));
+    if (pivot) GPE_CUDA(c, cudaMemcpy(pivot, c->d_pivot.p, (size_t)c->b_slots * sizeof(u32), cudaMemcpyDeviceToHost));
+    return GPE_OK;
+}
+
+}  // extern "C"

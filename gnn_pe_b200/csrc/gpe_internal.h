@@ -1,0 +1,241 @@
+// gpe_internal.h -- context, device buffers and launch declarations shared by the .cu files.
+// Product code: nothing here may include or call anything under oracle/.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gpe.h"
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+namespace gpe {
+
+// ---- compile-time geometry of the scan -------------------------------------------------------
+constexpr int kTileRows = 256;   // rows per tile; one consumer thread per row
+constexpr int kQB = 8;           // query paths per query-path block
+constexpr int kStages = 4;       // TMA pipeline depth per CTA
+constexpr int kMaxL = 4;         // path positions supported by the compiled kernels (l = 2, 3)
+constexpr int kMaxE = 8;
+constexpr u32 kKeyBudget = 1u << 22;  // max label-sequence buckets of the table directory
+constexpr double kEps = 1e-6;    // custom.h:43
+
+// Grow-only device buffer.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes + bytes / 4 + 256);
+        if (e == cudaSuccess) cap = bytes + bytes / 4 + 256;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// Device-side view of the data graph and the per-vertex tables (replicated on every GPU).
+struct GraphView {
+    u32 V;
+    const u32 *off;    // V+1
+    const u32 *nbr;    // 2E, ascending per vertex
+    const u32 *label;  // V
+    const u32 *deg;    // V
+    const u32 *rank;   // V: position in membership.txt
+    const double *vde; // V x e
+    u32 e;
+};
+
+// Physical layout of the path table: tile-major blocked structure-of-arrays.
+//   scan tile t (tile_bytes each): labels[L][R] u32 | degs[L][R] u32 | pde[L*e][R] f64
+//   vids tile t:                   vids[L][R] u32   (separate array, only survivors read it)
+struct TableView {
+    u32 L, E, D;
+    u64 n_rows, n_tiles;
+    u32 tile_bytes;
+    unsigned char *tiles;
+    u32 *vids;
+    // per-tile summaries (the analogue of Partition::build_auxiliary_index, custom.h:268-364)
+    u32 *lab_min, *lab_max, *deg_max;  // [L][n_tiles]
+    double *pde_max;                   // [D][n_tiles]
+    // label-sequence directory
+    u32 key_radix[kMaxL], key_stride[kMaxL];
+    u32 n_keys;
+    const u64 *bucket_start;  // n_keys + 1
+};
+
+// One query-path block: up to kQB plan paths that share a table bucket, laid out so that one
+// cp.async.bulk brings it into shared memory next to the tile it is compared with.
+template <int L, int E>
+struct alignas(16) QBlockRec {
+    u32 n;
+    u32 first_qpath;  // index of the block's first plan path (survivor counters)
+    u32 pad[2];
+    u32 labels[kQB][L];
+    u32 degs[kQB][L];
+    u32 slot[kQB][L];   // candidate bitmap of (query, plan path vertex k)
+    u32 qpath[kQB];
+    double pde[kQB][L * E];
+};
+
+struct QBlockHost {  // layout-agnostic staging on the host
+    u32 n, first_qpath;
+    u32 t0, t1;  // tile range from the directory
+};
+
+// Per-depth join plan of one query vertex slot (filled by the order kernel).
+struct JoinDepth {
+    u32 u;          // query vertex matched at this depth (order[d])
+    u32 label;
+    u32 deg;
+    u32 pivot_depth;  // depth at which pivot[d] was matched
+    u64 bn_mask;      // depths of the other backward neighbours (generateBN, custom.h:724-755)
+};
+
+}  // namespace gpe
+
+struct gpe_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing = false;
+    std::string err;
+    gpe_stats stats{};
+
+    // graph
+    u32 V = 0, n_adj = 0, n_labels = 0, max_degree = 0;
+    gpe::DevBuf d_off, d_nbr, d_label, d_deg, d_rank, d_sorted, d_member, d_vde;
+    u32 e = 0;
+    bool have_graph = false, have_emb = false, have_enum = false, have_table = false;
+
+    // enumeration
+    u32 L = 0, p = 0;
+    gpe::DevBuf d_offr;       // u32 V+1: rank-ordered CSR offsets
+    gpe::DevBuf d_ebase;      // u64 n_adj+1: first path id of every rank-ordered (a,b) slot
+    gpe::DevBuf d_scan_tmp;   // scratch of the device-wide scan
+    gpe::DevBuf d_start_rows; // u64 V+1 (+p): first path id of every start vertex, rank order
+    u64 n_rows = 0;
+    std::vector<u32> h_member;
+
+    // table
+    gpe::TableView tv{};
+    gpe::DevBuf d_tiles, d_vids, d_sum_u32, d_sum_f64, d_bucket, d_cursor;
+    std::vector<u64> h_bucket_start;
+
+    // batch / filter state
+    u32 b_nq = 0;          // queries
+    u32 b_slots = 0;       // sum of query vertices
+    u32 b_qpaths = 0, b_qblocks = 0;
+    u32 b_flags = 0;
+    u64 b_words = 0;       // bitmap words per slot
+    u64 b_items_cap = 0, b_items_unpruned = 0;
+    u64 b_n_cand = 0;
+    bool b_filtered = false, b_joined = false, b_cand_external = false;
+    std::vector<u32> h_q_vbase, h_q_ebase, h_q_offsets, h_q_nbrs, h_q_labels;
+    std::vector<u64> h_limits;
+    std::vector<u32> h_slot_query;  // slot -> query
+    gpe::DevBuf d_qblocks, d_qb_t0, d_qb_prefix, d_worklist, d_counters, d_bitmap, d_survivors;
+    gpe::DevBuf d_chunk_cnt, d_chunk_off, d_cand, d_cand_off;
+    gpe::DevBuf d_q_vbase, d_q_ebase, d_q_offsets, d_q_nbrs, d_q_labels, d_limits;
+    gpe::DevBuf d_order, d_pivot, d_jplan, d_item_base, d_answers, d_matches, d_match_cursor;
+    gpe::PinnedBuf h_pin, h_pin2;
+    u64 b_chunks_per_slot = 0;
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define GPE_CUDA(ctx, expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return (ctx)->fail(GPE_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,           \
+                               cudaGetErrorString(e__));                                             \
+    } while (0)
+
+namespace gpe {
+
+// ---- launchers (defined in the .cu files) ------------------------------------------------------
+// device-wide exclusive scan of n u64 values, in place; total returned in d_total (device) if non-null
+cudaError_t exclusive_scan_u64(u64 *d_data, u64 n, DevBuf &tmp, cudaStream_t s);
+
+// K1
+cudaError_t k1_count(const GraphView &g, u32 L, const u32 *sorted, const u32 *offr, u64 *cnt_r, int sm_count,
+                     cudaStream_t s);
+cudaError_t k1_rows_per_partition(u32 V, const u32 *sorted, const u32 *offr, const u64 *ebase, const u32 *member,
+                                  u64 *part_rows, u64 *start_rows, cudaStream_t s);
+cudaError_t k1_dump(const GraphView &g, u32 L, const u32 *sorted, const u32 *offr, const u64 *ebase, u32 rank_lo,
+                    u32 rank_hi, u64 first, u64 n, u32 *out, cudaStream_t s);
+cudaError_t k1_histogram(const GraphView &g, const TableView &t, const u32 *sorted, const u32 *member,
+                         const unsigned char *part_sel, u64 *hist, int sm_count, cudaStream_t s);
+cudaError_t k1_fill(const GraphView &g, const TableView &t, const u32 *sorted, const u32 *member,
+                    const unsigned char *part_sel, u64 *cursor, int sm_count, cudaStream_t s);
+cudaError_t k1_summaries(const TableView &t, cudaStream_t s);
+cudaError_t k1_dump_table(const TableView &t, u64 first, u64 n, u32 *vids, u32 *labels, u32 *degs, double *pde,
+                          cudaStream_t s);
+
+// K2
+size_t qblock_rec_bytes(u32 L, u32 E);
+// labels/degs/slots: n x L, pde: n x L*E (already gathered in block order); qpath_ids: n
+void qblock_pack(u32 L, u32 E, void *dst_rec, u32 n, u32 first_qpath, const u32 *qpath_ids, const u32 *labels,
+                 const u32 *degs, const u32 *slots, const double *pde);
+cudaError_t k2_select(const TableView &t, const void *qblocks, const u32 *qb_t0, const u64 *qb_prefix, u32 n_qblocks,
+                      u64 n_items, bool prune, u64 *worklist, u64 *counters, cudaStream_t s);
+cudaError_t k2_scan(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters, u32 *bitmap,
+                    u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s);
+bool k2_supported(u32 L, u32 E);
+
+// K3 (candidate compaction, matching order, join)
+constexpr u32 kChunkWords = 256;  // bitmap words per compaction chunk
+cudaError_t k3_chunk_count(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slot, u32 n_slots, u64 *chunk_cnt,
+                           cudaStream_t s);
+cudaError_t k3_compact(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slot, u32 n_slots, const u64 *chunk_off,
+                       u32 *cand, u64 *cand_off, cudaStream_t s);
+cudaError_t k3_scatter(const u32 *counts, const u32 *cand, u64 stride, u32 world, u32 n_slots, u32 *bitmap,
+                       u64 words_per_slot, u64 *prefix_tmp /*world x n_slots*/, cudaStream_t s);
+cudaError_t k3_counts_from_offsets(const u64 *cand_off, u32 n_slots, u32 *counts, cudaStream_t s);
+cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebase, const u32 *q_offsets,
+                     const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
+                     JoinDepth *jplan, u64 *item_base, u32 rank, u32 world, cudaStream_t s);
+cudaError_t k3_join(const GraphView &g, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan, const u64 *cand_off,
+                    const u32 *cand, const u64 *item_base, const u64 *limits, u64 *answers, u64 *work_counter,
+                    u32 rank, u32 world, u32 *matches, u64 matches_cap, u64 *match_cursor, int sm_count,
+                    cudaStream_t s);
+
+}  // namespace gpe

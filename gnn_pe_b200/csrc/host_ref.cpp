@@ -1,0 +1,226 @@
+// host_ref.cpp -- host-side mirror of the reference's cheap, serial steps: the `.graph` loader,
+// vertex embeddings and the per-query plan.  Pure host C++ (no CUDA); these run in microseconds to
+// milliseconds and feed the kernels.  Product code: never includes anything from oracle/.
+//
+// Citations are relative to the reference's GNN-PE/ directory.
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <numeric>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "gpe.h"
+#include "host_ref.h"
+
+namespace gpe {
+
+// libsrc/graph/graph.cpp:163-242.  Same accepted grammar: 't V E', 'v id label degree', 'e u v';
+// CSR offsets come from the declared degrees (graph.cpp:192), adjacency sorted ascending (:231-233).
+int load_graph_file(const char *path, HostGraph &g, std::string &err) {
+    std::ifstream in(path);
+    if (!in.is_open()) {
+        err = std::string("Can not open the graph file ") + path + " .";  // graph.cpp:167
+        return GPE_ERR_IO;
+    }
+    char tag;
+    uint32_t V = 0, E = 0;
+    in >> tag >> V >> E;
+    g.offsets.assign((size_t)V + 1, 0);
+    g.nbrs.assign((size_t)E * 2, 0);
+    g.labels.assign(V, 0);
+    std::vector<uint32_t> used(V, 0);
+    while (in >> tag) {
+        if (tag == 'v') {
+            uint32_t id, label, degree;
+            in >> id >> label >> degree;
+            if (id >= V) { err = "vertex id out of range"; return GPE_ERR_INVALID; }
+            g.labels[id] = label;
+            g.offsets[id + 1] = g.offsets[id] + degree;
+        } else if (tag == 'e') {
+            uint32_t u, v;
+            in >> u >> v;
+            if (u >= V || v >= V) { err = "edge endpoint out of range"; return GPE_ERR_INVALID; }
+            size_t pu = (size_t)g.offsets[u] + used[u], pv = (size_t)g.offsets[v] + used[v];
+            if (pu >= g.nbrs.size() || pv >= g.nbrs.size() || used[u] >= g.offsets[u + 1] - g.offsets[u] ||
+                used[v] >= g.offsets[v + 1] - g.offsets[v]) {
+                err = "declared vertex degrees do not match the edge list";
+                return GPE_ERR_INVALID;
+            }
+            g.nbrs[pu] = v;
+            g.nbrs[pv] = u;
+            used[u]++;
+            used[v]++;
+        }
+    }
+    for (uint32_t v = 0; v < V; v++) std::sort(g.nbrs.begin() + g.offsets[v], g.nbrs.begin() + g.offsets[v + 1]);
+    return GPE_OK;
+}
+
+// custom.h:492-511: mt19937 seeded with the label, `e` draws of uniform_real_distribution<double>(0,1),
+// normalised by their sum.  Uses the very libstdc++ facilities the reference uses.
+static void label_embedding(uint32_t label, uint32_t e, double *out) {
+    std::mt19937 gen(label);
+    std::uniform_real_distribution<double> dis(0.0, 1.0);
+    for (uint32_t i = 0; i < e; i++) out[i] = dis(gen);
+    double sum = std::accumulate(out, out + e, 0.0);
+    for (uint32_t i = 0; i < e; i++) out[i] = out[i] / sum;
+}
+
+// custom.h:513-544.
+void gen_vde(uint32_t V, const uint32_t *off, const uint32_t *nbr, const uint32_t *labels, uint32_t e, double *x,
+             double *vde) {
+    uint32_t max_label = 0;
+    for (uint32_t v = 0; v < V; v++) max_label = std::max(max_label, labels[v]);
+    std::vector<double> table;
+    std::vector<char> have;
+    if (V) { table.resize(((size_t)max_label + 1) * e); have.assign((size_t)max_label + 1, 0); }
+    for (uint32_t v = 0; v < V; v++) {
+        uint32_t lab = labels[v];
+        if (!have[lab]) { label_embedding(lab, e, &table[(size_t)lab * e]); have[lab] = 1; }
+        std::memcpy(x + (size_t)v * e, &table[(size_t)lab * e], sizeof(double) * e);
+    }
+    for (uint32_t v = 0; v < V; v++) {
+        double *out = vde + (size_t)v * e;
+        for (uint32_t k = 0; k < e; k++) out[k] = 0.0;
+        for (uint32_t j = off[v]; j < off[v + 1]; j++) {  // ascending neighbour id, FP64 adds in that order
+            const double *xn = x + (size_t)nbr[j] * e;
+            for (uint32_t k = 0; k < e; k++) out[k] += xn[k];
+        }
+        for (uint32_t k = 0; k < e; k++) out[k] = x[(size_t)v * e + k] + out[k];
+    }
+}
+
+bool query_connected(uint32_t nq, const uint32_t *off, const uint32_t *nbr) {
+    if (nq == 0) return true;
+    std::vector<char> seen(nq, 0);
+    std::vector<uint32_t> stack(1, 0);
+    seen[0] = 1;
+    uint32_t n = 1;
+    while (!stack.empty()) {
+        uint32_t v = stack.back();
+        stack.pop_back();
+        for (uint32_t j = off[v]; j < off[v + 1]; j++)
+            if (!seen[nbr[j]]) { seen[nbr[j]] = 1; n++; stack.push_back(nbr[j]); }
+    }
+    return n == nq;
+}
+
+// The query's simple paths of L vertices in dfs_query order (custom.h:94-119, main.cpp:142-146): start
+// vertices 0..nq-1, neighbours ascending, a path kept iff its reverse was not kept earlier, i.e. iff
+// first < last (the closed form of the hash-set dedup on a simple graph).
+static void query_paths(uint32_t nq, const uint32_t *off, const uint32_t *nbr, uint32_t L, std::vector<uint32_t> &rows) {
+    uint32_t path[GPE_MAX_QUERY_VERTICES];
+    struct Rec {
+        static void go(uint32_t len, uint32_t L, uint32_t *path, const uint32_t *off, const uint32_t *nbr,
+                       std::vector<uint32_t> &rows) {
+            if (len == L) {
+                if (path[0] < path[L - 1]) rows.insert(rows.end(), path, path + L);
+                return;
+            }
+            uint32_t last = path[len - 1];
+            for (uint32_t j = off[last]; j < off[last + 1]; j++) {
+                uint32_t nb = nbr[j];
+                bool dup = false;
+                for (uint32_t k = 0; k < len; k++) dup = dup || path[k] == nb;
+                if (dup) continue;
+                path[len] = nb;
+                go(len + 1, L, path, off, nbr, rows);
+            }
+        }
+    };
+    for (uint32_t s = 0; s < nq; s++) {
+        path[0] = s;
+        Rec::go(1, L, path, off, nbr, rows);
+    }
+}
+
+// custom.h:574-633.  std::sort by weight (sum of degrees) descending -- the reference's comparator on the
+// reference's initial order, with libstdc++'s std::sort, so ties fall exactly as they do there (SURVEY.md
+// Q4) -- then the greedy vertex cover.
+void query_plan(uint32_t nq, const uint32_t *off, const uint32_t *nbr, const uint32_t *labels, uint32_t L, uint32_t e,
+                QueryPlan &plan) {
+    std::vector<uint32_t> rows;
+    query_paths(nq, off, nbr, L, rows);
+    std::vector<double> x((size_t)nq * e), vde((size_t)nq * e);
+    gen_vde(nq, off, nbr, labels, e, x.data(), vde.data());
+
+    struct Item { uint32_t weight, row; };
+    size_t n = rows.size() / L;
+    std::vector<Item> items(n);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t w = 0;
+        for (uint32_t k = 0; k < L; k++) { uint32_t v = rows[i * L + k]; w += off[v + 1] - off[v]; }
+        items[i] = Item{w, (uint32_t)i};
+    }
+    std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.weight > b.weight; });
+
+    std::vector<char> covered(nq, 0);
+    uint32_t n_covered = 0;
+    plan.n = 0;
+    plan.L = L;
+    plan.e = e;
+    plan.vids.clear(); plan.labels.clear(); plan.degs.clear(); plan.pde.clear();
+    plan.n_query_paths = (uint32_t)n;
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t *row = &rows[(size_t)items[i].row * L];
+        uint32_t inside = 0;
+        for (uint32_t k = 0; k < L; k++) inside += covered[row[k]] ? 1 : 0;
+        if (inside != L) {
+            for (uint32_t k = 0; k < L; k++) {
+                uint32_t v = row[k];
+                if (!covered[v]) { covered[v] = 1; n_covered++; }
+                plan.vids.push_back(v);
+                plan.labels.push_back(labels[v]);
+                plan.degs.push_back(off[v + 1] - off[v]);
+                for (uint32_t d = 0; d < e; d++) plan.pde.push_back(vde[(size_t)v * e + d]);
+            }
+            plan.n++;
+        }
+        if (n_covered == nq) break;
+    }
+}
+
+}  // namespace gpe
+
+// ---- C ABI ---------------------------------------------------------------------------------------------------
+static thread_local std::string g_host_err;
+const char *gpe_host_last_error_internal() { return g_host_err.c_str(); }
+
+extern "C" int gpe_host_load_graph(const char *path, uint32_t *V, uint32_t *E, uint32_t *offsets, uint32_t *nbrs,
+                                   uint32_t *labels) {
+    gpe::HostGraph g;
+    int rc = gpe::load_graph_file(path, g, g_host_err);
+    if (rc) return rc;
+    if (V) *V = (uint32_t)g.labels.size();
+    if (E) *E = (uint32_t)(g.nbrs.size() / 2);
+    if (offsets) std::copy(g.offsets.begin(), g.offsets.end(), offsets);
+    if (nbrs) std::copy(g.nbrs.begin(), g.nbrs.end(), nbrs);
+    if (labels) std::copy(g.labels.begin(), g.labels.end(), labels);
+    return GPE_OK;
+}
+
+extern "C" int gpe_host_gen_vde(uint32_t V, const uint32_t *offsets, const uint32_t *nbrs, const uint32_t *labels,
+                                uint32_t e, double *x, double *vde) {
+    if (!offsets || !labels || !x || !vde || e == 0) return GPE_ERR_INVALID;
+    gpe::gen_vde(V, offsets, nbrs, labels, e, x, vde);
+    return GPE_OK;
+}
+
+extern "C" int gpe_host_query_plan(uint32_t nq, const uint32_t *q_offsets, const uint32_t *q_nbrs,
+                                   const uint32_t *q_labels, uint32_t L, uint32_t e, uint32_t cap, uint32_t *vids,
+                                   uint32_t *labels, uint32_t *degs, double *pde, uint32_t *n) {
+    if (nq > GPE_MAX_QUERY_VERTICES || L < 2 || L > GPE_MAX_QUERY_VERTICES || e == 0) return GPE_ERR_INVALID;
+    gpe::QueryPlan plan;
+    gpe::query_plan(nq, q_offsets, q_nbrs, q_labels, L, e, plan);
+    uint32_t m = std::min(plan.n, cap);
+    if (vids) std::copy(plan.vids.begin(), plan.vids.begin() + (size_t)m * L, vids);
+    if (labels) std::copy(plan.labels.begin(), plan.labels.begin() + (size_t)m * L, labels);
+    if (degs) std::copy(plan.degs.begin(), plan.degs.begin() + (size_t)m * L, degs);
+    if (pde) std::copy(plan.pde.begin(), plan.pde.begin() + (size_t)m * L * e, pde);
+    if (n) *n = plan.n;
+    return GPE_OK;
+}

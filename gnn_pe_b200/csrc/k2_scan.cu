@@ -1,0 +1,352 @@
+// k2_scan.cu -- the dominance scan (hot path 1).
+//
+// Replaces Partition::query (custom.h:366-489): the best-first R*-tree traversal becomes a streaming
+// compare of query-path blocks against tiles of the structure-of-arrays path table.
+//   * the per-row test is the reference's leaf compare, custom.h:407-435, in FP64:
+//       accept iff for every position k: q.label[k] == p.label[k] and q.degree[k] <= p.degree[k]
+//              and for every dimension d: not (q.pde[d] > p.pde[d] and |q.pde[d] - p.pde[d]| > 1e-6)
+//     (q > p  =>  |q-p| = q-p, so the second line is  not (q.pde[d] - p.pde[d] > 1e-6));
+//   * internal-node routing (custom.h:439-484) becomes k2_select: a (block, tile) pair is dropped when the
+//     tile's label range, max degrees or max-corner rule out every plan path of the block.  Pruning never
+//     changes the result, only the number of tiles read;
+//   * candidates[q.vids[k]].insert(p.vids[k]) (custom.h:429-432) becomes a test-and-set in a per-
+//     (query vertex) bitmap over data vertices.
+//
+// HBM-bound: 72 B/row at l=2,e=2.  Each CTA is a TMA pipeline: one producer lane issues
+// cp.async.bulk copies of (tile, query-path block) into a kStages-deep shared-memory ring guarded by
+// mbarriers; 256 consumer threads compare one row each.  No tensor cores: nothing here is a contraction.
+#include "gpe_internal.h"
+
+namespace gpe {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// ---- mbarrier / bulk-copy PTX -------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ u64 make_evict_first_policy() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, u32 bytes, u64 *bar, u64 policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_nohint(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+template <int L, int E>
+struct ScanGeom {
+    static constexpr int D = L * E;
+    static constexpr int kTileBytes = kTileRows * (8 * L + 8 * D);
+    static constexpr int kRecBytes = (int)sizeof(QBlockRec<L, E>);
+    static constexpr int kStageBytes = ((kTileBytes + kRecBytes + 127) / 128) * 128;
+    static constexpr int kNumStages = (kStages * kStageBytes <= 200 * 1024) ? kStages
+                                       : ((200 * 1024) / kStageBytes >= 2 ? (200 * 1024) / kStageBytes : 2);
+    static constexpr int kSmemBytes = kNumStages * kStageBytes + 1024;  // ring + barriers/meta + alignment slack
+};
+
+// ---- tile selection -------------------------------------------------------------------------------------
+template <int L, int E>
+__global__ void __launch_bounds__(256) k2_select_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks,
+                                                        const u32 *__restrict__ qb_t0,
+                                                        const u64 *__restrict__ qb_prefix, u32 n_qblocks, u64 n_items,
+                                                        bool prune, u64 *__restrict__ worklist, u64 *counters) {
+    constexpr int D = L * E;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 base = (u64)blockIdx.x * blockDim.x; base < n_items; base += stride) {
+        u64 idx = base + threadIdx.x;
+        bool pass = false;
+        u32 tile = 0, b = 0;
+        if (idx < n_items) {
+            u32 lo = 0, hi = n_qblocks;  // last b with qb_prefix[b] <= idx
+            while (hi - lo > 1) {
+                u32 mid = (lo + hi) >> 1;
+                if (qb_prefix[mid] <= idx) lo = mid; else hi = mid;
+            }
+            b = lo;
+            tile = qb_t0[b] + (u32)(idx - qb_prefix[b]);
+            if (!prune) {
+                pass = true;
+            } else {
+                const QBlockRec<L, E> &rec = qblocks[b];
+                for (u32 j = 0; j < rec.n && !pass; j++) {
+                    bool ok = true;
+#pragma unroll
+                    for (int k = 0; k < L; k++) {
+                        u32 ql = rec.labels[j][k];
+                        ok = ok && ql >= t.lab_min[k * t.n_tiles + tile] && ql <= t.lab_max[k * t.n_tiles + tile] &&
+                             rec.degs[j][k] <= t.deg_max[k * t.n_tiles + tile];
+                    }
+                    if (ok) {
+#pragma unroll
+                        for (int d = 0; d < D; d++)
+                            ok = ok && !(rec.pde[j][d] - t.pde_max[d * t.n_tiles + tile] > kEps);
+                    }
+                    pass = ok;
+                }
+            }
+        }
+        unsigned m = __ballot_sync(kFull, pass);
+        if (m) {
+            u64 wbase = 0;
+            int leader = __ffs(m) - 1;
+            if ((int)(threadIdx.x & 31) == leader)
+                wbase = atomicAdd((unsigned long long *)&counters[0], (unsigned long long)__popc(m));
+            wbase = __shfl_sync(kFull, wbase, leader);
+            if (pass) worklist[wbase + __popc(m & lanemask_lt())] = ((u64)b << 32) | tile;
+        }
+    }
+}
+
+// ---- the scan ----------------------------------------------------------------------------------------------
+template <int L, int E>
+__global__ void __launch_bounds__(kTileRows + 32, 1)
+k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u64 *__restrict__ worklist,
+               const u64 *__restrict__ counters, u32 *__restrict__ bitmap, u64 words_per_slot,
+               u64 *__restrict__ survivors) {
+    using G = ScanGeom<L, E>;
+    constexpr int D = G::D;
+    constexpr int NS = G::kNumStages;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    unsigned char *ring = smem;
+    u64 *full_bar = reinterpret_cast<u64 *>(smem + NS * G::kStageBytes);
+    u64 *empty_bar = full_bar + NS;
+    u64 *meta = empty_bar + NS;  // work item of every stage
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kConsumerWarps = kTileRows / 32;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const u64 n_items = counters[0];
+    const u64 first = blockIdx.x;
+    const u64 n_my = first < n_items ? (n_items - first + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == kConsumerWarps) {
+        // ---------------- producer warp: lane 0 issues the copies, the warp prefetches work items ---------
+        const u64 policy = make_evict_first_policy();
+        int stage = 0;
+        u32 phase = 0;
+        for (u64 k0 = 0; k0 < n_my; k0 += 32) {
+            u64 mine = (k0 + lane < n_my) ? worklist[first + (k0 + lane) * gridDim.x] : 0;
+            int cnt = (int)min((u64)32, n_my - k0);
+            for (int i = 0; i < cnt; i++) {
+                u64 item = __shfl_sync(kFull, mine, i);
+                if (lane == 0) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    u32 tile = (u32)item, b = (u32)(item >> 32);
+                    unsigned char *dst = ring + stage * G::kStageBytes;
+                    meta[stage] = item;
+                    mbar_arrive_expect_tx(&full_bar[stage], G::kTileBytes + G::kRecBytes);
+                    bulk_load(dst, t.tiles + (u64)tile * G::kTileBytes, G::kTileBytes, &full_bar[stage], policy);
+                    bulk_load_nohint(dst + G::kTileBytes, &qblocks[b], G::kRecBytes, &full_bar[stage]);
+                }
+                if (++stage == NS) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ---------------- consumers: one row per thread ---------------------------------------------------
+        const u32 r = threadIdx.x;
+        int stage = 0;
+        u32 phase = 0;
+        for (u64 k = 0; k < n_my; k++) {
+            mbar_wait(&full_bar[stage], phase);
+            const unsigned char *buf = ring + stage * G::kStageBytes;
+            const u64 item = meta[stage];
+            const u32 tile = (u32)item;
+            const u32 *s_lab = reinterpret_cast<const u32 *>(buf);
+            const u32 *s_deg = reinterpret_cast<const u32 *>(buf + 4 * L * kTileRows);
+            const double *s_pde = reinterpret_cast<const double *>(buf + 8 * L * kTileRows);
+            const QBlockRec<L, E> *rec = reinterpret_cast<const QBlockRec<L, E> *>(buf + G::kTileBytes);
+            const bool valid = (u64)tile * kTileRows + r < t.n_rows;
+
+            u32 lab[L], dg[L];
+#pragma unroll
+            for (int kk = 0; kk < L; kk++) {
+                lab[kk] = s_lab[kk * kTileRows + r];
+                dg[kk] = s_deg[kk * kTileRows + r];
+            }
+            const u32 nq = rec->n;
+            for (u32 j = 0; j < nq; j++) {
+                bool ok = valid;
+#pragma unroll
+                for (int kk = 0; kk < L; kk++) ok = ok && (rec->labels[j][kk] == lab[kk]) && (rec->degs[j][kk] <= dg[kk]);
+                if (ok) {
+#pragma unroll
+                    for (int d = 0; d < D; d++) ok = ok && !(rec->pde[j][d] - s_pde[d * kTileRows + r] > kEps);
+                }
+                unsigned m = __ballot_sync(kFull, ok);
+                if (m) {
+                    if (lane == 0) atomicAdd((unsigned long long *)&survivors[rec->qpath[j]], (unsigned long long)__popc(m));
+                    if (ok) {
+#pragma unroll
+                        for (int kk = 0; kk < L; kk++) {
+                            u32 v = t.vids[((u64)tile * L + kk) * kTileRows + r];
+                            u32 *word = bitmap + (u64)rec->slot[j][kk] * words_per_slot + (v >> 5);
+                            u32 bit = 1u << (v & 31);
+                            if (!(*word & bit)) atomicOr(word, bit);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+    }
+}
+
+template <int L, int E>
+cudaError_t launch_select(const TableView &t, const void *qblocks, const u32 *qb_t0, const u64 *qb_prefix,
+                          u32 n_qblocks, u64 n_items, bool prune, u64 *worklist, u64 *counters, cudaStream_t s) {
+    if (n_items == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)std::min<u64>((n_items + 255) / 256, 148 * 16);
+    k2_select_kernel<L, E><<<blocks, 256, 0, s>>>(t, reinterpret_cast<const QBlockRec<L, E> *>(qblocks), qb_t0,
+                                                  qb_prefix, n_qblocks, n_items, prune, worklist, counters);
+    return cudaGetLastError();
+}
+
+template <int L, int E>
+cudaError_t launch_scan(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters,
+                        u32 *bitmap, u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s) {
+    using G = ScanGeom<L, E>;
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(k2_scan_kernel<L, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             G::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k2_scan_kernel<L, E>, kTileRows + 32, G::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = n < 1 ? 1 : n;
+    }
+    unsigned blocks = (unsigned)(sm_count * ctas_per_sm);
+    k2_scan_kernel<L, E><<<blocks, kTileRows + 32, G::kSmemBytes, s>>>(
+        t, reinterpret_cast<const QBlockRec<L, E> *>(qblocks), worklist, counters, bitmap, words_per_slot, survivors);
+    return cudaGetLastError();
+}
+
+template <int L, int E>
+void pack_rec(void *dst, u32 n, u32 first_qpath, const u32 *qpath_ids, const u32 *labels, const u32 *degs,
+              const u32 *slots, const double *pde) {
+    QBlockRec<L, E> rec;
+    memset(&rec, 0, sizeof rec);
+    rec.n = n;
+    rec.first_qpath = first_qpath;
+    for (u32 j = 0; j < n; j++) {
+        for (int k = 0; k < L; k++) {
+            rec.labels[j][k] = labels[j * L + k];
+            rec.degs[j][k] = degs[j * L + k];
+            rec.slot[j][k] = slots[j * L + k];
+        }
+        rec.qpath[j] = qpath_ids[j];
+        for (int d = 0; d < L * E; d++) rec.pde[j][d] = pde[(size_t)j * L * E + d];
+    }
+    memcpy(dst, &rec, sizeof rec);
+}
+
+}  // namespace
+
+#define GPE_DISPATCH_LE(L_, E_, CALL)                                    \
+    do {                                                                 \
+        if ((L_) == 3 && (E_) == 1) { CALL(3, 1); }                      \
+        else if ((L_) == 3 && (E_) == 2) { CALL(3, 2); }                 \
+        else if ((L_) == 3 && (E_) == 3) { CALL(3, 3); }                 \
+        else if ((L_) == 3 && (E_) == 4) { CALL(3, 4); }                 \
+        else if ((L_) == 3 && (E_) == 8) { CALL(3, 8); }                 \
+        else if ((L_) == 4 && (E_) == 1) { CALL(4, 1); }                 \
+        else if ((L_) == 4 && (E_) == 2) { CALL(4, 2); }                 \
+        else if ((L_) == 4 && (E_) == 3) { CALL(4, 3); }                 \
+        else if ((L_) == 4 && (E_) == 4) { CALL(4, 4); }                 \
+        else if ((L_) == 4 && (E_) == 8) { CALL(4, 8); }                 \
+    } while (0)
+
+bool k2_supported(u32 L, u32 E) {
+    return (L == 3 || L == 4) && (E == 1 || E == 2 || E == 3 || E == 4 || E == 8);
+}
+
+size_t qblock_rec_bytes(u32 L, u32 E) {
+    size_t r = 0;
+#define CALL(l, e) r = sizeof(QBlockRec<l, e>)
+    GPE_DISPATCH_LE(L, E, CALL);
+#undef CALL
+    return r;
+}
+
+void qblock_pack(u32 L, u32 E, void *dst, u32 n, u32 first_qpath, const u32 *qpath_ids, const u32 *labels,
+                 const u32 *degs, const u32 *slots, const double *pde) {
+#define CALL(l, e) pack_rec<l, e>(dst, n, first_qpath, qpath_ids, labels, degs, slots, pde)
+    GPE_DISPATCH_LE(L, E, CALL);
+#undef CALL
+}
+
+cudaError_t k2_select(const TableView &t, const void *qblocks, const u32 *qb_t0, const u64 *qb_prefix, u32 n_qblocks,
+                      u64 n_items, bool prune, u64 *worklist, u64 *counters, cudaStream_t s) {
+    cudaError_t e = cudaErrorInvalidValue;
+#define CALL(l, e_) e = launch_select<l, e_>(t, qblocks, qb_t0, qb_prefix, n_qblocks, n_items, prune, worklist, counters, s)
+    GPE_DISPATCH_LE(t.L, t.E, CALL);
+#undef CALL
+    return e;
+}
+
+cudaError_t k2_scan(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters, u32 *bitmap,
+                    u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s) {
+    cudaError_t e = cudaErrorInvalidValue;
+#define CALL(l, e_) e = launch_scan<l, e_>(t, qblocks, worklist, counters, bitmap, words_per_slot, survivors, sm_count, s)
+    GPE_DISPATCH_LE(t.L, t.E, CALL);
+#undef CALL
+    return e;
+}
+
+}  // namespace gpe

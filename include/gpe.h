@@ -1,0 +1,175 @@
+/* gpe.h -- C ABI of libgpe.so, the B200-native replacement for GNN-PE's three hot paths.
+ *
+ * The reference (JamesWhiteSnow/GNN-PE) has no plugin or FFI interface: include/custom.h is
+ * compiled into src/main.cpp's single translation unit.  The seams a maintainer would cut are
+ * three call sites in src/main.cpp; each group of entry points below names the one it replaces
+ * (file:line relative to the reference's GNN-PE/ directory).  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; vertex / label ids are uint32_t (reference `ui`,
+ *     include/configuration/types.h:13-17), embeddings are double, row counts are uint64_t
+ *     (the reference's 32-bit `ui path_num`, custom.h:548, overflows at BASELINE.json's sizes);
+ *   - every call returns 0 on success, non-zero on error; gpe_last_error() gives the message;
+ *     the library never calls exit() (the reference's R-tree library does, functions.cpp:24-29);
+ *   - host pointers passed in are caller-owned and not retained after the call returns;
+ *   - a context owns one GPU and one CUDA stream and is not thread-safe: where the reference
+ *     runs one OpenMP thread per partition (main.cpp:160-164) the caller makes ONE call;
+ *   - there is no CPU fallback: without a usable sm_100 device gpe_create() fails.
+ */
+#ifndef GPE_H_
+#define GPE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpe_ctx gpe_ctx;
+
+#define GPE_OK 0
+#define GPE_ERR_INVALID 1     /* bad argument / call order */
+#define GPE_ERR_CUDA 2        /* CUDA runtime error (message has the detail) */
+#define GPE_ERR_UNSUPPORTED 3 /* (L, e) or query size outside the compiled kernels */
+#define GPE_ERR_IO 4
+
+#define GPE_LIMIT_MAX 0xFFFFFFFFull /* `-n MAX` = UINT_MAX, main.cpp:62-65 */
+#define GPE_MAX_QUERY_VERTICES 64   /* MAXIMUM_QUERY_GRAPH_SIZE, include/configuration/config.h:3 */
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+int gpe_create(int device, gpe_ctx **out);
+void gpe_destroy(gpe_ctx *ctx);
+const char *gpe_last_error(const gpe_ctx *ctx); /* ctx may be NULL: error of the last failed gpe_create */
+int gpe_abi_version(void);
+
+/* ---- host-side mirror of the reference's cheap serial steps (pure host code, no GPU) --- */
+
+/* Static_Graph::loadGraphFromFile, libsrc/graph/graph.cpp:163-242.  Two-call pattern: with
+ * offsets == NULL only V, E are returned.  nbrs come back sorted ascending per vertex (:231-233). */
+int gpe_host_load_graph(const char *path, uint32_t *V, uint32_t *E, uint32_t *offsets /*V+1*/,
+                        uint32_t *nbrs /*2E*/, uint32_t *labels /*V*/);
+/* gen_vde_x + gen_vde, custom.h:492-544.  x, vde: V x e, row-major. */
+int gpe_host_gen_vde(uint32_t V, const uint32_t *offsets, const uint32_t *nbrs, const uint32_t *labels,
+                     uint32_t e, double *x, double *vde);
+/* dfs_query (custom.h:94-119, main.cpp:142-146) + gen_vde(query) + gen_query_pde (custom.h:574-633).
+ * Writes at most cap plan paths (vids/labels/degs: n x L, pde: n x L*e) and returns the plan size in *n. */
+int gpe_host_query_plan(uint32_t nq, const uint32_t *q_offsets, const uint32_t *q_nbrs, const uint32_t *q_labels,
+                        uint32_t L, uint32_t e, uint32_t cap, uint32_t *vids, uint32_t *labels, uint32_t *degs,
+                        double *pde, uint32_t *n);
+
+/* ---- data graph + embeddings ------------------------------------------------------------ */
+
+/* The CSR Static_Graph holds (graph.h:61-63).  Simple graph required (no loops, no duplicate
+ * edges): the reference's hash-set dedup (custom.h:68-79) is what a duplicate edge would need. */
+int gpe_set_graph(gpe_ctx *ctx, uint32_t V, const uint32_t *offsets, const uint32_t *nbrs, const uint32_t *labels);
+/* Per-vertex dominance embeddings, V x e row-major: the `vde` gen_vde returns (custom.h:536-540).
+ * Host-computed so the FP64 compares see the reference's exact values. */
+int gpe_set_embeddings(gpe_ctx *ctx, uint32_t e, const double *vde);
+
+/* ---- seam S1: offline path enumeration (main.cpp:92-96 `dfs` loop, custom.h:66-92) ------ */
+
+/* L = l + 1 vertices per path.  sorted_nodes = line order of membership.txt (main.cpp:80-85);
+ * membership[v] in [0, p).  Counts only; returns the row count of every partition (a path belongs to
+ * the partition of its FIRST vertex, custom.h:74) and the total.  Path ids are the reference's. */
+int gpe_enumerate(gpe_ctx *ctx, uint32_t L, const uint32_t *sorted_nodes, const uint32_t *membership, uint32_t p,
+                  uint64_t *rows_per_partition /*p*/, uint64_t *n_rows);
+/* Rows [first, first+n) of all_paths.txt in the reference's order (main.cpp:110-119), n x L row-major. */
+int gpe_dump_paths(gpe_ctx *ctx, uint64_t first, uint64_t n, uint32_t *vids);
+/* First path id of every start vertex, in membership.txt order (V+1 entries); partition_paths.txt
+ * (main.cpp:98-108) is the concatenation of [start_row[i], start_row[i+1]) over a partition's vertices. */
+int gpe_start_rows(gpe_ctx *ctx, uint64_t *start_row /*V+1*/);
+
+/* ---- seam S2: the dominance filter (gen_pde custom.h:546-572 + Partition ctor :205-266 +
+ *      Partition::query :366-489 + the merge main.cpp:166-172) ------------------------------ */
+
+/* Materialise the structure-of-arrays path table (labels, degrees, path embeddings; vertex ids beside
+ * it) for the partitions with part_select[i] != 0 (NULL = all).  Needs gpe_enumerate + gpe_set_embeddings. */
+int gpe_build_table(gpe_ctx *ctx, const uint8_t *part_select /*p or NULL*/, uint64_t *n_table_rows);
+/* Copy the table back in its physical (label-bucketed) row order, for parity checks: any may be NULL. */
+int gpe_dump_table(gpe_ctx *ctx, uint64_t first, uint64_t n, uint32_t *vids /*n x L*/, uint32_t *labels /*n x L*/,
+                   uint32_t *degs /*n x L*/, double *pde /*n x L*e*/);
+
+#define GPE_FILTER_NO_PRUNE 1u /* streaming mode: every plan path is compared with every table row */
+
+/* One query: the plan paths (Query_Plan Q of Partition::query) against the whole table.  The candidate
+ * sets stay on the device; cand_offsets (nq+1) gives their sizes, survivors (n_qpaths, may be NULL) the
+ * number of (plan path, data path) pairs that passed the leaf compare (custom.h:407-435). */
+int gpe_filter(gpe_ctx *ctx, uint32_t n_qpaths, const uint32_t *q_vids, const uint32_t *q_labels,
+               const uint32_t *q_degs, const double *q_pde, uint32_t nq, uint32_t flags,
+               uint64_t *cand_offsets /*nq+1*/, uint64_t *survivors);
+/* Sorted, duplicate-free candidate lists of the last gpe_filter, concatenated (std::set order). */
+int gpe_get_candidates(gpe_ctx *ctx, uint32_t *cand);
+
+/* ---- seam S3: refinement (custom.h:890-932, called at main.cpp:177) ---------------------- */
+
+/* Matching order (generateGQLQueryPlan :670-722), backward neighbours (:724-755) and the enumeration
+ * (:757-888) from caller-supplied candidate sets.  limit = MAX_LIMIT (main.cpp:62-69).  n_matches is
+ * min(total, max(limit,1)) like the reference's early exit (:851-854).  order_out / pivot_out (nq, may
+ * be NULL) return the plan.  matches (may be NULL) receives up to matches_cap embeddings, nq ids each,
+ * indexed by query vertex, in no particular order. */
+int gpe_refine(gpe_ctx *ctx, uint32_t nq, const uint32_t *q_offsets, const uint32_t *q_nbrs, const uint32_t *q_labels,
+               const uint64_t *cand_offsets, const uint32_t *cand, uint64_t limit, uint64_t *n_matches,
+               uint32_t *order_out, uint32_t *pivot_out, uint32_t *matches, uint64_t matches_cap);
+
+/* ---- the whole online stage for a batch of queries (main.cpp:136-179 per query) ---------- */
+
+/* Queries are concatenated: query i has vertices [q_vbase[i], q_vbase[i+1]) of q_labels, local CSR
+ * offsets q_offsets[q_vbase[i] + i .. ] (nq_i + 1 entries, starting at 0) and adjacency
+ * q_nbrs[q_ebase[i] ..] (local vertex ids).  answers[i] as gpe_refine's n_matches. */
+typedef struct gpe_batch {
+    uint32_t n_queries;
+    const uint32_t *q_vbase;   /* n_queries + 1 */
+    const uint32_t *q_ebase;   /* n_queries + 1 */
+    const uint32_t *q_offsets; /* sum(nq_i + 1) */
+    const uint32_t *q_nbrs;
+    const uint32_t *q_labels;
+    const uint64_t *limits;    /* n_queries, or NULL for GPE_LIMIT_MAX everywhere */
+} gpe_batch;
+
+/* Stage 1 (host): plan every query (gpe_host_query_plan) and copy the batch to the device. */
+int gpe_batch_upload(gpe_ctx *ctx, const gpe_batch *batch, uint32_t flags);
+/* Stage 2 (device only, asynchronous on the context's stream): tile selection, dominance scan,
+ * candidate compaction.  With world > 1 this is the local shard's contribution. */
+int gpe_batch_filter(gpe_ctx *ctx);
+/* Stage 3 (device only): matching orders + join over the start candidates idx % world == rank. */
+int gpe_batch_join(gpe_ctx *ctx, uint32_t rank, uint32_t world);
+/* Stage 4: wait, copy the per-query counts back.  Raw totals (not yet clamped by the limit) so that
+ * shards can be summed; gpe_clamp_answer applies the reference's limit rule. */
+int gpe_batch_download(gpe_ctx *ctx, uint64_t *raw_counts /*n_queries*/);
+uint64_t gpe_clamp_answer(uint64_t raw_total, uint64_t limit);
+/* All four stages for one GPU, host buffers in, answers out: the end-to-end call. */
+int gpe_query_batch(gpe_ctx *ctx, const gpe_batch *batch, uint32_t flags, uint64_t *answers);
+
+/* Candidate exchange between shards (replaces the serial merge main.cpp:166-172 when the table is
+ * sharded over GPUs).  Device pointers: the caller moves them with NCCL. */
+int gpe_batch_cand_info(gpe_ctx *ctx, uint64_t *n_slots, uint64_t *n_cand_total);
+int gpe_batch_cand_export(gpe_ctx *ctx, void *d_counts_u32 /*n_slots*/, void *d_cand_u32 /*n_cand_total*/);
+/* Replace the batch's candidate sets by the union of `world` shards' lists.  d_counts: world x n_slots
+ * (u32), d_cand: world x stride (u32), shard r's lists concatenated at d_cand + r*stride. */
+int gpe_batch_cand_merge(gpe_ctx *ctx, uint32_t world, const void *d_counts, const void *d_cand, uint64_t stride);
+/* Per-query-vertex candidate counts / lists of the current batch (after filter or merge), host side. */
+int gpe_batch_get_candidates(gpe_ctx *ctx, uint64_t *cand_offsets /*n_slots+1*/, uint32_t *cand /*or NULL*/);
+int gpe_batch_get_plan(gpe_ctx *ctx, uint32_t *order /*n_slots*/, uint32_t *pivot /*n_slots*/);
+
+/* ---- measurement hooks ------------------------------------------------------------------- */
+typedef struct gpe_stats {
+    uint64_t table_rows, table_tiles, tile_rows, row_bytes;  /* row_bytes = L*4 + L*4 + L*e*8 */
+    uint64_t scan_items;        /* (query-path block, tile) pairs the last scan examined */
+    uint64_t scan_items_unpruned;
+    uint64_t scan_rows;         /* rows examined = scan_items * tile_rows (tail tile included) */
+    uint64_t scan_launches, select_launches, compact_launches, join_launches, build_launches;
+    float last_scan_ms, last_select_ms, last_compact_ms, last_join_ms, last_build_ms, last_enumerate_ms;
+    uint64_t n_qpaths, n_qblocks, n_slots, n_candidates, join_items;
+} gpe_stats;
+int gpe_get_stats(gpe_ctx *ctx, gpe_stats *out);
+/* The context's CUDA stream (cudaStream_t) so callers can bracket calls with their own events. */
+void *gpe_stream(gpe_ctx *ctx);
+int gpe_sync(gpe_ctx *ctx);
+/* Record per-kernel CUDA-event timings (costs a stream sync per stage); off by default. */
+int gpe_set_timing(gpe_ctx *ctx, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPE_H_ */

@@ -1,0 +1,86 @@
+"""CPU-side checks of the product library: it loads, exports every symbol include/gpe.h declares, fails
+loudly without a GPU, and its host mirror (loader, embeddings, query plan) agrees with the golden vectors
+of the unmodified reference.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gnn_pe_b200 import gpe, graph_io
+from tests.golden_util import CASES, ROOT, hex_to_f64, load_case
+
+
+@pytest.fixture(scope="module")
+def lib():
+    gpe.build()
+    return gpe.lib()
+
+
+def test_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "gpe.h")).read()
+    declared = set(re.findall(r"\b(gpe_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(gpe.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.gpe_abi_version() == 1
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = ctypes.c_void_p()
+    rc = lib.gpe_create(0, ctypes.byref(h))
+    assert rc != 0 and not h.value
+    assert b"no CUDA device" in lib.gpe_last_error(None)
+    with pytest.raises(gpe.GpeError):
+        gpe.GpeContext(0)
+
+
+def test_product_never_imports_oracle():
+    for d, _, files in os.walk(os.path.join(ROOT, "gnn_pe_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                src = open(os.path.join(d, f)).read()
+                for line in src.splitlines():
+                    s = line.strip()
+                    if s.startswith(("import ", "from ", "#include")):
+                        assert "oracle" not in s, (f, line)
+
+
+def test_clamp_answer(lib):
+    assert lib.gpe_clamp_answer(45426, gpe.LIMIT_MAX) == 45426
+    assert lib.gpe_clamp_answer(45426, 100) == 100
+    assert lib.gpe_clamp_answer(5, 100) == 5
+    assert lib.gpe_clamp_answer(5, 0) == 1   # custom.h:851: the limit is tested after counting a match
+    assert lib.gpe_clamp_answer(0, 0) == 0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_mirror_against_golden(lib, name):
+    gold = load_case(name)
+    off, nbr, lab = gpe.host_load_graph(gold["data_path"])
+    g = graph_io.read_graph(gold["data_path"])
+    assert np.array_equal(off, g.offsets) and np.array_equal(nbr, g.nbrs) and np.array_equal(lab, g.labels)
+    e, L = gold["e"], gold["l"] + 1
+    x, vde = gpe.host_gen_vde(off, nbr, lab, e)
+    q0 = gold["queries"][0]
+    for v, hexes in q0["data_vde_sample"].items():
+        assert vde[int(v)].tobytes() == hex_to_f64(hexes).tobytes()
+    for qf, rec in zip(gold["query_paths_files"], gold["queries"]):
+        qo, qn, ql = gpe.host_load_graph(qf)
+        plan = gpe.host_query_plan(qo, qn, ql, L, e)
+        assert plan["vids"].tolist() == [p["vids"] for p in rec["plan"]]
+        for j, p in enumerate(rec["plan"]):
+            assert plan["pde"][j].tobytes() == hex_to_f64(p["pde"]).tobytes()
+        qx, _ = gpe.host_gen_vde(qo, qn, ql, e)
+        for labn, hexes in rec["label_x"].items():
+            for u in np.nonzero(ql == int(labn))[0]:
+                assert qx[u].tobytes() == hex_to_f64(hexes).tobytes()
+
+
+def test_host_loader_errors(lib, tmp_path):
+    with pytest.raises(gpe.GpeError):
+        gpe.host_load_graph(str(tmp_path / "missing.graph"))

@@ -1,0 +1,222 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the golden vectors of the unmodified
+reference and against the oracle on seeded inputs.  Bit-exact everywhere: integer ids, candidate sets and
+counts; the FP64 compares consume identical values so no tolerance is involved."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from gnn_pe_b200 import gpe, graph_io, synth
+from tests.golden_util import CASES, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx_for(gold):
+    g = graph_io.read_graph(gold["data_path"])
+    sorted_nodes, membership = graph_io.read_membership(gold["membership_path"], g.V)
+    ctx = gpe.GpeContext(0)
+    ctx.set_graph(g.offsets, g.nbrs, g.labels)
+    _, vde = gpe.host_gen_vde(g.offsets, g.nbrs, g.labels, gold["e"])
+    ctx.set_embeddings(vde)
+    n_rows, rows_pp = ctx.enumerate(gold["l"] + 1, sorted_nodes, membership, gold["p"])
+    return ctx, g, vde, sorted_nodes, membership, n_rows, rows_pp
+
+
+@pytest.fixture(scope="module", params=CASES)
+def case(request):
+    gold = load_case(request.param)
+    ctx, g, vde, sorted_nodes, membership, n_rows, rows_pp = _ctx_for(gold)
+    ctx.build_table()
+    yield gold, ctx, g, vde, sorted_nodes, membership, n_rows, rows_pp
+    ctx.close()
+
+
+def _text(rows):
+    return f"{len(rows)}\n" + "".join(" ".join(map(str, r)) + " \n" for r in rows.tolist())
+
+
+def test_enumerate_matches_reference_all_paths(case):
+    gold, ctx, g, vde, sorted_nodes, membership, n_rows, rows_pp = case
+    assert n_rows == gold["n_rows"]
+    assert rows_pp.tolist() == gold["rows_per_partition"]
+    rows = ctx.dump_paths()
+    assert rows[: len(gold["first_rows"])].tolist() == gold["first_rows"]
+    assert hashlib.md5(_text(rows).encode()).hexdigest() == gold["all_paths_md5"]
+    # windows that start and end inside a start vertex's block
+    for first, n in [(1, 1), (n_rows // 3, 1000), (n_rows - 7, 7)]:
+        assert np.array_equal(ctx.dump_paths(first, n), rows[first:first + n])
+    # partition_paths.txt content (T6): ids of the paths whose first vertex is in the partition
+    start = ctx.start_rows()
+    assert start[-1] == n_rows
+    firsts_member = membership[rows[:, 0]]
+    for i in range(gold["p"]):
+        assert int((firsts_member == i).sum()) == gold["rows_per_partition"][i]
+
+
+def test_table_is_the_same_multiset_with_right_columns(case):
+    gold, ctx, g, vde, *_ = case
+    rows = ctx.dump_paths()
+    vids, labels, degs, pde = ctx.dump_table()
+    assert len(vids) == gold["n_rows"]
+    key = lambda a: a[np.lexsort(a.T[::-1])]
+    assert np.array_equal(key(vids), key(rows))
+    deg = g.degrees
+    assert np.array_equal(labels, g.labels[vids])
+    assert np.array_equal(degs, deg[vids])
+    assert pde.tobytes() == vde[vids].reshape(len(vids), -1).tobytes()
+
+
+@pytest.mark.parametrize("flags", [0, gpe.FILTER_NO_PRUNE])
+def test_filter_candidates_and_survivors(case, flags):
+    gold, ctx, *_ = case
+    L, e = gold["l"] + 1, gold["e"]
+    for qf, rec in zip(gold["query_paths_files"], gold["queries"]):
+        qo, qn, ql = gpe.host_load_graph(qf)
+        plan = gpe.host_query_plan(qo, qn, ql, L, e)
+        sets, surv = ctx.filter(plan, len(ql), flags)
+        assert [s.tolist() for s in sets] == rec["candidates"]
+        assert surv.tolist() == [p["survivors"] for p in rec["plan"]]
+    st = ctx.stats()
+    if flags:
+        assert st["scan_items"] == st["scan_items_unpruned"]
+
+
+def test_refine_order_and_answer(case):
+    gold, ctx, *_ = case
+    for qf, rec in zip(gold["query_paths_files"], gold["queries"]):
+        qo, qn, ql = gpe.host_load_graph(qf)
+        cands = [np.array(c, dtype=np.uint32) for c in rec["candidates"]]
+        limit = rec["limit"] if rec["limit"] is not None else gpe.LIMIT_MAX
+        res = ctx.refine(qo, qn, ql, cands, limit)
+        assert res["order"].tolist() == rec["order"]
+        assert res["pivot"].tolist()[1:] == rec["pivot"][1:]
+        assert res["n_matches"] == rec["answer"]
+
+
+def test_query_batch_end_to_end(case):
+    gold, ctx, *_ = case
+    queries = [graph_io.read_graph(qf) for qf in gold["query_paths_files"]]
+    limits = [r["limit"] if r["limit"] is not None else gpe.LIMIT_MAX for r in gold["queries"]]
+    ans = ctx.query_batch(queries, limits)
+    assert ans.tolist() == [r["answer"] for r in gold["queries"]]
+    # same batch, streaming (unpruned) scan
+    ans2 = ctx.query_batch(queries, limits, flags=gpe.FILTER_NO_PRUNE)
+    assert ans2.tolist() == ans.tolist()
+    # candidate sets of the batch equal the per-query golden sets
+    off, cand = ctx.batch_get_candidates()
+    slot = 0
+    for r in gold["queries"]:
+        for c in r["candidates"]:
+            assert cand[int(off[slot]):int(off[slot + 1])].tolist() == c
+            slot += 1
+
+
+def test_match_set_equals_oracle():
+    from oracle import oracle
+    gold = load_case("uniform300")
+    ctx, g, *_ = _ctx_for(gold)
+    og = oracle.OracleGraph.load(gold["data_path"])
+    for qi in (0, 1, 3, 6, 7):
+        rec = gold["queries"][qi]
+        if rec["limit"] is not None:
+            continue
+        qf = gold["query_paths_files"][qi]
+        qo, qn, ql = gpe.host_load_graph(qf)
+        cands = [np.array(c, dtype=np.uint32) for c in rec["candidates"]]
+        res = ctx.refine(qo, qn, ql, cands, want_matches=rec["answer"] + 16)
+        n, om = oracle.refine(og, oracle.OracleGraph.load(qf), cands, want_matches=rec["answer"] + 16)
+        assert res["n_matches"] == n == rec["answer"]
+        assert sorted(map(tuple, res["matches"].tolist())) == sorted(map(tuple, om.tolist()))
+    ctx.close()
+
+
+def test_sharded_tables_union_to_the_full_result():
+    """Path table sharded by partition (what each GPU of a multi-GPU run holds): the union of the shards'
+    candidate sets equals the unsharded result, and shard row counts are the reference's per-partition counts."""
+    gold = load_case("quickstart")
+    ctx, g, vde, sorted_nodes, membership, n_rows, rows_pp = _ctx_for(gold)
+    L, e, p = gold["l"] + 1, gold["e"], gold["p"]
+    rec = gold["queries"][0]
+    qo, qn, ql = gpe.host_load_graph(gold["query_paths_files"][0])
+    plan = gpe.host_query_plan(qo, qn, ql, L, e)
+    union = [set() for _ in range(len(ql))]
+    total = 0
+    for shard in range(2):
+        sel = np.array([1 if i % 2 == shard else 0 for i in range(p)], dtype=np.uint8)
+        rows = ctx.build_table(sel)
+        assert rows == sum(r for i, r in enumerate(gold["rows_per_partition"]) if i % 2 == shard)
+        total += rows
+        sets, _ = ctx.filter(plan, len(ql))
+        for u, s in enumerate(sets):
+            union[u] |= set(s.tolist())
+    assert total == n_rows
+    assert [sorted(s) for s in union] == rec["candidates"]
+    ctx.close()
+
+
+def test_edge_cases():
+    gold = load_case("uniform300")
+    ctx, g, *_ = _ctx_for(gold)
+    ctx.build_table()
+    # a 2-vertex query has no path of 3 vertices: empty plan, empty candidates, answer 0
+    q2 = graph_io.csr_from_edges(2, np.array([[0, 1]]), np.array([0, 1]))
+    assert ctx.query_batch([q2]).tolist() == [0]
+    # a label that does not occur in the data graph
+    q3 = graph_io.csr_from_edges(3, np.array([[0, 1], [1, 2]]), np.array([0, 99, 1]))
+    assert ctx.query_batch([q3]).tolist() == [0]
+    # disconnected queries are rejected (undefined behaviour in the reference)
+    qd = graph_io.csr_from_edges(4, np.array([[0, 1], [2, 3]]), np.array([0, 1, 2, 3]))
+    with pytest.raises(gpe.GpeError, match="disconnected"):
+        ctx.query_batch([qd])
+    # empty batch
+    assert ctx.query_batch([]).tolist() == []
+    # errors: wrong call order and unsupported shapes
+    c2 = gpe.GpeContext(0)
+    with pytest.raises(gpe.GpeError):
+        c2.build_table()
+    c2.set_graph(g.offsets, g.nbrs, g.labels)
+    with pytest.raises(gpe.GpeError, match="unsupported"):
+        c2.enumerate(6, graph_io.degree_order(g), graph_io.block_membership(g.V, 2), 2)
+    bad = g.nbrs.copy()
+    bad[0], bad[1] = bad[1], bad[0]
+    with pytest.raises(gpe.GpeError, match="ascending"):
+        c2.set_graph(g.offsets, bad, g.labels)
+    c2.close()
+    ctx.close()
+
+
+@pytest.mark.parametrize("seed,V,E,nl,l,e", [(1, 2000, 12000, 5, 2, 2), (2, 1500, 6000, 3, 3, 4), (3, 3000, 30000, 8, 2, 8),
+                                             (4, 5000, 20000, 200, 2, 1)])
+def test_random_graphs_against_oracle(seed, V, E, nl, l, e):
+    from oracle import oracle
+    g = synth.chung_lu_graph(V, E, nl, gamma=2.6, degree_cap=80, seed=seed)
+    sorted_nodes = graph_io.degree_order(g)
+    p = 3
+    membership = graph_io.block_membership(V, p)
+    og = oracle.OracleGraph.from_csr(g.offsets, g.nbrs, g.labels)
+    n = og.enumerate(l + 1, sorted_nodes)
+    ctx = gpe.GpeContext(0)
+    ctx.set_graph(g.offsets, g.nbrs, g.labels)
+    _, vde = gpe.host_gen_vde(g.offsets, g.nbrs, g.labels, e)
+    assert vde.tobytes() == og.embeddings(e)[1].tobytes()
+    ctx.set_embeddings(vde)
+    n_rows, rows_pp = ctx.enumerate(l + 1, sorted_nodes, membership, p)
+    assert n_rows == n
+    assert rows_pp.tolist() == og.rows_per_partition(membership, p).tolist()
+    if n < 3_000_000:
+        assert np.array_equal(ctx.dump_paths(), og.paths())
+    ctx.build_table()
+    queries = synth.query_batch(g, 6, (4, 9), seed=seed + 100, mixed=True)
+    expect = []
+    for q in queries:
+        oq = oracle.OracleGraph.from_csr(q.offsets, q.nbrs, q.labels)
+        sets, surv = oracle.filter_candidates(og, oq, e)
+        plan = gpe.host_query_plan(q.offsets, q.nbrs, q.labels, l + 1, e)
+        gsets, gsurv = ctx.filter(plan, q.V)
+        assert [s.tolist() for s in gsets] == [s.tolist() for s in sets]
+        assert gsurv.tolist() == surv.tolist()
+        expect.append(oracle.refine(og, oq, sets, limit=2_000_000))
+    ans = ctx.query_batch(queries, [2_000_000] * len(queries))
+    assert ans.tolist() == expect
+    ctx.close()
