@@ -12,20 +12,35 @@ static std::string g_create_err;
 
 namespace {
 
+enum Stage { kStageSelect = 0, kStageScan = 1, kStageCompact = 2, kStageJoin = 3, kStageEnumerate = 4, kNumStages_ = 5 };
+
 struct StageTimer {
     gpe_ctx *c;
     float *dst;
-    StageTimer(gpe_ctx *ctx, float *d) : c(ctx), dst(d) {
-        if (c->timing) cudaEventRecord(c->ev0, c->stream);
+    int span = -1;
+    StageTimer(gpe_ctx *ctx, float *d, int stage) : c(ctx), dst(d) {
+        if (c->timing == 1) cudaEventRecord(c->ev0, c->stream);
+        if (c->timing == 2 && c->spans_used < (1u << 16)) {
+            if (c->spans_used == c->spans.size()) {
+                gpe_ctx::Span sp;
+                cudaEventCreate(&sp.a);
+                cudaEventCreate(&sp.b);
+                c->spans.push_back(sp);
+            }
+            span = (int)c->spans_used++;
+            c->spans[span].stage = stage;
+            cudaEventRecord(c->spans[span].a, c->stream);
+        }
     }
     ~StageTimer() {
-        if (c->timing) {
+        if (c->timing == 1) {
             cudaEventRecord(c->ev1, c->stream);
             cudaEventSynchronize(c->ev1);
             float ms = 0;
             cudaEventElapsedTime(&ms, c->ev0, c->ev1);
             *dst = ms;
         }
+        if (span >= 0) cudaEventRecord(c->spans[span].b, c->stream);
     }
 };
 
@@ -141,6 +156,7 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
         GPE_CUDA(c, cudaMemcpyAsync(c->d_qblocks.p, pin + o_rec, recs.size(), cudaMemcpyHostToDevice, c->stream));
     GPE_CUDA(c, cudaMemcpyAsync(c->d_qb_t0.p, pin + o_t0, (nb + 1) * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
     GPE_CUDA(c, cudaMemcpyAsync(c->d_qb_prefix.p, pin + o_pf, (nb + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += recs.size() + (nb + 1) * (sizeof(u32) + sizeof(u64));
     c->b_filtered = false;
     c->b_joined = false;
     c->stats.n_qpaths = n;
@@ -152,7 +168,7 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
 
 // bitmap -> sorted candidate lists (d_cand, d_cand_off); one host sync for the total
 int compact_candidates(gpe_ctx *c) {
-    StageTimer tm(c, &c->stats.last_compact_ms);
+    StageTimer tm(c, &c->stats.last_compact_ms, kStageCompact);
     const u64 n_chunks = c->b_chunks_per_slot * c->b_slots;
     GPE_CUDA(c, c->d_chunk_off.reserve((n_chunks + 1) * sizeof(u64)));
     GPE_CUDA(c, c->d_cand_off.reserve(((u64)c->b_slots + 1) * sizeof(u64)));
@@ -177,6 +193,8 @@ int compact_candidates(gpe_ctx *c) {
                                c->d_chunk_off.as<u64>(), c->d_cand.as<u32>(), c->d_cand_off.as<u64>(), c->stream));
     }
     c->stats.compact_launches += 3;
+    c->stats.kernel_launches += 1 + exclusive_scan_launches(n_chunks + 1) + (n_chunks ? 1 : 0);
+    c->stats.d2h_bytes += 3 * sizeof(u64);
     return GPE_OK;
 }
 
@@ -187,17 +205,19 @@ int run_filter(gpe_ctx *c) {
     GPE_CUDA(c, cudaMemsetAsync(c->d_bitmap.p, 0, std::max<u64>((u64)c->b_slots * c->b_words, 1) * sizeof(u32), c->stream));
     if (n_items > 0 && c->b_qblocks > 0) {
         {
-            StageTimer tm(c, &c->stats.last_select_ms);
+            StageTimer tm(c, &c->stats.last_select_ms, kStageSelect);
             GPE_CUDA(c, k2_select(c->tv, c->d_qblocks.p, c->d_qb_t0.as<u32>(), c->d_qb_prefix.as<u64>(), c->b_qblocks,
                                   n_items, !(c->b_flags & GPE_FILTER_NO_PRUNE), c->d_worklist.as<u64>(),
                                   c->d_counters.as<u64>(), c->stream));
             c->stats.select_launches++;
+            c->stats.kernel_launches++;
         }
         {
-            StageTimer tm(c, &c->stats.last_scan_ms);
+            StageTimer tm(c, &c->stats.last_scan_ms, kStageScan);
             GPE_CUDA(c, k2_scan(c->tv, c->d_qblocks.p, c->d_worklist.as<u64>(), c->d_counters.as<u64>(),
                                 c->d_bitmap.as<u32>(), c->b_words, c->d_survivors.as<u64>(), c->sm_count, c->stream));
             c->stats.scan_launches++;
+            c->stats.kernel_launches++;
         }
     }
     int rc = compact_candidates(c);
@@ -211,6 +231,8 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
                    const u32 *q_nbrs, const u32 *q_labels, const u64 *limits) {
     const u32 n_slots = q_vbase[n_queries], n_adj = q_ebase[n_queries];
     c->b_nq = n_queries;
+    c->stats.h2d_bytes = 0;
+    c->stats.d2h_bytes = 0;
     c->h_q_vbase.assign(q_vbase, q_vbase + n_queries + 1);
     c->h_limits.assign(n_queries, GPE_LIMIT_MAX);
     if (limits) c->h_limits.assign(limits, limits + n_queries);
@@ -235,13 +257,14 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
     GPE_CUDA(c, c->d_item_base.reserve(((size_t)n_queries + 1) * sizeof(u64)));
     GPE_CUDA(c, c->d_answers.reserve(((size_t)n_queries + 2) * sizeof(u64)));
     GPE_CUDA(c, c->d_match_cursor.reserve(2 * sizeof(u64)));
+    c->stats.h2d_bytes += sz[0] + sz[1] + sz[2] + (size_t)n_adj * sizeof(u32) + (size_t)n_slots * sizeof(u32) + sz[5];
     // pageable sources: make sure the copies are done before the caller's buffers go away
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
     return GPE_OK;
 }
 
 int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
-    StageTimer tm(c, &c->stats.last_join_ms);
+    StageTimer tm(c, &c->stats.last_join_ms, kStageJoin);
     const u32 nq = c->b_nq;
     GPE_CUDA(c, cudaMemsetAsync(c->d_answers.p, 0, ((size_t)nq + 2) * sizeof(u64), c->stream));
     GPE_CUDA(c, cudaMemsetAsync(c->d_match_cursor.p, 0, 2 * sizeof(u64), c->stream));
@@ -254,6 +277,7 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
                         c->d_cand.as<u32>(), c->d_item_base.as<u64>(), c->d_limits.as<u64>(), answers, answers + nq + 1,
                         rank, world, d_matches, matches_cap, c->d_match_cursor.as<u64>(), c->sm_count, c->stream));
     c->stats.join_launches += 2;
+    c->stats.kernel_launches += 2;
     c->b_joined = true;
     return GPE_OK;
 }
@@ -338,6 +362,7 @@ void gpe_destroy(gpe_ctx *c) {
     for (DevBuf *b : bufs) b->release();
     c->h_pin.release();
     c->h_pin2.release();
+    for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
@@ -353,9 +378,25 @@ int gpe_sync(gpe_ctx *c) {
     return GPE_OK;
 }
 
-int gpe_set_timing(gpe_ctx *c, int enabled) {
-    if (!c) return GPE_ERR_INVALID;
-    c->timing = enabled != 0;
+int gpe_set_timing(gpe_ctx *c, int mode) {
+    if (!c || mode < 0 || mode > 2) return GPE_ERR_INVALID;
+    c->timing = mode;
+    return GPE_OK;
+}
+
+int gpe_collect_timings(gpe_ctx *c, double *sum_ms, uint64_t *count) {
+    if (!c || !sum_ms || !count) return GPE_ERR_INVALID;
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < GPE_NUM_STAGES; i++) { sum_ms[i] = 0; count[i] = 0; }
+    for (size_t i = 0; i < c->spans_used; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c->spans[i].a, c->spans[i].b) == cudaSuccess) {
+            sum_ms[c->spans[i].stage] += ms;
+            count[c->spans[i].stage]++;
+        }
+    }
+    c->spans_used = 0;
     return GPE_OK;
 }
 
@@ -462,7 +503,7 @@ int gpe_enumerate(gpe_ctx *c, uint32_t L, const uint32_t *sorted_nodes, const ui
     u64 *start_rows = c->d_start_rows.as<u64>();
     u64 *part_rows = start_rows + V + 1;
     {
-        StageTimer tm(c, &c->stats.last_enumerate_ms);
+        StageTimer tm(c, &c->stats.last_enumerate_ms, kStageEnumerate);
         GPE_CUDA(c, cudaMemsetAsync(ebase + c->n_adj, 0, sizeof(u64), c->stream));
         GPE_CUDA(c, cudaMemsetAsync(part_rows, 0, p * sizeof(u64), c->stream));
         GPE_CUDA(c, k1_count(graph_view(c), L, c->d_sorted.as<u32>(), c->d_offr.as<u32>(), ebase, c->sm_count, c->stream));
@@ -471,6 +512,7 @@ int gpe_enumerate(gpe_ctx *c, uint32_t L, const uint32_t *sorted_nodes, const ui
                                           part_rows, start_rows, c->stream));
     }
     c->stats.build_launches += 3;
+    c->stats.kernel_launches += 2 + exclusive_scan_launches((u64)c->n_adj + 1);
     std::vector<u64> host((size_t)V + 1 + p);
     GPE_CUDA(c, cudaMemcpyAsync(host.data(), start_rows, host.size() * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -596,6 +638,7 @@ int gpe_build_table(gpe_ctx *c, const uint8_t *part_select, uint64_t *n_table_ro
     cudaEventDestroy(b1);
     d_sel.release();
     c->stats.build_launches += 5;
+    c->stats.kernel_launches += 3 + exclusive_scan_launches((u64)t.n_keys + 1);
     c->tv = t;
     c->have_table = true;
     if (n_table_rows) *n_table_rows = t.n_rows;
@@ -768,6 +811,7 @@ int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) {
     GPE_CUDA(c, cudaMemcpyAsync(c->h_pin2.p, c->d_answers.p, (size_t)c->b_nq * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
     memcpy(raw_counts, c->h_pin2.p, (size_t)c->b_nq * sizeof(u64));
+    c->stats.d2h_bytes += (size_t)c->b_nq * sizeof(u64);
     return GPE_OK;
 }
 

@@ -127,7 +127,10 @@ struct gpe_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool timing = false;
+    int timing = 0;  // 0 off, 1 synchronous per stage, 2 deferred (events queued, read by gpe_collect_timings)
+    struct Span { cudaEvent_t a, b; int stage; };
+    std::vector<Span> spans;
+    size_t spans_used = 0;
     std::string err;
     gpe_stats stats{};
 
@@ -194,6 +197,7 @@ namespace gpe {
 // ---- launchers (defined in the .cu files) ------------------------------------------------------
 // device-wide exclusive scan of n u64 values, in place; total returned in d_total (device) if non-null
 cudaError_t exclusive_scan_u64(u64 *d_data, u64 n, DevBuf &tmp, cudaStream_t s);
+u64 exclusive_scan_launches(u64 n);
 
 // K1
 cudaError_t k1_count(const GraphView &g, u32 L, const u32 *sorted, const u32 *offr, u64 *cnt_r, int sm_count,

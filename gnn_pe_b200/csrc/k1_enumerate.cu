@@ -379,6 +379,13 @@ int walk_grid(int sm_count) { return sm_count * 8; }  // 8 CTAs of 8 warps per S
 
 }  // namespace
 
+u64 exclusive_scan_launches(u64 n) {
+    if (n == 0) return 0;
+    u64 levels = 0;
+    while (n > (u64)kScanBlock) { n = (n + kScanBlock - 1) / kScanBlock; levels++; }
+    return 1 + 2 * levels;
+}
+
 cudaError_t exclusive_scan_u64(u64 *d_data, u64 n, DevBuf &tmp, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     // sizes of every level

@@ -49,7 +49,8 @@ class Stats(C.Structure):
                [(n, C.c_float) for n in
                 ("last_scan_ms", "last_select_ms", "last_compact_ms", "last_join_ms", "last_build_ms",
                  "last_enumerate_ms")] + \
-               [(n, C.c_uint64) for n in ("n_qpaths", "n_qblocks", "n_slots", "n_candidates", "join_items")]
+               [(n, C.c_uint64) for n in ("n_qpaths", "n_qblocks", "n_slots", "n_candidates", "join_items",
+                                        "kernel_launches", "h2d_bytes", "d2h_bytes")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -63,6 +64,7 @@ SYMBOLS = [
     "gpe_batch_upload", "gpe_batch_filter", "gpe_batch_join", "gpe_batch_download", "gpe_clamp_answer",
     "gpe_query_batch", "gpe_batch_cand_info", "gpe_batch_cand_export", "gpe_batch_cand_merge",
     "gpe_batch_get_candidates", "gpe_batch_get_plan", "gpe_get_stats", "gpe_stream", "gpe_sync", "gpe_set_timing",
+    "gpe_collect_timings",
 ]
 
 
@@ -110,6 +112,7 @@ def lib():
         L.gpe_stream.restype = vp
         L.gpe_sync.argtypes = [vp]
         L.gpe_set_timing.argtypes = [vp, C.c_int]
+        L.gpe_collect_timings.argtypes = [vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -357,8 +360,16 @@ class GpeContext:
         self._ck(self._L.gpe_get_stats(self._h, C.byref(s)))
         return s.asdict()
 
-    def set_timing(self, on: bool):
-        self._ck(self._L.gpe_set_timing(self._h, 1 if on else 0))
+    def set_timing(self, mode: int):
+        """0 off, 1 synchronous per stage (stats()['last_*_ms']), 2 deferred (collect_timings())."""
+        self._ck(self._L.gpe_set_timing(self._h, int(mode)))
+
+    def collect_timings(self) -> dict:
+        ms = np.zeros(5, dtype=np.float64)
+        cnt = np.zeros(5, dtype=np.uint64)
+        self._ck(self._L.gpe_collect_timings(self._h, _ptr(ms), _ptr(cnt)))
+        names = ["select", "scan", "compact", "join", "enumerate"]
+        return {n: dict(ms=float(ms[i]), launches=int(cnt[i])) for i, n in enumerate(names)}
 
     def sync(self):
         self._ck(self._L.gpe_sync(self._h))

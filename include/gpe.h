@@ -161,13 +161,26 @@ typedef struct gpe_stats {
     uint64_t scan_launches, select_launches, compact_launches, join_launches, build_launches;
     float last_scan_ms, last_select_ms, last_compact_ms, last_join_ms, last_build_ms, last_enumerate_ms;
     uint64_t n_qpaths, n_qblocks, n_slots, n_candidates, join_items;
+    uint64_t kernel_launches;          /* kernels launched by this context since creation */
+    uint64_t h2d_bytes, d2h_bytes;     /* host<->device bytes of the last batch (upload .. download) */
 } gpe_stats;
 int gpe_get_stats(gpe_ctx *ctx, gpe_stats *out);
 /* The context's CUDA stream (cudaStream_t) so callers can bracket calls with their own events. */
 void *gpe_stream(gpe_ctx *ctx);
 int gpe_sync(gpe_ctx *ctx);
-/* Record per-kernel CUDA-event timings (costs a stream sync per stage); off by default. */
-int gpe_set_timing(gpe_ctx *ctx, int enabled);
+/* Per-stage CUDA-event timing on the context's stream.  mode 0: off (default).  mode 1: synchronous, each
+ * stage is followed by an event sync and lands in gpe_stats.last_*_ms.  mode 2: deferred, event pairs are
+ * queued without any extra sync and summed by gpe_collect_timings -- the way to time kernels inside a
+ * timed region without perturbing it. */
+int gpe_set_timing(gpe_ctx *ctx, int mode);
+#define GPE_STAGE_SELECT 0
+#define GPE_STAGE_SCAN 1
+#define GPE_STAGE_COMPACT 2
+#define GPE_STAGE_JOIN 3
+#define GPE_STAGE_ENUMERATE 4
+#define GPE_NUM_STAGES 5
+/* Syncs the stream, returns per-stage summed milliseconds and launch counts since the last call. */
+int gpe_collect_timings(gpe_ctx *ctx, double *sum_ms /*GPE_NUM_STAGES*/, uint64_t *count /*GPE_NUM_STAGES*/);
 
 #ifdef __cplusplus
 }
