@@ -231,6 +231,8 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
                    const u32 *q_nbrs, const u32 *q_labels, const u64 *limits) {
     const u32 n_slots = q_vbase[n_queries], n_adj = q_ebase[n_queries];
     c->b_nq = n_queries;
+    c->b_max_nq = 1;
+    for (u32 q = 0; q < n_queries; q++) c->b_max_nq = std::max(c->b_max_nq, q_vbase[q + 1] - q_vbase[q]);
     c->stats.h2d_bytes = 0;
     c->stats.d2h_bytes = 0;
     c->h_q_vbase.assign(q_vbase, q_vbase + n_queries + 1);
@@ -255,7 +257,7 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
     GPE_CUDA(c, c->d_pivot.reserve(std::max<size_t>(n_slots, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_jplan.reserve(std::max<size_t>(n_slots, 1) * sizeof(JoinDepth)));
     GPE_CUDA(c, c->d_item_base.reserve(((size_t)n_queries + 1) * sizeof(u64)));
-    GPE_CUDA(c, c->d_answers.reserve(((size_t)n_queries + 2) * sizeof(u64)));
+    GPE_CUDA(c, c->d_answers.reserve(((size_t)n_queries + 8) * sizeof(u64)));
     GPE_CUDA(c, c->d_match_cursor.reserve(2 * sizeof(u64)));
     c->stats.h2d_bytes += sz[0] + sz[1] + sz[2] + (size_t)n_adj * sizeof(u32) + (size_t)n_slots * sizeof(u32) + sz[5];
     // pageable sources: make sure the copies are done before the caller's buffers go away
@@ -263,21 +265,56 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
     return GPE_OK;
 }
 
+constexpr u64 kJoinItemCap = 1ull << 22;  // work items per round buffer
+constexpr u32 kJoinBudget = 1024;         // DFS steps before a thread exports its continuation
+
 int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     StageTimer tm(c, &c->stats.last_join_ms, kStageJoin);
     const u32 nq = c->b_nq;
-    GPE_CUDA(c, cudaMemsetAsync(c->d_answers.p, 0, ((size_t)nq + 2) * sizeof(u64), c->stream));
+    // answers[0..nq) | fetch counter | round counters: n_in(0), n_out(1) alternate
+    u64 *answers = c->d_answers.as<u64>();
+    GPE_CUDA(c, cudaMemsetAsync(c->d_answers.p, 0, ((size_t)nq + 8) * sizeof(u64), c->stream));
     GPE_CUDA(c, cudaMemsetAsync(c->d_match_cursor.p, 0, 2 * sizeof(u64), c->stream));
     GPE_CUDA(c, k3_order(nq, c->V, c->d_q_vbase.as<u32>(), c->d_q_ebase.as<u32>(), c->d_q_offsets.as<u32>(),
                          c->d_q_nbrs.as<u32>(), c->d_q_labels.as<u32>(), c->d_cand_off.as<u64>(), c->d_order.as<u32>(),
                          c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_item_base.as<u64>(), rank, world,
                          c->stream));
-    u64 *answers = c->d_answers.as<u64>();
-    GPE_CUDA(c, k3_join(graph_view(c), nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
-                        c->d_cand.as<u32>(), c->d_item_base.as<u64>(), c->d_limits.as<u64>(), answers, answers + nq + 1,
-                        rank, world, d_matches, matches_cap, c->d_match_cursor.as<u64>(), c->sm_count, c->stream));
-    c->stats.join_launches += 2;
+    JoinView jv{c->d_off.as<u32>(), c->d_nbr.as<u32>(), c->d_deg.as<u32>(), c->d_label.as<u32>(), c->d_nbrL.as<u32>(),
+                c->d_gtab.as<u32>(), c->V, c->n_labels};
+    const u32 stride = k3_item_stride(c->b_max_nq);
+    // round 0 holds one item per start candidate of this shard; b_n_cand bounds that from above
+    const u64 cap = std::max<u64>(kJoinItemCap, c->b_n_cand + 1);
+    GPE_CUDA(c, c->d_items[0].reserve(cap * stride * sizeof(u32)));
+    GPE_CUDA(c, c->d_items[1].reserve(cap * stride * sizeof(u32)));
+    u64 *fetch = answers + nq + 1, *cnt0 = answers + nq + 2, *cnt1 = answers + nq + 3;
+    GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
+                              c->d_cand.as<u32>(), c->d_item_base.as<u64>(), rank, world, c->d_items[0].as<u32>(), stride,
+                              answers, cnt0, c->sm_count, c->stream));
     c->stats.kernel_launches += 2;
+    GPE_CUDA(c, c->h_pin2.reserve(16 * sizeof(u64)));
+    u64 *pin = c->h_pin2.as<u64>();
+    int cur = 0;
+    u64 rounds = 0, items_total = 0;
+    for (;; rounds++) {
+        u64 *n_in = cur == 0 ? cnt0 : cnt1, *n_out = cur == 0 ? cnt1 : cnt0;
+        GPE_CUDA(c, cudaMemsetAsync(n_out, 0, sizeof(u64), c->stream));
+        GPE_CUDA(c, cudaMemsetAsync(fetch, 0, sizeof(u64), c->stream));
+        GPE_CUDA(c, k3_dfs_round(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_limits.as<u64>(),
+                                 answers, c->d_items[cur].as<u32>(), n_in, c->d_items[cur ^ 1].as<u32>(), n_out, cap, fetch,
+                                 kJoinBudget, d_matches, matches_cap, c->d_match_cursor.as<u64>(), c->sm_count, c->stream));
+        c->stats.kernel_launches++;
+        GPE_CUDA(c, cudaMemcpyAsync(pin, n_in, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        GPE_CUDA(c, cudaMemcpyAsync(pin + 1, n_out, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->stats.d2h_bytes += 2 * sizeof(u64);
+        items_total += pin[0];
+        if (pin[1] == 0) { rounds++; break; }
+        if (rounds > 100000) return c->fail(GPE_ERR_CUDA, "join did not converge");
+        cur ^= 1;
+    }
+    c->stats.join_launches += 2 + rounds;
+    c->stats.join_items = items_total;
+    c->join_rounds = rounds;
     c->b_joined = true;
     return GPE_OK;
 }
@@ -352,7 +389,7 @@ void gpe_destroy(gpe_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
+    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrL, &c->d_gtab, &c->d_items[0], &c->d_items[1], &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
                       &c->d_offr, &c->d_ebase, &c->d_start_rows, &c->d_scan_tmp, &c->d_tiles, &c->d_vids, &c->d_sum_u32, &c->d_sum_f64,
                       &c->d_bucket, &c->d_cursor, &c->d_qblocks, &c->d_qb_t0, &c->d_qb_prefix, &c->d_worklist,
                       &c->d_counters, &c->d_bitmap, &c->d_survivors, &c->d_chunk_cnt, &c->d_chunk_off, &c->d_cand,
@@ -443,6 +480,32 @@ int gpe_set_graph(gpe_ctx *c, uint32_t V, const uint32_t *offsets, const uint32_
     if (n_adj) GPE_CUDA(c, cudaMemcpyAsync(c->d_nbr.p, nbrs, (size_t)n_adj * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
     if (V) GPE_CUDA(c, cudaMemcpyAsync(c->d_label.p, labels, (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
     if (V) GPE_CUDA(c, cudaMemcpyAsync(c->d_deg.p, deg.data(), (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    // label-grouped copy of the adjacency + per-(vertex, label) group starts, for the join: the reference
+    // builds the same structure in Static_Graph::BuildLabelOffset (graph.cpp:126-160) but never uses it.
+    {
+        const u32 nl = c->n_labels;
+        const u64 gt_entries = (u64)V * (nl + 1);
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (gt_entries * sizeof(u32) > free_b / 4)
+            return c->fail(GPE_ERR_UNSUPPORTED, "label directory of %llu entries (V x (labels+1)) does not fit; "
+                                                "a sparse directory is not built yet", (unsigned long long)gt_entries);
+        std::vector<u32> nbrL(std::max<size_t>(n_adj, 1)), gtab(std::max<u64>(gt_entries, 1)), cnt(nl + 1);
+        for (u32 v = 0; v < V; v++) {
+            std::fill(cnt.begin(), cnt.end(), 0u);
+            for (u32 j = offsets[v]; j < offsets[v + 1]; j++) cnt[labels[nbrs[j]]]++;
+            u32 run = offsets[v];
+            u32 *row = &gtab[(u64)v * (nl + 1)];
+            for (u32 l = 0; l < nl; l++) { row[l] = run; run += cnt[l]; cnt[l] = row[l]; }
+            row[nl] = run;
+            for (u32 j = offsets[v]; j < offsets[v + 1]; j++) nbrL[cnt[labels[nbrs[j]]]++] = nbrs[j];  // stable: ids stay ascending
+        }
+        GPE_CUDA(c, c->d_nbrL.reserve(nbrL.size() * sizeof(u32)));
+        GPE_CUDA(c, c->d_gtab.reserve(gtab.size() * sizeof(u32)));
+        GPE_CUDA(c, cudaMemcpyAsync(c->d_nbrL.p, nbrL.data(), nbrL.size() * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+        GPE_CUDA(c, cudaMemcpyAsync(c->d_gtab.p, gtab.data(), gtab.size() * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+        GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
     c->have_graph = true;
     c->have_emb = c->have_enum = c->have_table = false;

@@ -137,6 +137,10 @@ struct gpe_ctx {
     // graph
     u32 V = 0, n_adj = 0, n_labels = 0, max_degree = 0;
     gpe::DevBuf d_off, d_nbr, d_label, d_deg, d_rank, d_sorted, d_member, d_vde;
+    gpe::DevBuf d_nbrL, d_gtab;  // label-grouped adjacency + group directory (join)
+    gpe::DevBuf d_items[2];     // join work items, double-buffered between rounds
+    u32 b_max_nq = 0;
+    u64 join_rounds = 0, join_items_total = 0;
     u32 e = 0;
     bool have_graph = false, have_emb = false, have_enum = false, have_table = false;
 
@@ -237,9 +241,18 @@ cudaError_t k3_counts_from_offsets(const u64 *cand_off, u32 n_slots, u32 *counts
 cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebase, const u32 *q_offsets,
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
                      JoinDepth *jplan, u64 *item_base, u32 rank, u32 world, cudaStream_t s);
-cudaError_t k3_join(const GraphView &g, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan, const u64 *cand_off,
-                    const u32 *cand, const u64 *item_base, const u64 *limits, u64 *answers, u64 *work_counter,
-                    u32 rank, u32 world, u32 *matches, u64 matches_cap, u64 *match_cursor, int sm_count,
-                    cudaStream_t s);
+// label-grouped adjacency for the join (built on the host in gpe_set_graph)
+struct JoinView {
+    const u32 *off, *nbr, *deg, *label, *nbrL, *gtab;
+    u32 V, nl;
+};
+u32 k3_item_stride(u32 max_nq);
+cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
+                          const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world, u32 *items,
+                          u32 stride, u64 *answers, u64 *n_items_out, int sm_count, cudaStream_t s);
+cudaError_t k3_dfs_round(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const u64 *limits,
+                         u64 *answers, const u32 *items_in, const u64 *n_in, u32 *items_out, u64 *out_count, u64 out_cap,
+                         u64 *fetch_counter, u32 budget, u32 *matches, u64 matches_cap, u64 *match_cursor, int sm_count,
+                         cudaStream_t s);
 
 }  // namespace gpe

@@ -6,13 +6,12 @@
 //   * candidate bitmaps -> sorted duplicate-free lists: popcount per chunk, device-wide scan, expand
 //     (a std::set iterates ascending; so does a bitmap);
 //   * matching order: one thread per query, the reference's greedy rule restated on bitmasks;
-//   * join: one warp per (query, start candidate).  The reference's per-depth candidate buffers
-//     (valid_candidate[depth], sized by max label frequency) are not materialised: a depth keeps a cursor
-//     into the pivot's adjacency list and a 32-bit mask of the lanes of the current 32-wide chunk that
-//     passed label / degree / not-yet-used / backward-edge tests, so a warp's whole DFS state is a few
-//     hundred bytes of shared memory.  Edge tests are the reference's binary search in the shorter
-//     adjacency list (graph.h:215-236).  As in the reference, candidate sets are only used for the start
-//     vertex and for ordering.
+//   * join: one thread per work item (a partial embedding + a candidate range), explicit-stack DFS with a
+//     step budget and continuation export between bounded kernel rounds (see "the join" below).  The
+//     reference's per-depth candidate buffers (valid_candidate[depth], sized by max label frequency) are
+//     not materialised: a depth keeps a cursor into the pivot's label group.  Edge tests are the
+//     reference's binary search in the shorter adjacency list (graph.h:215-236).  As in the reference,
+//     candidate sets are only used for the start vertex and for ordering.
 //
 // Latency / divergence bound (L2-resident CSR gathers), no bandwidth roofline, no tensor cores.
 #include "gpe_internal.h"
@@ -22,7 +21,6 @@ namespace gpe {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kJoinWarps = 8;
 constexpr int kMaxNQ = GPE_MAX_QUERY_VERTICES;
 
 __device__ __forceinline__ unsigned lanemask_lt() {
@@ -202,18 +200,27 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
 }
 
 // ---- the join ------------------------------------------------------------------------------------------------
-struct WarpState {
-    u32 emb[kMaxNQ];
-    u32 pos[kMaxNQ];
-    u32 msk[kMaxNQ];
-    u32 lab[kMaxNQ];
-    u32 deg[kMaxNQ];
-    u32 pvd[kMaxNQ];
-    u32 qv[kMaxNQ];
-    u64 bn[kMaxNQ];
+//
+// Work item = a partial embedding (the first `depth` vertices of the matching order) plus a range [lo, hi)
+// of the candidate segment for the next vertex.  One THREAD runs one item as an explicit-stack DFS; a
+// candidate segment is the label group of the pivot's adjacency (JoinGraph::nbrL / gtab), so a step touches
+// only neighbours that already carry the right label.  Parallelism in the reference's own decomposition is
+// tiny (|C(order[0])| start candidates, often < 100) and subtree sizes are heavy-tailed, so every item gets
+// a step budget: a thread that exhausts it writes its continuation -- for every stack level the unexplored
+// sibling range is an independent subtree -- as new items for the next round.  Rounds are plain bounded
+// kernel launches: no spinning, no device-side queue.
+struct JoinGraph {
+    const u32 *off, *nbr, *deg;  // id-sorted CSR: edge tests (graph.h:215-236)
+    const u32 *label;
+    const u32 *nbrL;             // the same adjacency grouped by neighbour label, ascending id inside a group
+    const u32 *gtab;             // V x (nl+1): start of every label group of every vertex (absolute, into nbrL)
+    u32 V, nl;
 };
 
-__device__ __forceinline__ bool has_edge(const GraphView &g, u32 u, u32 v) {
+constexpr int kItemHdr = 4;  // q, depth, lo, hi
+constexpr u32 kSplit = 8;
+
+__device__ __forceinline__ bool has_edge(const JoinGraph &g, u32 u, u32 v) {
     // graph.h:215-236: search for the larger-degree endpoint in the smaller list
     u32 du = g.deg[u], dv = g.deg[v];
     if (du < dv) { u32 t = u; u = v; v = t; dv = du; }
@@ -228,117 +235,183 @@ __device__ __forceinline__ bool has_edge(const GraphView &g, u32 u, u32 v) {
     return false;
 }
 
-__global__ void __launch_bounds__(kJoinWarps * 32) k3_join_kernel(
-    GraphView g, u32 n_queries, const u32 *__restrict__ q_vbase, const JoinDepth *__restrict__ jplan,
-    const u64 *__restrict__ cand_off, const u32 *__restrict__ cand, const u64 *__restrict__ item_base,
-    const u64 *__restrict__ limits, u64 *answers, u64 *work_counter, u32 rank, u32 world, u32 *matches,
-    u64 matches_cap, u64 *match_cursor) {
-    __shared__ WarpState s_state[kJoinWarps];
-    WarpState &st = s_state[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const u64 n_items = item_base[n_queries];
+__device__ __forceinline__ void group_range(const JoinGraph &g, u32 v, u32 label, u32 &lo, u32 &hi) {
+    if (label >= g.nl) { lo = hi = 0; return; }
+    const u32 *row = g.gtab + (u64)v * (g.nl + 1) + label;
+    lo = row[0];
+    hi = row[1];
+}
 
-    while (true) {
-        u64 item = 0;
-        if (lane == 0) item = atomicAdd((unsigned long long *)work_counter, 1ull);
-        item = __shfl_sync(kFull, item, 0);
-        if (item >= n_items) break;
-        u32 lo = 0, hi = n_queries;  // last q with item_base[q] <= item
+// depth-1 items from the start candidates of this shard (idx % world == rank)
+__global__ void __launch_bounds__(256) k3_init_items_kernel(JoinGraph g, u32 n_queries, const u32 *__restrict__ q_vbase,
+                                                            const JoinDepth *__restrict__ jplan,
+                                                            const u64 *__restrict__ cand_off, const u32 *__restrict__ cand,
+                                                            const u64 *__restrict__ item_base, u32 rank, u32 world,
+                                                            u32 *items, u32 stride, u64 *answers, u64 *n_items_out) {
+    const u64 n_items = item_base[n_queries];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_items_out = n_items;
+    for (u64 item = (u64)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (u64)gridDim.x * blockDim.x) {
+        u32 lo = 0, hi = n_queries;
         while (hi - lo > 1) {
             u32 mid = (lo + hi) >> 1;
             if (item_base[mid] <= item) lo = mid; else hi = mid;
         }
-        const u32 q = lo;
-        const u32 vb = q_vbase[q], nq = q_vbase[q + 1] - vb;
-        u64 limit = limits ? limits[q] : GPE_LIMIT_MAX;
-        if (limit == 0) limit = 1;  // the reference tests the limit only after counting a match (:851)
-        if (*(volatile u64 *)&answers[q] >= limit) continue;
-
-        __syncwarp();
-        for (u32 d = lane; d < nq; d += 32) {
-            JoinDepth jd = jplan[vb + d];
-            st.lab[d] = jd.label;
-            st.deg[d] = jd.deg;
-            st.pvd[d] = jd.pivot_depth;
-            st.qv[d] = jd.u;
-            st.bn[d] = jd.bn_mask;
-        }
-        __syncwarp();
+        const u32 q = lo, vb = q_vbase[q], nq = q_vbase[q + 1] - vb;
         const u64 idx = (item - item_base[q]) * world + rank;
-        const u32 v0 = cand[cand_off[vb + st.qv[0]] + idx];
-        u64 found = 0;
+        const u32 v0 = cand[cand_off[vb + jplan[vb].u] + idx];
+        u32 *it = items + item * stride;
+        it[0] = q;
+        it[1] = 1;
+        it[kItemHdr] = v0;
         if (nq == 1) {
-            found = 1;
-            if (matches && lane == 0) {
-                u64 p = atomicAdd((unsigned long long *)match_cursor, 1ull);
-                if (p < matches_cap) matches[p] = v0;
-            }
+            it[2] = it[3] = 0;  // nothing below the start vertex: the candidate itself is the match
+            atomicAdd((unsigned long long *)&answers[q], 1ull);
         } else {
-            if (lane == 0) { st.emb[0] = v0; st.pos[1] = 0; st.msk[1] = 0; }
-            __syncwarp();
-            int d = 1;
-            while (d >= 1) {
-                u32 m = st.msk[d];
-                const u32 p = st.emb[st.pvd[d]];
-                const u32 beg = g.off[p], end = g.off[p + 1];
-                if (m == 0) {
-                    const u32 at = beg + st.pos[d];
-                    if (at >= end) { d--; continue; }
-                    const u32 i = at + lane;
-                    bool ok = false;
-                    u32 c = 0;
-                    if (i < end) {
-                        c = g.nbr[i];
-                        ok = g.label[c] == st.lab[d] && g.deg[c] >= st.deg[d];
-                        for (int t = 0; ok && t < d; t++) ok = st.emb[t] != c;
-                        u64 bn = st.bn[d];
-                        while (ok && bn) {
-                            int t = __ffsll((long long)bn) - 1;
-                            bn &= bn - 1;
-                            ok = has_edge(g, c, st.emb[t]);
-                        }
+            u32 s, e;
+            group_range(g, v0, jplan[vb + 1].label, s, e);  // pivot of depth 1 is always the start vertex
+            it[2] = s;
+            it[3] = e;
+        }
+    }
+}
+
+template <int MAXNQ>
+__global__ void __launch_bounds__(256) k3_dfs_kernel(JoinGraph g, const u32 *__restrict__ q_vbase,
+                                                     const JoinDepth *__restrict__ jplan, const u64 *__restrict__ limits,
+                                                     u64 *answers, const u32 *__restrict__ items_in,
+                                                     const u64 *__restrict__ n_in_ptr, u32 *items_out, u64 *out_count,
+                                                     u64 out_cap, u64 *fetch_counter, u32 budget, u32 *matches,
+                                                     u64 matches_cap, u64 *match_cursor) {
+    constexpr u32 stride = MAXNQ + kItemHdr;
+    const int lane = threadIdx.x & 31;
+    const u64 n_in = *n_in_ptr;
+    u32 emb[MAXNQ], cur[MAXNQ], end[MAXNQ];
+    bool have = false, exhausted = false;
+    u32 q = 0, vb = 0, nq = 0, base = 0, d = 0, steps = 0, lab0 = 0;
+    u32 acc_q = 0xffffffffu;
+    u64 acc = 0;
+
+    for (;;) {
+        // ---- fetch: lanes without an item claim consecutive indices with one atomic per warp ----
+        unsigned need = __ballot_sync(kFull, !have && !exhausted);
+        if (need) {
+            int leader = __ffs(need) - 1;
+            u64 b = 0;
+            if (lane == leader) b = atomicAdd((unsigned long long *)fetch_counter, (unsigned long long)__popc(need));
+            b = __shfl_sync(kFull, b, leader);
+            if (!have && !exhausted) {
+                u64 idx = b + __popc(need & lanemask_lt());
+                if (idx >= n_in) {
+                    exhausted = true;
+                } else {
+                    const u32 *it = items_in + idx * stride;
+                    u32 iq = it[0];
+                    if (iq != acc_q) {
+                        if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
+                        acc = 0;
+                        acc_q = iq;
                     }
-                    m = __ballot_sync(kFull, ok);
-                    __syncwarp();
-                    if (lane == 0) st.pos[d] += 32;
-                    if (d == (int)nq - 1) {
-                        if (m) {
-                            found += __popc(m);
-                            if (matches) {
-                                u64 mb = 0;
-                                if (lane == 0) mb = atomicAdd((unsigned long long *)match_cursor, (unsigned long long)__popc(m));
-                                mb = __shfl_sync(kFull, mb, 0);
-                                u64 mine = mb + __popc(m & lanemask_lt());
-                                if (ok && mine < matches_cap) {
-                                    u32 *row = matches + mine * nq;
-                                    for (int t = 0; t < d; t++) row[st.qv[t]] = st.emb[t];
-                                    row[st.qv[d]] = c;
-                                }
-                            }
-                        }
-                        __syncwarp();
-                        continue;
+                    u64 limit = limits ? limits[iq] : GPE_LIMIT_MAX;
+                    if (limit == 0) limit = 1;  // the reference tests the limit only after counting a match (:851)
+                    q = iq;
+                    vb = q_vbase[q];
+                    nq = q_vbase[q + 1] - vb;
+                    base = it[1];
+                    if (base < nq && *(volatile u64 *)&answers[q] < limit) {
+                        for (u32 t = 0; t < base; t++) emb[t] = it[kItemHdr + t];
+                        lab0 = g.label[emb[0]];  // caller-supplied start candidates need not carry the query label
+                        d = base;
+                        cur[d] = it[2];
+                        end[d] = it[3];
+                        steps = 0;
+                        have = true;
                     }
-                    if (lane == 0) st.msk[d] = m;
-                    __syncwarp();
-                    if (m == 0) continue;
                 }
-                // descend into the lowest remaining lane of this chunk
-                const int b = __ffs(m) - 1;
-                const u32 c = g.nbr[beg + st.pos[d] - 32 + b];
-                __syncwarp();
-                if (lane == 0) {
-                    st.msk[d] = m & (m - 1);
-                    st.emb[d] = c;
-                    st.pos[d + 1] = 0;
-                    st.msk[d + 1] = 0;
-                }
-                __syncwarp();
-                d++;
             }
         }
-        if (lane == 0 && found) atomicAdd((unsigned long long *)&answers[q], (unsigned long long)found);
+        if (__ballot_sync(kFull, have) == 0) break;
+        if (!have) continue;
+
+        // ---- one DFS step ----
+        if (cur[d] < end[d]) {
+            const u32 c = g.nbrL[cur[d]++];
+            const JoinDepth jd = jplan[vb + d];
+            bool ok = jd.deg <= 1 || g.deg[c] >= jd.deg;  // a neighbour has degree >= 1
+            for (u32 t = 0; ok && t < d; t++) ok = emb[t] != c;
+            u64 bn = jd.bn_mask;
+            while (ok && bn) {
+                int t = __ffsll((long long)bn) - 1;
+                bn &= bn - 1;
+                ok = has_edge(g, c, emb[t]);
+            }
+            if (ok) {
+                if (d == nq - 1) {
+                    acc++;
+                    if (matches) {
+                        u64 pos = atomicAdd((unsigned long long *)match_cursor, 1ull);
+                        if (pos < matches_cap) {
+                            u32 *row = matches + pos * nq;
+                            for (u32 t = 0; t < d; t++) row[jplan[vb + t].u] = emb[t];
+                            row[jd.u] = c;
+                        }
+                    }
+                } else {
+                    emb[d] = c;
+                    d++;
+                    const JoinDepth nd = jplan[vb + d];
+                    u32 s, e;
+                    group_range(g, emb[nd.pivot_depth], nd.label, s, e);
+                    if (d == nq - 1 && nd.bn_mask == 0 && nd.deg <= 1 && !matches) {
+                        // leaf fast path: every member of the group matches unless it is already used; the used
+                        // vertices inside the group are the embedded ones with this label adjacent to the pivot
+                        u32 used = 0;
+                        const u32 p = emb[nd.pivot_depth];
+                        for (u32 t = 0; t < d; t++)
+                            if (t != nd.pivot_depth && (t ? jplan[vb + t].label : lab0) == nd.label && has_edge(g, p, emb[t])) used++;
+                        acc += (e - s) - used;
+                        d--;
+                    } else {
+                        cur[d] = s;
+                        end[d] = e;
+                    }
+                }
+            }
+        } else if (d == base) {
+            have = false;
+        } else {
+            d--;
+        }
+
+        // ---- budget: hand the unexplored sibling ranges of every stack level to the next round ----
+        if (have && ++steps >= budget) {
+            u32 pieces = 0;
+            for (u32 l = base; l <= d; l++) pieces += min(end[l] - cur[l], kSplit);
+            if (pieces == 0) {
+                have = false;
+            } else {
+                u64 o = atomicAdd((unsigned long long *)out_count, (unsigned long long)pieces);
+                if (o + pieces > out_cap) {
+                    atomicAdd((unsigned long long *)out_count, (unsigned long long)(0ull - pieces));  // undo; keep running
+                    steps = 0;
+                } else {
+                    for (u32 l = base; l <= d; l++) {
+                        u32 len = end[l] - cur[l], np = min(len, kSplit);
+                        for (u32 k = 0; k < np; k++) {
+                            u32 *it = items_out + o * stride;
+                            it[0] = q;
+                            it[1] = l;
+                            it[2] = cur[l] + (u32)((u64)len * k / np);
+                            it[3] = cur[l] + (u32)((u64)len * (k + 1) / np);
+                            for (u32 t = 0; t < l; t++) it[kItemHdr + t] = emb[t];
+                            o++;
+                        }
+                    }
+                    have = false;
+                }
+            }
+        }
     }
+    if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
 }
 
 }  // namespace
@@ -385,13 +458,39 @@ cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebas
     return cudaGetLastError();
 }
 
-cudaError_t k3_join(const GraphView &g, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan, const u64 *cand_off,
-                    const u32 *cand, const u64 *item_base, const u64 *limits, u64 *answers, u64 *work_counter,
-                    u32 rank, u32 world, u32 *matches, u64 matches_cap, u64 *match_cursor, int sm_count,
-                    cudaStream_t s) {
-    k3_join_kernel<<<sm_count * 4, kJoinWarps * 32, 0, s>>>(g, n_queries, q_vbase, jplan, cand_off, cand, item_base,
-                                                           limits, answers, work_counter, rank, world, matches,
-                                                           matches_cap, match_cursor);
+u32 k3_item_stride(u32 max_nq) {
+    u32 m = max_nq <= 8 ? 8 : max_nq <= 16 ? 16 : max_nq <= 32 ? 32 : 64;
+    return m + kItemHdr;
+}
+
+cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
+                          const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world, u32 *items,
+                          u32 stride, u64 *answers, u64 *n_items_out, int sm_count, cudaStream_t s) {
+    JoinGraph g{jv.off, jv.nbr, jv.deg, jv.label, jv.nbrL, jv.gtab, jv.V, jv.nl};
+    k3_init_items_kernel<<<sm_count * 4, 256, 0, s>>>(g, n_queries, q_vbase, jplan, cand_off, cand, item_base, rank, world,
+                                                     items, stride, answers, n_items_out);
+    return cudaGetLastError();
+}
+
+cudaError_t k3_dfs_round(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const u64 *limits,
+                         u64 *answers, const u32 *items_in, const u64 *n_in, u32 *items_out, u64 *out_count, u64 out_cap,
+                         u64 *fetch_counter, u32 budget, u32 *matches, u64 matches_cap, u64 *match_cursor, int sm_count,
+                         cudaStream_t s) {
+    JoinGraph g{jv.off, jv.nbr, jv.deg, jv.label, jv.nbrL, jv.gtab, jv.V, jv.nl};
+#define LAUNCH(M)                                                                                                     \
+    static int per_sm_##M = 0;                                                                                        \
+    if (!per_sm_##M) {                                                                                                \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_##M, k3_dfs_kernel<M>, 256, 0) != cudaSuccess ||    \
+            per_sm_##M < 1)                                                                                           \
+            per_sm_##M = 4;                                                                                           \
+    }                                                                                                                 \
+    k3_dfs_kernel<M><<<sm_count * per_sm_##M, 256, 0, s>>>(g, q_vbase, jplan, limits, answers, items_in, n_in, items_out, out_count, \
+                                            out_cap, fetch_counter, budget, matches, matches_cap, match_cursor)
+    if (max_nq <= 8) { LAUNCH(8); }
+    else if (max_nq <= 16) { LAUNCH(16); }
+    else if (max_nq <= 32) { LAUNCH(32); }
+    else { LAUNCH(64); }
+#undef LAUNCH
     return cudaGetLastError();
 }
 

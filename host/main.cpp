@@ -1,0 +1,205 @@
+// main.cpp -- the reference's command line (GNN-PE/src/main.cpp:38-184) on top of libgpe.so.
+//
+//   main -f <dataset dir/> -d <data.graph> -q <query.graph> -m offline|online -p <partitions>
+//        -l <path length> -e <embedding dim> -n <MAX|answers>
+//
+// Same flags (short and long forms, main.cpp:46-54), same defaults (main.cpp:40-44, custom.h:47-50), same
+// files (gnn-pe/membership.txt in, gnn-pe/all_paths.txt and partitions/partition-i/partition_paths.txt
+// out) and the same stdout lines (graph.cpp:244-247, custom.h:630, main.cpp:179).  Everything
+// data-parallel goes through the C ABI in include/gpe.h; there is no CPU fallback.
+//
+// Differences, all deliberate:
+//   * online mode does not parse all_paths.txt / build index.dat: it re-enumerates on the GPU from the
+//     graph and membership.txt (milliseconds) and scans instead of traversing an R*-tree;
+//   * missing input files are errors (the reference reads zeros silently, main.cpp:80-85);
+//   * -l other than 2 follows the patched-oracle semantics of SURVEY.md F5 (only l=2 and l=3 are built).
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "gpe.h"
+
+namespace {
+
+struct Options {
+    std::string file = "../Test/", data = "../Test/data_graph.graph", query = "../Test/query_graph.graph";
+    std::string mode = "offline", answers = "MAX";
+    uint32_t partitions = 5, length = 2, embedding = 2;
+};
+
+bool parse(int argc, char **argv, Options &o) {
+    struct Opt { const char *s, *l; int id; };
+    static const Opt opts[] = {{"-f", "--file", 0}, {"-d", "--data", 1}, {"-q", "--query", 2}, {"-m", "--mode", 3},
+                               {"-p", "--partition", 4}, {"-l", "--length", 5}, {"-e", "--embedding", 6},
+                               {"-n", "--answers", 7}};
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i], val;
+        int id = -1;
+        for (const Opt &op : opts) {
+            std::string s = op.s, l = op.l;
+            if (a == s || a == l) { id = op.id; if (i + 1 < argc) val = argv[++i]; else return false; break; }
+            if (a.rfind(l + "=", 0) == 0) { id = op.id; val = a.substr(l.size() + 1); break; }
+            if (a.rfind(s, 0) == 0 && a.size() > 2 && a[1] != '-') { id = op.id; val = a.substr(a[2] == '=' ? 3 : 2); break; }
+        }
+        if (a == "-h" || a == "--help") {
+            std::puts("usage: main [-f dir/] [-d data.graph] [-q query.graph] [-m offline|online] [-p N] [-l N] [-e N] [-n MAX|N]");
+            std::exit(0);
+        }
+        if (id < 0) { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return false; }
+        switch (id) {
+            case 0: o.file = val; break;
+            case 1: o.data = val; break;
+            case 2: o.query = val; break;
+            case 3: o.mode = val; break;
+            case 4: o.partitions = (uint32_t)std::stoul(val); break;
+            case 5: o.length = (uint32_t)std::stoul(val); break;
+            case 6: o.embedding = (uint32_t)std::stoul(val); break;
+            case 7: o.answers = val; break;
+        }
+    }
+    return true;
+}
+
+struct Graph {
+    uint32_t V = 0, E = 0;
+    std::vector<uint32_t> off, nbr, lab;
+};
+
+bool load(const std::string &path, Graph &g) {
+    if (gpe_host_load_graph(path.c_str(), &g.V, &g.E, nullptr, nullptr, nullptr) != GPE_OK) {
+        std::cout << "Can not open the graph file " << path << " ." << std::endl;  // graph.cpp:166-168
+        return false;
+    }
+    g.off.assign((size_t)g.V + 1, 0);
+    g.nbr.assign(std::max<size_t>((size_t)g.E * 2, 1), 0);
+    g.lab.assign(std::max<size_t>(g.V, 1), 0);
+    return gpe_host_load_graph(path.c_str(), &g.V, &g.E, g.off.data(), g.nbr.data(), g.lab.data()) == GPE_OK;
+}
+
+void print_meta(const Graph &g) {  // Static_Graph::printGraphMetaData, graph.cpp:244-247
+    std::unordered_map<uint32_t, uint32_t> freq;
+    uint32_t max_label = 0, max_deg = 0, max_freq = 0;
+    for (uint32_t v = 0; v < g.V; v++) {
+        max_label = std::max(max_label, g.lab[v]);
+        max_deg = std::max(max_deg, g.off[v + 1] - g.off[v]);
+        max_freq = std::max(max_freq, ++freq[g.lab[v]]);
+    }
+    uint32_t labels_count = g.V ? std::max<uint32_t>((uint32_t)freq.size(), max_label + 1) : 0;  // graph.cpp:223
+    std::cout << "|V|: " << g.V << ", |E|: " << g.E << ", |Σ|: " << labels_count << std::endl;
+    std::cout << "Max Degree: " << max_deg << ", Max Label Frequency: " << max_freq << std::endl;
+}
+
+bool read_membership(const std::string &path, uint32_t V, std::vector<uint32_t> &sorted, std::vector<uint32_t> &member) {
+    std::ifstream fin(path);
+    if (!fin.is_open()) { std::fprintf(stderr, "cannot open %s (run gnnpe.py first)\n", path.c_str()); return false; }
+    sorted.assign(V, 0);
+    member.assign(V, 0);
+    for (uint32_t i = 0; i < V; i++) {  // main.cpp:81-84
+        uint32_t v, part;
+        if (!(fin >> v >> part) || v >= V) { std::fprintf(stderr, "%s: bad line %u\n", path.c_str(), i); return false; }
+        sorted[i] = v;
+        member[v] = part;
+    }
+    return true;
+}
+
+#define CK(ctx, call)                                                                  \
+    do {                                                                               \
+        if ((call) != GPE_OK) {                                                        \
+            std::fprintf(stderr, "libgpe: %s\n", gpe_last_error(ctx));                 \
+            return 1;                                                                  \
+        }                                                                              \
+    } while (0)
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    Options o;
+    if (!parse(argc, argv, o)) return 2;
+    const uint32_t L = o.length + 1;  // main.cpp:58
+    uint64_t limit = GPE_LIMIT_MAX;   // main.cpp:62-69
+    if (o.answers != "MAX") limit = (uint64_t)(uint32_t)std::stoi(o.answers);
+    const std::string partitions_path = o.file + "gnn-pe/partitions/";
+
+    Graph G;
+    if (!load(o.data, G)) return -1;
+    print_meta(G);
+
+    std::vector<uint32_t> sorted, member;
+    if (!read_membership(o.file + "gnn-pe/membership.txt", G.V, sorted, member)) return 1;
+    for (uint32_t v = 0; v < G.V; v++)
+        if (member[v] >= o.partitions) { std::fprintf(stderr, "membership.txt names partition %u but -p is %u\n", member[v], o.partitions); return 1; }
+
+    gpe_ctx *ctx = nullptr;
+    if (gpe_create(0, &ctx) != GPE_OK) { std::fprintf(stderr, "libgpe: %s\n", gpe_last_error(nullptr)); return 1; }
+    CK(ctx, gpe_set_graph(ctx, G.V, G.off.data(), G.nbr.data(), G.lab.data()));
+    std::vector<uint64_t> rows_pp(o.partitions);
+    uint64_t n_rows = 0;
+    CK(ctx, gpe_enumerate(ctx, L, sorted.data(), member.data(), o.partitions, rows_pp.data(), &n_rows));
+
+    if (o.mode == "offline") {
+        if (n_rows > UINT_MAX) { std::fprintf(stderr, "%llu paths do not fit the reference's 32-bit text format\n", (unsigned long long)n_rows); return 1; }
+        std::vector<uint64_t> start((size_t)G.V + 1);
+        CK(ctx, gpe_start_rows(ctx, start.data()));
+        for (uint32_t i = 0; i < o.partitions; i++) {  // main.cpp:98-108
+            std::string name = partitions_path + "partition-" + std::to_string(i) + "/partition_paths.txt";
+            FILE *f = std::fopen(name.c_str(), "w");
+            if (!f) { std::fprintf(stderr, "cannot write %s\n", name.c_str()); return 1; }
+            std::fprintf(f, "%llu\n", (unsigned long long)rows_pp[i]);
+            for (uint32_t r = 0; r < G.V; r++)
+                if (member[sorted[r]] == i)
+                    for (uint64_t id = start[r]; id < start[r + 1]; id++) std::fprintf(f, "%llu\n", (unsigned long long)id);
+            std::fclose(f);
+        }
+        std::string name = o.file + "/gnn-pe/all_paths.txt";  // main.cpp:110-119
+        FILE *f = std::fopen(name.c_str(), "w");
+        if (!f) { std::fprintf(stderr, "cannot write %s\n", name.c_str()); return 1; }
+        std::fprintf(f, "%llu\n", (unsigned long long)n_rows);
+        const uint64_t chunk = 1u << 22;
+        std::vector<uint32_t> rows;
+        for (uint64_t first = 0; first < n_rows; first += chunk) {
+            uint64_t n = std::min(chunk, n_rows - first);
+            rows.resize(n * L);
+            CK(ctx, gpe_dump_paths(ctx, first, n, rows.data()));
+            for (uint64_t r = 0; r < n; r++) {
+                for (uint32_t k = 0; k < L; k++) std::fprintf(f, "%u ", rows[r * L + k]);
+                std::fputc('\n', f);
+            }
+        }
+        std::fclose(f);
+    }
+
+    if (o.mode == "online") {
+        std::vector<double> x((size_t)G.V * o.embedding), vde((size_t)G.V * o.embedding);
+        CK(ctx, gpe_host_gen_vde(G.V, G.off.data(), G.nbr.data(), G.lab.data(), o.embedding, x.data(), vde.data()));
+        CK(ctx, gpe_set_embeddings(ctx, o.embedding, vde.data()));
+        uint64_t table_rows = 0;
+        CK(ctx, gpe_build_table(ctx, nullptr, &table_rows));
+
+        Graph Q;
+        if (!load(o.query, Q)) return -1;
+        uint32_t vbase[2] = {0, Q.V}, ebase[2] = {0, Q.off[Q.V]};
+        gpe_batch batch{1, vbase, ebase, Q.off.data(), Q.nbr.data(), Q.lab.data(), &limit};
+        uint32_t plan_size = 0;
+        CK(ctx, gpe_host_query_plan(Q.V, Q.off.data(), Q.nbr.data(), Q.lab.data(), L, o.embedding, 0, nullptr, nullptr,
+                                    nullptr, nullptr, &plan_size));
+        std::cout << plan_size << std::endl;  // custom.h:630
+        uint64_t answer = 0;
+        auto t0 = std::chrono::high_resolution_clock::now();  // plan + filter + refinement, as main.cpp:148-179 sums
+        CK(ctx, gpe_query_batch(ctx, &batch, 0, &answer));
+        auto t1 = std::chrono::high_resolution_clock::now();
+        double ms = std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count() / 1e6;
+        std::cout << "Answer Number: " << (uint32_t)answer << " Query Time (ms): " << ms << std::endl;  // main.cpp:179
+    }
+    gpe_destroy(ctx);
+    return 0;
+}

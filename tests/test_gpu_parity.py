@@ -220,3 +220,40 @@ def test_random_graphs_against_oracle(seed, V, E, nl, l, e):
     ans = ctx.query_batch(queries, [2_000_000] * len(queries))
     assert ans.tolist() == expect
     ctx.close()
+
+
+def test_host_cli_quickstart(tmp_path):
+    """The C++ host keeps the reference's CLI, files and stdout: offline then online on the quick start."""
+    import os
+    import shutil
+    import subprocess
+    from tests.golden_util import ROOT
+    main = os.path.join(ROOT, "host", "main")
+    if not os.path.exists(main):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "host")])
+    gold = load_case("quickstart")
+    d = str(tmp_path) + "/"
+    os.makedirs(d + "gnn-pe/partitions")
+    for i in range(gold["p"]):
+        os.makedirs(d + f"gnn-pe/partitions/partition-{i}")
+    shutil.copy(gold["membership_path"], d + "gnn-pe/membership.txt")
+    out = subprocess.check_output([main, "-f", d, "-d", gold["data_path"], "-m", "offline"]).decode()
+    assert "|V|: 3112, |E|: 12519, |Σ|: 71" in out and "Max Degree: 168, Max Label Frequency: 622" in out
+    text = open(d + "gnn-pe/all_paths.txt", "rb").read()
+    assert hashlib.md5(text).hexdigest() == gold["all_paths_md5"] == "61f074b1f90c96806c20f7000d1979a6"
+    ids = []
+    for i in range(gold["p"]):
+        lines = open(d + f"gnn-pe/partitions/partition-{i}/partition_paths.txt").read().split()
+        assert int(lines[0]) == gold["rows_per_partition"][i] == len(lines) - 1
+        part = list(map(int, lines[1:]))
+        assert part == sorted(part)
+        ids += part
+    assert sorted(ids) == list(range(gold["n_rows"]))
+    out = subprocess.check_output([main, "--file", d, "--data", gold["data_path"], "--query",
+                                   gold["query_paths_files"][0], "--mode=online", "-p5", "-l", "2", "-e", "2"]).decode()
+    lines = out.strip().splitlines()
+    assert lines[2] == "6"                       # plan size, custom.h:630
+    assert lines[3].startswith("Answer Number: 45426 Query Time (ms): ")
+    out = subprocess.check_output([main, "-f", d, "-d", gold["data_path"], "-q", gold["query_paths_files"][0],
+                                   "-m", "online", "-n", "1000"]).decode()
+    assert "Answer Number: 1000 " in out
