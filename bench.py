@@ -186,17 +186,15 @@ def main():
 
     w, g, queries = load_workload(args.workload, rank, world, barrier)
     L, e, p = w["l"] + 1, w["e"], max(w["p"], world)
+    from gnn_pe_b200 import sharding
     ctx = gpe.GpeContext(local)
+    eng = sharding.ShardedEngine(ctx, rank, world)
     t0 = time.time()
-    ctx.set_graph(g.offsets, g.nbrs, g.labels)
     _, vde = gpe.host_gen_vde(g.offsets, g.nbrs, g.labels, e)
-    ctx.set_embeddings(vde)
     sorted_nodes = graph_io.degree_order(g)
     membership = graph_io.block_membership(g.V, p)
     ctx.set_timing(1)
-    n_rows, rows_pp = ctx.enumerate(L, sorted_nodes, membership, p)
-    sel = np.array([1 if i % world == rank else 0 for i in range(p)], dtype=np.uint8)
-    table_rows = ctx.build_table(sel if world > 1 else None)
+    n_rows, rows_pp, table_rows = eng.build(g, w["l"], e, p, sorted_nodes, membership, vde)
     st = ctx.stats()
     build = dict(enumerate_ms=st["last_enumerate_ms"], build_table_ms=st["last_build_ms"], rows=n_rows,
                  table_rows_this_rank=table_rows, setup_s=time.time() - t0)
@@ -205,37 +203,8 @@ def main():
     stream = torch.cuda.ExternalStream(ctx.stream)
     nq = len(queries)
     limits = [gpe.LIMIT_MAX] * nq
-
-    def step_resident():
-        ctx.batch_filter()
-        if world > 1:
-            exchange()
-        ctx.batch_join(rank, world)
-
-    def exchange():
-        # C1: all-gather of the shards' sorted candidate lists over NCCL, then a device-side union
-        n_slots, total = ctx.batch_cand_info()
-        counts = torch.empty(n_slots, dtype=torch.int32, device="cuda")
-        tot = torch.tensor([total], dtype=torch.int64, device="cuda")
-        tots = torch.empty(world, dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(tots, tot)
-        stride = int(tots.max().item())
-        cand = torch.zeros(max(stride, 1), dtype=torch.int32, device="cuda")
-        ctx.batch_cand_export(counts.data_ptr(), cand.data_ptr())
-        all_counts = torch.empty(world * n_slots, dtype=torch.int32, device="cuda")
-        all_cand = torch.empty(world * max(stride, 1), dtype=torch.int32, device="cuda")
-        dist.all_gather_into_tensor(all_counts, counts)
-        dist.all_gather_into_tensor(all_cand, cand)
-        torch.cuda.current_stream().synchronize()
-        ctx.batch_cand_merge(world, all_counts.data_ptr(), all_cand.data_ptr(), max(stride, 1))
-
-    def finish():
-        raw = ctx.batch_download()
-        if world > 1:
-            t = torch.from_numpy(raw.astype(np.int64)).cuda()
-            dist.all_reduce(t)  # C2: match counts summed over shards
-            raw = t.cpu().numpy().astype(np.uint64)
-        return np.array([ctx.clamp(r, l) for r, l in zip(raw, limits)], dtype=np.uint64)
+    step_resident = eng.step
+    finish = lambda: eng.finish(limits)
 
     with torch.cuda.stream(stream):
         ctx.batch_upload(queries, limits)

@@ -268,6 +268,15 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
 constexpr u64 kJoinItemCap = 1ull << 22;  // work items per round buffer
 constexpr u32 kJoinBudget = 1024;         // DFS steps before a thread exports its continuation
 
+u32 join_budget() {
+    static u32 b = 0;
+    if (!b) {
+        const char *e = getenv("GPE_JOIN_BUDGET");  // tuning knob for experiments
+        b = e && atoi(e) > 0 ? (u32)atoi(e) : kJoinBudget;
+    }
+    return b;
+}
+
 int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     StageTimer tm(c, &c->stats.last_join_ms, kStageJoin);
     const u32 nq = c->b_nq;
@@ -286,7 +295,10 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     const u64 cap = std::max<u64>(kJoinItemCap, c->b_n_cand + 1);
     GPE_CUDA(c, c->d_items[0].reserve(cap * stride * sizeof(u32)));
     GPE_CUDA(c, c->d_items[1].reserve(cap * stride * sizeof(u32)));
-    u64 *fetch = answers + nq + 1, *cnt0 = answers + nq + 2, *cnt1 = answers + nq + 3;
+    u64 *fetch = answers + nq + 1, *cnt0 = answers + nq + 2, *cnt1 = answers + nq + 3, *step_ctr = answers + nq + 4;
+    const bool trace = getenv("GPE_TRACE_JOIN") != nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (trace) { cudaEventCreate(&t0); cudaEventCreate(&t1); }
     GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
                               c->d_cand.as<u32>(), c->d_item_base.as<u64>(), rank, world, c->d_items[0].as<u32>(), stride,
                               answers, cnt0, c->sm_count, c->stream));
@@ -299,14 +311,25 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
         u64 *n_in = cur == 0 ? cnt0 : cnt1, *n_out = cur == 0 ? cnt1 : cnt0;
         GPE_CUDA(c, cudaMemsetAsync(n_out, 0, sizeof(u64), c->stream));
         GPE_CUDA(c, cudaMemsetAsync(fetch, 0, sizeof(u64), c->stream));
+        if (trace) cudaEventRecord(t0, c->stream);
         GPE_CUDA(c, k3_dfs_round(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_limits.as<u64>(),
                                  answers, c->d_items[cur].as<u32>(), n_in, c->d_items[cur ^ 1].as<u32>(), n_out, cap, fetch,
-                                 kJoinBudget, d_matches, matches_cap, c->d_match_cursor.as<u64>(), c->sm_count, c->stream));
+                                 join_budget(), d_matches, matches_cap, c->d_match_cursor.as<u64>(), step_ctr, c->sm_count,
+                                 c->stream));
+        if (trace) cudaEventRecord(t1, c->stream);
         c->stats.kernel_launches++;
         GPE_CUDA(c, cudaMemcpyAsync(pin, n_in, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
         GPE_CUDA(c, cudaMemcpyAsync(pin + 1, n_out, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        GPE_CUDA(c, cudaMemcpyAsync(pin + 2, step_ctr, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
         GPE_CUDA(c, cudaStreamSynchronize(c->stream));
-        c->stats.d2h_bytes += 2 * sizeof(u64);
+        c->stats.d2h_bytes += 3 * sizeof(u64);
+        if (trace) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, t0, t1);
+            fprintf(stderr, "[gpe join] round %llu: items_in=%llu items_out=%llu steps_so_far=%llu %.3f ms\n",
+                    (unsigned long long)rounds, (unsigned long long)pin[0], (unsigned long long)pin[1],
+                    (unsigned long long)pin[2], ms);
+        }
         items_total += pin[0];
         if (pin[1] == 0) { rounds++; break; }
         if (rounds > 100000) return c->fail(GPE_ERR_CUDA, "join did not converge");
@@ -314,7 +337,9 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     }
     c->stats.join_launches += 2 + rounds;
     c->stats.join_items = items_total;
-    c->join_rounds = rounds;
+    c->stats.join_rounds = rounds;
+    c->stats.join_steps = pin[2];
+    if (trace) { cudaEventDestroy(t0); cudaEventDestroy(t1); }
     c->b_joined = true;
     return GPE_OK;
 }

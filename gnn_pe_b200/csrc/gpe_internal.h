@@ -118,6 +118,9 @@ struct JoinDepth {
     u32 deg;
     u32 pivot_depth;  // depth at which pivot[d] was matched
     u64 bn_mask;      // depths of the other backward neighbours (generateBN, custom.h:724-755)
+    u64 same_mask;    // earlier depths whose vertex may equal a candidate of this depth (same label)
+    u32 tail_k;       // [depth 0 only] number of trailing leaves counted instead of walked
+    u32 tail_mode;    // [depth 0 only] 0 none, 1 product of distinct-label leaves, 2 two leaves sharing a label
 };
 
 }  // namespace gpe
@@ -252,7 +255,7 @@ cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase,
                           u32 stride, u64 *answers, u64 *n_items_out, int sm_count, cudaStream_t s);
 cudaError_t k3_dfs_round(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const u64 *limits,
                          u64 *answers, const u32 *items_in, const u64 *n_in, u32 *items_out, u64 *out_count, u64 out_cap,
-                         u64 *fetch_counter, u32 budget, u32 *matches, u64 matches_cap, u64 *match_cursor, int sm_count,
-                         cudaStream_t s);
+                         u64 *fetch_counter, u32 budget, u32 *matches, u64 matches_cap, u64 *match_cursor,
+                         u64 *step_counter, int sm_count, cudaStream_t s);
 
 }  // namespace gpe

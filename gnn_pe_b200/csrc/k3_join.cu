@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
             }
             u32 depth_of[kMaxNQ];
             for (u32 i = 0; i < nq; i++) depth_of[ord[i]] = i;
+            u32 pvd[kMaxNQ], lab[kMaxNQ];
+            bool fast[kMaxNQ];
             for (u32 i = 0; i < nq; i++) {
                 u32 u = ord[i];
                 JoinDepth jd;
@@ -170,6 +172,9 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 jd.deg = qdeg(u);
                 jd.pivot_depth = 0;
                 jd.bn_mask = 0;
+                jd.same_mask = 0;
+                jd.tail_k = 0;
+                jd.tail_mode = 0;
                 if (i > 0) {
                     u32 pv = 0xffffffffu;
                     for (u32 j = 0; j < i; j++)
@@ -180,9 +185,34 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                         u32 w = nbr[j];
                         if (depth_of[w] < i && w != pv) jd.bn_mask |= 1ull << depth_of[w];
                     }
+                    // depths whose vertex can equal a candidate of this depth: same query label; depth 0 always,
+                    // because caller-supplied start candidates (gpe_refine) are not label-checked
+                    jd.same_mask = 1ull;
+                    for (u32 j = 1; j < i; j++)
+                        if (lab[j] == jd.label) jd.same_mask |= 1ull << j;
                 }
+                lab[i] = jd.label;
+                pvd[i] = jd.pivot_depth;
+                fast[i] = i > 0 && jd.bn_mask == 0 && jd.deg <= 1;
                 jplan[vb + i] = jd;
             }
+            // trailing leaves that can be counted instead of walked (see "the join")
+            u32 k = 0;
+            while (k + 1 < nq) {
+                u32 t = nq - 1 - k;  // candidate new tail member; the prefix would be depths [0, t)
+                bool ok = fast[t];
+                for (u32 i = t; i < nq && ok; i++) ok = pvd[i] < t;
+                for (u32 i = t + 1; i < nq && ok; i++) ok = lab[i] != lab[t];
+                if (!ok) break;
+                k++;
+            }
+            u32 mode = k ? 1 : 0;
+            if (k == 1 && nq >= 3) {
+                u32 t = nq - 2;
+                if (fast[t] && pvd[t] < t && pvd[nq - 1] < t && lab[t] == lab[nq - 1]) { k = 2; mode = 2; }
+            }
+            jplan[vb].tail_k = k;
+            jplan[vb].tail_mode = mode;
             u64 total = count(start);
             items = total > rank ? (total - rank + world - 1) / world : 0;
         }
@@ -202,13 +232,19 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
 // ---- the join ------------------------------------------------------------------------------------------------
 //
 // Work item = a partial embedding (the first `depth` vertices of the matching order) plus a range [lo, hi)
-// of the candidate segment for the next vertex.  One THREAD runs one item as an explicit-stack DFS; a
-// candidate segment is the label group of the pivot's adjacency (JoinGraph::nbrL / gtab), so a step touches
-// only neighbours that already carry the right label.  Parallelism in the reference's own decomposition is
-// tiny (|C(order[0])| start candidates, often < 100) and subtree sizes are heavy-tailed, so every item gets
-// a step budget: a thread that exhausts it writes its continuation -- for every stack level the unexplored
-// sibling range is an independent subtree -- as new items for the next round.  Rounds are plain bounded
-// kernel launches: no spinning, no device-side queue.
+// of the candidate segment for the next vertex.  One THREAD runs one item as an explicit-stack DFS (stack in
+// shared memory, [level][thread] so accesses never bank-conflict); a candidate segment is the label group of
+// the pivot's adjacency (JoinGraph::nbrL / gtab), so a step touches only neighbours that already carry the
+// right label.  Parallelism in the reference's own decomposition is small (|C(order[0])| start candidates)
+// and subtree sizes are heavy-tailed, so every item gets a step budget: a thread that exhausts it writes its
+// continuation -- for every stack level the unexplored sibling range is an independent subtree -- as new
+// items for the next round.  Rounds are plain bounded kernel launches: no spinning, no device-side queue.
+//
+// Counting shortcut (results unchanged): when the last k vertices of the matching order are leaves of the
+// query that only constrain label (query degree 1, no backward neighbour besides the pivot, pivot in the
+// first n-k vertices) and carry pairwise different labels, the completions of an (n-k)-prefix are counted as
+// the product of the sizes of their label groups minus the members already used, instead of being walked.
+// Two trailing leaves with the SAME label are handled by |A||B| - |A n B|.
 struct JoinGraph {
     const u32 *off, *nbr, *deg;  // id-sorted CSR: edge tests (graph.h:215-236)
     const u32 *label;
@@ -219,6 +255,7 @@ struct JoinGraph {
 
 constexpr int kItemHdr = 4;  // q, depth, lo, hi
 constexpr u32 kSplit = 8;
+constexpr int kDfsThreads = 256;
 
 __device__ __forceinline__ bool has_edge(const JoinGraph &g, u32 u, u32 v) {
     // graph.h:215-236: search for the larger-degree endpoint in the smaller list
@@ -276,20 +313,28 @@ __global__ void __launch_bounds__(256) k3_init_items_kernel(JoinGraph g, u32 n_q
 }
 
 template <int MAXNQ>
-__global__ void __launch_bounds__(256) k3_dfs_kernel(JoinGraph g, const u32 *__restrict__ q_vbase,
-                                                     const JoinDepth *__restrict__ jplan, const u64 *__restrict__ limits,
-                                                     u64 *answers, const u32 *__restrict__ items_in,
-                                                     const u64 *__restrict__ n_in_ptr, u32 *items_out, u64 *out_count,
-                                                     u64 out_cap, u64 *fetch_counter, u32 budget, u32 *matches,
-                                                     u64 matches_cap, u64 *match_cursor) {
+__global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const u32 *__restrict__ q_vbase,
+                                                             const JoinDepth *__restrict__ jplan,
+                                                             const u64 *__restrict__ limits, u64 *answers,
+                                                             const u32 *__restrict__ items_in,
+                                                             const u64 *__restrict__ n_in_ptr, u32 *items_out,
+                                                             u64 *out_count, u64 out_cap, u64 *fetch_counter, u32 budget,
+                                                             u32 *matches, u64 matches_cap, u64 *match_cursor,
+                                                             u64 *step_counter) {
     constexpr u32 stride = MAXNQ + kItemHdr;
+    extern __shared__ u32 s_stack[];  // emb | cur | end, each [MAXNQ][kDfsThreads]
+    u32 *emb = s_stack + threadIdx.x;
+    u32 *cur = emb + MAXNQ * kDfsThreads;
+    u32 *end = cur + MAXNQ * kDfsThreads;
+#define EMB(t) emb[(t) * kDfsThreads]
+#define CUR(t) cur[(t) * kDfsThreads]
+#define END(t) end[(t) * kDfsThreads]
     const int lane = threadIdx.x & 31;
     const u64 n_in = *n_in_ptr;
-    u32 emb[MAXNQ], cur[MAXNQ], end[MAXNQ];
     bool have = false, exhausted = false;
-    u32 q = 0, vb = 0, nq = 0, base = 0, d = 0, steps = 0, lab0 = 0;
+    u32 q = 0, vb = 0, nq = 0, base = 0, d = 0, steps = 0, lab0 = 0, tail_at = 0, tail_mode = 0;
     u32 acc_q = 0xffffffffu;
-    u64 acc = 0;
+    u64 acc = 0, my_steps = 0;
 
     for (;;) {
         // ---- fetch: lanes without an item claim consecutive indices with one atomic per warp ----
@@ -317,12 +362,15 @@ __global__ void __launch_bounds__(256) k3_dfs_kernel(JoinGraph g, const u32 *__r
                     vb = q_vbase[q];
                     nq = q_vbase[q + 1] - vb;
                     base = it[1];
-                    if (base < nq && *(volatile u64 *)&answers[q] < limit) {
-                        for (u32 t = 0; t < base; t++) emb[t] = it[kItemHdr + t];
-                        lab0 = g.label[emb[0]];  // caller-supplied start candidates need not carry the query label
+                    if (base < nq && it[2] < it[3] && *(volatile u64 *)&answers[q] < limit) {
+                        for (u32 t = 0; t < base; t++) EMB(t) = it[kItemHdr + t];
+                        lab0 = g.label[it[kItemHdr]];  // caller-supplied start candidates need not carry the query label
+                        const JoinDepth j0 = jplan[vb];
+                        tail_mode = matches ? 0 : j0.tail_mode;
+                        tail_at = tail_mode ? nq - j0.tail_k : nq;  // depth at which the counting shortcut takes over
                         d = base;
-                        cur[d] = it[2];
-                        end[d] = it[3];
+                        CUR(d) = it[2];
+                        END(d) = it[3];
                         steps = 0;
                         have = true;
                     }
@@ -332,17 +380,25 @@ __global__ void __launch_bounds__(256) k3_dfs_kernel(JoinGraph g, const u32 *__r
         if (__ballot_sync(kFull, have) == 0) break;
         if (!have) continue;
 
-        // ---- one DFS step ----
-        if (cur[d] < end[d]) {
-            const u32 c = g.nbrL[cur[d]++];
+        // ---- one DFS step: test the next candidate of level d ----
+        my_steps++;
+        {
+            const u32 at = CUR(d);
+            const u32 c = g.nbrL[at];
+            CUR(d) = at + 1;
             const JoinDepth jd = jplan[vb + d];
-            bool ok = jd.deg <= 1 || g.deg[c] >= jd.deg;  // a neighbour has degree >= 1
-            for (u32 t = 0; ok && t < d; t++) ok = emb[t] != c;
+            bool ok = jd.deg <= 1 || g.deg[c] >= jd.deg;  // a neighbour always has degree >= 1
+            u64 sm = jd.same_mask;                          // earlier depths that can hold a vertex of this label
+            while (ok && sm) {
+                int t = __ffsll((long long)sm) - 1;
+                sm &= sm - 1;
+                ok = EMB(t) != c;
+            }
             u64 bn = jd.bn_mask;
             while (ok && bn) {
                 int t = __ffsll((long long)bn) - 1;
                 bn &= bn - 1;
-                ok = has_edge(g, c, emb[t]);
+                ok = has_edge(g, c, EMB(t));
             }
             if (ok) {
                 if (d == nq - 1) {
@@ -351,67 +407,109 @@ __global__ void __launch_bounds__(256) k3_dfs_kernel(JoinGraph g, const u32 *__r
                         u64 pos = atomicAdd((unsigned long long *)match_cursor, 1ull);
                         if (pos < matches_cap) {
                             u32 *row = matches + pos * nq;
-                            for (u32 t = 0; t < d; t++) row[jplan[vb + t].u] = emb[t];
+                            for (u32 t = 0; t < d; t++) row[jplan[vb + t].u] = EMB(t);
                             row[jd.u] = c;
                         }
                     }
                 } else {
-                    emb[d] = c;
-                    d++;
-                    const JoinDepth nd = jplan[vb + d];
-                    u32 s, e;
-                    group_range(g, emb[nd.pivot_depth], nd.label, s, e);
-                    if (d == nq - 1 && nd.bn_mask == 0 && nd.deg <= 1 && !matches) {
-                        // leaf fast path: every member of the group matches unless it is already used; the used
-                        // vertices inside the group are the embedded ones with this label adjacent to the pivot
-                        u32 used = 0;
-                        const u32 p = emb[nd.pivot_depth];
-                        for (u32 t = 0; t < d; t++)
-                            if (t != nd.pivot_depth && (t ? jplan[vb + t].label : lab0) == nd.label && has_edge(g, p, emb[t])) used++;
-                        acc += (e - s) - used;
-                        d--;
+                    EMB(d) = c;
+                    const u32 nd = d + 1;
+                    if (nd == tail_at) {
+                        // counting shortcut over the trailing leaves nd .. nq-1
+                        u64 total = 1;
+                        u32 sz[2] = {0, 0}, gs[2] = {0, 0}, ge[2] = {0, 0}, pv[2] = {0, 0};
+                        for (u32 i = nd; i < nq && total; i++) {
+                            const JoinDepth ld = jplan[vb + i];
+                            const u32 p = EMB(ld.pivot_depth);
+                            u32 s, e;
+                            group_range(g, p, ld.label, s, e);
+                            u32 used = 0;  // prefix vertices that sit in this group
+                            u64 m = ld.same_mask & ((1ull << nd) - 1);
+                            while (m) {
+                                int t = __ffsll((long long)m) - 1;
+                                m &= m - 1;
+                                if ((u32)t != ld.pivot_depth && (t != 0 || lab0 == ld.label) && has_edge(g, p, EMB(t))) used++;
+                            }
+                            const u32 n_free = (e - s) - used;
+                            if (tail_mode == 2) {
+                                sz[i - nd] = n_free; gs[i - nd] = s; ge[i - nd] = e; pv[i - nd] = p;
+                            } else {
+                                total *= n_free;
+                            }
+                        }
+                        if (tail_mode == 2) {
+                            // both leaves carry the same label: ordered pairs of distinct vertices
+                            u64 inter;
+                            if (pv[0] == pv[1]) {
+                                inter = sz[0];
+                            } else {
+                                inter = 0;  // |G(p0) n G(p1)| without the used members: merge two ascending id lists
+                                u32 x = gs[0], y = gs[1];
+                                while (x < ge[0] && y < ge[1]) {
+                                    const u32 vx = g.nbrL[x], vy = g.nbrL[y];
+                                    if (vx == vy) {
+                                        bool is_used = false;
+                                        for (u32 t = 0; t < nd; t++) is_used = is_used || EMB(t) == vx;
+                                        inter += is_used ? 0 : 1;
+                                        x++;
+                                        y++;
+                                    } else if (vx < vy) {
+                                        x++;
+                                    } else {
+                                        y++;
+                                    }
+                                }
+                            }
+                            total = (u64)sz[0] * sz[1] - inter;
+                        }
+                        acc += total;
                     } else {
-                        cur[d] = s;
-                        end[d] = e;
+                        const JoinDepth ndj = jplan[vb + nd];
+                        u32 s, e;
+                        group_range(g, EMB(ndj.pivot_depth), ndj.label, s, e);
+                        d = nd;
+                        CUR(d) = s;
+                        END(d) = e;
                     }
                 }
             }
-        } else if (d == base) {
-            have = false;
-        } else {
-            d--;
+        }
+        // ---- pop exhausted levels ----
+        while (have && CUR(d) >= END(d)) {
+            if (d == base) have = false; else d--;
         }
 
         // ---- budget: hand the unexplored sibling ranges of every stack level to the next round ----
         if (have && ++steps >= budget) {
             u32 pieces = 0;
-            for (u32 l = base; l <= d; l++) pieces += min(end[l] - cur[l], kSplit);
-            if (pieces == 0) {
-                have = false;
+            for (u32 l = base; l <= d; l++) pieces += min(END(l) - CUR(l), kSplit);
+            u64 o = atomicAdd((unsigned long long *)out_count, (unsigned long long)pieces);
+            if (o + pieces > out_cap) {
+                atomicAdd((unsigned long long *)out_count, (unsigned long long)(0ull - pieces));  // undo; keep running
+                steps = 0;
             } else {
-                u64 o = atomicAdd((unsigned long long *)out_count, (unsigned long long)pieces);
-                if (o + pieces > out_cap) {
-                    atomicAdd((unsigned long long *)out_count, (unsigned long long)(0ull - pieces));  // undo; keep running
-                    steps = 0;
-                } else {
-                    for (u32 l = base; l <= d; l++) {
-                        u32 len = end[l] - cur[l], np = min(len, kSplit);
-                        for (u32 k = 0; k < np; k++) {
-                            u32 *it = items_out + o * stride;
-                            it[0] = q;
-                            it[1] = l;
-                            it[2] = cur[l] + (u32)((u64)len * k / np);
-                            it[3] = cur[l] + (u32)((u64)len * (k + 1) / np);
-                            for (u32 t = 0; t < l; t++) it[kItemHdr + t] = emb[t];
-                            o++;
-                        }
+                for (u32 l = base; l <= d; l++) {
+                    u32 len = END(l) - CUR(l), np = min(len, kSplit);
+                    for (u32 k = 0; k < np; k++) {
+                        u32 *it = items_out + o * stride;
+                        it[0] = q;
+                        it[1] = l;
+                        it[2] = CUR(l) + (u32)((u64)len * k / np);
+                        it[3] = CUR(l) + (u32)((u64)len * (k + 1) / np);
+                        for (u32 t = 0; t < l; t++) it[kItemHdr + t] = EMB(t);
+                        o++;
                     }
-                    have = false;
                 }
+                have = false;
             }
         }
     }
     if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
+    for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(kFull, my_steps, o);
+    if (lane == 0 && my_steps) atomicAdd((unsigned long long *)step_counter, (unsigned long long)my_steps);
+#undef EMB
+#undef CUR
+#undef END
 }
 
 }  // namespace
@@ -474,18 +572,20 @@ cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase,
 
 cudaError_t k3_dfs_round(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const u64 *limits,
                          u64 *answers, const u32 *items_in, const u64 *n_in, u32 *items_out, u64 *out_count, u64 out_cap,
-                         u64 *fetch_counter, u32 budget, u32 *matches, u64 matches_cap, u64 *match_cursor, int sm_count,
-                         cudaStream_t s) {
+                         u64 *fetch_counter, u32 budget, u32 *matches, u64 matches_cap, u64 *match_cursor,
+                         u64 *step_counter, int sm_count, cudaStream_t s) {
     JoinGraph g{jv.off, jv.nbr, jv.deg, jv.label, jv.nbrL, jv.gtab, jv.V, jv.nl};
 #define LAUNCH(M)                                                                                                     \
     static int per_sm_##M = 0;                                                                                        \
+    const size_t smem_##M = (size_t)3 * M * kDfsThreads * sizeof(u32);                                                \
     if (!per_sm_##M) {                                                                                                \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_##M, k3_dfs_kernel<M>, 256, 0) != cudaSuccess ||    \
-            per_sm_##M < 1)                                                                                           \
-            per_sm_##M = 4;                                                                                           \
+        cudaFuncSetAttribute(k3_dfs_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_##M);           \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_##M, k3_dfs_kernel<M>, kDfsThreads, smem_##M) !=    \
+                cudaSuccess || per_sm_##M < 1)                                                                        \
+            per_sm_##M = 1;                                                                                           \
     }                                                                                                                 \
-    k3_dfs_kernel<M><<<sm_count * per_sm_##M, 256, 0, s>>>(g, q_vbase, jplan, limits, answers, items_in, n_in, items_out, out_count, \
-                                            out_cap, fetch_counter, budget, matches, matches_cap, match_cursor)
+    k3_dfs_kernel<M><<<sm_count * per_sm_##M, kDfsThreads, smem_##M, s>>>(g, q_vbase, jplan, limits, answers, items_in, n_in, items_out, out_count, \
+                                            out_cap, fetch_counter, budget, matches, matches_cap, match_cursor, step_counter)
     if (max_nq <= 8) { LAUNCH(8); }
     else if (max_nq <= 16) { LAUNCH(16); }
     else if (max_nq <= 32) { LAUNCH(32); }

@@ -257,3 +257,46 @@ def test_host_cli_quickstart(tmp_path):
     out = subprocess.check_output([main, "-f", d, "-d", gold["data_path"], "-q", gold["query_paths_files"][0],
                                    "-m", "online", "-n", "1000"]).decode()
     assert "Answer Number: 1000 " in out
+
+
+def test_two_shards_in_one_process_match_single_gpu():
+    """The multi-GPU data flow (shard tables -> export lists -> union -> split join -> sum) exercised with two
+    contexts on one GPU, no NCCL: results must equal the unsharded run."""
+    import torch
+    gold = load_case("powerlaw500_e3")
+    queries = [graph_io.read_graph(qf) for qf in gold["query_paths_files"]][:2] + \
+              [graph_io.read_graph(qf) for qf in load_case("powerlaw500_e3")["query_paths_files"]][3:]
+    want = [gold["queries"][i]["answer"] for i in (0, 1, 3)]
+    limits = [gold["queries"][i]["limit"] or gpe.LIMIT_MAX for i in (0, 1, 3)]
+    world = 2
+    ctxs = []
+    for r in range(world):
+        ctx, g, vde, sorted_nodes, membership, n_rows, rows_pp = _ctx_for(gold)
+        sel = np.array([1 if i % world == r else 0 for i in range(gold["p"])], dtype=np.uint8)
+        ctx.build_table(sel)
+        ctx.batch_upload(queries, limits)
+        ctx.batch_filter()
+        ctxs.append(ctx)
+    infos = [c.batch_cand_info() for c in ctxs]
+    n_slots = infos[0][0]
+    stride = max(max(t for _, t in infos), 1)
+    all_counts = torch.zeros(world, n_slots, dtype=torch.int32, device="cuda")
+    all_cand = torch.zeros(world, stride, dtype=torch.int32, device="cuda")
+    for r, c in enumerate(ctxs):
+        c.batch_cand_export(all_counts[r].data_ptr(), all_cand[r].data_ptr())
+    torch.cuda.synchronize()
+    raw = np.zeros(len(queries), dtype=np.uint64)
+    for r, c in enumerate(ctxs):
+        c.batch_cand_merge(world, all_counts.data_ptr(), all_cand.data_ptr(), stride)
+        off, cand = c.batch_get_candidates()
+        slot = 0
+        for qi in (0, 1, 3):
+            for cset in gold["queries"][qi]["candidates"]:
+                assert cand[int(off[slot]):int(off[slot + 1])].tolist() == cset
+                slot += 1
+        c.batch_join(r, world)
+        raw += c.batch_download()
+    got = [ctxs[0].clamp(int(x), l) for x, l in zip(raw, limits)]
+    assert got == want
+    for c in ctxs:
+        c.close()
