@@ -265,82 +265,53 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
     return GPE_OK;
 }
 
-constexpr u64 kJoinItemCap = 1ull << 22;  // work items per round buffer
-constexpr u32 kJoinBudget = 1024;         // DFS steps before a thread exports its continuation
-
-u32 join_budget() {
-    static u32 b = 0;
-    if (!b) {
-        const char *e = getenv("GPE_JOIN_BUDGET");  // tuning knob for experiments
-        b = e && atoi(e) > 0 ? (u32)atoi(e) : kJoinBudget;
-    }
-    return b;
-}
+constexpr u64 kJoinExportCap = 1ull << 22;  // room for exported work items on top of the start candidates
 
 int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     StageTimer tm(c, &c->stats.last_join_ms, kStageJoin);
     const u32 nq = c->b_nq;
-    // answers[0..nq) | fetch counter | round counters: n_in(0), n_out(1) alternate
     u64 *answers = c->d_answers.as<u64>();
     GPE_CUDA(c, cudaMemsetAsync(c->d_answers.p, 0, ((size_t)nq + 8) * sizeof(u64), c->stream));
     GPE_CUDA(c, cudaMemsetAsync(c->d_match_cursor.p, 0, 2 * sizeof(u64), c->stream));
+    GPE_CUDA(c, c->d_jq.reserve(sizeof(JoinQueue)));
     GPE_CUDA(c, k3_order(nq, c->V, c->d_q_vbase.as<u32>(), c->d_q_ebase.as<u32>(), c->d_q_offsets.as<u32>(),
                          c->d_q_nbrs.as<u32>(), c->d_q_labels.as<u32>(), c->d_cand_off.as<u64>(), c->d_order.as<u32>(),
                          c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_item_base.as<u64>(), rank, world,
                          c->stream));
-    JoinView jv{c->d_off.as<u32>(), c->d_nbr.as<u32>(), c->d_deg.as<u32>(), c->d_label.as<u32>(), c->d_nbrL.as<u32>(),
-                c->d_gtab.as<u32>(), c->V, c->n_labels};
+    JoinView jv{c->d_label.as<u32>(), c->d_nbrL.as<u32>(), c->d_gtab.as<u32>(), c->V, c->n_labels};
     const u32 stride = k3_item_stride(c->b_max_nq);
-    // round 0 holds one item per start candidate of this shard; b_n_cand bounds that from above
-    const u64 cap = std::max<u64>(kJoinItemCap, c->b_n_cand + 1);
-    GPE_CUDA(c, c->d_items[0].reserve(cap * stride * sizeof(u32)));
-    GPE_CUDA(c, c->d_items[1].reserve(cap * stride * sizeof(u32)));
-    u64 *fetch = answers + nq + 1, *cnt0 = answers + nq + 2, *cnt1 = answers + nq + 3, *step_ctr = answers + nq + 4;
-    const bool trace = getenv("GPE_TRACE_JOIN") != nullptr;
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
-    if (trace) { cudaEventCreate(&t0); cudaEventCreate(&t1); }
-    GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
-                              c->d_cand.as<u32>(), c->d_item_base.as<u64>(), rank, world, c->d_items[0].as<u32>(), stride,
-                              answers, cnt0, c->sm_count, c->stream));
-    c->stats.kernel_launches += 2;
-    GPE_CUDA(c, c->h_pin2.reserve(16 * sizeof(u64)));
-    u64 *pin = c->h_pin2.as<u64>();
-    int cur = 0;
-    u64 rounds = 0, items_total = 0;
-    for (;; rounds++) {
-        u64 *n_in = cur == 0 ? cnt0 : cnt1, *n_out = cur == 0 ? cnt1 : cnt0;
-        GPE_CUDA(c, cudaMemsetAsync(n_out, 0, sizeof(u64), c->stream));
-        GPE_CUDA(c, cudaMemsetAsync(fetch, 0, sizeof(u64), c->stream));
-        if (trace) cudaEventRecord(t0, c->stream);
-        GPE_CUDA(c, k3_dfs_round(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_limits.as<u64>(),
-                                 answers, c->d_items[cur].as<u32>(), n_in, c->d_items[cur ^ 1].as<u32>(), n_out, cap, fetch,
-                                 join_budget(), d_matches, matches_cap, c->d_match_cursor.as<u64>(), step_ctr, c->sm_count,
-                                 c->stream));
-        if (trace) cudaEventRecord(t1, c->stream);
-        c->stats.kernel_launches++;
-        GPE_CUDA(c, cudaMemcpyAsync(pin, n_in, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-        GPE_CUDA(c, cudaMemcpyAsync(pin + 1, n_out, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-        GPE_CUDA(c, cudaMemcpyAsync(pin + 2, step_ctr, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-        GPE_CUDA(c, cudaStreamSynchronize(c->stream));
-        c->stats.d2h_bytes += 3 * sizeof(u64);
-        if (trace) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, t0, t1);
-            fprintf(stderr, "[gpe join] round %llu: items_in=%llu items_out=%llu steps_so_far=%llu %.3f ms\n",
-                    (unsigned long long)rounds, (unsigned long long)pin[0], (unsigned long long)pin[1],
-                    (unsigned long long)pin[2], ms);
-        }
-        items_total += pin[0];
-        if (pin[1] == 0) { rounds++; break; }
-        if (rounds > 100000) return c->fail(GPE_ERR_CUDA, "join did not converge");
-        cur ^= 1;
+    // tickets [0, n_init) hold one item per start candidate of this shard (b_n_cand bounds that from above),
+    // the rest of the buffer receives exported subtrees
+    const u64 cap = c->b_n_cand + kJoinExportCap;
+    GPE_CUDA(c, c->d_items.reserve(cap * stride * sizeof(u32)));
+    if (c->d_ready.cap < cap * sizeof(u32) || c->join_epoch == 0xffffffffu) {
+        GPE_CUDA(c, c->d_ready.reserve(cap * sizeof(u32)));
+        GPE_CUDA(c, cudaMemsetAsync(c->d_ready.p, 0, c->d_ready.cap, c->stream));
+        c->join_epoch = 0;
     }
-    c->stats.join_launches += 2 + rounds;
-    c->stats.join_items = items_total;
-    c->stats.join_rounds = rounds;
-    c->stats.join_steps = pin[2];
-    if (trace) { cudaEventDestroy(t0); cudaEventDestroy(t1); }
+    const u32 epoch = ++c->join_epoch;
+    JoinQueue *jq = c->d_jq.as<JoinQueue>();
+    GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
+                              c->d_cand.as<u32>(), c->d_item_base.as<u64>(), rank, world, c->d_items.as<u32>(), stride,
+                              answers, jq, c->sm_count, c->stream));
+    GPE_CUDA(c, k3_dfs(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_limits.as<u64>(), answers,
+                       c->d_items.as<u32>(), cap, c->d_ready.as<u32>(), epoch, jq, d_matches, matches_cap,
+                       c->d_match_cursor.as<u64>(), c->sm_count, c->stream));
+    c->stats.kernel_launches += 3;
+    c->stats.join_launches += 3;
     c->b_joined = true;
+    return GPE_OK;
+}
+
+// queue counters of the last join (items produced, DFS steps); needs the stream to be idle
+int read_join_stats(gpe_ctx *c) {
+    JoinQueue h;
+    GPE_CUDA(c, cudaMemcpyAsync(&h, c->d_jq.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stats.join_items = h.tail;
+    c->stats.join_exports = h.exports;
+    c->stats.join_donations = h.donations;
+    c->stats.join_steps = h.steps;
     return GPE_OK;
 }
 
@@ -414,7 +385,7 @@ void gpe_destroy(gpe_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrL, &c->d_gtab, &c->d_items[0], &c->d_items[1], &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
+    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrL, &c->d_gtab, &c->d_items, &c->d_ready, &c->d_jq, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
                       &c->d_offr, &c->d_ebase, &c->d_start_rows, &c->d_scan_tmp, &c->d_tiles, &c->d_vids, &c->d_sum_u32, &c->d_sum_f64,
                       &c->d_bucket, &c->d_cursor, &c->d_qblocks, &c->d_qb_t0, &c->d_qb_prefix, &c->d_worklist,
                       &c->d_counters, &c->d_bitmap, &c->d_survivors, &c->d_chunk_cnt, &c->d_chunk_off, &c->d_cand,
@@ -515,7 +486,7 @@ int gpe_set_graph(gpe_ctx *c, uint32_t V, const uint32_t *offsets, const uint32_
         if (gt_entries * sizeof(u32) > free_b / 4)
             return c->fail(GPE_ERR_UNSUPPORTED, "label directory of %llu entries (V x (labels+1)) does not fit; "
                                                 "a sparse directory is not built yet", (unsigned long long)gt_entries);
-        std::vector<u32> nbrL(std::max<size_t>(n_adj, 1)), gtab(std::max<u64>(gt_entries, 1)), cnt(nl + 1);
+        std::vector<u32> nbrL(std::max<size_t>(n_adj, 1) * 2), gtab(std::max<u64>(gt_entries, 1)), cnt(nl + 1);
         for (u32 v = 0; v < V; v++) {
             std::fill(cnt.begin(), cnt.end(), 0u);
             for (u32 j = offsets[v]; j < offsets[v + 1]; j++) cnt[labels[nbrs[j]]]++;
@@ -523,7 +494,11 @@ int gpe_set_graph(gpe_ctx *c, uint32_t V, const uint32_t *offsets, const uint32_
             u32 *row = &gtab[(u64)v * (nl + 1)];
             for (u32 l = 0; l < nl; l++) { row[l] = run; run += cnt[l]; cnt[l] = row[l]; }
             row[nl] = run;
-            for (u32 j = offsets[v]; j < offsets[v + 1]; j++) nbrL[cnt[labels[nbrs[j]]]++] = nbrs[j];  // stable: ids stay ascending
+            for (u32 j = offsets[v]; j < offsets[v + 1]; j++) {  // stable: ids stay ascending inside a group
+                const u32 w = nbrs[j], at = cnt[labels[w]]++;
+                nbrL[2 * (size_t)at] = w;
+                nbrL[2 * (size_t)at + 1] = deg[w];
+            }
         }
         GPE_CUDA(c, c->d_nbrL.reserve(nbrL.size() * sizeof(u32)));
         GPE_CUDA(c, c->d_gtab.reserve(gtab.size() * sizeof(u32)));
@@ -823,6 +798,7 @@ int gpe_refine(gpe_ctx *c, uint32_t nq, const uint32_t *q_offsets, const uint32_
         GPE_CUDA(c, c->d_rank.reserve(16));
     }
     c->b_slots = nq;
+    c->b_n_cand = total;
     GPE_CUDA(c, c->d_cand.reserve(std::max<u64>(total, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_cand_off.reserve(((size_t)nq + 1) * sizeof(u64)));
     if (total) GPE_CUDA(c, cudaMemcpyAsync(c->d_cand.p, cand, total * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
@@ -845,6 +821,7 @@ int gpe_refine(gpe_ctx *c, uint32_t nq, const uint32_t *q_offsets, const uint32_
         if (n) GPE_CUDA(c, cudaMemcpy(matches, d_matches, n * nq * sizeof(u32), cudaMemcpyDeviceToHost));
     }
     if (n_matches) *n_matches = gpe_clamp_answer(raw, limit);
+    if ((rc = read_join_stats(c))) return rc;
     c->b_filtered = false;
     return GPE_OK;
 }
@@ -895,11 +872,19 @@ int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) {
     if (!c || !raw_counts) return GPE_ERR_INVALID;
     if (!c->b_joined) return c->fail(GPE_ERR_INVALID, "gpe_batch_join first");
     GPE_CUDA(c, cudaSetDevice(c->device));
-    GPE_CUDA(c, c->h_pin2.reserve(std::max<size_t>(c->b_nq, 16) * sizeof(u64)));
-    GPE_CUDA(c, cudaMemcpyAsync(c->h_pin2.p, c->d_answers.p, (size_t)c->b_nq * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, c->h_pin2.reserve((std::max<size_t>(c->b_nq, 16) + 16) * sizeof(u64)));
+    u64 *pin = c->h_pin2.as<u64>();
+    GPE_CUDA(c, cudaMemcpyAsync(pin, c->d_answers.p, (size_t)c->b_nq * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(pin + c->b_nq, c->d_jq.p, sizeof(JoinQueue), cudaMemcpyDeviceToHost, c->stream));
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
-    memcpy(raw_counts, c->h_pin2.p, (size_t)c->b_nq * sizeof(u64));
-    c->stats.d2h_bytes += (size_t)c->b_nq * sizeof(u64);
+    memcpy(raw_counts, pin, (size_t)c->b_nq * sizeof(u64));
+    JoinQueue jq;
+    memcpy(&jq, pin + c->b_nq, sizeof jq);
+    c->stats.join_items = jq.tail;
+    c->stats.join_exports = jq.exports;
+    c->stats.join_donations = jq.donations;
+    c->stats.join_steps = jq.steps;
+    c->stats.d2h_bytes += (size_t)c->b_nq * sizeof(u64) + sizeof(JoinQueue);
     return GPE_OK;
 }
 

@@ -111,16 +111,39 @@ struct QBlockHost {  // layout-agnostic staging on the host
     u32 t0, t1;  // tile range from the directory
 };
 
-// Per-depth join plan of one query vertex slot (filled by the order kernel).
-struct JoinDepth {
-    u32 u;          // query vertex matched at this depth (order[d])
+// Per-depth join plan of one query (filled by the order kernel), in EXECUTION order: depth 0 is the
+// reference's start vertex (generateGQLQueryPlan, custom.h:670-722); the remaining vertices are ordered by the
+// same greedy rule, except that query leaves are moved to the end ("tail") where their completions are counted
+// instead of walked.  The number of embeddings does not depend on the order below the start vertex.
+struct alignas(16) JoinDepth {
+    u32 u;            // query vertex matched at this depth
     u32 label;
     u32 deg;
-    u32 pivot_depth;  // depth at which pivot[d] was matched
+    u32 pivot_depth;  // depth at which the pivot (first earlier query neighbour) was matched
     u64 bn_mask;      // depths of the other backward neighbours (generateBN, custom.h:724-755)
-    u64 same_mask;    // earlier depths whose vertex may equal a candidate of this depth (same label)
-    u32 tail_k;       // [depth 0 only] number of trailing leaves counted instead of walked
-    u32 tail_mode;    // [depth 0 only] 0 none, 1 product of distinct-label leaves, 2 two leaves sharing a label
+    u64 same_mask;    // earlier depths whose vertex may equal a candidate of this depth (same label; depth 0 always)
+    u64 tail_mask;    // [tail depths] prefix depths that may sit in this leaf's label group and need an edge test
+    u32 tail_k;       // [depth 0] number of tail depths;  [tail depths] operation, see kTail*
+    u32 sure_used;    // [tail depths] prefix vertices known to sit in the group (same label, query-adjacent to the pivot)
+};
+constexpr u32 kTailMul = 0;    // multiply by the free members of the leaf's label group
+constexpr u32 kTailFall = 1;   // same pivot and label as the previous tail depth: multiply by (previous factor - 1)
+constexpr u32 kTailPairA = 2;  // two same-label leaves on different pivots: |A||B| - |A n B| (this depth and the next)
+constexpr u32 kTailPairB = 3;
+
+// Work queue of the join (device memory): tickets [0, n_init) are the start-candidate items, later tickets are
+// subtrees exported on demand by busy threads.
+struct alignas(16) JoinQueue {
+    unsigned long long head;     // tickets claimed by consumers
+    unsigned long long tail;     // items produced
+    long long pending;           // items published and not yet retired; 0 <=> the join is complete
+    unsigned long long idle;     // warps without any busy lane
+    unsigned long long n_init;
+    unsigned long long steps;    // DFS steps, summed over threads
+    unsigned long long exports;  // hand-overs between warps (through the queue)
+    unsigned long long donations;  // hand-overs inside a warp (through shared memory)
+    unsigned long long full;     // set once the item buffer overflowed (exports stop; result unaffected)
+    unsigned long long pad[3];
 };
 
 }  // namespace gpe
@@ -141,9 +164,9 @@ struct gpe_ctx {
     u32 V = 0, n_adj = 0, n_labels = 0, max_degree = 0;
     gpe::DevBuf d_off, d_nbr, d_label, d_deg, d_rank, d_sorted, d_member, d_vde;
     gpe::DevBuf d_nbrL, d_gtab;  // label-grouped adjacency + group directory (join)
-    gpe::DevBuf d_items[2];     // join work items, double-buffered between rounds
+    gpe::DevBuf d_items, d_ready, d_jq;  // join work items, their publication flags, the queue header
+    u32 join_epoch = 0;
     u32 b_max_nq = 0;
-    u64 join_rounds = 0, join_items_total = 0;
     u32 e = 0;
     bool have_graph = false, have_emb = false, have_enum = false, have_table = false;
 
@@ -246,16 +269,16 @@ cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebas
                      JoinDepth *jplan, u64 *item_base, u32 rank, u32 world, cudaStream_t s);
 // label-grouped adjacency for the join (built on the host in gpe_set_graph)
 struct JoinView {
-    const u32 *off, *nbr, *deg, *label, *nbrL, *gtab;
+    const u32 *label, *nbrL /* (neighbour, degree) pairs */, *gtab;
     u32 V, nl;
 };
 u32 k3_item_stride(u32 max_nq);
 cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
                           const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world, u32 *items,
-                          u32 stride, u64 *answers, u64 *n_items_out, int sm_count, cudaStream_t s);
-cudaError_t k3_dfs_round(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const u64 *limits,
-                         u64 *answers, const u32 *items_in, const u64 *n_in, u32 *items_out, u64 *out_count, u64 out_cap,
-                         u64 *fetch_counter, u32 budget, u32 *matches, u64 matches_cap, u64 *match_cursor,
-                         u64 *step_counter, int sm_count, cudaStream_t s);
+                          u32 stride, u64 *answers, JoinQueue *jq, int sm_count, cudaStream_t s);
+// one persistent launch: every thread runs work items (explicit-stack DFS) and exports subtrees when others starve
+cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const u64 *limits,
+                   u64 *answers, u32 *items, u64 item_cap, u32 *ready, u32 epoch, JoinQueue *jq, u32 *matches,
+                   u64 matches_cap, u64 *match_cursor, int sm_count, cudaStream_t s);
 
 }  // namespace gpe

@@ -131,12 +131,14 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
         const u32 vb = q_vbase[q], nq = q_vbase[q + 1] - vb;
         const u32 *off = q_offsets + vb + q;  // nq + 1 local offsets
         const u32 *nbr = q_nbrs + q_ebase[q];
+        const u32 *qlab = q_labels + vb;
         const u64 *co = cand_off + vb;
         u32 *ord = order + vb, *piv = pivot + vb;
         auto count = [&](u32 u) { return (u32)(co[u + 1] - co[u]); };
         auto qdeg = [&](u32 u) { return off[u + 1] - off[u]; };
         u64 items = 0;
         if (nq > 0) {
+            // ---- the reference's plan (reported through gpe_refine / gpe_batch_get_plan) ----
             u32 start = 0;  // selectGQLStartVertex, custom.h:635-654
             for (u32 i = 1; i < nq; i++) {
                 if (count(i) < count(start)) start = i;
@@ -159,31 +161,96 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 }
                 mark(next);
                 ord[i] = next;
+                u32 pv = 0xffffffffu;
+                for (u32 j = 0; j < i; j++)
+                    if (q_edge(off, nbr, next, ord[j])) { pv = ord[j]; break; }
+                piv[i] = pv;
             }
-            u32 depth_of[kMaxNQ];
-            for (u32 i = 0; i < nq; i++) depth_of[ord[i]] = i;
-            u32 pvd[kMaxNQ], lab[kMaxNQ];
-            bool fast[kMaxNQ];
+
+            // ---- the execution plan: same start vertex, query leaves counted at the end ----
+            u64 tail_set = 0;
+            u32 tail_list[kMaxNQ], n_tail = 0;
+            for (u32 u = 0; u < nq && nq >= 3 && n_tail + 2 < nq; u++) {
+                if (u == start || qdeg(u) != 1) continue;
+                const u32 pv = nbr[off[u]];
+                u32 r = 0, p0 = 0;
+                bool mixed = false;
+                for (u32 k = 0; k < n_tail; k++) {
+                    const u32 t = tail_list[k];
+                    if (qlab[t] != qlab[u]) continue;
+                    const u32 pt = nbr[off[t]];
+                    if (r == 0) p0 = pt; else if (pt != p0) mixed = true;
+                    r++;
+                }
+                // a label may appear on one tail leaf, on several leaves of ONE pivot, or on two leaves of two pivots
+                if (r == 0 || (!mixed && pv == p0) || (r == 1 && pv != p0)) {
+                    tail_list[n_tail++] = u;
+                    tail_set |= 1ull << u;
+                }
+            }
+            const u32 n_walk = nq - n_tail;
+            u32 xo[kMaxNQ], depth_of[kMaxNQ], lab[kMaxNQ], top[kMaxNQ];
+            xo[0] = start;
+            visited = 0;
+            adjacent = 0;
+            mark(start);
+            for (u32 i = 1; i < n_walk; i++) {
+                u32 next = 0, best = V + 1;
+                for (u32 u = 0; u < nq; u++) {
+                    if ((visited >> u & 1) || !(adjacent >> u & 1) || (tail_set >> u & 1)) continue;
+                    if (count(u) < best) { best = count(u); next = u; }
+                    else if (count(u) == best && qdeg(u) > qdeg(next)) next = u;
+                }
+                mark(next);
+                xo[i] = next;
+            }
+            {   // tail depths, grouped by label
+                u64 placed = 0;
+                u32 at = n_walk;
+                for (u32 k = 0; k < n_tail; k++) {
+                    const u32 t = tail_list[k];
+                    if (placed >> t & 1) continue;
+                    placed |= 1ull << t;
+                    const u32 first_at = at;
+                    xo[at] = t;
+                    top[at++] = kTailMul;
+                    for (u32 k2 = k + 1; k2 < n_tail; k2++) {
+                        const u32 t2 = tail_list[k2];
+                        if ((placed >> t2 & 1) || qlab[t2] != qlab[t]) continue;
+                        placed |= 1ull << t2;
+                        xo[at] = t2;
+                        if (nbr[off[t2]] == nbr[off[t]]) {
+                            top[at++] = kTailFall;
+                        } else {
+                            top[first_at] = kTailPairA;
+                            top[at++] = kTailPairB;
+                        }
+                    }
+                }
+            }
+            for (u32 i = 0; i < nq; i++) { depth_of[xo[i]] = i; lab[i] = qlab[xo[i]]; }
             for (u32 i = 0; i < nq; i++) {
-                u32 u = ord[i];
+                const u32 u = xo[i];
                 JoinDepth jd;
                 jd.u = u;
-                jd.label = q_labels[vb + u];
+                jd.label = lab[i];
                 jd.deg = qdeg(u);
                 jd.pivot_depth = 0;
                 jd.bn_mask = 0;
                 jd.same_mask = 0;
+                jd.tail_mask = 0;
                 jd.tail_k = 0;
-                jd.tail_mode = 0;
+                jd.sure_used = 0;
                 if (i > 0) {
-                    u32 pv = 0xffffffffu;
-                    for (u32 j = 0; j < i; j++)
-                        if (q_edge(off, nbr, u, ord[j])) { pv = ord[j]; break; }
-                    piv[i] = pv;
-                    jd.pivot_depth = pv == 0xffffffffu ? 0 : depth_of[pv];
+                    u32 pd = 0xffffffffu;  // pivot: the earliest-matched query neighbour
                     for (u32 j = off[u]; j < off[u + 1]; j++) {
-                        u32 w = nbr[j];
-                        if (depth_of[w] < i && w != pv) jd.bn_mask |= 1ull << depth_of[w];
+                        const u32 dw = depth_of[nbr[j]];
+                        if (dw < i && dw < pd) pd = dw;
+                    }
+                    jd.pivot_depth = pd == 0xffffffffu ? 0 : pd;
+                    for (u32 j = off[u]; j < off[u + 1]; j++) {
+                        const u32 dw = depth_of[nbr[j]];
+                        if (dw < i && dw != jd.pivot_depth) jd.bn_mask |= 1ull << dw;
                     }
                     // depths whose vertex can equal a candidate of this depth: same query label; depth 0 always,
                     // because caller-supplied start candidates (gpe_refine) are not label-checked
@@ -191,28 +258,19 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                     for (u32 j = 1; j < i; j++)
                         if (lab[j] == jd.label) jd.same_mask |= 1ull << j;
                 }
-                lab[i] = jd.label;
-                pvd[i] = jd.pivot_depth;
-                fast[i] = i > 0 && jd.bn_mask == 0 && jd.deg <= 1;
+                if (i >= n_walk) {
+                    jd.tail_k = top[i];
+                    const u32 pvu = xo[jd.pivot_depth];
+                    for (u32 t = 0; t < n_walk; t++) {
+                        if (t == jd.pivot_depth) continue;
+                        if (t == 0) { jd.tail_mask |= 1ull; continue; }  // its data label is only known at run time
+                        if (lab[t] != jd.label) continue;
+                        if (q_edge(off, nbr, xo[t], pvu)) jd.sure_used++; else jd.tail_mask |= 1ull << t;
+                    }
+                }
                 jplan[vb + i] = jd;
             }
-            // trailing leaves that can be counted instead of walked (see "the join")
-            u32 k = 0;
-            while (k + 1 < nq) {
-                u32 t = nq - 1 - k;  // candidate new tail member; the prefix would be depths [0, t)
-                bool ok = fast[t];
-                for (u32 i = t; i < nq && ok; i++) ok = pvd[i] < t;
-                for (u32 i = t + 1; i < nq && ok; i++) ok = lab[i] != lab[t];
-                if (!ok) break;
-                k++;
-            }
-            u32 mode = k ? 1 : 0;
-            if (k == 1 && nq >= 3) {
-                u32 t = nq - 2;
-                if (fast[t] && pvd[t] < t && pvd[nq - 1] < t && lab[t] == lab[nq - 1]) { k = 2; mode = 2; }
-            }
-            jplan[vb].tail_k = k;
-            jplan[vb].tail_mode = mode;
+            jplan[vb].tail_k = n_tail;
             u64 total = count(start);
             items = total > rank ? (total - rank + world - 1) / world : 0;
         }
@@ -231,46 +289,42 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
 
 // ---- the join ------------------------------------------------------------------------------------------------
 //
-// Work item = a partial embedding (the first `depth` vertices of the matching order) plus a range [lo, hi)
+// Work item = a partial embedding (the first `depth` vertices of the execution order) plus a range [lo, hi)
 // of the candidate segment for the next vertex.  One THREAD runs one item as an explicit-stack DFS (stack in
 // shared memory, [level][thread] so accesses never bank-conflict); a candidate segment is the label group of
 // the pivot's adjacency (JoinGraph::nbrL / gtab), so a step touches only neighbours that already carry the
-// right label.  Parallelism in the reference's own decomposition is small (|C(order[0])| start candidates)
-// and subtree sizes are heavy-tailed, so every item gets a step budget: a thread that exhausts it writes its
-// continuation -- for every stack level the unexplored sibling range is an independent subtree -- as new
-// items for the next round.  Rounds are plain bounded kernel launches: no spinning, no device-side queue.
+// right label.  Label groups are short (degree / labels), which is why a warp per segment would idle.
 //
-// Counting shortcut (results unchanged): when the last k vertices of the matching order are leaves of the
-// query that only constrain label (query degree 1, no backward neighbour besides the pivot, pivot in the
-// first n-k vertices) and carry pairwise different labels, the completions of an (n-k)-prefix are counted as
-// the product of the sizes of their label groups minus the members already used, instead of being walked.
-// Two trailing leaves with the SAME label are handled by |A||B| - |A n B|.
+// One persistent launch, two levels of load balancing (subtree sizes are heavy-tailed):
+//   * inside a warp: a lane without work takes the upper half of the shallowest unexplored sibling range of
+//     a busy lane, straight out of the donor's shared-memory stack column (no global traffic);
+//   * between warps: items live in a linear buffer addressed by ticket.  Tickets [0, n_init) are the start
+//     candidates.  Lanes claim tickets while published items are available; a warp without any busy lane
+//     registers as idle and polls the queue header with back-off; busy warps look at the header every
+//     kExportEvery iterations and, when idle warps outnumber the published items, one lane hands over the
+//     unexplored siblings of its shallowest level as new items.  JoinQueue::pending counts published items
+//     whose work has not been retired; a warp retires what it claimed whenever all its lanes run dry, so
+//     pending == 0 means the join is complete.  Exporting is only load balancing: if the buffer fills up,
+//     threads simply keep their work.
+//
+// Counting shortcut (results unchanged): the tail depths are query leaves whose only neighbour is in the walked
+// prefix.  Their completions are counted, not walked: a leaf contributes the size of its pivot's label group
+// minus the prefix vertices inside it; leaves with different labels multiply; r same-label leaves on one pivot
+// give a falling factorial; two same-label leaves on different pivots give |A||B| - |A n B|.
+//
+// Edge tests (checkEdgeExistence, graph.h:215-236) are binary searches too, but inside the label group of one
+// endpoint instead of its whole adjacency list: same answer, a fraction of the dependent loads.
 struct JoinGraph {
-    const u32 *off, *nbr, *deg;  // id-sorted CSR: edge tests (graph.h:215-236)
     const u32 *label;
-    const u32 *nbrL;             // the same adjacency grouped by neighbour label, ascending id inside a group
-    const u32 *gtab;             // V x (nl+1): start of every label group of every vertex (absolute, into nbrL)
+    const uint2 *nbrL;  // adjacency grouped by neighbour label, ascending id inside a group: (neighbour, its degree)
+    const u32 *gtab;    // V x (nl+1): start of every label group of every vertex (absolute, into nbrL)
     u32 V, nl;
 };
 
 constexpr int kItemHdr = 4;  // q, depth, lo, hi
 constexpr u32 kSplit = 8;
 constexpr int kDfsThreads = 256;
-
-__device__ __forceinline__ bool has_edge(const JoinGraph &g, u32 u, u32 v) {
-    // graph.h:215-236: search for the larger-degree endpoint in the smaller list
-    u32 du = g.deg[u], dv = g.deg[v];
-    if (du < dv) { u32 t = u; u = v; v = t; dv = du; }
-    const u32 *a = g.nbr + g.off[v];
-    int lo = 0, hi = (int)dv - 1;
-    while (lo <= hi) {
-        int mid = lo + ((hi - lo) >> 1);
-        u32 x = a[mid];
-        if (x == u) return true;
-        if (x > u) hi = mid - 1; else lo = mid + 1;
-    }
-    return false;
-}
+constexpr u32 kExportEvery = 32;
 
 __device__ __forceinline__ void group_range(const JoinGraph &g, u32 v, u32 label, u32 &lo, u32 &hi) {
     if (label >= g.nl) { lo = hi = 0; return; }
@@ -279,14 +333,57 @@ __device__ __forceinline__ void group_range(const JoinGraph &g, u32 v, u32 label
     hi = row[1];
 }
 
+// is v a member of the group nbrL[s, e)?  (ids ascending)
+__device__ __forceinline__ bool in_group(const JoinGraph &g, u32 s, u32 e, u32 v) {
+    while (s < e) {
+        const u32 mid = s + ((e - s) >> 1);
+        const u32 x = g.nbrL[mid].x;
+        if (x == v) return true;
+        if (x < v) s = mid + 1; else e = mid;
+    }
+    return false;
+}
+
+// edge test between a (label la) and b (label lb)
+__device__ __forceinline__ bool has_edge(const JoinGraph &g, u32 a, u32 la, u32 b, u32 lb, bool search_at_a) {
+    u32 s, e;
+    if (search_at_a) { group_range(g, a, lb, s, e); return in_group(g, s, e, b); }
+    group_range(g, b, la, s, e);
+    return in_group(g, s, e, a);
+}
+
+__device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(u32 *p, u32 v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ u64 ld_relaxed_u64(const void *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // depth-1 items from the start candidates of this shard (idx % world == rank)
 __global__ void __launch_bounds__(256) k3_init_items_kernel(JoinGraph g, u32 n_queries, const u32 *__restrict__ q_vbase,
                                                             const JoinDepth *__restrict__ jplan,
                                                             const u64 *__restrict__ cand_off, const u32 *__restrict__ cand,
                                                             const u64 *__restrict__ item_base, u32 rank, u32 world,
-                                                            u32 *items, u32 stride, u64 *answers, u64 *n_items_out) {
+                                                            u32 *items, u32 stride, u64 *answers, JoinQueue *jq) {
     const u64 n_items = item_base[n_queries];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *n_items_out = n_items;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        jq->head = 0;
+        jq->tail = n_items;
+        jq->pending = (long long)n_items;
+        jq->idle = 0;
+        jq->n_init = n_items;
+        jq->steps = 0;
+        jq->exports = 0;
+        jq->donations = 0;
+        jq->full = 0;
+    }
     for (u64 item = (u64)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (u64)gridDim.x * blockDim.x) {
         u32 lo = 0, hi = n_queries;
         while (hi - lo > 1) {
@@ -315,90 +412,182 @@ __global__ void __launch_bounds__(256) k3_init_items_kernel(JoinGraph g, u32 n_q
 template <int MAXNQ>
 __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const u32 *__restrict__ q_vbase,
                                                              const JoinDepth *__restrict__ jplan,
-                                                             const u64 *__restrict__ limits, u64 *answers,
-                                                             const u32 *__restrict__ items_in,
-                                                             const u64 *__restrict__ n_in_ptr, u32 *items_out,
-                                                             u64 *out_count, u64 out_cap, u64 *fetch_counter, u32 budget,
-                                                             u32 *matches, u64 matches_cap, u64 *match_cursor,
-                                                             u64 *step_counter) {
+                                                             const u64 *__restrict__ limits, u64 *answers, u32 *items,
+                                                             u64 item_cap, u32 *ready, u32 epoch, JoinQueue *jq,
+                                                             u32 *matches, u64 matches_cap, u64 *match_cursor) {
     constexpr u32 stride = MAXNQ + kItemHdr;
     extern __shared__ u32 s_stack[];  // emb | cur | end, each [MAXNQ][kDfsThreads]
     u32 *emb = s_stack + threadIdx.x;
     u32 *cur = emb + MAXNQ * kDfsThreads;
     u32 *end = cur + MAXNQ * kDfsThreads;
+    const u32 *emb_warp = s_stack + (threadIdx.x & ~31u);  // this warp's 32 stack columns
 #define EMB(t) emb[(t) * kDfsThreads]
 #define CUR(t) cur[(t) * kDfsThreads]
 #define END(t) end[(t) * kDfsThreads]
     const int lane = threadIdx.x & 31;
-    const u64 n_in = *n_in_ptr;
-    bool have = false, exhausted = false;
-    u32 q = 0, vb = 0, nq = 0, base = 0, d = 0, steps = 0, lab0 = 0, tail_at = 0, tail_mode = 0;
+    const unsigned lt = lanemask_lt();
+    const u64 n_init = jq->n_init;  // written by k3_init_items_kernel, the previous launch on this stream
+    bool have = false, ticketed = false, can_export = true;
+    bool registered = false;  // warp-uniform: counted in JoinQueue::idle
+    u64 ticket = 0;
+    u32 q = 0, vb = 0, nq = 0, base = 0, d = 0, lab0 = 0, tail_at = 0;
     u32 acc_q = 0xffffffffu;
-    u64 acc = 0, my_steps = 0;
+    u64 acc = 0, my_steps = 0, my_exports = 0, my_donations = 0;
+    u32 claimed = 0, iter = 0, backoff = 32;           // warp-uniform
+    u64 h_head = 0, h_tail = n_init, h_idle = 0;        // warp-uniform cached copy of the queue header
+    long long h_pending = 1;
 
     for (;;) {
-        // ---- fetch: lanes without an item claim consecutive indices with one atomic per warp ----
-        unsigned need = __ballot_sync(kFull, !have && !exhausted);
-        if (need) {
-            int leader = __ffs(need) - 1;
-            u64 b = 0;
-            if (lane == leader) b = atomicAdd((unsigned long long *)fetch_counter, (unsigned long long)__popc(need));
-            b = __shfl_sync(kFull, b, leader);
-            if (!have && !exhausted) {
-                u64 idx = b + __popc(need & lanemask_lt());
-                if (idx >= n_in) {
-                    exhausted = true;
-                } else {
-                    const u32 *it = items_in + idx * stride;
-                    u32 iq = it[0];
-                    if (iq != acc_q) {
-                        if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
-                        acc = 0;
-                        acc_q = iq;
-                    }
-                    u64 limit = limits ? limits[iq] : GPE_LIMIT_MAX;
-                    if (limit == 0) limit = 1;  // the reference tests the limit only after counting a match (:851)
-                    q = iq;
-                    vb = q_vbase[q];
-                    nq = q_vbase[q + 1] - vb;
-                    base = it[1];
-                    if (base < nq && it[2] < it[3] && *(volatile u64 *)&answers[q] < limit) {
-                        for (u32 t = 0; t < base; t++) EMB(t) = it[kItemHdr + t];
-                        lab0 = g.label[it[kItemHdr]];  // caller-supplied start candidates need not carry the query label
-                        const JoinDepth j0 = jplan[vb];
-                        tail_mode = matches ? 0 : j0.tail_mode;
-                        tail_at = tail_mode ? nq - j0.tail_k : nq;  // depth at which the counting shortcut takes over
-                        d = base;
-                        CUR(d) = it[2];
-                        END(d) = it[3];
-                        steps = 0;
-                        have = true;
-                    }
-                }
+        ++iter;
+        unsigned busy = __ballot_sync(kFull, have);
+        unsigned tick = __ballot_sync(kFull, ticketed);
+        if (!busy && claimed) {  // everything this warp took from the queue is finished
+            if (lane == 0) atomicAdd((unsigned long long *)&jq->pending, 0ull - (unsigned long long)claimed);
+            claimed = 0;
+        }
+        unsigned free_m = ~(busy | tick);
+        const bool refresh = !busy || (iter & (kExportEvery - 1)) == 0 || ((free_m | tick) && (iter & 7) == 0);
+        if (refresh) {
+            u64 a = 0, b = 0, c = 0, e = 0;
+            if (lane == 0) {
+                a = ld_relaxed_u64(&jq->head);
+                b = ld_relaxed_u64(&jq->tail);
+                c = ld_relaxed_u64(&jq->pending);
+                e = ld_relaxed_u64(&jq->idle);
+            }
+            h_head = __shfl_sync(kFull, a, 0);
+            h_tail = __shfl_sync(kFull, b, 0);
+            h_pending = (long long)__shfl_sync(kFull, c, 0);
+            h_idle = __shfl_sync(kFull, e, 0);
+            if (h_pending <= 0 && !busy) break;  // join complete
+        }
+        // ---- tickets: lanes without work claim published items (far from the end of the queue the cached
+        //      header is good enough; near the end only a fresh one is trusted)
+        if (free_m && h_head < h_tail && (refresh || h_head + 65536 < h_tail)) {
+            const u64 avail = h_tail - h_head;
+            const u32 n_want = (u32)min((u64)__popc(free_m), avail);
+            u64 b0 = 0;
+            if (lane == 0) b0 = atomicAdd(&jq->head, (unsigned long long)n_want);
+            b0 = __shfl_sync(kFull, b0, 0);
+            h_head = b0 + n_want;
+            const u32 r = __popc(free_m & lt);
+            if ((free_m >> lane & 1) && r < n_want) {
+                ticket = b0 + r;
+                ticketed = true;
             }
         }
-        if (__ballot_sync(kFull, have) == 0) break;
-        if (!have) continue;
+        // ---- ticketed lanes: start candidates are always there, exported items once their flag is up
+        bool got = false;
+        if (ticketed && (ticket < n_init || (refresh && ticket < item_cap && ld_acquire_u32(ready + ticket) == epoch))) {
+            ticketed = false;
+            got = true;
+            const u32 *it = items + ticket * stride;
+            const u32 iq = it[0];
+            if (iq != acc_q) {
+                if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
+                acc = 0;
+                acc_q = iq;
+            }
+            u64 limit = limits ? limits[iq] : GPE_LIMIT_MAX;
+            if (limit == 0) limit = 1;  // the reference tests the limit only after counting a match (:851)
+            q = iq;
+            vb = q_vbase[q];
+            nq = q_vbase[q + 1] - vb;
+            base = it[1];
+            if (base < nq && it[2] < it[3] && *(volatile u64 *)&answers[q] < limit) {
+                for (u32 t = 0; t < base; t++) EMB(t) = it[kItemHdr + t];
+                lab0 = g.label[it[kItemHdr]];  // caller-supplied start candidates need not carry the query label
+                tail_at = matches ? nq : nq - jplan[vb].tail_k;  // depth at which the counting shortcut takes over
+                d = base;
+                CUR(d) = it[2];
+                END(d) = it[3];
+                have = true;
+            }
+        }
+        claimed += __popc(__ballot_sync(kFull, got));
+        busy = __ballot_sync(kFull, have);
+        if (!busy) {
+            if (!registered) {
+                registered = true;
+                if (lane == 0) atomicAdd(&jq->idle, 1ull);
+            }
+            __nanosleep(backoff);
+            if (backoff < 1024) backoff <<= 1;
+            continue;
+        }
+        if (registered) {
+            registered = false;
+            backoff = 32;
+            if (lane == 0) atomicAdd(&jq->idle, 0ull - 1ull);
+        }
 
-        // ---- one DFS step: test the next candidate of level d ----
-        my_steps++;
-        {
+        // ---- inside the warp: lanes without work take half of a busy lane's shallowest sibling range ----
+        free_m = ~(busy | __ballot_sync(kFull, ticketed));
+        if (free_m) {
+            u32 l = 0, rem = 0;
+            if (have) {
+                for (l = base; l <= d; l++) {
+                    const u32 r = END(l) - CUR(l);  // CUR <= END always
+                    if (r >= 2 || (r == 1 && l < d)) { rem = r; break; }
+                }
+            }
+            const unsigned don_m = __ballot_sync(kFull, rem > 0);
+            const int n_pairs = min(__popc(free_m), __popc(don_m));
+            if (n_pairs) {
+                const bool is_free = free_m >> lane & 1;
+                const int my_rank = is_free ? __popc(free_m & lt) : __popc(don_m & lt);
+                const bool give = rem > 0 && my_rank < n_pairs;
+                const bool take = is_free && my_rank < n_pairs;
+                const int partner = take ? (int)__fns(don_m, 0, my_rank + 1) : lane;
+                u32 lo_g = 0, hi_g = 0;
+                if (give) {
+                    hi_g = END(l);
+                    lo_g = hi_g - (rem == 1 ? 1u : rem / 2);  // keep the lower part, give the upper one
+                    END(l) = lo_g;
+                }
+                __syncwarp();
+                const u32 p_q = __shfl_sync(kFull, q, partner), p_vb = __shfl_sync(kFull, vb, partner);
+                const u32 p_nq = __shfl_sync(kFull, nq, partner), p_lab0 = __shfl_sync(kFull, lab0, partner);
+                const u32 p_tail = __shfl_sync(kFull, tail_at, partner), p_l = __shfl_sync(kFull, l, partner);
+                const u32 p_lo = __shfl_sync(kFull, lo_g, partner), p_hi = __shfl_sync(kFull, hi_g, partner);
+                if (take) {
+                    if (p_q != acc_q) {
+                        if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
+                        acc = 0;
+                        acc_q = p_q;
+                    }
+                    q = p_q; vb = p_vb; nq = p_nq; lab0 = p_lab0; tail_at = p_tail;
+                    base = d = p_l;
+                    for (u32 t = 0; t < p_l; t++) EMB(t) = emb_warp[t * kDfsThreads + partner];
+                    CUR(d) = p_lo;
+                    END(d) = p_hi;
+                    have = true;
+                    my_donations++;
+                }
+                __syncwarp();
+            }
+        }
+
+        if (have) {
+            // ---- one DFS step: test the next candidate of level d ----
+            my_steps++;
             const u32 at = CUR(d);
-            const u32 c = g.nbrL[at];
+            const uint2 cd = g.nbrL[at];
+            const u32 c = cd.x;
             CUR(d) = at + 1;
-            const JoinDepth jd = jplan[vb + d];
-            bool ok = jd.deg <= 1 || g.deg[c] >= jd.deg;  // a neighbour always has degree >= 1
-            u64 sm = jd.same_mask;                          // earlier depths that can hold a vertex of this label
+            const JoinDepth *jd = jplan + vb + d;
+            bool ok = cd.y >= jd->deg;
+            u64 sm = jd->same_mask;  // earlier depths that can hold a vertex of this label
             while (ok && sm) {
                 int t = __ffsll((long long)sm) - 1;
                 sm &= sm - 1;
                 ok = EMB(t) != c;
             }
-            u64 bn = jd.bn_mask;
+            u64 bn = jd->bn_mask;
             while (ok && bn) {
                 int t = __ffsll((long long)bn) - 1;
                 bn &= bn - 1;
-                ok = has_edge(g, c, EMB(t));
+                ok = has_edge(g, c, jd->label, EMB(t), t ? jplan[vb + t].label : lab0, cd.y <= 64);
             }
             if (ok) {
                 if (d == nq - 1) {
@@ -408,45 +597,49 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
                         if (pos < matches_cap) {
                             u32 *row = matches + pos * nq;
                             for (u32 t = 0; t < d; t++) row[jplan[vb + t].u] = EMB(t);
-                            row[jd.u] = c;
+                            row[jd->u] = c;
                         }
                     }
                 } else {
                     EMB(d) = c;
                     const u32 nd = d + 1;
                     if (nd == tail_at) {
-                        // counting shortcut over the trailing leaves nd .. nq-1
+                        // counting shortcut over the tail depths nd .. nq-1
                         u64 total = 1;
-                        u32 sz[2] = {0, 0}, gs[2] = {0, 0}, ge[2] = {0, 0}, pv[2] = {0, 0};
+                        u32 n_run = 0, a_n = 0, a_s = 0, a_e = 0;
                         for (u32 i = nd; i < nq && total; i++) {
-                            const JoinDepth ld = jplan[vb + i];
-                            const u32 p = EMB(ld.pivot_depth);
+                            const JoinDepth *ld = jplan + vb + i;
+                            const u32 op = ld->tail_k;
+                            if (op == kTailFall) {
+                                n_run = n_run ? n_run - 1 : 0;
+                                total *= n_run;
+                                continue;
+                            }
+                            const u32 llab = ld->label;
                             u32 s, e;
-                            group_range(g, p, ld.label, s, e);
-                            u32 used = 0;  // prefix vertices that sit in this group
-                            u64 m = ld.same_mask & ((1ull << nd) - 1);
-                            while (m) {
+                            group_range(g, EMB(ld->pivot_depth), llab, s, e);
+                            u32 used = ld->sure_used;  // prefix vertices that sit in this group
+                            u64 m = ld->tail_mask;
+                            while (m && s < e) {
                                 int t = __ffsll((long long)m) - 1;
                                 m &= m - 1;
-                                if ((u32)t != ld.pivot_depth && (t != 0 || lab0 == ld.label) && has_edge(g, p, EMB(t))) used++;
+                                if ((t != 0 || lab0 == llab) && in_group(g, s, e, EMB(t))) used++;
                             }
                             const u32 n_free = (e - s) - used;
-                            if (tail_mode == 2) {
-                                sz[i - nd] = n_free; gs[i - nd] = s; ge[i - nd] = e; pv[i - nd] = p;
-                            } else {
+                            if (op == kTailMul) {
+                                n_run = n_free;
                                 total *= n_free;
-                            }
-                        }
-                        if (tail_mode == 2) {
-                            // both leaves carry the same label: ordered pairs of distinct vertices
-                            u64 inter;
-                            if (pv[0] == pv[1]) {
-                                inter = sz[0];
+                            } else if (op == kTailPairA) {
+                                a_n = n_free;
+                                a_s = s;
+                                a_e = e;
                             } else {
-                                inter = 0;  // |G(p0) n G(p1)| without the used members: merge two ascending id lists
-                                u32 x = gs[0], y = gs[1];
-                                while (x < ge[0] && y < ge[1]) {
-                                    const u32 vx = g.nbrL[x], vy = g.nbrL[y];
+                                // ordered pairs of distinct vertices: |A||B| - |A n B| over the free members;
+                                // the groups are ascending id lists, so the intersection is a merge
+                                u64 inter = 0;
+                                u32 x = a_s, y = s;
+                                while (x < a_e && y < e) {
+                                    const u32 vx = g.nbrL[x].x, vy = g.nbrL[y].x;
                                     if (vx == vy) {
                                         bool is_used = false;
                                         for (u32 t = 0; t < nd; t++) is_used = is_used || EMB(t) == vx;
@@ -459,14 +652,14 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
                                         y++;
                                     }
                                 }
+                                total *= (u64)a_n * n_free - inter;
                             }
-                            total = (u64)sz[0] * sz[1] - inter;
                         }
                         acc += total;
                     } else {
-                        const JoinDepth ndj = jplan[vb + nd];
+                        const JoinDepth *ndj = jplan + vb + nd;
                         u32 s, e;
-                        group_range(g, EMB(ndj.pivot_depth), ndj.label, s, e);
+                        group_range(g, EMB(ndj->pivot_depth), ndj->label, s, e);
                         d = nd;
                         CUR(d) = s;
                         END(d) = e;
@@ -474,39 +667,52 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
                 }
             }
         }
+
+        // ---- between warps: when idle warps outnumber the published items, one lane gives work away ----
+        if ((iter & (kExportEvery - 1)) == 0 && h_idle > 0 && (long long)(h_tail - h_head) < (long long)(h_idle * 4)) {
+            u32 key = 0xffffffffu, l = 0;
+            if (have && can_export) {
+                for (l = base; l <= d; l++)
+                    if (CUR(l) < END(l)) { key = (l << 5) | (u32)lane; break; }
+            }
+            const u32 best = __reduce_min_sync(kFull, key);
+            if (best != 0xffffffffu && key == best) {
+                const u32 c0 = CUR(l), len = END(l) - c0, np = min(len, kSplit);
+                const u64 o = atomicAdd(&jq->tail, (unsigned long long)np);
+                if (o + np > item_cap) {
+                    can_export = false;  // those tickets are never published; their holders idle until the end
+                    jq->full = 1;
+                } else {
+                    atomicAdd((unsigned long long *)&jq->pending, (unsigned long long)np);
+                    for (u32 k = 0; k < np; k++) {
+                        u32 *it = items + (o + k) * stride;
+                        it[0] = q;
+                        it[1] = l;
+                        it[2] = c0 + (u32)((u64)len * k / np);
+                        it[3] = c0 + (u32)((u64)len * (k + 1) / np);
+                        for (u32 t = 0; t < l; t++) it[kItemHdr + t] = EMB(t);
+                    }
+                    __threadfence();
+                    for (u32 k = 0; k < np; k++) st_relaxed_u32(ready + o + k, epoch);
+                    END(l) = c0;
+                    my_exports++;
+                }
+            }
+        }
         // ---- pop exhausted levels ----
         while (have && CUR(d) >= END(d)) {
             if (d == base) have = false; else d--;
         }
-
-        // ---- budget: hand the unexplored sibling ranges of every stack level to the next round ----
-        if (have && ++steps >= budget) {
-            u32 pieces = 0;
-            for (u32 l = base; l <= d; l++) pieces += min(END(l) - CUR(l), kSplit);
-            u64 o = atomicAdd((unsigned long long *)out_count, (unsigned long long)pieces);
-            if (o + pieces > out_cap) {
-                atomicAdd((unsigned long long *)out_count, (unsigned long long)(0ull - pieces));  // undo; keep running
-                steps = 0;
-            } else {
-                for (u32 l = base; l <= d; l++) {
-                    u32 len = END(l) - CUR(l), np = min(len, kSplit);
-                    for (u32 k = 0; k < np; k++) {
-                        u32 *it = items_out + o * stride;
-                        it[0] = q;
-                        it[1] = l;
-                        it[2] = CUR(l) + (u32)((u64)len * k / np);
-                        it[3] = CUR(l) + (u32)((u64)len * (k + 1) / np);
-                        for (u32 t = 0; t < l; t++) it[kItemHdr + t] = EMB(t);
-                        o++;
-                    }
-                }
-                have = false;
-            }
-        }
     }
     if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
-    for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(kFull, my_steps, o);
-    if (lane == 0 && my_steps) atomicAdd((unsigned long long *)step_counter, (unsigned long long)my_steps);
+    for (int o = 16; o; o >>= 1) {
+        my_steps += __shfl_xor_sync(kFull, my_steps, o);
+        my_exports += __shfl_xor_sync(kFull, my_exports, o);
+        my_donations += __shfl_xor_sync(kFull, my_donations, o);
+    }
+    if (lane == 0 && my_steps) atomicAdd(&jq->steps, (unsigned long long)my_steps);
+    if (lane == 0 && my_exports) atomicAdd(&jq->exports, (unsigned long long)my_exports);
+    if (lane == 0 && my_donations) atomicAdd(&jq->donations, (unsigned long long)my_donations);
 #undef EMB
 #undef CUR
 #undef END
@@ -563,18 +769,17 @@ u32 k3_item_stride(u32 max_nq) {
 
 cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
                           const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world, u32 *items,
-                          u32 stride, u64 *answers, u64 *n_items_out, int sm_count, cudaStream_t s) {
-    JoinGraph g{jv.off, jv.nbr, jv.deg, jv.label, jv.nbrL, jv.gtab, jv.V, jv.nl};
+                          u32 stride, u64 *answers, JoinQueue *jq, int sm_count, cudaStream_t s) {
+    JoinGraph g{jv.label, reinterpret_cast<const uint2 *>(jv.nbrL), jv.gtab, jv.V, jv.nl};
     k3_init_items_kernel<<<sm_count * 4, 256, 0, s>>>(g, n_queries, q_vbase, jplan, cand_off, cand, item_base, rank, world,
-                                                     items, stride, answers, n_items_out);
+                                                     items, stride, answers, jq);
     return cudaGetLastError();
 }
 
-cudaError_t k3_dfs_round(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const u64 *limits,
-                         u64 *answers, const u32 *items_in, const u64 *n_in, u32 *items_out, u64 *out_count, u64 out_cap,
-                         u64 *fetch_counter, u32 budget, u32 *matches, u64 matches_cap, u64 *match_cursor,
-                         u64 *step_counter, int sm_count, cudaStream_t s) {
-    JoinGraph g{jv.off, jv.nbr, jv.deg, jv.label, jv.nbrL, jv.gtab, jv.V, jv.nl};
+cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const u64 *limits,
+                   u64 *answers, u32 *items, u64 item_cap, u32 *ready, u32 epoch, JoinQueue *jq, u32 *matches,
+                   u64 matches_cap, u64 *match_cursor, int sm_count, cudaStream_t s) {
+    JoinGraph g{jv.label, reinterpret_cast<const uint2 *>(jv.nbrL), jv.gtab, jv.V, jv.nl};
 #define LAUNCH(M)                                                                                                     \
     static int per_sm_##M = 0;                                                                                        \
     const size_t smem_##M = (size_t)3 * M * kDfsThreads * sizeof(u32);                                                \
@@ -584,8 +789,8 @@ cudaError_t k3_dfs_round(const JoinView &jv, u32 max_nq, const u32 *q_vbase, con
                 cudaSuccess || per_sm_##M < 1)                                                                        \
             per_sm_##M = 1;                                                                                           \
     }                                                                                                                 \
-    k3_dfs_kernel<M><<<sm_count * per_sm_##M, kDfsThreads, smem_##M, s>>>(g, q_vbase, jplan, limits, answers, items_in, n_in, items_out, out_count, \
-                                            out_cap, fetch_counter, budget, matches, matches_cap, match_cursor, step_counter)
+    k3_dfs_kernel<M><<<sm_count * per_sm_##M, kDfsThreads, smem_##M, s>>>(g, q_vbase, jplan, limits, answers, items,  \
+                                            item_cap, ready, epoch, jq, matches, matches_cap, match_cursor)
     if (max_nq <= 8) { LAUNCH(8); }
     else if (max_nq <= 16) { LAUNCH(16); }
     else if (max_nq <= 32) { LAUNCH(32); }

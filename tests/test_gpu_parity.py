@@ -300,3 +300,53 @@ def test_two_shards_in_one_process_match_single_gpu():
     assert got == want
     for c in ctxs:
         c.close()
+
+
+# Query shapes that exercise every branch of the join's counted tail (leaves with distinct labels, several
+# same-label leaves on one pivot, two same-label leaves on two pivots, leaves that share a label with walked
+# vertices, leaves next to cycles) and the subtree hand-over between threads.
+_TAIL_SHAPES = {
+    "star4_same": ([(0, 1), (0, 2), (0, 3), (0, 4)], [0, 1, 1, 1, 1]),
+    "star5_mixed": ([(0, 1), (0, 2), (0, 3), (0, 4), (0, 5)], [0, 1, 1, 2, 2, 0]),
+    "two_hubs_pair": ([(0, 1), (0, 2), (1, 3)], [0, 1, 2, 2]),
+    "two_hubs_four_leaves": ([(0, 1), (0, 2), (0, 3), (1, 4), (1, 5)], [0, 1, 2, 2, 2, 2]),
+    "path_with_pendants": ([(0, 1), (1, 2), (2, 3), (1, 4), (2, 5), (3, 6)], [0, 1, 0, 1, 0, 1, 2]),
+    "triangle_pendants": ([(0, 1), (1, 2), (0, 2), (0, 3), (1, 4), (2, 5)], [0, 1, 2, 1, 2, 0]),
+    "square_pendant": ([(0, 1), (1, 2), (2, 3), (0, 3), (2, 4), (2, 5)], [0, 1, 0, 1, 1, 1]),
+    "caterpillar": ([(0, 1), (1, 2), (2, 3), (0, 4), (1, 5), (2, 6), (3, 7)], [0, 1, 2, 0, 1, 2, 0, 1]),
+    "leaf_label_equals_pivot_neighbour": ([(0, 1), (1, 2), (1, 3), (3, 4)], [0, 1, 2, 2, 0]),
+    "edge_plus_leaf": ([(0, 1), (1, 2)], [0, 1, 0]),
+}
+
+
+@pytest.mark.parametrize("nl,seed", [(2, 11), (3, 12), (5, 13)])
+def test_join_counted_tail_equals_reference_enumeration(nl, seed):
+    from oracle import oracle
+    g = synth.chung_lu_graph(300, 1500, nl, gamma=2.4, degree_cap=60, seed=seed)
+    og = oracle.OracleGraph.from_csr(g.offsets, g.nbrs, g.labels)
+    ctx = gpe.GpeContext(0)
+    ctx.set_graph(g.offsets, g.nbrs, g.labels)
+    rng = np.random.default_rng(seed)
+    for name, (edges, labels) in _TAIL_SHAPES.items():
+        labels = np.array(labels) % nl
+        q = graph_io.csr_from_edges(len(labels), np.array(edges), labels)
+        oq = oracle.OracleGraph.from_csr(q.offsets, q.nbrs, q.labels)
+        # candidate sets as a caller may supply them: right-label vertices thinned at random, plus a few
+        # vertices of the wrong label (the reference only ever iterates the start vertex's set, unchecked)
+        cands = []
+        for u in range(q.V):
+            right = np.nonzero(g.labels == labels[u])[0]
+            keep = right[rng.random(len(right)) < rng.uniform(0.3, 1.0)]
+            wrong = rng.choice(g.V, size=3, replace=False)
+            cands.append(np.unique(np.concatenate([keep, wrong])).astype(np.uint32))
+        expect = oracle.refine(og, oq, cands)
+        res = ctx.refine(q.offsets, q.nbrs, q.labels, cands)
+        order, pivot = oracle.matching_order(og, oq, [len(c) for c in cands])
+        assert res["order"].tolist() == order.tolist(), name
+        assert res["n_matches"] == min(expect, gpe.LIMIT_MAX), (name, res["n_matches"], expect)
+        if 0 < expect <= 200_000:
+            n, om = oracle.refine(og, oq, cands, want_matches=expect + 8)
+            rm = ctx.refine(q.offsets, q.nbrs, q.labels, cands, want_matches=expect + 8)
+            assert rm["n_matches"] == expect, name
+            assert sorted(map(tuple, rm["matches"].tolist())) == sorted(map(tuple, om.tolist())), name
+    ctx.close()

@@ -38,7 +38,7 @@ for i, q in enumerate(queries):
         k += 1
     off, cand = ctx.batch_get_candidates()
     cnt = np.diff(off.astype(np.int64))
-    rows.append((a, st["join_steps"], st["join_rounds"], k, int(cnt[int(order[0])]), [int(deg[int(u)]) for u in order]))
+    rows.append((a, st["join_steps"], st["join_exports"], k, int(cnt[int(order[0])]), [int(deg[int(u)]) for u in order]))
 rows_sorted = sorted(rows, key=lambda r: -r[1])
 tot_steps = sum(r[1] for r in rows)
 print("total matches", sum(r[0] for r in rows), "total steps", tot_steps)

@@ -13,4 +13,4 @@ ctx.build_table()
 for i in range(2):
     t=time.time(); a = ctx.query_batch(queries); dt=time.time()-t
     st = ctx.stats()
-    print(f"batch: {dt*1e3:.2f} ms  matches={int(a.sum())} rounds={st['join_rounds']} steps={st['join_steps']} items={st['join_items']}", file=sys.stderr)
+    print(f"batch: {dt*1e3:.2f} ms  matches={int(a.sum())} rounds={st['join_exports']} steps={st['join_steps']} items={st['join_items']}", file=sys.stderr)

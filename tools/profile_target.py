@@ -22,7 +22,7 @@ for _ in range(steps):
     ctx.batch_join()
 ans = ctx.batch_download()
 st = ctx.stats()
-print("answers checksum", int(ans.sum()), {k: st[k] for k in ("scan_items", "scan_rows", "n_candidates", "join_items", "join_rounds", "join_steps", "kernel_launches")})
+print("answers checksum", int(ans.sum()), {k: st[k] for k in ("scan_items", "scan_rows", "n_candidates", "join_items", "join_exports", "join_steps", "kernel_launches")})
 q0 = queries[0]
 plan = gpe.host_query_plan(q0.offsets, q0.nbrs, q0.labels, w["l"] + 1, w["e"])
 for _ in range(stream_reps):
