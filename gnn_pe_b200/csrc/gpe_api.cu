@@ -215,7 +215,8 @@ int run_filter(gpe_ctx *c) {
         {
             StageTimer tm(c, &c->stats.last_scan_ms, kStageScan);
             GPE_CUDA(c, k2_scan(c->tv, c->d_qblocks.p, c->d_worklist.as<u64>(), c->d_counters.as<u64>(),
-                                c->d_bitmap.as<u32>(), c->b_words, c->d_survivors.as<u64>(), c->sm_count, c->stream));
+                                c->d_bitmap.as<u32>(), c->b_words, c->d_survivors.as<u64>(),
+                                !(c->b_flags & GPE_FILTER_NO_PRUNE), c->sm_count, c->stream));
             c->stats.scan_launches++;
             c->stats.kernel_launches++;
         }
@@ -312,6 +313,8 @@ int read_join_stats(gpe_ctx *c) {
     c->stats.join_exports = h.exports;
     c->stats.join_donations = h.donations;
     c->stats.join_steps = h.steps;
+    c->stats.join_warp_iters = h.warp_iters;
+    c->stats.join_idle_polls = h.idle_polls;
     return GPE_OK;
 }
 
@@ -884,6 +887,8 @@ int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) {
     c->stats.join_exports = jq.exports;
     c->stats.join_donations = jq.donations;
     c->stats.join_steps = jq.steps;
+    c->stats.join_warp_iters = jq.warp_iters;
+    c->stats.join_idle_polls = jq.idle_polls;
     c->stats.d2h_bytes += (size_t)c->b_nq * sizeof(u64) + sizeof(JoinQueue);
     return GPE_OK;
 }

@@ -143,7 +143,9 @@ struct alignas(16) JoinQueue {
     unsigned long long exports;  // hand-overs between warps (through the queue)
     unsigned long long donations;  // hand-overs inside a warp (through shared memory)
     unsigned long long full;     // set once the item buffer overflowed (exports stop; result unaffected)
-    unsigned long long pad[3];
+    unsigned long long warp_iters;  // loop iterations of warps that had at least one busy lane (32 x this = lane slots)
+    unsigned long long lane_iters;  // unused
+    unsigned long long idle_polls;  // loop iterations of warps without any busy lane
 };
 
 }  // namespace gpe
@@ -251,8 +253,9 @@ void qblock_pack(u32 L, u32 E, void *dst_rec, u32 n, u32 first_qpath, const u32 
                  const u32 *degs, const u32 *slots, const double *pde);
 cudaError_t k2_select(const TableView &t, const void *qblocks, const u32 *qb_t0, const u64 *qb_prefix, u32 n_qblocks,
                       u64 n_items, bool prune, u64 *worklist, u64 *counters, cudaStream_t s);
+// with_vids: the tiles' vertex ids travel with them through the TMA ring (pruned work lists, survivors common)
 cudaError_t k2_scan(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters, u32 *bitmap,
-                    u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s);
+                    u64 words_per_slot, u64 *survivors, bool with_vids, int sm_count, cudaStream_t s);
 bool k2_supported(u32 L, u32 E);
 
 // K3 (candidate compaction, matching order, join)

@@ -77,12 +77,13 @@ __device__ __forceinline__ void bulk_load_nohint(void *dst, const void *src, u32
                  : "memory");
 }
 
-template <int L, int E>
+template <int L, int E, bool VIDS>
 struct ScanGeom {
     static constexpr int D = L * E;
     static constexpr int kTileBytes = kTileRows * (8 * L + 8 * D);
+    static constexpr int kVidBytes = VIDS ? kTileRows * 4 * L : 0;  // the tile's vertex ids ride along when survivors are the rule
     static constexpr int kRecBytes = (int)sizeof(QBlockRec<L, E>);
-    static constexpr int kStageBytes = ((kTileBytes + kRecBytes + 127) / 128) * 128;
+    static constexpr int kStageBytes = ((kTileBytes + kVidBytes + kRecBytes + 127) / 128) * 128;
     static constexpr int kNumStages = (kStages * kStageBytes <= 200 * 1024) ? kStages
                                        : ((200 * 1024) / kStageBytes >= 2 ? (200 * 1024) / kStageBytes : 2);
     static constexpr int kSmemBytes = kNumStages * kStageBytes + 1024;  // ring + barriers/meta + alignment slack
@@ -142,12 +143,17 @@ __global__ void __launch_bounds__(256) k2_select_kernel(TableView t, const QBloc
 }
 
 // ---- the scan ----------------------------------------------------------------------------------------------
-template <int L, int E>
+// VIDS = true  (pruned work list: the tiles come from the plan paths' own label buckets, most rows pass the label
+//               test and survivors are common): the tile's vertex ids are part of the stage, no dependent global load;
+// VIDS = false (streaming, every row against every plan path: survivors are rare): vertex ids are fetched from
+//               global memory by the few rows that need them.
+// Survivors set their bits with fire-and-forget reductions (RED.OR): nothing in the consumer loop waits on L2.
+template <int L, int E, bool VIDS>
 __global__ void __launch_bounds__(kTileRows + 32, 1)
 k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u64 *__restrict__ worklist,
                const u64 *__restrict__ counters, u32 *__restrict__ bitmap, u64 words_per_slot,
                u64 *__restrict__ survivors) {
-    using G = ScanGeom<L, E>;
+    using G = ScanGeom<L, E, VIDS>;
     constexpr int D = G::D;
     constexpr int NS = G::kNumStages;
     extern __shared__ unsigned char smem_raw[];
@@ -188,9 +194,11 @@ k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u
                     u32 tile = (u32)item, b = (u32)(item >> 32);
                     unsigned char *dst = ring + stage * G::kStageBytes;
                     meta[stage] = item;
-                    mbar_arrive_expect_tx(&full_bar[stage], G::kTileBytes + G::kRecBytes);
+                    mbar_arrive_expect_tx(&full_bar[stage], G::kTileBytes + G::kVidBytes + G::kRecBytes);
                     bulk_load(dst, t.tiles + (u64)tile * G::kTileBytes, G::kTileBytes, &full_bar[stage], policy);
-                    bulk_load_nohint(dst + G::kTileBytes, &qblocks[b], G::kRecBytes, &full_bar[stage]);
+                    if (VIDS)
+                        bulk_load(dst + G::kTileBytes, t.vids + (u64)tile * L * kTileRows, G::kVidBytes, &full_bar[stage], policy);
+                    bulk_load_nohint(dst + G::kTileBytes + G::kVidBytes, &qblocks[b], G::kRecBytes, &full_bar[stage]);
                 }
                 if (++stage == NS) { stage = 0; phase ^= 1; }
             }
@@ -200,43 +208,67 @@ k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u
         const u32 r = threadIdx.x;
         int stage = 0;
         u32 phase = 0;
+        // survivor counters: lane j < kQB of every warp counts plan path j of the block the warp is working on
+        u32 cur_b = 0xffffffffu, my_cnt = 0, my_qpath = 0;
         for (u64 k = 0; k < n_my; k++) {
             mbar_wait(&full_bar[stage], phase);
             const unsigned char *buf = ring + stage * G::kStageBytes;
             const u64 item = meta[stage];
-            const u32 tile = (u32)item;
+            const u32 tile = (u32)item, b = (u32)(item >> 32);
             const u32 *s_lab = reinterpret_cast<const u32 *>(buf);
             const u32 *s_deg = reinterpret_cast<const u32 *>(buf + 4 * L * kTileRows);
             const double *s_pde = reinterpret_cast<const double *>(buf + 8 * L * kTileRows);
-            const QBlockRec<L, E> *rec = reinterpret_cast<const QBlockRec<L, E> *>(buf + G::kTileBytes);
+            const u32 *s_vid = reinterpret_cast<const u32 *>(buf + G::kTileBytes);
+            const QBlockRec<L, E> *rec = reinterpret_cast<const QBlockRec<L, E> *>(buf + G::kTileBytes + G::kVidBytes);
             const bool valid = (u64)tile * kTileRows + r < t.n_rows;
+            if (b != cur_b) {
+                if (my_cnt) atomicAdd((unsigned long long *)&survivors[my_qpath], (unsigned long long)my_cnt);
+                my_cnt = 0;
+                cur_b = b;
+                my_qpath = lane < kQB ? rec->qpath[lane] : 0;
+            }
 
             u32 lab[L], dg[L];
+            double pde[D];
 #pragma unroll
             for (int kk = 0; kk < L; kk++) {
                 lab[kk] = s_lab[kk * kTileRows + r];
                 dg[kk] = s_deg[kk * kTileRows + r];
             }
+#pragma unroll
+            for (int d = 0; d < D; d++) pde[d] = s_pde[d * kTileRows + r];
             const u32 nq = rec->n;
+            u32 okm = 0;  // plan paths of the block this row survives
             for (u32 j = 0; j < nq; j++) {
                 bool ok = valid;
 #pragma unroll
                 for (int kk = 0; kk < L; kk++) ok = ok && (rec->labels[j][kk] == lab[kk]) && (rec->degs[j][kk] <= dg[kk]);
                 if (ok) {
 #pragma unroll
-                    for (int d = 0; d < D; d++) ok = ok && !(rec->pde[j][d] - s_pde[d * kTileRows + r] > kEps);
+                    for (int d = 0; d < D; d++) ok = ok && !(rec->pde[j][d] - pde[d] > kEps);
                 }
-                unsigned m = __ballot_sync(kFull, ok);
-                if (m) {
-                    if (lane == 0) atomicAdd((unsigned long long *)&survivors[rec->qpath[j]], (unsigned long long)__popc(m));
-                    if (ok) {
+                const unsigned m = __ballot_sync(kFull, ok);
+                if (lane == (int)j) my_cnt += __popc(m);
+                okm |= (u32)ok << j;
+            }
+            if (__any_sync(kFull, okm != 0)) {
+                u32 v[L];
 #pragma unroll
-                        for (int kk = 0; kk < L; kk++) {
-                            u32 v = t.vids[((u64)tile * L + kk) * kTileRows + r];
-                            u32 *word = bitmap + (u64)rec->slot[j][kk] * words_per_slot + (v >> 5);
-                            u32 bit = 1u << (v & 31);
-                            if (!(*word & bit)) atomicOr(word, bit);
-                        }
+                for (int kk = 0; kk < L; kk++)
+                    v[kk] = !okm ? 0xffffffffu
+                                 : VIDS ? s_vid[kk * kTileRows + r] : t.vids[((u64)tile * L + kk) * kTileRows + r];
+                // rows of one start vertex are neighbours in the table: a lane whose left neighbour sets the same bits
+                // for the same vertex stays silent
+                const u32 okm_left = __shfl_up_sync(kFull, okm, 1);
+#pragma unroll
+                for (int kk = 0; kk < L; kk++) {
+                    const u32 v_left = __shfl_up_sync(kFull, v[kk], 1);
+                    u32 todo = okm;
+                    if (lane > 0 && v_left == v[kk]) todo &= ~okm_left;
+                    while (todo) {
+                        const int j = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        atomicOr(bitmap + (u64)rec->slot[j][kk] * words_per_slot + (v[kk] >> 5), 1u << (v[kk] & 31));
                     }
                 }
             }
@@ -244,6 +276,7 @@ k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
             if (++stage == NS) { stage = 0; phase ^= 1; }
         }
+        if (my_cnt) atomicAdd((unsigned long long *)&survivors[my_qpath], (unsigned long long)my_cnt);
     }
 }
 
@@ -257,24 +290,31 @@ cudaError_t launch_select(const TableView &t, const void *qblocks, const u32 *qb
     return cudaGetLastError();
 }
 
-template <int L, int E>
-cudaError_t launch_scan(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters,
-                        u32 *bitmap, u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s) {
-    using G = ScanGeom<L, E>;
+template <int L, int E, bool VIDS>
+cudaError_t launch_scan_v(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters,
+                          u32 *bitmap, u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s) {
+    using G = ScanGeom<L, E, VIDS>;
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(k2_scan_kernel<L, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k2_scan_kernel<L, E, VIDS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              G::kSmemBytes);
         if (e != cudaSuccess) return e;
         int n = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k2_scan_kernel<L, E>, kTileRows + 32, G::kSmemBytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k2_scan_kernel<L, E, VIDS>, kTileRows + 32, G::kSmemBytes);
         if (e != cudaSuccess) return e;
         ctas_per_sm = n < 1 ? 1 : n;
     }
     unsigned blocks = (unsigned)(sm_count * ctas_per_sm);
-    k2_scan_kernel<L, E><<<blocks, kTileRows + 32, G::kSmemBytes, s>>>(
+    k2_scan_kernel<L, E, VIDS><<<blocks, kTileRows + 32, G::kSmemBytes, s>>>(
         t, reinterpret_cast<const QBlockRec<L, E> *>(qblocks), worklist, counters, bitmap, words_per_slot, survivors);
     return cudaGetLastError();
+}
+
+template <int L, int E>
+cudaError_t launch_scan(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters,
+                        u32 *bitmap, u64 words_per_slot, u64 *survivors, bool with_vids, int sm_count, cudaStream_t s) {
+    return with_vids ? launch_scan_v<L, E, true>(t, qblocks, worklist, counters, bitmap, words_per_slot, survivors, sm_count, s)
+                     : launch_scan_v<L, E, false>(t, qblocks, worklist, counters, bitmap, words_per_slot, survivors, sm_count, s);
 }
 
 template <int L, int E>
@@ -341,9 +381,9 @@ cudaError_t k2_select(const TableView &t, const void *qblocks, const u32 *qb_t0,
 }
 
 cudaError_t k2_scan(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters, u32 *bitmap,
-                    u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s) {
+                    u64 words_per_slot, u64 *survivors, bool with_vids, int sm_count, cudaStream_t s) {
     cudaError_t e = cudaErrorInvalidValue;
-#define CALL(l, e_) e = launch_scan<l, e_>(t, qblocks, worklist, counters, bitmap, words_per_slot, survivors, sm_count, s)
+#define CALL(l, e_) e = launch_scan<l, e_>(t, qblocks, worklist, counters, bitmap, words_per_slot, survivors, with_vids, sm_count, s)
     GPE_DISPATCH_LE(t.L, t.E, CALL);
 #undef CALL
     return e;

@@ -383,6 +383,9 @@ __global__ void __launch_bounds__(256) k3_init_items_kernel(JoinGraph g, u32 n_q
         jq->exports = 0;
         jq->donations = 0;
         jq->full = 0;
+        jq->warp_iters = 0;
+        jq->lane_iters = 0;
+        jq->idle_polls = 0;
     }
     for (u64 item = (u64)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (u64)gridDim.x * blockDim.x) {
         u32 lo = 0, hi = n_queries;
@@ -433,6 +436,7 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
     u32 q = 0, vb = 0, nq = 0, base = 0, d = 0, lab0 = 0, tail_at = 0;
     u32 acc_q = 0xffffffffu;
     u64 acc = 0, my_steps = 0, my_exports = 0, my_donations = 0;
+    u64 w_iters = 0, w_polls = 0;  // warp-uniform: iterations with at least one busy lane / without any
     u32 claimed = 0, iter = 0, backoff = 32;           // warp-uniform
     u64 h_head = 0, h_tail = n_init, h_idle = 0;        // warp-uniform cached copy of the queue header
     long long h_pending = 1;
@@ -513,6 +517,7 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
             }
             __nanosleep(backoff);
             if (backoff < 1024) backoff <<= 1;
+            w_polls++;
             continue;
         }
         if (registered) {
@@ -568,6 +573,7 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
             }
         }
 
+        w_iters++;
         if (have) {
             // ---- one DFS step: test the next candidate of level d ----
             my_steps++;
@@ -713,6 +719,8 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
     if (lane == 0 && my_steps) atomicAdd(&jq->steps, (unsigned long long)my_steps);
     if (lane == 0 && my_exports) atomicAdd(&jq->exports, (unsigned long long)my_exports);
     if (lane == 0 && my_donations) atomicAdd(&jq->donations, (unsigned long long)my_donations);
+    if (lane == 0 && w_iters) atomicAdd(&jq->warp_iters, (unsigned long long)w_iters);
+    if (lane == 0 && w_polls) atomicAdd(&jq->idle_polls, (unsigned long long)w_polls);
 #undef EMB
 #undef CUR
 #undef END
