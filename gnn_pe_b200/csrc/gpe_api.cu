@@ -257,6 +257,7 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
     GPE_CUDA(c, c->d_order.reserve(std::max<size_t>(n_slots, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_pivot.reserve(std::max<size_t>(n_slots, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_jplan.reserve(std::max<size_t>(n_slots, 1) * sizeof(JoinDepth)));
+    GPE_CUDA(c, c->d_kids.reserve(std::max<size_t>(n_slots, 1) * 2 * sizeof(u32)));
     GPE_CUDA(c, c->d_item_base.reserve(((size_t)n_queries + 1) * sizeof(u64)));
     GPE_CUDA(c, c->d_answers.reserve(((size_t)n_queries + 8) * sizeof(u64)));
     GPE_CUDA(c, c->d_match_cursor.reserve(2 * sizeof(u64)));
@@ -266,7 +267,7 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
     return GPE_OK;
 }
 
-constexpr u64 kJoinExportCap = 1ull << 22;  // room for exported work items on top of the start candidates
+constexpr u64 kJoinExportBytes = 256ull << 20;  // room for exported work items
 
 int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     StageTimer tm(c, &c->stats.last_join_ms, kStageJoin);
@@ -277,13 +278,14 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     GPE_CUDA(c, c->d_jq.reserve(sizeof(JoinQueue)));
     GPE_CUDA(c, k3_order(nq, c->V, c->d_q_vbase.as<u32>(), c->d_q_ebase.as<u32>(), c->d_q_offsets.as<u32>(),
                          c->d_q_nbrs.as<u32>(), c->d_q_labels.as<u32>(), c->d_cand_off.as<u64>(), c->d_order.as<u32>(),
-                         c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_item_base.as<u64>(), rank, world,
+                         c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_item_base.as<u64>(), rank, world,
                          c->stream));
     JoinView jv{c->d_label.as<u32>(), c->d_nbrL.as<u32>(), c->d_gtab.as<u32>(), c->V, c->n_labels};
     const u32 stride = k3_item_stride(c->b_max_nq);
-    // tickets [0, n_init) hold one item per start candidate of this shard (b_n_cand bounds that from above),
-    // the rest of the buffer receives exported subtrees
-    const u64 cap = c->b_n_cand + kJoinExportCap;
+    // tickets [0, n_init) are the start candidates of this shard (b_n_cand bounds their number from above);
+    // later tickets are subtrees exported by busy threads
+    const u64 cap = kJoinExportBytes / (stride * sizeof(u32));
+    GPE_CUDA(c, c->d_init.reserve(std::max<u64>(c->b_n_cand, 1) * 2 * sizeof(u32)));
     GPE_CUDA(c, c->d_items.reserve(cap * stride * sizeof(u32)));
     if (c->d_ready.cap < cap * sizeof(u32) || c->join_epoch == 0xffffffffu) {
         GPE_CUDA(c, c->d_ready.reserve(cap * sizeof(u32)));
@@ -292,12 +294,11 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     }
     const u32 epoch = ++c->join_epoch;
     JoinQueue *jq = c->d_jq.as<JoinQueue>();
-    GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
-                              c->d_cand.as<u32>(), c->d_item_base.as<u64>(), rank, world, c->d_items.as<u32>(), stride,
-                              answers, jq, c->sm_count, c->stream));
-    GPE_CUDA(c, k3_dfs(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_limits.as<u64>(), answers,
-                       c->d_items.as<u32>(), cap, c->d_ready.as<u32>(), epoch, jq, d_matches, matches_cap,
-                       c->d_match_cursor.as<u64>(), c->sm_count, c->stream));
+    GPE_CUDA(c, k3_init_items(nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
+                              c->d_item_base.as<u64>(), rank, world, c->d_init.p, jq, c->sm_count, c->stream));
+    GPE_CUDA(c, k3_dfs(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_cand.as<u32>(),
+                       c->d_init.p, c->d_limits.as<u64>(), answers, c->d_items.as<u32>(), cap, c->d_ready.as<u32>(), epoch,
+                       jq, d_matches, matches_cap, c->d_match_cursor.as<u64>(), c->sm_count, c->stream));
     c->stats.kernel_launches += 3;
     c->stats.join_launches += 3;
     c->b_joined = true;
@@ -388,7 +389,7 @@ void gpe_destroy(gpe_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrL, &c->d_gtab, &c->d_items, &c->d_ready, &c->d_jq, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
+    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrL, &c->d_gtab, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
                       &c->d_offr, &c->d_ebase, &c->d_start_rows, &c->d_scan_tmp, &c->d_tiles, &c->d_vids, &c->d_sum_u32, &c->d_sum_f64,
                       &c->d_bucket, &c->d_cursor, &c->d_qblocks, &c->d_qb_t0, &c->d_qb_prefix, &c->d_worklist,
                       &c->d_counters, &c->d_bitmap, &c->d_survivors, &c->d_chunk_cnt, &c->d_chunk_off, &c->d_cand,

@@ -123,9 +123,13 @@ struct alignas(16) JoinDepth {
     u64 bn_mask;      // depths of the other backward neighbours (generateBN, custom.h:724-755)
     u64 same_mask;    // earlier depths whose vertex may equal a candidate of this depth (same label; depth 0 always)
     u64 tail_mask;    // [tail depths] prefix depths that may sit in this leaf's label group and need an edge test
+    u32 kid_begin, kid_count;  // later depths (walked or tail) whose pivot is this depth, as a slice of the query's kid list
+                               // (depth, label): their label groups are looked up when this depth is matched
+    u64 units_mask;   // [walked depths] heads of the counted-tail units whose factor becomes computable at this depth
     u32 tail_k;       // [depth 0] number of tail depths;  [tail depths] operation, see kTail*
     u32 sure_used;    // [tail depths] prefix vertices known to sit in the group (same label, query-adjacent to the pivot)
 };
+static_assert(sizeof(JoinDepth) == 64, "JoinDepth is read as four 16-byte words");
 constexpr u32 kTailMul = 0;    // multiply by the free members of the leaf's label group
 constexpr u32 kTailFall = 1;   // same pivot and label as the previous tail depth: multiply by (previous factor - 1)
 constexpr u32 kTailPairA = 2;  // two same-label leaves on different pivots: |A||B| - |A n B| (this depth and the next)
@@ -166,7 +170,7 @@ struct gpe_ctx {
     u32 V = 0, n_adj = 0, n_labels = 0, max_degree = 0;
     gpe::DevBuf d_off, d_nbr, d_label, d_deg, d_rank, d_sorted, d_member, d_vde;
     gpe::DevBuf d_nbrL, d_gtab;  // label-grouped adjacency + group directory (join)
-    gpe::DevBuf d_items, d_ready, d_jq;  // join work items, their publication flags, the queue header
+    gpe::DevBuf d_items, d_ready, d_jq, d_init, d_kids;  // exported join work items, their publication flags, the queue header, start tickets
     u32 join_epoch = 0;
     u32 b_max_nq = 0;
     u32 e = 0;
@@ -269,19 +273,21 @@ cudaError_t k3_scatter(const u32 *counts, const u32 *cand, u64 stride, u32 world
 cudaError_t k3_counts_from_offsets(const u64 *cand_off, u32 n_slots, u32 *counts, cudaStream_t s);
 cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebase, const u32 *q_offsets,
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
-                     JoinDepth *jplan, u64 *item_base, u32 rank, u32 world, cudaStream_t s);
+                     JoinDepth *jplan, void *kids /*uint2 per query vertex*/, u64 *item_base, u32 rank, u32 world,
+                     cudaStream_t s);
 // label-grouped adjacency for the join (built on the host in gpe_set_graph)
 struct JoinView {
     const u32 *label, *nbrL /* (neighbour, degree) pairs */, *gtab;
     u32 V, nl;
 };
-u32 k3_item_stride(u32 max_nq);
-cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
-                          const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world, u32 *items,
-                          u32 stride, u64 *answers, JoinQueue *jq, int sm_count, cudaStream_t s);
+u32 k3_item_stride(u32 max_nq);  // u32 words per exported work item
+// one ticket (query, position in cand[]) per start candidate of this shard; init: 8 bytes per ticket
+cudaError_t k3_init_items(u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan, const u64 *cand_off,
+                          const u64 *item_base, u32 rank, u32 world, void *init, JoinQueue *jq, int sm_count,
+                          cudaStream_t s);
 // one persistent launch: every thread runs work items (explicit-stack DFS) and exports subtrees when others starve
-cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const u64 *limits,
-                   u64 *answers, u32 *items, u64 item_cap, u32 *ready, u32 epoch, JoinQueue *jq, u32 *matches,
-                   u64 matches_cap, u64 *match_cursor, int sm_count, cudaStream_t s);
+cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
+                   const void *init, const u64 *limits, u64 *answers, u32 *items, u64 export_cap, u32 *ready, u32 epoch,
+                   JoinQueue *jq, u32 *matches, u64 matches_cap, u64 *match_cursor, int sm_count, cudaStream_t s);
 
 }  // namespace gpe

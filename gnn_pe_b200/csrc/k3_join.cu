@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                                                        const u32 *__restrict__ q_offsets,
                                                        const u32 *__restrict__ q_nbrs, const u32 *__restrict__ q_labels,
                                                        const u64 *__restrict__ cand_off, u32 *order, u32 *pivot,
-                                                       JoinDepth *jplan, u64 *item_base, u32 rank, u32 world) {
+                                                       JoinDepth *jplan, uint2 *kids, u64 *item_base, u32 rank,
+                                                       u32 world) {
     for (u32 q = threadIdx.x; q < n_queries; q += blockDim.x) {
         const u32 vb = q_vbase[q], nq = q_vbase[q + 1] - vb;
         const u32 *off = q_offsets + vb + q;  // nq + 1 local offsets
@@ -241,6 +242,9 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 jd.tail_mask = 0;
                 jd.tail_k = 0;
                 jd.sure_used = 0;
+                jd.kid_begin = 0;
+                jd.kid_count = 0;
+                jd.units_mask = 0;
                 if (i > 0) {
                     u32 pd = 0xffffffffu;  // pivot: the earliest-matched query neighbour
                     for (u32 j = off[u]; j < off[u + 1]; j++) {
@@ -271,6 +275,32 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 jplan[vb + i] = jd;
             }
             jplan[vb].tail_k = n_tail;
+            // depths that draw their candidates from the vertex matched at depth t
+            {
+                u32 at = 0;
+                for (u32 t = 0; t < nq; t++) {
+                    jplan[vb + t].kid_begin = at;
+                    for (u32 i = t + 1; i < nq; i++)
+                        if (jplan[vb + i].pivot_depth == t) kids[vb + at++] = make_uint2(i, jplan[vb + i].label);
+                    jplan[vb + t].kid_count = at - jplan[vb + t].kid_begin;
+                }
+            }
+            // counted-tail units (a Mul leaf with its Fall followers, or a PairA/PairB couple) are evaluated at the
+            // shallowest depth at which every vertex they depend on is matched
+            for (u32 i = n_walk; i < nq; i++) {
+                const u32 op = top[i];
+                if (op != kTailMul && op != kTailPairA) continue;
+                auto msb = [](u64 m) { u32 r = 0; while (m >>= 1) r++; return r; };
+                u32 dep = jplan[vb + i].pivot_depth;
+                if (jplan[vb + i].tail_mask) dep = max(dep, msb(jplan[vb + i].tail_mask));
+                if (op == kTailPairA) {
+                    dep = max(dep, jplan[vb + i + 1].pivot_depth);
+                    if (jplan[vb + i + 1].tail_mask) dep = max(dep, msb(jplan[vb + i + 1].tail_mask));
+                    for (u32 t = 1; t < n_walk; t++)
+                        if (lab[t] == lab[i]) dep = max(dep, t);  // its vertex may sit in both groups
+                }
+                jplan[vb + dep].units_mask |= 1ull << i;
+            }
             u64 total = count(start);
             items = total > rank ? (total - rank + world - 1) / world : 0;
         }
@@ -289,28 +319,38 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
 
 // ---- the join ------------------------------------------------------------------------------------------------
 //
-// Work item = a partial embedding (the first `depth` vertices of the execution order) plus a range [lo, hi)
-// of the candidate segment for the next vertex.  One THREAD runs one item as an explicit-stack DFS (stack in
-// shared memory, [level][thread] so accesses never bank-conflict); a candidate segment is the label group of
-// the pivot's adjacency (JoinGraph::nbrL / gtab), so a step touches only neighbours that already carry the
-// right label.  Label groups are short (degree / labels), which is why a warp per segment would idle.
+// Work item = a partial embedding (the first `level` vertices of the execution order) plus a range [lo, hi) of
+// the candidate segment of that level.  One THREAD runs one item as an explicit-stack DFS (stack in shared
+// memory, [level][thread] so accesses never bank-conflict); a candidate segment is the label group of the
+// pivot's adjacency (JoinGraph::nbrL / gtab), so a step touches only neighbours that already carry the right
+// label (level 0 walks the start vertex's candidate list instead).  Label groups are short (degree / labels),
+// which is why a warp per segment would idle.
 //
-// One persistent launch, two levels of load balancing (subtree sizes are heavy-tailed):
-//   * inside a warp: a lane without work takes the upper half of the shallowest unexplored sibling range of
-//     a busy lane, straight out of the donor's shared-memory stack column (no global traffic);
-//   * between warps: items live in a linear buffer addressed by ticket.  Tickets [0, n_init) are the start
-//     candidates.  Lanes claim tickets while published items are available; a warp without any busy lane
-//     registers as idle and polls the queue header with back-off; busy warps look at the header every
-//     kExportEvery iterations and, when idle warps outnumber the published items, one lane hands over the
-//     unexplored siblings of its shallowest level as new items.  JoinQueue::pending counts published items
-//     whose work has not been retired; a warp retires what it claimed whenever all its lanes run dry, so
-//     pending == 0 means the join is complete.  Exporting is only load balancing: if the buffer fills up,
-//     threads simply keep their work.
+// What a step costs is the chain of dependent loads, so everything a matched vertex c decides is looked up ONCE,
+// when c is matched, and kept on the stack:
+//   * the label groups of c that later depths draw their candidates from (S0/E0 of every depth pivoting on c) --
+//     all in c's row of gtab, fetched together; an empty group rejects c on the spot;
+//   * the counted-tail factors (below) that become computable at this depth, folded into a running product
+//     PROD(level); a zero factor rejects c.
+// Descending is then a copy of two stack words, and the deepest walked level only adds PROD to the count.
 //
 // Counting shortcut (results unchanged): the tail depths are query leaves whose only neighbour is in the walked
 // prefix.  Their completions are counted, not walked: a leaf contributes the size of its pivot's label group
 // minus the prefix vertices inside it; leaves with different labels multiply; r same-label leaves on one pivot
-// give a falling factorial; two same-label leaves on different pivots give |A||B| - |A n B|.
+// give a falling factorial; two same-label leaves on different pivots give |A||B| - |A n B|.  A factor is
+// evaluated at the shallowest depth at which every vertex it depends on is matched (JoinDepth::units_mask).
+//
+// One persistent launch, two levels of load balancing (subtree sizes are heavy-tailed):
+//   * inside a warp: a lane without work takes the upper half of the shallowest unexplored sibling range of
+//     a busy lane, straight out of the donor's shared-memory stack column (no global traffic);
+//   * between warps: tickets [0, n_init) are the start candidates (JoinInit), later tickets are exported items
+//     in a linear buffer.  Lanes claim tickets while published items are available; a warp without any busy lane
+//     registers as idle and polls the queue header with back-off; busy warps look at the header every
+//     kExportEvery iterations (the loads are issued one iteration ahead of their use) and, when idle warps
+//     outnumber the published items, one lane hands over the unexplored siblings of its shallowest level as new
+//     items.  JoinQueue::pending counts published items whose work has not been retired; a warp retires what it
+//     claimed whenever all its lanes run dry, so pending == 0 means the join is complete.  Exporting is only load
+//     balancing: if the buffer fills up, threads simply keep their work.
 //
 // Edge tests (checkEdgeExistence, graph.h:215-236) are binary searches too, but inside the label group of one
 // endpoint instead of its whole adjacency list: same answer, a fraction of the dependent loads.
@@ -321,35 +361,30 @@ struct JoinGraph {
     u32 V, nl;
 };
 
-constexpr int kItemHdr = 4;  // q, depth, lo, hi
+constexpr int kItemHdr = 8;  // q, level, lo, hi, prod (2 words), label of the start vertex, pad; then EMB | S0 | E0
 constexpr u32 kSplit = 8;
-constexpr int kDfsThreads = 256;
 constexpr u32 kExportEvery = 32;
 
+__host__ __device__ constexpr u32 item_stride(u32 m) { return kItemHdr + 3 * m; }
+
+// gtab rows and binary-search probes are random reads without reuse inside an SM: they go around L1 (ld.global.cg) so
+// that the small, hot join plan stays resident in what the stack leaves of it
 __device__ __forceinline__ void group_range(const JoinGraph &g, u32 v, u32 label, u32 &lo, u32 &hi) {
     if (label >= g.nl) { lo = hi = 0; return; }
     const u32 *row = g.gtab + (u64)v * (g.nl + 1) + label;
-    lo = row[0];
-    hi = row[1];
+    lo = __ldcg(row);
+    hi = __ldcg(row + 1);
 }
 
 // is v a member of the group nbrL[s, e)?  (ids ascending)
 __device__ __forceinline__ bool in_group(const JoinGraph &g, u32 s, u32 e, u32 v) {
     while (s < e) {
         const u32 mid = s + ((e - s) >> 1);
-        const u32 x = g.nbrL[mid].x;
+        const u32 x = __ldcg(&g.nbrL[mid].x);
         if (x == v) return true;
         if (x < v) s = mid + 1; else e = mid;
     }
     return false;
-}
-
-// edge test between a (label la) and b (label lb)
-__device__ __forceinline__ bool has_edge(const JoinGraph &g, u32 a, u32 la, u32 b, u32 lb, bool search_at_a) {
-    u32 s, e;
-    if (search_at_a) { group_range(g, a, lb, s, e); return in_group(g, s, e, b); }
-    group_range(g, b, la, s, e);
-    return in_group(g, s, e, a);
 }
 
 __device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
@@ -360,18 +395,16 @@ __device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
 __device__ __forceinline__ void st_relaxed_u32(u32 *p, u32 v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ u64 ld_relaxed_u64(const void *p) {
-    u64 v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void ld_relaxed_2xu64(const void *p, u64 &a, u64 &b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
-// depth-1 items from the start candidates of this shard (idx % world == rank)
-__global__ void __launch_bounds__(256) k3_init_items_kernel(JoinGraph g, u32 n_queries, const u32 *__restrict__ q_vbase,
+// one ticket per start candidate of this shard (idx % world == rank): (query, position in cand[])
+__global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const u32 *__restrict__ q_vbase,
                                                             const JoinDepth *__restrict__ jplan,
-                                                            const u64 *__restrict__ cand_off, const u32 *__restrict__ cand,
+                                                            const u64 *__restrict__ cand_off,
                                                             const u64 *__restrict__ item_base, u32 rank, u32 world,
-                                                            u32 *items, u32 stride, u64 *answers, JoinQueue *jq) {
+                                                            uint2 *init, JoinQueue *jq) {
     const u64 n_items = item_base[n_queries];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         jq->head = 0;
@@ -393,40 +426,35 @@ __global__ void __launch_bounds__(256) k3_init_items_kernel(JoinGraph g, u32 n_q
             u32 mid = (lo + hi) >> 1;
             if (item_base[mid] <= item) lo = mid; else hi = mid;
         }
-        const u32 q = lo, vb = q_vbase[q], nq = q_vbase[q + 1] - vb;
+        const u32 q = lo, vb = q_vbase[q];
         const u64 idx = (item - item_base[q]) * world + rank;
-        const u32 v0 = cand[cand_off[vb + jplan[vb].u] + idx];
-        u32 *it = items + item * stride;
-        it[0] = q;
-        it[1] = 1;
-        it[kItemHdr] = v0;
-        if (nq == 1) {
-            it[2] = it[3] = 0;  // nothing below the start vertex: the candidate itself is the match
-            atomicAdd((unsigned long long *)&answers[q], 1ull);
-        } else {
-            u32 s, e;
-            group_range(g, v0, jplan[vb + 1].label, s, e);  // pivot of depth 1 is always the start vertex
-            it[2] = s;
-            it[3] = e;
-        }
+        init[item] = make_uint2(q, (u32)(cand_off[vb + jplan[vb].u] + idx));
     }
 }
 
-template <int MAXNQ>
-__global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const u32 *__restrict__ q_vbase,
-                                                             const JoinDepth *__restrict__ jplan,
-                                                             const u64 *__restrict__ limits, u64 *answers, u32 *items,
-                                                             u64 item_cap, u32 *ready, u32 epoch, JoinQueue *jq,
-                                                             u32 *matches, u64 matches_cap, u64 *match_cursor) {
-    constexpr u32 stride = MAXNQ + kItemHdr;
-    extern __shared__ u32 s_stack[];  // emb | cur | end, each [MAXNQ][kDfsThreads]
-    u32 *emb = s_stack + threadIdx.x;
-    u32 *cur = emb + MAXNQ * kDfsThreads;
-    u32 *end = cur + MAXNQ * kDfsThreads;
-    const u32 *emb_warp = s_stack + (threadIdx.x & ~31u);  // this warp's 32 stack columns
-#define EMB(t) emb[(t) * kDfsThreads]
-#define CUR(t) cur[(t) * kDfsThreads]
-#define END(t) end[(t) * kDfsThreads]
+template <int M, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, const u32 *__restrict__ q_vbase,
+                                                         const JoinDepth *__restrict__ jplan,
+                                                         const uint2 *__restrict__ kids,
+                                                         const u32 *__restrict__ cand, const uint2 *__restrict__ init,
+                                                         const u64 *__restrict__ limits, u64 *answers, u32 *items,
+                                                         u64 export_cap, u32 *ready, u32 epoch, JoinQueue *jq,
+                                                         u32 *matches, u64 matches_cap, u64 *match_cursor) {
+    constexpr u32 stride = item_stride(M);
+    extern __shared__ u64 s_stack64[];  // prod [M][THREADS] u64 | emb | cur | end | s0 | e0, each [M][THREADS] u32
+    u64 *prod = s_stack64 + threadIdx.x;
+    u32 *emb = reinterpret_cast<u32 *>(s_stack64 + M * THREADS) + threadIdx.x;
+    u32 *cur = emb + M * THREADS;
+    u32 *end = cur + M * THREADS;
+    u32 *s0 = end + M * THREADS;
+    u32 *e0 = s0 + M * THREADS;
+    unsigned char *w_slot = reinterpret_cast<unsigned char *>(s_stack64 + (size_t)M * THREADS * 7 / 2) + (threadIdx.x & ~31u);
+#define PROD(t) prod[(t) * THREADS]
+#define EMB(t) emb[(t) * THREADS]
+#define CUR(t) cur[(t) * THREADS]
+#define END(t) end[(t) * THREADS]
+#define S0(t) s0[(t) * THREADS]
+#define E0(t) e0[(t) * THREADS]
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
     const u64 n_init = jq->n_init;  // written by k3_init_items_kernel, the previous launch on this stream
@@ -436,10 +464,12 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
     u32 q = 0, vb = 0, nq = 0, base = 0, d = 0, lab0 = 0, tail_at = 0;
     u32 acc_q = 0xffffffffu;
     u64 acc = 0, my_steps = 0, my_exports = 0, my_donations = 0;
-    u64 w_iters = 0, w_polls = 0;  // warp-uniform: iterations with at least one busy lane / without any
-    u32 claimed = 0, iter = 0, backoff = 32;           // warp-uniform
+    u64 w_iters = 0, w_polls = 0;                       // warp-uniform: iterations with / without a busy lane
+    u32 claimed = 0, iter = 0, backoff = 64;            // warp-uniform
     u64 h_head = 0, h_tail = n_init, h_idle = 0;        // warp-uniform cached copy of the queue header
     long long h_pending = 1;
+    u64 pf_a = 0, pf_b = 0, pf_c = 0, pf_d = 0;         // lane 0: header words in flight (issued last iteration)
+    bool pf_valid = false;                              // warp-uniform
 
     for (;;) {
         ++iter;
@@ -450,24 +480,35 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
             claimed = 0;
         }
         unsigned free_m = ~(busy | tick);
-        const bool refresh = !busy || (iter & (kExportEvery - 1)) == 0 || ((free_m | tick) && (iter & 7) == 0);
-        if (refresh) {
-            u64 a = 0, b = 0, c = 0, e = 0;
+        // ---- queue header: a warp without work reads it now; a busy warp consumes the copy it asked for one
+        //      iteration ago, so the round trip to L2 hides behind a DFS step
+        bool fresh = false;
+        if (!busy) {
             if (lane == 0) {
-                a = ld_relaxed_u64(&jq->head);
-                b = ld_relaxed_u64(&jq->tail);
-                c = ld_relaxed_u64(&jq->pending);
-                e = ld_relaxed_u64(&jq->idle);
+                ld_relaxed_2xu64(&jq->head, pf_a, pf_b);
+                ld_relaxed_2xu64(&jq->pending, pf_c, pf_d);
             }
-            h_head = __shfl_sync(kFull, a, 0);
-            h_tail = __shfl_sync(kFull, b, 0);
-            h_pending = (long long)__shfl_sync(kFull, c, 0);
-            h_idle = __shfl_sync(kFull, e, 0);
+            pf_valid = true;
+        }
+        if (pf_valid) {
+            h_head = __shfl_sync(kFull, pf_a, 0);
+            h_tail = __shfl_sync(kFull, pf_b, 0);
+            h_pending = (long long)__shfl_sync(kFull, pf_c, 0);
+            h_idle = __shfl_sync(kFull, pf_d, 0);
+            pf_valid = false;
+            fresh = true;
             if (h_pending <= 0 && !busy) break;  // join complete
+        }
+        if (busy && ((iter & (kExportEvery - 1)) == 0 || ((free_m | tick) && (iter & 7) == 0))) {
+            if (lane == 0) {
+                ld_relaxed_2xu64(&jq->head, pf_a, pf_b);
+                ld_relaxed_2xu64(&jq->pending, pf_c, pf_d);
+            }
+            pf_valid = true;
         }
         // ---- tickets: lanes without work claim published items (far from the end of the queue the cached
         //      header is good enough; near the end only a fresh one is trusted)
-        if (free_m && h_head < h_tail && (refresh || h_head + 65536 < h_tail)) {
+        if (free_m && h_head < h_tail && (fresh || h_head + 65536 < h_tail)) {
             const u64 avail = h_tail - h_head;
             const u32 n_want = (u32)min((u64)__popc(free_m), avail);
             u64 b0 = 0;
@@ -482,33 +523,65 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
         }
         // ---- ticketed lanes: start candidates are always there, exported items once their flag is up
         bool got = false;
-        if (ticketed && (ticket < n_init || (refresh && ticket < item_cap && ld_acquire_u32(ready + ticket) == epoch))) {
-            ticketed = false;
-            got = true;
-            const u32 *it = items + ticket * stride;
-            const u32 iq = it[0];
-            if (iq != acc_q) {
-                if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
-                acc = 0;
-                acc_q = iq;
-            }
-            u64 limit = limits ? limits[iq] : GPE_LIMIT_MAX;
-            if (limit == 0) limit = 1;  // the reference tests the limit only after counting a match (:851)
-            q = iq;
-            vb = q_vbase[q];
-            nq = q_vbase[q + 1] - vb;
-            base = it[1];
-            if (base < nq && it[2] < it[3] && *(volatile u64 *)&answers[q] < limit) {
-                for (u32 t = 0; t < base; t++) EMB(t) = it[kItemHdr + t];
-                lab0 = g.label[it[kItemHdr]];  // caller-supplied start candidates need not carry the query label
-                tail_at = matches ? nq : nq - jplan[vb].tail_k;  // depth at which the counting shortcut takes over
-                d = base;
-                CUR(d) = it[2];
-                END(d) = it[3];
-                have = true;
+        if (ticketed) {
+            if (ticket < n_init) {
+                ticketed = false;
+                got = true;
+                const uint2 it = init[ticket];
+                const u32 iq = it.x;
+                if (iq != acc_q) {
+                    if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
+                    acc = 0;
+                    acc_q = iq;
+                }
+                u64 limit = limits ? limits[iq] : GPE_LIMIT_MAX;
+                if (limit == 0) limit = 1;  // the reference tests the limit only after counting a match (:851)
+                q = iq;
+                vb = q_vbase[q];
+                nq = q_vbase[q + 1] - vb;
+                if (*(volatile u64 *)&answers[q] < limit) {
+                    tail_at = matches ? nq : nq - jplan[vb].tail_k;  // depth at which the counting shortcut takes over
+                    base = d = 0;
+                    CUR(0) = it.y;
+                    END(0) = it.y + 1;
+                    have = true;
+                }
+            } else if (fresh && ticket - n_init < export_cap && ld_acquire_u32(ready + (ticket - n_init)) == epoch) {
+                ticketed = false;
+                got = true;
+                const u32 *it = items + (ticket - n_init) * stride;
+                const u32 iq = it[0];
+                if (iq != acc_q) {
+                    if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
+                    acc = 0;
+                    acc_q = iq;
+                }
+                u64 limit = limits ? limits[iq] : GPE_LIMIT_MAX;
+                if (limit == 0) limit = 1;
+                q = iq;
+                vb = q_vbase[q];
+                nq = q_vbase[q + 1] - vb;
+                base = it[1];
+                if (it[2] < it[3] && *(volatile u64 *)&answers[q] < limit) {
+                    lab0 = it[6];
+                    tail_at = matches ? nq : nq - jplan[vb].tail_k;
+                    for (u32 t = 0; t < base; t++) EMB(t) = it[kItemHdr + t];
+                    for (u32 t = base; t < nq; t++) {
+                        S0(t) = it[kItemHdr + M + t];
+                        E0(t) = it[kItemHdr + 2 * M + t];
+                    }
+                    if (base) PROD(base - 1) = (u64)it[4] | ((u64)it[5] << 32);
+                    d = base;
+                    CUR(d) = it[2];
+                    END(d) = it[3];
+                    have = true;
+                }
             }
         }
-        claimed += __popc(__ballot_sync(kFull, got));
+        {
+            const unsigned got_m = __ballot_sync(kFull, got);
+            if (got_m) claimed += __popc(got_m);
+        }
         busy = __ballot_sync(kFull, have);
         if (!busy) {
             if (!registered) {
@@ -516,13 +589,13 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
                 if (lane == 0) atomicAdd(&jq->idle, 1ull);
             }
             __nanosleep(backoff);
-            if (backoff < 1024) backoff <<= 1;
+            if (backoff < 4096) backoff <<= 1;
             w_polls++;
             continue;
         }
         if (registered) {
             registered = false;
-            backoff = 32;
+            backoff = 64;
             if (lane == 0) atomicAdd(&jq->idle, 0ull - 1ull);
         }
 
@@ -543,7 +616,9 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
                 const int my_rank = is_free ? __popc(free_m & lt) : __popc(don_m & lt);
                 const bool give = rem > 0 && my_rank < n_pairs;
                 const bool take = is_free && my_rank < n_pairs;
-                const int partner = take ? (int)__fns(don_m, 0, my_rank + 1) : lane;
+                if (give) w_slot[my_rank] = (unsigned char)lane;
+                __syncwarp();
+                const int partner = take ? (int)w_slot[my_rank] : lane;
                 u32 lo_g = 0, hi_g = 0;
                 if (give) {
                     hi_g = END(l);
@@ -563,7 +638,13 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
                     }
                     q = p_q; vb = p_vb; nq = p_nq; lab0 = p_lab0; tail_at = p_tail;
                     base = d = p_l;
-                    for (u32 t = 0; t < p_l; t++) EMB(t) = emb_warp[t * kDfsThreads + partner];
+                    const int col = partner - lane;  // the donor's stack column, relative to mine
+                    for (u32 t = 0; t < p_l; t++) EMB(t) = emb[t * THREADS + col];
+                    for (u32 t = p_l; t < p_nq; t++) {
+                        S0(t) = s0[t * THREADS + col];
+                        E0(t) = e0[t * THREADS + col];
+                    }
+                    if (p_l) PROD(p_l - 1) = prod[(p_l - 1) * THREADS + col];
                     CUR(d) = p_lo;
                     END(d) = p_hi;
                     have = true;
@@ -578,104 +659,129 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
             // ---- one DFS step: test the next candidate of level d ----
             my_steps++;
             const u32 at = CUR(d);
-            const uint2 cd = g.nbrL[at];
-            const u32 c = cd.x;
             CUR(d) = at + 1;
             const JoinDepth *jd = jplan + vb + d;
-            bool ok = cd.y >= jd->deg;
-            u64 sm = jd->same_mask;  // earlier depths that can hold a vertex of this label
-            while (ok && sm) {
-                int t = __ffsll((long long)sm) - 1;
-                sm &= sm - 1;
-                ok = EMB(t) != c;
+            u32 c, cdeg;
+            if (d == 0) {  // start candidates are taken as they are (the reference never checks them, custom.h:827-830)
+                c = cand[at];
+                cdeg = 0xffffffffu;
+                lab0 = g.label[c];
+            } else {
+                const uint2 cd = g.nbrL[at];
+                c = cd.x;
+                cdeg = cd.y;
             }
-            u64 bn = jd->bn_mask;
-            while (ok && bn) {
-                int t = __ffsll((long long)bn) - 1;
-                bn &= bn - 1;
-                ok = has_edge(g, c, jd->label, EMB(t), t ? jplan[vb + t].label : lab0, cd.y <= 64);
+            // (bit scans -- ffs/popc -- run on the quarter-rate XU pipe, which a first version of this loop saturated:
+            //  the masks of the plan are walked with shifts instead)
+            bool ok = cdeg >= jd->deg || d == 0;
+            for (u32 t = 0; t < d; t++) ok = ok && EMB(t) != c;  // injective (only same-label depths could collide)
+            const u32 *row = g.gtab + (u64)c * (g.nl + 1);
+            u64 bn = d ? jd->bn_mask : 0;
+            for (u32 t = 0; ok && bn; t++, bn >>= 1) {  // the other backward neighbours: edge (c, EMB(t)) must exist
+                if (!(bn & 1)) continue;
+                const u32 lt_ = t ? jplan[vb + t].label : lab0;
+                if (cdeg <= 64) {  // search c's (short) group of label(EMB(t))
+                    ok = lt_ < g.nl && in_group(g, __ldcg(row + lt_), __ldcg(row + lt_ + 1), EMB(t));
+                } else {           // search EMB(t)'s group of c's label
+                    u32 s, e;
+                    group_range(g, EMB(t), jd->label, s, e);
+                    ok = in_group(g, s, e, c);
+                }
             }
             if (ok) {
-                if (d == nq - 1) {
-                    acc++;
-                    if (matches) {
-                        u64 pos = atomicAdd((unsigned long long *)match_cursor, 1ull);
-                        if (pos < matches_cap) {
-                            u32 *row = matches + pos * nq;
-                            for (u32 t = 0; t < d; t++) row[jplan[vb + t].u] = EMB(t);
-                            row[jd->u] = c;
-                        }
+                EMB(d) = c;
+                // (1) label groups of c that later depths draw from: all in c's gtab row, two lookups in flight
+                const uint2 *kl = kids + vb + jd->kid_begin;
+                const u32 kn = jd->kid_count;
+                for (u32 k = 0; k < kn; k += 2) {
+                    const uint2 k0 = kl[k], k1 = kl[min(k + 1, kn - 1)];  // (depth, label)
+                    const u32 i0 = k0.x, l0 = k0.y, i1 = k1.x, l1 = k1.y;
+                    u32 a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+                    if (l0 < g.nl) { a0 = __ldcg(row + l0); b0 = __ldcg(row + l0 + 1); }
+                    if (l1 < g.nl) { a1 = __ldcg(row + l1); b1 = __ldcg(row + l1 + 1); }
+                    S0(i0) = a0; E0(i0) = b0;
+                    S0(i1) = a1; E0(i1) = b1;
+                    if (a0 >= b0 || a1 >= b1) { ok = false; break; }  // nothing to draw from: no match below c
+                }
+            }
+            if (ok) {
+                // (2) counted-tail factors that close at this depth
+                u64 p = d ? PROD(d - 1) : 1;
+                u64 um = tail_at < nq ? jd->units_mask >> tail_at : 0;
+                for (u32 i = tail_at; um && p; i++, um >>= 1) {
+                    if (!(um & 1)) continue;
+                    const JoinDepth *ld = jplan + vb + i;
+                    // free members of leaf i's group: its size minus the prefix vertices inside it
+                    u32 s = S0(i), e = E0(i), used = ld->sure_used;
+                    {
+                        const u32 llab = ld->label;
+                        u64 m = ld->tail_mask;
+                        for (u32 t = 0; m; t++, m >>= 1)
+                            if ((m & 1) && (t != 0 || lab0 == llab) && in_group(g, s, e, EMB(t))) used++;
                     }
-                } else {
-                    EMB(d) = c;
-                    const u32 nd = d + 1;
-                    if (nd == tail_at) {
-                        // counting shortcut over the tail depths nd .. nq-1
-                        u64 total = 1;
-                        u32 n_run = 0, a_n = 0, a_s = 0, a_e = 0;
-                        for (u32 i = nd; i < nq && total; i++) {
-                            const JoinDepth *ld = jplan + vb + i;
-                            const u32 op = ld->tail_k;
-                            if (op == kTailFall) {
-                                n_run = n_run ? n_run - 1 : 0;
-                                total *= n_run;
-                                continue;
-                            }
-                            const u32 llab = ld->label;
-                            u32 s, e;
-                            group_range(g, EMB(ld->pivot_depth), llab, s, e);
-                            u32 used = ld->sure_used;  // prefix vertices that sit in this group
-                            u64 m = ld->tail_mask;
-                            while (m && s < e) {
-                                int t = __ffsll((long long)m) - 1;
-                                m &= m - 1;
-                                if ((t != 0 || lab0 == llab) && in_group(g, s, e, EMB(t))) used++;
-                            }
-                            const u32 n_free = (e - s) - used;
-                            if (op == kTailMul) {
-                                n_run = n_free;
-                                total *= n_free;
-                            } else if (op == kTailPairA) {
-                                a_n = n_free;
-                                a_s = s;
-                                a_e = e;
+                    const u32 n_free = (e - s) - used;
+                    if (ld->tail_k == kTailMul) {
+                        u64 f = n_free;
+                        u32 n_run = n_free;
+                        for (u32 k = i + 1; k < nq && jplan[vb + k].tail_k == kTailFall; k++) {
+                            n_run = n_run ? n_run - 1 : 0;
+                            f *= n_run;
+                        }
+                        p *= f;
+                    } else {  // kTailPairA: leaf i and leaf i+1, same label, different pivots
+                        const JoinDepth *lb = ld + 1;
+                        const u32 s2 = S0(i + 1), e2 = E0(i + 1);
+                        u32 used2 = lb->sure_used;
+                        {
+                            const u32 llab = lb->label;
+                            u64 m = lb->tail_mask;
+                            for (u32 t = 0; m; t++, m >>= 1)
+                                if ((m & 1) && (t != 0 || lab0 == llab) && in_group(g, s2, e2, EMB(t))) used2++;
+                        }
+                        const u32 n_free2 = (e2 - s2) - used2;
+                        // ordered pairs of distinct vertices: |A||B| - |A n B| over the free members; the groups are
+                        // ascending id lists, so the intersection is a merge
+                        u64 inter = 0;
+                        u32 x = s, y = s2;
+                        while (x < e && y < e2) {
+                            const u32 vx = __ldcg(&g.nbrL[x].x), vy = __ldcg(&g.nbrL[y].x);
+                            if (vx == vy) {
+                                bool is_used = false;
+                                for (u32 t = 0; t <= d; t++) is_used = is_used || EMB(t) == vx;
+                                inter += is_used ? 0 : 1;
+                                x++;
+                                y++;
+                            } else if (vx < vy) {
+                                x++;
                             } else {
-                                // ordered pairs of distinct vertices: |A||B| - |A n B| over the free members;
-                                // the groups are ascending id lists, so the intersection is a merge
-                                u64 inter = 0;
-                                u32 x = a_s, y = s;
-                                while (x < a_e && y < e) {
-                                    const u32 vx = g.nbrL[x].x, vy = g.nbrL[y].x;
-                                    if (vx == vy) {
-                                        bool is_used = false;
-                                        for (u32 t = 0; t < nd; t++) is_used = is_used || EMB(t) == vx;
-                                        inter += is_used ? 0 : 1;
-                                        x++;
-                                        y++;
-                                    } else if (vx < vy) {
-                                        x++;
-                                    } else {
-                                        y++;
-                                    }
-                                }
-                                total *= (u64)a_n * n_free - inter;
+                                y++;
                             }
                         }
-                        acc += total;
+                        p *= (u64)n_free * n_free2 - inter;
+                    }
+                }
+                if (p) {
+                    if (d + 1 == tail_at) {
+                        acc += p;
+                        if (matches) {  // tail_at == nq here: every vertex was walked
+                            u64 pos = atomicAdd((unsigned long long *)match_cursor, 1ull);
+                            if (pos < matches_cap) {
+                                u32 *out = matches + pos * nq;
+                                for (u32 t = 0; t <= d; t++) out[jplan[vb + t].u] = EMB(t);
+                            }
+                        }
                     } else {
-                        const JoinDepth *ndj = jplan + vb + nd;
-                        u32 s, e;
-                        group_range(g, EMB(ndj->pivot_depth), ndj->label, s, e);
-                        d = nd;
-                        CUR(d) = s;
-                        END(d) = e;
+                        PROD(d) = p;
+                        d++;
+                        CUR(d) = S0(d);
+                        END(d) = E0(d);
                     }
                 }
             }
         }
 
         // ---- between warps: when idle warps outnumber the published items, one lane gives work away ----
-        if ((iter & (kExportEvery - 1)) == 0 && h_idle > 0 && (long long)(h_tail - h_head) < (long long)(h_idle * 4)) {
+        if ((iter & (kExportEvery - 1)) == 1 && h_idle > 0 && (long long)(h_tail - h_head) < (long long)(h_idle * 4)) {
             u32 key = 0xffffffffu, l = 0;
             if (have && can_export) {
                 for (l = base; l <= d; l++)
@@ -684,19 +790,27 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
             const u32 best = __reduce_min_sync(kFull, key);
             if (best != 0xffffffffu && key == best) {
                 const u32 c0 = CUR(l), len = END(l) - c0, np = min(len, kSplit);
-                const u64 o = atomicAdd(&jq->tail, (unsigned long long)np);
-                if (o + np > item_cap) {
+                const u64 o = atomicAdd(&jq->tail, (unsigned long long)np) - n_init;
+                if (o + np > export_cap) {
                     can_export = false;  // those tickets are never published; their holders idle until the end
                     jq->full = 1;
                 } else {
                     atomicAdd((unsigned long long *)&jq->pending, (unsigned long long)np);
+                    const u64 pp = l ? PROD(l - 1) : 1;
                     for (u32 k = 0; k < np; k++) {
                         u32 *it = items + (o + k) * stride;
                         it[0] = q;
                         it[1] = l;
                         it[2] = c0 + (u32)((u64)len * k / np);
                         it[3] = c0 + (u32)((u64)len * (k + 1) / np);
+                        it[4] = (u32)pp;
+                        it[5] = (u32)(pp >> 32);
+                        it[6] = lab0;
                         for (u32 t = 0; t < l; t++) it[kItemHdr + t] = EMB(t);
+                        for (u32 t = l; t < nq; t++) {
+                            it[kItemHdr + M + t] = S0(t);
+                            it[kItemHdr + 2 * M + t] = E0(t);
+                        }
                     }
                     __threadfence();
                     for (u32 k = 0; k < np; k++) st_relaxed_u32(ready + o + k, epoch);
@@ -721,9 +835,12 @@ __global__ void __launch_bounds__(kDfsThreads) k3_dfs_kernel(JoinGraph g, const 
     if (lane == 0 && my_donations) atomicAdd(&jq->donations, (unsigned long long)my_donations);
     if (lane == 0 && w_iters) atomicAdd(&jq->warp_iters, (unsigned long long)w_iters);
     if (lane == 0 && w_polls) atomicAdd(&jq->idle_polls, (unsigned long long)w_polls);
+#undef PROD
 #undef EMB
 #undef CUR
 #undef END
+#undef S0
+#undef E0
 }
 
 }  // namespace
@@ -764,45 +881,51 @@ cudaError_t k3_counts_from_offsets(const u64 *cand_off, u32 n_slots, u32 *counts
 
 cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebase, const u32 *q_offsets,
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
-                     JoinDepth *jplan, u64 *item_base, u32 rank, u32 world, cudaStream_t s) {
+                     JoinDepth *jplan, void *kids, u64 *item_base, u32 rank, u32 world, cudaStream_t s) {
     k3_order_kernel<<<1, 256, 0, s>>>(n_queries, V, q_vbase, q_ebase, q_offsets, q_nbrs, q_labels, cand_off, order,
-                                      pivot, jplan, item_base, rank, world);
+                                      pivot, jplan, reinterpret_cast<uint2 *>(kids), item_base, rank, world);
     return cudaGetLastError();
 }
 
-u32 k3_item_stride(u32 max_nq) {
-    u32 m = max_nq <= 8 ? 8 : max_nq <= 16 ? 16 : max_nq <= 32 ? 32 : 64;
-    return m + kItemHdr;
-}
+static u32 join_m(u32 max_nq) { return max_nq <= 8 ? 8 : max_nq <= 16 ? 16 : max_nq <= 32 ? 32 : 64; }
 
-cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
-                          const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world, u32 *items,
-                          u32 stride, u64 *answers, JoinQueue *jq, int sm_count, cudaStream_t s) {
-    JoinGraph g{jv.label, reinterpret_cast<const uint2 *>(jv.nbrL), jv.gtab, jv.V, jv.nl};
-    k3_init_items_kernel<<<sm_count * 4, 256, 0, s>>>(g, n_queries, q_vbase, jplan, cand_off, cand, item_base, rank, world,
-                                                     items, stride, answers, jq);
+u32 k3_item_stride(u32 max_nq) { return item_stride(join_m(max_nq)); }
+
+cudaError_t k3_init_items(u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan, const u64 *cand_off,
+                          const u64 *item_base, u32 rank, u32 world, void *init, JoinQueue *jq, int sm_count,
+                          cudaStream_t s) {
+    k3_init_items_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, item_base, rank, world,
+                                                     reinterpret_cast<uint2 *>(init), jq);
     return cudaGetLastError();
 }
 
-cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const u64 *limits,
-                   u64 *answers, u32 *items, u64 item_cap, u32 *ready, u32 epoch, JoinQueue *jq, u32 *matches,
-                   u64 matches_cap, u64 *match_cursor, int sm_count, cudaStream_t s) {
+cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
+                   const void *init, const u64 *limits, u64 *answers, u32 *items, u64 export_cap, u32 *ready, u32 epoch,
+                   JoinQueue *jq, u32 *matches, u64 matches_cap, u64 *match_cursor, int sm_count, cudaStream_t s) {
     JoinGraph g{jv.label, reinterpret_cast<const uint2 *>(jv.nbrL), jv.gtab, jv.V, jv.nl};
-#define LAUNCH(M)                                                                                                     \
+    // stack bytes per thread: M x (8 + 5 x 4); threads per CTA chosen so that ~30 warps fit in an SM's shared memory
+#define LAUNCH(M, T, B)                                                                                                \
     static int per_sm_##M = 0;                                                                                        \
-    const size_t smem_##M = (size_t)3 * M * kDfsThreads * sizeof(u32);                                                \
+    const size_t smem_##M = (size_t)M * T * 28 + T;                                                                       \
     if (!per_sm_##M) {                                                                                                \
-        cudaFuncSetAttribute(k3_dfs_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_##M);           \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_##M, k3_dfs_kernel<M>, kDfsThreads, smem_##M) !=    \
+        cudaFuncSetAttribute(k3_dfs_kernel<M, T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_##M);        \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_##M, k3_dfs_kernel<M, T, B>, T, smem_##M) !=           \
                 cudaSuccess || per_sm_##M < 1)                                                                        \
             per_sm_##M = 1;                                                                                           \
     }                                                                                                                 \
-    k3_dfs_kernel<M><<<sm_count * per_sm_##M, kDfsThreads, smem_##M, s>>>(g, q_vbase, jplan, limits, answers, items,  \
-                                            item_cap, ready, epoch, jq, matches, matches_cap, match_cursor)
-    if (max_nq <= 8) { LAUNCH(8); }
-    else if (max_nq <= 16) { LAUNCH(16); }
-    else if (max_nq <= 32) { LAUNCH(32); }
-    else { LAUNCH(64); }
+    k3_dfs_kernel<M, T, B><<<sm_count * per_sm_##M, T, smem_##M, s>>>(g, q_vbase, jplan, reinterpret_cast<const uint2 *>(kids), cand, \
+                                            reinterpret_cast<const uint2 *>(init), limits, answers, items, export_cap, \
+                                            ready, epoch, jq, matches, matches_cap, match_cursor)
+    static const int geo = getenv("GPE_JOIN_GEOM") ? atoi(getenv("GPE_JOIN_GEOM")) : 0;
+    if (max_nq <= 8 && geo == 1) { LAUNCH(8, 256, 3); }
+    else if (max_nq <= 8 && geo == 2) { LAUNCH(8, 192, 5); }
+    else if (max_nq <= 8 && geo == 3) { LAUNCH(8, 128, 6); }
+    else if (max_nq <= 8 && geo == 4) { LAUNCH(8, 128, 5); }
+    else if (max_nq <= 8 && geo == 5) { LAUNCH(8, 128, 4); }
+    else if (max_nq <= 8) { LAUNCH(8, 192, 4); }
+    else if (max_nq <= 16) { LAUNCH(16, 128, 4); }
+    else if (max_nq <= 32) { LAUNCH(32, 128, 2); }
+    else { LAUNCH(64, 128, 1); }
 #undef LAUNCH
     return cudaGetLastError();
 }

@@ -29,7 +29,7 @@ for _ in range(3):
     st = ctx.stats()
     print(line("batch", st, int(a.sum())))
 rows = []
-for i, q in enumerate(queries):
+for i, q in enumerate(queries if top > 0 else []):
     ctx.query_batch([q])
     a = int(ctx.query_batch([q])[0])
     st = ctx.stats()
