@@ -279,13 +279,13 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     GPE_CUDA(c, k3_order(nq, c->V, c->d_q_vbase.as<u32>(), c->d_q_ebase.as<u32>(), c->d_q_offsets.as<u32>(),
                          c->d_q_nbrs.as<u32>(), c->d_q_labels.as<u32>(), c->d_cand_off.as<u64>(), c->d_order.as<u32>(),
                          c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_item_base.as<u64>(), rank, world,
-                         c->stream));
+                         1, c->stream));
     JoinView jv{c->d_label.as<u32>(), c->d_nbrL.as<u32>(), c->d_gtab.as<u32>(), c->V, c->n_labels};
+    // tickets [0, n_init) cover the start candidates of this shard (b_n_cand bounds their number from above);
+    // later tickets are subtrees exported by busy threads / warps
     const u32 stride = k3_item_stride(c->b_max_nq);
-    // tickets [0, n_init) are the start candidates of this shard (b_n_cand bounds their number from above);
-    // later tickets are subtrees exported by busy threads
     const u64 cap = kJoinExportBytes / (stride * sizeof(u32));
-    GPE_CUDA(c, c->d_init.reserve(std::max<u64>(c->b_n_cand, 1) * 2 * sizeof(u32)));
+    GPE_CUDA(c, c->d_init.reserve(std::max<u64>(c->b_n_cand, 1) * 2 * sizeof(u32) + ((size_t)nq + 1) * 16));
     GPE_CUDA(c, c->d_items.reserve(cap * stride * sizeof(u32)));
     if (c->d_ready.cap < cap * sizeof(u32) || c->join_epoch == 0xffffffffu) {
         GPE_CUDA(c, c->d_ready.reserve(cap * sizeof(u32)));

@@ -274,7 +274,7 @@ cudaError_t k3_counts_from_offsets(const u64 *cand_off, u32 n_slots, u32 *counts
 cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebase, const u32 *q_offsets,
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
                      JoinDepth *jplan, void *kids /*uint2 per query vertex*/, u64 *item_base, u32 rank, u32 world,
-                     cudaStream_t s);
+                     u32 per_ticket /*start candidates per ticket*/, cudaStream_t s);
 // label-grouped adjacency for the join (built on the host in gpe_set_graph)
 struct JoinView {
     const u32 *label, *nbrL /* (neighbour, degree) pairs */, *gtab;

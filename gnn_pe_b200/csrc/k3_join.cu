@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                                                        const u32 *__restrict__ q_nbrs, const u32 *__restrict__ q_labels,
                                                        const u64 *__restrict__ cand_off, u32 *order, u32 *pivot,
                                                        JoinDepth *jplan, uint2 *kids, u64 *item_base, u32 rank,
-                                                       u32 world) {
+                                                       u32 world, u32 per_ticket) {
     for (u32 q = threadIdx.x; q < n_queries; q += blockDim.x) {
         const u32 vb = q_vbase[q], nq = q_vbase[q + 1] - vb;
         const u32 *off = q_offsets + vb + q;  // nq + 1 local offsets
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
             u64 total = count(start);
             items = total > rank ? (total - rank + world - 1) / world : 0;
         }
-        item_base[q + 1] = items;  // turned into a prefix below
+        item_base[q + 1] = (items + per_ticket - 1) / per_ticket;  // tickets of this query; turned into a prefix below
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -881,9 +881,9 @@ cudaError_t k3_counts_from_offsets(const u64 *cand_off, u32 n_slots, u32 *counts
 
 cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebase, const u32 *q_offsets,
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
-                     JoinDepth *jplan, void *kids, u64 *item_base, u32 rank, u32 world, cudaStream_t s) {
+                     JoinDepth *jplan, void *kids, u64 *item_base, u32 rank, u32 world, u32 per_ticket, cudaStream_t s) {
     k3_order_kernel<<<1, 256, 0, s>>>(n_queries, V, q_vbase, q_ebase, q_offsets, q_nbrs, q_labels, cand_off, order,
-                                      pivot, jplan, reinterpret_cast<uint2 *>(kids), item_base, rank, world);
+                                      pivot, jplan, reinterpret_cast<uint2 *>(kids), item_base, rank, world, per_ticket);
     return cudaGetLastError();
 }
 
@@ -916,13 +916,7 @@ cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const Joi
     k3_dfs_kernel<M, T, B><<<sm_count * per_sm_##M, T, smem_##M, s>>>(g, q_vbase, jplan, reinterpret_cast<const uint2 *>(kids), cand, \
                                             reinterpret_cast<const uint2 *>(init), limits, answers, items, export_cap, \
                                             ready, epoch, jq, matches, matches_cap, match_cursor)
-    static const int geo = getenv("GPE_JOIN_GEOM") ? atoi(getenv("GPE_JOIN_GEOM")) : 0;
-    if (max_nq <= 8 && geo == 1) { LAUNCH(8, 256, 3); }
-    else if (max_nq <= 8 && geo == 2) { LAUNCH(8, 192, 5); }
-    else if (max_nq <= 8 && geo == 3) { LAUNCH(8, 128, 6); }
-    else if (max_nq <= 8 && geo == 4) { LAUNCH(8, 128, 5); }
-    else if (max_nq <= 8 && geo == 5) { LAUNCH(8, 128, 4); }
-    else if (max_nq <= 8) { LAUNCH(8, 192, 4); }
+    if (max_nq <= 8) { LAUNCH(8, 128, 5); }
     else if (max_nq <= 16) { LAUNCH(16, 128, 4); }
     else if (max_nq <= 32) { LAUNCH(32, 128, 2); }
     else { LAUNCH(64, 128, 1); }
