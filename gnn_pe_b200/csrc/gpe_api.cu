@@ -225,6 +225,7 @@ int run_filter(gpe_ctx *c) {
     if (rc) return rc;
     c->b_filtered = true;
     c->b_cand_external = false;
+    c->b_cand_clean = true;  // every candidate of a slot carries the slot's label, and the slot's bitmap is on the device
     return GPE_OK;
 }
 
@@ -276,16 +277,34 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     GPE_CUDA(c, cudaMemsetAsync(c->d_answers.p, 0, ((size_t)nq + 8) * sizeof(u64), c->stream));
     GPE_CUDA(c, cudaMemsetAsync(c->d_match_cursor.p, 0, 2 * sizeof(u64), c->stream));
     GPE_CUDA(c, c->d_jq.reserve(sizeof(JoinQueue)));
+    // Subtree tables are only sound when the start vertex's candidates carry its label; that holds for the
+    // filter's own candidate sets (their bitmaps are on the device), not for caller-supplied ones (gpe_refine).
+    const bool enumerate = d_matches != nullptr;
+    const bool clean_start = c->b_cand_clean && !enumerate;
+    const u32 n_slots = c->b_slots;
+    GPE_CUDA(c, c->d_tjobs.reserve(std::max<size_t>(n_slots, 1) * sizeof(TreeJob)));
+    GPE_CUDA(c, c->d_tchild.reserve(std::max<size_t>(n_slots, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_tcursor.reserve(2 * sizeof(u64)));
+    GPE_CUDA(c, c->d_tpool.reserve(std::max<u64>((u64)n_slots * c->max_class, 1) * sizeof(u64)));
+    GPE_CUDA(c, cudaMemsetAsync(c->d_tcursor.p, 0, 2 * sizeof(u64), c->stream));
     GPE_CUDA(c, k3_order(nq, c->V, c->d_q_vbase.as<u32>(), c->d_q_ebase.as<u32>(), c->d_q_offsets.as<u32>(),
                          c->d_q_nbrs.as<u32>(), c->d_q_labels.as<u32>(), c->d_cand_off.as<u64>(), c->d_order.as<u32>(),
                          c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_item_base.as<u64>(), rank, world,
-                         1, c->stream));
-    JoinView jv{c->d_label.as<u32>(), c->d_nbrL.as<u32>(), c->d_gtab.as<u32>(), c->V, c->n_labels};
-    // tickets [0, n_init) cover the start candidates of this shard (b_n_cand bounds their number from above);
-    // later tickets are subtrees exported by busy threads / warps
+                         enumerate, clean_start, c->n_labels, c->d_lcoff.as<u32>(), c->d_tjobs.as<TreeJob>(),
+                         c->d_tchild.as<u32>(), c->d_tcursor.as<u64>(), c->stream));
+    JoinView jv{c->d_label.as<u32>(), c->d_nbrL.as<u32>(), c->d_gtab.as<u32>(), c->V, c->n_labels, c->d_deg.as<u32>(),
+                c->d_lclass.as<u32>(), c->d_lpos.as<u32>(), c->d_lcoff.as<u32>(), c->d_tpool.as<u64>()};
+    u32 tree_launches = 0;
+    if (!enumerate && c->b_max_nq >= 2) {
+        tree_launches = c->b_max_nq - 1;
+        GPE_CUDA(c, k3_tree_tables(jv, n_slots, c->max_class, tree_launches, c->d_tjobs.as<TreeJob>(), c->d_tchild.as<u32>(),
+                                   clean_start ? c->d_bitmap.as<u32>() : nullptr, c->b_words, c->d_tpool.as<u64>(), c->stream));
+    }
+    // tickets [0, n_init) are the root candidates of this shard (b_n_cand + V bounds their number from above);
+    // later tickets are subtrees exported by busy threads
     const u32 stride = k3_item_stride(c->b_max_nq);
     const u64 cap = kJoinExportBytes / (stride * sizeof(u32));
-    GPE_CUDA(c, c->d_init.reserve(std::max<u64>(c->b_n_cand, 1) * 2 * sizeof(u32) + ((size_t)nq + 1) * 16));
+    GPE_CUDA(c, c->d_init.reserve((std::max<u64>(c->b_n_cand, 1) + (u64)nq * c->max_class) * 2 * sizeof(u32)));
     GPE_CUDA(c, c->d_items.reserve(cap * stride * sizeof(u32)));
     if (c->d_ready.cap < cap * sizeof(u32) || c->join_epoch == 0xffffffffu) {
         GPE_CUDA(c, c->d_ready.reserve(cap * sizeof(u32)));
@@ -294,11 +313,13 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     }
     const u32 epoch = ++c->join_epoch;
     JoinQueue *jq = c->d_jq.as<JoinQueue>();
-    GPE_CUDA(c, k3_init_items(nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
+    GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
                               c->d_item_base.as<u64>(), rank, world, c->d_init.p, jq, c->sm_count, c->stream));
     GPE_CUDA(c, k3_dfs(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_cand.as<u32>(),
                        c->d_init.p, c->d_limits.as<u64>(), answers, c->d_items.as<u32>(), cap, c->d_ready.as<u32>(), epoch,
                        jq, d_matches, matches_cap, c->d_match_cursor.as<u64>(), c->sm_count, c->stream));
+    c->stats.kernel_launches += tree_launches;
+    c->stats.join_launches += tree_launches;
     c->stats.kernel_launches += 3;
     c->stats.join_launches += 3;
     c->b_joined = true;
@@ -389,7 +410,7 @@ void gpe_destroy(gpe_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrL, &c->d_gtab, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
+    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrL, &c->d_gtab, &c->d_lclass, &c->d_lpos, &c->d_lcoff, &c->d_tjobs, &c->d_tchild, &c->d_tpool, &c->d_tcursor, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
                       &c->d_offr, &c->d_ebase, &c->d_start_rows, &c->d_scan_tmp, &c->d_tiles, &c->d_vids, &c->d_sum_u32, &c->d_sum_f64,
                       &c->d_bucket, &c->d_cursor, &c->d_qblocks, &c->d_qb_t0, &c->d_qb_prefix, &c->d_worklist,
                       &c->d_counters, &c->d_bitmap, &c->d_survivors, &c->d_chunk_cnt, &c->d_chunk_off, &c->d_cand,
@@ -504,6 +525,29 @@ int gpe_set_graph(gpe_ctx *c, uint32_t V, const uint32_t *offsets, const uint32_
                 nbrL[2 * (size_t)at + 1] = deg[w];
             }
         }
+        // label classes: vertices sorted by (label, id), the position of every vertex inside its class (the index of the
+        // join's per-query-vertex subtree tables), and the class boundaries
+        std::vector<u32> lclass(std::max<size_t>(V, 1)), lpos(std::max<size_t>(V, 1)), lcoff((size_t)nl + 2, 0);
+        for (u32 v = 0; v < V; v++) lcoff[labels[v] + 1]++;
+        c->max_class = 0;
+        for (u32 l = 0; l < nl; l++) {
+            c->max_class = std::max(c->max_class, lcoff[l + 1]);
+            lcoff[l + 1] += lcoff[l];
+        }
+        {
+            std::vector<u32> at(lcoff.begin(), lcoff.end() - 1);
+            for (u32 v = 0; v < V; v++) {
+                const u32 l = labels[v];
+                lpos[v] = at[l] - lcoff[l];
+                lclass[at[l]++] = v;
+            }
+        }
+        GPE_CUDA(c, c->d_lclass.reserve(lclass.size() * sizeof(u32)));
+        GPE_CUDA(c, c->d_lpos.reserve(lpos.size() * sizeof(u32)));
+        GPE_CUDA(c, c->d_lcoff.reserve(lcoff.size() * sizeof(u32)));
+        GPE_CUDA(c, cudaMemcpyAsync(c->d_lclass.p, lclass.data(), lclass.size() * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+        GPE_CUDA(c, cudaMemcpyAsync(c->d_lpos.p, lpos.data(), lpos.size() * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+        GPE_CUDA(c, cudaMemcpyAsync(c->d_lcoff.p, lcoff.data(), lcoff.size() * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
         GPE_CUDA(c, c->d_nbrL.reserve(nbrL.size() * sizeof(u32)));
         GPE_CUDA(c, c->d_gtab.reserve(gtab.size() * sizeof(u32)));
         GPE_CUDA(c, cudaMemcpyAsync(c->d_nbrL.p, nbrL.data(), nbrL.size() * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
@@ -803,6 +847,7 @@ int gpe_refine(gpe_ctx *c, uint32_t nq, const uint32_t *q_offsets, const uint32_
     }
     c->b_slots = nq;
     c->b_n_cand = total;
+    c->b_cand_clean = false;  // caller-supplied sets: the reference takes them as they are
     GPE_CUDA(c, c->d_cand.reserve(std::max<u64>(total, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_cand_off.reserve(((size_t)nq + 1) * sizeof(u64)));
     if (total) GPE_CUDA(c, cudaMemcpyAsync(c->d_cand.p, cand, total * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
@@ -936,6 +981,7 @@ int gpe_batch_cand_merge(gpe_ctx *c, uint32_t world, const void *d_counts, const
     if (rc) return rc;
     c->b_filtered = true;
     c->b_cand_external = true;
+    c->b_cand_clean = true;  // a union of filter outputs
     return GPE_OK;
 }
 

@@ -134,6 +134,16 @@ constexpr u32 kTailMul = 0;    // multiply by the free members of the leaf's lab
 constexpr u32 kTailFall = 1;   // same pivot and label as the previous tail depth: multiply by (previous factor - 1)
 constexpr u32 kTailPairA = 2;  // two same-label leaves on different pivots: |A||B| - |A n B| (this depth and the next)
 constexpr u32 kTailPairB = 3;
+constexpr u32 kTailTree = 4;   // a peeled subtree (all labels unique in the query): sum of its root's table over the group
+
+// One per query vertex slot: the table of a peeled subtree vertex (level 0 = none: core vertex or plain leaf).
+struct TreeJob {
+    u32 level;       // 1 + the highest level among its children (children are tabulated first)
+    u32 label, qdeg;
+    u32 start_slot;  // candidate bitmap to test (this vertex is the query's start vertex) or 0xffffffff
+    u64 table_off;   // into the table pool, one u64 per vertex of the label class
+    u32 child_begin, n_child;  // slice of the child-slot array
+};
 
 // Work queue of the join (device memory): tickets [0, n_init) are the start-candidate items, later tickets are
 // subtrees exported on demand by busy threads.
@@ -170,6 +180,9 @@ struct gpe_ctx {
     u32 V = 0, n_adj = 0, n_labels = 0, max_degree = 0;
     gpe::DevBuf d_off, d_nbr, d_label, d_deg, d_rank, d_sorted, d_member, d_vde;
     gpe::DevBuf d_nbrL, d_gtab;  // label-grouped adjacency + group directory (join)
+    gpe::DevBuf d_lclass, d_lpos, d_lcoff;  // label classes: vertices by (label, id), position in class, class offsets
+    gpe::DevBuf d_tjobs, d_tchild, d_tpool, d_tcursor;  // subtree tables of the join (jobs, child lists, value pool, pool cursor)
+    u32 max_class = 0;
     gpe::DevBuf d_items, d_ready, d_jq, d_init, d_kids;  // exported join work items, their publication flags, the queue header, start tickets
     u32 join_epoch = 0;
     u32 b_max_nq = 0;
@@ -198,7 +211,7 @@ struct gpe_ctx {
     u64 b_words = 0;       // bitmap words per slot
     u64 b_items_cap = 0, b_items_unpruned = 0;
     u64 b_n_cand = 0;
-    bool b_filtered = false, b_joined = false, b_cand_external = false;
+    bool b_filtered = false, b_joined = false, b_cand_external = false, b_cand_clean = false;
     std::vector<u32> h_q_vbase, h_q_ebase, h_q_offsets, h_q_nbrs, h_q_labels;
     std::vector<u64> h_limits;
     std::vector<u32> h_slot_query;  // slot -> query
@@ -274,17 +287,24 @@ cudaError_t k3_counts_from_offsets(const u64 *cand_off, u32 n_slots, u32 *counts
 cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebase, const u32 *q_offsets,
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
                      JoinDepth *jplan, void *kids /*uint2 per query vertex*/, u64 *item_base, u32 rank, u32 world,
-                     u32 per_ticket /*start candidates per ticket*/, cudaStream_t s);
+                     bool enumerate /*walk every vertex (matches wanted)*/, bool clean_start /*start candidates carry the
+                     query label (they come from the filter)*/, u32 n_labels, const u32 *lcoff, TreeJob *tjobs, u32 *tchild,
+                     u64 *tcursor, cudaStream_t s);
 // label-grouped adjacency for the join (built on the host in gpe_set_graph)
 struct JoinView {
     const u32 *label, *nbrL /* (neighbour, degree) pairs */, *gtab;
     u32 V, nl;
+    const u32 *deg, *lclass, *lpos, *lcoff;
+    const u64 *tpool;
 };
+// tables of the peeled subtrees, levels 1..max_level (one launch each)
+cudaError_t k3_tree_tables(const JoinView &jv, u32 n_slots, u32 max_class, u32 max_level, const TreeJob *tjobs,
+                           const u32 *tchild, const u32 *bitmap, u64 words_per_slot, u64 *tpool, cudaStream_t s);
 u32 k3_item_stride(u32 max_nq);  // u32 words per exported work item
 // one ticket (query, position in cand[]) per start candidate of this shard; init: 8 bytes per ticket
-cudaError_t k3_init_items(u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan, const u64 *cand_off,
-                          const u64 *item_base, u32 rank, u32 world, void *init, JoinQueue *jq, int sm_count,
-                          cudaStream_t s);
+cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
+                          const u64 *cand_off, const u64 *item_base, u32 rank, u32 world, void *init, JoinQueue *jq,
+                          int sm_count, cudaStream_t s);
 // one persistent launch: every thread runs work items (explicit-stack DFS) and exports subtrees when others starve
 cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
                    const void *init, const u64 *limits, u64 *answers, u32 *items, u64 export_cap, u32 *ready, u32 epoch,

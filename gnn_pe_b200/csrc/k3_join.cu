@@ -127,7 +127,9 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                                                        const u32 *__restrict__ q_nbrs, const u32 *__restrict__ q_labels,
                                                        const u64 *__restrict__ cand_off, u32 *order, u32 *pivot,
                                                        JoinDepth *jplan, uint2 *kids, u64 *item_base, u32 rank,
-                                                       u32 world, u32 per_ticket) {
+                                                       u32 world, u32 per_ticket, bool enumerate, bool clean_start,
+                                                       u32 n_labels, const u32 *__restrict__ lcoff, TreeJob *tjobs,
+                                                       u32 *tchild, u64 *tcursor) {
     for (u32 q = threadIdx.x; q < n_queries; q += blockDim.x) {
         const u32 vb = q_vbase[q], nq = q_vbase[q + 1] - vb;
         const u32 *off = q_offsets + vb + q;  // nq + 1 local offsets
@@ -168,11 +170,58 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 piv[i] = pv;
             }
 
-            // ---- the execution plan: same start vertex, query leaves counted at the end ----
+            // ---- the execution plan ---------------------------------------------------------------------------
+            // Counting mode: pendant subtrees whose vertices all carry labels that are unique in the query cannot
+            // collide with anything, so the number of ways to complete one below a matched vertex x is a function
+            // of x alone.  They are peeled off here (leaves first), tabulated per data vertex by k3_tree_tables and
+            // enter the walk as one factor at their attachment vertex.  What remains (the core: cycles, repeated
+            // labels and whatever connects them) is walked; its own query leaves are counted as before.
+            // Enumeration mode (matches wanted): nothing is peeled, the root is the start vertex.
+            u64 alive = nq >= 64 ? ~0ull : (1ull << nq) - 1;
+            u64 uniq = 0;
+            u32 par[kMaxNQ], remdeg[kMaxNQ], peel[kMaxNQ], n_peel = 0;
+            for (u32 u = 0; u < nq; u++) {
+                remdeg[u] = qdeg(u);
+                par[u] = 0xffffffffu;
+                bool un = true;
+                for (u32 v = 0; v < nq; v++) un = un && (v == u || qlab[v] != qlab[u]);
+                if (un) uniq |= 1ull << u;
+            }
+            if (!enumerate) {
+                for (int pass = 0; pass < 2; pass++) {  // the start vertex goes last, and only if its candidates are label-clean
+                    bool changed = true;
+                    while (changed) {
+                        changed = false;
+                        for (u32 u = 0; u < nq; u++) {
+                            if (!(alive >> u & 1) || remdeg[u] != 1 || !(uniq >> u & 1)) continue;
+                            if (u == start && (pass == 0 || !clean_start)) continue;
+                            u32 p = 0;
+                            for (u32 j = off[u]; j < off[u + 1]; j++)
+                                if (alive >> nbr[j] & 1) p = nbr[j];
+                            par[u] = p;
+                            alive &= ~(1ull << u);
+                            remdeg[p]--;
+                            peel[n_peel++] = u;
+                            changed = true;
+                        }
+                    }
+                }
+            }
+            const u32 nK = nq - n_peel;
+            const bool root_is_start = alive >> start & 1;
+            u32 root = start;
+            if (!root_is_start) {  // the walk starts at the core vertex with the smallest label class
+                u32 best = 0xffffffffu;
+                for (u32 u = 0; u < nq; u++) {
+                    if (!(alive >> u & 1)) continue;
+                    const u32 sz = qlab[u] < n_labels ? lcoff[qlab[u] + 1] - lcoff[qlab[u]] : 0;
+                    if (sz < best || (sz == best && qdeg(u) > qdeg(root))) { best = sz; root = u; }
+                }
+            }
             u64 tail_set = 0;
             u32 tail_list[kMaxNQ], n_tail = 0;
-            for (u32 u = 0; u < nq && nq >= 3 && n_tail + 2 < nq; u++) {
-                if (u == start || qdeg(u) != 1) continue;
+            for (u32 u = 0; u < nq && nK >= 3 && n_tail + 2 < nK; u++) {
+                if (u == root || !(alive >> u & 1) || qdeg(u) != 1) continue;
                 const u32 pv = nbr[off[u]];
                 u32 r = 0, p0 = 0;
                 bool mixed = false;
@@ -189,22 +238,23 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                     tail_set |= 1ull << u;
                 }
             }
-            const u32 n_walk = nq - n_tail;
+            const u32 n_walk = nK - n_tail;
             u32 xo[kMaxNQ], depth_of[kMaxNQ], lab[kMaxNQ], top[kMaxNQ];
-            xo[0] = start;
+            xo[0] = root;
             visited = 0;
             adjacent = 0;
-            mark(start);
+            mark(root);
             for (u32 i = 1; i < n_walk; i++) {
                 u32 next = 0, best = V + 1;
                 for (u32 u = 0; u < nq; u++) {
-                    if ((visited >> u & 1) || !(adjacent >> u & 1) || (tail_set >> u & 1)) continue;
+                    if ((visited >> u & 1) || !(adjacent >> u & 1) || (tail_set >> u & 1) || !(alive >> u & 1)) continue;
                     if (count(u) < best) { best = count(u); next = u; }
                     else if (count(u) == best && qdeg(u) > qdeg(next)) next = u;
                 }
                 mark(next);
                 xo[i] = next;
             }
+            u32 n_exec = n_walk;
             {   // tail depths, grouped by label
                 u64 placed = 0;
                 u32 at = n_walk;
@@ -228,9 +278,51 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                         }
                     }
                 }
+                n_exec = at;
             }
-            for (u32 i = 0; i < nq; i++) { depth_of[xo[i]] = i; lab[i] = qlab[xo[i]]; }
-            for (u32 i = 0; i < nq; i++) {
+            // peeled subtrees: children lists, tables (a vertex needs one unless it is a plain leaf), unit depths
+            u32 n_child[kMaxNQ], tlevel[kMaxNQ];
+            for (u32 u = 0; u < nq; u++) { n_child[u] = 0; tlevel[u] = 0; }
+            {
+                u32 at = 0;
+                for (u32 u = 0; u < nq; u++) {  // children of u, contiguous in tchild
+                    u32 first = at;
+                    for (u32 k = 0; k < n_peel; k++)
+                        if (par[peel[k]] == u) tchild[vb + at++] = vb + peel[k];
+                    n_child[u] = at - first;
+                    tjobs[vb + u].child_begin = vb + first;
+                    tjobs[vb + u].n_child = at - first;
+                }
+            }
+            for (u32 k = 0; k < n_peel; k++) {  // peel order: children before parents
+                const u32 w = peel[k];
+                u32 lvl = 0;
+                if (n_child[w] || w == start) {
+                    lvl = 1;
+                    for (u32 k2 = 0; k2 < k; k2++)
+                        if (par[peel[k2]] == w && tlevel[peel[k2]] + 1 > lvl) lvl = tlevel[peel[k2]] + 1;
+                }
+                tlevel[w] = lvl;
+                TreeJob &tj = tjobs[vb + w];
+                tj.level = lvl;
+                tj.label = qlab[w];
+                tj.qdeg = qdeg(w);
+                tj.start_slot = w == start ? vb + start : 0xffffffffu;
+                tj.table_off = 0;
+                if (lvl) {
+                    const u32 sz = qlab[w] < n_labels ? lcoff[qlab[w] + 1] - lcoff[qlab[w]] : 0;
+                    tj.table_off = atomicAdd((unsigned long long *)tcursor, (unsigned long long)sz);
+                }
+                if (alive >> par[w] & 1) {  // attached to the core: a unit of the counted tail
+                    xo[n_exec] = w;
+                    top[n_exec++] = lvl ? kTailTree : kTailMul;
+                }
+            }
+            for (u32 u = 0; u < nq; u++)
+                if (alive >> u & 1) tjobs[vb + u].level = 0;
+            for (u32 u = 0; u < nq; u++) depth_of[u] = 0xffffffffu;
+            for (u32 i = 0; i < n_exec; i++) { depth_of[xo[i]] = i; lab[i] = qlab[xo[i]]; }
+            for (u32 i = 0; i < n_exec; i++) {
                 const u32 u = xo[i];
                 JoinDepth jd;
                 jd.u = u;
@@ -264,35 +356,41 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 }
                 if (i >= n_walk) {
                     jd.tail_k = top[i];
-                    const u32 pvu = xo[jd.pivot_depth];
-                    for (u32 t = 0; t < n_walk; t++) {
-                        if (t == jd.pivot_depth) continue;
-                        if (t == 0) { jd.tail_mask |= 1ull; continue; }  // its data label is only known at run time
-                        if (lab[t] != jd.label) continue;
-                        if (q_edge(off, nbr, xo[t], pvu)) jd.sure_used++; else jd.tail_mask |= 1ull << t;
+                    jd.bn_mask = 0;
+                    if (top[i] == kTailTree) {
+                        jd.bn_mask = tjobs[vb + u].table_off;  // (a tail depth has no backward neighbours: the field carries the table)
+                    } else {
+                        const u32 pvu = xo[jd.pivot_depth];
+                        for (u32 t = 0; t < n_walk; t++) {
+                            if (t == jd.pivot_depth) continue;
+                            if (t == 0 && root_is_start && !clean_start) { jd.tail_mask |= 1ull; continue; }  // its data label is only known at run time
+                            if (lab[t] != jd.label) continue;
+                            if (q_edge(off, nbr, xo[t], pvu)) jd.sure_used++; else jd.tail_mask |= 1ull << t;
+                        }
                     }
                 }
                 jplan[vb + i] = jd;
             }
-            jplan[vb].tail_k = n_tail;
-            // depths that draw their candidates from the vertex matched at depth t
-            {
+            jplan[vb].tail_k = n_exec - n_walk;              // [depth 0] number of tail depths
+            jplan[vb].sure_used = n_exec;                    // [depth 0] depths of the execution plan
+            jplan[vb].tail_mask = root_is_start ? 0 : 1;     // [depth 0] the walk starts from: 0 the start vertex's candidate list, 1 the root's label class
+            {   // depths that draw their candidates from the vertex matched at depth t, as (depth, label) lists
                 u32 at = 0;
-                for (u32 t = 0; t < nq; t++) {
+                for (u32 t = 0; t < n_exec; t++) {
                     jplan[vb + t].kid_begin = at;
-                    for (u32 i = t + 1; i < nq; i++)
+                    for (u32 i = t + 1; i < n_exec; i++)
                         if (jplan[vb + i].pivot_depth == t) kids[vb + at++] = make_uint2(i, jplan[vb + i].label);
                     jplan[vb + t].kid_count = at - jplan[vb + t].kid_begin;
                 }
             }
-            // counted-tail units (a Mul leaf with its Fall followers, or a PairA/PairB couple) are evaluated at the
-            // shallowest depth at which every vertex they depend on is matched
-            for (u32 i = n_walk; i < nq; i++) {
+            // counted-tail units (a Mul leaf with its Fall followers, a PairA/PairB couple, a subtree table) are
+            // evaluated at the shallowest depth at which every vertex they depend on is matched
+            for (u32 i = n_walk; i < n_exec; i++) {
                 const u32 op = top[i];
-                if (op != kTailMul && op != kTailPairA) continue;
+                if (op == kTailFall || op == kTailPairB) continue;
                 auto msb = [](u64 m) { u32 r = 0; while (m >>= 1) r++; return r; };
                 u32 dep = jplan[vb + i].pivot_depth;
-                if (jplan[vb + i].tail_mask) dep = max(dep, msb(jplan[vb + i].tail_mask));
+                if (op != kTailTree && jplan[vb + i].tail_mask) dep = max(dep, msb(jplan[vb + i].tail_mask));
                 if (op == kTailPairA) {
                     dep = max(dep, jplan[vb + i + 1].pivot_depth);
                     if (jplan[vb + i + 1].tail_mask) dep = max(dep, msb(jplan[vb + i + 1].tail_mask));
@@ -301,7 +399,9 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 }
                 jplan[vb + dep].units_mask |= 1ull << i;
             }
-            u64 total = count(start);
+            u64 total;
+            if (root_is_start) total = count(start);
+            else total = qlab[root] < n_labels ? lcoff[qlab[root] + 1] - lcoff[qlab[root]] : 0;
             items = total > rank ? (total - rank + world - 1) / world : 0;
         }
         item_base[q + 1] = (items + per_ticket - 1) / per_ticket;  // tickets of this query; turned into a prefix below
@@ -359,6 +459,11 @@ struct JoinGraph {
     const uint2 *nbrL;  // adjacency grouped by neighbour label, ascending id inside a group: (neighbour, its degree)
     const u32 *gtab;    // V x (nl+1): start of every label group of every vertex (absolute, into nbrL)
     u32 V, nl;
+    const u32 *deg;     // V
+    const u32 *lclass;  // vertices by (label, id)
+    const u32 *lpos;    // position of a vertex inside its label class
+    const u32 *lcoff;   // nl + 1 class offsets into lclass
+    const u64 *tpool;   // subtree tables (k3_tree_tables), indexed [table offset + lpos]
 };
 
 constexpr int kItemHdr = 8;  // q, level, lo, hi, prod (2 words), label of the start vertex, pad; then EMB | S0 | E0
@@ -399,10 +504,11 @@ __device__ __forceinline__ void ld_relaxed_2xu64(const void *p, u64 &a, u64 &b) 
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
-// one ticket per start candidate of this shard (idx % world == rank): (query, position in cand[])
+// one ticket per root candidate of this shard (idx % world == rank): (query, position in cand[] or in lclass[])
 __global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const u32 *__restrict__ q_vbase,
                                                             const JoinDepth *__restrict__ jplan,
                                                             const u64 *__restrict__ cand_off,
+                                                            const u32 *__restrict__ lcoff, u32 n_labels,
                                                             const u64 *__restrict__ item_base, u32 rank, u32 world,
                                                             uint2 *init, JoinQueue *jq) {
     const u64 n_items = item_base[n_queries];
@@ -428,7 +534,45 @@ __global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const
         }
         const u32 q = lo, vb = q_vbase[q];
         const u64 idx = (item - item_base[q]) * world + rank;
-        init[item] = make_uint2(q, (u32)(cand_off[vb + jplan[vb].u] + idx));
+        const JoinDepth &j0 = jplan[vb];
+        const u64 first = j0.tail_mask ? (j0.label < n_labels ? lcoff[j0.label] : 0) : cand_off[vb + j0.u];
+        init[item] = make_uint2(q, (u32)(first + idx));
+    }
+}
+
+// ---- subtree tables ---------------------------------------------------------------------------------------------
+// T_w[y], for a peeled query vertex w and every data vertex y of w's label: the number of ways to map the subtree
+// hanging below w when w -> y (1 for a leaf; the start vertex also requires y in C(start)):
+//     T_w[y] = [deg(y) >= deg(w)] * prod over children c of w ( sum over z in N(y), label(z) = label(c) of T_c[z] ).
+// All labels of a peeled subtree are unique in the query, so these maps are injective and disjoint from the rest.
+// One launch per table level (children before parents); blockIdx.y = query vertex slot.
+__global__ void __launch_bounds__(256) k3_tree_tables_kernel(JoinGraph g, const TreeJob *__restrict__ tjobs,
+                                                             const u32 *__restrict__ tchild, u32 level,
+                                                             const u32 *__restrict__ bitmap, u64 words_per_slot,
+                                                             u64 *tpool) {
+    const TreeJob job = tjobs[blockIdx.y];
+    if (job.level != level || job.label >= g.nl) return;
+    const u32 c0 = g.lcoff[job.label], n = g.lcoff[job.label + 1] - c0;
+    for (u32 pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
+        const u32 y = g.lclass[c0 + pos];
+        u64 val = g.deg[y] >= job.qdeg ? 1 : 0;
+        if (val && job.start_slot != 0xffffffffu)
+            val = bitmap[(u64)job.start_slot * words_per_slot + (y >> 5)] >> (y & 31) & 1;
+        const u32 *row = g.gtab + (u64)y * (g.nl + 1);
+        for (u32 k = 0; k < job.n_child && val; k++) {
+            const TreeJob cj = tjobs[tchild[job.child_begin + k]];
+            u64 sum = 0;
+            if (cj.label < g.nl) {
+                const u32 s = row[cj.label], e = row[cj.label + 1];
+                if (cj.level == 0) {
+                    sum = e - s;  // plain leaves: every neighbour of the label (its degree is >= 1)
+                } else {
+                    for (u32 x = s; x < e; x++) sum += tpool[cj.table_off + g.lpos[g.nbrL[x].x]];
+                }
+            }
+            val *= sum;
+        }
+        tpool[job.table_off + pos] = val;
     }
 }
 
@@ -538,7 +682,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 if (limit == 0) limit = 1;  // the reference tests the limit only after counting a match (:851)
                 q = iq;
                 vb = q_vbase[q];
-                nq = q_vbase[q + 1] - vb;
+                nq = jplan[vb].sure_used;  // depths of the execution plan (peeled subtrees are not walked)
                 if (*(volatile u64 *)&answers[q] < limit) {
                     tail_at = matches ? nq : nq - jplan[vb].tail_k;  // depth at which the counting shortcut takes over
                     base = d = 0;
@@ -560,7 +704,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 if (limit == 0) limit = 1;
                 q = iq;
                 vb = q_vbase[q];
-                nq = q_vbase[q + 1] - vb;
+                nq = jplan[vb].sure_used;
                 base = it[1];
                 if (it[2] < it[3] && *(volatile u64 *)&answers[q] < limit) {
                     lab0 = it[6];
@@ -662,10 +806,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             CUR(d) = at + 1;
             const JoinDepth *jd = jplan + vb + d;
             u32 c, cdeg;
-            if (d == 0) {  // start candidates are taken as they are (the reference never checks them, custom.h:827-830)
-                c = cand[at];
-                cdeg = 0xffffffffu;
-                lab0 = g.label[c];
+            if (d == 0) {
+                if (jd->tail_mask) {  // the walk starts from the root's label class (the start vertex was peeled)
+                    c = g.lclass[at];
+                    cdeg = g.deg[c];
+                    lab0 = jd->label;
+                } else {  // start candidates are taken as they are (the reference never checks them, custom.h:827-830)
+                    c = cand[at];
+                    cdeg = 0xffffffffu;
+                    lab0 = g.label[c];
+                }
             } else {
                 const uint2 cd = g.nbrL[at];
                 c = cd.x;
@@ -673,7 +823,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             }
             // (bit scans -- ffs/popc -- run on the quarter-rate XU pipe, which a first version of this loop saturated:
             //  the masks of the plan are walked with shifts instead)
-            bool ok = cdeg >= jd->deg || d == 0;
+            bool ok = cdeg >= jd->deg;
             for (u32 t = 0; t < d; t++) ok = ok && EMB(t) != c;  // injective (only same-label depths could collide)
             const u32 *row = g.gtab + (u64)c * (g.nl + 1);
             u64 bn = d ? jd->bn_mask : 0;
@@ -711,6 +861,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 for (u32 i = tail_at; um && p; i++, um >>= 1) {
                     if (!(um & 1)) continue;
                     const JoinDepth *ld = jplan + vb + i;
+                    if (ld->tail_k == kTailTree) {  // a peeled subtree: sum its root's table over the group
+                        const u64 *tab = g.tpool + ld->bn_mask;
+                        u64 f = 0;
+                        for (u32 x = S0(i), e = E0(i); x < e; x++) f += __ldcg(tab + g.lpos[g.nbrL[x].x]);
+                        p *= f;
+                        continue;
+                    }
                     // free members of leaf i's group: its size minus the prefix vertices inside it
                     u32 s = S0(i), e = E0(i), used = ld->sure_used;
                     {
@@ -881,9 +1038,11 @@ cudaError_t k3_counts_from_offsets(const u64 *cand_off, u32 n_slots, u32 *counts
 
 cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebase, const u32 *q_offsets,
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
-                     JoinDepth *jplan, void *kids, u64 *item_base, u32 rank, u32 world, u32 per_ticket, cudaStream_t s) {
+                     JoinDepth *jplan, void *kids, u64 *item_base, u32 rank, u32 world, bool enumerate, bool clean_start,
+                     u32 n_labels, const u32 *lcoff, TreeJob *tjobs, u32 *tchild, u64 *tcursor, cudaStream_t s) {
     k3_order_kernel<<<1, 256, 0, s>>>(n_queries, V, q_vbase, q_ebase, q_offsets, q_nbrs, q_labels, cand_off, order,
-                                      pivot, jplan, reinterpret_cast<uint2 *>(kids), item_base, rank, world, per_ticket);
+                                      pivot, jplan, reinterpret_cast<uint2 *>(kids), item_base, rank, world, 1, enumerate,
+                                      clean_start, n_labels, lcoff, tjobs, tchild, tcursor);
     return cudaGetLastError();
 }
 
@@ -891,18 +1050,33 @@ static u32 join_m(u32 max_nq) { return max_nq <= 8 ? 8 : max_nq <= 16 ? 16 : max
 
 u32 k3_item_stride(u32 max_nq) { return item_stride(join_m(max_nq)); }
 
-cudaError_t k3_init_items(u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan, const u64 *cand_off,
-                          const u64 *item_base, u32 rank, u32 world, void *init, JoinQueue *jq, int sm_count,
-                          cudaStream_t s) {
-    k3_init_items_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, item_base, rank, world,
-                                                     reinterpret_cast<uint2 *>(init), jq);
+static JoinGraph join_graph(const JoinView &jv) {
+    return JoinGraph{jv.label, reinterpret_cast<const uint2 *>(jv.nbrL), jv.gtab, jv.V, jv.nl, jv.deg, jv.lclass, jv.lpos,
+                     jv.lcoff, jv.tpool};
+}
+
+cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
+                          const u64 *cand_off, const u64 *item_base, u32 rank, u32 world, void *init, JoinQueue *jq,
+                          int sm_count, cudaStream_t s) {
+    k3_init_items_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, jv.lcoff, jv.nl, item_base,
+                                                     rank, world, reinterpret_cast<uint2 *>(init), jq);
+    return cudaGetLastError();
+}
+
+cudaError_t k3_tree_tables(const JoinView &jv, u32 n_slots, u32 max_class, u32 max_level, const TreeJob *tjobs,
+                           const u32 *tchild, const u32 *bitmap, u64 words_per_slot, u64 *tpool, cudaStream_t s) {
+    if (n_slots == 0 || max_class == 0) return cudaSuccess;
+    JoinGraph g = join_graph(jv);
+    dim3 grid(std::min<u32>((max_class + 255) / 256, 64), n_slots);
+    for (u32 level = 1; level <= max_level; level++)
+        k3_tree_tables_kernel<<<grid, 256, 0, s>>>(g, tjobs, tchild, level, bitmap, words_per_slot, tpool);
     return cudaGetLastError();
 }
 
 cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
                    const void *init, const u64 *limits, u64 *answers, u32 *items, u64 export_cap, u32 *ready, u32 epoch,
                    JoinQueue *jq, u32 *matches, u64 matches_cap, u64 *match_cursor, int sm_count, cudaStream_t s) {
-    JoinGraph g{jv.label, reinterpret_cast<const uint2 *>(jv.nbrL), jv.gtab, jv.V, jv.nl};
+    JoinGraph g = join_graph(jv);
     // stack bytes per thread: M x (8 + 5 x 4); threads per CTA chosen so that ~30 warps fit in an SM's shared memory
 #define LAUNCH(M, T, B)                                                                                                \
     static int per_sm_##M = 0;                                                                                        \
