@@ -121,7 +121,7 @@ struct alignas(16) JoinDepth {
     u32 deg;
     u32 pivot_depth;  // depth at which the pivot (first earlier query neighbour) was matched
     u64 bn_mask;      // depths of the other backward neighbours (generateBN, custom.h:724-755)
-    u64 same_mask;    // earlier depths whose vertex may equal a candidate of this depth (same label; depth 0 always)
+    u64 tree_off;     // table of everything that hangs below this vertex in peeled subtrees (pool offset), or kNoTree
     u64 tail_mask;    // [tail depths] prefix depths that may sit in this leaf's label group and need an edge test
     u32 kid_begin, kid_count;  // later depths (walked or tail) whose pivot is this depth, as a slice of the query's kid list
                                // (depth, label): their label groups are looked up when this depth is matched
@@ -134,15 +134,15 @@ constexpr u32 kTailMul = 0;    // multiply by the free members of the leaf's lab
 constexpr u32 kTailFall = 1;   // same pivot and label as the previous tail depth: multiply by (previous factor - 1)
 constexpr u32 kTailPairA = 2;  // two same-label leaves on different pivots: |A||B| - |A n B| (this depth and the next)
 constexpr u32 kTailPairB = 3;
-constexpr u32 kTailTree = 4;   // a peeled subtree (all labels unique in the query): sum of its root's table over the group
+constexpr u64 kNoTree = ~0ull;
 
-// One per query vertex slot: the table of a peeled subtree vertex (level 0 = none: core vertex or plain leaf).
+// One per query vertex slot: the table of a vertex with peeled children (level 0 = none).
 struct TreeJob {
-    u32 level;       // 1 + the highest level among its children (children are tabulated first)
+    u32 level;       // 1 + the highest level among its peeled children (children are tabulated first)
     u32 label, qdeg;
-    u32 start_slot;  // candidate bitmap to test (this vertex is the query's start vertex) or 0xffffffff
+    u32 start_slot;  // this vertex is the peeled start vertex: candidate bitmap its matches must be in, else 0xffffffff
     u64 table_off;   // into the table pool, one u64 per vertex of the label class
-    u32 child_begin, n_child;  // slice of the child-slot array
+    u32 child_begin, n_child;  // peeled children: slice of the child-slot array
 };
 
 // Work queue of the join (device memory): tickets [0, n_init) are the start-candidate items, later tickets are

@@ -187,14 +187,16 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 for (u32 v = 0; v < nq; v++) un = un && (v == u || qlab[v] != qlab[u]);
                 if (un) uniq |= 1ull << u;
             }
-            if (!enumerate) {
-                for (int pass = 0; pass < 2; pass++) {  // the start vertex goes last, and only if its candidates are label-clean
+            // (a start candidate of the wrong label -- possible with caller-supplied sets, which the reference takes as
+            //  they are -- could collide with a peeled vertex: no peeling then)
+            if (!enumerate && clean_start) {
+                for (int pass = 0; pass < 2; pass++) {  // the start vertex goes last
                     bool changed = true;
                     while (changed) {
                         changed = false;
                         for (u32 u = 0; u < nq; u++) {
                             if (!(alive >> u & 1) || remdeg[u] != 1 || !(uniq >> u & 1)) continue;
-                            if (u == start && (pass == 0 || !clean_start)) continue;
+                            if (u == start && pass == 0) continue;
                             u32 p = 0;
                             for (u32 j = off[u]; j < off[u + 1]; j++)
                                 if (alive >> nbr[j] & 1) p = nbr[j];
@@ -280,46 +282,40 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 }
                 n_exec = at;
             }
-            // peeled subtrees: children lists, tables (a vertex needs one unless it is a plain leaf), unit depths
-            u32 n_child[kMaxNQ], tlevel[kMaxNQ];
-            for (u32 u = 0; u < nq; u++) { n_child[u] = 0; tlevel[u] = 0; }
+            // peeled subtrees: every vertex with peeled children gets a table over its own label class (k3_tree_tables);
+            // the core vertices' tables are the factors of the walk
+            u32 tlevel[kMaxNQ];
             {
                 u32 at = 0;
-                for (u32 u = 0; u < nq; u++) {  // children of u, contiguous in tchild
-                    u32 first = at;
+                for (u32 u = 0; u < nq; u++) {  // peeled children of u, contiguous in tchild
+                    const u32 first = at;
                     for (u32 k = 0; k < n_peel; k++)
                         if (par[peel[k]] == u) tchild[vb + at++] = vb + peel[k];
-                    n_child[u] = at - first;
-                    tjobs[vb + u].child_begin = vb + first;
-                    tjobs[vb + u].n_child = at - first;
+                    TreeJob &tj = tjobs[vb + u];
+                    tj.child_begin = vb + first;
+                    tj.n_child = at - first;
+                    tj.level = 0;
+                    tj.label = qlab[u];
+                    tj.qdeg = qdeg(u);
+                    tj.start_slot = (u == start && !(alive >> u & 1)) ? vb + start : 0xffffffffu;
+                    tj.table_off = 0;
+                    tlevel[u] = 0;
                 }
             }
-            for (u32 k = 0; k < n_peel; k++) {  // peel order: children before parents
-                const u32 w = peel[k];
-                u32 lvl = 0;
-                if (n_child[w] || w == start) {
-                    lvl = 1;
-                    for (u32 k2 = 0; k2 < k; k2++)
-                        if (par[peel[k2]] == w && tlevel[peel[k2]] + 1 > lvl) lvl = tlevel[peel[k2]] + 1;
-                }
-                tlevel[w] = lvl;
-                TreeJob &tj = tjobs[vb + w];
+            auto make_table = [&](u32 v) {  // children are final (peel order: children before parents)
+                TreeJob &tj = tjobs[vb + v];
+                if (!tj.n_child) return;
+                u32 lvl = 1;
+                for (u32 k = 0; k < n_peel; k++)
+                    if (par[peel[k]] == v && tlevel[peel[k]] + 1 > lvl) lvl = tlevel[peel[k]] + 1;
+                tlevel[v] = lvl;
                 tj.level = lvl;
-                tj.label = qlab[w];
-                tj.qdeg = qdeg(w);
-                tj.start_slot = w == start ? vb + start : 0xffffffffu;
-                tj.table_off = 0;
-                if (lvl) {
-                    const u32 sz = qlab[w] < n_labels ? lcoff[qlab[w] + 1] - lcoff[qlab[w]] : 0;
-                    tj.table_off = atomicAdd((unsigned long long *)tcursor, (unsigned long long)sz);
-                }
-                if (alive >> par[w] & 1) {  // attached to the core: a unit of the counted tail
-                    xo[n_exec] = w;
-                    top[n_exec++] = lvl ? kTailTree : kTailMul;
-                }
-            }
+                const u32 sz = qlab[v] < n_labels ? lcoff[qlab[v] + 1] - lcoff[qlab[v]] : 0;
+                tj.table_off = atomicAdd((unsigned long long *)tcursor, (unsigned long long)sz);
+            };
+            for (u32 k = 0; k < n_peel; k++) make_table(peel[k]);
             for (u32 u = 0; u < nq; u++)
-                if (alive >> u & 1) tjobs[vb + u].level = 0;
+                if (alive >> u & 1) make_table(u);
             for (u32 u = 0; u < nq; u++) depth_of[u] = 0xffffffffu;
             for (u32 i = 0; i < n_exec; i++) { depth_of[xo[i]] = i; lab[i] = qlab[xo[i]]; }
             for (u32 i = 0; i < n_exec; i++) {
@@ -330,7 +326,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 jd.deg = qdeg(u);
                 jd.pivot_depth = 0;
                 jd.bn_mask = 0;
-                jd.same_mask = 0;
+                jd.tree_off = tjobs[vb + u].level ? tjobs[vb + u].table_off : kNoTree;
                 jd.tail_mask = 0;
                 jd.tail_k = 0;
                 jd.sure_used = 0;
@@ -348,25 +344,15 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                         const u32 dw = depth_of[nbr[j]];
                         if (dw < i && dw != jd.pivot_depth) jd.bn_mask |= 1ull << dw;
                     }
-                    // depths whose vertex can equal a candidate of this depth: same query label; depth 0 always,
-                    // because caller-supplied start candidates (gpe_refine) are not label-checked
-                    jd.same_mask = 1ull;
-                    for (u32 j = 1; j < i; j++)
-                        if (lab[j] == jd.label) jd.same_mask |= 1ull << j;
                 }
                 if (i >= n_walk) {
                     jd.tail_k = top[i];
-                    jd.bn_mask = 0;
-                    if (top[i] == kTailTree) {
-                        jd.bn_mask = tjobs[vb + u].table_off;  // (a tail depth has no backward neighbours: the field carries the table)
-                    } else {
-                        const u32 pvu = xo[jd.pivot_depth];
-                        for (u32 t = 0; t < n_walk; t++) {
-                            if (t == jd.pivot_depth) continue;
-                            if (t == 0 && root_is_start && !clean_start) { jd.tail_mask |= 1ull; continue; }  // its data label is only known at run time
-                            if (lab[t] != jd.label) continue;
-                            if (q_edge(off, nbr, xo[t], pvu)) jd.sure_used++; else jd.tail_mask |= 1ull << t;
-                        }
+                    const u32 pvu = xo[jd.pivot_depth];
+                    for (u32 t = 0; t < n_walk; t++) {
+                        if (t == jd.pivot_depth) continue;
+                        if (t == 0 && root_is_start && !clean_start) { jd.tail_mask |= 1ull; continue; }  // its data label is only known at run time
+                        if (lab[t] != jd.label) continue;
+                        if (q_edge(off, nbr, xo[t], pvu)) jd.sure_used++; else jd.tail_mask |= 1ull << t;
                     }
                 }
                 jplan[vb + i] = jd;
@@ -383,14 +369,14 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                     jplan[vb + t].kid_count = at - jplan[vb + t].kid_begin;
                 }
             }
-            // counted-tail units (a Mul leaf with its Fall followers, a PairA/PairB couple, a subtree table) are
+            // counted-tail units (a Mul leaf with its Fall followers, or a PairA/PairB couple) are
             // evaluated at the shallowest depth at which every vertex they depend on is matched
             for (u32 i = n_walk; i < n_exec; i++) {
                 const u32 op = top[i];
                 if (op == kTailFall || op == kTailPairB) continue;
                 auto msb = [](u64 m) { u32 r = 0; while (m >>= 1) r++; return r; };
                 u32 dep = jplan[vb + i].pivot_depth;
-                if (op != kTailTree && jplan[vb + i].tail_mask) dep = max(dep, msb(jplan[vb + i].tail_mask));
+                if (jplan[vb + i].tail_mask) dep = max(dep, msb(jplan[vb + i].tail_mask));
                 if (op == kTailPairA) {
                     dep = max(dep, jplan[vb + i + 1].pivot_depth);
                     if (jplan[vb + i + 1].tail_mask) dep = max(dep, msb(jplan[vb + i + 1].tail_mask));
@@ -541,11 +527,13 @@ __global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const
 }
 
 // ---- subtree tables ---------------------------------------------------------------------------------------------
-// T_w[y], for a peeled query vertex w and every data vertex y of w's label: the number of ways to map the subtree
-// hanging below w when w -> y (1 for a leaf; the start vertex also requires y in C(start)):
-//     T_w[y] = [deg(y) >= deg(w)] * prod over children c of w ( sum over z in N(y), label(z) = label(c) of T_c[z] ).
-// All labels of a peeled subtree are unique in the query, so these maps are injective and disjoint from the rest.
-// One launch per table level (children before parents); blockIdx.y = query vertex slot.
+// N_v[x], for a query vertex v with peeled children and every data vertex x of v's label: the number of ways to map
+// everything that hangs below v in peeled subtrees when v -> x,
+//     N_v[x] = prod over peeled children c of v ( sum over y in N(x), label(y) = label(c), deg(y) >= deg(c)
+//                                                  [, y in C(start) when c is the start vertex] of N_c[y] ),
+// with N_c = 1 for a child without children.  All labels of a peeled subtree are unique in the query, so these maps
+// are injective and disjoint from the rest by construction.  One launch per table level (children before parents);
+// blockIdx.y = query vertex slot.
 __global__ void __launch_bounds__(256) k3_tree_tables_kernel(JoinGraph g, const TreeJob *__restrict__ tjobs,
                                                              const u32 *__restrict__ tchild, u32 level,
                                                              const u32 *__restrict__ bitmap, u64 words_per_slot,
@@ -554,20 +542,24 @@ __global__ void __launch_bounds__(256) k3_tree_tables_kernel(JoinGraph g, const 
     if (job.level != level || job.label >= g.nl) return;
     const u32 c0 = g.lcoff[job.label], n = g.lcoff[job.label + 1] - c0;
     for (u32 pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
-        const u32 y = g.lclass[c0 + pos];
-        u64 val = g.deg[y] >= job.qdeg ? 1 : 0;
-        if (val && job.start_slot != 0xffffffffu)
-            val = bitmap[(u64)job.start_slot * words_per_slot + (y >> 5)] >> (y & 31) & 1;
-        const u32 *row = g.gtab + (u64)y * (g.nl + 1);
+        const u32 x = g.lclass[c0 + pos];
+        const u32 *row = g.gtab + (u64)x * (g.nl + 1);
+        u64 val = 1;
         for (u32 k = 0; k < job.n_child && val; k++) {
             const TreeJob cj = tjobs[tchild[job.child_begin + k]];
             u64 sum = 0;
             if (cj.label < g.nl) {
                 const u32 s = row[cj.label], e = row[cj.label + 1];
-                if (cj.level == 0) {
-                    sum = e - s;  // plain leaves: every neighbour of the label (its degree is >= 1)
+                if (cj.level == 0 && cj.start_slot == 0xffffffffu) {
+                    sum = e - s;  // a plain leaf: every neighbour of the label (its degree is >= 1)
                 } else {
-                    for (u32 x = s; x < e; x++) sum += tpool[cj.table_off + g.lpos[g.nbrL[x].x]];
+                    const u32 *bm = cj.start_slot == 0xffffffffu ? nullptr : bitmap + (u64)cj.start_slot * words_per_slot;
+                    for (u32 at = s; at < e; at++) {
+                        const uint2 yd = g.nbrL[at];
+                        if (yd.y < cj.qdeg) continue;
+                        if (bm && !(bm[yd.x >> 5] >> (yd.x & 31) & 1)) continue;
+                        sum += cj.level ? tpool[cj.table_off + g.lpos[yd.x]] : 1;
+                    }
                 }
             }
             val *= sum;
@@ -824,6 +816,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             // (bit scans -- ffs/popc -- run on the quarter-rate XU pipe, which a first version of this loop saturated:
             //  the masks of the plan are walked with shifts instead)
             bool ok = cdeg >= jd->deg;
+            // everything that hangs below this query vertex in peeled subtrees: one factor per data vertex
+            const u64 tree_off = matches ? kNoTree : jd->tree_off;
+            u64 tree_f = 1;
+            if (ok && tree_off != kNoTree) {
+                tree_f = __ldcg(g.tpool + tree_off + g.lpos[c]);
+                ok = tree_f != 0;
+            }
             for (u32 t = 0; t < d; t++) ok = ok && EMB(t) != c;  // injective (only same-label depths could collide)
             const u32 *row = g.gtab + (u64)c * (g.nl + 1);
             u64 bn = d ? jd->bn_mask : 0;
@@ -856,18 +855,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             }
             if (ok) {
                 // (2) counted-tail factors that close at this depth
-                u64 p = d ? PROD(d - 1) : 1;
+                u64 p = (d ? PROD(d - 1) : 1) * tree_f;
                 u64 um = tail_at < nq ? jd->units_mask >> tail_at : 0;
                 for (u32 i = tail_at; um && p; i++, um >>= 1) {
                     if (!(um & 1)) continue;
                     const JoinDepth *ld = jplan + vb + i;
-                    if (ld->tail_k == kTailTree) {  // a peeled subtree: sum its root's table over the group
-                        const u64 *tab = g.tpool + ld->bn_mask;
-                        u64 f = 0;
-                        for (u32 x = S0(i), e = E0(i); x < e; x++) f += __ldcg(tab + g.lpos[g.nbrL[x].x]);
-                        p *= f;
-                        continue;
-                    }
                     // free members of leaf i's group: its size minus the prefix vertices inside it
                     u32 s = S0(i), e = E0(i), used = ld->sure_used;
                     {

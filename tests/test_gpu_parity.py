@@ -350,3 +350,56 @@ def test_join_counted_tail_equals_reference_enumeration(nl, seed):
             assert rm["n_matches"] == expect, name
             assert sorted(map(tuple, rm["matches"].tolist())) == sorted(map(tuple, om.tolist())), name
     ctx.close()
+
+
+def _random_query(rng, nq, extra_edges, nl):
+    """A connected query: random tree plus a few extra edges, labels drawn from nl labels."""
+    edges = set()
+    for v in range(1, nq):
+        edges.add((int(rng.integers(0, v)), v))
+    for _ in range(extra_edges):
+        a, b = sorted(rng.choice(nq, size=2, replace=False).tolist())
+        edges.add((a, b))
+    return np.array(sorted(edges)), rng.integers(0, nl, size=nq)
+
+
+# The whole online stage (filter -> candidates -> join) on query shapes that exercise the join's factorisation:
+# peeled pendant subtrees (labels unique in the query) tabulated per data vertex, a walk that starts from the core's
+# label class when the start vertex itself is peeled, counted leaves with repeated labels, cycles.  The oracle
+# enumerates every embedding the way the reference does.
+@pytest.mark.parametrize("nl,seed", [(4, 21), (9, 22), (16, 23)])
+def test_factorised_join_equals_reference_enumeration(nl, seed):
+    from oracle import oracle
+    g = synth.chung_lu_graph(1200, 7000, nl, gamma=2.4, degree_cap=60, seed=seed)
+    og = oracle.OracleGraph.from_csr(g.offsets, g.nbrs, g.labels)
+    ctx = gpe.GpeContext(0)
+    ctx.set_graph(g.offsets, g.nbrs, g.labels)
+    _, vde = gpe.host_gen_vde(g.offsets, g.nbrs, g.labels, 2)
+    ctx.set_embeddings(vde)
+    sorted_nodes = graph_io.degree_order(g)
+    assert ctx.enumerate(3, sorted_nodes, graph_io.block_membership(g.V, 3), 3)[0] == og.enumerate(3, sorted_nodes)
+    ctx.build_table()
+    rng = np.random.default_rng(seed)
+    queries, names = [], []
+    for name, (edges, labels) in _TAIL_SHAPES.items():
+        if len(labels) < 3:
+            continue
+        for variant in range(2):  # the shape's own label pattern, and one with all labels distinct where possible
+            lab = np.array(labels) % nl if variant == 0 else rng.permutation(max(nl, len(labels)))[:len(labels)] % nl
+            queries.append(graph_io.csr_from_edges(len(lab), np.array(edges), lab))
+            names.append(f"{name}/{variant}")
+    for i in range(24):
+        nq = int(rng.integers(3, 10))
+        edges, lab = _random_query(rng, nq, int(rng.integers(0, 3)), nl)
+        queries.append(graph_io.csr_from_edges(nq, edges, lab))
+        names.append(f"random{i}")
+    limit = 50_000_000
+    expect = [oracle.online(og, oracle.OracleGraph.from_csr(q.offsets, q.nbrs, q.labels), 2, limit) for q in queries]
+    ans = ctx.query_batch(queries, [limit] * len(queries)).tolist()
+    bad = [(n, a, e) for n, a, e in zip(names, ans, expect) if a != e]
+    assert not bad, bad
+    assert sum(1 for e in expect if e > 0) >= len(expect) // 4  # the cases are not vacuous
+    # one query at a time gives the same answers (different batch composition, same plans)
+    for q, e in list(zip(queries, expect))[::5]:
+        assert int(ctx.query_batch([q], [limit])[0]) == e
+    ctx.close()
