@@ -284,9 +284,9 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     const u32 n_slots = c->b_slots;
     GPE_CUDA(c, c->d_tjobs.reserve(std::max<size_t>(n_slots, 1) * sizeof(TreeJob)));
     GPE_CUDA(c, c->d_tchild.reserve(std::max<size_t>(n_slots, 1) * sizeof(u32)));
-    GPE_CUDA(c, c->d_tcursor.reserve(2 * sizeof(u64)));
+    GPE_CUDA(c, c->d_tcursor.reserve(4 * sizeof(u64)));
     GPE_CUDA(c, c->d_tpool.reserve(std::max<u64>((u64)n_slots * c->max_class, 1) * sizeof(u64)));
-    GPE_CUDA(c, cudaMemsetAsync(c->d_tcursor.p, 0, 2 * sizeof(u64), c->stream));
+    GPE_CUDA(c, cudaMemsetAsync(c->d_tcursor.p, 0, 4 * sizeof(u64), c->stream));
     GPE_CUDA(c, k3_order(nq, c->V, c->d_q_vbase.as<u32>(), c->d_q_ebase.as<u32>(), c->d_q_offsets.as<u32>(),
                          c->d_q_nbrs.as<u32>(), c->d_q_labels.as<u32>(), c->d_cand_off.as<u64>(), c->d_order.as<u32>(),
                          c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_item_base.as<u64>(), rank, world,
@@ -313,8 +313,10 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     }
     const u32 epoch = ++c->join_epoch;
     JoinQueue *jq = c->d_jq.as<JoinQueue>();
+    const u32 heavy_deg = std::max<u32>(32, c->V ? (u32)(4ull * c->n_adj / c->V) : 32);  // 4 x the mean degree
     GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
-                              c->d_item_base.as<u64>(), rank, world, c->d_init.p, jq, c->sm_count, c->stream));
+                              c->d_cand.as<u32>(), c->d_item_base.as<u64>(), rank, world, heavy_deg,
+                              c->d_tcursor.as<u64>() + 2, c->d_init.p, jq, c->sm_count, c->stream));
     GPE_CUDA(c, k3_dfs(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_cand.as<u32>(),
                        c->d_init.p, c->d_limits.as<u64>(), answers, c->d_items.as<u32>(), cap, c->d_ready.as<u32>(), epoch,
                        jq, d_matches, matches_cap, c->d_match_cursor.as<u64>(), c->sm_count, c->stream));

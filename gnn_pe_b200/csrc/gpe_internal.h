@@ -303,8 +303,9 @@ cudaError_t k3_tree_tables(const JoinView &jv, u32 n_slots, u32 max_class, u32 m
 u32 k3_item_stride(u32 max_nq);  // u32 words per exported work item
 // one ticket (query, position in cand[]) per start candidate of this shard; init: 8 bytes per ticket
 cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
-                          const u64 *cand_off, const u64 *item_base, u32 rank, u32 world, void *init, JoinQueue *jq,
-                          int sm_count, cudaStream_t s);
+                          const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world,
+                          u32 heavy_deg /*roots of at least this degree are ticketed first*/, u64 *cursors /*2, zeroed*/,
+                          void *init, JoinQueue *jq, int sm_count, cudaStream_t s);
 // one persistent launch: every thread runs work items (explicit-stack DFS) and exports subtrees when others starve
 cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
                    const void *init, const u64 *limits, u64 *answers, u32 *items, u64 export_cap, u32 *ready, u32 epoch,

@@ -454,7 +454,8 @@ struct JoinGraph {
 
 constexpr int kItemHdr = 8;  // q, level, lo, hi, prod (2 words), label of the start vertex, pad; then EMB | S0 | E0
 constexpr u32 kSplit = 8;
-constexpr u32 kExportEvery = 32;
+constexpr u32 kExportEvery = 16;
+constexpr int kExportLanes = 4;  // lanes of a warp that may hand work over in one round
 
 __host__ __device__ constexpr u32 item_stride(u32 m) { return kItemHdr + 3 * m; }
 
@@ -490,13 +491,20 @@ __device__ __forceinline__ void ld_relaxed_2xu64(const void *p, u64 &a, u64 &b) 
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
-// one ticket per root candidate of this shard (idx % world == rank): (query, position in cand[] or in lclass[])
+// One ticket per root candidate of this shard (idx % world == rank): (query, position in cand[] or in lclass[]).
+// Subtree sizes are heavy-tailed and grow with the root's degree, so high-degree roots are ticketed first (longest
+// jobs first: the end of the join is then made of small items); cursors[0] counts heavy tickets from the front,
+// cursors[1] light ones from the back.  A warp allocates its share with one atomic per class, so consecutive
+// candidates of a query stay neighbours in the ticket order.
 __global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const u32 *__restrict__ q_vbase,
                                                             const JoinDepth *__restrict__ jplan,
                                                             const u64 *__restrict__ cand_off,
+                                                            const u32 *__restrict__ cand,
+                                                            const u32 *__restrict__ lclass,
+                                                            const u32 *__restrict__ deg,
                                                             const u32 *__restrict__ lcoff, u32 n_labels,
                                                             const u64 *__restrict__ item_base, u32 rank, u32 world,
-                                                            uint2 *init, JoinQueue *jq) {
+                                                            u32 heavy_deg, u64 *cursors, uint2 *init, JoinQueue *jq) {
     const u64 n_items = item_base[n_queries];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         jq->head = 0;
@@ -512,17 +520,39 @@ __global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const
         jq->lane_iters = 0;
         jq->idle_polls = 0;
     }
-    for (u64 item = (u64)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (u64)gridDim.x * blockDim.x) {
-        u32 lo = 0, hi = n_queries;
-        while (hi - lo > 1) {
-            u32 mid = (lo + hi) >> 1;
-            if (item_base[mid] <= item) lo = mid; else hi = mid;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = lanemask_lt();
+    const u64 n_round = (n_items + 31) / 32 * 32;
+    for (u64 item = (u64)blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += (u64)gridDim.x * blockDim.x) {
+        const bool valid = item < n_items;
+        u32 q = 0, pos = 0;
+        bool heavy = false;
+        if (valid) {
+            u32 lo = 0, hi = n_queries;
+            while (hi - lo > 1) {
+                u32 mid = (lo + hi) >> 1;
+                if (item_base[mid] <= item) lo = mid; else hi = mid;
+            }
+            q = lo;
+            const u32 vb = q_vbase[q];
+            const u64 idx = (item - item_base[q]) * world + rank;
+            const JoinDepth &j0 = jplan[vb];
+            const u64 first = j0.tail_mask ? (j0.label < n_labels ? lcoff[j0.label] : 0) : cand_off[vb + j0.u];
+            pos = (u32)(first + idx);
+            heavy = deg[j0.tail_mask ? lclass[pos] : cand[pos]] >= heavy_deg;
         }
-        const u32 q = lo, vb = q_vbase[q];
-        const u64 idx = (item - item_base[q]) * world + rank;
-        const JoinDepth &j0 = jplan[vb];
-        const u64 first = j0.tail_mask ? (j0.label < n_labels ? lcoff[j0.label] : 0) : cand_off[vb + j0.u];
-        init[item] = make_uint2(q, (u32)(first + idx));
+        const unsigned hm = __ballot_sync(kFull, valid && heavy), lm = __ballot_sync(kFull, valid && !heavy);
+        u64 h0 = 0, l0 = 0;
+        if (lane == 0) {
+            if (hm) h0 = atomicAdd((unsigned long long *)&cursors[0], (unsigned long long)__popc(hm));
+            if (lm) l0 = atomicAdd((unsigned long long *)&cursors[1], (unsigned long long)__popc(lm));
+        }
+        h0 = __shfl_sync(kFull, h0, 0);
+        l0 = __shfl_sync(kFull, l0, 0);
+        if (valid) {
+            const u64 at = heavy ? h0 + __popc(hm & lt) : n_items - 1 - (l0 + __popc(lm & lt));
+            init[at] = make_uint2(q, pos);
+        }
     }
 }
 
@@ -929,15 +959,19 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             }
         }
 
-        // ---- between warps: when idle warps outnumber the published items, one lane gives work away ----
-        if ((iter & (kExportEvery - 1)) == 1 && h_idle > 0 && (long long)(h_tail - h_head) < (long long)(h_idle * 4)) {
+        // ---- between warps: when idle warps outnumber the published items, the lanes with the shallowest unexplored
+        //      sibling ranges give them away ----
+        if ((iter & (kExportEvery - 1)) == 1 && h_idle > 0 && (long long)(h_tail - h_head) < (long long)(h_idle * 8)) {
             u32 key = 0xffffffffu, l = 0;
             if (have && can_export) {
                 for (l = base; l <= d; l++)
                     if (CUR(l) < END(l)) { key = (l << 5) | (u32)lane; break; }
             }
-            const u32 best = __reduce_min_sync(kFull, key);
-            if (best != 0xffffffffu && key == best) {
+            for (int round = 0; round < kExportLanes; round++) {
+                const u32 best = __reduce_min_sync(kFull, key);
+                if (best == 0xffffffffu) break;
+                if (key != best) continue;
+                key = 0xffffffffu;
                 const u32 c0 = CUR(l), len = END(l) - c0, np = min(len, kSplit);
                 const u64 o = atomicAdd(&jq->tail, (unsigned long long)np) - n_init;
                 if (o + np > export_cap) {
@@ -1048,10 +1082,11 @@ static JoinGraph join_graph(const JoinView &jv) {
 }
 
 cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
-                          const u64 *cand_off, const u64 *item_base, u32 rank, u32 world, void *init, JoinQueue *jq,
-                          int sm_count, cudaStream_t s) {
-    k3_init_items_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, jv.lcoff, jv.nl, item_base,
-                                                     rank, world, reinterpret_cast<uint2 *>(init), jq);
+                          const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world, u32 heavy_deg,
+                          u64 *cursors, void *init, JoinQueue *jq, int sm_count, cudaStream_t s) {
+    k3_init_items_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, cand, jv.lclass, jv.deg, jv.lcoff,
+                                                     jv.nl, item_base, rank, world, heavy_deg, cursors,
+                                                     reinterpret_cast<uint2 *>(init), jq);
     return cudaGetLastError();
 }
 
