@@ -293,7 +293,8 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
                          enumerate, clean_start, c->n_labels, c->d_lcoff.as<u32>(), c->d_tjobs.as<TreeJob>(),
                          c->d_tchild.as<u32>(), c->d_tcursor.as<u64>(), c->stream));
     JoinView jv{c->d_label.as<u32>(), c->d_nbrL.as<u32>(), c->d_gtab.as<u32>(), c->V, c->n_labels, c->d_deg.as<u32>(),
-                c->d_lclass.as<u32>(), c->d_lpos.as<u32>(), c->d_lcoff.as<u32>(), c->d_tpool.as<u64>()};
+                c->d_lclass.as<u32>(), c->d_lpos.as<u32>(), c->d_lcoff.as<u32>(), c->d_tpool.as<u64>(), c->d_bloom.as<u32>(),
+                c->bloom_bits - 1};
     u32 tree_launches = 0;
     if (!enumerate && c->b_max_nq >= 2) {
         tree_launches = c->b_max_nq - 1;
@@ -412,7 +413,7 @@ void gpe_destroy(gpe_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrL, &c->d_gtab, &c->d_lclass, &c->d_lpos, &c->d_lcoff, &c->d_tjobs, &c->d_tchild, &c->d_tpool, &c->d_tcursor, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
+    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrL, &c->d_gtab, &c->d_lclass, &c->d_lpos, &c->d_lcoff, &c->d_bloom, &c->d_tjobs, &c->d_tchild, &c->d_tpool, &c->d_tcursor, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
                       &c->d_offr, &c->d_ebase, &c->d_start_rows, &c->d_scan_tmp, &c->d_tiles, &c->d_vids, &c->d_sum_u32, &c->d_sum_f64,
                       &c->d_bucket, &c->d_cursor, &c->d_qblocks, &c->d_qb_t0, &c->d_qb_prefix, &c->d_worklist,
                       &c->d_counters, &c->d_bitmap, &c->d_survivors, &c->d_chunk_cnt, &c->d_chunk_off, &c->d_cand,
@@ -543,6 +544,15 @@ int gpe_set_graph(gpe_ctx *c, uint32_t V, const uint32_t *offsets, const uint32_
                 lpos[v] = at[l] - lcoff[l];
                 lclass[at[l]++] = v;
             }
+        }
+        {   // edge filter: 16 bits per undirected edge, two of them set
+            u64 bits = 1024;
+            while (bits < 8ull * n_adj) bits <<= 1;
+            std::vector<u32> words(bits / 32, 0u);
+            k3_bloom_build(V, offsets, nbrs, bits, words.data());
+            c->bloom_bits = bits;
+            GPE_CUDA(c, c->d_bloom.reserve(words.size() * sizeof(u32)));
+            GPE_CUDA(c, cudaMemcpy(c->d_bloom.p, words.data(), words.size() * sizeof(u32), cudaMemcpyHostToDevice));
         }
         GPE_CUDA(c, c->d_lclass.reserve(lclass.size() * sizeof(u32)));
         GPE_CUDA(c, c->d_lpos.reserve(lpos.size() * sizeof(u32)));

@@ -183,6 +183,8 @@ struct gpe_ctx {
     gpe::DevBuf d_lclass, d_lpos, d_lcoff;  // label classes: vertices by (label, id), position in class, class offsets
     gpe::DevBuf d_tjobs, d_tchild, d_tpool, d_tcursor;  // subtree tables of the join (jobs, child lists, value pool, pool cursor)
     u32 max_class = 0;
+    gpe::DevBuf d_bloom;  // edge filter of the join
+    u64 bloom_bits = 0;
     gpe::DevBuf d_items, d_ready, d_jq, d_init, d_kids;  // exported join work items, their publication flags, the queue header, start tickets
     u32 join_epoch = 0;
     u32 b_max_nq = 0;
@@ -296,7 +298,11 @@ struct JoinView {
     u32 V, nl;
     const u32 *deg, *lclass, *lpos, *lcoff;
     const u64 *tpool;
+    const u32 *bloom;
+    u64 bloom_mask;
 };
+// host: two bits per undirected edge into a table of n_bits (power of two) bits
+void k3_bloom_build(u32 V, const u32 *offsets, const u32 *nbrs, u64 n_bits, u32 *words);
 // tables of the peeled subtrees, levels 1..max_level (one launch each)
 cudaError_t k3_tree_tables(const JoinView &jv, u32 n_slots, u32 max_class, u32 max_level, const TreeJob *tjobs,
                            const u32 *tchild, const u32 *bitmap, u64 words_per_slot, u64 *tpool, cudaStream_t s);

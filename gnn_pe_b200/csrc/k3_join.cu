@@ -450,11 +450,14 @@ struct JoinGraph {
     const u32 *lpos;    // position of a vertex inside its label class
     const u32 *lcoff;   // nl + 1 class offsets into lclass
     const u64 *tpool;   // subtree tables (k3_tree_tables), indexed [table offset + lpos]
+    const u32 *bloom;   // edge filter: two bits per undirected edge in a table of bloom_mask + 1 bits
+    u64 bloom_mask;
 };
 
 constexpr int kItemHdr = 8;  // q, level, lo, hi, prod (2 words), label of the start vertex, pad; then EMB | S0 | E0
 constexpr u32 kSplit = 8;
-constexpr u32 kExportEvery = 16;
+constexpr u32 kExportEvery = 8;      // rounds between two looks at the queue header
+constexpr int kStepsPerRound = 2;   // DFS steps of a lane between two rounds of scheduling (tickets, donation, export)
 constexpr int kExportLanes = 4;  // lanes of a warp that may hand work over in one round
 
 __host__ __device__ constexpr u32 item_stride(u32 m) { return kItemHdr + 3 * m; }
@@ -466,6 +469,22 @@ __device__ __forceinline__ void group_range(const JoinGraph &g, u32 v, u32 label
     const u32 *row = g.gtab + (u64)v * (g.nl + 1) + label;
     lo = __ldcg(row);
     hi = __ldcg(row + 1);
+}
+
+// Edge filter: "no" is exact, "maybe" has to be confirmed by a search.  Most membership / edge tests of the join
+// fail (a prefix vertex is rarely adjacent to the pivot), and a failed test costs two independent loads here
+// instead of a chain of binary-search probes.
+__host__ __device__ __forceinline__ u64 edge_hash(u32 a, u32 b, u64 salt) {
+    u64 x = ((u64)(a < b ? a : b) << 32 | (a < b ? b : a)) + salt;
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+__device__ __forceinline__ bool edge_maybe(const JoinGraph &g, u32 a, u32 b) {
+    const u64 h1 = edge_hash(a, b, 0) & g.bloom_mask, h2 = edge_hash(a, b, 0x9e3779b97f4a7c15ull) & g.bloom_mask;
+    const u32 w1 = __ldg(g.bloom + (h1 >> 5)), w2 = __ldg(g.bloom + (h2 >> 5));
+    return (w1 >> (h1 & 31) & 1) && (w2 >> (h2 & 31) & 1);
 }
 
 // is v a member of the group nbrL[s, e)?  (ids ascending)
@@ -820,8 +839,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             }
         }
 
-        w_iters++;
-        if (have) {
+        w_iters += kStepsPerRound;
+        for (int rep = 0; rep < kStepsPerRound && have; rep++) {
             // ---- one DFS step: test the next candidate of level d ----
             my_steps++;
             const u32 at = CUR(d);
@@ -859,7 +878,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             for (u32 t = 0; ok && bn; t++, bn >>= 1) {  // the other backward neighbours: edge (c, EMB(t)) must exist
                 if (!(bn & 1)) continue;
                 const u32 lt_ = t ? jplan[vb + t].label : lab0;
-                if (cdeg <= 64) {  // search c's (short) group of label(EMB(t))
+                if (!edge_maybe(g, c, EMB(t))) {
+                    ok = false;
+                } else if (cdeg <= 64) {  // search c's (short) group of label(EMB(t))
                     ok = lt_ < g.nl && in_group(g, __ldcg(row + lt_), __ldcg(row + lt_ + 1), EMB(t));
                 } else {           // search EMB(t)'s group of c's label
                     u32 s, e;
@@ -894,9 +915,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                     u32 s = S0(i), e = E0(i), used = ld->sure_used;
                     {
                         const u32 llab = ld->label;
+                        const u32 pvx = EMB(ld->pivot_depth);
                         u64 m = ld->tail_mask;
                         for (u32 t = 0; m; t++, m >>= 1)
-                            if ((m & 1) && (t != 0 || lab0 == llab) && in_group(g, s, e, EMB(t))) used++;
+                            if ((m & 1) && (t != 0 || lab0 == llab) && edge_maybe(g, pvx, EMB(t)) && in_group(g, s, e, EMB(t))) used++;
                     }
                     const u32 n_free = (e - s) - used;
                     if (ld->tail_k == kTailMul) {
@@ -913,9 +935,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                         u32 used2 = lb->sure_used;
                         {
                             const u32 llab = lb->label;
+                            const u32 pvx = EMB(lb->pivot_depth);
                             u64 m = lb->tail_mask;
                             for (u32 t = 0; m; t++, m >>= 1)
-                                if ((m & 1) && (t != 0 || lab0 == llab) && in_group(g, s2, e2, EMB(t))) used2++;
+                                if ((m & 1) && (t != 0 || lab0 == llab) && edge_maybe(g, pvx, EMB(t)) && in_group(g, s2, e2, EMB(t))) used2++;
                         }
                         const u32 n_free2 = (e2 - s2) - used2;
                         // ordered pairs of distinct vertices: |A||B| - |A n B| over the free members; the groups are
@@ -956,6 +979,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                         END(d) = E0(d);
                     }
                 }
+            }
+            // pop exhausted levels
+            while (have && CUR(d) >= END(d)) {
+                if (d == base) have = false; else d--;
             }
         }
 
@@ -1001,10 +1028,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                     my_exports++;
                 }
             }
-        }
-        // ---- pop exhausted levels ----
-        while (have && CUR(d) >= END(d)) {
-            if (d == base) have = false; else d--;
+            while (have && CUR(d) >= END(d)) {  // the exported range may have been this lane's current level
+                if (d == base) have = false; else d--;
+            }
         }
     }
     if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
@@ -1078,7 +1104,7 @@ u32 k3_item_stride(u32 max_nq) { return item_stride(join_m(max_nq)); }
 
 static JoinGraph join_graph(const JoinView &jv) {
     return JoinGraph{jv.label, reinterpret_cast<const uint2 *>(jv.nbrL), jv.gtab, jv.V, jv.nl, jv.deg, jv.lclass, jv.lpos,
-                     jv.lcoff, jv.tpool};
+                     jv.lcoff, jv.tpool, jv.bloom, jv.bloom_mask};
 }
 
 cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
@@ -1123,6 +1149,18 @@ cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const Joi
     else { LAUNCH(64, 128, 1); }
 #undef LAUNCH
     return cudaGetLastError();
+}
+
+void k3_bloom_build(u32 V, const u32 *offsets, const u32 *nbrs, u64 n_bits /*power of two*/, u32 *words) {
+    const u64 mask = n_bits - 1;
+    for (u32 v = 0; v < V; v++)
+        for (u32 j = offsets[v]; j < offsets[v + 1]; j++) {
+            const u32 w = nbrs[j];
+            if (w < v) continue;
+            const u64 h1 = edge_hash(v, w, 0) & mask, h2 = edge_hash(v, w, 0x9e3779b97f4a7c15ull) & mask;
+            words[h1 >> 5] |= 1u << (h1 & 31);
+            words[h2 >> 5] |= 1u << (h2 & 31);
+        }
 }
 
 }  // namespace gpe
