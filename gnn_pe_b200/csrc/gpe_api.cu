@@ -287,11 +287,14 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     GPE_CUDA(c, c->d_tcursor.reserve(4 * sizeof(u64)));
     GPE_CUDA(c, c->d_tpool.reserve(std::max<u64>((u64)n_slots * c->max_class, 1) * sizeof(u64)));
     GPE_CUDA(c, cudaMemsetAsync(c->d_tcursor.p, 0, 4 * sizeof(u64), c->stream));
+    GPE_CUDA(c, c->d_tlist.reserve(((size_t)kMaxTreeLevels * std::max<u32>(n_slots, 1) + kMaxTreeLevels) * sizeof(u32)));
+    u32 *tcount = c->d_tlist.as<u32>(), *tlist = tcount + kMaxTreeLevels;
+    GPE_CUDA(c, cudaMemsetAsync(tcount, 0, kMaxTreeLevels * sizeof(u32), c->stream));
     GPE_CUDA(c, k3_order(nq, c->V, c->d_q_vbase.as<u32>(), c->d_q_ebase.as<u32>(), c->d_q_offsets.as<u32>(),
                          c->d_q_nbrs.as<u32>(), c->d_q_labels.as<u32>(), c->d_cand_off.as<u64>(), c->d_order.as<u32>(),
                          c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_item_base.as<u64>(), rank, world,
                          enumerate, clean_start, c->n_labels, c->d_lcoff.as<u32>(), c->d_tjobs.as<TreeJob>(),
-                         c->d_tchild.as<u32>(), c->d_tcursor.as<u64>(), c->stream));
+                         c->d_tchild.as<u32>(), c->d_tcursor.as<u64>(), tcount, tlist, n_slots, c->stream));
     JoinView jv{c->d_label.as<u32>(), c->d_nbrL.as<u32>(), c->d_gtab.as<u32>(), c->V, c->n_labels, c->d_deg.as<u32>(),
                 c->d_lclass.as<u32>(), c->d_lpos.as<u32>(), c->d_lcoff.as<u32>(), c->d_tpool.as<u64>(), c->d_bloom.as<u32>(),
                 c->bloom_bits - 1};
@@ -299,7 +302,8 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     if (!enumerate && c->b_max_nq >= 2) {
         tree_launches = c->b_max_nq - 1;
         GPE_CUDA(c, k3_tree_tables(jv, n_slots, c->max_class, tree_launches, c->d_tjobs.as<TreeJob>(), c->d_tchild.as<u32>(),
-                                   clean_start ? c->d_bitmap.as<u32>() : nullptr, c->b_words, c->d_tpool.as<u64>(), c->stream));
+                                   tcount, tlist, clean_start ? c->d_bitmap.as<u32>() : nullptr, c->b_words,
+                                   c->d_tpool.as<u64>(), c->sm_count, c->stream));
     }
     // tickets [0, n_init) are the root candidates of this shard (b_n_cand + V bounds their number from above);
     // later tickets are subtrees exported by busy threads
@@ -315,16 +319,18 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     const u32 epoch = ++c->join_epoch;
     JoinQueue *jq = c->d_jq.as<JoinQueue>();
     const u32 heavy_deg = std::max<u32>(32, c->V ? (u32)(4ull * c->n_adj / c->V) : 32);  // 4 x the mean degree
+    GPE_CUDA(c, c->d_qcur.reserve(((size_t)nq + 1) * 5 * sizeof(u64)));
+    GPE_CUDA(c, cudaMemsetAsync(c->d_qcur.p, 0, ((size_t)nq + 1) * 5 * sizeof(u64), c->stream));
     GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
                               c->d_cand.as<u32>(), c->d_item_base.as<u64>(), rank, world, heavy_deg,
-                              c->d_tcursor.as<u64>() + 2, c->d_init.p, jq, c->sm_count, c->stream));
+                              c->d_qcur.as<u64>(), c->d_init.p, jq, c->sm_count, c->stream));
     GPE_CUDA(c, k3_dfs(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_cand.as<u32>(),
                        c->d_init.p, c->d_limits.as<u64>(), answers, c->d_items.as<u32>(), cap, c->d_ready.as<u32>(), epoch,
                        jq, d_matches, matches_cap, c->d_match_cursor.as<u64>(), c->sm_count, c->stream));
     c->stats.kernel_launches += tree_launches;
     c->stats.join_launches += tree_launches;
-    c->stats.kernel_launches += 3;
-    c->stats.join_launches += 3;
+    c->stats.kernel_launches += 5;
+    c->stats.join_launches += 5;
     c->b_joined = true;
     return GPE_OK;
 }
@@ -413,7 +419,7 @@ void gpe_destroy(gpe_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrL, &c->d_gtab, &c->d_lclass, &c->d_lpos, &c->d_lcoff, &c->d_bloom, &c->d_tjobs, &c->d_tchild, &c->d_tpool, &c->d_tcursor, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
+    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrL, &c->d_gtab, &c->d_lclass, &c->d_lpos, &c->d_lcoff, &c->d_bloom, &c->d_tjobs, &c->d_tchild, &c->d_tpool, &c->d_tcursor, &c->d_tlist, &c->d_qcur, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
                       &c->d_offr, &c->d_ebase, &c->d_start_rows, &c->d_scan_tmp, &c->d_tiles, &c->d_vids, &c->d_sum_u32, &c->d_sum_f64,
                       &c->d_bucket, &c->d_cursor, &c->d_qblocks, &c->d_qb_t0, &c->d_qb_prefix, &c->d_worklist,
                       &c->d_counters, &c->d_bitmap, &c->d_survivors, &c->d_chunk_cnt, &c->d_chunk_off, &c->d_cand,

@@ -181,7 +181,7 @@ struct gpe_ctx {
     gpe::DevBuf d_off, d_nbr, d_label, d_deg, d_rank, d_sorted, d_member, d_vde;
     gpe::DevBuf d_nbrL, d_gtab;  // label-grouped adjacency + group directory (join)
     gpe::DevBuf d_lclass, d_lpos, d_lcoff;  // label classes: vertices by (label, id), position in class, class offsets
-    gpe::DevBuf d_tjobs, d_tchild, d_tpool, d_tcursor;  // subtree tables of the join (jobs, child lists, value pool, pool cursor)
+    gpe::DevBuf d_tjobs, d_tchild, d_tpool, d_tcursor, d_tlist, d_qcur;  // subtree tables of the join (jobs, child lists, value pool, pool cursor)
     u32 max_class = 0;
     gpe::DevBuf d_bloom;  // edge filter of the join
     u64 bloom_bits = 0;
@@ -291,7 +291,8 @@ cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebas
                      JoinDepth *jplan, void *kids /*uint2 per query vertex*/, u64 *item_base, u32 rank, u32 world,
                      bool enumerate /*walk every vertex (matches wanted)*/, bool clean_start /*start candidates carry the
                      query label (they come from the filter)*/, u32 n_labels, const u32 *lcoff, TreeJob *tjobs, u32 *tchild,
-                     u64 *tcursor, cudaStream_t s);
+                     u64 *tcursor, u32 *tcount /*kMaxTreeLevels, zeroed*/, u32 *tlist /*kMaxTreeLevels x n_slots*/, u32 n_slots,
+                     cudaStream_t s);
 // label-grouped adjacency for the join (built on the host in gpe_set_graph)
 struct JoinView {
     const u32 *label, *nbrL /* (neighbour, degree) pairs */, *gtab;
@@ -304,13 +305,15 @@ struct JoinView {
 // host: two bits per undirected edge into a table of n_bits (power of two) bits
 void k3_bloom_build(u32 V, const u32 *offsets, const u32 *nbrs, u64 n_bits, u32 *words);
 // tables of the peeled subtrees, levels 1..max_level (one launch each)
+constexpr u32 kMaxTreeLevels = GPE_MAX_QUERY_VERTICES;
 cudaError_t k3_tree_tables(const JoinView &jv, u32 n_slots, u32 max_class, u32 max_level, const TreeJob *tjobs,
-                           const u32 *tchild, const u32 *bitmap, u64 words_per_slot, u64 *tpool, cudaStream_t s);
+                           const u32 *tchild, const u32 *tcount, const u32 *tlist, const u32 *bitmap, u64 words_per_slot,
+                           u64 *tpool, int sm_count, cudaStream_t s);
 u32 k3_item_stride(u32 max_nq);  // u32 words per exported work item
 // one ticket (query, position in cand[]) per start candidate of this shard; init: 8 bytes per ticket
 cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
                           const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world,
-                          u32 heavy_deg /*roots of at least this degree are ticketed first*/, u64 *cursors /*2, zeroed*/,
+                          u32 heavy_deg /*roots of at least this degree are ticketed first*/, u64 *cursors /*5 per query, zeroed*/,
                           void *init, JoinQueue *jq, int sm_count, cudaStream_t s);
 // one persistent launch: every thread runs work items (explicit-stack DFS) and exports subtrees when others starve
 cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                                                        JoinDepth *jplan, uint2 *kids, u64 *item_base, u32 rank,
                                                        u32 world, u32 per_ticket, bool enumerate, bool clean_start,
                                                        u32 n_labels, const u32 *__restrict__ lcoff, TreeJob *tjobs,
-                                                       u32 *tchild, u64 *tcursor) {
+                                                       u32 *tchild, u64 *tcursor, u32 *tcount, u32 *tlist, u32 n_slots) {
     for (u32 q = threadIdx.x; q < n_queries; q += blockDim.x) {
         const u32 vb = q_vbase[q], nq = q_vbase[q + 1] - vb;
         const u32 *off = q_offsets + vb + q;  // nq + 1 local offsets
@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 tj.level = lvl;
                 const u32 sz = qlab[v] < n_labels ? lcoff[qlab[v] + 1] - lcoff[qlab[v]] : 0;
                 tj.table_off = atomicAdd((unsigned long long *)tcursor, (unsigned long long)sz);
+                tlist[(u64)lvl * n_slots + atomicAdd(&tcount[lvl], 1u)] = vb + v;  // this level's launch works on it
             };
             for (u32 k = 0; k < n_peel; k++) make_table(peel[k]);
             for (u32 u = 0; u < nq; u++)
@@ -512,9 +513,81 @@ __device__ __forceinline__ void ld_relaxed_2xu64(const void *p, u64 &a, u64 &b) 
 
 // One ticket per root candidate of this shard (idx % world == rank): (query, position in cand[] or in lclass[]).
 // Subtree sizes are heavy-tailed and grow with the root's degree, so high-degree roots are ticketed first (longest
-// jobs first: the end of the join is then made of small items); cursors[0] counts heavy tickets from the front,
-// cursors[1] light ones from the back.  A warp allocates its share with one atomic per class, so consecutive
-// candidates of a query stay neighbours in the ticket order.
+// jobs first: the end of the join is then made of small items).  Ticket order: the heavy roots of query 0, 1, ...,
+// then the light roots of query 0, 1, ... -- neighbouring tickets belong to one query, so the lanes of a warp mostly
+// read the same plan.  Three small launches: count the heavy roots per query, prefix, place.
+struct RootItem { u32 q, pos; bool heavy; };
+
+__device__ __forceinline__ RootItem root_item(u64 item, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
+                                              const u64 *cand_off, const u32 *cand, const u32 *lclass, const u32 *deg,
+                                              const u32 *lcoff, u32 n_labels, const u64 *item_base, u32 rank, u32 world,
+                                              u32 heavy_deg) {
+    u32 lo = 0, hi = n_queries;
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (item_base[mid] <= item) lo = mid; else hi = mid;
+    }
+    RootItem r;
+    r.q = lo;
+    const u32 vb = q_vbase[r.q];
+    const u64 idx = (item - item_base[r.q]) * world + rank;
+    const JoinDepth &j0 = jplan[vb];
+    const u64 first = j0.tail_mask ? (j0.label < n_labels ? lcoff[j0.label] : 0) : cand_off[vb + j0.u];
+    r.pos = (u32)(first + idx);
+    r.heavy = deg[j0.tail_mask ? lclass[r.pos] : cand[r.pos]] >= heavy_deg;
+    return r;
+}
+
+// qcur: per query [0] heavy count, [1] heavy base, [2] light base, [3] heavy cursor, [4] light cursor (u64 each)
+__global__ void __launch_bounds__(256) k3_init_count_kernel(u32 n_queries, const u32 *__restrict__ q_vbase,
+                                                            const JoinDepth *__restrict__ jplan,
+                                                            const u64 *__restrict__ cand_off,
+                                                            const u32 *__restrict__ cand,
+                                                            const u32 *__restrict__ lclass,
+                                                            const u32 *__restrict__ deg,
+                                                            const u32 *__restrict__ lcoff, u32 n_labels,
+                                                            const u64 *__restrict__ item_base, u32 rank, u32 world,
+                                                            u32 heavy_deg, u64 *qcur) {
+    const u64 n_items = item_base[n_queries], n_round = (n_items + 31) / 32 * 32;
+    const int lane = threadIdx.x & 31;
+    for (u64 item = (u64)blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += (u64)gridDim.x * blockDim.x) {
+        RootItem r{0xffffffffu, 0, false};
+        if (item < n_items)
+            r = root_item(item, n_queries, q_vbase, jplan, cand_off, cand, lclass, deg, lcoff, n_labels, item_base, rank, world,
+                          heavy_deg);
+        // one atomic per (warp, query): consecutive items belong to one query almost always
+        const unsigned peers = __match_any_sync(kFull, r.heavy ? r.q : 0xffffffffu);
+        if (r.heavy && lane == __ffs(peers) - 1) atomicAdd((unsigned long long *)&qcur[5 * (u64)r.q], (unsigned long long)__popc(peers));
+    }
+}
+
+__global__ void k3_init_prefix_kernel(u32 n_queries, const u64 *__restrict__ item_base, u64 *qcur, JoinQueue *jq) {
+    if (threadIdx.x || blockIdx.x) return;
+    const u64 n_items = item_base[n_queries];
+    jq->head = 0;
+    jq->tail = n_items;
+    jq->pending = (long long)n_items;
+    jq->idle = 0;
+    jq->n_init = n_items;
+    jq->steps = 0;
+    jq->exports = 0;
+    jq->donations = 0;
+    jq->full = 0;
+    jq->warp_iters = 0;
+    jq->lane_iters = 0;
+    jq->idle_polls = 0;
+    u64 heavy = 0;
+    for (u32 q = 0; q < n_queries; q++) {
+        qcur[5 * (u64)q + 1] = heavy;
+        heavy += qcur[5 * (u64)q];
+    }
+    u64 light = heavy;
+    for (u32 q = 0; q < n_queries; q++) {
+        qcur[5 * (u64)q + 2] = light;
+        light += (item_base[q + 1] - item_base[q]) - qcur[5 * (u64)q];
+    }
+}
+
 __global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const u32 *__restrict__ q_vbase,
                                                             const JoinDepth *__restrict__ jplan,
                                                             const u64 *__restrict__ cand_off,
@@ -523,55 +596,27 @@ __global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const
                                                             const u32 *__restrict__ deg,
                                                             const u32 *__restrict__ lcoff, u32 n_labels,
                                                             const u64 *__restrict__ item_base, u32 rank, u32 world,
-                                                            u32 heavy_deg, u64 *cursors, uint2 *init, JoinQueue *jq) {
-    const u64 n_items = item_base[n_queries];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        jq->head = 0;
-        jq->tail = n_items;
-        jq->pending = (long long)n_items;
-        jq->idle = 0;
-        jq->n_init = n_items;
-        jq->steps = 0;
-        jq->exports = 0;
-        jq->donations = 0;
-        jq->full = 0;
-        jq->warp_iters = 0;
-        jq->lane_iters = 0;
-        jq->idle_polls = 0;
-    }
+                                                            u32 heavy_deg, u64 *qcur, uint2 *init) {
+    const u64 n_items = item_base[n_queries], n_round = (n_items + 31) / 32 * 32;
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
-    const u64 n_round = (n_items + 31) / 32 * 32;
     for (u64 item = (u64)blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += (u64)gridDim.x * blockDim.x) {
         const bool valid = item < n_items;
-        u32 q = 0, pos = 0;
-        bool heavy = false;
-        if (valid) {
-            u32 lo = 0, hi = n_queries;
-            while (hi - lo > 1) {
-                u32 mid = (lo + hi) >> 1;
-                if (item_base[mid] <= item) lo = mid; else hi = mid;
-            }
-            q = lo;
-            const u32 vb = q_vbase[q];
-            const u64 idx = (item - item_base[q]) * world + rank;
-            const JoinDepth &j0 = jplan[vb];
-            const u64 first = j0.tail_mask ? (j0.label < n_labels ? lcoff[j0.label] : 0) : cand_off[vb + j0.u];
-            pos = (u32)(first + idx);
-            heavy = deg[j0.tail_mask ? lclass[pos] : cand[pos]] >= heavy_deg;
+        RootItem r{0xffffffffu, 0, false};
+        if (valid)
+            r = root_item(item, n_queries, q_vbase, jplan, cand_off, cand, lclass, deg, lcoff, n_labels, item_base, rank, world,
+                          heavy_deg);
+        // one atomic per (warp, query, class)
+        const unsigned peers = __match_any_sync(kFull, valid ? (r.q << 1 | (r.heavy ? 1u : 0u)) : 0xffffffffu);
+        const int leader = __ffs(peers) - 1;
+        u64 base = 0;
+        if (valid && lane == leader) {
+            u64 *qc = qcur + 5 * (u64)r.q;
+            base = r.heavy ? qc[1] + atomicAdd((unsigned long long *)&qc[3], (unsigned long long)__popc(peers))
+                           : qc[2] + atomicAdd((unsigned long long *)&qc[4], (unsigned long long)__popc(peers));
         }
-        const unsigned hm = __ballot_sync(kFull, valid && heavy), lm = __ballot_sync(kFull, valid && !heavy);
-        u64 h0 = 0, l0 = 0;
-        if (lane == 0) {
-            if (hm) h0 = atomicAdd((unsigned long long *)&cursors[0], (unsigned long long)__popc(hm));
-            if (lm) l0 = atomicAdd((unsigned long long *)&cursors[1], (unsigned long long)__popc(lm));
-        }
-        h0 = __shfl_sync(kFull, h0, 0);
-        l0 = __shfl_sync(kFull, l0, 0);
-        if (valid) {
-            const u64 at = heavy ? h0 + __popc(hm & lt) : n_items - 1 - (l0 + __popc(lm & lt));
-            init[at] = make_uint2(q, pos);
-        }
+        base = __shfl_sync(kFull, base, leader);
+        if (valid) init[base + __popc(peers & lt)] = make_uint2(r.q, r.pos);
     }
 }
 
@@ -585,10 +630,14 @@ __global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const
 // blockIdx.y = query vertex slot.
 __global__ void __launch_bounds__(256) k3_tree_tables_kernel(JoinGraph g, const TreeJob *__restrict__ tjobs,
                                                              const u32 *__restrict__ tchild, u32 level,
+                                                             const u32 *__restrict__ tcount,
+                                                             const u32 *__restrict__ tlist, u32 n_slots,
                                                              const u32 *__restrict__ bitmap, u64 words_per_slot,
                                                              u64 *tpool) {
-    const TreeJob job = tjobs[blockIdx.y];
-    if (job.level != level || job.label >= g.nl) return;
+  const u32 n_jobs = tcount[level];
+  for (u32 ji = blockIdx.y; ji < n_jobs; ji += gridDim.y) {
+    const TreeJob job = tjobs[tlist[(u64)level * n_slots + ji]];
+    if (job.label >= g.nl) continue;
     const u32 c0 = g.lcoff[job.label], n = g.lcoff[job.label + 1] - c0;
     for (u32 pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
         const u32 x = g.lclass[c0 + pos];
@@ -615,6 +664,7 @@ __global__ void __launch_bounds__(256) k3_tree_tables_kernel(JoinGraph g, const 
         }
         tpool[job.table_off + pos] = val;
     }
+  }
 }
 
 template <int M, int THREADS, int MINB>
@@ -1091,10 +1141,11 @@ cudaError_t k3_counts_from_offsets(const u64 *cand_off, u32 n_slots, u32 *counts
 cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebase, const u32 *q_offsets,
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
                      JoinDepth *jplan, void *kids, u64 *item_base, u32 rank, u32 world, bool enumerate, bool clean_start,
-                     u32 n_labels, const u32 *lcoff, TreeJob *tjobs, u32 *tchild, u64 *tcursor, cudaStream_t s) {
+                     u32 n_labels, const u32 *lcoff, TreeJob *tjobs, u32 *tchild, u64 *tcursor, u32 *tcount, u32 *tlist,
+                     u32 n_slots, cudaStream_t s) {
     k3_order_kernel<<<1, 256, 0, s>>>(n_queries, V, q_vbase, q_ebase, q_offsets, q_nbrs, q_labels, cand_off, order,
                                       pivot, jplan, reinterpret_cast<uint2 *>(kids), item_base, rank, world, 1, enumerate,
-                                      clean_start, n_labels, lcoff, tjobs, tchild, tcursor);
+                                      clean_start, n_labels, lcoff, tjobs, tchild, tcursor, tcount, tlist, n_slots);
     return cudaGetLastError();
 }
 
@@ -1110,19 +1161,26 @@ static JoinGraph join_graph(const JoinView &jv) {
 cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
                           const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world, u32 heavy_deg,
                           u64 *cursors, void *init, JoinQueue *jq, int sm_count, cudaStream_t s) {
+    k3_init_count_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, cand, jv.lclass, jv.deg, jv.lcoff,
+                                                     jv.nl, item_base, rank, world, heavy_deg, cursors);
+    k3_init_prefix_kernel<<<1, 32, 0, s>>>(n_queries, item_base, cursors, jq);
     k3_init_items_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, cand, jv.lclass, jv.deg, jv.lcoff,
                                                      jv.nl, item_base, rank, world, heavy_deg, cursors,
-                                                     reinterpret_cast<uint2 *>(init), jq);
+                                                     reinterpret_cast<uint2 *>(init));
     return cudaGetLastError();
 }
 
 cudaError_t k3_tree_tables(const JoinView &jv, u32 n_slots, u32 max_class, u32 max_level, const TreeJob *tjobs,
-                           const u32 *tchild, const u32 *bitmap, u64 words_per_slot, u64 *tpool, cudaStream_t s) {
+                           const u32 *tchild, const u32 *tcount, const u32 *tlist, const u32 *bitmap, u64 words_per_slot,
+                           u64 *tpool, int sm_count, cudaStream_t s) {
     if (n_slots == 0 || max_class == 0) return cudaSuccess;
     JoinGraph g = join_graph(jv);
-    dim3 grid(std::min<u32>((max_class + 255) / 256, 64), n_slots);
+    const u32 gy = std::min<u32>(n_slots, (u32)sm_count * 2);
+    const u32 gx = std::max<u32>(1, std::min<u32>((max_class + 255) / 256, ((u32)sm_count * 8 + gy - 1) / gy));
+    dim3 grid(gx, gy);
     for (u32 level = 1; level <= max_level; level++)
-        k3_tree_tables_kernel<<<grid, 256, 0, s>>>(g, tjobs, tchild, level, bitmap, words_per_slot, tpool);
+        k3_tree_tables_kernel<<<grid, 256, 0, s>>>(g, tjobs, tchild, level, tcount, tlist, n_slots, bitmap,
+                                                   words_per_slot, tpool);
     return cudaGetLastError();
 }
 
