@@ -54,6 +54,9 @@ GraphView graph_view(const gpe_ctx *c) {
     g.rank = c->d_rank.as<u32>();
     g.vde = c->d_vde.as<double>();
     g.e = c->e;
+    g.lpos = c->d_lpos.as<u32>();
+    g.lclass = c->d_lclass.as<u32>();
+    g.lcoff = c->d_lcoff.as<u32>();
     return g;
 }
 
@@ -132,7 +135,18 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
         prefix[b + 1] = prefix[b] + (blocks[b].t1 - blocks[b].t0);
     }
     c->b_items_unpruned = prefix[nb];
-    c->b_words = ((u64)(c->V + 31) / 32 + kChunkWords - 1) / kChunkWords * kChunkWords;
+    // candidate bitmaps are local to the slot's label class: bit i of slot s = the i-th vertex (by id) of label(s).
+    // 20x smaller than one bit per data vertex at 20 labels, so they stay in L2 while the table streams through
+    c->b_words = ((u64)(c->max_class + 31) / 32 + kChunkWords - 1) / kChunkWords * kChunkWords;
+    if (c->b_words == 0) c->b_words = kChunkWords;
+    {   // label of every slot, from the plan paths that cover it (an uncovered slot stays empty)
+        std::vector<u32> slot_label(std::max<u32>(n_slots, 1), 0xffffffffu);
+        for (u32 i = 0; i < n; i++)
+            for (u32 k = 0; k < L; k++) slot_label[qp.slots[(size_t)i * L + k]] = qp.labels[(size_t)i * L + k];
+        GPE_CUDA(c, c->d_slot_label.reserve(slot_label.size() * sizeof(u32)));
+        GPE_CUDA(c, cudaMemcpyAsync(c->d_slot_label.p, slot_label.data(), slot_label.size() * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+        GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     c->b_chunks_per_slot = c->b_words / kChunkWords;
 
     GPE_CUDA(c, c->d_qblocks.reserve(std::max<size_t>(recs.size(), 16)));
@@ -190,7 +204,8 @@ int compact_candidates(gpe_ctx *c) {
         GPE_CUDA(c, cudaMemsetAsync(c->d_cand_off.p, 0, sizeof(u64), c->stream));
     } else {
         GPE_CUDA(c, k3_compact(c->d_bitmap.as<u32>(), c->b_words, c->b_chunks_per_slot, c->b_slots,
-                               c->d_chunk_off.as<u64>(), c->d_cand.as<u32>(), c->d_cand_off.as<u64>(), c->stream));
+                               c->d_chunk_off.as<u64>(), c->d_slot_label.as<u32>(), c->d_lclass.as<u32>(),
+                               c->d_lcoff.as<u32>(), c->n_labels, c->d_cand.as<u32>(), c->d_cand_off.as<u64>(), c->stream));
     }
     c->stats.compact_launches += 3;
     c->stats.kernel_launches += 1 + exclusive_scan_launches(n_chunks + 1) + (n_chunks ? 1 : 0);
@@ -422,7 +437,7 @@ void gpe_destroy(gpe_ctx *c) {
     DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrL, &c->d_gtab, &c->d_lclass, &c->d_lpos, &c->d_lcoff, &c->d_bloom, &c->d_tjobs, &c->d_tchild, &c->d_tpool, &c->d_tcursor, &c->d_tlist, &c->d_qcur, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
                       &c->d_offr, &c->d_ebase, &c->d_start_rows, &c->d_scan_tmp, &c->d_tiles, &c->d_vids, &c->d_sum_u32, &c->d_sum_f64,
                       &c->d_bucket, &c->d_cursor, &c->d_qblocks, &c->d_qb_t0, &c->d_qb_prefix, &c->d_worklist,
-                      &c->d_counters, &c->d_bitmap, &c->d_survivors, &c->d_chunk_cnt, &c->d_chunk_off, &c->d_cand,
+                      &c->d_counters, &c->d_bitmap, &c->d_survivors, &c->d_slot_label, &c->d_chunk_cnt, &c->d_chunk_off, &c->d_cand,
                       &c->d_cand_off, &c->d_q_vbase, &c->d_q_ebase, &c->d_q_offsets, &c->d_q_nbrs, &c->d_q_labels,
                       &c->d_limits, &c->d_order, &c->d_pivot, &c->d_jplan, &c->d_item_base, &c->d_answers,
                       &c->d_matches, &c->d_match_cursor};
@@ -788,7 +803,7 @@ int gpe_dump_table(gpe_ctx *c, uint64_t first, uint64_t n, uint32_t *vids, uint3
     if (degs && e == cudaSuccess) e = dd.reserve(n * L * sizeof(u32));
     if (pde && e == cudaSuccess) e = dp.reserve(n * D * sizeof(double));
     if (e == cudaSuccess)
-        e = k1_dump_table(c->tv, first, n, vids ? dv.as<u32>() : nullptr, labels ? dl.as<u32>() : nullptr,
+        e = k1_dump_table(c->tv, graph_view(c), first, n, vids ? dv.as<u32>() : nullptr, labels ? dl.as<u32>() : nullptr,
                           degs ? dd.as<u32>() : nullptr, pde ? dp.as<double>() : nullptr, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (vids && e == cudaSuccess) e = cudaMemcpy(vids, dv.p, n * L * sizeof(u32), cudaMemcpyDeviceToHost);
@@ -993,8 +1008,8 @@ int gpe_batch_cand_merge(gpe_ctx *c, uint32_t world, const void *d_counts, const
     GPE_CUDA(c, cudaSetDevice(c->device));
     GPE_CUDA(c, cudaMemsetAsync(c->d_bitmap.p, 0, std::max<u64>((u64)c->b_slots * c->b_words, 1) * sizeof(u32), c->stream));
     GPE_CUDA(c, c->d_chunk_cnt.reserve(std::max<size_t>((size_t)world * c->b_slots, 1) * sizeof(u64)));
-    GPE_CUDA(c, k3_scatter((const u32 *)d_counts, (const u32 *)d_cand, stride, world, c->b_slots, c->d_bitmap.as<u32>(),
-                           c->b_words, c->d_chunk_cnt.as<u64>(), c->stream));
+    GPE_CUDA(c, k3_scatter((const u32 *)d_counts, (const u32 *)d_cand, stride, world, c->b_slots, c->d_lpos.as<u32>(),
+                           c->d_bitmap.as<u32>(), c->b_words, c->d_chunk_cnt.as<u64>(), c->stream));
     int rc = compact_candidates(c);
     if (rc) return rc;
     c->b_filtered = true;

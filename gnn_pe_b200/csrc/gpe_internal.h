@@ -72,11 +72,16 @@ struct GraphView {
     const u32 *rank;   // V: position in membership.txt
     const double *vde; // V x e
     u32 e;
+    const u32 *lpos;   // V: position of a vertex inside its label class
+    const u32 *lclass; // vertices by (label, id)
+    const u32 *lcoff;  // labels + 1 class offsets
 };
 
 // Physical layout of the path table: tile-major blocked structure-of-arrays.
 //   scan tile t (tile_bytes each): labels[L][R] u32 | degs[L][R] u32 | pde[L*e][R] f64
-//   vids tile t:                   vids[L][R] u32   (separate array, only survivors read it)
+//   vids tile t:                   vids[L][R] u32   (separate array, only survivors read it): the POSITION of the
+//                                  vertex inside its label class (lpos), which is the bit index of the candidate
+//                                  bitmaps; the id is lclass[lcoff[label] + position]
 struct TableView {
     u32 L, E, D;
     u64 n_rows, n_tiles;
@@ -217,7 +222,7 @@ struct gpe_ctx {
     std::vector<u32> h_q_vbase, h_q_ebase, h_q_offsets, h_q_nbrs, h_q_labels;
     std::vector<u64> h_limits;
     std::vector<u32> h_slot_query;  // slot -> query
-    gpe::DevBuf d_qblocks, d_qb_t0, d_qb_prefix, d_worklist, d_counters, d_bitmap, d_survivors;
+    gpe::DevBuf d_qblocks, d_qb_t0, d_qb_prefix, d_worklist, d_counters, d_bitmap, d_survivors, d_slot_label;
     gpe::DevBuf d_chunk_cnt, d_chunk_off, d_cand, d_cand_off;
     gpe::DevBuf d_q_vbase, d_q_ebase, d_q_offsets, d_q_nbrs, d_q_labels, d_limits;
     gpe::DevBuf d_order, d_pivot, d_jplan, d_item_base, d_answers, d_matches, d_match_cursor;
@@ -262,8 +267,8 @@ cudaError_t k1_histogram(const GraphView &g, const TableView &t, const u32 *sort
 cudaError_t k1_fill(const GraphView &g, const TableView &t, const u32 *sorted, const u32 *member,
                     const unsigned char *part_sel, u64 *cursor, int sm_count, cudaStream_t s);
 cudaError_t k1_summaries(const TableView &t, cudaStream_t s);
-cudaError_t k1_dump_table(const TableView &t, u64 first, u64 n, u32 *vids, u32 *labels, u32 *degs, double *pde,
-                          cudaStream_t s);
+cudaError_t k1_dump_table(const TableView &t, const GraphView &g, u64 first, u64 n, u32 *vids, u32 *labels, u32 *degs,
+                          double *pde, cudaStream_t s);
 
 // K2
 size_t qblock_rec_bytes(u32 L, u32 E);
@@ -281,10 +286,12 @@ bool k2_supported(u32 L, u32 E);
 constexpr u32 kChunkWords = 256;  // bitmap words per compaction chunk
 cudaError_t k3_chunk_count(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slot, u32 n_slots, u64 *chunk_cnt,
                            cudaStream_t s);
+// bit i of slot s stands for vertex lclass[lcoff[slot_label[s]] + i]
 cudaError_t k3_compact(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slot, u32 n_slots, const u64 *chunk_off,
-                       u32 *cand, u64 *cand_off, cudaStream_t s);
-cudaError_t k3_scatter(const u32 *counts, const u32 *cand, u64 stride, u32 world, u32 n_slots, u32 *bitmap,
-                       u64 words_per_slot, u64 *prefix_tmp /*world x n_slots*/, cudaStream_t s);
+                       const u32 *slot_label, const u32 *lclass, const u32 *lcoff, u32 n_labels, u32 *cand, u64 *cand_off,
+                       cudaStream_t s);
+cudaError_t k3_scatter(const u32 *counts, const u32 *cand, u64 stride, u32 world, u32 n_slots, const u32 *lpos,
+                       u32 *bitmap, u64 words_per_slot, u64 *prefix_tmp /*world x n_slots*/, cudaStream_t s);
 cudaError_t k3_counts_from_offsets(const u64 *cand_off, u32 n_slots, u32 *counts, cudaStream_t s);
 cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebase, const u32 *q_offsets,
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,

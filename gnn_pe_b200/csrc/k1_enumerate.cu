@@ -259,7 +259,7 @@ struct FillF {
         reinterpret_cast<u32 *>(base + 4u * L * kTileRows)[k * kTileRows + r] = dg;
         double *pde = reinterpret_cast<double *>(base + 8u * L * kTileRows);
         for (u32 x = 0; x < t.E; x++) pde[(k * t.E + x) * kTileRows + r] = g.vde[(u64)v * t.E + x];
-        t.vids[(tile * L + k) * kTileRows + r] = v;
+        t.vids[(tile * L + k) * kTileRows + r] = g.lpos[v];  // bit index of the candidate bitmaps
     }
     __device__ void chunk(u32 b, u32 c, u32 d, bool valid) {
         unsigned act = __ballot_sync(kFull, valid);
@@ -350,7 +350,8 @@ __global__ void __launch_bounds__(kTileRows) k1_summary_kernel(TableView t) {
     }
 }
 
-__global__ void k1_dump_table_kernel(TableView t, u64 first, u64 n, u32 *vids, u32 *labels, u32 *degs, double *pde) {
+__global__ void k1_dump_table_kernel(TableView t, GraphView g, u64 first, u64 n, u32 *vids, u32 *labels, u32 *degs,
+                                     double *pde) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u64 row = first + i;
@@ -361,7 +362,7 @@ __global__ void k1_dump_table_kernel(TableView t, u64 first, u64 n, u32 *vids, u
     const u32 *dg = reinterpret_cast<const u32 *>(base + 4u * t.L * kTileRows);
     const double *pd = reinterpret_cast<const double *>(base + 8u * t.L * kTileRows);
     for (u32 k = 0; k < t.L; k++) {
-        if (vids) vids[i * t.L + k] = t.vids[(tile * t.L + k) * kTileRows + r];
+        if (vids) vids[i * t.L + k] = g.lclass[g.lcoff[lab[k * kTileRows + r]] + t.vids[(tile * t.L + k) * kTileRows + r]];
         if (labels) labels[i * t.L + k] = lab[k * kTileRows + r];
         if (degs) degs[i * t.L + k] = dg[k * kTileRows + r];
     }
@@ -465,10 +466,10 @@ cudaError_t k1_summaries(const TableView &t, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t k1_dump_table(const TableView &t, u64 first, u64 n, u32 *vids, u32 *labels, u32 *degs, double *pde,
-                          cudaStream_t s) {
+cudaError_t k1_dump_table(const TableView &t, const GraphView &g, u64 first, u64 n, u32 *vids, u32 *labels, u32 *degs,
+                          double *pde, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    k1_dump_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t, first, n, vids, labels, degs, pde);
+    k1_dump_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t, g, first, n, vids, labels, degs, pde);
     return cudaGetLastError();
 }
 

@@ -156,8 +156,9 @@ k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u
     using G = ScanGeom<L, E, VIDS>;
     constexpr int D = G::D;
     constexpr int NS = G::kNumStages;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // (no manual re-alignment through an integer cast: it would hide the shared address space from the compiler and
+    //  turn every read of the stage into a generic load; bulk copies need 16 bytes, the declaration asks for 128)
+    extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *ring = smem;
     u64 *full_bar = reinterpret_cast<u64 *>(smem + NS * G::kStageBytes);
     u64 *empty_bar = full_bar + NS;
@@ -240,12 +241,15 @@ k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u
             const u32 nq = rec->n;
             u32 okm = 0;  // plan paths of the block this row survives
             for (u32 j = 0; j < nq; j++) {
+                // label/degree test and embedding test are each branch-free (broadcast shared-memory reads, no
+                // serialising short-circuits); the FP64 part is skipped by rows that already failed -- in streaming
+                // mode that is nearly all of them, and the FP64 pipe would otherwise bound the scan
                 bool ok = valid;
 #pragma unroll
-                for (int kk = 0; kk < L; kk++) ok = ok && (rec->labels[j][kk] == lab[kk]) && (rec->degs[j][kk] <= dg[kk]);
+                for (int kk = 0; kk < L; kk++) ok &= (rec->labels[j][kk] == lab[kk]) & (rec->degs[j][kk] <= dg[kk]);
                 if (ok) {
 #pragma unroll
-                    for (int d = 0; d < D; d++) ok = ok && !(rec->pde[j][d] - pde[d] > kEps);
+                    for (int d = 0; d < D; d++) ok &= !(rec->pde[j][d] - pde[d] > kEps);
                 }
                 const unsigned m = __ballot_sync(kFull, ok);
                 if (lane == (int)j) my_cnt += __popc(m);

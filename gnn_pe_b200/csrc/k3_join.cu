@@ -51,8 +51,11 @@ __global__ void __launch_bounds__(256) k3_chunk_count_kernel(const u32 *__restri
 
 __global__ void __launch_bounds__(256) k3_compact_kernel(const u32 *__restrict__ bitmap, u64 words_per_slot,
                                                          u64 chunks_per_slot, u64 n_chunks, u32 n_slots,
-                                                         const u64 *__restrict__ chunk_off, u32 *__restrict__ cand,
-                                                         u64 *__restrict__ cand_off) {
+                                                         const u64 *__restrict__ chunk_off,
+                                                         const u32 *__restrict__ slot_label,
+                                                         const u32 *__restrict__ lclass,
+                                                         const u32 *__restrict__ lcoff, u32 n_labels,
+                                                         u32 *__restrict__ cand, u64 *__restrict__ cand_off) {
     const int lane = threadIdx.x & 31;
     u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n_chunks) return;
@@ -65,6 +68,9 @@ __global__ void __launch_bounds__(256) k3_compact_kernel(const u32 *__restrict__
     if (chunk_off[w + 1] == out) return;
     const u32 *p = bitmap + slot * words_per_slot + c * kChunkWords;
     u32 vbase = (u32)(c * kChunkWords * 32);
+    // bit -> vertex: positions inside the slot's label class (ascending position = ascending id)
+    const u32 sl = slot_label[slot];
+    const u32 *cls = lclass + (sl < n_labels ? lcoff[sl] : 0);
     for (int i = 0; i < (int)kChunkWords / 32; i++) {
         u32 word = p[i * 32 + lane];
         u32 n = __popc(word), inc = n;
@@ -78,7 +84,7 @@ __global__ void __launch_bounds__(256) k3_compact_kernel(const u32 *__restrict__
         while (word) {
             int b = __ffs(word) - 1;
             word &= word - 1;
-            cand[my++] = v0 + b;
+            cand[my++] = cls[v0 + b];
         }
         out += __shfl_sync(kFull, inc, 31);
     }
@@ -97,13 +103,14 @@ __global__ void k3_scatter_prefix_kernel(const u32 *__restrict__ counts, u32 wor
 
 __global__ void __launch_bounds__(256) k3_scatter_kernel(const u32 *__restrict__ counts, const u32 *__restrict__ cand,
                                                          const u64 *__restrict__ prefix, u64 stride, u32 world,
-                                                         u32 n_slots, u32 *bitmap, u64 words_per_slot) {
+                                                         u32 n_slots, const u32 *__restrict__ lpos, u32 *bitmap,
+                                                         u64 words_per_slot) {
     for (u32 job = blockIdx.x; job < world * n_slots; job += gridDim.x) {
         u32 r = job / n_slots, slot = job % n_slots;
         u32 n = counts[(u64)r * n_slots + slot];
         const u32 *list = cand + (u64)r * stride + prefix[(u64)r * n_slots + slot];
         for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
-            u32 v = list[i];
+            u32 v = lpos[list[i]];  // candidates of a slot all carry the slot's label: the bit is the class position
             atomicOr(bitmap + (u64)slot * words_per_slot + (v >> 5), 1u << (v & 31));
         }
     }
@@ -655,8 +662,9 @@ __global__ void __launch_bounds__(256) k3_tree_tables_kernel(JoinGraph g, const 
                     for (u32 at = s; at < e; at++) {
                         const uint2 yd = g.nbrL[at];
                         if (yd.y < cj.qdeg) continue;
-                        if (bm && !(bm[yd.x >> 5] >> (yd.x & 31) & 1)) continue;
-                        sum += cj.level ? tpool[cj.table_off + g.lpos[yd.x]] : 1;
+                        const u32 yp = g.lpos[yd.x];
+                        if (bm && !(bm[yp >> 5] >> (yp & 31) & 1)) continue;
+                        sum += cj.level ? tpool[cj.table_off + yp] : 1;
                     }
                 }
             }
@@ -1114,21 +1122,22 @@ cudaError_t k3_chunk_count(const u32 *bitmap, u64 words_per_slot, u64 chunks_per
 }
 
 cudaError_t k3_compact(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slot, u32 n_slots, const u64 *chunk_off,
-                       u32 *cand, u64 *cand_off, cudaStream_t s) {
+                       const u32 *slot_label, const u32 *lclass, const u32 *lcoff, u32 n_labels, u32 *cand, u64 *cand_off,
+                       cudaStream_t s) {
     u64 n_chunks = chunks_per_slot * n_slots;
     if (n_chunks == 0) return cudaSuccess;
     k3_compact_kernel<<<(unsigned)((n_chunks * 32 + 255) / 256), 256, 0, s>>>(bitmap, words_per_slot, chunks_per_slot,
-                                                                             n_chunks, n_slots, chunk_off, cand,
-                                                                             cand_off);
+                                                                             n_chunks, n_slots, chunk_off, slot_label,
+                                                                             lclass, lcoff, n_labels, cand, cand_off);
     return cudaGetLastError();
 }
 
-cudaError_t k3_scatter(const u32 *counts, const u32 *cand, u64 stride, u32 world, u32 n_slots, u32 *bitmap,
-                       u64 words_per_slot, u64 *prefix_tmp, cudaStream_t s) {
+cudaError_t k3_scatter(const u32 *counts, const u32 *cand, u64 stride, u32 world, u32 n_slots, const u32 *lpos,
+                       u32 *bitmap, u64 words_per_slot, u64 *prefix_tmp, cudaStream_t s) {
     if (world * n_slots == 0) return cudaSuccess;
     k3_scatter_prefix_kernel<<<(world + 31) / 32, 32, 0, s>>>(counts, world, n_slots, prefix_tmp);
     unsigned blocks = std::min<unsigned>(world * n_slots, 148 * 8);
-    k3_scatter_kernel<<<blocks, 256, 0, s>>>(counts, cand, prefix_tmp, stride, world, n_slots, bitmap, words_per_slot);
+    k3_scatter_kernel<<<blocks, 256, 0, s>>>(counts, cand, prefix_tmp, stride, world, n_slots, lpos, bitmap, words_per_slot);
     return cudaGetLastError();
 }
 
