@@ -1184,8 +1184,10 @@ cudaError_t k3_tree_tables(const JoinView &jv, u32 n_slots, u32 max_class, u32 m
                            u64 *tpool, int sm_count, cudaStream_t s) {
     if (n_slots == 0 || max_class == 0) return cudaSuccess;
     JoinGraph g = join_graph(jv);
+    // a level may hold a handful of tables only (chains are peeled one level at a time), so a table gets up to 64
+    // blocks of its own; rows of the grid beyond the level's job count exit at once
     const u32 gy = std::min<u32>(n_slots, (u32)sm_count * 2);
-    const u32 gx = std::max<u32>(1, std::min<u32>((max_class + 255) / 256, ((u32)sm_count * 8 + gy - 1) / gy));
+    const u32 gx = std::max<u32>(1, std::min<u32>((max_class + 255) / 256, 64));
     dim3 grid(gx, gy);
     for (u32 level = 1; level <= max_level; level++)
         k3_tree_tables_kernel<<<grid, 256, 0, s>>>(g, tjobs, tchild, level, tcount, tlist, n_slots, bitmap,
