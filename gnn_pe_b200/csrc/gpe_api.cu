@@ -57,6 +57,7 @@ GraphView graph_view(const gpe_ctx *c) {
     g.lpos = c->d_lpos.as<u32>();
     g.lclass = c->d_lclass.as<u32>();
     g.lcoff = c->d_lcoff.as<u32>();
+    g.nbrL = c->d_nbrL.as<uint2>();
     return g;
 }
 

@@ -75,6 +75,7 @@ struct GraphView {
     const u32 *lpos;   // V: position of a vertex inside its label class
     const u32 *lclass; // vertices by (label, id)
     const u32 *lcoff;  // labels + 1 class offsets
+    const uint2 *nbrL; // adjacency grouped by neighbour label (neighbour, its degree); same offsets as nbr
 };
 
 // Physical layout of the path table: tile-major blocked structure-of-arrays.

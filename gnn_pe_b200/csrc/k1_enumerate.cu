@@ -91,7 +91,11 @@ __global__ void scan_apply_kernel(u64 *data, u64 n, const u64 *block_offsets) {
 // ------------------------------------------------------------------------------------------------
 // The walk: one warp, one start vertex `a` (rank ra).  F is a functor with warp-uniform hooks.
 // ------------------------------------------------------------------------------------------------
-template <int L, class F>
+// GROUPED: the innermost adjacency list is read in label-grouped order (nbrL) instead of id order.  The set of rows
+// is the same; consecutive lanes then mostly share a label, hence a table bucket, and the fill writes runs of
+// consecutive rows (full sectors) instead of one row per bucket.  Only for the order-insensitive passes (histogram,
+// fill): count and dump reproduce the reference's order and walk by id.
+template <int L, bool GROUPED, class F>
 __device__ __forceinline__ void walk_start_vertex(const GraphView &g, u32 a, u32 ra, int lane, F &f) {
     const u32 a0 = g.off[a], a1 = g.off[a + 1];
     for (u32 s = a0; s < a1; ++s) {
@@ -102,7 +106,7 @@ __device__ __forceinline__ void walk_start_vertex(const GraphView &g, u32 a, u32
             for (u32 j = b0; j < b1; j += 32) {
                 u32 jj = j + lane;
                 bool in = jj < b1;
-                u32 c = in ? g.nbr[jj] : 0u;
+                u32 c = in ? (GROUPED ? g.nbrL[jj].x : g.nbr[jj]) : 0u;
                 bool valid = in && g.rank[c] > ra;  // c != a follows from the strict rank test
                 f.chunk(b, c, 0u, valid);
             }
@@ -114,7 +118,7 @@ __device__ __forceinline__ void walk_start_vertex(const GraphView &g, u32 a, u32
                 for (u32 j = c0; j < c1; j += 32) {
                     u32 jj = j + lane;
                     bool in = jj < c1;
-                    u32 d = in ? g.nbr[jj] : 0u;
+                    u32 d = in ? (GROUPED ? g.nbrL[jj].x : g.nbr[jj]) : 0u;
                     bool valid = in && d != b && g.rank[d] > ra;  // d != a by rank, d != c: no loops
                     f.chunk(b, c, d, valid);
                 }
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(256) k1_count_kernel(GraphView g, const u32 *_
     for (u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < g.V; i += nwarps) {
         u32 a = sorted[i];
         CountF f{cnt_r + offr[i], 0, lane};
-        walk_start_vertex<L>(g, a, i, lane, f);
+        walk_start_vertex<L, false>(g, a, i, lane, f);
     }
 }
 
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(256) k1_dump_kernel(GraphView g, const u32 *__
     const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
     for (u32 i = rank_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i <= rank_hi && i < g.V; i += nwarps) {
         DumpF<L> f{ebase + offr[i], sorted[i], first, n, out, 0, lane};
-        walk_start_vertex<L>(g, sorted[i], i, lane, f);
+        walk_start_vertex<L, false>(g, sorted[i], i, lane, f);
     }
 }
 
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(256) k1_hist_kernel(GraphView g, KeyParams kp,
         u32 a = sorted[i];
         if (part_sel && !part_sel[member[a]]) continue;
         HistF<L> f{g, kp, hist, key_term(kp, 0, g.label[a]), 0};
-        walk_start_vertex<L>(g, a, i, lane, f);
+        walk_start_vertex<L, true>(g, a, i, lane, f);
     }
 }
 
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(256) k1_fill_kernel(GraphView g, KeyParams kp,
         u32 a = sorted[i];
         if (part_sel && !part_sel[member[a]]) continue;
         FillF<L> f{g, kp, t, cursor, a, key_term(kp, 0, g.label[a]), 0};
-        walk_start_vertex<L>(g, a, i, lane, f);
+        walk_start_vertex<L, true>(g, a, i, lane, f);
     }
 }
 
