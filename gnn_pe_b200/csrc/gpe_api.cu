@@ -172,6 +172,7 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
     GPE_CUDA(c, cudaMemcpyAsync(c->d_qb_t0.p, pin + o_t0, (nb + 1) * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
     GPE_CUDA(c, cudaMemcpyAsync(c->d_qb_prefix.p, pin + o_pf, (nb + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
     c->stats.h2d_bytes += recs.size() + (nb + 1) * (sizeof(u32) + sizeof(u64));
+    c->b_scanned = false;
     c->b_filtered = false;
     c->b_joined = false;
     c->stats.n_qpaths = n;
@@ -181,15 +182,20 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
     return GPE_OK;
 }
 
-// bitmap -> sorted candidate lists (d_cand, d_cand_off); one host sync for the total
-int compact_candidates(gpe_ctx *c) {
+// bitmap -> sorted candidate lists (d_cand, d_cand_off); one host sync for the total.  With d_all != null the bitmaps
+// are first replaced by the union of `world` all-gathered shard bitmaps (same kernel as the popcount pass).
+int compact_candidates(gpe_ctx *c, const u32 *d_all = nullptr, u32 world = 0) {
     StageTimer tm(c, &c->stats.last_compact_ms, kStageCompact);
     const u64 n_chunks = c->b_chunks_per_slot * c->b_slots;
     GPE_CUDA(c, c->d_chunk_off.reserve((n_chunks + 1) * sizeof(u64)));
     GPE_CUDA(c, c->d_cand_off.reserve(((u64)c->b_slots + 1) * sizeof(u64)));
     GPE_CUDA(c, c->d_counters.reserve(8 * sizeof(u64)));
-    GPE_CUDA(c, k3_chunk_count(c->d_bitmap.as<u32>(), c->b_words, c->b_chunks_per_slot, c->b_slots,
-                               c->d_chunk_off.as<u64>(), c->stream));
+    if (d_all)
+        GPE_CUDA(c, k3_merge_count(d_all, (u64)c->b_slots * c->b_words, world, c->d_bitmap.as<u32>(), c->b_words,
+                                   c->b_chunks_per_slot, c->b_slots, c->d_chunk_off.as<u64>(), c->stream));
+    else
+        GPE_CUDA(c, k3_chunk_count(c->d_bitmap.as<u32>(), c->b_words, c->b_chunks_per_slot, c->b_slots,
+                                   c->d_chunk_off.as<u64>(), c->stream));
     GPE_CUDA(c, exclusive_scan_u64(c->d_chunk_off.as<u64>(), n_chunks + 1, c->d_scan_tmp, c->stream));
     GPE_CUDA(c, c->h_pin2.reserve(16 * sizeof(u64)));
     u64 *pin = c->h_pin2.as<u64>();
@@ -214,7 +220,8 @@ int compact_candidates(gpe_ctx *c) {
     return GPE_OK;
 }
 
-int run_filter(gpe_ctx *c) {
+// select + scan: the candidate bitmaps of this GPU's table (shard) are on the device afterwards
+int run_scan(gpe_ctx *c) {
     const u64 n_items = c->b_items_unpruned;
     GPE_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(u64), c->stream));
     GPE_CUDA(c, cudaMemsetAsync(c->d_survivors.p, 0, std::max<u32>(c->b_qpaths, 1) * sizeof(u64), c->stream));
@@ -237,8 +244,15 @@ int run_filter(gpe_ctx *c) {
             c->stats.kernel_launches++;
         }
     }
-    int rc = compact_candidates(c);
+    c->b_scanned = true;
+    c->b_filtered = false;
+    return GPE_OK;
+}
+
+int run_filter(gpe_ctx *c) {
+    int rc = run_scan(c);
     if (rc) return rc;
+    if ((rc = compact_candidates(c))) return rc;
     c->b_filtered = true;
     c->b_cand_external = false;
     c->b_cand_clean = true;  // every candidate of a slot carries the slot's label, and the slot's bitmap is on the device
@@ -1012,6 +1026,33 @@ int gpe_batch_cand_merge(gpe_ctx *c, uint32_t world, const void *d_counts, const
     GPE_CUDA(c, k3_scatter((const u32 *)d_counts, (const u32 *)d_cand, stride, world, c->b_slots, c->d_lpos.as<u32>(),
                            c->d_bitmap.as<u32>(), c->b_words, c->d_chunk_cnt.as<u64>(), c->stream));
     int rc = compact_candidates(c);
+    if (rc) return rc;
+    c->b_filtered = true;
+    c->b_cand_external = true;
+    c->b_cand_clean = true;  // a union of filter outputs
+    return GPE_OK;
+}
+
+int gpe_batch_scan(gpe_ctx *c) {
+    if (!c) return GPE_ERR_INVALID;
+    if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    return run_scan(c);
+}
+
+int gpe_batch_bitmap(gpe_ctx *c, void **d_bitmap, uint64_t *n_bytes) {
+    if (!c) return GPE_ERR_INVALID;
+    if (!c->b_scanned && !c->b_filtered) return c->fail(GPE_ERR_INVALID, "gpe_batch_scan first");
+    if (d_bitmap) *d_bitmap = c->d_bitmap.p;
+    if (n_bytes) *n_bytes = (u64)c->b_slots * c->b_words * sizeof(u32);
+    return GPE_OK;
+}
+
+int gpe_batch_bitmap_merge(gpe_ctx *c, uint32_t world, const void *d_all) {
+    if (!c || !d_all || world == 0) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
+    if (!c->b_scanned && !c->b_filtered) return c->fail(GPE_ERR_INVALID, "gpe_batch_scan first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    int rc = compact_candidates(c, (const u32 *)d_all, world);
     if (rc) return rc;
     c->b_filtered = true;
     c->b_cand_external = true;

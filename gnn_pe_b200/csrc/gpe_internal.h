@@ -219,7 +219,7 @@ struct gpe_ctx {
     u64 b_words = 0;       // bitmap words per slot
     u64 b_items_cap = 0, b_items_unpruned = 0;
     u64 b_n_cand = 0;
-    bool b_filtered = false, b_joined = false, b_cand_external = false, b_cand_clean = false;
+    bool b_scanned = false, b_filtered = false, b_joined = false, b_cand_external = false, b_cand_clean = false;
     std::vector<u32> h_q_vbase, h_q_ebase, h_q_offsets, h_q_nbrs, h_q_labels;
     std::vector<u64> h_limits;
     std::vector<u32> h_slot_query;  // slot -> query
@@ -287,6 +287,9 @@ bool k2_supported(u32 L, u32 E);
 constexpr u32 kChunkWords = 256;  // bitmap words per compaction chunk
 cudaError_t k3_chunk_count(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slot, u32 n_slots, u64 *chunk_cnt,
                            cudaStream_t s);
+// same, fused with the union of `world` all-gathered shard bitmaps (shard r at all + r * shard_words) into `bitmap`
+cudaError_t k3_merge_count(const u32 *all, u64 shard_words, u32 world, u32 *bitmap, u64 words_per_slot,
+                           u64 chunks_per_slot, u32 n_slots, u64 *chunk_cnt, cudaStream_t s);
 // bit i of slot s stands for vertex lclass[lcoff[slot_label[s]] + i]
 cudaError_t k3_compact(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slot, u32 n_slots, const u64 *chunk_off,
                        const u32 *slot_label, const u32 *lclass, const u32 *lcoff, u32 n_labels, u32 *cand, u64 *cand_off,

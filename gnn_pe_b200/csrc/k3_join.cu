@@ -49,6 +49,34 @@ __global__ void __launch_bounds__(256) k3_chunk_count_kernel(const u32 *__restri
     if (lane == 0) chunk_cnt[w] = n;
 }
 
+// Multi-GPU merge fused with the popcount pass: word = OR over the `world` shards' bitmaps (all-gathered, one after
+// the other, `shard_words` apart), stored into this GPU's bitmap and counted per chunk.  A path belongs to the shard of
+// its FIRST vertex (custom.h:74) but sets bits for all its vertices, so the shards' sets overlap: the union is an OR.
+__global__ void __launch_bounds__(256) k3_merge_count_kernel(const u32 *__restrict__ all, u64 shard_words, u32 world,
+                                                             u32 *__restrict__ bitmap, u64 words_per_slot,
+                                                             u64 chunks_per_slot, u64 n_chunks,
+                                                             u64 *__restrict__ chunk_cnt) {
+    const int lane = threadIdx.x & 31;
+    u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_chunks) {
+        if (w == n_chunks && lane == 0) chunk_cnt[n_chunks] = 0;
+        return;
+    }
+    const u64 slot = w / chunks_per_slot, c = w % chunks_per_slot;
+    const u64 at = slot * words_per_slot + c * kChunkWords;
+    u32 n = 0;
+#pragma unroll
+    for (int i = 0; i < (int)kChunkWords / 32; i++) {
+        u32 word = 0;
+        for (u32 r = 0; r < world; r++) word |= __ldcs(all + (u64)r * shard_words + at + i * 32 + lane);
+        bitmap[at + i * 32 + lane] = word;
+        n += __popc(word);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(kFull, n, o);
+    if (lane == 0) chunk_cnt[w] = n;
+}
+
 __global__ void __launch_bounds__(256) k3_compact_kernel(const u32 *__restrict__ bitmap, u64 words_per_slot,
                                                          u64 chunks_per_slot, u64 n_chunks, u32 n_slots,
                                                          const u64 *__restrict__ chunk_off,
@@ -1118,6 +1146,15 @@ cudaError_t k3_chunk_count(const u32 *bitmap, u64 words_per_slot, u64 chunks_per
     u64 warps = n_chunks + 1;
     k3_chunk_count_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(bitmap, words_per_slot, chunks_per_slot,
                                                                               n_chunks, chunk_cnt);
+    return cudaGetLastError();
+}
+
+cudaError_t k3_merge_count(const u32 *all, u64 shard_words, u32 world, u32 *bitmap, u64 words_per_slot,
+                           u64 chunks_per_slot, u32 n_slots, u64 *chunk_cnt, cudaStream_t s) {
+    u64 n_chunks = chunks_per_slot * n_slots;
+    u64 warps = n_chunks + 1;
+    k3_merge_count_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(all, shard_words, world, bitmap, words_per_slot,
+                                                                              chunks_per_slot, n_chunks, chunk_cnt);
     return cudaGetLastError();
 }
 

@@ -63,6 +63,7 @@ SYMBOLS = [
     "gpe_start_rows", "gpe_build_table", "gpe_dump_table", "gpe_filter", "gpe_get_candidates", "gpe_refine",
     "gpe_batch_upload", "gpe_batch_filter", "gpe_batch_join", "gpe_batch_download", "gpe_clamp_answer",
     "gpe_query_batch", "gpe_batch_cand_info", "gpe_batch_cand_export", "gpe_batch_cand_merge",
+    "gpe_batch_scan", "gpe_batch_bitmap", "gpe_batch_bitmap_merge",
     "gpe_batch_get_candidates", "gpe_batch_get_plan", "gpe_get_stats", "gpe_stream", "gpe_sync", "gpe_set_timing",
     "gpe_collect_timings",
 ]
@@ -105,6 +106,9 @@ def lib():
         L.gpe_batch_cand_info.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
         L.gpe_batch_cand_export.argtypes = [vp, vp, vp]
         L.gpe_batch_cand_merge.argtypes = [vp, u32, vp, vp, u64]
+        L.gpe_batch_scan.argtypes = [vp]
+        L.gpe_batch_bitmap.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+        L.gpe_batch_bitmap_merge.argtypes = [vp, u32, vp]
         L.gpe_batch_get_candidates.argtypes = [vp, vp, vp]
         L.gpe_batch_get_plan.argtypes = [vp, vp, vp]
         L.gpe_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -337,6 +341,18 @@ class GpeContext:
 
     def batch_cand_merge(self, world: int, d_counts_ptr: int, d_cand_ptr: int, stride: int):
         self._ck(self._L.gpe_batch_cand_merge(self._h, world, d_counts_ptr, d_cand_ptr, stride))
+
+    def batch_scan(self):
+        self._ck(self._L.gpe_batch_scan(self._h))
+
+    def batch_bitmap(self):
+        """(device pointer, bytes) of the batch's candidate bitmaps."""
+        p, n = C.c_void_p(), C.c_uint64(0)
+        self._ck(self._L.gpe_batch_bitmap(self._h, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def batch_bitmap_merge(self, world: int, d_all_ptr: int):
+        self._ck(self._L.gpe_batch_bitmap_merge(self._h, world, d_all_ptr))
 
     def batch_get_candidates(self):
         n_slots, total = self.batch_cand_info()

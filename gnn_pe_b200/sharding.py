@@ -4,8 +4,11 @@ The reference is single-process; its only parallelism is one OpenMP thread per g
 std::set results are merged serially (src/main.cpp:160-172).  Here GPU `r` of `world` owns the partitions
 `i % world == r` (a path belongs to the partition of its FIRST vertex, custom.h:74), scans only its own
 path table, and the serial merge becomes
-  C1: a variable-length all-gather of the per-query-vertex sorted candidate lists (counts, then lists padded
-      to the longest shard), followed by a device-side union (gpe_batch_cand_merge);
+  C1: an all-gather of the shards' candidate bitmaps (fixed size: one bit per vertex of the slot's label class,
+      identical layout on every shard, so there is no count exchange and no host sync), whose union is fused
+      into the compaction's popcount pass (gpe_batch_bitmap_merge).  The list form of the same exchange
+      (allgather_candidates + gpe_batch_cand_merge: counts, then lists padded to the longest shard) is kept
+      for callers that hold sorted lists;
   C2: an all-reduce(sum) of the per-query match counts after the join has been split by start candidate.
 The CSR, labels and vertex embeddings are replicated, so the join needs no other exchange.
 These helpers are backend-agnostic (NCCL on GPUs, gloo in the CPU tests).
@@ -46,6 +49,26 @@ def allgather_candidates(counts: torch.Tensor, cand: torch.Tensor, group=None):
     return all_counts.view(world, -1), all_cand.view(world, stride), stride
 
 
+class _DevMem:
+    """A span of device memory owned by libgpe, exposed through __cuda_array_interface__ (zero-copy torch view)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = dict(shape=(nbytes,), typestr="|u1", data=(ptr, False), version=3, strides=None)
+
+
+def allgather_bitmaps(local: torch.Tensor, group=None) -> torch.Tensor:
+    """C1, bitmap form.  local: uint8 [n_bytes] (this shard's candidate bitmaps).  Returns uint8 [world, n_bytes]."""
+    world = dist.get_world_size(group)
+    out = torch.empty(world * local.numel(), dtype=torch.uint8, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out.view(world, local.numel())
+
+
+def union_bitmaps_reference(all_bitmaps: np.ndarray) -> np.ndarray:
+    """Host statement of what gpe_batch_bitmap_merge computes: the OR of the shards' bitmaps."""
+    return np.bitwise_or.reduce(all_bitmaps, axis=0)
+
+
 def union_reference(all_counts: np.ndarray, all_cand: np.ndarray):
     """Host statement of what gpe_batch_cand_merge computes: per slot, the sorted union of the shards' lists."""
     world, n_slots = all_counts.shape
@@ -80,6 +103,19 @@ class ShardedEngine:
         return n_rows, rows_pp, table_rows
 
     def exchange(self):
+        """C1 on the context's stream: NCCL orders the all-gather after the scan and the merge after the all-gather,
+        no host sync in between."""
+        ptr, nbytes = self.ctx.batch_bitmap()
+        stream = torch.cuda.ExternalStream(self.ctx.stream)
+        with torch.cuda.stream(stream):
+            if nbytes == 0:
+                return self.ctx.batch_bitmap_merge(1, ptr)
+            local = torch.as_tensor(_DevMem(ptr, nbytes), device="cuda")
+            self._all = allgather_bitmaps(local)  # kept alive until the next exchange
+            self.ctx.batch_bitmap_merge(self.world, self._all.data_ptr())
+
+    def exchange_lists(self):
+        """The list form of C1 (sorted candidate lists, variable length)."""
         n_slots, total = self.ctx.batch_cand_info()
         counts = torch.empty(max(n_slots, 1), dtype=torch.int32, device="cuda")
         cand = torch.zeros(max(total, 1), dtype=torch.int32, device="cuda")
@@ -88,10 +124,15 @@ class ShardedEngine:
         torch.cuda.current_stream().synchronize()
         self.ctx.batch_cand_merge(self.world, all_counts.data_ptr(), all_cand.data_ptr(), stride)
 
-    def step(self):
-        """filter (local shard) -> C1 -> join (this rank's start candidates).  Batch must be uploaded."""
-        self.ctx.batch_filter()
-        if self.world > 1:
+    def step(self, lists: bool = False):
+        """scan (local shard) -> C1 -> join (this rank's start candidates).  Batch must be uploaded."""
+        if self.world == 1:
+            self.ctx.batch_filter()
+        elif lists:
+            self.ctx.batch_filter()
+            self.exchange_lists()
+        else:
+            self.ctx.batch_scan()
             self.exchange()
         self.ctx.batch_join(self.rank, self.world)
 

@@ -148,6 +148,17 @@ int gpe_batch_cand_export(gpe_ctx *ctx, void *d_counts_u32 /*n_slots*/, void *d_
 /* Replace the batch's candidate sets by the union of `world` shards' lists.  d_counts: world x n_slots
  * (u32), d_cand: world x stride (u32), shard r's lists concatenated at d_cand + r*stride. */
 int gpe_batch_cand_merge(gpe_ctx *ctx, uint32_t world, const void *d_counts, const void *d_cand, uint64_t stride);
+/* The same exchange in bitmap form, the one the multi-GPU engine uses: fixed size (no count exchange, no host
+ * sync), one all-gather, and the union is fused into the compaction's popcount pass.
+ *   gpe_batch_scan         stage 2 without the compaction: tile selection + dominance scan of the local shard;
+ *   gpe_batch_bitmap       device pointer and size of the batch's candidate bitmaps: n_slots x words, bit i of slot s
+ *                          = the i-th vertex (ascending id) of the slot's label -- identical layout on every shard;
+ *   gpe_batch_bitmap_merge d_all = `world` such bitmaps one after the other (the all-gather's output, device memory);
+ *                          replaces the local bitmaps by their OR and builds the sorted candidate lists.
+ * All three are asynchronous on the context's stream up to the one host read of the candidate total. */
+int gpe_batch_scan(gpe_ctx *ctx);
+int gpe_batch_bitmap(gpe_ctx *ctx, void **d_bitmap, uint64_t *n_bytes);
+int gpe_batch_bitmap_merge(gpe_ctx *ctx, uint32_t world, const void *d_all);
 /* Per-query-vertex candidate counts / lists of the current batch (after filter or merge), host side. */
 int gpe_batch_get_candidates(gpe_ctx *ctx, uint64_t *cand_offsets /*n_slots+1*/, uint32_t *cand /*or NULL*/);
 int gpe_batch_get_plan(gpe_ctx *ctx, uint32_t *order /*n_slots*/, uint32_t *pivot /*n_slots*/);

@@ -6,7 +6,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from gnn_pe_b200 import gpe, graph_io, synth
+from gnn_pe_b200 import gpe, graph_io, sharding, synth
 from tests.golden_util import CASES, load_case
 
 pytestmark = pytest.mark.gpu
@@ -298,6 +298,49 @@ def test_two_shards_in_one_process_match_single_gpu():
         raw += c.batch_download()
     got = [ctxs[0].clamp(int(x), l) for x, l in zip(raw, limits)]
     assert got == want
+    for c in ctxs:
+        c.close()
+
+
+def test_two_shards_bitmap_exchange_matches_single_gpu():
+    """The same flow in the bitmap form the multi-GPU engine uses (scan -> gather the shards' bitmaps -> OR fused
+    into the compaction -> split join -> sum), two contexts on one GPU standing in for two ranks."""
+    import torch
+    gold = load_case("powerlaw500_e3")
+    qfiles = gold["query_paths_files"]
+    queries = [graph_io.read_graph(qfiles[i]) for i in (0, 1, 3)]
+    want = [gold["queries"][i]["answer"] for i in (0, 1, 3)]
+    limits = [gold["queries"][i]["limit"] or gpe.LIMIT_MAX for i in (0, 1, 3)]
+    world = 2
+    ctxs, parts = [], []
+    for r in range(world):
+        ctx, g, vde, sorted_nodes, membership, n_rows, rows_pp = _ctx_for(gold)
+        ctx.build_table(sharding.partitions_of_rank(gold["p"], r, world))
+        ctx.batch_upload(queries, limits)
+        ctx.batch_scan()
+        ctx.sync()
+        ptr, nbytes = ctx.batch_bitmap()
+        parts.append(torch.as_tensor(sharding._DevMem(ptr, nbytes), device="cuda").clone())
+        ctxs.append(ctx)
+    assert parts[0].numel() == parts[1].numel() > 0
+    all_bm = torch.stack(parts).contiguous()
+    union = sharding.union_bitmaps_reference(all_bm.cpu().numpy())
+    torch.cuda.synchronize()
+    raw = np.zeros(len(queries), dtype=np.uint64)
+    for r, c in enumerate(ctxs):
+        c.batch_bitmap_merge(world, all_bm.data_ptr())
+        ptr, nbytes = c.batch_bitmap()
+        c.sync()
+        assert np.array_equal(torch.as_tensor(sharding._DevMem(ptr, nbytes), device="cuda").cpu().numpy(), union)
+        off, cand = c.batch_get_candidates()
+        slot = 0
+        for qi in (0, 1, 3):
+            for cset in gold["queries"][qi]["candidates"]:
+                assert cand[int(off[slot]):int(off[slot + 1])].tolist() == cset
+                slot += 1
+        c.batch_join(r, world)
+        raw += c.batch_download()
+    assert [ctxs[0].clamp(int(x), l) for x, l in zip(raw, limits)] == want
     for c in ctxs:
         c.close()
 

@@ -36,6 +36,15 @@ def _worker(rank, world, port, q):
         assert all_counts.shape == (world, n_slots) and all_cand.shape == (world, stride)
         merged = sharding.union_reference(all_counts.numpy(), all_cand.numpy())
         ok = all(np.array_equal(m, f) for m, f in zip(merged, full))
+        # C1, bitmap form: same sets as bitmaps of 512 bits per slot
+        bm = np.zeros((n_slots, 64), dtype=np.uint8)
+        for sl, c in enumerate(mine):
+            np.bitwise_or.at(bm[sl], c >> 3, (1 << (c & 7)).astype(np.uint8))
+        allb = sharding.allgather_bitmaps(torch.from_numpy(bm.reshape(-1)))
+        assert allb.shape == (world, n_slots * 64)
+        un = sharding.union_bitmaps_reference(allb.numpy()).reshape(n_slots, 64)
+        for sl, f in enumerate(full):
+            ok = ok and np.array_equal(np.flatnonzero(np.unpackbits(un[sl], bitorder="little")), f)
         # C2: match counts summed over shards, start candidates dealt round-robin
         total = 1001
         mine_n = sharding.start_candidates_of_rank(total, rank, world)
