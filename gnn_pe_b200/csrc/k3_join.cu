@@ -14,6 +14,8 @@
 //     candidate sets are only used for the start vertex and for ordering.
 //
 // Latency / divergence bound (L2-resident CSR gathers), no bandwidth roofline, no tensor cores.
+#include <cstdlib>
+
 #include "gpe_internal.h"
 
 namespace gpe {
@@ -495,6 +497,7 @@ constexpr u32 kSplit = 8;
 constexpr u32 kExportEvery = 8;      // rounds between two looks at the queue header
 constexpr int kStepsPerRound = 2;   // DFS steps of a lane between two rounds of scheduling (tickets, donation, export)
 constexpr int kExportLanes = 4;  // lanes of a warp that may hand work over in one round
+constexpr int kTailBatch = 8;    // parked lanes that trigger a joint evaluation of their counted-tail factors
 
 __host__ __device__ constexpr u32 item_stride(u32 m) { return kItemHdr + 3 * m; }
 
@@ -510,17 +513,21 @@ __device__ __forceinline__ void group_range(const JoinGraph &g, u32 v, u32 label
 // Edge filter: "no" is exact, "maybe" has to be confirmed by a search.  Most membership / edge tests of the join
 // fail (a prefix vertex is rarely adjacent to the pivot), and a failed test costs two independent loads here
 // instead of a chain of binary-search probes.
-__host__ __device__ __forceinline__ u64 edge_hash(u32 a, u32 b, u64 salt) {
-    u64 x = ((u64)(a < b ? a : b) << 32 | (a < b ? b : a)) + salt;
-    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
-    x ^= x >> 27; x *= 0x94d049bb133111ebull;
-    x ^= x >> 31;
-    return x;
+// Blocked: both bits of an edge live in ONE 64-bit word (one 8-byte load per test), and the hash is a handful of
+// 32-bit multiplies -- the r01k capture had 16 % of the kernel's instructions in two 64-bit mixers per test.
+__host__ __device__ __forceinline__ void edge_probe(u32 a, u32 b, u64 word_mask, u64 &word, u64 &bits) {
+    const u32 lo = a < b ? a : b, hi = a < b ? b : a;
+    u32 x = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
+    x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
+    u32 y = (lo ^ 0x68E31DA4u) * 0xB5297A4Du + hi * 0x1B56C4E9u;
+    y ^= y >> 16;
+    word = (u64)x & word_mask;
+    bits = (1ull << (y & 63)) | (1ull << (y >> 6 & 63));
 }
 __device__ __forceinline__ bool edge_maybe(const JoinGraph &g, u32 a, u32 b) {
-    const u64 h1 = edge_hash(a, b, 0) & g.bloom_mask, h2 = edge_hash(a, b, 0x9e3779b97f4a7c15ull) & g.bloom_mask;
-    const u32 w1 = __ldg(g.bloom + (h1 >> 5)), w2 = __ldg(g.bloom + (h2 >> 5));
-    return (w1 >> (h1 & 31) & 1) && (w2 >> (h2 & 31) & 1);
+    u64 word, bits;
+    edge_probe(a, b, g.bloom_mask >> 6, word, bits);
+    return (__ldg(reinterpret_cast<const u64 *>(g.bloom) + word) & bits) == bits;
 }
 
 // is v a member of the group nbrL[s, e)?  (ids ascending)
@@ -533,6 +540,8 @@ __device__ __forceinline__ bool in_group(const JoinGraph &g, u32 s, u32 e, u32 v
     }
     return false;
 }
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
     u32 v;
@@ -710,8 +719,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                                                          const u32 *__restrict__ cand, const uint2 *__restrict__ init,
                                                          const u64 *__restrict__ limits, u64 *answers, u32 *items,
                                                          u64 export_cap, u32 *ready, u32 epoch, JoinQueue *jq,
-                                                         u32 *matches, u64 matches_cap, u64 *match_cursor) {
+                                                         u32 *matches, u64 matches_cap, u64 *match_cursor, u32 flags) {
     constexpr u32 stride = item_stride(M);
+    const bool pf = flags & 1u;  // software prefetch of what the NEXT sibling candidate will need
+    const int tail_batch = (int)(flags >> 8 & 0xffu);  // parked lanes that trigger a joint evaluation (kTailBatch)
+    const int spr = (int)(flags >> 16 & 0xffu);        // DFS steps of a lane between two rounds of scheduling (kStepsPerRound)
     extern __shared__ u64 s_stack64[];  // prod [M][THREADS] u64 | emb | cur | end | s0 | e0, each [M][THREADS] u32
     u64 *prod = s_stack64 + threadIdx.x;
     u32 *emb = reinterpret_cast<u32 *>(s_stack64 + M * THREADS) + threadIdx.x;
@@ -730,6 +742,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
     const unsigned lt = lanemask_lt();
     const u64 n_init = jq->n_init;  // written by k3_init_items_kernel, the previous launch on this stream
     bool have = false, ticketed = false, can_export = true;
+    bool pend = false;  // parked: EMB(d) holds a candidate that passed the test and waits for its counted-tail factors
+    u64 pend_p = 0;     // its product so far
     bool registered = false;  // warp-uniform: counted in JoinQueue::idle
     u64 ticket = 0;
     u32 q = 0, vb = 0, nq = 0, base = 0, d = 0, lab0 = 0, tail_at = 0;
@@ -925,8 +939,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             }
         }
 
-        w_iters += kStepsPerRound;
-        for (int rep = 0; rep < kStepsPerRound && have; rep++) {
+        w_iters += spr;
+        for (int rep = 0; rep < spr; rep++) {
+          // A step has two parts with very different lane populations: the candidate test (most busy lanes) and the
+          // counted-tail factors of a candidate that passed it (r01k capture: 40 % of the kernel's instructions with
+          // 3-4 active lanes).  A lane whose candidate needs factors PARKS (pend) instead of evaluating them on the
+          // spot; the warp evaluates all parked lanes together once kTailBatch of them wait or nobody else can move.
+          u64 fin_p = 0;  // product to bank (leaf of the walk) or to descend with; 0 = nothing to do
+          if (have && !pend) {
             // ---- one DFS step: test the next candidate of level d ----
             my_steps++;
             const u32 at = CUR(d);
@@ -947,6 +967,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 const uint2 cd = g.nbrL[at];
                 c = cd.x;
                 cdeg = cd.y;
+                // the next sibling (usually in the same 32-byte sector) is tested one step from now: start pulling its
+                // gtab row and its class position towards L2 while this candidate's dependent loads are in flight
+                if (pf && at + 1 < END(d)) {
+                    const u32 c2 = g.nbrL[at + 1].x;
+                    const u32 pl = jd->kid_count ? kids[vb + jd->kid_begin].y : jd->label;
+                    prefetch_l2(g.gtab + (u64)c2 * (g.nl + 1) + (pl < g.nl ? pl : 0));
+                    if (jd->tree_off != kNoTree) prefetch_l2(g.lpos + c2);
+                }
             }
             // (bit scans -- ffs/popc -- run on the quarter-rate XU pipe, which a first version of this loop saturated:
             //  the masks of the plan are walked with shifts instead)
@@ -987,13 +1015,27 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                     if (l1 < g.nl) { a1 = __ldcg(row + l1); b1 = __ldcg(row + l1 + 1); }
                     S0(i0) = a0; E0(i0) = b0;
                     S0(i1) = a1; E0(i1) = b1;
+                    if (pf) {  // first candidates of the depths that pivot on c
+                        prefetch_l2(g.nbrL + a0);
+                        prefetch_l2(g.nbrL + a1);
+                    }
                     if (a0 >= b0 || a1 >= b1) { ok = false; break; }  // nothing to draw from: no match below c
                 }
             }
             if (ok) {
-                // (2) counted-tail factors that close at this depth
-                u64 p = (d ? PROD(d - 1) : 1) * tree_f;
-                u64 um = tail_at < nq ? jd->units_mask >> tail_at : 0;
+                const u64 p = (d ? PROD(d - 1) : 1) * tree_f;
+                const u64 um = tail_at < nq ? jd->units_mask >> tail_at : 0;
+                if (um && p) { pend = true; pend_p = p; } else fin_p = p;
+            }
+          }
+          // ---- (2) counted-tail factors that close at this depth, for all parked lanes at once ----
+          const unsigned pend_m = __ballot_sync(kFull, pend);
+          if (pend_m && (__popc(pend_m) >= tail_batch || !__ballot_sync(kFull, have && !pend))) {
+            if (pend) {
+                pend = false;
+                const JoinDepth *jd = jplan + vb + d;
+                u64 p = pend_p;
+                u64 um = jd->units_mask >> tail_at;
                 for (u32 i = tail_at; um && p; i++, um >>= 1) {
                     if (!(um & 1)) continue;
                     const JoinDepth *ld = jplan + vb + i;
@@ -1048,6 +1090,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                         p *= (u64)n_free * n_free2 - inter;
                     }
                 }
+                fin_p = p;
+            }
+          }
+          {
+            {
+                const u64 p = fin_p;
                 if (p) {
                     if (d + 1 == tail_at) {
                         acc += p;
@@ -1066,10 +1114,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                     }
                 }
             }
-            // pop exhausted levels
-            while (have && CUR(d) >= END(d)) {
+            // pop exhausted levels (a parked lane keeps its depth: its candidate is still to be descended from)
+            while (have && !pend && CUR(d) >= END(d)) {
                 if (d == base) have = false; else d--;
             }
+          }
         }
 
         // ---- between warps: when idle warps outnumber the published items, the lanes with the shallowest unexplored
@@ -1114,7 +1163,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                     my_exports++;
                 }
             }
-            while (have && CUR(d) >= END(d)) {  // the exported range may have been this lane's current level
+            while (have && !pend && CUR(d) >= END(d)) {  // the exported range may have been this lane's current level
                 if (d == base) have = false; else d--;
             }
         }
@@ -1238,18 +1287,31 @@ cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const Joi
     JoinGraph g = join_graph(jv);
     // stack bytes per thread: M x (8 + 5 x 4); threads per CTA chosen so that ~30 warps fit in an SM's shared memory
 #define LAUNCH(M, T, B)                                                                                                \
-    static int per_sm_##M = 0;                                                                                        \
-    const size_t smem_##M = (size_t)M * T * 28 + T;                                                                       \
-    if (!per_sm_##M) {                                                                                                \
-        cudaFuncSetAttribute(k3_dfs_kernel<M, T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_##M);        \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_##M, k3_dfs_kernel<M, T, B>, T, smem_##M) !=           \
-                cudaSuccess || per_sm_##M < 1)                                                                        \
-            per_sm_##M = 1;                                                                                           \
+    static int per_sm_##M##_##B = 0;                                                                                        \
+    const size_t smem_##M##_##B = (size_t)M * T * 28 + T;                                                                       \
+    if (!per_sm_##M##_##B) {                                                                                                \
+        cudaFuncSetAttribute(k3_dfs_kernel<M, T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_##M##_##B);        \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_##M##_##B, k3_dfs_kernel<M, T, B>, T, smem_##M##_##B) !=           \
+                cudaSuccess || per_sm_##M##_##B < 1)                                                                        \
+            per_sm_##M##_##B = 1;                                                                                           \
     }                                                                                                                 \
-    k3_dfs_kernel<M, T, B><<<sm_count * per_sm_##M, T, smem_##M, s>>>(g, q_vbase, jplan, reinterpret_cast<const uint2 *>(kids), cand, \
+    k3_dfs_kernel<M, T, B><<<sm_count * per_sm_##M##_##B, T, smem_##M##_##B, s>>>(g, q_vbase, jplan, reinterpret_cast<const uint2 *>(kids), cand, \
                                             reinterpret_cast<const uint2 *>(init), limits, answers, items, export_cap, \
-                                            ready, epoch, jq, matches, matches_cap, match_cursor)
-    if (max_nq <= 8) { LAUNCH(8, 128, 5); }
+                                            ready, epoch, jq, matches, matches_cap, match_cursor, flags)
+    static int env_pf = -1;
+    if (env_pf < 0) { const char *e = getenv("GPE_JOIN_PF"); env_pf = e ? atoi(e) : 0; }
+    static int env_tb = -1;
+    if (env_tb < 0) { const char *e = getenv("GPE_JOIN_TAILBATCH"); env_tb = e ? atoi(e) : kTailBatch; if (env_tb < 1 || env_tb > 32) env_tb = kTailBatch; }
+    static int env_spr = -1;
+    if (env_spr < 0) { const char *e = getenv("GPE_JOIN_SPR"); env_spr = e ? atoi(e) : kStepsPerRound; if (env_spr < 1 || env_spr > 64) env_spr = kStepsPerRound; }
+    const u32 flags = (env_pf ? 1u : 0u) | ((u32)env_tb << 8) | ((u32)env_spr << 16);
+    // 8-vertex stacks, CTAs of 128 threads per SM (config 2, ms per batch): 5 (96 registers) 15.97, 6 (80 registers, 92 bytes of
+    // spills) 15.61, 7 (72 registers) 19.9 -- beyond 6 the stacks leave too little of the SM's memory to L1, which holds the plans
+    static int env_blocks = -1;
+    if (env_blocks < 0) { const char *e = getenv("GPE_JOIN_BLOCKS"); env_blocks = e ? atoi(e) : 6; }
+    if (max_nq <= 8 && env_blocks == 7) { LAUNCH(8, 128, 7); }
+    else if (max_nq <= 8 && env_blocks == 6) { LAUNCH(8, 128, 6); }
+    else if (max_nq <= 8) { LAUNCH(8, 128, 5); }
     else if (max_nq <= 16) { LAUNCH(16, 128, 4); }
     else if (max_nq <= 32) { LAUNCH(32, 128, 2); }
     else { LAUNCH(64, 128, 1); }
@@ -1257,15 +1319,16 @@ cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const Joi
     return cudaGetLastError();
 }
 
-void k3_bloom_build(u32 V, const u32 *offsets, const u32 *nbrs, u64 n_bits /*power of two*/, u32 *words) {
-    const u64 mask = n_bits - 1;
+void k3_bloom_build(u32 V, const u32 *offsets, const u32 *nbrs, u64 n_bits /*power of two, >= 64*/, u32 *words) {
+    u64 *w64 = reinterpret_cast<u64 *>(words);
+    const u64 word_mask = (n_bits >> 6) - 1;
     for (u32 v = 0; v < V; v++)
         for (u32 j = offsets[v]; j < offsets[v + 1]; j++) {
             const u32 w = nbrs[j];
             if (w < v) continue;
-            const u64 h1 = edge_hash(v, w, 0) & mask, h2 = edge_hash(v, w, 0x9e3779b97f4a7c15ull) & mask;
-            words[h1 >> 5] |= 1u << (h1 & 31);
-            words[h2 >> 5] |= 1u << (h2 & 31);
+            u64 word, bits;
+            edge_probe(v, w, word_mask, word, bits);
+            w64[word] |= bits;
         }
 }
 
