@@ -2,6 +2,7 @@
 // Product code: no CPU fallback, nothing from oracle/.
 #include <algorithm>
 #include <numeric>
+#include <thread>
 
 #include "gpe_internal.h"
 #include "host_ref.h"
@@ -932,14 +933,35 @@ int gpe_batch_upload(gpe_ctx *c, const gpe_batch *b, uint32_t flags) {
     QPathSet qp;
     qp.L = L;
     qp.D = D;
-    QueryPlan plan;
     std::string why;
     for (u32 q = 0; q < b->n_queries; q++) {
         const u32 vb = b->q_vbase[q], nq = b->q_vbase[q + 1] - vb;
-        const u32 *off = b->q_offsets + vb + q;
-        const u32 *nbr = b->q_nbrs + b->q_ebase[q];
-        if (!check_query(c, nq, off, nbr, why)) return c->fail(GPE_ERR_INVALID, "query %u: %s", q, why.c_str());
-        query_plan(nq, off, nbr, b->q_labels + vb, L, E, plan);
+        if (!check_query(c, nq, b->q_offsets + vb + q, b->q_nbrs + b->q_ebase[q], why))
+            return c->fail(GPE_ERR_INVALID, "query %u: %s", q, why.c_str());
+    }
+    // the reference plans one query at a time (main.cpp:142-158); here the queries of a batch are planned by a few
+    // host threads, label embeddings come from a table filled once per batch
+    c->label_table.fill(b->q_labels, b->q_vbase[b->n_queries], E);
+    std::vector<QueryPlan> plans(b->n_queries);
+    auto plan_range = [&](u32 q0, u32 q1) {
+        for (u32 q = q0; q < q1; q++) {
+            const u32 vb = b->q_vbase[q], nq = b->q_vbase[q + 1] - vb;
+            query_plan(nq, b->q_offsets + vb + q, b->q_nbrs + b->q_ebase[q], b->q_labels + vb, L, E, plans[q], &c->label_table);
+        }
+    };
+    const u32 n_thr = b->n_queries >= 64 ? std::min<u32>(8, std::max<u32>(1, std::thread::hardware_concurrency() / 2)) : 1;
+    if (n_thr <= 1) {
+        plan_range(0, b->n_queries);
+    } else {
+        std::vector<std::thread> pool;
+        const u32 per = (b->n_queries + n_thr - 1) / n_thr;
+        for (u32 t = 1; t < n_thr; t++) pool.emplace_back(plan_range, std::min(t * per, b->n_queries), std::min((t + 1) * per, b->n_queries));
+        plan_range(0, std::min(per, b->n_queries));
+        for (auto &th : pool) th.join();
+    }
+    for (u32 q = 0; q < b->n_queries; q++) {
+        const QueryPlan &plan = plans[q];
+        const u32 vb = b->q_vbase[q];
         for (u32 i = 0; i < plan.n * L; i++) qp.slots.push_back(vb + plan.vids[i]);
         qp.labels.insert(qp.labels.end(), plan.labels.begin(), plan.labels.end());
         qp.degs.insert(qp.degs.end(), plan.degs.begin(), plan.degs.end());

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "gpe.h"
+#include "host_ref.h"
 
 typedef uint32_t u32;
 typedef uint64_t u64;
@@ -228,6 +229,7 @@ struct gpe_ctx {
     gpe::DevBuf d_q_vbase, d_q_ebase, d_q_offsets, d_q_nbrs, d_q_labels, d_limits;
     gpe::DevBuf d_order, d_pivot, d_jplan, d_item_base, d_answers, d_matches, d_match_cursor;
     gpe::PinnedBuf h_pin, h_pin2;
+    gpe::LabelTable label_table;  // label embeddings of the queries seen so far (host planning)
     u64 b_chunks_per_slot = 0;
 
     int fail(int code, const char *fmt, ...) {

@@ -70,15 +70,35 @@ static void label_embedding(uint32_t label, uint32_t e, double *out) {
     for (uint32_t i = 0; i < e; i++) out[i] = out[i] / sum;
 }
 
+void LabelTable::fill(const uint32_t *labels, size_t n, uint32_t e_) {
+    if (e_ != e) { e = e_; x.clear(); have.clear(); }
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t lab = labels[i];
+        if (lab >= (1u << 24)) continue;  // sparse huge labels: computed on the fly
+        if (lab >= have.size()) { have.resize((size_t)lab + 1, 0); x.resize(((size_t)lab + 1) * e, 0.0); }
+        if (!have[lab]) { label_embedding(lab, e, &x[(size_t)lab * e]); have[lab] = 1; }
+    }
+}
+
 // custom.h:513-544.
 void gen_vde(uint32_t V, const uint32_t *off, const uint32_t *nbr, const uint32_t *labels, uint32_t e, double *x,
-             double *vde) {
+             double *vde, const LabelTable *cache) {
+    if (cache && cache->e == e) {
+        bool all = true;
+        for (uint32_t v = 0; v < V && all; v++) {
+            const double *src = cache->get(labels[v]);
+            if (src) std::memcpy(x + (size_t)v * e, src, sizeof(double) * e); else all = false;
+        }
+        if (!all) cache = nullptr;
+    } else {
+        cache = nullptr;
+    }
     uint32_t max_label = 0;
     for (uint32_t v = 0; v < V; v++) max_label = std::max(max_label, labels[v]);
     std::vector<double> table;
     std::vector<char> have;
-    if (V) { table.resize(((size_t)max_label + 1) * e); have.assign((size_t)max_label + 1, 0); }
-    for (uint32_t v = 0; v < V; v++) {
+    if (V && !cache) { table.resize(((size_t)max_label + 1) * e); have.assign((size_t)max_label + 1, 0); }
+    for (uint32_t v = 0; v < V && !cache; v++) {
         uint32_t lab = labels[v];
         if (!have[lab]) { label_embedding(lab, e, &table[(size_t)lab * e]); have[lab] = 1; }
         std::memcpy(x + (size_t)v * e, &table[(size_t)lab * e], sizeof(double) * e);
@@ -142,11 +162,11 @@ static void query_paths(uint32_t nq, const uint32_t *off, const uint32_t *nbr, u
 // reference's initial order, with libstdc++'s std::sort, so ties fall exactly as they do there (SURVEY.md
 // Q4) -- then the greedy vertex cover.
 void query_plan(uint32_t nq, const uint32_t *off, const uint32_t *nbr, const uint32_t *labels, uint32_t L, uint32_t e,
-                QueryPlan &plan) {
+                QueryPlan &plan, const LabelTable *table) {
     std::vector<uint32_t> rows;
     query_paths(nq, off, nbr, L, rows);
     std::vector<double> x((size_t)nq * e), vde((size_t)nq * e);
-    gen_vde(nq, off, nbr, labels, e, x.data(), vde.data());
+    gen_vde(nq, off, nbr, labels, e, x.data(), vde.data(), table);
 
     struct Item { uint32_t weight, row; };
     size_t n = rows.size() / L;

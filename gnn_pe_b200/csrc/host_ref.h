@@ -16,12 +16,23 @@ struct QueryPlan {
     std::vector<double> pde;                   // n x L*e
 };
 
+// Label embeddings (gen_vde_x, custom.h:492-511) depend on (label, e) only: a table filled on first use saves a
+// mt19937 seeding per query vertex when thousands of queries are planned.  Thread-safe for concurrent readers once a
+// label is present; fill() is called up front for the labels of a batch.
+struct LabelTable {
+    uint32_t e = 0;
+    std::vector<double> x;    // (label) x e
+    std::vector<char> have;
+    void fill(const uint32_t *labels, size_t n, uint32_t e_);
+    const double *get(uint32_t label) const { return label < have.size() && have[label] ? &x[(size_t)label * e] : nullptr; }
+};
+
 int load_graph_file(const char *path, HostGraph &g, std::string &err);
 void gen_vde(uint32_t V, const uint32_t *off, const uint32_t *nbr, const uint32_t *labels, uint32_t e, double *x,
-             double *vde);
+             double *vde, const LabelTable *table = nullptr);
 bool query_connected(uint32_t nq, const uint32_t *off, const uint32_t *nbr);
 void query_plan(uint32_t nq, const uint32_t *off, const uint32_t *nbr, const uint32_t *labels, uint32_t L, uint32_t e,
-                QueryPlan &plan);
+                QueryPlan &plan, const LabelTable *table = nullptr);
 
 }  // namespace gpe
 

@@ -15,6 +15,8 @@
 // HBM-bound: 72 B/row at l=2,e=2.  Each CTA is a TMA pipeline: one producer lane issues
 // cp.async.bulk copies of (tile, query-path block) into a kStages-deep shared-memory ring guarded by
 // mbarriers; 256 consumer threads compare one row each.  No tensor cores: nothing here is a contraction.
+#include <cstdlib>
+
 #include "gpe_internal.h"
 
 namespace gpe {
@@ -152,7 +154,7 @@ template <int L, int E, bool VIDS>
 __global__ void __launch_bounds__(kTileRows + 32, 1)
 k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u64 *__restrict__ worklist,
                const u64 *__restrict__ counters, u32 *__restrict__ bitmap, u64 words_per_slot,
-               u64 *__restrict__ survivors) {
+               u64 *__restrict__ survivors, int red_mode, u32 stage_words) {
     using G = ScanGeom<L, E, VIDS>;
     constexpr int D = G::D;
     constexpr int NS = G::kNumStages;
@@ -163,6 +165,14 @@ k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u
     u64 *full_bar = reinterpret_cast<u64 *>(smem + NS * G::kStageBytes);
     u64 *empty_bar = full_bar + NS;
     u64 *meta = empty_bar + NS;  // work item of every stage
+    // Survivor staging (pruned work lists): a CTA works on a CONTIGUOUS chunk of the work list, i.e. on one query-path
+    // block for hundreds of tiles, and a slot's class-local bitmap is a few KB: survivors set their bits in a shared-
+    // memory copy (ATOMS) and the CTA flushes the non-zero words with one RED each when the block changes.  Without it
+    // the REDs of the c-position (one per surviving row, no runs to deduplicate) cost 0.26 of the scan's 0.74 ms.
+    int *stg_off = reinterpret_cast<int *>(meta + NS);           // [kQB * L] word offset of (path j, position k), or -1
+    u32 *stg_slot = reinterpret_cast<u32 *>(stg_off + kQB * L);  // [kQB * L] slot of every staged segment
+    u32 *stg_used = stg_slot + kQB * L;                          // staged words in use
+    u32 *stg = reinterpret_cast<u32 *>(smem + G::kSmemBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kConsumerWarps = kTileRows / 32;
@@ -177,8 +187,17 @@ k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u
     __syncthreads();
 
     const u64 n_items = counters[0];
-    const u64 first = blockIdx.x;
-    const u64 n_my = first < n_items ? (n_items - first + gridDim.x - 1) / gridDim.x : 0;
+    // streaming: items dealt round-robin; pruned lists: one contiguous chunk per CTA (see the staging above)
+    const u64 per = (n_items + gridDim.x - 1) / gridDim.x;
+    const u64 first = VIDS ? min((u64)blockIdx.x * per, n_items) : (u64)blockIdx.x;
+    const u64 step = VIDS ? 1 : (u64)gridDim.x;
+    const u64 n_my = VIDS ? min(per, n_items - first) : (first < n_items ? (n_items - first + gridDim.x - 1) / gridDim.x : 0);
+    const bool staging = VIDS && stage_words >= words_per_slot && red_mode == 0;
+    if (staging) {
+        for (u32 i = threadIdx.x; i < stage_words; i += blockDim.x) stg[i] = 0;
+        if (threadIdx.x == 0) *stg_used = 0;
+        __syncthreads();
+    }
 
     if (warp == kConsumerWarps) {
         // ---------------- producer warp: lane 0 issues the copies, the warp prefetches work items ---------
@@ -186,7 +205,7 @@ k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u
         int stage = 0;
         u32 phase = 0;
         for (u64 k0 = 0; k0 < n_my; k0 += 32) {
-            u64 mine = (k0 + lane < n_my) ? worklist[first + (k0 + lane) * gridDim.x] : 0;
+            u64 mine = (k0 + lane < n_my) ? worklist[first + (k0 + lane) * step] : 0;
             int cnt = (int)min((u64)32, n_my - k0);
             for (int i = 0; i < cnt; i++) {
                 u64 item = __shfl_sync(kFull, mine, i);
@@ -227,6 +246,35 @@ k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u
                 my_cnt = 0;
                 cur_b = b;
                 my_qpath = lane < kQB ? rec->qpath[lane] : 0;
+                if (staging) {  // every consumer warp passes here at the same item: named barrier of the 256 consumers
+                    const u32 wps = (u32)words_per_slot;
+                    asm volatile("bar.sync 1, %0;" ::"n"(kTileRows) : "memory");  // the previous block's tiles are done
+                    const u32 used = *stg_used;
+                    for (u32 i = threadIdx.x; i < used; i += kTileRows) {
+                        const u32 v = stg[i];
+                        if (v) {
+                            const u32 seg = i / wps;
+                            atomicOr(bitmap + (u64)stg_slot[seg] * words_per_slot + (i - seg * wps), v);
+                            stg[i] = 0;
+                        }
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(kTileRows) : "memory");
+                    if (threadIdx.x == 0) {  // the c-position first: its bits have no runs to deduplicate
+                        const u32 cap = stage_words / wps;
+                        u32 n_seg = 0;
+                        for (int kk = L - 1; kk >= 0; kk--)
+                            for (u32 j = 0; j < kQB; j++) {
+                                int off = -1;
+                                if (j < rec->n && n_seg < cap) {
+                                    off = (int)(n_seg * wps);
+                                    stg_slot[n_seg++] = rec->slot[j][kk];
+                                }
+                                stg_off[j * L + kk] = off;
+                            }
+                        *stg_used = n_seg * wps;
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(kTileRows) : "memory");
+                }
             }
 
             u32 lab[L], dg[L];
@@ -272,7 +320,15 @@ k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u
                     while (todo) {
                         const int j = __ffs(todo) - 1;
                         todo &= todo - 1;
-                        atomicOr(bitmap + (u64)rec->slot[j][kk] * words_per_slot + (v[kk] >> 5), 1u << (v[kk] & 31));
+                        u32 *w = bitmap + (u64)rec->slot[j][kk] * words_per_slot + (v[kk] >> 5);
+                        const u32 bit = 1u << (v[kk] & 31);
+                        // red_mode 1: look before setting.  Bits only ever get set, so a stale (L1) copy can at worst
+                        // cost a redundant RED; most survivors of a power-law graph name a vertex that is already in
+                        if (red_mode == 1 && (__ldca(w) & bit)) continue;
+                        if (red_mode == 2) continue;  // measurement only: no bitmap traffic at all
+                        const int so = staging ? stg_off[j * L + kk] : -1;
+                        if (so >= 0) atomicOr(stg + so + (v[kk] >> 5), bit);
+                        else atomicOr(w, bit);
                     }
                 }
             }
@@ -281,6 +337,18 @@ k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u
             if (++stage == NS) { stage = 0; phase ^= 1; }
         }
         if (my_cnt) atomicAdd((unsigned long long *)&survivors[my_qpath], (unsigned long long)my_cnt);
+        if (staging) {
+            const u32 wps = (u32)words_per_slot;
+            asm volatile("bar.sync 1, %0;" ::"n"(kTileRows) : "memory");
+            const u32 used = *stg_used;
+            for (u32 i = threadIdx.x; i < used; i += kTileRows) {
+                const u32 v = stg[i];
+                if (v) {
+                    const u32 seg = i / wps;
+                    atomicOr(bitmap + (u64)stg_slot[seg] * words_per_slot + (i - seg * wps), v);
+                }
+            }
+        }
     }
 }
 
@@ -294,23 +362,51 @@ cudaError_t launch_select(const TableView &t, const void *qblocks, const u32 *qb
     return cudaGetLastError();
 }
 
+inline int scan_red_mode() {
+    static int mode = -1;
+    if (mode < 0) { const char *e = getenv("GPE_SCAN_RED"); mode = e ? atoi(e) : 0; }
+    return mode;
+}
+
+inline bool scan_stage_on() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("GPE_SCAN_STAGE"); on = e ? atoi(e) : 1; }
+    return on != 0;
+}
+
 template <int L, int E, bool VIDS>
 cudaError_t launch_scan_v(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters,
                           u32 *bitmap, u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s) {
     using G = ScanGeom<L, E, VIDS>;
+    // Staging capacity: what two CTAs per SM leave next to the ring, in whole slots (at most one per (path, position)
+    // of a block); when not even one slot fits (huge label classes) the kernel falls back to direct REDs.
     static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
+    static u64 cfg_words = ~0ull;
+    static u32 stage_words = 0;
+    static size_t smem_bytes = 0;
+    if (ctas_per_sm == 0 || cfg_words != words_per_slot) {
+        stage_words = 0;
+        if (VIDS && words_per_slot > 0 && scan_stage_on()) {
+            const size_t budget = (size_t)(227 * 1024) / 2 - 1024;  // per CTA, two CTAs per SM (1 KB reserved each)
+            if (budget > (size_t)G::kSmemBytes) {
+                const u64 slots = std::min<u64>((budget - G::kSmemBytes) / 4 / words_per_slot, (u64)kQB * L);
+                stage_words = (u32)(slots * words_per_slot);
+            }
+        }
+        smem_bytes = (size_t)G::kSmemBytes + (size_t)stage_words * 4;
         cudaError_t e = cudaFuncSetAttribute(k2_scan_kernel<L, E, VIDS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             G::kSmemBytes);
+                                             (int)smem_bytes);
         if (e != cudaSuccess) return e;
         int n = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k2_scan_kernel<L, E, VIDS>, kTileRows + 32, G::kSmemBytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k2_scan_kernel<L, E, VIDS>, kTileRows + 32, smem_bytes);
         if (e != cudaSuccess) return e;
         ctas_per_sm = n < 1 ? 1 : n;
+        cfg_words = words_per_slot;
     }
     unsigned blocks = (unsigned)(sm_count * ctas_per_sm);
-    k2_scan_kernel<L, E, VIDS><<<blocks, kTileRows + 32, G::kSmemBytes, s>>>(
-        t, reinterpret_cast<const QBlockRec<L, E> *>(qblocks), worklist, counters, bitmap, words_per_slot, survivors);
+    k2_scan_kernel<L, E, VIDS><<<blocks, kTileRows + 32, smem_bytes, s>>>(
+        t, reinterpret_cast<const QBlockRec<L, E> *>(qblocks), worklist, counters, bitmap, words_per_slot, survivors,
+        scan_red_mode(), stage_words);
     return cudaGetLastError();
 }
 
