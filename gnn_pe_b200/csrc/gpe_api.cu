@@ -328,7 +328,7 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
                          c->d_tchild.as<u32>(), c->d_tcursor.as<u64>(), tcount, tlist, n_slots, c->stream));
     JoinView jv{c->d_label.as<u32>(), c->d_nbrL.as<u32>(), c->d_gtab.as<u32>(), c->V, c->n_labels, c->d_deg.as<u32>(),
                 c->d_lclass.as<u32>(), c->d_lpos.as<u32>(), c->d_lcoff.as<u32>(), c->d_tpool.as<u64>(), c->d_bloom.as<u32>(),
-                c->bloom_bits - 1};
+                c->bloom_bits - 1, c->lpos_packed};
     u32 tree_launches = 0;
     if (!enumerate && c->b_max_nq >= 2) {
         tree_launches = c->b_max_nq - 1;
@@ -350,11 +350,11 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     const u32 epoch = ++c->join_epoch;
     JoinQueue *jq = c->d_jq.as<JoinQueue>();
     const u32 heavy_deg = std::max<u32>(32, c->V ? (u32)(4ull * c->n_adj / c->V) : 32);  // 4 x the mean degree
-    GPE_CUDA(c, c->d_qcur.reserve(((size_t)nq + 1) * 5 * sizeof(u64)));
-    GPE_CUDA(c, cudaMemsetAsync(c->d_qcur.p, 0, ((size_t)nq + 1) * 5 * sizeof(u64), c->stream));
+    GPE_CUDA(c, c->d_qcur.reserve(((size_t)nq + 1) * 6 * sizeof(u64)));
+    GPE_CUDA(c, cudaMemsetAsync(c->d_qcur.p, 0, ((size_t)nq + 1) * 6 * sizeof(u64), c->stream));
     GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
                               c->d_cand.as<u32>(), c->d_item_base.as<u64>(), rank, world, heavy_deg,
-                              c->d_qcur.as<u64>(), c->d_init.p, jq, c->sm_count, c->stream));
+                              c->d_qcur.as<u64>(), c->d_init.p, jq, tree_launches > 0, c->sm_count, c->stream));
     GPE_CUDA(c, k3_dfs(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_cand.as<u32>(),
                        c->d_init.p, c->d_limits.as<u64>(), answers, c->d_items.as<u32>(), cap, c->d_ready.as<u32>(), epoch,
                        jq, d_matches, matches_cap, c->d_match_cursor.as<u64>(), c->sm_count, c->stream));
@@ -582,6 +582,15 @@ int gpe_set_graph(gpe_ctx *c, uint32_t V, const uint32_t *offsets, const uint32_
                 lclass[at[l]++] = v;
             }
         }
+        // second word of a grouped-adjacency entry: the neighbour's degree saturated at 255 (query degrees are < 64, so
+        // every `degree >= query degree` test is exact) and, above it, the neighbour's position in its label class --
+        // the subtree-table index -- so a candidate test needs no separate lookup of it
+        c->lpos_packed = c->max_class < (1u << 24);
+        if (c->lpos_packed)
+            for (size_t i = 0; i < (size_t)n_adj; i++) {
+                const u32 w = nbrL[2 * i];
+                nbrL[2 * i + 1] = std::min<u32>(deg[w], 255u) | (lpos[w] << 8);
+            }
         {   // edge filter: 16 bits per undirected edge, two of them set
             u64 bits = 1024;
             while (bits < 8ull * n_adj) bits <<= 1;

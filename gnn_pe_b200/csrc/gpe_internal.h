@@ -76,7 +76,7 @@ struct GraphView {
     const u32 *lpos;   // V: position of a vertex inside its label class
     const u32 *lclass; // vertices by (label, id)
     const u32 *lcoff;  // labels + 1 class offsets
-    const uint2 *nbrL; // adjacency grouped by neighbour label (neighbour, its degree); same offsets as nbr
+    const uint2 *nbrL; // adjacency grouped by neighbour label: (neighbour, degree [| class position << 8]); same offsets as nbr
 };
 
 // Physical layout of the path table: tile-major blocked structure-of-arrays.
@@ -129,7 +129,8 @@ struct alignas(16) JoinDepth {
     u32 pivot_depth;  // depth at which the pivot (first earlier query neighbour) was matched
     u64 bn_mask;      // depths of the other backward neighbours (generateBN, custom.h:724-755)
     u64 tree_off;     // table of everything that hangs below this vertex in peeled subtrees (pool offset), or kNoTree
-    u64 tail_mask;    // [tail depths] prefix depths that may sit in this leaf's label group and need an edge test
+    u64 tail_mask;    // [tail depths] prefix depths that may sit in this leaf's label group and need an edge test;  [walked depths >= 1]
+                      // earlier depths of the same label (the only ones a candidate could coincide with);  [depth 0] walk starts from: 0 list, 1 class
     u32 kid_begin, kid_count;  // later depths (walked or tail) whose pivot is this depth, as a slice of the query's kid list
                                // (depth, label): their label groups are looked up when this depth is matched
     u64 units_mask;   // [walked depths] heads of the counted-tail units whose factor becomes computable at this depth
@@ -190,6 +191,7 @@ struct gpe_ctx {
     gpe::DevBuf d_lclass, d_lpos, d_lcoff;  // label classes: vertices by (label, id), position in class, class offsets
     gpe::DevBuf d_tjobs, d_tchild, d_tpool, d_tcursor, d_tlist, d_qcur;  // subtree tables of the join (jobs, child lists, value pool, pool cursor)
     u32 max_class = 0;
+    bool lpos_packed = false;
     gpe::DevBuf d_bloom;  // edge filter of the join
     u64 bloom_bits = 0;
     gpe::DevBuf d_items, d_ready, d_jq, d_init, d_kids;  // exported join work items, their publication flags, the queue header, start tickets
@@ -314,6 +316,7 @@ struct JoinView {
     const u64 *tpool;
     const u32 *bloom;
     u64 bloom_mask;
+    bool lpos_packed;  // nbrL[.].y = min(degree, 255) | class position << 8 (else the plain degree)
 };
 // host: two bits per undirected edge into a table of n_bits (power of two) bits
 void k3_bloom_build(u32 V, const u32 *offsets, const u32 *nbrs, u64 n_bits, u32 *words);
@@ -326,8 +329,9 @@ u32 k3_item_stride(u32 max_nq);  // u32 words per exported work item
 // one ticket (query, position in cand[]) per start candidate of this shard; init: 8 bytes per ticket
 cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
                           const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world,
-                          u32 heavy_deg /*roots of at least this degree are ticketed first*/, u64 *cursors /*5 per query, zeroed*/,
-                          void *init, JoinQueue *jq, int sm_count, cudaStream_t s);
+                          u32 heavy_deg /*roots of at least this degree are ticketed first*/, u64 *cursors /*6 per query, zeroed*/,
+                          void *init, JoinQueue *jq, bool use_tables /*subtree tables are valid: dead roots get no ticket*/,
+                          int sm_count, cudaStream_t s);
 // one persistent launch: every thread runs work items (explicit-stack DFS) and exports subtrees when others starve
 cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
                    const void *init, const u64 *limits, u64 *answers, u32 *items, u64 export_cap, u32 *ready, u32 epoch,

@@ -383,6 +383,14 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                         if (dw < i && dw != jd.pivot_depth) jd.bn_mask |= 1ull << dw;
                     }
                 }
+                if (i > 0 && i < n_walk) {
+                    // [walked depths] earlier depths a candidate of this one could coincide with: only those of the same
+                    // label (candidates come from a label group); depth 0 too when its data label is only known at run time
+                    u64 sm = (root_is_start && !clean_start) ? 1ull : 0ull;
+                    for (u32 t = 0; t < i; t++)
+                        if (lab[t] == lab[i]) sm |= 1ull << t;
+                    jd.tail_mask = sm;
+                }
                 if (i >= n_walk) {
                     jd.tail_k = top[i];
                     const u32 pvu = xo[jd.pivot_depth];
@@ -490,6 +498,7 @@ struct JoinGraph {
     const u64 *tpool;   // subtree tables (k3_tree_tables), indexed [table offset + lpos]
     const u32 *bloom;   // edge filter: two bits per undirected edge in a table of bloom_mask + 1 bits
     u64 bloom_mask;
+    bool packed;        // nbrL[.].y = min(degree, 255) | class position << 8
 };
 
 constexpr int kItemHdr = 8;  // q, level, lo, hi, prod (2 words), label of the start vertex, pad; then EMB | S0 | E0
@@ -497,6 +506,8 @@ constexpr u32 kSplit = 8;
 constexpr u32 kExportEvery = 8;      // rounds between two looks at the queue header
 constexpr int kStepsPerRound = 2;   // DFS steps of a lane between two rounds of scheduling (tickets, donation, export)
 constexpr int kExportLanes = 4;  // lanes of a warp that may hand work over in one round
+constexpr int kTries = 1;        // sibling candidates a lane may test per step until one passes the cheap filters (measured on
+                                 // config 2: 1 -> 15.95 ms, 2 -> 16.55, 4 -> 17.19, 8 -> 17.34: a retry lengthens the warp's critical chain)
 constexpr int kTailBatch = 8;    // parked lanes that trigger a joint evaluation of their counted-tail factors
 
 __host__ __device__ constexpr u32 item_stride(u32 m) { return kItemHdr + 3 * m; }
@@ -524,10 +535,12 @@ __host__ __device__ __forceinline__ void edge_probe(u32 a, u32 b, u64 word_mask,
     word = (u64)x & word_mask;
     bits = (1ull << (y & 63)) | (1ull << (y >> 6 & 63));
 }
+template <bool CG>
 __device__ __forceinline__ bool edge_maybe(const JoinGraph &g, u32 a, u32 b) {
     u64 word, bits;
     edge_probe(a, b, g.bloom_mask >> 6, word, bits);
-    return (__ldg(reinterpret_cast<const u64 *>(g.bloom) + word) & bits) == bits;
+    const u64 *p = reinterpret_cast<const u64 *>(g.bloom) + word;
+    return ((CG ? __ldcg(p) : __ldg(p)) & bits) == bits;  // CG: around L1 (random, no reuse), which holds the plans
 }
 
 // is v a member of the group nbrL[s, e)?  (ids ascending)
@@ -540,8 +553,6 @@ __device__ __forceinline__ bool in_group(const JoinGraph &g, u32 s, u32 e, u32 v
     }
     return false;
 }
-
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ u32 ld_acquire_u32(const u32 *p) {
     u32 v;
@@ -560,12 +571,16 @@ __device__ __forceinline__ void ld_relaxed_2xu64(const void *p, u64 &a, u64 &b) 
 // jobs first: the end of the join is then made of small items).  Ticket order: the heavy roots of query 0, 1, ...,
 // then the light roots of query 0, 1, ... -- neighbouring tickets belong to one query, so the lanes of a warp mostly
 // read the same plan.  Three small launches: count the heavy roots per query, prefix, place.
-struct RootItem { u32 q, pos; bool heavy; };
+struct RootItem { u32 q, pos; bool heavy, alive; };
 
+// A root that fails the tests the walk would apply to it first -- its degree (class starts only: listed start candidates
+// are taken as they are, custom.h:827-830) and the subtree table of the root's query vertex, which for a peeled start
+// vertex carries the candidate bitmap -- never gets a ticket: the test runs here, coalesced over the class, instead of
+// costing a ticket claim and a divergent first step in the walk.
 __device__ __forceinline__ RootItem root_item(u64 item, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
                                               const u64 *cand_off, const u32 *cand, const u32 *lclass, const u32 *deg,
                                               const u32 *lcoff, u32 n_labels, const u64 *item_base, u32 rank, u32 world,
-                                              u32 heavy_deg) {
+                                              u32 heavy_deg, const u32 *lpos, const u64 *tpool) {
     u32 lo = 0, hi = n_queries;
     while (hi - lo > 1) {
         u32 mid = (lo + hi) >> 1;
@@ -578,11 +593,16 @@ __device__ __forceinline__ RootItem root_item(u64 item, u32 n_queries, const u32
     const JoinDepth &j0 = jplan[vb];
     const u64 first = j0.tail_mask ? (j0.label < n_labels ? lcoff[j0.label] : 0) : cand_off[vb + j0.u];
     r.pos = (u32)(first + idx);
-    r.heavy = deg[j0.tail_mask ? lclass[r.pos] : cand[r.pos]] >= heavy_deg;
+    const u32 c = j0.tail_mask ? lclass[r.pos] : cand[r.pos];
+    const u32 dg = deg[c];
+    r.heavy = dg >= heavy_deg;
+    r.alive = !j0.tail_mask || dg >= j0.deg;
+    if (r.alive && tpool && j0.tree_off != kNoTree) r.alive = tpool[j0.tree_off + lpos[c]] != 0;
     return r;
 }
 
-// qcur: per query [0] heavy count, [1] heavy base, [2] light base, [3] heavy cursor, [4] light cursor (u64 each)
+// qcur: per query [0] heavy count, [1] heavy base, [2] light base, [3] heavy cursor, [4] light cursor, [5] light count
+constexpr int kQCur = 6;
 __global__ void __launch_bounds__(256) k3_init_count_kernel(u32 n_queries, const u32 *__restrict__ q_vbase,
                                                             const JoinDepth *__restrict__ jplan,
                                                             const u64 *__restrict__ cand_off,
@@ -591,23 +611,35 @@ __global__ void __launch_bounds__(256) k3_init_count_kernel(u32 n_queries, const
                                                             const u32 *__restrict__ deg,
                                                             const u32 *__restrict__ lcoff, u32 n_labels,
                                                             const u64 *__restrict__ item_base, u32 rank, u32 world,
-                                                            u32 heavy_deg, u64 *qcur) {
+                                                            u32 heavy_deg, const u32 *__restrict__ lpos,
+                                                            const u64 *__restrict__ tpool, u64 *qcur) {
     const u64 n_items = item_base[n_queries], n_round = (n_items + 31) / 32 * 32;
     const int lane = threadIdx.x & 31;
     for (u64 item = (u64)blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += (u64)gridDim.x * blockDim.x) {
-        RootItem r{0xffffffffu, 0, false};
+        RootItem r{0xffffffffu, 0, false, false};
         if (item < n_items)
             r = root_item(item, n_queries, q_vbase, jplan, cand_off, cand, lclass, deg, lcoff, n_labels, item_base, rank, world,
-                          heavy_deg);
-        // one atomic per (warp, query): consecutive items belong to one query almost always
-        const unsigned peers = __match_any_sync(kFull, r.heavy ? r.q : 0xffffffffu);
-        if (r.heavy && lane == __ffs(peers) - 1) atomicAdd((unsigned long long *)&qcur[5 * (u64)r.q], (unsigned long long)__popc(peers));
+                          heavy_deg, lpos, tpool);
+        // one atomic per (warp, query, class): consecutive items belong to one query almost always
+        const unsigned peers = __match_any_sync(kFull, r.alive ? (r.q << 1 | (r.heavy ? 1u : 0u)) : 0xffffffffu);
+        if (r.alive && lane == __ffs(peers) - 1)
+            atomicAdd((unsigned long long *)&qcur[kQCur * (u64)r.q + (r.heavy ? 0 : 5)], (unsigned long long)__popc(peers));
     }
 }
 
-__global__ void k3_init_prefix_kernel(u32 n_queries, const u64 *__restrict__ item_base, u64 *qcur, JoinQueue *jq) {
+__global__ void k3_init_prefix_kernel(u32 n_queries, u64 *qcur, JoinQueue *jq) {
     if (threadIdx.x || blockIdx.x) return;
-    const u64 n_items = item_base[n_queries];
+    u64 heavy = 0;
+    for (u32 q = 0; q < n_queries; q++) {
+        qcur[kQCur * (u64)q + 1] = heavy;
+        heavy += qcur[kQCur * (u64)q];
+    }
+    u64 light = heavy;
+    for (u32 q = 0; q < n_queries; q++) {
+        qcur[kQCur * (u64)q + 2] = light;
+        light += qcur[kQCur * (u64)q + 5];
+    }
+    const u64 n_items = light;  // live roots = tickets
     jq->head = 0;
     jq->tail = n_items;
     jq->pending = (long long)n_items;
@@ -620,16 +652,6 @@ __global__ void k3_init_prefix_kernel(u32 n_queries, const u64 *__restrict__ ite
     jq->warp_iters = 0;
     jq->lane_iters = 0;
     jq->idle_polls = 0;
-    u64 heavy = 0;
-    for (u32 q = 0; q < n_queries; q++) {
-        qcur[5 * (u64)q + 1] = heavy;
-        heavy += qcur[5 * (u64)q];
-    }
-    u64 light = heavy;
-    for (u32 q = 0; q < n_queries; q++) {
-        qcur[5 * (u64)q + 2] = light;
-        light += (item_base[q + 1] - item_base[q]) - qcur[5 * (u64)q];
-    }
 }
 
 __global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const u32 *__restrict__ q_vbase,
@@ -640,22 +662,23 @@ __global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const
                                                             const u32 *__restrict__ deg,
                                                             const u32 *__restrict__ lcoff, u32 n_labels,
                                                             const u64 *__restrict__ item_base, u32 rank, u32 world,
-                                                            u32 heavy_deg, u64 *qcur, uint2 *init) {
+                                                            u32 heavy_deg, const u32 *__restrict__ lpos,
+                                                            const u64 *__restrict__ tpool, u64 *qcur, uint2 *init) {
     const u64 n_items = item_base[n_queries], n_round = (n_items + 31) / 32 * 32;
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
     for (u64 item = (u64)blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += (u64)gridDim.x * blockDim.x) {
-        const bool valid = item < n_items;
-        RootItem r{0xffffffffu, 0, false};
-        if (valid)
+        RootItem r{0xffffffffu, 0, false, false};
+        if (item < n_items)
             r = root_item(item, n_queries, q_vbase, jplan, cand_off, cand, lclass, deg, lcoff, n_labels, item_base, rank, world,
-                          heavy_deg);
+                          heavy_deg, lpos, tpool);
+        const bool valid = r.alive;
         // one atomic per (warp, query, class)
         const unsigned peers = __match_any_sync(kFull, valid ? (r.q << 1 | (r.heavy ? 1u : 0u)) : 0xffffffffu);
         const int leader = __ffs(peers) - 1;
         u64 base = 0;
         if (valid && lane == leader) {
-            u64 *qc = qcur + 5 * (u64)r.q;
+            u64 *qc = qcur + kQCur * (u64)r.q;
             base = r.heavy ? qc[1] + atomicAdd((unsigned long long *)&qc[3], (unsigned long long)__popc(peers))
                            : qc[2] + atomicAdd((unsigned long long *)&qc[4], (unsigned long long)__popc(peers));
         }
@@ -698,8 +721,8 @@ __global__ void __launch_bounds__(256) k3_tree_tables_kernel(JoinGraph g, const 
                     const u32 *bm = cj.start_slot == 0xffffffffu ? nullptr : bitmap + (u64)cj.start_slot * words_per_slot;
                     for (u32 at = s; at < e; at++) {
                         const uint2 yd = g.nbrL[at];
-                        if (yd.y < cj.qdeg) continue;
-                        const u32 yp = g.lpos[yd.x];
+                        if ((g.packed ? yd.y & 255u : yd.y) < cj.qdeg) continue;
+                        const u32 yp = g.packed ? yd.y >> 8 : g.lpos[yd.x];
                         if (bm && !(bm[yp >> 5] >> (yp & 31) & 1)) continue;
                         sum += cj.level ? tpool[cj.table_off + yp] : 1;
                     }
@@ -721,7 +744,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                                                          u64 export_cap, u32 *ready, u32 epoch, JoinQueue *jq,
                                                          u32 *matches, u64 matches_cap, u64 *match_cursor, u32 flags) {
     constexpr u32 stride = item_stride(M);
-    const bool pf = flags & 1u;  // software prefetch of what the NEXT sibling candidate will need
+    const int tries = max(1, (int)(flags >> 24 & 0xffu));  // candidates a lane may test per step (see the step)
+    const bool cgl = flags & 2u;  // bloom words and class positions go around L1
+    const bool spec = flags & 4u; // gtab lookups of the first kids issued together with the subtree-table lookup
     const int tail_batch = (int)(flags >> 8 & 0xffu);  // parked lanes that trigger a joint evaluation (kTailBatch)
     const int spr = (int)(flags >> 16 & 0xffu);        // DFS steps of a lane between two rounds of scheduling (kStepsPerRound)
     extern __shared__ u64 s_stack64[];  // prod [M][THREADS] u64 | emb | cur | end | s0 | e0, each [M][THREADS] u32
@@ -824,7 +849,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 q = iq;
                 vb = q_vbase[q];
                 nq = jplan[vb].sure_used;  // depths of the execution plan (peeled subtrees are not walked)
-                if (*(volatile u64 *)&answers[q] < limit) {
+                if (limit >= GPE_LIMIT_MAX || *(volatile u64 *)&answers[q] < limit) {  // (no limit: nothing to read)
                     tail_at = matches ? nq : nq - jplan[vb].tail_k;  // depth at which the counting shortcut takes over
                     base = d = 0;
                     CUR(0) = it.y;
@@ -847,7 +872,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 vb = q_vbase[q];
                 nq = jplan[vb].sure_used;
                 base = it[1];
-                if (it[2] < it[3] && *(volatile u64 *)&answers[q] < limit) {
+                if (it[2] < it[3] && (limit >= GPE_LIMIT_MAX || *(volatile u64 *)&answers[q] < limit)) {
                     lab0 = it[6];
                     tail_at = matches ? nq : nq - jplan[vb].tail_k;
                     for (u32 t = 0; t < base; t++) EMB(t) = it[kItemHdr + t];
@@ -947,52 +972,71 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
           // spot; the warp evaluates all parked lanes together once kTailBatch of them wait or nobody else can move.
           u64 fin_p = 0;  // product to bank (leaf of the walk) or to descend with; 0 = nothing to do
           if (have && !pend) {
-            // ---- one DFS step: test the next candidate of level d ----
-            my_steps++;
-            const u32 at = CUR(d);
-            CUR(d) = at + 1;
+            // ---- one DFS step: test the next candidate(s) of level d ----
+            // Most candidates fall at the cheap tests (degree, subtree table, injectivity), which cost one or two
+            // dependent loads and nothing else.  A lane keeps trying siblings until one passes them (at most `tries`),
+            // so that the expensive rest of the step (edge tests, group lookups) runs with more lanes on board.
             const JoinDepth *jd = jplan + vb + d;
-            u32 c, cdeg;
-            if (d == 0) {
-                if (jd->tail_mask) {  // the walk starts from the root's label class (the start vertex was peeled)
-                    c = g.lclass[at];
-                    cdeg = g.deg[c];
-                    lab0 = jd->label;
-                } else {  // start candidates are taken as they are (the reference never checks them, custom.h:827-830)
-                    c = cand[at];
-                    cdeg = 0xffffffffu;
-                    lab0 = g.label[c];
-                }
-            } else {
-                const uint2 cd = g.nbrL[at];
-                c = cd.x;
-                cdeg = cd.y;
-                // the next sibling (usually in the same 32-byte sector) is tested one step from now: start pulling its
-                // gtab row and its class position towards L2 while this candidate's dependent loads are in flight
-                if (pf && at + 1 < END(d)) {
-                    const u32 c2 = g.nbrL[at + 1].x;
-                    const u32 pl = jd->kid_count ? kids[vb + jd->kid_begin].y : jd->label;
-                    prefetch_l2(g.gtab + (u64)c2 * (g.nl + 1) + (pl < g.nl ? pl : 0));
-                    if (jd->tree_off != kNoTree) prefetch_l2(g.lpos + c2);
-                }
-            }
-            // (bit scans -- ffs/popc -- run on the quarter-rate XU pipe, which a first version of this loop saturated:
-            //  the masks of the plan are walked with shifts instead)
-            bool ok = cdeg >= jd->deg;
-            // everything that hangs below this query vertex in peeled subtrees: one factor per data vertex
             const u64 tree_off = matches ? kNoTree : jd->tree_off;
+            u32 c = 0, cdeg = 0, cpos = 0;
             u64 tree_f = 1;
-            if (ok && tree_off != kNoTree) {
-                tree_f = __ldcg(g.tpool + tree_off + g.lpos[c]);
-                ok = tree_f != 0;
+            bool ok = false;
+            const uint2 *kl = kids + vb + jd->kid_begin;
+            const u32 kn = jd->kid_count;
+            uint2 sk0 = make_uint2(0, 0), sk1 = make_uint2(0, 0);
+            u32 sa0 = 0, sb0 = 0, sa1 = 0, sb1 = 0;
+            for (int tr = 0; tr < tries && !ok; tr++) {
+                const u32 at = CUR(d);
+                if (at >= END(d)) break;
+                my_steps++;
+                CUR(d) = at + 1;
+                if (d == 0) {
+                    if (jd->tail_mask) {  // the walk starts from the root's label class (the start vertex was peeled)
+                        c = g.lclass[at];
+                        cdeg = g.deg[c];
+                        lab0 = jd->label;
+                    } else {  // start candidates are taken as they are (the reference never checks them, custom.h:827-830)
+                        c = cand[at];
+                        cdeg = 0xffffffffu;
+                        lab0 = g.label[c];
+                    }
+                } else {
+                    const uint2 cd = g.nbrL[at];
+                    c = cd.x;
+                    cdeg = g.packed ? cd.y & 255u : cd.y;
+                    cpos = cd.y >> 8;
+                }
+                // (bit scans -- ffs/popc -- run on the quarter-rate XU pipe, which a first version of this loop
+                //  saturated: the masks of the plan are walked with shifts instead)
+                ok = cdeg >= jd->deg;
+                // The label groups of c that later depths draw from (first two kids) depend on c alone: their gtab
+                // lookups are issued NOW, next to the subtree-table lookup, instead of one round trip after it
+                if (spec && ok && kn) {
+                    sk0 = kl[0];
+                    sk1 = kl[min(1u, kn - 1)];
+                    const u32 *row_ = g.gtab + (u64)c * (g.nl + 1);
+                    if (sk0.y < g.nl) { sa0 = __ldcg(row_ + sk0.y); sb0 = __ldcg(row_ + sk0.y + 1); } else { sa0 = sb0 = 0; }
+                    if (sk1.y < g.nl) { sa1 = __ldcg(row_ + sk1.y); sb1 = __ldcg(row_ + sk1.y + 1); } else { sa1 = sb1 = 0; }
+                }
+                // everything that hangs below this query vertex in peeled subtrees: one factor per data vertex
+                tree_f = 1;
+                if (ok && tree_off != kNoTree) {
+                    const u32 pos = (g.packed && d) ? cpos : (cgl ? __ldcg(g.lpos + c) : g.lpos[c]);
+                    tree_f = __ldcg(g.tpool + tree_off + pos);
+                    ok = tree_f != 0;
+                }
+                // injective: only earlier depths of the same label could collide (k3_order); enumeration mode also walks
+                // the tail depths, whose tail_mask means something else: there every earlier depth is compared
+                u64 sm = d ? (matches ? (1ull << d) - 1 : jd->tail_mask) : 0;
+                for (u32 t = 0; sm; t++, sm >>= 1)
+                    if (sm & 1) ok = ok && EMB(t) != c;
             }
-            for (u32 t = 0; t < d; t++) ok = ok && EMB(t) != c;  // injective (only same-label depths could collide)
             const u32 *row = g.gtab + (u64)c * (g.nl + 1);
             u64 bn = d ? jd->bn_mask : 0;
             for (u32 t = 0; ok && bn; t++, bn >>= 1) {  // the other backward neighbours: edge (c, EMB(t)) must exist
                 if (!(bn & 1)) continue;
                 const u32 lt_ = t ? jplan[vb + t].label : lab0;
-                if (!edge_maybe(g, c, EMB(t))) {
+                if (!(cgl ? edge_maybe<true>(g, c, EMB(t)) : edge_maybe<false>(g, c, EMB(t)))) {
                     ok = false;
                 } else if (cdeg <= 64) {  // search c's (short) group of label(EMB(t))
                     ok = lt_ < g.nl && in_group(g, __ldcg(row + lt_), __ldcg(row + lt_ + 1), EMB(t));
@@ -1005,20 +1049,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             if (ok) {
                 EMB(d) = c;
                 // (1) label groups of c that later depths draw from: all in c's gtab row, two lookups in flight
-                const uint2 *kl = kids + vb + jd->kid_begin;
-                const u32 kn = jd->kid_count;
                 for (u32 k = 0; k < kn; k += 2) {
-                    const uint2 k0 = kl[k], k1 = kl[min(k + 1, kn - 1)];  // (depth, label)
+                    const bool pre = spec && k == 0;  // looked up ahead of the subtree-table test
+                    const uint2 k0 = pre ? sk0 : kl[k], k1 = pre ? sk1 : kl[min(k + 1, kn - 1)];  // (depth, label)
                     const u32 i0 = k0.x, l0 = k0.y, i1 = k1.x, l1 = k1.y;
-                    u32 a0 = 0, b0 = 0, a1 = 0, b1 = 0;
-                    if (l0 < g.nl) { a0 = __ldcg(row + l0); b0 = __ldcg(row + l0 + 1); }
-                    if (l1 < g.nl) { a1 = __ldcg(row + l1); b1 = __ldcg(row + l1 + 1); }
+                    u32 a0 = sa0, b0 = sb0, a1 = sa1, b1 = sb1;
+                    if (!pre) {
+                        a0 = b0 = a1 = b1 = 0;
+                        if (l0 < g.nl) { a0 = __ldcg(row + l0); b0 = __ldcg(row + l0 + 1); }
+                        if (l1 < g.nl) { a1 = __ldcg(row + l1); b1 = __ldcg(row + l1 + 1); }
+                    }
                     S0(i0) = a0; E0(i0) = b0;
                     S0(i1) = a1; E0(i1) = b1;
-                    if (pf) {  // first candidates of the depths that pivot on c
-                        prefetch_l2(g.nbrL + a0);
-                        prefetch_l2(g.nbrL + a1);
-                    }
                     if (a0 >= b0 || a1 >= b1) { ok = false; break; }  // nothing to draw from: no match below c
                 }
             }
@@ -1046,7 +1088,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                         const u32 pvx = EMB(ld->pivot_depth);
                         u64 m = ld->tail_mask;
                         for (u32 t = 0; m; t++, m >>= 1)
-                            if ((m & 1) && (t != 0 || lab0 == llab) && edge_maybe(g, pvx, EMB(t)) && in_group(g, s, e, EMB(t))) used++;
+                            if ((m & 1) && (t != 0 || lab0 == llab) && (cgl ? edge_maybe<true>(g, pvx, EMB(t)) : edge_maybe<false>(g, pvx, EMB(t))) && in_group(g, s, e, EMB(t))) used++;
                     }
                     const u32 n_free = (e - s) - used;
                     if (ld->tail_k == kTailMul) {
@@ -1066,7 +1108,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                             const u32 pvx = EMB(lb->pivot_depth);
                             u64 m = lb->tail_mask;
                             for (u32 t = 0; m; t++, m >>= 1)
-                                if ((m & 1) && (t != 0 || lab0 == llab) && edge_maybe(g, pvx, EMB(t)) && in_group(g, s2, e2, EMB(t))) used2++;
+                                if ((m & 1) && (t != 0 || lab0 == llab) && (cgl ? edge_maybe<true>(g, pvx, EMB(t)) : edge_maybe<false>(g, pvx, EMB(t))) && in_group(g, s2, e2, EMB(t))) used2++;
                         }
                         const u32 n_free2 = (e2 - s2) - used2;
                         // ordered pairs of distinct vertices: |A||B| - |A n B| over the free members; the groups are
@@ -1250,17 +1292,19 @@ u32 k3_item_stride(u32 max_nq) { return item_stride(join_m(max_nq)); }
 
 static JoinGraph join_graph(const JoinView &jv) {
     return JoinGraph{jv.label, reinterpret_cast<const uint2 *>(jv.nbrL), jv.gtab, jv.V, jv.nl, jv.deg, jv.lclass, jv.lpos,
-                     jv.lcoff, jv.tpool, jv.bloom, jv.bloom_mask};
+                     jv.lcoff, jv.tpool, jv.bloom, jv.bloom_mask, jv.lpos_packed};
 }
 
 cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
                           const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world, u32 heavy_deg,
-                          u64 *cursors, void *init, JoinQueue *jq, int sm_count, cudaStream_t s) {
+                          u64 *cursors, void *init, JoinQueue *jq, bool use_tables, int sm_count, cudaStream_t s) {
+    // (enumeration mode walks every vertex and ignores the tables: roots are then only filtered by degree)
+    const u64 *tp = use_tables ? jv.tpool : nullptr;
     k3_init_count_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, cand, jv.lclass, jv.deg, jv.lcoff,
-                                                     jv.nl, item_base, rank, world, heavy_deg, cursors);
-    k3_init_prefix_kernel<<<1, 32, 0, s>>>(n_queries, item_base, cursors, jq);
+                                                     jv.nl, item_base, rank, world, heavy_deg, jv.lpos, tp, cursors);
+    k3_init_prefix_kernel<<<1, 32, 0, s>>>(n_queries, cursors, jq);
     k3_init_items_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, cand, jv.lclass, jv.deg, jv.lcoff,
-                                                     jv.nl, item_base, rank, world, heavy_deg, cursors,
+                                                     jv.nl, item_base, rank, world, heavy_deg, jv.lpos, tp, cursors,
                                                      reinterpret_cast<uint2 *>(init));
     return cudaGetLastError();
 }
@@ -1298,13 +1342,17 @@ cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const Joi
     k3_dfs_kernel<M, T, B><<<sm_count * per_sm_##M##_##B, T, smem_##M##_##B, s>>>(g, q_vbase, jplan, reinterpret_cast<const uint2 *>(kids), cand, \
                                             reinterpret_cast<const uint2 *>(init), limits, answers, items, export_cap, \
                                             ready, epoch, jq, matches, matches_cap, match_cursor, flags)
-    static int env_pf = -1;
-    if (env_pf < 0) { const char *e = getenv("GPE_JOIN_PF"); env_pf = e ? atoi(e) : 0; }
+    static int env_tries = -1;
+    if (env_tries < 0) { const char *e = getenv("GPE_JOIN_TRIES"); env_tries = e ? atoi(e) : kTries; if (env_tries < 1 || env_tries > 255) env_tries = kTries; }
     static int env_tb = -1;
     if (env_tb < 0) { const char *e = getenv("GPE_JOIN_TAILBATCH"); env_tb = e ? atoi(e) : kTailBatch; if (env_tb < 1 || env_tb > 32) env_tb = kTailBatch; }
     static int env_spr = -1;
     if (env_spr < 0) { const char *e = getenv("GPE_JOIN_SPR"); env_spr = e ? atoi(e) : kStepsPerRound; if (env_spr < 1 || env_spr > 64) env_spr = kStepsPerRound; }
-    const u32 flags = (env_pf ? 1u : 0u) | ((u32)env_tb << 8) | ((u32)env_spr << 16);
+    static int env_cg = -1;
+    if (env_cg < 0) { const char *e = getenv("GPE_JOIN_CG"); env_cg = e ? atoi(e) : 1; }
+    static int env_spec = -1;
+    if (env_spec < 0) { const char *e = getenv("GPE_JOIN_SPEC"); env_spec = e ? atoi(e) : 1; }
+    const u32 flags = ((u32)env_tries << 24) | (env_cg ? 2u : 0u) | (env_spec ? 4u : 0u) | ((u32)env_tb << 8) | ((u32)env_spr << 16);
     // 8-vertex stacks, CTAs of 128 threads per SM (config 2, ms per batch): 5 (96 registers) 15.97, 6 (80 registers, 92 bytes of
     // spills) 15.61, 7 (72 registers) 19.9 -- beyond 6 the stacks leave too little of the SM's memory to L1, which holds the plans
     static int env_blocks = -1;
