@@ -1,6 +1,7 @@
 // gpe_api.cu -- the C ABI (include/gpe.h) and the host orchestration of the three kernel groups.
 // Product code: no CPU fallback, nothing from oracle/.
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 #include <thread>
 
@@ -301,8 +302,10 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
 
 constexpr u64 kJoinExportBytes = 256ull << 20;  // room for exported work items
 
-int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
+int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, bool force_dfs = false) {
     StageTimer tm(c, &c->stats.last_join_ms, kStageJoin);
+    c->b_rank = rank;
+    c->b_world = world;
     const u32 nq = c->b_nq;
     u64 *answers = c->d_answers.as<u64>();
     GPE_CUDA(c, cudaMemsetAsync(c->d_answers.p, 0, ((size_t)nq + 8) * sizeof(u64), c->stream));
@@ -355,9 +358,45 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap) {
     GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
                               c->d_cand.as<u32>(), c->d_item_base.as<u64>(), rank, world, heavy_deg,
                               c->d_qcur.as<u64>(), c->d_init.p, jq, tree_launches > 0, c->sm_count, c->stream));
+    // Schedule: the depth-first kernel by default.  GPE_JOIN_MODE=bfs selects the level-synchronous schedule (every
+    // candidate of a depth gets a thread of its own) where it applies: counting without any answer limit from the
+    // filter's own candidate sets.  Measured on config 2 it is slower (18.3 against 15.6 ms per batch: both test the same
+    // 172 M candidates at ~10 G/s), so it stays an option with a parity test, not the default.
+    bool use_bfs = !force_dfs && !enumerate && clean_start && nq > 0;
+    for (u32 q = 0; q < nq && use_bfs; q++) use_bfs = c->h_limits[q] >= GPE_LIMIT_MAX;
+    {
+        const char *e = getenv("GPE_JOIN_MODE");
+        use_bfs = use_bfs && e && strcmp(e, "bfs") == 0;
+    }
+    if (use_bfs) {
+        if (c->bfs_cap_e == 0 || c->bfs_max_nq < c->b_max_nq) {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            free_b += c->d_bfs.cap;
+            const u64 budget = std::min<u64>(free_b / 3, 16ull << 30);
+            const u64 per_entry = k3_bfs_bytes(c->b_max_nq, 1, 2) - 4096;  // one entry + two candidate slots
+            u64 cap_e = std::min<u64>(budget / std::max<u64>(per_entry, 1), 128ull << 20);
+            if (const char *e = getenv("GPE_BFS_CAP")) cap_e = std::min<u64>(cap_e, strtoull(e, nullptr, 10));  // tests: force the fallback
+            cap_e = std::max<u64>(cap_e, 1024);
+            GPE_CUDA(c, c->d_bfs.reserve(k3_bfs_bytes(c->b_max_nq, cap_e, 2 * cap_e)));
+            GPE_CUDA(c, c->d_bfs_cnt.reserve(256 * sizeof(u32)));
+            c->bfs_cap_e = cap_e;
+            c->bfs_cap_c = 2 * cap_e;
+            c->bfs_max_nq = c->b_max_nq;
+        }
+        GPE_CUDA(c, cudaMemsetAsync(c->d_bfs_cnt.p, 0, 256 * sizeof(u32), c->stream));
+        GPE_CUDA(c, k3_bfs(jv, c->bfs_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_cand.as<u32>(),
+                           c->d_init.p, jq, answers, c->d_bfs.p, c->bfs_cap_e, c->bfs_cap_c, c->d_bfs_cnt.as<u32>(),
+                           c->b_max_nq, c->sm_count, c->stream));
+        c->stats.kernel_launches += 2 * (c->b_max_nq - 1);
+        c->stats.join_launches += 2 * (c->b_max_nq - 1);
+    } else {
     GPE_CUDA(c, k3_dfs(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_cand.as<u32>(),
                        c->d_init.p, c->d_limits.as<u64>(), answers, c->d_items.as<u32>(), cap, c->d_ready.as<u32>(), epoch,
                        jq, d_matches, matches_cap, c->d_match_cursor.as<u64>(), c->sm_count, c->stream));
+    }
+    c->b_bfs_used = use_bfs;
+    c->stats.join_bfs = use_bfs ? 1 : 0;
     c->stats.kernel_launches += tree_launches;
     c->stats.join_launches += tree_launches;
     c->stats.kernel_launches += 5;
@@ -1005,6 +1044,28 @@ int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) {
     GPE_CUDA(c, cudaMemcpyAsync(pin, c->d_answers.p, (size_t)c->b_nq * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     GPE_CUDA(c, cudaMemcpyAsync(pin + c->b_nq, c->d_jq.p, sizeof(JoinQueue), cudaMemcpyDeviceToHost, c->stream));
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->b_bfs_used) {  // level-synchronous join: did every frontier fit?  (else recompute depth-first, once)
+        u32 cnt[72];
+        GPE_CUDA(c, cudaMemcpyAsync(cnt, c->d_bfs_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+        GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (cnt[64]) {
+            c->stats.join_fallbacks++;
+            int rc = run_join(c, c->b_rank, c->b_world, nullptr, 0, /*force_dfs=*/true);
+            if (rc) return rc;
+            return gpe_batch_download(c, raw_counts);
+        }
+        memcpy(raw_counts, pin, (size_t)c->b_nq * sizeof(u64));
+        JoinQueue jq;
+        memcpy(&jq, pin + c->b_nq, sizeof jq);
+        u64 steps;
+        memcpy(&steps, cnt + 66, sizeof steps);
+        c->stats.join_items = jq.n_init;
+        c->stats.join_exports = c->stats.join_donations = c->stats.join_idle_polls = 0;
+        c->stats.join_steps = steps;
+        c->stats.join_warp_iters = (steps + 31) / 32;
+        c->stats.d2h_bytes += (size_t)c->b_nq * sizeof(u64) + sizeof(JoinQueue) + sizeof cnt;
+        return GPE_OK;
+    }
     memcpy(raw_counts, pin, (size_t)c->b_nq * sizeof(u64));
     JoinQueue jq;
     memcpy(&jq, pin + c->b_nq, sizeof jq);

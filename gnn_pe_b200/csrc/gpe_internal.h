@@ -194,6 +194,10 @@ struct gpe_ctx {
     bool lpos_packed = false;
     gpe::DevBuf d_bloom;  // edge filter of the join
     u64 bloom_bits = 0;
+    gpe::DevBuf d_bfs, d_bfs_cnt;  // level-synchronous join: frontiers + counters
+    bool b_bfs_used = false;
+    u64 bfs_cap_e = 0, bfs_cap_c = 0;
+    u32 bfs_max_nq = 0, b_rank = 0, b_world = 1;
     gpe::DevBuf d_items, d_ready, d_jq, d_init, d_kids;  // exported join work items, their publication flags, the queue header, start tickets
     u32 join_epoch = 0;
     u32 b_max_nq = 0;
@@ -336,5 +340,13 @@ cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase,
 cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
                    const void *init, const u64 *limits, u64 *answers, u32 *items, u64 export_cap, u32 *ready, u32 epoch,
                    JoinQueue *jq, u32 *matches, u64 matches_cap, u64 *match_cursor, int sm_count, cudaStream_t s);
+
+// level-synchronous join (counting, no answer limits): frontier buffers in `buf` (k3_bfs_bytes), counters = 256 u32, zeroed;
+// counters[64] != 0 afterwards means a frontier outgrew its buffer and the result must be recomputed depth-first;
+// the u64 at counters + 66 counts the candidates tested
+size_t k3_bfs_bytes(u32 max_nq, u64 cap_e, u64 cap_c);
+cudaError_t k3_bfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
+                   const void *init, const JoinQueue *jq, u64 *answers, void *buf, u64 cap_e, u64 cap_c, u32 *counters,
+                   u32 levels, int sm_count, cudaStream_t s);
 
 }  // namespace gpe

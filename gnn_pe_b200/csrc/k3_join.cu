@@ -1229,6 +1229,292 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
 #undef E0
 }
 
+// ---- the level-synchronous join ----------------------------------------------------------------------------------
+//
+// Counting without an answer limit needs no early exit, so the walk can run one depth at a time over ALL partial
+// embeddings of ALL queries instead of one depth-first stack per thread: a frontier entry is (query, matched vertices
+// 0..L, running product); a level turns entries into candidates (one per member of the pivot's label group), tests
+// every candidate with one thread, and appends the survivors as the next frontier.  Same plan, same tests, same
+// counted-tail factors and subtree tables as the depth-first kernel -- only the schedule differs: every thread of the
+// GPU has a candidate of its own, there is no stack, no ticket queue and no work stealing, and the random gathers
+// (adjacency, tables, group directory, edge filter) are in flight by the million instead of one chain per lane.
+// The depth-first kernel remains for answer limits (`-n N` stops early), enumeration (matches wanted), caller-
+// supplied candidate sets, and as the fallback when a frontier outgrows its buffer (overflow flag, checked on download).
+struct BfsView {
+    u32 cap_e, cap_c;     // entries per frontier buffer, candidates per level
+    u32 *fq[2];           // query of every entry (two frontiers: current / next)
+    u64 *fprod[2];        // running product
+    u32 *femb[2];         // matched vertices, [depth][cap_e]
+    u32 *fS, *foff;       // per current entry: start of its candidate group in nbrL, first candidate slot
+    u32 *parent;          // per candidate slot: the entry it extends
+    u32 *n_entries;       // [depth]: entries with depths 0..depth matched
+    unsigned long long *n_cands;  // [depth]: candidates for that depth
+    u32 *overflow;
+    unsigned long long *steps;
+};
+
+// everything a freshly matched depth D decides (emb[D] = c is set): empty label groups for later depths reject it;
+// the counted-tail factors that close at D multiply into p.  Returns the new product (0 = no match below).
+template <int M, int T>
+__device__ u64 bfs_close(const JoinGraph &g, const JoinDepth *plan, const uint2 *kids_q, u32 n_exec, u32 tail_at, u32 D,
+                         const u32 *emb /*[t * T]*/, u32 lab0, u64 p) {
+#define BE(t) emb[(t) * T]
+    const JoinDepth *jd = plan + D;
+    const u32 c = BE(D);
+    const uint2 *kl = kids_q + jd->kid_begin;
+    const u32 *row = g.gtab + (u64)c * (g.nl + 1);
+    for (u32 k = 0; k < jd->kid_count; k++) {
+        const u32 l = kl[k].y;
+        if (l >= g.nl) return 0;
+        if (__ldcg(row + l) >= __ldcg(row + l + 1)) return 0;  // nothing to draw from: no match below c
+    }
+    u64 um = tail_at < n_exec ? jd->units_mask >> tail_at : 0;
+    for (u32 i = tail_at; um && p; i++, um >>= 1) {
+        if (!(um & 1)) continue;
+        const JoinDepth *ld = plan + i;
+        u32 s, e, used = ld->sure_used;
+        group_range(g, BE(ld->pivot_depth), ld->label, s, e);
+        {
+            const u32 llab = ld->label, pvx = BE(ld->pivot_depth);
+            u64 m = ld->tail_mask;
+            for (u32 t = 0; m; t++, m >>= 1)
+                if ((m & 1) && (t != 0 || lab0 == llab) && edge_maybe<true>(g, pvx, BE(t)) && in_group(g, s, e, BE(t))) used++;
+        }
+        const u32 n_free = (e - s) - used;
+        if (ld->tail_k == kTailMul) {
+            u64 f = n_free;
+            u32 n_run = n_free;
+            for (u32 k = i + 1; k < n_exec && plan[k].tail_k == kTailFall; k++) {
+                n_run = n_run ? n_run - 1 : 0;
+                f *= n_run;
+            }
+            p *= f;
+        } else {  // kTailPairA: leaf i and leaf i+1, same label, different pivots
+            const JoinDepth *lb = ld + 1;
+            u32 s2, e2, used2 = lb->sure_used;
+            group_range(g, BE(lb->pivot_depth), lb->label, s2, e2);
+            {
+                const u32 llab = lb->label, pvx = BE(lb->pivot_depth);
+                u64 m = lb->tail_mask;
+                for (u32 t = 0; m; t++, m >>= 1)
+                    if ((m & 1) && (t != 0 || lab0 == llab) && edge_maybe<true>(g, pvx, BE(t)) && in_group(g, s2, e2, BE(t))) used2++;
+            }
+            const u32 n_free2 = (e2 - s2) - used2;
+            u64 inter = 0;
+            u32 x = s, y = s2;
+            while (x < e && y < e2) {
+                const u32 vx = __ldcg(&g.nbrL[x].x), vy = __ldcg(&g.nbrL[y].x);
+                if (vx == vy) {
+                    bool is_used = false;
+                    for (u32 t = 0; t <= D; t++) is_used = is_used || BE(t) == vx;
+                    inter += is_used ? 0 : 1;
+                    x++;
+                    y++;
+                } else if (vx < vy) {
+                    x++;
+                } else {
+                    y++;
+                }
+            }
+            p *= (u64)n_free * n_free2 - inter;
+        }
+    }
+    return p;
+#undef BE
+}
+
+// bank a finished product / append a surviving entry; called by all 32 lanes
+__device__ __forceinline__ void bfs_bank(u64 *answers, u32 q, u64 p, bool fin) {
+    const unsigned m = __ballot_sync(kFull, fin);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    const u32 q0 = __shfl_sync(kFull, q, leader);
+    if (__all_sync(kFull, !fin || q == q0)) {
+        u64 v = fin ? p : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if (lane == leader) atomicAdd((unsigned long long *)&answers[q0], (unsigned long long)v);
+    } else if (fin) {
+        atomicAdd((unsigned long long *)&answers[q], (unsigned long long)p);
+    }
+}
+__device__ __forceinline__ u32 bfs_append_slot(u32 *counter, bool app) {
+    const unsigned m = __ballot_sync(kFull, app);
+    if (!m) return 0xffffffffu;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    u32 base = 0;
+    if (lane == leader) base = atomicAdd(counter, (u32)__popc(m));
+    base = __shfl_sync(kFull, base, leader);
+    return app ? base + __popc(m & lanemask_lt()) : 0xffffffffu;
+}
+
+// depth 0: one thread per live root (the ticket list of k3_init_items)
+template <int M, int T>
+__global__ void __launch_bounds__(T) k3_bfs_root_kernel(JoinGraph g, BfsView b, const u32 *__restrict__ q_vbase,
+                                                        const JoinDepth *__restrict__ jplan,
+                                                        const uint2 *__restrict__ kids, const u32 *__restrict__ cand,
+                                                        const uint2 *__restrict__ init, const JoinQueue *jq, u64 *answers) {
+    extern __shared__ u32 s_emb[];  // [M][T]
+    u32 *emb = s_emb + threadIdx.x;
+    const u64 n = jq->n_init, n_round = (n + 31) / 32 * 32;
+    u64 my_steps = 0;
+    for (u64 i = (u64)blockIdx.x * T + threadIdx.x; i < n_round; i += (u64)gridDim.x * T) {
+        bool fin = false, app = false;
+        u32 q = 0, c = 0;
+        u64 p = 0;
+        if (i < n) {
+            const uint2 it = init[i];
+            q = it.x;
+            const u32 vb = q_vbase[q];
+            const JoinDepth *plan = jplan + vb;
+            const u32 n_exec = plan->sure_used, tail_at = n_exec - plan->tail_k;
+            c = plan->tail_mask ? g.lclass[it.y] : cand[it.y];
+            my_steps++;
+            u64 tree_f = 1;
+            if (plan->tree_off != kNoTree) tree_f = __ldcg(g.tpool + plan->tree_off + __ldcg(g.lpos + c));
+            if (tree_f) {
+                emb[0] = c;
+                p = bfs_close<M, T>(g, plan, kids + vb, n_exec, tail_at, 0, emb, plan->label, tree_f);
+                fin = p != 0 && tail_at == 1;
+                app = p != 0 && tail_at > 1;
+            }
+        }
+        bfs_bank(answers, q, p, fin);
+        const u32 slot = bfs_append_slot(b.n_entries, app);
+        if (app) {
+            if (slot < b.cap_e) {
+                b.fq[0][slot] = q;
+                b.fprod[0][slot] = p;
+                b.femb[0][slot] = c;
+            } else {
+                *b.overflow = 1;
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(kFull, my_steps, o);
+    if ((threadIdx.x & 31) == 0 && my_steps) atomicAdd(b.steps, (unsigned long long)my_steps);
+}
+
+// entries with depths 0..D-1 matched -> candidate slots for depth D (one per member of the pivot's label group)
+__global__ void __launch_bounds__(256) k3_bfs_count_kernel(JoinGraph g, BfsView b, u32 D, const u32 *__restrict__ q_vbase,
+                                                           const JoinDepth *__restrict__ jplan) {
+    const int cur = (D - 1) & 1, lane = threadIdx.x & 31;
+    if (*b.overflow) return;  // the result is recomputed depth-first anyway
+    const u32 n = min(b.n_entries[D - 1], b.cap_e), n_round = (n + 31) / 32 * 32;
+    for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n_round; e += gridDim.x * blockDim.x) {
+        u32 S = 0, cnt = 0;
+        if (e < n) {
+            const JoinDepth *jd = jplan + q_vbase[b.fq[cur][e]] + D;
+            u32 E;
+            group_range(g, b.femb[cur][(u64)jd->pivot_depth * b.cap_e + e], jd->label, S, E);
+            cnt = E - S;
+        }
+        u32 inc = cnt;  // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const u32 total = __shfl_sync(kFull, inc, 31);
+        u64 base = 0;
+        if (lane == 31 && total) base = atomicAdd(&b.n_cands[D], (unsigned long long)total);
+        base = __shfl_sync(kFull, base, 31) + inc - cnt;
+        const bool fits = base + cnt <= b.cap_c;
+        if (e < n) {
+            b.fS[e] = S;
+            b.foff[e] = (u32)base;
+            if (cnt && !fits) *b.overflow = 1;
+        }
+        // parent ids: short groups by their own thread, long ones by the whole warp
+        if (fits && cnt <= 8)
+            for (u32 k = 0; k < cnt; k++) b.parent[(u32)base + k] = e;
+        unsigned big = __ballot_sync(kFull, fits && cnt > 8);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const u32 bb = __shfl_sync(kFull, (u32)base, src), cc = __shfl_sync(kFull, cnt, src), ee = __shfl_sync(kFull, e, src);
+            for (u32 k = lane; k < cc; k += 32) b.parent[bb + k] = ee;
+        }
+    }
+}
+
+// one thread per candidate of depth D
+template <int M, int T>
+__global__ void __launch_bounds__(T) k3_bfs_expand_kernel(JoinGraph g, BfsView b, u32 D, const u32 *__restrict__ q_vbase,
+                                                          const JoinDepth *__restrict__ jplan,
+                                                          const uint2 *__restrict__ kids, u64 *answers) {
+    extern __shared__ u32 s_emb[];  // [M][T]
+    u32 *emb = s_emb + threadIdx.x;
+#define BE(t) emb[(t) * T]
+    const int cur = (D - 1) & 1, nxt = D & 1;
+    if (*b.overflow) return;
+    const u32 n = (u32)min(b.n_cands[D], (unsigned long long)b.cap_c), n_round = (n + 31) / 32 * 32;
+    u64 my_steps = 0;
+    for (u32 sidx = blockIdx.x * T + threadIdx.x; sidx < n_round; sidx += gridDim.x * T) {
+        bool fin = false, app = false;
+        u32 q = 0, c = 0, e = 0;
+        u64 p = 0;
+        if (sidx < n) {
+            e = b.parent[sidx];
+            q = b.fq[cur][e];
+            const u32 vb = q_vbase[q];
+            const JoinDepth *plan = jplan + vb, *jd = plan + D;
+            const u32 n_exec = plan->sure_used, tail_at = n_exec - plan->tail_k, lab0 = plan->label;
+            const uint2 cd = g.nbrL[b.fS[e] + (sidx - b.foff[e])];
+            c = cd.x;
+            const u32 cdeg = g.packed ? cd.y & 255u : cd.y;
+            my_steps++;
+            bool ok = cdeg >= jd->deg;
+            u64 tree_f = 1;
+            if (ok && jd->tree_off != kNoTree) {
+                tree_f = __ldcg(g.tpool + jd->tree_off + (g.packed ? cd.y >> 8 : __ldcg(g.lpos + c)));
+                ok = tree_f != 0;
+            }
+            if (ok) {
+                for (u32 t = 0; t < D; t++) BE(t) = b.femb[cur][(u64)t * b.cap_e + e];
+                u64 sm = jd->tail_mask;  // earlier depths of the same label (k3_order)
+                for (u32 t = 0; sm; t++, sm >>= 1)
+                    if (sm & 1) ok = ok && BE(t) != c;
+                const u32 *row = g.gtab + (u64)c * (g.nl + 1);
+                u64 bn = jd->bn_mask;
+                for (u32 t = 0; ok && bn; t++, bn >>= 1) {  // the other backward neighbours: edge (c, emb[t]) must exist
+                    if (!(bn & 1)) continue;
+                    const u32 lt_ = t ? plan[t].label : lab0;
+                    if (!edge_maybe<true>(g, c, BE(t))) {
+                        ok = false;
+                    } else if (cdeg <= 64) {
+                        ok = lt_ < g.nl && in_group(g, __ldcg(row + lt_), __ldcg(row + lt_ + 1), BE(t));
+                    } else {
+                        u32 s2, e2;
+                        group_range(g, BE(t), jd->label, s2, e2);
+                        ok = in_group(g, s2, e2, c);
+                    }
+                }
+            }
+            if (ok) {
+                BE(D) = c;
+                p = bfs_close<M, T>(g, plan, kids + vb, n_exec, tail_at, D, emb, lab0, b.fprod[cur][e] * tree_f);
+                fin = p != 0 && D + 1 == tail_at;
+                app = p != 0 && D + 1 < tail_at;
+            }
+        }
+        bfs_bank(answers, q, p, fin);
+        const u32 slot = bfs_append_slot(&b.n_entries[D], app);
+        if (app) {
+            if (slot < b.cap_e) {
+                b.fq[nxt][slot] = q;
+                b.fprod[nxt][slot] = p;
+                for (u32 t = 0; t <= D; t++) b.femb[nxt][(u64)t * b.cap_e + slot] = BE(t);
+            } else {
+                *b.overflow = 1;
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(kFull, my_steps, o);
+    if ((threadIdx.x & 31) == 0 && my_steps) atomicAdd(b.steps, (unsigned long long)my_steps);
+#undef BE
+}
+
 }  // namespace
 
 cudaError_t k3_chunk_count(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slot, u32 n_slots, u64 *chunk_cnt,
@@ -1364,6 +1650,54 @@ cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const Joi
     else if (max_nq <= 32) { LAUNCH(32, 128, 2); }
     else { LAUNCH(64, 128, 1); }
 #undef LAUNCH
+    return cudaGetLastError();
+}
+
+// ---- level-synchronous join: buffers carved out of one allocation, 1 + 2 x (levels) launches, no host sync ---------
+size_t k3_bfs_bytes(u32 max_nq, u64 cap_e, u64 cap_c) {
+    const u64 m = join_m(max_nq);
+    return (size_t)(2 * cap_e * (4 + 8 + 4 * m) + cap_e * 8 + cap_c * 4 + 4096);
+}
+
+cudaError_t k3_bfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
+                   const void *init, const JoinQueue *jq, u64 *answers, void *buf, u64 cap_e, u64 cap_c, u32 *counters /*256 u32, zeroed*/,
+                   u32 levels /*depths to run: the batch's largest query*/, int sm_count, cudaStream_t s) {
+    JoinGraph g = join_graph(jv);
+    const u64 m = join_m(max_nq);
+    BfsView b;
+    b.cap_e = (u32)cap_e;
+    b.cap_c = (u32)cap_c;
+    unsigned char *p = reinterpret_cast<unsigned char *>(buf);
+    for (int i = 0; i < 2; i++) { b.fprod[i] = reinterpret_cast<u64 *>(p); p += cap_e * 8; }
+    for (int i = 0; i < 2; i++) { b.fq[i] = reinterpret_cast<u32 *>(p); p += cap_e * 4; }
+    for (int i = 0; i < 2; i++) { b.femb[i] = reinterpret_cast<u32 *>(p); p += cap_e * 4 * m; }
+    b.fS = reinterpret_cast<u32 *>(p); p += cap_e * 4;
+    b.foff = reinterpret_cast<u32 *>(p); p += cap_e * 4;
+    b.parent = reinterpret_cast<u32 *>(p);
+    b.n_entries = counters;
+    b.overflow = counters + 64;
+    b.steps = reinterpret_cast<unsigned long long *>(counters + 66);
+    b.n_cands = reinterpret_cast<unsigned long long *>(counters + 68);
+    const unsigned grid = (unsigned)sm_count * 8;
+#define BFS_LAUNCH(M)                                                                                                         \
+    do {                                                                                                                      \
+        constexpr int T = (M) <= 16 ? 256 : 128;                                                                              \
+        const size_t smem = (size_t)(M) * T * 4;                                                                              \
+        cudaFuncSetAttribute(k3_bfs_root_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+        cudaFuncSetAttribute(k3_bfs_expand_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+        k3_bfs_root_kernel<M, T><<<grid, T, smem, s>>>(g, b, q_vbase, jplan, reinterpret_cast<const uint2 *>(kids), cand,     \
+                                                       reinterpret_cast<const uint2 *>(init), jq, answers);                   \
+        for (u32 D = 1; D < levels; D++) {                                                                                    \
+            k3_bfs_count_kernel<<<grid, 256, 0, s>>>(g, b, D, q_vbase, jplan);                                                \
+            k3_bfs_expand_kernel<M, T><<<grid, T, smem, s>>>(g, b, D, q_vbase, jplan, reinterpret_cast<const uint2 *>(kids),  \
+                                                             answers);                                                       \
+        }                                                                                                                     \
+    } while (0)
+    if (m == 8) BFS_LAUNCH(8);
+    else if (m == 16) BFS_LAUNCH(16);
+    else if (m == 32) BFS_LAUNCH(32);
+    else BFS_LAUNCH(64);
+#undef BFS_LAUNCH
     return cudaGetLastError();
 }
 

@@ -176,6 +176,8 @@ typedef struct gpe_stats {
     uint64_t h2d_bytes, d2h_bytes;     /* host<->device bytes of the last batch (upload .. download) */
     uint64_t join_exports, join_donations, join_steps;  /* last join: subtree hand-overs between threads, DFS steps summed over threads */
     uint64_t join_warp_iters, join_idle_polls;          /* last join: warp loop iterations with / without a busy lane (lane utilisation = steps / (32 x warp_iters)) */
+    uint64_t join_bfs;        /* last join ran level-synchronously (counting, no answer limits) instead of depth-first */
+    uint64_t join_fallbacks;  /* level-synchronous joins recomputed depth-first because a frontier outgrew its buffer */
 } gpe_stats;
 int gpe_get_stats(gpe_ctx *ctx, gpe_stats *out);
 /* The context's CUDA stream (cudaStream_t) so callers can bracket calls with their own events. */

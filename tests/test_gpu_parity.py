@@ -446,3 +446,58 @@ def test_factorised_join_equals_reference_enumeration(nl, seed):
     for q, e in list(zip(queries, expect))[::5]:
         assert int(ctx.query_batch([q], [limit])[0]) == e
     ctx.close()
+
+
+# The level-synchronous schedule of the join (GPE_JOIN_MODE=bfs: counting, no answer limit) against the oracle's
+# enumeration and against the depth-first kernel on the same batch; with a frontier buffer too small for the batch the
+# library must notice, recompute depth-first and still return the same counts.
+@pytest.mark.parametrize("nl,seed", [(9, 31), (16, 32)])
+def test_level_synchronous_join_equals_depth_first_and_oracle(nl, seed, monkeypatch):
+    from oracle import oracle
+    g = synth.chung_lu_graph(1200, 7000, nl, gamma=2.4, degree_cap=60, seed=seed)
+    og = oracle.OracleGraph.from_csr(g.offsets, g.nbrs, g.labels)
+    sorted_nodes = graph_io.degree_order(g)
+    og.enumerate(3, sorted_nodes)
+    rng = np.random.default_rng(seed)
+    queries = []
+    for name, (edges, labels) in _TAIL_SHAPES.items():
+        if len(labels) >= 3:
+            queries.append(graph_io.csr_from_edges(len(labels), np.array(edges), np.array(labels) % nl))
+    for i in range(24):
+        nq = int(rng.integers(3, 10))
+        edges, lab = _random_query(rng, nq, int(rng.integers(0, 3)), nl)
+        queries.append(graph_io.csr_from_edges(nq, edges, lab))
+    cap = 20_000_000  # bounds the oracle's enumeration; queries that reach it are left out (no limit may be set here)
+    expect = [oracle.online(og, oracle.OracleGraph.from_csr(q.offsets, q.nbrs, q.labels), 2, cap) for q in queries]
+    queries = [q for q, e in zip(queries, expect) if e < cap]
+    expect = [e for e in expect if e < cap]
+    assert len(queries) >= 20 and sum(1 for e in expect if e > 0) >= len(expect) // 4
+
+    def run(env):
+        for k in ("GPE_JOIN_MODE", "GPE_BFS_CAP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = gpe.GpeContext(0)
+        ctx.set_graph(g.offsets, g.nbrs, g.labels)
+        _, vde = gpe.host_gen_vde(g.offsets, g.nbrs, g.labels, 2)
+        ctx.set_embeddings(vde)
+        ctx.enumerate(3, sorted_nodes, graph_io.block_membership(g.V, 3), 3)
+        ctx.build_table()
+        ans = ctx.query_batch(queries).tolist()
+        st = ctx.stats()
+        one = [int(ctx.query_batch([q])[0]) for q in queries[::7]]
+        ctx.close()
+        return ans, st, one
+
+    bfs, st_b, one_b = run({"GPE_JOIN_MODE": "bfs"})
+    assert st_b["join_bfs"] == 1 and st_b["join_fallbacks"] == 0
+    bad = [(i, a, e) for i, (a, e) in enumerate(zip(bfs, expect)) if a != e]
+    assert not bad, bad
+    assert one_b == expect[::7]
+    dfs, st_d, _ = run({})
+    assert st_d["join_bfs"] == 0 and dfs == expect
+    small, st_s, _ = run({"GPE_JOIN_MODE": "bfs", "GPE_BFS_CAP": "1024"})
+    assert small == expect
+    if nl == 9:  # (with 16 labels no frontier of this batch reaches the 1024-entry floor)
+        assert st_s["join_fallbacks"] >= 1
