@@ -11,6 +11,10 @@
 // Differences, all deliberate:
 //   * online mode does not parse all_paths.txt / build index.dat: it re-enumerates on the GPU from the
 //     graph and membership.txt (milliseconds) and scans instead of traversing an R*-tree;
+//   * the offline -> online handoff is a small versioned binary manifest (gnn-pe/paths.gpe: hashes of the graph and of
+//     membership.txt, l, p, row counts) next to the reference's text files.  Online mode checks it and refuses to run
+//     against outputs of another graph / membership / -l / -p -- the reference reuses a stale index.dat silently
+//     (custom.h:218-258);
 //   * missing input files are errors (the reference reads zeros silently, main.cpp:80-85);
 //   * -l other than 2 follows the patched-oracle semantics of SURVEY.md F5 (only l=2 and l=3 are built).
 #include <algorithm>
@@ -112,6 +116,52 @@ bool read_membership(const std::string &path, uint32_t V, std::vector<uint32_t> 
     return true;
 }
 
+// ---- offline -> online manifest ---------------------------------------------------------------------------------
+struct Manifest {
+    char magic[8];       // "GPEPATHS"
+    uint32_t version;    // 1
+    uint32_t L, p, V, E, reserved;
+    uint64_t graph_hash, membership_hash, n_rows;
+};
+
+uint64_t fnv1a(const void *data, size_t n, uint64_t h = 1469598103934665603ull) {
+    const unsigned char *b = static_cast<const unsigned char *>(data);
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+Manifest make_manifest(const Graph &g, const std::vector<uint32_t> &sorted, const std::vector<uint32_t> &member, uint32_t L,
+                       uint32_t p, uint64_t n_rows) {
+    Manifest m{};
+    std::memcpy(m.magic, "GPEPATHS", 8);
+    m.version = 1;
+    m.L = L; m.p = p; m.V = g.V; m.E = g.E;
+    uint64_t h = fnv1a(g.off.data(), ((size_t)g.V + 1) * 4);
+    h = fnv1a(g.nbr.data(), (size_t)g.off[g.V] * 4, h);
+    m.graph_hash = fnv1a(g.lab.data(), (size_t)g.V * 4, h);
+    m.membership_hash = fnv1a(member.data(), member.size() * 4, fnv1a(sorted.data(), sorted.size() * 4));
+    m.n_rows = n_rows;
+    return m;
+}
+
+// 0 = matches, 1 = no manifest (outputs of the reference's own offline run, or none: nothing to check), 2 = stale
+int check_manifest(const std::string &path, const Manifest &now, const std::vector<uint64_t> &rows_pp, std::string &why) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) return 1;
+    Manifest m{};
+    std::vector<uint64_t> pp(now.p);
+    bool ok = std::fread(&m, sizeof m, 1, f) == 1 && std::memcmp(m.magic, "GPEPATHS", 8) == 0 && m.version == 1;
+    if (ok && m.p == now.p) ok = std::fread(pp.data(), sizeof(uint64_t), now.p, f) == now.p;
+    std::fclose(f);
+    if (!ok) { why = "unreadable or from another version"; return 2; }
+    if (m.graph_hash != now.graph_hash || m.V != now.V || m.E != now.E) { why = "written for a different data graph"; return 2; }
+    if (m.membership_hash != now.membership_hash) { why = "written for a different membership.txt"; return 2; }
+    if (m.L != now.L) { why = "written for -l " + std::to_string(m.L - 1); return 2; }
+    if (m.p != now.p) { why = "written for -p " + std::to_string(m.p); return 2; }
+    if (m.n_rows != now.n_rows || pp != rows_pp) { why = "row counts differ"; return 2; }
+    return 0;
+}
+
 #define CK(ctx, call)                                                                  \
     do {                                                                               \
         if ((call) != GPE_OK) {                                                        \
@@ -176,9 +226,23 @@ int main(int argc, char **argv) {
             }
         }
         std::fclose(f);
+        const Manifest m = make_manifest(G, sorted, member, L, o.partitions, n_rows);
+        name = o.file + "gnn-pe/paths.gpe";
+        f = std::fopen(name.c_str(), "wb");
+        if (!f || std::fwrite(&m, sizeof m, 1, f) != 1 ||
+            std::fwrite(rows_pp.data(), sizeof(uint64_t), rows_pp.size(), f) != rows_pp.size()) {
+            std::fprintf(stderr, "cannot write %s\n", name.c_str());
+            return 1;
+        }
+        std::fclose(f);
     }
 
     if (o.mode == "online") {
+        std::string why;
+        if (check_manifest(o.file + "gnn-pe/paths.gpe", make_manifest(G, sorted, member, L, o.partitions, n_rows), rows_pp, why) == 2) {
+            std::fprintf(stderr, "%sgnn-pe/paths.gpe is stale (%s): run -m offline again\n", o.file.c_str(), why.c_str());
+            return 1;
+        }
         std::vector<double> x((size_t)G.V * o.embedding), vde((size_t)G.V * o.embedding);
         CK(ctx, gpe_host_gen_vde(G.V, G.off.data(), G.nbr.data(), G.lab.data(), o.embedding, x.data(), vde.data()));
         CK(ctx, gpe_set_embeddings(ctx, o.embedding, vde.data()));

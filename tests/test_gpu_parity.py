@@ -257,6 +257,18 @@ def test_host_cli_quickstart(tmp_path):
     out = subprocess.check_output([main, "-f", d, "-d", gold["data_path"], "-q", gold["query_paths_files"][0],
                                    "-m", "online", "-n", "1000"]).decode()
     assert "Answer Number: 1000 " in out
+    # the binary manifest of the offline run ties the outputs to (graph, membership.txt, -l, -p): other settings are refused
+    assert os.path.getsize(d + "gnn-pe/paths.gpe") == 56 + 8 * gold["p"]
+    r = subprocess.run([main, "-f", d, "-d", gold["data_path"], "-q", gold["query_paths_files"][0], "-m", "online", "-l", "3"],
+                       capture_output=True)
+    assert r.returncode == 1 and b"paths.gpe is stale (written for -l 2)" in r.stderr
+    other = load_case("uniform300")
+    r = subprocess.run([main, "-f", d, "-d", other["data_path"], "-q", gold["query_paths_files"][0], "-m", "online"],
+                       capture_output=True)
+    assert r.returncode == 1  # (membership.txt of another graph: rejected before or by the manifest)
+    os.remove(d + "gnn-pe/paths.gpe")   # outputs of the reference's own offline run carry no manifest: nothing to check
+    out = subprocess.check_output([main, "-f", d, "-d", gold["data_path"], "-q", gold["query_paths_files"][0], "-m", "online"]).decode()
+    assert "Answer Number: 45426 " in out
 
 
 def test_two_shards_in_one_process_match_single_gpu():
