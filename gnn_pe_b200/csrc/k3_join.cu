@@ -506,8 +506,6 @@ constexpr u32 kSplit = 8;
 constexpr u32 kExportEvery = 8;      // rounds between two looks at the queue header
 constexpr int kStepsPerRound = 2;   // DFS steps of a lane between two rounds of scheduling (tickets, donation, export)
 constexpr int kExportLanes = 4;  // lanes of a warp that may hand work over in one round
-constexpr int kTries = 1;        // sibling candidates a lane may test per step until one passes the cheap filters (measured on
-                                 // config 2: 1 -> 15.95 ms, 2 -> 16.55, 4 -> 17.19, 8 -> 17.34: a retry lengthens the warp's critical chain)
 constexpr int kTailBatch = 8;    // parked lanes that trigger a joint evaluation of their counted-tail factors
 
 __host__ __device__ constexpr u32 item_stride(u32 m) { return kItemHdr + 3 * m; }
@@ -744,9 +742,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                                                          u64 export_cap, u32 *ready, u32 epoch, JoinQueue *jq,
                                                          u32 *matches, u64 matches_cap, u64 *match_cursor, u32 flags) {
     constexpr u32 stride = item_stride(M);
-    const int tries = max(1, (int)(flags >> 24 & 0xffu));  // candidates a lane may test per step (see the step)
     const bool cgl = flags & 2u;  // bloom words and class positions go around L1
-    const bool spec = flags & 4u; // gtab lookups of the first kids issued together with the subtree-table lookup
     const int tail_batch = (int)(flags >> 8 & 0xffu);  // parked lanes that trigger a joint evaluation (kTailBatch)
     const int spr = (int)(flags >> 16 & 0xffu);        // DFS steps of a lane between two rounds of scheduling (kStepsPerRound)
     extern __shared__ u64 s_stack64[];  // prod [M][THREADS] u64 | emb | cur | end | s0 | e0, each [M][THREADS] u32
@@ -972,65 +968,47 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
           // spot; the warp evaluates all parked lanes together once kTailBatch of them wait or nobody else can move.
           u64 fin_p = 0;  // product to bank (leaf of the walk) or to descend with; 0 = nothing to do
           if (have && !pend) {
-            // ---- one DFS step: test the next candidate(s) of level d ----
-            // Most candidates fall at the cheap tests (degree, subtree table, injectivity), which cost one or two
-            // dependent loads and nothing else.  A lane keeps trying siblings until one passes them (at most `tries`),
-            // so that the expensive rest of the step (edge tests, group lookups) runs with more lanes on board.
+            // ---- one DFS step: test the next candidate of level d ----
+            // (measured and dropped, config 2: letting a lane retry siblings until one passes the cheap tests -- 2/4/8 tries
+            //  cost +0.6/+1.2/+1.4 ms, a retry lengthens the warp's critical chain; software prefetch of the next
+            //  sibling's rows +0.9 ms; group lookups issued ahead of the subtree-table test: no change)
+            my_steps++;
+            const u32 at = CUR(d);
+            CUR(d) = at + 1;
             const JoinDepth *jd = jplan + vb + d;
-            const u64 tree_off = matches ? kNoTree : jd->tree_off;
-            u32 c = 0, cdeg = 0, cpos = 0;
-            u64 tree_f = 1;
-            bool ok = false;
-            const uint2 *kl = kids + vb + jd->kid_begin;
-            const u32 kn = jd->kid_count;
-            uint2 sk0 = make_uint2(0, 0), sk1 = make_uint2(0, 0);
-            u32 sa0 = 0, sb0 = 0, sa1 = 0, sb1 = 0;
-            for (int tr = 0; tr < tries && !ok; tr++) {
-                const u32 at = CUR(d);
-                if (at >= END(d)) break;
-                my_steps++;
-                CUR(d) = at + 1;
-                if (d == 0) {
-                    if (jd->tail_mask) {  // the walk starts from the root's label class (the start vertex was peeled)
-                        c = g.lclass[at];
-                        cdeg = g.deg[c];
-                        lab0 = jd->label;
-                    } else {  // start candidates are taken as they are (the reference never checks them, custom.h:827-830)
-                        c = cand[at];
-                        cdeg = 0xffffffffu;
-                        lab0 = g.label[c];
-                    }
-                } else {
-                    const uint2 cd = g.nbrL[at];
-                    c = cd.x;
-                    cdeg = g.packed ? cd.y & 255u : cd.y;
-                    cpos = cd.y >> 8;
+            u32 c, cdeg, cpos = 0;
+            if (d == 0) {
+                if (jd->tail_mask) {  // the walk starts from the root's label class (the start vertex was peeled)
+                    c = g.lclass[at];
+                    cdeg = g.deg[c];
+                    lab0 = jd->label;
+                } else {  // start candidates are taken as they are (the reference never checks them, custom.h:827-830)
+                    c = cand[at];
+                    cdeg = 0xffffffffu;
+                    lab0 = g.label[c];
                 }
-                // (bit scans -- ffs/popc -- run on the quarter-rate XU pipe, which a first version of this loop
-                //  saturated: the masks of the plan are walked with shifts instead)
-                ok = cdeg >= jd->deg;
-                // The label groups of c that later depths draw from (first two kids) depend on c alone: their gtab
-                // lookups are issued NOW, next to the subtree-table lookup, instead of one round trip after it
-                if (spec && ok && kn) {
-                    sk0 = kl[0];
-                    sk1 = kl[min(1u, kn - 1)];
-                    const u32 *row_ = g.gtab + (u64)c * (g.nl + 1);
-                    if (sk0.y < g.nl) { sa0 = __ldcg(row_ + sk0.y); sb0 = __ldcg(row_ + sk0.y + 1); } else { sa0 = sb0 = 0; }
-                    if (sk1.y < g.nl) { sa1 = __ldcg(row_ + sk1.y); sb1 = __ldcg(row_ + sk1.y + 1); } else { sa1 = sb1 = 0; }
-                }
-                // everything that hangs below this query vertex in peeled subtrees: one factor per data vertex
-                tree_f = 1;
-                if (ok && tree_off != kNoTree) {
-                    const u32 pos = (g.packed && d) ? cpos : (cgl ? __ldcg(g.lpos + c) : g.lpos[c]);
-                    tree_f = __ldcg(g.tpool + tree_off + pos);
-                    ok = tree_f != 0;
-                }
-                // injective: only earlier depths of the same label could collide (k3_order); enumeration mode also walks
-                // the tail depths, whose tail_mask means something else: there every earlier depth is compared
-                u64 sm = d ? (matches ? (1ull << d) - 1 : jd->tail_mask) : 0;
-                for (u32 t = 0; sm; t++, sm >>= 1)
-                    if (sm & 1) ok = ok && EMB(t) != c;
+            } else {
+                const uint2 cd = g.nbrL[at];
+                c = cd.x;
+                cdeg = g.packed ? cd.y & 255u : cd.y;
+                cpos = cd.y >> 8;
             }
+            // (bit scans -- ffs/popc -- run on the quarter-rate XU pipe, which a first version of this loop saturated:
+            //  the masks of the plan are walked with shifts instead)
+            bool ok = cdeg >= jd->deg;
+            // everything that hangs below this query vertex in peeled subtrees: one factor per data vertex
+            const u64 tree_off = matches ? kNoTree : jd->tree_off;
+            u64 tree_f = 1;
+            if (ok && tree_off != kNoTree) {
+                const u32 pos = (g.packed && d) ? cpos : (cgl ? __ldcg(g.lpos + c) : g.lpos[c]);
+                tree_f = __ldcg(g.tpool + tree_off + pos);
+                ok = tree_f != 0;
+            }
+            // injective: only earlier depths of the same label could collide (k3_order); enumeration mode also walks the
+            // tail depths, whose tail_mask means something else: there every earlier depth is compared
+            u64 sm = d ? (matches ? (1ull << d) - 1 : jd->tail_mask) : 0;
+            for (u32 t = 0; sm; t++, sm >>= 1)
+                if (sm & 1) ok = ok && EMB(t) != c;
             const u32 *row = g.gtab + (u64)c * (g.nl + 1);
             u64 bn = d ? jd->bn_mask : 0;
             for (u32 t = 0; ok && bn; t++, bn >>= 1) {  // the other backward neighbours: edge (c, EMB(t)) must exist
@@ -1049,16 +1027,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             if (ok) {
                 EMB(d) = c;
                 // (1) label groups of c that later depths draw from: all in c's gtab row, two lookups in flight
+                const uint2 *kl = kids + vb + jd->kid_begin;
+                const u32 kn = jd->kid_count;
                 for (u32 k = 0; k < kn; k += 2) {
-                    const bool pre = spec && k == 0;  // looked up ahead of the subtree-table test
-                    const uint2 k0 = pre ? sk0 : kl[k], k1 = pre ? sk1 : kl[min(k + 1, kn - 1)];  // (depth, label)
+                    const uint2 k0 = kl[k], k1 = kl[min(k + 1, kn - 1)];  // (depth, label)
                     const u32 i0 = k0.x, l0 = k0.y, i1 = k1.x, l1 = k1.y;
-                    u32 a0 = sa0, b0 = sb0, a1 = sa1, b1 = sb1;
-                    if (!pre) {
-                        a0 = b0 = a1 = b1 = 0;
-                        if (l0 < g.nl) { a0 = __ldcg(row + l0); b0 = __ldcg(row + l0 + 1); }
-                        if (l1 < g.nl) { a1 = __ldcg(row + l1); b1 = __ldcg(row + l1 + 1); }
-                    }
+                    u32 a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+                    if (l0 < g.nl) { a0 = __ldcg(row + l0); b0 = __ldcg(row + l0 + 1); }
+                    if (l1 < g.nl) { a1 = __ldcg(row + l1); b1 = __ldcg(row + l1 + 1); }
                     S0(i0) = a0; E0(i0) = b0;
                     S0(i1) = a1; E0(i1) = b1;
                     if (a0 >= b0 || a1 >= b1) { ok = false; break; }  // nothing to draw from: no match below c
@@ -1628,17 +1604,13 @@ cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const Joi
     k3_dfs_kernel<M, T, B><<<sm_count * per_sm_##M##_##B, T, smem_##M##_##B, s>>>(g, q_vbase, jplan, reinterpret_cast<const uint2 *>(kids), cand, \
                                             reinterpret_cast<const uint2 *>(init), limits, answers, items, export_cap, \
                                             ready, epoch, jq, matches, matches_cap, match_cursor, flags)
-    static int env_tries = -1;
-    if (env_tries < 0) { const char *e = getenv("GPE_JOIN_TRIES"); env_tries = e ? atoi(e) : kTries; if (env_tries < 1 || env_tries > 255) env_tries = kTries; }
     static int env_tb = -1;
     if (env_tb < 0) { const char *e = getenv("GPE_JOIN_TAILBATCH"); env_tb = e ? atoi(e) : kTailBatch; if (env_tb < 1 || env_tb > 32) env_tb = kTailBatch; }
     static int env_spr = -1;
     if (env_spr < 0) { const char *e = getenv("GPE_JOIN_SPR"); env_spr = e ? atoi(e) : kStepsPerRound; if (env_spr < 1 || env_spr > 64) env_spr = kStepsPerRound; }
     static int env_cg = -1;
     if (env_cg < 0) { const char *e = getenv("GPE_JOIN_CG"); env_cg = e ? atoi(e) : 1; }
-    static int env_spec = -1;
-    if (env_spec < 0) { const char *e = getenv("GPE_JOIN_SPEC"); env_spec = e ? atoi(e) : 1; }
-    const u32 flags = ((u32)env_tries << 24) | (env_cg ? 2u : 0u) | (env_spec ? 4u : 0u) | ((u32)env_tb << 8) | ((u32)env_spr << 16);
+    const u32 flags = (env_cg ? 2u : 0u) | ((u32)env_tb << 8) | ((u32)env_spr << 16);
     // 8-vertex stacks, CTAs of 128 threads per SM (config 2, ms per batch): 5 (96 registers) 15.97, 6 (80 registers, 92 bytes of
     // spills) 15.61, 7 (72 registers) 19.9 -- beyond 6 the stacks leave too little of the SM's memory to L1, which holds the plans
     static int env_blocks = -1;
