@@ -838,7 +838,7 @@ int gpe_build_table(gpe_ctx *c, const uint8_t *part_select, uint64_t *n_table_ro
     }
     GPE_CUDA(c, cudaMemcpyAsync(c->d_cursor.p, bucket, ((size_t)t.n_keys + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
     GPE_CUDA(c, k1_fill(g, t, c->d_sorted.as<u32>(), c->d_member.as<u32>(), sel, c->d_cursor.as<u64>(), c->sm_count, c->stream));
-    GPE_CUDA(c, k1_summaries(t, c->stream));
+    GPE_CUDA(c, k1_expand(t, g, c->sm_count, c->stream));
     cudaEventRecord(b1, c->stream);
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaEventElapsedTime(&c->stats.last_build_ms, b0, b1);

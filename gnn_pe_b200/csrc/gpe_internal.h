@@ -275,7 +275,8 @@ cudaError_t k1_histogram(const GraphView &g, const TableView &t, const u32 *sort
                          const unsigned char *part_sel, u64 *hist, int sm_count, cudaStream_t s);
 cudaError_t k1_fill(const GraphView &g, const TableView &t, const u32 *sorted, const u32 *member,
                     const unsigned char *part_sel, u64 *cursor, int sm_count, cudaStream_t s);
-cudaError_t k1_summaries(const TableView &t, cudaStream_t s);
+// vertex ids (written by k1_fill) -> scan tiles + class positions + per-tile summaries
+cudaError_t k1_expand(const TableView &t, const GraphView &g, int sm_count, cudaStream_t s);
 cudaError_t k1_dump_table(const TableView &t, const GraphView &g, u64 first, u64 n, u32 *vids, u32 *labels, u32 *degs,
                           double *pde, cudaStream_t s);
 

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) k1_hist_kernel(GraphView g, KeyParams kp,
     }
 }
 
-// ---- fill: every row goes to the next free position of its bucket -------------------------------------
+// ---- fill: every row (its vertex ids) goes to the next free position of its bucket --------------------
 template <int L>
 struct FillF {
     const GraphView &g;
@@ -254,16 +254,11 @@ struct FillF {
     u64 *cursor;
     u32 a, key_a, key_ab;
     __device__ void begin_slot(u32, u32 b) { key_ab = key_a + key_term(kp, 1, g.label[b]); }
+    // Only the vertex ids are scattered (12 bytes per row at l=2): the 72-byte scan row is materialised afterwards by
+    // k1_expand, tile by tile with full-line stores.  Scattering whole rows cost 21 partial-sector stores per row
+    // (r01q capture: 3.7 G write sectors and 29 GB of DRAM read-for-fill for 43 GB of payload, 88 ms).
     __device__ void put(u64 row, int k, u32 v) const {
-        u64 tile = row / kTileRows;
-        u32 r = (u32)(row % kTileRows);
-        unsigned char *base = t.tiles + tile * t.tile_bytes;
-        u32 lab = g.label[v], dg = g.deg[v];
-        reinterpret_cast<u32 *>(base)[k * kTileRows + r] = lab;
-        reinterpret_cast<u32 *>(base + 4u * L * kTileRows)[k * kTileRows + r] = dg;
-        double *pde = reinterpret_cast<double *>(base + 8u * L * kTileRows);
-        for (u32 x = 0; x < t.E; x++) pde[(k * t.E + x) * kTileRows + r] = g.vde[(u64)v * t.E + x];
-        t.vids[(tile * L + k) * kTileRows + r] = g.lpos[v];  // bit index of the candidate bitmaps
+        t.vids[((row / kTileRows) * L + k) * kTileRows + (u32)(row % kTileRows)] = v;
     }
     __device__ void chunk(u32 b, u32 c, u32 d, bool valid) {
         unsigned act = __ballot_sync(kFull, valid);
@@ -326,31 +321,50 @@ __device__ __forceinline__ double block_reduce_max_f64(double v, double *s) {
     return r;
 }
 
-__global__ void __launch_bounds__(kTileRows) k1_summary_kernel(TableView t) {
+// ---- expand: vertex ids -> scan tiles, and the per-tile summaries in the same pass ----------------------
+// One CTA per tile, one thread per row: reads the row's vertex ids (coalesced), gathers label / degree / embedding /
+// class position of every vertex (28 bytes per vertex, the whole per-vertex table is L2-resident), writes the tile's
+// structure-of-arrays columns with full-line stores, replaces the ids by class positions (the bit index of the
+// candidate bitmaps), and reduces the tile's label range, max degrees and max-corner.  HBM-write bound:
+// (8L + 8Le + 4L) bytes per row.
+template <int L>
+__global__ void __launch_bounds__(kTileRows) k1_expand_kernel(TableView t, GraphView g) {
     __shared__ u32 s_u[kTileRows / 32];
     __shared__ double s_d[kTileRows / 32];
-    const u64 tile = blockIdx.x;
     const u32 r = threadIdx.x;
-    const bool valid = tile * kTileRows + r < t.n_rows;
-    const unsigned char *base = t.tiles + tile * t.tile_bytes;
-    const u32 *lab = reinterpret_cast<const u32 *>(base);
-    const u32 *dg = reinterpret_cast<const u32 *>(base + 4u * t.L * kTileRows);
-    const double *pde = reinterpret_cast<const double *>(base + 8u * t.L * kTileRows);
-    for (u32 k = 0; k < t.L; k++) {
-        u32 l = valid ? lab[k * kTileRows + r] : 0xffffffffu;
-        u32 mn = block_reduce_u32(l, true, s_u);
-        u32 mx = block_reduce_u32(valid ? l : 0u, false, s_u);
-        u32 dm = block_reduce_u32(valid ? dg[k * kTileRows + r] : 0u, false, s_u);
-        if (r == 0) {
-            t.lab_min[k * t.n_tiles + tile] = mn;
-            t.lab_max[k * t.n_tiles + tile] = mx;
-            t.deg_max[k * t.n_tiles + tile] = dm;
+    for (u64 tile = blockIdx.x; tile < t.n_tiles; tile += gridDim.x) {
+        const bool valid = tile * kTileRows + r < t.n_rows;
+        unsigned char *base = t.tiles + tile * t.tile_bytes;
+        u32 *lab = reinterpret_cast<u32 *>(base);
+        u32 *dg = reinterpret_cast<u32 *>(base + 4u * L * kTileRows);
+        double *pde = reinterpret_cast<double *>(base + 8u * L * kTileRows);
+        u32 *vid = t.vids + tile * L * kTileRows;
+#pragma unroll
+        for (int k = 0; k < L; k++) {
+            u32 l = 0xffffffffu, d = 0;
+            if (valid) {
+                const u32 v = vid[k * kTileRows + r];
+                l = g.label[v];
+                d = g.deg[v];
+                lab[k * kTileRows + r] = l;
+                dg[k * kTileRows + r] = d;
+                vid[k * kTileRows + r] = g.lpos[v];
+                for (u32 x = 0; x < t.E; x++) pde[(k * t.E + x) * kTileRows + r] = g.vde[(u64)v * t.E + x];
+            }
+            const u32 mn = block_reduce_u32(l, true, s_u);
+            const u32 mx = block_reduce_u32(valid ? l : 0u, false, s_u);
+            const u32 dm = block_reduce_u32(d, false, s_u);
+            if (r == 0) {
+                t.lab_min[k * t.n_tiles + tile] = mn;
+                t.lab_max[k * t.n_tiles + tile] = mx;
+                t.deg_max[k * t.n_tiles + tile] = dm;
+            }
         }
-    }
-    for (u32 d = 0; d < t.D; d++) {
-        double v = valid ? pde[d * kTileRows + r] : -1.0;
-        double mx = block_reduce_max_f64(v, s_d);
-        if (r == 0) t.pde_max[d * t.n_tiles + tile] = mx;
+        for (u32 dd = 0; dd < t.D; dd++) {
+            const double v = valid ? pde[dd * kTileRows + r] : -1.0;  // (own store, read back through L1)
+            const double mx = block_reduce_max_f64(v, s_d);
+            if (r == 0) t.pde_max[dd * t.n_tiles + tile] = mx;
+        }
     }
 }
 
@@ -464,9 +478,11 @@ cudaError_t k1_fill(const GraphView &g, const TableView &t, const u32 *sorted, c
     return cudaGetLastError();
 }
 
-cudaError_t k1_summaries(const TableView &t, cudaStream_t s) {
+cudaError_t k1_expand(const TableView &t, const GraphView &g, int sm_count, cudaStream_t s) {
     if (t.n_tiles == 0) return cudaSuccess;
-    k1_summary_kernel<<<(unsigned)t.n_tiles, kTileRows, 0, s>>>(t);
+    const unsigned blocks = (unsigned)std::min<u64>(t.n_tiles, (u64)sm_count * 8 * 16);
+    if (t.L == 3) k1_expand_kernel<3><<<blocks, kTileRows, 0, s>>>(t, g);
+    else k1_expand_kernel<4><<<blocks, kTileRows, 0, s>>>(t, g);
     return cudaGetLastError();
 }
 
