@@ -294,34 +294,8 @@ __global__ void __launch_bounds__(256) k1_fill_kernel(GraphView g, KeyParams kp,
     }
 }
 
-// ---- per-tile summaries: label range, max degree, max-corner of the path embeddings -------------------
-//      (the GPU analogue of build_auxiliary_index, custom.h:268-364)
-__device__ __forceinline__ u32 block_reduce_u32(u32 v, bool is_min, u32 *s) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        u32 t = __shfl_xor_sync(kFull, v, o);
-        v = is_min ? min(v, t) : max(v, t);
-    }
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
-    __syncthreads();
-    u32 r = s[0];
-    for (int w = 1; w < kTileRows / 32; w++) r = is_min ? min(r, s[w]) : max(r, s[w]);
-    __syncthreads();
-    return r;
-}
-
-__device__ __forceinline__ double block_reduce_max_f64(double v, double *s) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double r = s[0];
-    for (int w = 1; w < kTileRows / 32; w++) r = fmax(r, s[w]);
-    __syncthreads();
-    return r;
-}
-
-// ---- expand: vertex ids -> scan tiles, and the per-tile summaries in the same pass ----------------------
+// ---- expand: vertex ids -> scan tiles, and the per-tile summaries (label range, max degree, max-corner of the path
+//      embeddings: the GPU analogue of build_auxiliary_index, custom.h:268-364) in the same pass ----------
 // One CTA per tile, one thread per row: reads the row's vertex ids (coalesced), gathers label / degree / embedding /
 // class position of every vertex (28 bytes per vertex, the whole per-vertex table is L2-resident), writes the tile's
 // structure-of-arrays columns with full-line stores, replaces the ids by class positions (the bit index of the
@@ -329,10 +303,13 @@ __device__ __forceinline__ double block_reduce_max_f64(double v, double *s) {
 // (8L + 8Le + 4L) bytes per row.
 template <int L>
 __global__ void __launch_bounds__(kTileRows) k1_expand_kernel(TableView t, GraphView g) {
-    __shared__ u32 s_u[kTileRows / 32];
-    __shared__ double s_d[kTileRows / 32];
-    const u32 r = threadIdx.x;
-    for (u64 tile = blockIdx.x; tile < t.n_tiles; tile += gridDim.x) {
+    constexpr int W = kTileRows / 32;
+    __shared__ u32 s_u[2][3 * L][W];            // per-warp partials: label min, label max, max degree per position
+    __shared__ double s_d[2][kMaxL * kMaxE][W]; // per-warp partials of the max-corner; double-buffered by tile parity,
+    const u32 r = threadIdx.x;                  // so one barrier per tile is enough
+    const int lane = r & 31, warp = r >> 5;
+    int buf = 0;
+    for (u64 tile = blockIdx.x; tile < t.n_tiles; tile += gridDim.x, buf ^= 1) {
         const bool valid = tile * kTileRows + r < t.n_rows;
         unsigned char *base = t.tiles + tile * t.tile_bytes;
         u32 *lab = reinterpret_cast<u32 *>(base);
@@ -341,29 +318,47 @@ __global__ void __launch_bounds__(kTileRows) k1_expand_kernel(TableView t, Graph
         u32 *vid = t.vids + tile * L * kTileRows;
 #pragma unroll
         for (int k = 0; k < L; k++) {
-            u32 l = 0xffffffffu, d = 0;
+            u32 l = 0xffffffffu, d = 0, v = 0;
             if (valid) {
-                const u32 v = vid[k * kTileRows + r];
+                // streaming loads/stores for the table (touched once), so the per-vertex arrays stay in L2
+                v = __ldcs(vid + k * kTileRows + r);
                 l = g.label[v];
                 d = g.deg[v];
-                lab[k * kTileRows + r] = l;
-                dg[k * kTileRows + r] = d;
-                vid[k * kTileRows + r] = g.lpos[v];
-                for (u32 x = 0; x < t.E; x++) pde[(k * t.E + x) * kTileRows + r] = g.vde[(u64)v * t.E + x];
+                __stcs(lab + k * kTileRows + r, l);
+                __stcs(dg + k * kTileRows + r, d);
+                __stcs(vid + k * kTileRows + r, g.lpos[v]);
             }
-            const u32 mn = block_reduce_u32(l, true, s_u);
-            const u32 mx = block_reduce_u32(valid ? l : 0u, false, s_u);
-            const u32 dm = block_reduce_u32(d, false, s_u);
-            if (r == 0) {
-                t.lab_min[k * t.n_tiles + tile] = mn;
-                t.lab_max[k * t.n_tiles + tile] = mx;
-                t.deg_max[k * t.n_tiles + tile] = dm;
+            u32 mn = l, mx = valid ? l : 0u, dm = d;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                mn = min(mn, __shfl_xor_sync(kFull, mn, o));
+                mx = max(mx, __shfl_xor_sync(kFull, mx, o));
+                dm = max(dm, __shfl_xor_sync(kFull, dm, o));
+            }
+            if (lane == 0) { s_u[buf][3 * k][warp] = mn; s_u[buf][3 * k + 1][warp] = mx; s_u[buf][3 * k + 2][warp] = dm; }
+            for (u32 x = 0; x < t.E; x++) {
+                double e = -1.0;
+                if (valid) {
+                    e = g.vde[(u64)v * t.E + x];
+                    __stcs(pde + (k * t.E + x) * kTileRows + r, e);
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) e = fmax(e, __shfl_xor_sync(kFull, e, o));
+                if (lane == 0) s_d[buf][k * t.E + x][warp] = e;
             }
         }
-        for (u32 dd = 0; dd < t.D; dd++) {
-            const double v = valid ? pde[dd * kTileRows + r] : -1.0;  // (own store, read back through L1)
-            const double mx = block_reduce_max_f64(v, s_d);
-            if (r == 0) t.pde_max[dd * t.n_tiles + tile] = mx;
+        __syncthreads();
+        if (r < 3 * L) {
+            const int k = r / 3, what = r % 3;
+            u32 acc = s_u[buf][r][0];
+            for (int w = 1; w < W; w++) acc = what == 0 ? min(acc, s_u[buf][r][w]) : max(acc, s_u[buf][r][w]);
+            u32 *dst = what == 0 ? t.lab_min : what == 1 ? t.lab_max : t.deg_max;
+            dst[k * t.n_tiles + tile] = acc;
+        } else if (r >= 32 && r - 32 < t.D) {
+            const u32 dd = r - 32;
+            double acc = s_d[buf][dd][0];
+            for (int w = 1; w < W; w++) acc = fmax(acc, s_d[buf][dd][w]);
+            t.pde_max[dd * t.n_tiles + tile] = acc;
         }
     }
 }
