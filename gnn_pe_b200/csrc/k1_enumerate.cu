@@ -316,19 +316,37 @@ __global__ void __launch_bounds__(kTileRows) k1_expand_kernel(TableView t, Graph
         u32 *dg = reinterpret_cast<u32 *>(base + 4u * L * kTileRows);
         double *pde = reinterpret_cast<double *>(base + 8u * L * kTileRows);
         u32 *vid = t.vids + tile * L * kTileRows;
+        // all of a row's loads are issued before anything depends on them: ids first, then the per-vertex gathers
+        u32 v[L], l[L], d[L], ps[L];
+#pragma unroll
+        for (int k = 0; k < L; k++) v[k] = valid ? __ldcs(vid + k * kTileRows + r) : 0u;  // streaming: the table is touched once,
+#pragma unroll                                                                          // the per-vertex arrays stay in L2
+        for (int k = 0; k < L; k++) {
+            l[k] = valid ? g.label[v[k]] : 0xffffffffu;
+            d[k] = valid ? g.deg[v[k]] : 0u;
+            ps[k] = valid ? g.lpos[v[k]] : 0u;
+        }
 #pragma unroll
         for (int k = 0; k < L; k++) {
-            u32 l = 0xffffffffu, d = 0, v = 0;
-            if (valid) {
-                // streaming loads/stores for the table (touched once), so the per-vertex arrays stay in L2
-                v = __ldcs(vid + k * kTileRows + r);
-                l = g.label[v];
-                d = g.deg[v];
-                __stcs(lab + k * kTileRows + r, l);
-                __stcs(dg + k * kTileRows + r, d);
-                __stcs(vid + k * kTileRows + r, g.lpos[v]);
+            for (u32 x = 0; x < t.E; x++) {
+                double e = -1.0;
+                if (valid) {
+                    e = g.vde[(u64)v[k] * t.E + x];
+                    __stcs(pde + (k * t.E + x) * kTileRows + r, e);
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) e = fmax(e, __shfl_xor_sync(kFull, e, o));
+                if (lane == 0) s_d[buf][k * t.E + x][warp] = e;
             }
-            u32 mn = l, mx = valid ? l : 0u, dm = d;
+        }
+#pragma unroll
+        for (int k = 0; k < L; k++) {
+            if (valid) {
+                __stcs(lab + k * kTileRows + r, l[k]);
+                __stcs(dg + k * kTileRows + r, d[k]);
+                __stcs(vid + k * kTileRows + r, ps[k]);
+            }
+            u32 mn = l[k], mx = valid ? l[k] : 0u, dm = d[k];
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
                 mn = min(mn, __shfl_xor_sync(kFull, mn, o));
@@ -336,16 +354,6 @@ __global__ void __launch_bounds__(kTileRows) k1_expand_kernel(TableView t, Graph
                 dm = max(dm, __shfl_xor_sync(kFull, dm, o));
             }
             if (lane == 0) { s_u[buf][3 * k][warp] = mn; s_u[buf][3 * k + 1][warp] = mx; s_u[buf][3 * k + 2][warp] = dm; }
-            for (u32 x = 0; x < t.E; x++) {
-                double e = -1.0;
-                if (valid) {
-                    e = g.vde[(u64)v * t.E + x];
-                    __stcs(pde + (k * t.E + x) * kTileRows + r, e);
-                }
-#pragma unroll
-                for (int o = 16; o; o >>= 1) e = fmax(e, __shfl_xor_sync(kFull, e, o));
-                if (lane == 0) s_d[buf][k * t.E + x][warp] = e;
-            }
         }
         __syncthreads();
         if (r < 3 * L) {
