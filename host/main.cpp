@@ -16,7 +16,9 @@
 //     against outputs of another graph / membership / -l / -p -- the reference reuses a stale index.dat silently
 //     (custom.h:218-258);
 //   * missing input files are errors (the reference reads zeros silently, main.cpp:80-85);
-//   * -l other than 2 follows the patched-oracle semantics of SURVEY.md F5 (only l=2 and l=3 are built).
+//   * -l other than 2 follows the patched-oracle semantics of SURVEY.md F5 (only l=2 and l=3 are built);
+//   * -q may name a DIRECTORY: every *.graph file in it (sorted by name) is answered in one batch -- one
+//     `<file>: Answer Number: N` line per query, then the batch's total time and queries/s (BASELINE.json config 5).
 #include <algorithm>
 #include <chrono>
 #include <climits>
@@ -24,6 +26,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dirent.h>
+#include <sys/stat.h>
 #include <fstream>
 #include <iostream>
 #include <string>
@@ -249,6 +253,41 @@ int main(int argc, char **argv) {
         uint64_t table_rows = 0;
         CK(ctx, gpe_build_table(ctx, nullptr, &table_rows));
 
+        struct stat st_q{};
+        if (stat(o.query.c_str(), &st_q) == 0 && S_ISDIR(st_q.st_mode)) {  // a directory of queries: one batch
+            std::vector<std::string> files;
+            if (DIR *dir = opendir(o.query.c_str())) {
+                while (dirent *e = readdir(dir)) {
+                    std::string n = e->d_name;
+                    if (n.size() > 6 && n.compare(n.size() - 6, 6, ".graph") == 0) files.push_back(n);
+                }
+                closedir(dir);
+            }
+            std::sort(files.begin(), files.end());
+            if (files.empty()) { std::fprintf(stderr, "no *.graph files in %s\n", o.query.c_str()); return 1; }
+            std::vector<uint32_t> vbase(1, 0), ebase(1, 0), offs, nbrs, labs;
+            for (const std::string &n : files) {
+                Graph Qi;
+                if (!load(o.query + "/" + n, Qi)) return -1;
+                offs.insert(offs.end(), Qi.off.begin(), Qi.off.end());
+                nbrs.insert(nbrs.end(), Qi.nbr.begin(), Qi.nbr.begin() + Qi.off[Qi.V]);
+                labs.insert(labs.end(), Qi.lab.begin(), Qi.lab.begin() + Qi.V);
+                vbase.push_back(vbase.back() + Qi.V);
+                ebase.push_back(ebase.back() + Qi.off[Qi.V]);
+            }
+            nbrs.push_back(0);
+            std::vector<uint64_t> limits(files.size(), limit), answers(files.size(), 0);
+            gpe_batch batch{(uint32_t)files.size(), vbase.data(), ebase.data(), offs.data(), nbrs.data(), labs.data(), limits.data()};
+            auto t0 = std::chrono::high_resolution_clock::now();
+            CK(ctx, gpe_query_batch(ctx, &batch, 0, answers.data()));
+            auto t1 = std::chrono::high_resolution_clock::now();
+            double ms = std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count() / 1e6;
+            for (size_t i = 0; i < files.size(); i++)
+                std::cout << files[i] << ": Answer Number: " << (uint32_t)answers[i] << std::endl;
+            std::cout << "Queries: " << files.size() << " Query Time (ms): " << ms << " Queries/s: " << files.size() / (ms / 1e3) << std::endl;
+            gpe_destroy(ctx);
+            return 0;
+        }
         Graph Q;
         if (!load(o.query, Q)) return -1;
         uint32_t vbase[2] = {0, Q.V}, ebase[2] = {0, Q.off[Q.V]};

@@ -257,6 +257,13 @@ def test_host_cli_quickstart(tmp_path):
     out = subprocess.check_output([main, "-f", d, "-d", gold["data_path"], "-q", gold["query_paths_files"][0],
                                    "-m", "online", "-n", "1000"]).decode()
     assert "Answer Number: 1000 " in out
+    # a directory as -q: all its queries in one batch
+    qdir = d + "queries"
+    os.makedirs(qdir)
+    for i in range(3):
+        shutil.copy(gold["query_paths_files"][0], f"{qdir}/q{i}.graph")
+    out = subprocess.check_output([main, "-f", d, "-d", gold["data_path"], "-q", qdir, "-m", "online"]).decode()
+    assert out.count(": Answer Number: 45426") == 3 and "Queries: 3 Query Time (ms): " in out
     # the binary manifest of the offline run ties the outputs to (graph, membership.txt, -l, -p): other settings are refused
     assert os.path.getsize(d + "gnn-pe/paths.gpe") == 56 + 8 * gold["p"]
     r = subprocess.run([main, "-f", d, "-d", gold["data_path"], "-q", gold["query_paths_files"][0], "-m", "online", "-l", "3"],
