@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
 //   * between warps: tickets [0, n_init) are the start candidates (JoinInit), later tickets are exported items
 //     in a linear buffer.  Lanes claim tickets while published items are available; a warp without any busy lane
 //     registers as idle and polls the queue header with back-off; busy warps look at the header every
-//     kExportEvery iterations (the loads are issued one iteration ahead of their use) and, when idle warps
+//     2^kExportEveryLog2 iterations (the loads are issued one iteration ahead of their use) and, when idle warps
 //     outnumber the published items, one lane hands over the unexplored siblings of its shallowest level as new
 //     items.  JoinQueue::pending counts published items whose work has not been retired; a warp retires what it
 //     claimed whenever all its lanes run dry, so pending == 0 means the join is complete.  Exporting is only load
@@ -503,7 +503,9 @@ struct JoinGraph {
 
 constexpr int kItemHdr = 8;  // q, level, lo, hi, prod (2 words), label of the start vertex, pad; then EMB | S0 | E0
 constexpr u32 kSplit = 8;
-constexpr u32 kExportEvery = 8;      // rounds between two looks at the queue header
+constexpr int kExportEveryLog2 = 1;  // log2 of the rounds between two looks at the queue header (config 2, ms per batch:
+                                     // every 8 rounds 15.60, 4: 15.28, 2: 15.22, 1: 15.71 -- the end of the join is a few
+                                     // generations of subtree hand-overs, each waiting for a busy warp's next look)
 constexpr int kStepsPerRound = 2;   // DFS steps of a lane between two rounds of scheduling (tickets, donation, export)
 constexpr int kExportLanes = 4;  // lanes of a warp that may hand work over in one round
 constexpr int kTailBatch = 8;    // parked lanes that trigger a joint evaluation of their counted-tail factors
@@ -743,6 +745,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                                                          u32 *matches, u64 matches_cap, u64 *match_cursor, u32 flags) {
     constexpr u32 stride = item_stride(M);
     const bool cgl = flags & 2u;  // bloom words and class positions go around L1
+    const u32 exp_mask = (1u << (flags >> 4 & 7u)) - 1;  // rounds between two looks at the queue header, minus one (kExportEvery)
     const int tail_batch = (int)(flags >> 8 & 0xffu);  // parked lanes that trigger a joint evaluation (kTailBatch)
     const int spr = (int)(flags >> 16 & 0xffu);        // DFS steps of a lane between two rounds of scheduling (kStepsPerRound)
     extern __shared__ u64 s_stack64[];  // prod [M][THREADS] u64 | emb | cur | end | s0 | e0, each [M][THREADS] u32
@@ -805,7 +808,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             fresh = true;
             if (h_pending <= 0 && !busy) break;  // join complete
         }
-        if (busy && ((iter & (kExportEvery - 1)) == 0 || ((free_m | tick) && (iter & 7) == 0))) {
+        if (busy && ((iter & exp_mask) == 0 || ((free_m | tick) && (iter & 7) == 0))) {
             if (lane == 0) {
                 ld_relaxed_2xu64(&jq->head, pf_a, pf_b);
                 ld_relaxed_2xu64(&jq->pending, pf_c, pf_d);
@@ -1141,7 +1144,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
 
         // ---- between warps: when idle warps outnumber the published items, the lanes with the shallowest unexplored
         //      sibling ranges give them away ----
-        if ((iter & (kExportEvery - 1)) == 1 && h_idle > 0 && (long long)(h_tail - h_head) < (long long)(h_idle * 8)) {
+        if ((iter & exp_mask) == (1u & exp_mask) && h_idle > 0 && (long long)(h_tail - h_head) < (long long)(h_idle * 8)) {
             u32 key = 0xffffffffu, l = 0;
             if (have && can_export) {
                 for (l = base; l <= d; l++)
@@ -1610,7 +1613,9 @@ cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const Joi
     if (env_spr < 0) { const char *e = getenv("GPE_JOIN_SPR"); env_spr = e ? atoi(e) : kStepsPerRound; if (env_spr < 1 || env_spr > 64) env_spr = kStepsPerRound; }
     static int env_cg = -1;
     if (env_cg < 0) { const char *e = getenv("GPE_JOIN_CG"); env_cg = e ? atoi(e) : 1; }
-    const u32 flags = (env_cg ? 2u : 0u) | ((u32)env_tb << 8) | ((u32)env_spr << 16);
+    static int env_exp = -1;
+    if (env_exp < 0) { const char *e = getenv("GPE_JOIN_EXPORT_LOG2"); env_exp = e ? atoi(e) : kExportEveryLog2; if (env_exp < 0 || env_exp > 7) env_exp = kExportEveryLog2; }
+    const u32 flags = (env_cg ? 2u : 0u) | ((u32)env_exp << 4) | ((u32)env_tb << 8) | ((u32)env_spr << 16);
     // 8-vertex stacks, CTAs of 128 threads per SM (config 2, ms per batch): 5 (96 registers) 15.97, 6 (80 registers, 92 bytes of
     // spills) 15.61, 7 (72 registers) 19.9 -- beyond 6 the stacks leave too little of the SM's memory to L1, which holds the plans
     static int env_blocks = -1;
