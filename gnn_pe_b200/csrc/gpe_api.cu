@@ -316,19 +316,32 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
     const bool enumerate = d_matches != nullptr;
     const bool clean_start = c->b_cand_clean && !enumerate;
     const u32 n_slots = c->b_slots;
-    GPE_CUDA(c, c->d_tjobs.reserve(std::max<size_t>(n_slots, 1) * sizeof(TreeJob)));
-    GPE_CUDA(c, c->d_tchild.reserve(std::max<size_t>(n_slots, 1) * sizeof(u32)));
+    // (two table jobs per slot at most: N_v of a vertex with peeled children, S_u of a weighted counted leaf)
+    GPE_CUDA(c, c->d_tjobs.reserve(2 * std::max<size_t>(n_slots, 1) * sizeof(TreeJob)));
+    GPE_CUDA(c, c->d_tchild.reserve(2 * std::max<size_t>(n_slots, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_tcursor.reserve(4 * sizeof(u64)));
-    GPE_CUDA(c, c->d_tpool.reserve(std::max<u64>((u64)n_slots * c->max_class, 1) * sizeof(u64)));
+    GPE_CUDA(c, c->d_tpool.reserve(2 * std::max<u64>((u64)n_slots * c->max_class, 1) * sizeof(u64)));
     GPE_CUDA(c, cudaMemsetAsync(c->d_tcursor.p, 0, 4 * sizeof(u64), c->stream));
-    GPE_CUDA(c, c->d_tlist.reserve(((size_t)kMaxTreeLevels * std::max<u32>(n_slots, 1) + kMaxTreeLevels) * sizeof(u32)));
+    GPE_CUDA(c, c->d_tlist.reserve(((size_t)kMaxTreeLevels * 2 * std::max<u32>(n_slots, 1) + kMaxTreeLevels) * sizeof(u32)));
+    // Schedule: the depth-first kernel by default.  GPE_JOIN_MODE=bfs selects the level-synchronous schedule (every
+    // candidate of a depth gets a thread of its own) where it applies: counting without any answer limit from the
+    // filter's own candidate sets.  Measured on config 2 it is slower (18.3 against 15.6 ms per batch: both test the same
+    // 172 M candidates at ~10 G/s), so it stays an option with a parity test, not the default.
+    bool use_bfs = !force_dfs && !enumerate && clean_start && nq > 0;
+    for (u32 q = 0; q < nq && use_bfs; q++) use_bfs = c->h_limits[q] >= GPE_LIMIT_MAX;
+    {
+        const char *e = getenv("GPE_JOIN_MODE");
+        use_bfs = use_bfs && e && strcmp(e, "bfs") == 0;
+    }
+    bool allow_weighted = !use_bfs;  // weighted counted leaves: depth-first kernel only
+    if (const char *e = getenv("GPE_JOIN_WEIGHTED")) allow_weighted = allow_weighted && atoi(e) != 0;
     u32 *tcount = c->d_tlist.as<u32>(), *tlist = tcount + kMaxTreeLevels;
     GPE_CUDA(c, cudaMemsetAsync(tcount, 0, kMaxTreeLevels * sizeof(u32), c->stream));
     GPE_CUDA(c, k3_order(nq, c->V, c->d_q_vbase.as<u32>(), c->d_q_ebase.as<u32>(), c->d_q_offsets.as<u32>(),
                          c->d_q_nbrs.as<u32>(), c->d_q_labels.as<u32>(), c->d_cand_off.as<u64>(), c->d_order.as<u32>(),
                          c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_item_base.as<u64>(), rank, world,
                          enumerate, clean_start, c->n_labels, c->d_lcoff.as<u32>(), c->d_tjobs.as<TreeJob>(),
-                         c->d_tchild.as<u32>(), c->d_tcursor.as<u64>(), tcount, tlist, n_slots, c->stream));
+                         c->d_tchild.as<u32>(), c->d_tcursor.as<u64>(), tcount, tlist, n_slots, allow_weighted, c->stream));
     JoinView jv{c->d_label.as<u32>(), c->d_nbrL.as<u32>(), c->d_gtab.as<u32>(), c->V, c->n_labels, c->d_deg.as<u32>(),
                 c->d_lclass.as<u32>(), c->d_lpos.as<u32>(), c->d_lcoff.as<u32>(), c->d_tpool.as<u64>(), c->d_bloom.as<u32>(),
                 c->bloom_bits - 1, c->lpos_packed};
@@ -358,16 +371,6 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
     GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
                               c->d_cand.as<u32>(), c->d_item_base.as<u64>(), rank, world, heavy_deg,
                               c->d_qcur.as<u64>(), c->d_init.p, jq, tree_launches > 0, c->sm_count, c->stream));
-    // Schedule: the depth-first kernel by default.  GPE_JOIN_MODE=bfs selects the level-synchronous schedule (every
-    // candidate of a depth gets a thread of its own) where it applies: counting without any answer limit from the
-    // filter's own candidate sets.  Measured on config 2 it is slower (18.3 against 15.6 ms per batch: both test the same
-    // 172 M candidates at ~10 G/s), so it stays an option with a parity test, not the default.
-    bool use_bfs = !force_dfs && !enumerate && clean_start && nq > 0;
-    for (u32 q = 0; q < nq && use_bfs; q++) use_bfs = c->h_limits[q] >= GPE_LIMIT_MAX;
-    {
-        const char *e = getenv("GPE_JOIN_MODE");
-        use_bfs = use_bfs && e && strcmp(e, "bfs") == 0;
-    }
     if (use_bfs) {
         if (c->bfs_cap_e == 0 || c->bfs_max_nq < c->b_max_nq) {
             size_t free_b = 0, total_b = 0;

@@ -142,6 +142,8 @@ constexpr u32 kTailMul = 0;    // multiply by the free members of the leaf's lab
 constexpr u32 kTailFall = 1;   // same pivot and label as the previous tail depth: multiply by (previous factor - 1)
 constexpr u32 kTailPairA = 2;  // two same-label leaves on different pivots: |A||B| - |A n B| (this depth and the next)
 constexpr u32 kTailPairB = 3;
+constexpr u32 kTailW = 0x100;  // flag: the leaf carries peeled subtrees; its members weigh N_u[y] (tree_off), the sum over a
+                               // pivot's group is tabulated as S_u (units_mask), bn_mask names the prefix vertices surely in it
 constexpr u64 kNoTree = ~0ull;
 
 // One per query vertex slot: the table of a vertex with peeled children (level 0 = none).
@@ -311,8 +313,8 @@ cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebas
                      JoinDepth *jplan, void *kids /*uint2 per query vertex*/, u64 *item_base, u32 rank, u32 world,
                      bool enumerate /*walk every vertex (matches wanted)*/, bool clean_start /*start candidates carry the
                      query label (they come from the filter)*/, u32 n_labels, const u32 *lcoff, TreeJob *tjobs, u32 *tchild,
-                     u64 *tcursor, u32 *tcount /*kMaxTreeLevels, zeroed*/, u32 *tlist /*kMaxTreeLevels x n_slots*/, u32 n_slots,
-                     cudaStream_t s);
+                     u64 *tcursor, u32 *tcount /*kMaxTreeLevels, zeroed*/, u32 *tlist /*kMaxTreeLevels x 2 n_slots*/, u32 n_slots,
+                     bool allow_weighted /*counted leaves may carry peeled subtrees (depth-first kernel only)*/, cudaStream_t s);
 // label-grouped adjacency for the join (built on the host in gpe_set_graph)
 struct JoinView {
     const u32 *label, *nbrL /* (neighbour, degree) pairs */, *gtab;

@@ -166,7 +166,9 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                                                        JoinDepth *jplan, uint2 *kids, u64 *item_base, u32 rank,
                                                        u32 world, u32 per_ticket, bool enumerate, bool clean_start,
                                                        u32 n_labels, const u32 *__restrict__ lcoff, TreeJob *tjobs,
-                                                       u32 *tchild, u64 *tcursor, u32 *tcount, u32 *tlist, u32 n_slots) {
+                                                       u32 *tchild, u64 *tcursor, u32 *tcount, u32 *tlist,
+                                                       u32 n_slots /*stride of tlist: 2 x slots*/, u32 sjob_base /*slots*/,
+                                                       bool allow_weighted) {
     for (u32 q = threadIdx.x; q < n_queries; q += blockDim.x) {
         const u32 vb = q_vbase[q], nq = q_vbase[q + 1] - vb;
         const u32 *off = q_offsets + vb + q;  // nq + 1 local offsets
@@ -257,24 +259,39 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                     if (sz < best || (sz == best && qdeg(u) > qdeg(root))) { best = sz; root = u; }
                 }
             }
-            u64 tail_set = 0;
-            u32 tail_list[kMaxNQ], n_tail = 0;
+            // Counted leaves: leaves of the CORE whose only core neighbour (their pivot) is walked.  A leaf that is also a
+            // leaf of the query contributes the number of free members of its pivot's label group; a leaf that carries
+            // peeled subtrees (it has a repeated label, so it could not be peeled itself) contributes the same sum
+            // WEIGHTED by its own table N_u: sum over free members y of N_u[y] = S_u[pivot image] - (N_u of the prefix
+            // vertices inside the group), with S_u tabulated like any parent-of-a-peeled-child table (k3_tree_tables).
+            u64 tail_set = 0, weighted = 0;
+            u32 tail_list[kMaxNQ], n_tail = 0, cpar[kMaxNQ];
+            for (u32 u = 0; u < nq; u++) {
+                cpar[u] = 0xffffffffu;
+                if (!(alive >> u & 1) || remdeg[u] != 1) continue;
+                for (u32 j = off[u]; j < off[u + 1]; j++)
+                    if (alive >> nbr[j] & 1) cpar[u] = nbr[j];
+            }
             for (u32 u = 0; u < nq && nK >= 3 && n_tail + 2 < nK; u++) {
-                if (u == root || !(alive >> u & 1) || qdeg(u) != 1) continue;
-                const u32 pv = nbr[off[u]];
+                if (u == root || !(alive >> u & 1) || remdeg[u] != 1) continue;
+                const bool wu = qdeg(u) != 1;  // carries peeled subtrees
+                if (wu && !allow_weighted) continue;
+                const u32 pv = cpar[u];
                 u32 r = 0, p0 = 0;
-                bool mixed = false;
+                bool mixed = false, any_w = wu;
                 for (u32 k = 0; k < n_tail; k++) {
                     const u32 t = tail_list[k];
                     if (qlab[t] != qlab[u]) continue;
-                    const u32 pt = nbr[off[t]];
+                    const u32 pt = cpar[t];
                     if (r == 0) p0 = pt; else if (pt != p0) mixed = true;
+                    any_w = any_w || (weighted >> t & 1);
                     r++;
                 }
-                // a label may appear on one tail leaf, on several leaves of ONE pivot, or on two leaves of two pivots
-                if (r == 0 || (!mixed && pv == p0) || (r == 1 && pv != p0)) {
+                // a label may appear on one tail leaf, on several plain leaves of ONE pivot, or on two leaves of two pivots
+                if (r == 0 || (!mixed && pv == p0 && !any_w) || (r == 1 && pv != p0)) {
                     tail_list[n_tail++] = u;
                     tail_set |= 1ull << u;
+                    if (wu) weighted |= 1ull << u;
                 }
             }
             const u32 n_walk = nK - n_tail;
@@ -309,7 +326,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                         if ((placed >> t2 & 1) || qlab[t2] != qlab[t]) continue;
                         placed |= 1ull << t2;
                         xo[at] = t2;
-                        if (nbr[off[t2]] == nbr[off[t]]) {
+                        if (cpar[t2] == cpar[t]) {
                             top[at++] = kTailFall;
                         } else {
                             top[first_at] = kTailPairA;
@@ -354,6 +371,27 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
             for (u32 k = 0; k < n_peel; k++) make_table(peel[k]);
             for (u32 u = 0; u < nq; u++)
                 if (alive >> u & 1) make_table(u);
+            // weighted counted leaves: S_u over the pivot's label class, S_u[x] = sum over y in N(x) of u's label and
+            // degree of N_u[y] -- the table of a job whose only child is u (second half of the job / child arrays)
+            u64 stab[kMaxNQ];
+            for (u32 k = 0; k < n_tail; k++) {
+                const u32 u = tail_list[k];
+                stab[u] = 0;
+                if (!(weighted >> u & 1)) continue;
+                const u32 pv = cpar[u], ji = sjob_base + vb + u;
+                tchild[ji] = vb + u;
+                TreeJob &sj = tjobs[ji];
+                sj.child_begin = ji;
+                sj.n_child = 1;
+                sj.level = tlevel[u] + 1;
+                sj.label = qlab[pv];
+                sj.qdeg = qdeg(pv);
+                sj.start_slot = 0xffffffffu;
+                const u32 sz = qlab[pv] < n_labels ? lcoff[qlab[pv] + 1] - lcoff[qlab[pv]] : 0;
+                sj.table_off = atomicAdd((unsigned long long *)tcursor, (unsigned long long)sz);
+                tlist[(u64)sj.level * n_slots + atomicAdd(&tcount[sj.level], 1u)] = ji;
+                stab[u] = sj.table_off;
+            }
             for (u32 u = 0; u < nq; u++) depth_of[u] = 0xffffffffu;
             for (u32 i = 0; i < n_exec; i++) { depth_of[xo[i]] = i; lab[i] = qlab[xo[i]]; }
             for (u32 i = 0; i < n_exec; i++) {
@@ -392,13 +430,19 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                     jd.tail_mask = sm;
                 }
                 if (i >= n_walk) {
-                    jd.tail_k = top[i];
+                    const bool wu = weighted >> u & 1;
+                    jd.tail_k = top[i] | (wu ? kTailW : 0u);
                     const u32 pvu = xo[jd.pivot_depth];
+                    u64 sure_mask = 0;
                     for (u32 t = 0; t < n_walk; t++) {
                         if (t == jd.pivot_depth) continue;
                         if (t == 0 && root_is_start && !clean_start) { jd.tail_mask |= 1ull; continue; }  // its data label is only known at run time
                         if (lab[t] != jd.label) continue;
-                        if (q_edge(off, nbr, xo[t], pvu)) jd.sure_used++; else jd.tail_mask |= 1ull << t;
+                        if (q_edge(off, nbr, xo[t], pvu)) { jd.sure_used++; sure_mask |= 1ull << t; } else jd.tail_mask |= 1ull << t;
+                    }
+                    if (wu) {  // (a core leaf has no backward neighbour besides its pivot: both words are free)
+                        jd.bn_mask = sure_mask;   // WHICH prefix vertices surely sit in the group: their weights are subtracted
+                        jd.units_mask = stab[u];  // table S_u (pool offset)
                     }
                 }
                 jplan[vb + i] = jd;
@@ -423,9 +467,14 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 auto msb = [](u64 m) { u32 r = 0; while (m >>= 1) r++; return r; };
                 u32 dep = jplan[vb + i].pivot_depth;
                 if (jplan[vb + i].tail_mask) dep = max(dep, msb(jplan[vb + i].tail_mask));
+                // (a weighted leaf subtracts the weights of the prefix vertices that surely sit in its group: they must
+                //  be matched by then; a plain leaf only counts them)
+                if ((jplan[vb + i].tail_k & kTailW) && jplan[vb + i].bn_mask) dep = max(dep, msb(jplan[vb + i].bn_mask));
                 if (op == kTailPairA) {
                     dep = max(dep, jplan[vb + i + 1].pivot_depth);
                     if (jplan[vb + i + 1].tail_mask) dep = max(dep, msb(jplan[vb + i + 1].tail_mask));
+                    if ((jplan[vb + i + 1].tail_k & kTailW) && jplan[vb + i + 1].bn_mask)
+                        dep = max(dep, msb(jplan[vb + i + 1].bn_mask));
                     for (u32 t = 1; t < n_walk; t++)
                         if (lab[t] == lab[i]) dep = max(dep, t);  // its vertex may sit in both groups
                 }
@@ -1060,20 +1109,47 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 for (u32 i = tail_at; um && p; i++, um >>= 1) {
                     if (!(um & 1)) continue;
                     const JoinDepth *ld = jplan + vb + i;
-                    // free members of leaf i's group: its size minus the prefix vertices inside it
-                    u32 s = S0(i), e = E0(i), used = ld->sure_used;
-                    {
-                        const u32 llab = ld->label;
-                        const u32 pvx = EMB(ld->pivot_depth);
-                        u64 m = ld->tail_mask;
-                        for (u32 t = 0; m; t++, m >>= 1)
-                            if ((m & 1) && (t != 0 || lab0 == llab) && (cgl ? edge_maybe<true>(g, pvx, EMB(t)) : edge_maybe<false>(g, pvx, EMB(t))) && in_group(g, s, e, EMB(t))) used++;
-                    }
-                    const u32 n_free = (e - s) - used;
-                    if (ld->tail_k == kTailMul) {
+                    // (weighted) number of free members of a counted leaf's group: its size minus the prefix vertices inside
+                    // it -- or, for a leaf that carries peeled subtrees, S_u[pivot] minus the N_u of those prefix vertices
+                    auto leaf_free = [&](const JoinDepth *lf, u32 s, u32 e) -> u64 {
+                        const u32 llab = lf->label, pvx = EMB(lf->pivot_depth);
+                        if (!(lf->tail_k & kTailW)) {
+                            u32 used = lf->sure_used;
+                            u64 m = lf->tail_mask;
+                            for (u32 t = 0; m; t++, m >>= 1)
+                                if ((m & 1) && (t != 0 || lab0 == llab) &&
+                                    (cgl ? edge_maybe<true>(g, pvx, EMB(t)) : edge_maybe<false>(g, pvx, EMB(t))) &&
+                                    in_group(g, s, e, EMB(t))) used++;
+                            return (u64)((e - s) - used);
+                        }
+                        u64 wsum = __ldcg(g.tpool + lf->units_mask + __ldcg(g.lpos + pvx));
+                        const u64 sure = lf->bn_mask;
+                        u64 m = lf->tail_mask | sure;
+                        for (u32 t = 0; m; t++, m >>= 1) {
+                            if (!(m & 1)) continue;
+                            const u32 y = EMB(t);
+                            const bool in = (sure >> t & 1) ||
+                                            ((t != 0 || lab0 == llab) &&
+                                             (cgl ? edge_maybe<true>(g, pvx, y) : edge_maybe<false>(g, pvx, y)) && in_group(g, s, e, y));
+                            if (in && g.deg[y] >= lf->deg)
+                                wsum -= lf->tree_off != kNoTree ? __ldcg(g.tpool + lf->tree_off + __ldcg(g.lpos + y)) : 1ull;
+                        }
+                        return wsum;
+                    };
+                    // weight of one group member (entry of nbrL) as image of a counted leaf
+                    auto leaf_weight = [&](const JoinDepth *lf, uint2 ent) -> u64 {
+                        if (!(lf->tail_k & kTailW)) return 1ull;
+                        const u32 dg = g.packed ? ent.y & 255u : ent.y;
+                        if (dg < lf->deg) return 0ull;
+                        if (lf->tree_off == kNoTree) return 1ull;
+                        return __ldcg(g.tpool + lf->tree_off + (g.packed ? ent.y >> 8 : __ldcg(g.lpos + ent.x)));
+                    };
+                    const u32 s = S0(i), e = E0(i);
+                    const u64 n_free = leaf_free(ld, s, e);
+                    if ((ld->tail_k & 0xffu) == kTailMul) {
                         u64 f = n_free;
-                        u32 n_run = n_free;
-                        for (u32 k = i + 1; k < nq && jplan[vb + k].tail_k == kTailFall; k++) {
+                        u64 n_run = n_free;  // (followers are plain leaves on the same pivot: falling factorial)
+                        for (u32 k = i + 1; k < nq && (jplan[vb + k].tail_k & 0xffu) == kTailFall; k++) {
                             n_run = n_run ? n_run - 1 : 0;
                             f *= n_run;
                         }
@@ -1081,34 +1157,26 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                     } else {  // kTailPairA: leaf i and leaf i+1, same label, different pivots
                         const JoinDepth *lb = ld + 1;
                         const u32 s2 = S0(i + 1), e2 = E0(i + 1);
-                        u32 used2 = lb->sure_used;
-                        {
-                            const u32 llab = lb->label;
-                            const u32 pvx = EMB(lb->pivot_depth);
-                            u64 m = lb->tail_mask;
-                            for (u32 t = 0; m; t++, m >>= 1)
-                                if ((m & 1) && (t != 0 || lab0 == llab) && (cgl ? edge_maybe<true>(g, pvx, EMB(t)) : edge_maybe<false>(g, pvx, EMB(t))) && in_group(g, s2, e2, EMB(t))) used2++;
-                        }
-                        const u32 n_free2 = (e2 - s2) - used2;
-                        // ordered pairs of distinct vertices: |A||B| - |A n B| over the free members; the groups are
-                        // ascending id lists, so the intersection is a merge
+                        const u64 n_free2 = leaf_free(lb, s2, e2);
+                        // ordered pairs of distinct vertices: W(A) W(B) - sum over the free members of both groups of
+                        // wA wB; the groups are ascending id lists, so the intersection is a merge
                         u64 inter = 0;
                         u32 x = s, y = s2;
                         while (x < e && y < e2) {
-                            const u32 vx = __ldcg(&g.nbrL[x].x), vy = __ldcg(&g.nbrL[y].x);
-                            if (vx == vy) {
+                            const uint2 ex = g.nbrL[x], ey = g.nbrL[y];
+                            if (ex.x == ey.x) {
                                 bool is_used = false;
-                                for (u32 t = 0; t <= d; t++) is_used = is_used || EMB(t) == vx;
-                                inter += is_used ? 0 : 1;
+                                for (u32 t = 0; t <= d; t++) is_used = is_used || EMB(t) == ex.x;
+                                if (!is_used) inter += leaf_weight(ld, ex) * leaf_weight(lb, ey);
                                 x++;
                                 y++;
-                            } else if (vx < vy) {
+                            } else if (ex.x < ey.x) {
                                 x++;
                             } else {
                                 y++;
                             }
                         }
-                        p *= (u64)n_free * n_free2 - inter;
+                        p *= n_free * n_free2 - inter;
                     }
                 }
                 fin_p = p;
@@ -1544,10 +1612,13 @@ cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebas
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
                      JoinDepth *jplan, void *kids, u64 *item_base, u32 rank, u32 world, bool enumerate, bool clean_start,
                      u32 n_labels, const u32 *lcoff, TreeJob *tjobs, u32 *tchild, u64 *tcursor, u32 *tcount, u32 *tlist,
-                     u32 n_slots, cudaStream_t s) {
+                     u32 n_slots, bool allow_weighted, cudaStream_t s) {
+    // jobs / child lists / per-level job lists hold 2 x n_slots entries: [0, n_slots) the tables N_v of vertices with
+    // peeled children, [n_slots, 2 n_slots) the tables S_u of weighted counted leaves
     k3_order_kernel<<<1, 256, 0, s>>>(n_queries, V, q_vbase, q_ebase, q_offsets, q_nbrs, q_labels, cand_off, order,
                                       pivot, jplan, reinterpret_cast<uint2 *>(kids), item_base, rank, world, 1, enumerate,
-                                      clean_start, n_labels, lcoff, tjobs, tchild, tcursor, tcount, tlist, n_slots);
+                                      clean_start, n_labels, lcoff, tjobs, tchild, tcursor, tcount, tlist, 2 * n_slots,
+                                      n_slots, allow_weighted);
     return cudaGetLastError();
 }
 
@@ -1585,7 +1656,7 @@ cudaError_t k3_tree_tables(const JoinView &jv, u32 n_slots, u32 max_class, u32 m
     const u32 gx = std::max<u32>(1, std::min<u32>((max_class + 255) / 256, 64));
     dim3 grid(gx, gy);
     for (u32 level = 1; level <= max_level; level++)
-        k3_tree_tables_kernel<<<grid, 256, 0, s>>>(g, tjobs, tchild, level, tcount, tlist, n_slots, bitmap,
+        k3_tree_tables_kernel<<<grid, 256, 0, s>>>(g, tjobs, tchild, level, tcount, tlist, 2 * n_slots /*list stride*/, bitmap,
                                                    words_per_slot, tpool);
     return cudaGetLastError();
 }
