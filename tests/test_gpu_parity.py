@@ -378,6 +378,12 @@ _TAIL_SHAPES = {
     "caterpillar": ([(0, 1), (1, 2), (2, 3), (0, 4), (1, 5), (2, 6), (3, 7)], [0, 1, 2, 0, 1, 2, 0, 1]),
     "leaf_label_equals_pivot_neighbour": ([(0, 1), (1, 2), (1, 3), (3, 4)], [0, 1, 2, 2, 0]),
     "edge_plus_leaf": ([(0, 1), (1, 2)], [0, 1, 0]),
+    # core ends with a repeated label that carry pendant subtrees of query-unique labels: counted with weights
+    # (one such end; a pair on two pivots; an end whose label also sits on a walked vertex next to / away from its pivot)
+    "weighted_end": ([(0, 1), (1, 2), (2, 3), (3, 4), (0, 5), (5, 6)], [0, 1, 2, 3, 0, 4, 5]),
+    "weighted_pair": ([(0, 1), (1, 2), (2, 3), (0, 4), (3, 5), (5, 6)], [0, 1, 2, 0, 3, 4, 5]),
+    "weighted_end_label_on_walk": ([(0, 1), (1, 2), (2, 3), (1, 4), (4, 5), (3, 6)], [0, 1, 0, 2, 0, 3, 4]),
+    "weighted_three": ([(0, 1), (1, 2), (2, 3), (3, 4), (0, 5), (4, 6), (2, 7)], [0, 1, 0, 2, 0, 3, 4, 5]),
 }
 
 

@@ -1,11 +1,13 @@
-"""Round-2 groundwork (analysis only, CPU): for config 2's queries with exactly ONE repeated label pair, compare
+"""Analysis only (CPU, numpy/scipy; not product code).  Round-2 groundwork: for config 2's queries with exactly ONE repeated label pair, compare
   walk  = partial label-paths a depth-first walk of the core path enumerates (both orientations, the cheaper one), with
   mitm  = half-length label-walks from both same-label endpoints (what meeting in the middle would enumerate to count
           the CLOSED walks that inclusion-exclusion subtracts from the table product).
 Degree filters and subtree-table pruning are ignored on both sides (upper bounds on both)."""
 import sys, pickle, re
 import numpy as np, scipy.sparse as sp
-sys.path.insert(0, '/root/repo')
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import bench
 from collections import Counter
 
@@ -39,7 +41,7 @@ def tree_path(q, a, b):
     return p[::-1]
 
 steps = {}
-for line in open('/root/repo/profiles/r01j_joinstats_config2.log'):
+for line in open(os.path.join(ROOT, 'profiles', 'r01j_joinstats_config2.log')):
     m = re.match(r'q(\d+) nq=(\d+) ne=(\d+): .*steps=(\d+) ', line)
     if m: steps[int(m[1])] = int(m[4])
 tot_walk = tot_mitm = tot_meas = 0
