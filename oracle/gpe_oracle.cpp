@@ -10,6 +10,9 @@
 // committed under tests/golden/ together with tests/golden/make_golden.py.
 // The only unpinned piece is the METIS partition assignment (pymetis is absent here);
 // path tables, candidate sets and answers do not depend on it.
+// The GNN-PGE section (orc_pge_*, citations relative to /root/reference/GNN-PGE/) is pinned the same
+// way: oracle/_ref/pge_main, oracle/_ref/pge_probe, tests/golden/make_golden_pge.py,
+// tests/test_oracle_pge.py.
 //
 // All file:line citations are relative to /root/reference/GNN-PE/.
 // Flat arrays, no classes from the reference, nothing copied: each routine restates
@@ -451,6 +454,80 @@ u64 enumerate_matches(const OGraph &g, const OGraph &q, const u32 *order, const 
     return found;
 }
 
+// ---------------------------------------------------------------------------------------
+// GNN-PGE (the reference's sibling variant; citations relative to the
+// reference's GNN-PGE/ directory).  Per-VERTEX filter: every vertex carries the bounding box of the
+// embeddings of all simple paths of `pl` vertices that start at it ("path group", src/main.cpp:91-176
+// for the data graph, :226-291 for the query), over the dominance embeddings (pg) and over the label
+// embeddings (plg); both as [lo0, hi0, lo1, hi1, ...] with pde = e * pl dimensions.
+// ---------------------------------------------------------------------------------------
+static void pge_walk(const OGraph &g, u32 pl, u32 e, const double *x, const double *vde, u32 *path, u32 len,
+                     double *pg, double *plg, bool &first) {
+    if (len == pl) {  // include/custom.h:52-57 + the min/max folds of main.cpp:145-176
+        for (u32 j = 0; j < pl; j++)
+            for (u32 k = 0; k < e; k++) {
+                const double a = vde[(size_t)path[j] * e + k], b = x[(size_t)path[j] * e + k];
+                const u32 d = j * e + k;
+                if (first) { pg[2 * d] = pg[2 * d + 1] = a; plg[2 * d] = plg[2 * d + 1] = b; }
+                else {
+                    if (pg[2 * d] > a) pg[2 * d] = a;
+                    if (pg[2 * d + 1] < a) pg[2 * d + 1] = a;
+                    if (plg[2 * d] > b) plg[2 * d] = b;
+                    if (plg[2 * d + 1] < b) plg[2 * d + 1] = b;
+                }
+            }
+        first = false;
+        return;
+    }
+    const u32 node = path[len - 1];
+    for (u32 j = g.off[node]; j < g.off[node + 1]; j++) {  // include/custom.h:59-70: simple paths only
+        const u32 nb = g.nbr[j];
+        bool seen = false;
+        for (u32 t = 0; t < len; t++) seen = seen || path[t] == nb;
+        if (seen) continue;
+        path[len] = nb;
+        pge_walk(g, pl, e, x, vde, path, len + 1, pg, plg, first);
+    }
+}
+
+// has[v] = 0 for a vertex without any such path: the data side then stores [vde, vde | 0 ...] and
+// [x, x | 0 ...] (main.cpp:103-121); the query side leaves the group empty (main.cpp:249-252)
+static void pge_groups(const OGraph &g, u32 pl, u32 e, const double *x, const double *vde, double *pg, double *plg,
+                       unsigned char *has) {
+    const u32 pde = pl * e;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long vv = 0; vv < (long long)g.V; vv++) {
+        const u32 v = (u32)vv;
+        u32 path[64];
+        double *a = pg + (size_t)v * 2 * pde, *b = plg + (size_t)v * 2 * pde;
+        bool first = true;
+        path[0] = v;
+        pge_walk(g, pl, e, x, vde, path, 1, a, b, first);
+        has[v] = first ? 0 : 1;
+        if (first) {
+            for (u32 d = 0; d < pde; d++) {
+                const double va = d < e ? vde[(size_t)v * e + d] : 0.0, vb = d < e ? x[(size_t)v * e + d] : 0.0;
+                a[2 * d] = a[2 * d + 1] = va;
+                b[2 * d] = b[2 * d + 1] = vb;
+            }
+        }
+    }
+}
+
+// The leaf test of Partition::query, include/custom.h:332-367: label equal, query degree <= data degree,
+// (the per-vertex embedding loop at :339-346 is dead: it starts at k = vde_dim), the label boxes overlap in
+// every dimension, and the data box's upper corner is not below the query box's lower corner in any
+// dimension (no epsilon here; the epsilon of :395 only routes inside the R*-tree).
+static inline bool pge_leaf_test(u32 pde, u32 qlabel, u32 qdeg, const double *qpg, const double *qplg, u32 vlabel,
+                                 u32 vdeg, const double *vpg, const double *vplg) {
+    if (!(qdeg <= vdeg && qlabel == vlabel)) return false;
+    for (u32 k = 0; k < pde; k++)
+        if (vplg[2 * k + 1] < qplg[2 * k] || vplg[2 * k] > qplg[2 * k + 1]) return false;
+    for (u32 k = 0; k < pde; k++)
+        if (vpg[2 * k + 1] < qpg[2 * k]) return false;
+    return true;
+}
+
 struct Handle {
     OGraph g;
     std::vector<u32> rows;       // enumerated path table, row-major n x L
@@ -688,6 +765,53 @@ u64 orc_online_streaming(void *gv, void *qv, u32 L, u32 e, const u32 *sorted_nod
 #endif
     if (t3) { t3[0] = t1 - t0; t3[1] = t2 - t1; t3[2] = t3e - t2; }
     return n;
+}
+
+
+// ---- GNN-PGE ------------------------------------------------------------------------------------------
+// pg, plg: V x 2*pl*e; has: V
+void orc_pge_groups(void *hv, u32 pl, u32 e, double *pg, double *plg, unsigned char *has) {
+    OGraph &g = ((Handle *)hv)->g;
+    std::vector<double> x((size_t)g.V * e), vde((size_t)g.V * e);
+    vertex_embeddings(g, e, x.data(), vde.data());
+    pge_groups(g, pl, e, x.data(), vde.data(), pg, plg, has);
+}
+
+// Candidate sets of every query vertex (ascending ids, like the std::set merge of main.cpp:331-338): all data
+// vertices that pass the leaf test.  Two-call pattern: cand == NULL returns the sizes in cand_off only.
+u64 orc_pge_filter(void *gv, void *qv, u32 pl, u32 e, u64 *cand_off, u32 *cand, u64 cand_cap) {
+    OGraph &g = ((Handle *)gv)->g;
+    OGraph &q = ((Handle *)qv)->g;
+    const u32 pde = pl * e;
+    std::vector<double> gpg((size_t)g.V * 2 * pde), gplg((size_t)g.V * 2 * pde), qpg((size_t)q.V * 2 * pde),
+        qplg((size_t)q.V * 2 * pde);
+    std::vector<unsigned char> ghas(g.V), qhas(q.V);
+    orc_pge_groups(gv, pl, e, gpg.data(), gplg.data(), ghas.data());
+    orc_pge_groups(qv, pl, e, qpg.data(), qplg.data(), qhas.data());
+    u64 total = 0;
+    for (u32 u = 0; u < q.V; u++) {
+        cand_off[u] = total;
+        if (!qhas[u]) continue;  // (the reference would read an empty vector here: undefined; connected queries of
+                                 //  at least pl vertices per path always have a group)
+        for (u32 v = 0; v < g.V; v++)
+            if (pge_leaf_test(pde, q.label[u], q.deg(u), &qpg[(size_t)u * 2 * pde], &qplg[(size_t)u * 2 * pde], g.label[v],
+                              g.deg(v), &gpg[(size_t)v * 2 * pde], &gplg[(size_t)v * 2 * pde])) {
+                if (cand && total < cand_cap) cand[total] = v;
+                total++;
+            }
+    }
+    cand_off[q.V] = total;
+    return total;
+}
+
+// filter + the (shared) refinement: the number the reference prints as "Answer Num" (main.cpp:343-346)
+u64 orc_pge_online(void *gv, void *qv, u32 pl, u32 e, u64 limit) {
+    OGraph &q = ((Handle *)qv)->g;
+    std::vector<u64> off(q.V + 1);
+    const u64 total = orc_pge_filter(gv, qv, pl, e, off.data(), nullptr, 0);
+    std::vector<u32> cand(total ? total : 1);
+    orc_pge_filter(gv, qv, pl, e, off.data(), cand.data(), total);
+    return orc_refine(gv, qv, off.data(), cand.data(), limit, nullptr, 0);
 }
 
 }  // extern "C"

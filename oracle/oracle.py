@@ -57,6 +57,11 @@ def lib():
         L.orc_matching_order.argtypes = [C.c_void_p, C.c_void_p, _u32p, _u32p, _u32p]
         L.orc_refine.restype = C.c_uint64
         L.orc_refine.argtypes = [C.c_void_p, C.c_void_p, _u64p, _u32p, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.orc_pge_groups.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, _f64p, _f64p, C.c_void_p]
+        L.orc_pge_filter.restype = C.c_uint64
+        L.orc_pge_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, _u64p, C.c_void_p, C.c_uint64]
+        L.orc_pge_online.restype = C.c_uint64
+        L.orc_pge_online.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64]
         L.orc_online.restype = C.c_uint64
         L.orc_online.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]
         L.orc_online_streaming.restype = C.c_uint64
@@ -207,3 +212,27 @@ def online_streaming(g: OracleGraph, q: OracleGraph, L: int, e: int, sorted_node
     n = int(lib().orc_online_streaming(g._h, q._h, L, e, np.ascontiguousarray(sorted_nodes, dtype=np.uint32),
                                        np.ascontiguousarray(vde, dtype=np.float64), limit, t3, threads))
     return n, t3
+
+
+# ---- GNN-PGE (the reference's per-vertex variant) ----------------------------------------
+def pge_groups(g: OracleGraph, pl: int, e: int):
+    """Path groups of every vertex: (pg, plg) as V x 2*pl*e arrays [lo0, hi0, lo1, hi1, ...] and has[V]."""
+    V = g.V
+    pg = np.zeros((max(V, 1), 2 * pl * e), dtype=np.float64)
+    plg = np.zeros((max(V, 1), 2 * pl * e), dtype=np.float64)
+    has = np.zeros(max(V, 1), dtype=np.uint8)
+    lib().orc_pge_groups(g._h, pl, e, pg, plg, has.ctypes.data_as(C.c_void_p))
+    return pg[:V], plg[:V], has[:V]
+
+
+def pge_filter(g: OracleGraph, q: OracleGraph, pl: int, e: int):
+    """Candidate set of every query vertex under GNN-PGE's leaf test (sorted ids)."""
+    off = np.zeros(q.V + 1, dtype=np.uint64)
+    total = int(lib().orc_pge_filter(g._h, q._h, pl, e, off, None, 0))
+    cand = np.zeros(max(total, 1), dtype=np.uint32)
+    lib().orc_pge_filter(g._h, q._h, pl, e, off, cand.ctypes.data_as(C.c_void_p), total)
+    return [cand[int(off[u]): int(off[u + 1])].copy() for u in range(q.V)]
+
+
+def pge_online(g: OracleGraph, q: OracleGraph, pl: int, e: int, limit: int = UINT_MAX) -> int:
+    return int(lib().orc_pge_online(g._h, q._h, pl, e, limit))
