@@ -1020,6 +1020,7 @@ int gpe_batch_upload(gpe_ctx *c, const gpe_batch *b, uint32_t flags) {
     }
     int rc = upload_queries(c, b->n_queries, b->q_vbase, b->q_ebase, b->q_offsets, b->q_nbrs, b->q_labels, b->limits);
     if (rc) return rc;
+    c->b_pge = false;
     return setup_filter(c, qp, b->q_vbase[b->n_queries], flags);
 }
 
@@ -1171,6 +1172,169 @@ int gpe_batch_get_plan(gpe_ctx *c, uint32_t *order, uint32_t *pivot) {
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
     if (order) GPE_CUDA(c, cudaMemcpy(order, c->d_order.p, (size_t)c->b_slots * sizeof(u32), cudaMemcpyDeviceToHost));
     if (pivot) GPE_CUDA(c, cudaMemcpy(pivot, c->d_pivot.p, (size_t)c->b_slots * sizeof(u32), cudaMemcpyDeviceToHost));
+    return GPE_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// GNN-PGE variant of seam S2 (see k4_pge.cu for its status).  Shares candidate bitmaps, compaction, matching order and
+// join with the path filter; only the table (one row per data vertex) and the scan differ.
+int gpe_pge_build(gpe_ctx *c, uint32_t pl, const double *x) {
+    if (!c || !x) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
+    if (!c->have_graph || !c->have_emb) return c->fail(GPE_ERR_INVALID, "gpe_set_graph and gpe_set_embeddings first");
+    if (pl < 1 || pl > (u32)kMaxL) return c->fail(GPE_ERR_UNSUPPORTED, "GNN-PGE path groups are built for 1..%d vertices per path", kMaxL);
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    const u32 pde = pl * c->e;
+    GPE_CUDA(c, c->d_pge_x.reserve(std::max<size_t>((size_t)c->V * c->e, 1) * sizeof(double)));
+    GPE_CUDA(c, c->d_pge.reserve(k4_pge_bytes(c->V, pde)));
+    if (c->V) GPE_CUDA(c, cudaMemcpyAsync(c->d_pge_x.p, x, (size_t)c->V * c->e * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, k4_pge_groups(graph_view(c), pl, c->d_pge_x.as<double>(), k4_pge_view(c->d_pge.p, c->V, pde), c->sm_count, c->stream));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stats.kernel_launches++;
+    c->pge_pl = pl;
+    c->have_pge = true;
+    return GPE_OK;
+}
+
+int gpe_pge_dump_groups(gpe_ctx *c, double *pg, double *plg, uint8_t *has) {
+    if (!c || !pg || !plg || !has) return GPE_ERR_INVALID;
+    if (!c->have_pge) return c->fail(GPE_ERR_INVALID, "gpe_pge_build first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    const u32 pde = c->pge_pl * c->e;
+    DevBuf a, b, h;
+    GPE_CUDA(c, a.reserve(std::max<size_t>((size_t)c->V * pde * 2, 1) * sizeof(double)));
+    GPE_CUDA(c, b.reserve(std::max<size_t>((size_t)c->V * pde * 2, 1) * sizeof(double)));
+    GPE_CUDA(c, h.reserve(std::max<size_t>(c->V, 1)));
+    cudaError_t e = k4_pge_dump(k4_pge_view(c->d_pge.p, c->V, pde), graph_view(c), pde, a.as<double>(), b.as<double>(),
+                                h.as<unsigned char>(), c->stream);
+    if (e == cudaSuccess && c->V) e = cudaMemcpyAsync(pg, a.p, (size_t)c->V * pde * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && c->V) e = cudaMemcpyAsync(plg, b.p, (size_t)c->V * pde * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && c->V) e = cudaMemcpyAsync(has, h.p, c->V, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    a.release(); b.release(); h.release();
+    GPE_CUDA(c, e);
+    return GPE_OK;
+}
+
+int gpe_pge_batch_upload(gpe_ctx *c, const gpe_batch *b) {
+    if (!c || !b || !b->q_vbase || !b->q_ebase || !b->q_offsets || !b->q_labels) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
+    if (!c->have_pge) return c->fail(GPE_ERR_INVALID, "gpe_pge_build first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    const u32 E = c->e, pl = c->pge_pl, pde = pl * E, n_slots = b->q_vbase[b->n_queries], nl = c->n_labels;
+    std::string why;
+    for (u32 q = 0; q < b->n_queries; q++) {
+        const u32 vb = b->q_vbase[q], nq = b->q_vbase[q + 1] - vb;
+        if (!check_query(c, nq, b->q_offsets + vb + q, b->q_nbrs + b->q_ebase[q], why))
+            return c->fail(GPE_ERR_INVALID, "query %u: %s", q, why.c_str());
+    }
+    // query records: the reference computes them inline per query (GNN-PGE/src/main.cpp:226-297)
+    c->label_table.fill(b->q_labels, n_slots, E);
+    std::vector<u32> q_deg(std::max<u32>(n_slots, 1)), slot_label(std::max<u32>(n_slots, 1), 0xffffffffu);
+    std::vector<double> q_pg_lo((size_t)std::max<u32>(n_slots, 1) * pde), q_plg_lo(q_pg_lo.size()), q_plg_hi(q_pg_lo.size());
+    std::vector<unsigned char> q_has(std::max<u32>(n_slots, 1), 0);
+    for (u32 q = 0; q < b->n_queries; q++) {
+        const u32 vb = b->q_vbase[q], nq = b->q_vbase[q + 1] - vb;
+        const u32 *off = b->q_offsets + vb + q, *nbr = b->q_nbrs + b->q_ebase[q], *lab = b->q_labels + vb;
+        std::vector<double> x((size_t)nq * E), vde((size_t)nq * E), pg((size_t)nq * 2 * pde), plg((size_t)nq * 2 * pde);
+        std::vector<unsigned char> has(nq);
+        gen_vde(nq, off, nbr, lab, E, x.data(), vde.data(), &c->label_table);
+        pge_groups(nq, off, nbr, pl, E, x.data(), vde.data(), pg.data(), plg.data(), has.data());
+        for (u32 u = 0; u < nq; u++) {
+            q_deg[vb + u] = off[u + 1] - off[u];
+            slot_label[vb + u] = lab[u];
+            q_has[vb + u] = has[u];
+            for (u32 d = 0; d < pde; d++) {
+                q_pg_lo[(size_t)(vb + u) * pde + d] = pg[((size_t)u * pde + d) * 2];
+                q_plg_lo[(size_t)(vb + u) * pde + d] = plg[((size_t)u * pde + d) * 2];
+                q_plg_hi[(size_t)(vb + u) * pde + d] = plg[((size_t)u * pde + d) * 2 + 1];
+            }
+        }
+    }
+    // slots grouped by label; a query vertex without a path group gets no candidates
+    std::vector<u32> ls_off((size_t)nl + 2, 0), slot_list(std::max<u32>(n_slots, 1));
+    for (u32 s2 = 0; s2 < n_slots; s2++)
+        if (q_has[s2] && slot_label[s2] < nl) ls_off[slot_label[s2] + 1]++;
+    for (u32 l = 0; l < nl; l++) ls_off[l + 1] += ls_off[l];
+    {
+        std::vector<u32> at(ls_off.begin(), ls_off.begin() + nl);
+        for (u32 s2 = 0; s2 < n_slots; s2++)
+            if (q_has[s2] && slot_label[s2] < nl) slot_list[at[slot_label[s2]]++] = s2;
+    }
+    int rc = upload_queries(c, b->n_queries, b->q_vbase, b->q_ebase, b->q_offsets, b->q_nbrs, b->q_labels, b->limits);
+    if (rc) return rc;
+    c->b_flags = 0;
+    c->b_slots = n_slots;
+    c->b_qpaths = 0;
+    c->b_qblocks = 0;
+    c->b_items_unpruned = 0;
+    c->b_words = ((u64)(c->max_class + 31) / 32 + kChunkWords - 1) / kChunkWords * kChunkWords;
+    if (c->b_words == 0) c->b_words = kChunkWords;
+    c->b_chunks_per_slot = c->b_words / kChunkWords;
+    // one device block: q_deg | slot_label | ls_off | slot_list | q_pg_lo | q_plg_lo | q_plg_hi
+    const size_t n1 = std::max<u32>(n_slots, 1);
+    const size_t o_deg = 0, o_lab = o_deg + n1 * 4, o_off = o_lab + n1 * 4, o_list = o_off + ((size_t)nl + 2) * 4;
+    const size_t o_d0 = (o_list + n1 * 4 + 15) / 16 * 16, dsz = n1 * pde * sizeof(double);
+    GPE_CUDA(c, c->d_pge_q.reserve(o_d0 + 3 * dsz));
+    unsigned char *base = c->d_pge_q.as<unsigned char>();
+    GPE_CUDA(c, cudaMemcpyAsync(base + o_deg, q_deg.data(), n1 * 4, cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(base + o_lab, slot_label.data(), n1 * 4, cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(base + o_off, ls_off.data(), ((size_t)nl + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(base + o_list, slot_list.data(), n1 * 4, cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(base + o_d0, q_pg_lo.data(), dsz, cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(base + o_d0 + dsz, q_plg_lo.data(), dsz, cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(base + o_d0 + 2 * dsz, q_plg_hi.data(), dsz, cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, c->d_slot_label.reserve(n1 * sizeof(u32)));
+    GPE_CUDA(c, cudaMemcpyAsync(c->d_slot_label.p, slot_label.data(), n1 * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, c->d_bitmap.reserve(std::max<u64>((u64)n_slots * c->b_words, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_counters.reserve(8 * sizeof(u64)));
+    GPE_CUDA(c, c->d_survivors.reserve(8 * sizeof(u64)));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));  // the staging vectors go out of scope
+    c->stats.h2d_bytes += o_d0 + 3 * dsz;
+    c->b_scanned = c->b_filtered = c->b_joined = false;
+    c->b_pge = true;
+    c->stats.n_slots = n_slots;
+    return GPE_OK;
+}
+
+int gpe_pge_batch_filter(gpe_ctx *c) {
+    if (!c) return GPE_ERR_INVALID;
+    if (!c->have_pge || !c->b_pge) return c->fail(GPE_ERR_INVALID, "gpe_pge_batch_upload first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    const u32 pde = c->pge_pl * c->e, nl = c->n_labels;
+    const size_t n1 = std::max<u32>(c->b_slots, 1);
+    const size_t o_deg = 0, o_lab = o_deg + n1 * 4, o_off = o_lab + n1 * 4, o_list = o_off + ((size_t)nl + 2) * 4;
+    const size_t o_d0 = (o_list + n1 * 4 + 15) / 16 * 16, dsz = n1 * pde * sizeof(double);
+    unsigned char *base = c->d_pge_q.as<unsigned char>();
+    GPE_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(u64), c->stream));
+    GPE_CUDA(c, cudaMemsetAsync(c->d_survivors.p, 0, 8 * sizeof(u64), c->stream));
+    GPE_CUDA(c, cudaMemsetAsync(c->d_bitmap.p, 0, std::max<u64>((u64)c->b_slots * c->b_words, 1) * sizeof(u32), c->stream));
+    {
+        StageTimer tm(c, &c->stats.last_scan_ms, kStageScan);
+        GPE_CUDA(c, k4_pge_scan(k4_pge_view(c->d_pge.p, c->V, pde), c->V, pde, nl, c->d_lcoff.as<u32>(),
+                                reinterpret_cast<const u32 *>(base + o_off), reinterpret_cast<const u32 *>(base + o_list),
+                                reinterpret_cast<const u32 *>(base + o_deg), reinterpret_cast<const double *>(base + o_d0),
+                                reinterpret_cast<const double *>(base + o_d0 + dsz),
+                                reinterpret_cast<const double *>(base + o_d0 + 2 * dsz), c->d_bitmap.as<u32>(), c->b_words,
+                                c->d_survivors.as<u64>(), c->sm_count, c->stream));
+        c->stats.scan_launches++;
+        c->stats.kernel_launches++;
+    }
+    int rc = compact_candidates(c);
+    if (rc) return rc;
+    c->b_filtered = true;
+    c->b_cand_external = false;
+    c->b_cand_clean = true;  // label equal and degree >= hold for every candidate; the bitmaps are on the device
+    return GPE_OK;
+}
+
+int gpe_pge_query_batch(gpe_ctx *c, const gpe_batch *b, uint64_t *answers) {
+    if (!c || !answers) return GPE_ERR_INVALID;
+    int rc = gpe_pge_batch_upload(c, b);
+    if (rc) return rc;
+    if ((rc = gpe_pge_batch_filter(c))) return rc;
+    if ((rc = run_join(c, 0, 1, nullptr, 0))) return rc;
+    if ((rc = gpe_batch_download(c, answers))) return rc;
+    for (u32 q = 0; q < b->n_queries; q++) answers[q] = gpe_clamp_answer(answers[q], c->h_limits[q]);
     return GPE_OK;
 }
 

@@ -196,6 +196,9 @@ struct gpe_ctx {
     bool lpos_packed = false;
     gpe::DevBuf d_bloom;  // edge filter of the join
     u64 bloom_bits = 0;
+    gpe::DevBuf d_pge, d_pge_x, d_pge_q;  // GNN-PGE: path groups of the data vertices, label embeddings, query records
+    u32 pge_pl = 0;
+    bool have_pge = false, b_pge = false;
     gpe::DevBuf d_bfs, d_bfs_cnt;  // level-synchronous join: frontiers + counters
     bool b_bfs_used = false;
     u64 bfs_cap_e = 0, bfs_cap_c = 0;
@@ -351,5 +354,21 @@ size_t k3_bfs_bytes(u32 max_nq, u64 cap_e, u64 cap_c);
 cudaError_t k3_bfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
                    const void *init, const JoinQueue *jq, u64 *answers, void *buf, u64 cap_e, u64 cap_c, u32 *counters,
                    u32 levels, int sm_count, cudaStream_t s);
+
+// K4: GNN-PGE (per-vertex path groups), see k4_pge.cu.  Rows in class order (index = lcoff[label] + lpos), columns by
+// dimension: pg_lo/pg_hi/plg_lo/plg_hi [pde][V], deg [V], has [V].
+struct PgeView {
+    double *pg_lo, *pg_hi, *plg_lo, *plg_hi;
+    u32 *deg;
+    unsigned char *has;
+};
+size_t k4_pge_bytes(u32 V, u32 pde);
+PgeView k4_pge_view(void *buf, u32 V, u32 pde);
+cudaError_t k4_pge_groups(const GraphView &g, u32 pl, const double *d_x, const PgeView &p, int sm_count, cudaStream_t s);
+cudaError_t k4_pge_scan(const PgeView &p, u32 V, u32 pde, u32 n_labels, const u32 *lcoff, const u32 *label_slot_off,
+                        const u32 *slot_list, const u32 *q_deg, const double *q_pg_lo, const double *q_plg_lo,
+                        const double *q_plg_hi, u32 *bitmap, u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s);
+cudaError_t k4_pge_dump(const PgeView &p, const GraphView &g, u32 pde, double *pg, double *plg, unsigned char *has,
+                        cudaStream_t s);
 
 }  // namespace gpe

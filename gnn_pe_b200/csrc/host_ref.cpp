@@ -204,6 +204,53 @@ void query_plan(uint32_t nq, const uint32_t *off, const uint32_t *nbr, const uin
     }
 }
 
+static void pge_walk(const uint32_t *off, const uint32_t *nbr, uint32_t pl, uint32_t e, const double *x, const double *vde,
+                     uint32_t *path, uint32_t len, double *pg, double *plg, bool &first) {
+    if (len == pl) {
+        for (uint32_t j = 0; j < pl; j++)
+            for (uint32_t k = 0; k < e; k++) {
+                const double a = vde[(size_t)path[j] * e + k], b = x[(size_t)path[j] * e + k];
+                const uint32_t d = j * e + k;
+                if (first) { pg[2 * d] = pg[2 * d + 1] = a; plg[2 * d] = plg[2 * d + 1] = b; }
+                else {
+                    if (pg[2 * d] > a) pg[2 * d] = a;
+                    if (pg[2 * d + 1] < a) pg[2 * d + 1] = a;
+                    if (plg[2 * d] > b) plg[2 * d] = b;
+                    if (plg[2 * d + 1] < b) plg[2 * d + 1] = b;
+                }
+            }
+        first = false;
+        return;
+    }
+    const uint32_t node = path[len - 1];
+    for (uint32_t j = off[node]; j < off[node + 1]; j++) {
+        const uint32_t nb = nbr[j];
+        bool seen = false;
+        for (uint32_t t = 0; t < len; t++) seen = seen || path[t] == nb;
+        if (seen) continue;
+        path[len] = nb;
+        pge_walk(off, nbr, pl, e, x, vde, path, len + 1, pg, plg, first);
+    }
+}
+
+void pge_groups(uint32_t V, const uint32_t *off, const uint32_t *nbr, uint32_t pl, uint32_t e, const double *x,
+                const double *vde, double *pg, double *plg, unsigned char *has) {
+    const uint32_t pde = pl * e;
+    uint32_t path[GPE_MAX_QUERY_VERTICES];
+    for (uint32_t v = 0; v < V; v++) {
+        double *a = pg + (size_t)v * 2 * pde, *b = plg + (size_t)v * 2 * pde;
+        bool first = true;
+        path[0] = v;
+        pge_walk(off, nbr, pl, e, x, vde, path, 1, a, b, first);
+        has[v] = first ? 0 : 1;
+        if (first)
+            for (uint32_t d = 0; d < pde; d++) {
+                a[2 * d] = a[2 * d + 1] = d < e ? vde[(size_t)v * e + d] : 0.0;
+                b[2 * d] = b[2 * d + 1] = d < e ? x[(size_t)v * e + d] : 0.0;
+            }
+    }
+}
+
 }  // namespace gpe
 
 // ---- C ABI ---------------------------------------------------------------------------------------------------
@@ -242,5 +289,14 @@ extern "C" int gpe_host_query_plan(uint32_t nq, const uint32_t *q_offsets, const
     if (degs) std::copy(plan.degs.begin(), plan.degs.begin() + (size_t)m * L, degs);
     if (pde) std::copy(plan.pde.begin(), plan.pde.begin() + (size_t)m * L * e, pde);
     if (n) *n = plan.n;
+    return GPE_OK;
+}
+
+extern "C" int gpe_host_pge_groups(uint32_t V, const uint32_t *offsets, const uint32_t *nbrs, const uint32_t *labels,
+                                   uint32_t pl, uint32_t e, double *pg, double *plg, uint8_t *has) {
+    if (!offsets || !labels || !pg || !plg || !has || e == 0 || pl == 0 || pl > GPE_MAX_QUERY_VERTICES) return GPE_ERR_INVALID;
+    std::vector<double> x((size_t)V * e), vde((size_t)V * e);
+    gpe::gen_vde(V, offsets, nbrs, labels, e, x.data(), vde.data());
+    gpe::pge_groups(V, offsets, nbrs, pl, e, x.data(), vde.data(), pg, plg, has);
     return GPE_OK;
 }

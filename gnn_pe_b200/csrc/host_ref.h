@@ -34,6 +34,12 @@ bool query_connected(uint32_t nq, const uint32_t *off, const uint32_t *nbr);
 void query_plan(uint32_t nq, const uint32_t *off, const uint32_t *nbr, const uint32_t *labels, uint32_t L, uint32_t e,
                 QueryPlan &plan, const LabelTable *table = nullptr);
 
+// GNN-PGE (GNN-PGE/src/main.cpp:226-291 for the query, :91-176 for the data graph): bounding boxes of the embeddings of all
+// simple paths of pl vertices from every vertex; pg, plg: V x pl*e x 2 ([lo, hi] per dimension), has[v] = 0 when v starts
+// no such path (the box is then [vde, vde | 0 ...] / [x, x | 0 ...] as on the data side).
+void pge_groups(uint32_t V, const uint32_t *off, const uint32_t *nbr, uint32_t pl, uint32_t e, const double *x,
+                const double *vde, double *pg, double *plg, unsigned char *has);
+
 }  // namespace gpe
 
 const char *gpe_host_last_error_internal();

@@ -64,7 +64,8 @@ SYMBOLS = [
     "gpe_batch_upload", "gpe_batch_filter", "gpe_batch_join", "gpe_batch_download", "gpe_clamp_answer",
     "gpe_query_batch", "gpe_batch_cand_info", "gpe_batch_cand_export", "gpe_batch_cand_merge",
     "gpe_batch_scan", "gpe_batch_bitmap", "gpe_batch_bitmap_merge",
-    "gpe_batch_get_candidates", "gpe_batch_get_plan", "gpe_get_stats", "gpe_stream", "gpe_sync", "gpe_set_timing",
+    "gpe_batch_get_candidates", "gpe_batch_get_plan", "gpe_pge_build", "gpe_host_pge_groups", "gpe_pge_dump_groups", "gpe_pge_batch_upload",
+    "gpe_pge_batch_filter", "gpe_pge_query_batch", "gpe_get_stats", "gpe_stream", "gpe_sync", "gpe_set_timing",
     "gpe_collect_timings",
 ]
 
@@ -109,6 +110,12 @@ def lib():
         L.gpe_batch_scan.argtypes = [vp]
         L.gpe_batch_bitmap.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         L.gpe_batch_bitmap_merge.argtypes = [vp, u32, vp]
+        L.gpe_pge_build.argtypes = [vp, u32, vp]
+        L.gpe_host_pge_groups.argtypes = [u32, vp, vp, vp, u32, u32, vp, vp, vp]
+        L.gpe_pge_dump_groups.argtypes = [vp, vp, vp, vp]
+        L.gpe_pge_batch_upload.argtypes = [vp, C.POINTER(Batch)]
+        L.gpe_pge_batch_filter.argtypes = [vp]
+        L.gpe_pge_query_batch.argtypes = [vp, C.POINTER(Batch), vp]
         L.gpe_batch_get_candidates.argtypes = [vp, vp, vp]
         L.gpe_batch_get_plan.argtypes = [vp, vp, vp]
         L.gpe_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -168,6 +175,19 @@ def host_query_plan(q_offsets, q_nbrs, q_labels, L: int, e: int):
         raise GpeError(f"gpe_host_query_plan failed with {rc}")
     k = n.value
     return dict(vids=vids[:k], labels=labels[:k], degrees=degs[:k], pde=pde[:k])
+
+
+def host_pge_groups(offsets, nbrs, labels, pl: int, e: int):
+    """GNN-PGE path groups on the host: (pg, plg) as V x 2*pl*e [lo, hi, ...] and has[V]."""
+    offsets, nbrs, labels = _u32(offsets), _u32(nbrs), _u32(labels)
+    V = len(labels)
+    pg = np.zeros((max(V, 1), 2 * pl * e), dtype=np.float64)
+    plg = np.zeros((max(V, 1), 2 * pl * e), dtype=np.float64)
+    has = np.zeros(max(V, 1), dtype=np.uint8)
+    rc = lib().gpe_host_pge_groups(V, _ptr(offsets), _ptr(nbrs), _ptr(labels), pl, e, _ptr(pg), _ptr(plg), _ptr(has))
+    if rc:
+        raise GpeError(f"gpe_host_pge_groups failed with {rc}")
+    return pg[:V], plg[:V], has[:V]
 
 
 def pack_queries(queries):
@@ -366,6 +386,34 @@ class GpeContext:
         pivot = np.zeros(max(n_slots, 1), dtype=np.uint32)
         self._ck(self._L.gpe_batch_get_plan(self._h, _ptr(order), _ptr(pivot)))
         return order[:n_slots], pivot[:n_slots]
+
+    # ---- GNN-PGE variant (see include/gpe.h for its status) ----
+    def pge_build(self, pl: int, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        self.pge_pl = pl
+        self._ck(self._L.gpe_pge_build(self._h, pl, _ptr(x)))
+
+    def pge_dump_groups(self):
+        pde = self.pge_pl * self.e
+        pg = np.zeros((max(self.V, 1), 2 * pde), dtype=np.float64)
+        plg = np.zeros((max(self.V, 1), 2 * pde), dtype=np.float64)
+        has = np.zeros(max(self.V, 1), dtype=np.uint8)
+        self._ck(self._L.gpe_pge_dump_groups(self._h, _ptr(pg), _ptr(plg), _ptr(has)))
+        return pg[: self.V], plg[: self.V], has[: self.V]
+
+    def pge_batch_upload(self, queries, limits=None):
+        b = self._batch_struct(queries, limits)
+        self._n_queries = len(queries)
+        self._ck(self._L.gpe_pge_batch_upload(self._h, C.byref(b)))
+
+    def pge_batch_filter(self):
+        self._ck(self._L.gpe_pge_batch_filter(self._h))
+
+    def pge_query_batch(self, queries, limits=None) -> np.ndarray:
+        b = self._batch_struct(queries, limits)
+        ans = np.zeros(max(len(queries), 1), dtype=np.uint64)
+        self._ck(self._L.gpe_pge_query_batch(self._h, C.byref(b), _ptr(ans)))
+        return ans[: len(queries)]
 
     def clamp(self, raw: int, limit: int) -> int:
         return int(self._L.gpe_clamp_answer(int(raw), int(limit)))

@@ -163,6 +163,28 @@ int gpe_batch_bitmap_merge(gpe_ctx *ctx, uint32_t world, const void *d_all);
 int gpe_batch_get_candidates(gpe_ctx *ctx, uint64_t *cand_offsets /*n_slots+1*/, uint32_t *cand /*or NULL*/);
 int gpe_batch_get_plan(gpe_ctx *ctx, uint32_t *order /*n_slots*/, uint32_t *pivot /*n_slots*/);
 
+/* ---- GNN-PGE: the reference's sibling variant of the filter (GNN-PGE/src/main.cpp, GNN-PGE/include/custom.h) --------
+ * One row per data VERTEX: the bounding box of the embeddings of all simple paths of `pl` vertices that start at it
+ * ("path group", src/main.cpp:91-176), over the dominance embeddings and over the label embeddings.  A data vertex v
+ * is a candidate of a query vertex u iff label and degree fit, the label boxes overlap and v's upper corner is not
+ * below u's lower corner (include/custom.h:332-367).  Matching order and join are shared with the path filter.
+ * STATUS: compiled, NOT yet verified on a GPU (written after round 1's GPU budget was spent); its oracle is pinned. */
+/* x: the label embeddings per vertex (V x e) as gpe_host_gen_vde returns them; needs gpe_set_graph + gpe_set_embeddings.
+ * pl = vertices per path (GNN-PGE's -l, default 2; 1..4 here). */
+int gpe_pge_build(gpe_ctx *ctx, uint32_t pl, const double *x);
+/* The same groups on the host (pure host code, no GPU): what the batch upload computes for every query graph, and a
+ * CPU statement of gpe_pge_build + gpe_pge_dump_groups for any graph.  pg, plg: V x (pl*e) x [lo, hi]. */
+int gpe_host_pge_groups(uint32_t V, const uint32_t *offsets, const uint32_t *nbrs, const uint32_t *labels, uint32_t pl,
+                        uint32_t e, double *pg, double *plg, uint8_t *has);
+/* The groups in vertex order, V x (pl*e) x [lo, hi] each, as src/main.cpp:179-194 writes them; has[v] = 0 marks a vertex
+ * without any such path (its box is then [vde, vde | 0 ...]). */
+int gpe_pge_dump_groups(gpe_ctx *ctx, double *pg, double *plg, uint8_t *has);
+/* The batch stages with the GNN-PGE filter in place of the path filter; continue with gpe_batch_join /
+ * gpe_batch_download (or gpe_batch_get_candidates). */
+int gpe_pge_batch_upload(gpe_ctx *ctx, const gpe_batch *batch);
+int gpe_pge_batch_filter(gpe_ctx *ctx);
+int gpe_pge_query_batch(gpe_ctx *ctx, const gpe_batch *batch, uint64_t *answers);
+
 /* ---- measurement hooks ------------------------------------------------------------------- */
 typedef struct gpe_stats {
     uint64_t table_rows, table_tiles, tile_rows, row_bytes;  /* row_bytes = L*4 + L*4 + L*e*8 */

@@ -84,3 +84,17 @@ def test_host_mirror_against_golden(lib, name):
 def test_host_loader_errors(lib, tmp_path):
     with pytest.raises(gpe.GpeError):
         gpe.host_load_graph(str(tmp_path / "missing.graph"))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_pge_groups_against_reference_golden(lib, name):
+    """The host mirror of GNN-PGE's path groups (what the batch upload computes per query) against data_vertices.bin of
+    the unmodified reference (tests/golden/<case>/golden_pge.json)."""
+    import hashlib
+    import json
+    gold = load_case(name)
+    pge = json.load(open(os.path.join(gold["dir"], "golden_pge.json")))
+    off, nbr, lab = gpe.host_load_graph(gold["data_path"])
+    pg, plg, has = gpe.host_pge_groups(off, nbr, lab, pge["pl"], pge["e"])
+    assert hashlib.md5(pg.tobytes()).hexdigest() == pge["pg_md5"]
+    assert hashlib.md5(plg.tobytes()).hexdigest() == pge["plg_md5"]
