@@ -55,5 +55,5 @@ print("ok", sys.argv[1], got)
 @pytest.mark.xfail(strict=False, reason="GNN-PGE kernels: written after round 1's GPU budget was spent, not yet seen on a GPU")
 @pytest.mark.parametrize("name", CASES)
 def test_pge_matches_reference_golden(name):
-    r = subprocess.run([sys.executable, "-c", _SCRIPT, name], capture_output=True, timeout=240, cwd=ROOT)
+    r = subprocess.run([sys.executable, "-c", _SCRIPT, name], capture_output=True, timeout=90, cwd=ROOT)
     assert r.returncode == 0, (r.stdout.decode()[-1500:], r.stderr.decode()[-3000:])
