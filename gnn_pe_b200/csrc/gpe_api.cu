@@ -292,7 +292,7 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
     GPE_CUDA(c, c->d_jplan.reserve(std::max<size_t>(n_slots, 1) * sizeof(JoinDepth)));
     GPE_CUDA(c, c->d_kids.reserve(std::max<size_t>(n_slots, 1) * 2 * sizeof(u32)));
     GPE_CUDA(c, c->d_item_base.reserve(((size_t)n_queries + 1) * sizeof(u64)));
-    GPE_CUDA(c, c->d_answers.reserve(((size_t)n_queries + 8) * sizeof(u64)));
+    GPE_CUDA(c, c->d_answers.reserve((2 * (size_t)n_queries + 8) * sizeof(u64)));
     GPE_CUDA(c, c->d_match_cursor.reserve(2 * sizeof(u64)));
     c->stats.h2d_bytes += sz[0] + sz[1] + sz[2] + (size_t)n_adj * sizeof(u32) + (size_t)n_slots * sizeof(u32) + sz[5];
     // pageable sources: make sure the copies are done before the caller's buffers go away
@@ -302,13 +302,15 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
 
 constexpr u64 kJoinExportBytes = 256ull << 20;  // room for exported work items
 
-int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, bool force_dfs = false) {
+// d_answers: [0, nq + 8) raw counts, [nq + 8, 2 nq + 8) per-query "inexact" flags (see kSat in k3_join.cu)
+int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, bool force_dfs = false,
+             const u32 *d_qmode = nullptr) {
     StageTimer tm(c, &c->stats.last_join_ms, kStageJoin);
     c->b_rank = rank;
     c->b_world = world;
     const u32 nq = c->b_nq;
     u64 *answers = c->d_answers.as<u64>();
-    GPE_CUDA(c, cudaMemsetAsync(c->d_answers.p, 0, ((size_t)nq + 8) * sizeof(u64), c->stream));
+    GPE_CUDA(c, cudaMemsetAsync(c->d_answers.p, 0, (2 * (size_t)nq + 8) * sizeof(u64), c->stream));
     GPE_CUDA(c, cudaMemsetAsync(c->d_match_cursor.p, 0, 2 * sizeof(u64), c->stream));
     GPE_CUDA(c, c->d_jq.reserve(sizeof(JoinQueue)));
     // Subtree tables are only sound when the start vertex's candidates carry its label; that holds for the
@@ -341,7 +343,7 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
                          c->d_q_nbrs.as<u32>(), c->d_q_labels.as<u32>(), c->d_cand_off.as<u64>(), c->d_order.as<u32>(),
                          c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_item_base.as<u64>(), rank, world,
                          enumerate, clean_start, c->n_labels, c->d_lcoff.as<u32>(), c->d_tjobs.as<TreeJob>(),
-                         c->d_tchild.as<u32>(), c->d_tcursor.as<u64>(), tcount, tlist, n_slots, allow_weighted, c->stream));
+                         c->d_tchild.as<u32>(), c->d_tcursor.as<u64>(), tcount, tlist, n_slots, allow_weighted, d_qmode, c->stream));
     JoinView jv{c->d_label.as<u32>(), c->d_nbrL.as<u32>(), c->d_gtab.as<u32>(), c->V, c->n_labels, c->d_deg.as<u32>(),
                 c->d_lclass.as<u32>(), c->d_lpos.as<u32>(), c->d_lcoff.as<u32>(), c->d_tpool.as<u64>(), c->d_bloom.as<u32>(),
                 c->bloom_bits - 1, c->lpos_packed};
@@ -396,7 +398,7 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
     } else {
     GPE_CUDA(c, k3_dfs(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_cand.as<u32>(),
                        c->d_init.p, c->d_limits.as<u64>(), answers, c->d_items.as<u32>(), cap, c->d_ready.as<u32>(), epoch,
-                       jq, d_matches, matches_cap, c->d_match_cursor.as<u64>(), c->sm_count, c->stream));
+                       jq, d_matches, matches_cap, c->d_match_cursor.as<u64>(), answers + nq + 8, c->sm_count, c->stream));
     }
     c->b_bfs_used = use_bfs;
     c->stats.join_bfs = use_bfs ? 1 : 0;
@@ -498,7 +500,7 @@ void gpe_destroy(gpe_ctx *c) {
                       &c->d_counters, &c->d_bitmap, &c->d_survivors, &c->d_slot_label, &c->d_chunk_cnt, &c->d_chunk_off, &c->d_cand,
                       &c->d_cand_off, &c->d_q_vbase, &c->d_q_ebase, &c->d_q_offsets, &c->d_q_nbrs, &c->d_q_labels,
                       &c->d_limits, &c->d_order, &c->d_pivot, &c->d_jplan, &c->d_item_base, &c->d_answers,
-                      &c->d_matches, &c->d_match_cursor};
+                      &c->d_matches, &c->d_match_cursor, &c->d_qmode, &c->d_pge, &c->d_pge_x, &c->d_pge_q, &c->d_bfs, &c->d_bfs_cnt};
     for (DevBuf *b : bufs) b->release();
     c->h_pin.release();
     c->h_pin2.release();
@@ -1043,11 +1045,17 @@ int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) {
     if (!c || !raw_counts) return GPE_ERR_INVALID;
     if (!c->b_joined) return c->fail(GPE_ERR_INVALID, "gpe_batch_join first");
     GPE_CUDA(c, cudaSetDevice(c->device));
-    GPE_CUDA(c, c->h_pin2.reserve((std::max<size_t>(c->b_nq, 16) + 16) * sizeof(u64)));
+    const size_t nq = c->b_nq;
+    GPE_CUDA(c, c->h_pin2.reserve((2 * std::max<size_t>(nq, 16) + 32) * sizeof(u64)));
     u64 *pin = c->h_pin2.as<u64>();
-    GPE_CUDA(c, cudaMemcpyAsync(pin, c->d_answers.p, (size_t)c->b_nq * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-    GPE_CUDA(c, cudaMemcpyAsync(pin + c->b_nq, c->d_jq.p, sizeof(JoinQueue), cudaMemcpyDeviceToHost, c->stream));
+    u64 *pin_flags = pin + nq + 16;  // behind the queue header
+    GPE_CUDA(c, cudaMemcpyAsync(pin, c->d_answers.p, nq * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(pin + nq, c->d_jq.p, sizeof(JoinQueue), cudaMemcpyDeviceToHost, c->stream));
+    static_assert(sizeof(JoinQueue) <= 16 * sizeof(u64), "pinned layout");
+    if (nq) GPE_CUDA(c, cudaMemcpyAsync(pin_flags, c->d_answers.as<u64>() + nq + 8, nq * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    // raw counts are exact below 2^44 and saturated beyond (k3_join.cu kSat); capped so that shards can still be summed
+    for (size_t q = 0; q < nq; q++) pin[q] = std::min<u64>(pin[q], 1ull << 48);
     if (c->b_bfs_used) {  // level-synchronous join: did every frontier fit?  (else recompute depth-first, once)
         u32 cnt[72];
         GPE_CUDA(c, cudaMemcpyAsync(cnt, c->d_bfs_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
@@ -1073,6 +1081,27 @@ int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) {
     memcpy(raw_counts, pin, (size_t)c->b_nq * sizeof(u64));
     JoinQueue jq;
     memcpy(&jq, pin + c->b_nq, sizeof jq);
+    {   // queries whose weighted counted leaves met a saturated table entry (a difference of two numbers beyond 2^62):
+        // joined once more with those leaves walked -- everything that is left saturates monotonically, so
+        // min(count, limit) is exact.  Local to this shard: each rank repairs the share of its own start candidates.
+        std::vector<u32> qmode;
+        for (size_t q = 0; q < nq; q++)
+            if (pin_flags[q]) { qmode.assign(nq, 2u); break; }
+        if (!qmode.empty()) {
+            for (size_t q = 0; q < nq; q++)
+                if (pin_flags[q]) qmode[q] = 1u;
+            GPE_CUDA(c, c->d_qmode.reserve(nq * sizeof(u32)));
+            GPE_CUDA(c, cudaMemcpyAsync(c->d_qmode.p, qmode.data(), nq * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+            int rc = run_join(c, c->b_rank, c->b_world, nullptr, 0, /*force_dfs=*/true, c->d_qmode.as<u32>());
+            if (rc) return rc;
+            std::vector<u64> second(nq);
+            GPE_CUDA(c, cudaMemcpyAsync(second.data(), c->d_answers.p, nq * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+            GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+            for (size_t q = 0; q < nq; q++)
+                if (qmode[q] == 1u) raw_counts[q] = std::min<u64>(second[q], 1ull << 48);
+            c->stats.join_reruns++;
+        }
+    }
     c->stats.join_items = jq.tail;
     c->stats.join_exports = jq.exports;
     c->stats.join_donations = jq.donations;

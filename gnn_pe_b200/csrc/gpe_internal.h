@@ -238,7 +238,7 @@ struct gpe_ctx {
     gpe::DevBuf d_qblocks, d_qb_t0, d_qb_prefix, d_worklist, d_counters, d_bitmap, d_survivors, d_slot_label;
     gpe::DevBuf d_chunk_cnt, d_chunk_off, d_cand, d_cand_off;
     gpe::DevBuf d_q_vbase, d_q_ebase, d_q_offsets, d_q_nbrs, d_q_labels, d_limits;
-    gpe::DevBuf d_order, d_pivot, d_jplan, d_item_base, d_answers, d_matches, d_match_cursor;
+    gpe::DevBuf d_order, d_pivot, d_jplan, d_item_base, d_answers, d_matches, d_match_cursor, d_qmode;
     gpe::PinnedBuf h_pin, h_pin2;
     gpe::LabelTable label_table;  // label embeddings of the queries seen so far (host planning)
     u64 b_chunks_per_slot = 0;
@@ -317,7 +317,8 @@ cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebas
                      bool enumerate /*walk every vertex (matches wanted)*/, bool clean_start /*start candidates carry the
                      query label (they come from the filter)*/, u32 n_labels, const u32 *lcoff, TreeJob *tjobs, u32 *tchild,
                      u64 *tcursor, u32 *tcount /*kMaxTreeLevels, zeroed*/, u32 *tlist /*kMaxTreeLevels x 2 n_slots*/, u32 n_slots,
-                     bool allow_weighted /*counted leaves may carry peeled subtrees (depth-first kernel only)*/, cudaStream_t s);
+                     bool allow_weighted /*counted leaves may carry peeled subtrees (depth-first kernel only)*/,
+                     const u32 *qmode /*per query or null: 0 as usual, 1 no weighted leaves, 2 leave the query out*/, cudaStream_t s);
 // label-grouped adjacency for the join (built on the host in gpe_set_graph)
 struct JoinView {
     const u32 *label, *nbrL /* (neighbour, degree) pairs */, *gtab;
@@ -345,7 +346,8 @@ cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase,
 // one persistent launch: every thread runs work items (explicit-stack DFS) and exports subtrees when others starve
 cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
                    const void *init, const u64 *limits, u64 *answers, u32 *items, u64 export_cap, u32 *ready, u32 epoch,
-                   JoinQueue *jq, u32 *matches, u64 matches_cap, u64 *match_cursor, int sm_count, cudaStream_t s);
+                   JoinQueue *jq, u32 *matches, u64 matches_cap, u64 *match_cursor, u64 *inexact /*per query, zeroed: set when a
+                   weighted count met a saturated operand*/, int sm_count, cudaStream_t s);
 
 // level-synchronous join (counting, no answer limits): frontier buffers in `buf` (k3_bfs_bytes), counters = 256 u32, zeroed;
 // counters[64] != 0 afterwards means a frontier outgrew its buffer and the result must be recomputed depth-first;

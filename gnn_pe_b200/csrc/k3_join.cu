@@ -31,6 +31,29 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
+// Counting arithmetic.  The reference counts one embedding at a time and stops at the answer limit, which is at most
+// UINT_MAX (custom.h:846-855, main.cpp:62-69), so what has to be exact is min(total, limit) with limit < 2^32.  The
+// factorised count multiplies and adds table entries instead; every such operation SATURATES at kSat = 2^62 (sums and
+// products of non-negative numbers: min(x, kSat) is closed under both), so a count beyond 2^64 can never wrap to a
+// small number.  The only subtractions are those of the weighted counted leaves (S_u[pivot] - N_u[prefix vertex],
+// W(A) W(B) - overlap); when one of their operands is saturated the difference is unknown, the query is flagged in
+// `inexact[]` and the host walks those leaves instead (run_join with qmode, gpe_api.cu).
+constexpr u64 kSat = 1ull << 62;
+constexpr u64 kFlushCap = 1ull << 44;   // a lane's contribution to answers[] per flush; totals below it are exact
+constexpr u64 kAnswerFull = 1ull << 48; // answers[] at or beyond this are not added to any more
+__device__ __forceinline__ u64 sat_mul(u64 a, u64 b) {
+    const u64 lo = a * b;
+    return (__umul64hi(a, b) != 0 || lo > kSat) ? kSat : lo;
+}
+__device__ __forceinline__ u64 sat_add(u64 a, u64 b) {  // a, b <= kSat
+    const u64 s = a + b;
+    return s > kSat ? kSat : s;
+}
+__device__ __forceinline__ void flush_answer(u64 *answers, u32 q, u64 acc) {
+    if (*(volatile u64 *)&answers[q] < kAnswerFull)
+        atomicAdd((unsigned long long *)&answers[q], (unsigned long long)(acc < kFlushCap ? acc : kFlushCap));
+}
+
 // ---- bitmap -> per-chunk popcounts ------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k3_chunk_count_kernel(const u32 *__restrict__ bitmap, u64 words_per_slot,
                                                              u64 chunks_per_slot, u64 n_chunks,
@@ -168,9 +191,13 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                                                        u32 n_labels, const u32 *__restrict__ lcoff, TreeJob *tjobs,
                                                        u32 *tchild, u64 *tcursor, u32 *tcount, u32 *tlist,
                                                        u32 n_slots /*stride of tlist: 2 x slots*/, u32 sjob_base /*slots*/,
-                                                       bool allow_weighted) {
+                                                       bool allow_weighted_all, const u32 *__restrict__ qmode) {
     for (u32 q = threadIdx.x; q < n_queries; q += blockDim.x) {
-        const u32 vb = q_vbase[q], nq = q_vbase[q + 1] - vb;
+        // qmode (second pass of a batch some of whose weighted counts saturated, see kSat): 0 as usual, 1 plan this query
+        // without weighted counted leaves, 2 leave this query out (no tickets, no tables)
+        const u32 mode = qmode ? qmode[q] : 0;
+        const bool allow_weighted = allow_weighted_all && mode == 0;
+        const u32 vb = q_vbase[q], nq = mode == 2 ? 0 : q_vbase[q + 1] - vb;
         const u32 *off = q_offsets + vb + q;  // nq + 1 local offsets
         const u32 *nbr = q_nbrs + q_ebase[q];
         const u32 *qlab = q_labels + vb;
@@ -773,11 +800,11 @@ __global__ void __launch_bounds__(256) k3_tree_tables_kernel(JoinGraph g, const 
                         if ((g.packed ? yd.y & 255u : yd.y) < cj.qdeg) continue;
                         const u32 yp = g.packed ? yd.y >> 8 : g.lpos[yd.x];
                         if (bm && !(bm[yp >> 5] >> (yp & 31) & 1)) continue;
-                        sum += cj.level ? tpool[cj.table_off + yp] : 1;
+                        sum = sat_add(sum, cj.level ? tpool[cj.table_off + yp] : 1);
                     }
                 }
             }
-            val *= sum;
+            val = sat_mul(val, sum);
         }
         tpool[job.table_off + pos] = val;
     }
@@ -791,7 +818,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                                                          const u32 *__restrict__ cand, const uint2 *__restrict__ init,
                                                          const u64 *__restrict__ limits, u64 *answers, u32 *items,
                                                          u64 export_cap, u32 *ready, u32 epoch, JoinQueue *jq,
-                                                         u32 *matches, u64 matches_cap, u64 *match_cursor, u32 flags) {
+                                                         u32 *matches, u64 matches_cap, u64 *match_cursor, u32 flags,
+                                                         u64 *inexact) {
     constexpr u32 stride = item_stride(M);
     const bool cgl = flags & 2u;  // bloom words and class positions go around L1
     const u32 exp_mask = (1u << (flags >> 4 & 7u)) - 1;  // rounds between two looks at the queue header, minus one (kExportEvery)
@@ -821,6 +849,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
     u64 ticket = 0;
     u32 q = 0, vb = 0, nq = 0, base = 0, d = 0, lab0 = 0, tail_at = 0;
     u32 acc_q = 0xffffffffu;
+    u32 lim32 = 0xffffffffu;  // answer limit of the lane's query (custom.h:851-854); 0xffffffff = `-n MAX`: count everything
     u64 acc = 0, my_steps = 0, my_exports = 0, my_donations = 0;
     u64 w_iters = 0, w_polls = 0;                       // warp-uniform: iterations with / without a busy lane
     u32 claimed = 0, iter = 0, backoff = 64;            // warp-uniform
@@ -888,12 +917,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 const uint2 it = init[ticket];
                 const u32 iq = it.x;
                 if (iq != acc_q) {
-                    if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
+                    if (acc) flush_answer(answers, acc_q, acc);
                     acc = 0;
                     acc_q = iq;
                 }
                 u64 limit = limits ? limits[iq] : GPE_LIMIT_MAX;
                 if (limit == 0) limit = 1;  // the reference tests the limit only after counting a match (:851)
+                lim32 = limit >= GPE_LIMIT_MAX ? 0xffffffffu : (u32)limit;
                 q = iq;
                 vb = q_vbase[q];
                 nq = jplan[vb].sure_used;  // depths of the execution plan (peeled subtrees are not walked)
@@ -910,12 +940,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 const u32 *it = items + (ticket - n_init) * stride;
                 const u32 iq = it[0];
                 if (iq != acc_q) {
-                    if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
+                    if (acc) flush_answer(answers, acc_q, acc);
                     acc = 0;
                     acc_q = iq;
                 }
                 u64 limit = limits ? limits[iq] : GPE_LIMIT_MAX;
                 if (limit == 0) limit = 1;
+                lim32 = limit >= GPE_LIMIT_MAX ? 0xffffffffu : (u32)limit;
                 q = iq;
                 vb = q_vbase[q];
                 nq = jplan[vb].sure_used;
@@ -988,13 +1019,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 const u32 p_nq = __shfl_sync(kFull, nq, partner), p_lab0 = __shfl_sync(kFull, lab0, partner);
                 const u32 p_tail = __shfl_sync(kFull, tail_at, partner), p_l = __shfl_sync(kFull, l, partner);
                 const u32 p_lo = __shfl_sync(kFull, lo_g, partner), p_hi = __shfl_sync(kFull, hi_g, partner);
+                const u32 p_lim = __shfl_sync(kFull, lim32, partner);
                 if (take) {
                     if (p_q != acc_q) {
-                        if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
+                        if (acc) flush_answer(answers, acc_q, acc);
                         acc = 0;
                         acc_q = p_q;
                     }
-                    q = p_q; vb = p_vb; nq = p_nq; lab0 = p_lab0; tail_at = p_tail;
+                    q = p_q; vb = p_vb; nq = p_nq; lab0 = p_lab0; tail_at = p_tail; lim32 = p_lim;
                     base = d = p_l;
                     const int col = partner - lane;  // the donor's stack column, relative to mine
                     for (u32 t = 0; t < p_l; t++) EMB(t) = emb[t * THREADS + col];
@@ -1012,6 +1044,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             }
         }
 
+        // answer limit (`-n N`): the reference stops enumerating once the count reaches it (custom.h:851-854); a lane of a
+        // limited query banks straight into answers[] (below) and drops its work as soon as the query's count is there
+        if (have && lim32 != 0xffffffffu && *(volatile u64 *)&answers[q] >= lim32) {
+            have = false;
+            pend = false;
+        }
         w_iters += spr;
         for (int rep = 0; rep < spr; rep++) {
           // A step has two parts with very different lane populations: the candidate test (most busy lanes) and the
@@ -1093,7 +1131,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 }
             }
             if (ok) {
-                const u64 p = (d ? PROD(d - 1) : 1) * tree_f;
+                const u64 p = d ? sat_mul(PROD(d - 1), tree_f) : tree_f;
                 const u64 um = tail_at < nq ? jd->units_mask >> tail_at : 0;
                 if (um && p) { pend = true; pend_p = p; } else fin_p = p;
             }
@@ -1123,6 +1161,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                             return (u64)((e - s) - used);
                         }
                         u64 wsum = __ldcg(g.tpool + lf->units_mask + __ldcg(g.lpos + pvx));
+                        if (wsum >= kSat) inexact[q] = 1;  // saturated minuend: the difference below is unknown
                         const u64 sure = lf->bn_mask;
                         u64 m = lf->tail_mask | sure;
                         for (u32 t = 0; m; t++, m >>= 1) {
@@ -1151,9 +1190,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                         u64 n_run = n_free;  // (followers are plain leaves on the same pivot: falling factorial)
                         for (u32 k = i + 1; k < nq && (jplan[vb + k].tail_k & 0xffu) == kTailFall; k++) {
                             n_run = n_run ? n_run - 1 : 0;
-                            f *= n_run;
+                            f = sat_mul(f, n_run);
                         }
-                        p *= f;
+                        p = sat_mul(p, f);
                     } else {  // kTailPairA: leaf i and leaf i+1, same label, different pivots
                         const JoinDepth *lb = ld + 1;
                         const u32 s2 = S0(i + 1), e2 = E0(i + 1);
@@ -1176,7 +1215,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                                 y++;
                             }
                         }
-                        p *= n_free * n_free2 - inter;
+                        // (plain leaves: group sizes, the product fits; weighted ones can exceed 64 bits)
+                        if (__umul64hi(n_free, n_free2) != 0 || n_free * n_free2 > kSat) inexact[q] = 1;
+                        p = sat_mul(p, n_free * n_free2 - inter);
                     }
                 }
                 fin_p = p;
@@ -1187,7 +1228,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 const u64 p = fin_p;
                 if (p) {
                     if (d + 1 == tail_at) {
-                        acc += p;
+                        if (lim32 != 0xffffffffu) {  // limited query: bank at once so that every lane sees the limit reached
+                            const u64 pc = p < kFlushCap ? p : kFlushCap;
+                            if (atomicAdd((unsigned long long *)&answers[q], (unsigned long long)pc) + pc >= lim32) have = false;
+                        } else {
+                            acc = sat_add(acc, p);
+                        }
                         if (matches) {  // tail_at == nq here: every vertex was walked
                             u64 pos = atomicAdd((unsigned long long *)match_cursor, 1ull);
                             if (pos < matches_cap) {
@@ -1257,7 +1303,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             }
         }
     }
-    if (acc) atomicAdd((unsigned long long *)&answers[acc_q], (unsigned long long)acc);
+    if (acc) flush_answer(answers, acc_q, acc);
     for (int o = 16; o; o >>= 1) {
         my_steps += __shfl_xor_sync(kFull, my_steps, o);
         my_exports += __shfl_xor_sync(kFull, my_exports, o);
@@ -1333,9 +1379,9 @@ __device__ u64 bfs_close(const JoinGraph &g, const JoinDepth *plan, const uint2 
             u32 n_run = n_free;
             for (u32 k = i + 1; k < n_exec && plan[k].tail_k == kTailFall; k++) {
                 n_run = n_run ? n_run - 1 : 0;
-                f *= n_run;
+                f = sat_mul(f, n_run);
             }
-            p *= f;
+            p = sat_mul(p, f);
         } else {  // kTailPairA: leaf i and leaf i+1, same label, different pivots
             const JoinDepth *lb = ld + 1;
             u32 s2, e2, used2 = lb->sure_used;
@@ -1363,7 +1409,7 @@ __device__ u64 bfs_close(const JoinGraph &g, const JoinDepth *plan, const uint2 
                     y++;
                 }
             }
-            p *= (u64)n_free * n_free2 - inter;
+            p = sat_mul(p, (u64)n_free * n_free2 - inter);
         }
     }
     return p;
@@ -1379,10 +1425,10 @@ __device__ __forceinline__ void bfs_bank(u64 *answers, u32 q, u64 p, bool fin) {
     if (__all_sync(kFull, !fin || q == q0)) {
         u64 v = fin ? p : 0;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-        if (lane == leader) atomicAdd((unsigned long long *)&answers[q0], (unsigned long long)v);
+        for (int o = 16; o; o >>= 1) v = sat_add(v, __shfl_xor_sync(kFull, v, o));
+        if (lane == leader) flush_answer(answers, q0, v);
     } else if (fin) {
-        atomicAdd((unsigned long long *)&answers[q], (unsigned long long)p);
+        flush_answer(answers, q, p);
     }
 }
 __device__ __forceinline__ u32 bfs_append_slot(u32 *counter, bool app) {
@@ -1540,7 +1586,7 @@ __global__ void __launch_bounds__(T) k3_bfs_expand_kernel(JoinGraph g, BfsView b
             }
             if (ok) {
                 BE(D) = c;
-                p = bfs_close<M, T>(g, plan, kids + vb, n_exec, tail_at, D, emb, lab0, b.fprod[cur][e] * tree_f);
+                p = bfs_close<M, T>(g, plan, kids + vb, n_exec, tail_at, D, emb, lab0, sat_mul(b.fprod[cur][e], tree_f));
                 fin = p != 0 && D + 1 == tail_at;
                 app = p != 0 && D + 1 < tail_at;
             }
@@ -1612,13 +1658,13 @@ cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebas
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
                      JoinDepth *jplan, void *kids, u64 *item_base, u32 rank, u32 world, bool enumerate, bool clean_start,
                      u32 n_labels, const u32 *lcoff, TreeJob *tjobs, u32 *tchild, u64 *tcursor, u32 *tcount, u32 *tlist,
-                     u32 n_slots, bool allow_weighted, cudaStream_t s) {
+                     u32 n_slots, bool allow_weighted, const u32 *qmode, cudaStream_t s) {
     // jobs / child lists / per-level job lists hold 2 x n_slots entries: [0, n_slots) the tables N_v of vertices with
     // peeled children, [n_slots, 2 n_slots) the tables S_u of weighted counted leaves
     k3_order_kernel<<<1, 256, 0, s>>>(n_queries, V, q_vbase, q_ebase, q_offsets, q_nbrs, q_labels, cand_off, order,
                                       pivot, jplan, reinterpret_cast<uint2 *>(kids), item_base, rank, world, 1, enumerate,
                                       clean_start, n_labels, lcoff, tjobs, tchild, tcursor, tcount, tlist, 2 * n_slots,
-                                      n_slots, allow_weighted);
+                                      n_slots, allow_weighted, qmode);
     return cudaGetLastError();
 }
 
@@ -1663,7 +1709,7 @@ cudaError_t k3_tree_tables(const JoinView &jv, u32 n_slots, u32 max_class, u32 m
 
 cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
                    const void *init, const u64 *limits, u64 *answers, u32 *items, u64 export_cap, u32 *ready, u32 epoch,
-                   JoinQueue *jq, u32 *matches, u64 matches_cap, u64 *match_cursor, int sm_count, cudaStream_t s) {
+                   JoinQueue *jq, u32 *matches, u64 matches_cap, u64 *match_cursor, u64 *inexact, int sm_count, cudaStream_t s) {
     JoinGraph g = join_graph(jv);
     // stack bytes per thread: M x (8 + 5 x 4); threads per CTA chosen so that ~30 warps fit in an SM's shared memory
 #define LAUNCH(M, T, B)                                                                                                \
@@ -1677,7 +1723,7 @@ cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const Joi
     }                                                                                                                 \
     k3_dfs_kernel<M, T, B><<<sm_count * per_sm_##M##_##B, T, smem_##M##_##B, s>>>(g, q_vbase, jplan, reinterpret_cast<const uint2 *>(kids), cand, \
                                             reinterpret_cast<const uint2 *>(init), limits, answers, items, export_cap, \
-                                            ready, epoch, jq, matches, matches_cap, match_cursor, flags)
+                                            ready, epoch, jq, matches, matches_cap, match_cursor, flags, inexact)
     static int env_tb = -1;
     if (env_tb < 0) { const char *e = getenv("GPE_JOIN_TAILBATCH"); env_tb = e ? atoi(e) : kTailBatch; if (env_tb < 1 || env_tb > 32) env_tb = kTailBatch; }
     static int env_spr = -1;

@@ -135,7 +135,9 @@ int gpe_batch_filter(gpe_ctx *ctx);
 /* Stage 3 (device only): matching orders + join over the start candidates idx % world == rank. */
 int gpe_batch_join(gpe_ctx *ctx, uint32_t rank, uint32_t world);
 /* Stage 4: wait, copy the per-query counts back.  Raw totals (not yet clamped by the limit) so that
- * shards can be summed; gpe_clamp_answer applies the reference's limit rule. */
+ * shards can be summed; gpe_clamp_answer applies the reference's limit rule.  A raw total is exact below 2^44
+ * and saturated (some value in [2^44, 2^48]) beyond: the reference's answer is min(total, limit) with
+ * limit <= UINT_MAX (custom.h:846-855), and every step of the counting join saturates instead of wrapping. */
 int gpe_batch_download(gpe_ctx *ctx, uint64_t *raw_counts /*n_queries*/);
 uint64_t gpe_clamp_answer(uint64_t raw_total, uint64_t limit);
 /* All four stages for one GPU, host buffers in, answers out: the end-to-end call. */
@@ -200,6 +202,8 @@ typedef struct gpe_stats {
     uint64_t join_warp_iters, join_idle_polls;          /* last join: warp loop iterations with / without a busy lane (lane utilisation = steps / (32 x warp_iters)) */
     uint64_t join_bfs;        /* last join ran level-synchronously (counting, no answer limits) instead of depth-first */
     uint64_t join_fallbacks;  /* level-synchronous joins recomputed depth-first because a frontier outgrew its buffer */
+    uint64_t join_reruns;     /* batches some of whose queries were joined a second time with their weighted counted leaves
+                                 walked, because a weighted count met a saturated (>= 2^62) table entry */
 } gpe_stats;
 int gpe_get_stats(gpe_ctx *ctx, gpe_stats *out);
 /* The context's CUDA stream (cudaStream_t) so callers can bracket calls with their own events. */
