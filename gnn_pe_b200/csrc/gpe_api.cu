@@ -59,7 +59,7 @@ GraphView graph_view(const gpe_ctx *c) {
     g.lpos = c->d_lpos.as<u32>();
     g.lclass = c->d_lclass.as<u32>();
     g.lcoff = c->d_lcoff.as<u32>();
-    g.nbrL = c->d_nbrL.as<uint2>();
+    g.nbrG = c->d_nbrG.as<u32>();
     return g;
 }
 
@@ -213,8 +213,8 @@ int compact_candidates(gpe_ctx *c, const u32 *d_all = nullptr, u32 world = 0) {
         GPE_CUDA(c, cudaMemsetAsync(c->d_cand_off.p, 0, sizeof(u64), c->stream));
     } else {
         GPE_CUDA(c, k3_compact(c->d_bitmap.as<u32>(), c->b_words, c->b_chunks_per_slot, c->b_slots,
-                               c->d_chunk_off.as<u64>(), c->d_slot_label.as<u32>(), c->d_lclass.as<u32>(),
-                               c->d_lcoff.as<u32>(), c->n_labels, c->d_cand.as<u32>(), c->d_cand_off.as<u64>(), c->stream));
+                               c->d_chunk_off.as<u64>(), c->d_slot_label.as<u32>(), c->d_lcoff.as<u32>(), c->n_labels,
+                               c->d_cand.as<u32>(), c->d_cand_off.as<u64>(), c->stream));
     }
     c->stats.compact_launches += 3;
     c->stats.kernel_launches += 1 + exclusive_scan_launches(n_chunks + 1) + (n_chunks ? 1 : 0);
@@ -325,18 +325,9 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
     GPE_CUDA(c, c->d_tpool.reserve(2 * std::max<u64>((u64)n_slots * c->max_class, 1) * sizeof(u64)));
     GPE_CUDA(c, cudaMemsetAsync(c->d_tcursor.p, 0, 4 * sizeof(u64), c->stream));
     GPE_CUDA(c, c->d_tlist.reserve(((size_t)kMaxTreeLevels * 2 * std::max<u32>(n_slots, 1) + kMaxTreeLevels) * sizeof(u32)));
-    // Schedule: the depth-first kernel by default.  GPE_JOIN_MODE=bfs selects the level-synchronous schedule (every
-    // candidate of a depth gets a thread of its own) where it applies: counting without any answer limit from the
-    // filter's own candidate sets.  Measured on config 2 it is slower (18.3 against 15.6 ms per batch: both test the same
-    // 172 M candidates at ~10 G/s), so it stays an option with a parity test, not the default.
-    bool use_bfs = !force_dfs && !enumerate && clean_start && nq > 0;
-    for (u32 q = 0; q < nq && use_bfs; q++) use_bfs = c->h_limits[q] >= GPE_LIMIT_MAX;
-    {
-        const char *e = getenv("GPE_JOIN_MODE");
-        use_bfs = use_bfs && e && strcmp(e, "bfs") == 0;
-    }
-    bool allow_weighted = !use_bfs;  // weighted counted leaves: depth-first kernel only
-    if (const char *e = getenv("GPE_JOIN_WEIGHTED")) allow_weighted = allow_weighted && atoi(e) != 0;
+    bool allow_weighted = true;  // counted leaves may carry peeled subtrees
+    if (const char *e = getenv("GPE_JOIN_WEIGHTED")) allow_weighted = atoi(e) != 0;
+    (void)force_dfs;
     u32 *tcount = c->d_tlist.as<u32>(), *tlist = tcount + kMaxTreeLevels;
     GPE_CUDA(c, cudaMemsetAsync(tcount, 0, kMaxTreeLevels * sizeof(u32), c->stream));
     GPE_CUDA(c, k3_order(nq, c->V, c->d_q_vbase.as<u32>(), c->d_q_ebase.as<u32>(), c->d_q_offsets.as<u32>(),
@@ -344,9 +335,11 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
                          c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_item_base.as<u64>(), rank, world,
                          enumerate, clean_start, c->n_labels, c->d_lcoff.as<u32>(), c->d_tjobs.as<TreeJob>(),
                          c->d_tchild.as<u32>(), c->d_tcursor.as<u64>(), tcount, tlist, n_slots, allow_weighted, d_qmode, c->stream));
-    JoinView jv{c->d_label.as<u32>(), c->d_nbrL.as<u32>(), c->d_gtab.as<u32>(), c->V, c->n_labels, c->d_deg.as<u32>(),
-                c->d_lclass.as<u32>(), c->d_lpos.as<u32>(), c->d_lcoff.as<u32>(), c->d_tpool.as<u64>(), c->d_bloom.as<u32>(),
-                c->bloom_bits - 1, c->lpos_packed};
+    // (the kernels that walk read tpool[tree_off + v'] with tree_off = table offset + V - lcoff[label]: pointer shifted by -V;
+    //  k3_tree_tables writes through the unshifted pointer it is given separately)
+    JoinGraph jv{c->V, c->n_labels, c->d_nbrJ.as<u32>(), c->d_gtab.as<unsigned char>(), c->dir_row_bytes, c->wide_adj,
+                 c->wide_dir, c->d_degJ.as<u32>(), c->d_labelJ.as<u32>(), c->d_lcoff.as<u32>(), c->d_lclass.as<u32>(),
+                 c->d_tpool.as<u64>() - c->V, c->d_bloom.as<u64>(), (c->bloom_bits >> 6) - 1};
     u32 tree_launches = 0;
     if (!enumerate && c->b_max_nq >= 2) {
         tree_launches = c->b_max_nq - 1;
@@ -373,35 +366,9 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
     GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
                               c->d_cand.as<u32>(), c->d_item_base.as<u64>(), rank, world, heavy_deg,
                               c->d_qcur.as<u64>(), c->d_init.p, jq, tree_launches > 0, c->sm_count, c->stream));
-    if (use_bfs) {
-        if (c->bfs_cap_e == 0 || c->bfs_max_nq < c->b_max_nq) {
-            size_t free_b = 0, total_b = 0;
-            cudaMemGetInfo(&free_b, &total_b);
-            free_b += c->d_bfs.cap;
-            const u64 budget = std::min<u64>(free_b / 3, 16ull << 30);
-            const u64 per_entry = k3_bfs_bytes(c->b_max_nq, 1, 2) - 4096;  // one entry + two candidate slots
-            u64 cap_e = std::min<u64>(budget / std::max<u64>(per_entry, 1), 128ull << 20);
-            if (const char *e = getenv("GPE_BFS_CAP")) cap_e = std::min<u64>(cap_e, strtoull(e, nullptr, 10));  // tests: force the fallback
-            cap_e = std::max<u64>(cap_e, 1024);
-            GPE_CUDA(c, c->d_bfs.reserve(k3_bfs_bytes(c->b_max_nq, cap_e, 2 * cap_e)));
-            GPE_CUDA(c, c->d_bfs_cnt.reserve(256 * sizeof(u32)));
-            c->bfs_cap_e = cap_e;
-            c->bfs_cap_c = 2 * cap_e;
-            c->bfs_max_nq = c->b_max_nq;
-        }
-        GPE_CUDA(c, cudaMemsetAsync(c->d_bfs_cnt.p, 0, 256 * sizeof(u32), c->stream));
-        GPE_CUDA(c, k3_bfs(jv, c->bfs_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_cand.as<u32>(),
-                           c->d_init.p, jq, answers, c->d_bfs.p, c->bfs_cap_e, c->bfs_cap_c, c->d_bfs_cnt.as<u32>(),
-                           c->b_max_nq, c->sm_count, c->stream));
-        c->stats.kernel_launches += 2 * (c->b_max_nq - 1);
-        c->stats.join_launches += 2 * (c->b_max_nq - 1);
-    } else {
     GPE_CUDA(c, k3_dfs(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_cand.as<u32>(),
                        c->d_init.p, c->d_limits.as<u64>(), answers, c->d_items.as<u32>(), cap, c->d_ready.as<u32>(), epoch,
                        jq, d_matches, matches_cap, c->d_match_cursor.as<u64>(), answers + nq + 8, c->sm_count, c->stream));
-    }
-    c->b_bfs_used = use_bfs;
-    c->stats.join_bfs = use_bfs ? 1 : 0;
     c->stats.kernel_launches += tree_launches;
     c->stats.join_launches += tree_launches;
     c->stats.kernel_launches += 5;
@@ -421,6 +388,20 @@ int read_join_stats(gpe_ctx *c) {
     c->stats.join_steps = h.steps;
     c->stats.join_warp_iters = h.warp_iters;
     c->stats.join_idle_polls = h.idle_polls;
+    return GPE_OK;
+}
+
+// the device's candidate lists hold class-order ids (ascending inside a slot, like the caller's ids: a slot's
+// candidates share a label and class order is by id inside a label); the host gets the caller's ids
+int download_candidates(gpe_ctx *c, u32 *cand) {
+    if (!c->b_n_cand) return GPE_OK;
+    DevBuf tmp;
+    GPE_CUDA(c, tmp.reserve(c->b_n_cand * sizeof(u32)));
+    cudaError_t e = k0_gather(c->b_n_cand, c->d_lclass.as<u32>(), c->d_cand.as<u32>(), tmp.as<u32>(), c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cand, tmp.p, c->b_n_cand * sizeof(u32), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    tmp.release();
+    GPE_CUDA(c, e);
     return GPE_OK;
 }
 
@@ -494,13 +475,13 @@ void gpe_destroy(gpe_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrL, &c->d_gtab, &c->d_lclass, &c->d_lpos, &c->d_lcoff, &c->d_bloom, &c->d_tjobs, &c->d_tchild, &c->d_tpool, &c->d_tcursor, &c->d_tlist, &c->d_qcur, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
+    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrJ, &c->d_gtab, &c->d_offJ, &c->d_degJ, &c->d_labelJ, &c->d_newid, &c->d_nbrG, &c->d_lclass, &c->d_lpos, &c->d_lcoff, &c->d_bloom, &c->d_tjobs, &c->d_tchild, &c->d_tpool, &c->d_tcursor, &c->d_tlist, &c->d_qcur, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
                       &c->d_offr, &c->d_ebase, &c->d_start_rows, &c->d_scan_tmp, &c->d_tiles, &c->d_vids, &c->d_sum_u32, &c->d_sum_f64,
                       &c->d_bucket, &c->d_cursor, &c->d_qblocks, &c->d_qb_t0, &c->d_qb_prefix, &c->d_worklist,
                       &c->d_counters, &c->d_bitmap, &c->d_survivors, &c->d_slot_label, &c->d_chunk_cnt, &c->d_chunk_off, &c->d_cand,
                       &c->d_cand_off, &c->d_q_vbase, &c->d_q_ebase, &c->d_q_offsets, &c->d_q_nbrs, &c->d_q_labels,
                       &c->d_limits, &c->d_order, &c->d_pivot, &c->d_jplan, &c->d_item_base, &c->d_answers,
-                      &c->d_matches, &c->d_match_cursor, &c->d_qmode, &c->d_pge, &c->d_pge_x, &c->d_pge_q, &c->d_bfs, &c->d_bfs_cnt};
+                      &c->d_matches, &c->d_match_cursor, &c->d_qmode, &c->d_pge, &c->d_pge_x, &c->d_pge_q};
     for (DevBuf *b : bufs) b->release();
     c->h_pin.release();
     c->h_pin2.release();
@@ -553,116 +534,95 @@ int gpe_get_stats(gpe_ctx *c, gpe_stats *out) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-int gpe_set_graph(gpe_ctx *c, uint32_t V, const uint32_t *offsets, const uint32_t *nbrs, const uint32_t *labels) {
+int gpe_set_graph(gpe_ctx *c, uint32_t V, const uint32_t *offsets, const uint32_t *nbrs, const uint32_t *labels) try {
     if (!c || !offsets || !labels || (V && !nbrs && offsets[V])) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
     GPE_CUDA(c, cudaSetDevice(c->device));
     if (offsets[0] != 0) return c->fail(GPE_ERR_INVALID, "offsets[0] must be 0");
     const u32 n_adj = offsets[V];
-    std::vector<u32> deg(V);
-    u32 max_label = 0, max_deg = 0;
-    for (u32 v = 0; v < V; v++) {
-        if (offsets[v + 1] < offsets[v]) return c->fail(GPE_ERR_INVALID, "offsets not monotone at vertex %u", v);
-        deg[v] = offsets[v + 1] - offsets[v];
-        max_deg = std::max(max_deg, deg[v]);
-        max_label = std::max(max_label, labels[v]);
-        for (u32 j = offsets[v]; j < offsets[v + 1]; j++) {
-            if (nbrs[j] >= V) return c->fail(GPE_ERR_INVALID, "neighbour id out of range at vertex %u", v);
-            if (nbrs[j] == v) return c->fail(GPE_ERR_INVALID, "self loop at vertex %u (simple graphs only)", v);
-            if (j > offsets[v] && nbrs[j - 1] >= nbrs[j])
-                return c->fail(GPE_ERR_INVALID, "adjacency of vertex %u not strictly ascending (sorted, no duplicate edges)", v);
-        }
-    }
-    if (max_label >= 0x7fffffffu) return c->fail(GPE_ERR_INVALID, "labels must be < 2^31");
-    c->V = V;
-    c->n_adj = n_adj;
-    c->n_labels = V ? max_label + 1 : 0;
-    c->max_degree = max_deg;
+    c->have_graph = c->have_emb = c->have_enum = c->have_table = c->have_pge = false;
+    // the CSR goes to the device as it is; validation, degrees, label classes and the join's copy are built there
     GPE_CUDA(c, c->d_off.reserve(((size_t)V + 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_nbr.reserve(std::max<size_t>(n_adj, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_label.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_deg.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_counters.reserve(8 * sizeof(u64)));
     GPE_CUDA(c, cudaMemcpyAsync(c->d_off.p, offsets, ((size_t)V + 1) * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
     if (n_adj) GPE_CUDA(c, cudaMemcpyAsync(c->d_nbr.p, nbrs, (size_t)n_adj * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
     if (V) GPE_CUDA(c, cudaMemcpyAsync(c->d_label.p, labels, (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
-    if (V) GPE_CUDA(c, cudaMemcpyAsync(c->d_deg.p, deg.data(), (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
-    // label-grouped copy of the adjacency + per-(vertex, label) group starts, for the join: the reference
-    // builds the same structure in Static_Graph::BuildLabelOffset (graph.cpp:126-160) but never uses it.
+    GPE_CUDA(c, k0_validate(V, n_adj, c->d_off.as<u32>(), c->d_nbr.as<u32>(), c->d_label.as<u32>(), c->d_deg.as<u32>(),
+                            c->d_counters.as<u64>(), c->stream));
+    u64 err3[3];
+    GPE_CUDA(c, cudaMemcpyAsync(err3, c->d_counters.p, sizeof err3, cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (err3[0] != ~0ull) {
+        const u32 v = (u32)err3[0];
+        switch (err3[0] >> 32) {
+            case 1: return c->fail(GPE_ERR_INVALID, "offsets not monotone at vertex %u", v);
+            case 2: return c->fail(GPE_ERR_INVALID, "neighbour id out of range at vertex %u", v);
+            case 3: return c->fail(GPE_ERR_INVALID, "self loop at vertex %u (simple graphs only)", v);
+            default: return c->fail(GPE_ERR_INVALID, "adjacency of vertex %u not strictly ascending (sorted, no duplicate edges)", v);
+        }
+    }
+    const u32 max_label = (u32)err3[1], max_deg = (u32)err3[2];
+    // label ids index dense per-label arrays (class offsets, the table's bucket directory, the group directory rows)
+    if (max_label >= (1u << 22))
+        return c->fail(GPE_ERR_UNSUPPORTED, "label id %u: label ids must be below 2^22 (dense per-label tables)", max_label);
+    c->V = V;
+    c->n_adj = n_adj;
+    c->n_labels = V ? max_label + 1 : 0;
+    c->max_degree = max_deg;
+    const u32 nl = c->n_labels;
+    // group directory: one row per vertex with the start of every label group of its adjacency; 16-bit offsets from the
+    // row's base while degrees allow it (46 bytes per vertex at 20 labels instead of 84)
+    c->wide_adj = V > (1u << 24);
+    c->wide_dir = max_deg >= 65536u;
+    c->dir_row_bytes = c->wide_dir ? (nl + 1) * 4 : (4 + (nl + 1) * 2 + 3) / 4 * 4;
+    const u64 dir_bytes = (u64)V * c->dir_row_bytes;
     {
-        const u32 nl = c->n_labels;
-        const u64 gt_entries = (u64)V * (nl + 1);
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        if (gt_entries * sizeof(u32) > free_b / 4)
-            return c->fail(GPE_ERR_UNSUPPORTED, "label directory of %llu entries (V x (labels+1)) does not fit; "
-                                                "a sparse directory is not built yet", (unsigned long long)gt_entries);
-        std::vector<u32> nbrL(std::max<size_t>(n_adj, 1) * 2), gtab(std::max<u64>(gt_entries, 1)), cnt(nl + 1);
-        for (u32 v = 0; v < V; v++) {
-            std::fill(cnt.begin(), cnt.end(), 0u);
-            for (u32 j = offsets[v]; j < offsets[v + 1]; j++) cnt[labels[nbrs[j]]]++;
-            u32 run = offsets[v];
-            u32 *row = &gtab[(u64)v * (nl + 1)];
-            for (u32 l = 0; l < nl; l++) { row[l] = run; run += cnt[l]; cnt[l] = row[l]; }
-            row[nl] = run;
-            for (u32 j = offsets[v]; j < offsets[v + 1]; j++) {  // stable: ids stay ascending inside a group
-                const u32 w = nbrs[j], at = cnt[labels[w]]++;
-                nbrL[2 * (size_t)at] = w;
-                nbrL[2 * (size_t)at + 1] = deg[w];
-            }
-        }
-        // label classes: vertices sorted by (label, id), the position of every vertex inside its class (the index of the
-        // join's per-query-vertex subtree tables), and the class boundaries
-        std::vector<u32> lclass(std::max<size_t>(V, 1)), lpos(std::max<size_t>(V, 1)), lcoff((size_t)nl + 2, 0);
-        for (u32 v = 0; v < V; v++) lcoff[labels[v] + 1]++;
-        c->max_class = 0;
-        for (u32 l = 0; l < nl; l++) {
-            c->max_class = std::max(c->max_class, lcoff[l + 1]);
-            lcoff[l + 1] += lcoff[l];
-        }
-        {
-            std::vector<u32> at(lcoff.begin(), lcoff.end() - 1);
-            for (u32 v = 0; v < V; v++) {
-                const u32 l = labels[v];
-                lpos[v] = at[l] - lcoff[l];
-                lclass[at[l]++] = v;
-            }
-        }
-        // second word of a grouped-adjacency entry: the neighbour's degree saturated at 255 (query degrees are < 64, so
-        // every `degree >= query degree` test is exact) and, above it, the neighbour's position in its label class --
-        // the subtree-table index -- so a candidate test needs no separate lookup of it
-        c->lpos_packed = c->max_class < (1u << 24);
-        if (c->lpos_packed)
-            for (size_t i = 0; i < (size_t)n_adj; i++) {
-                const u32 w = nbrL[2 * i];
-                nbrL[2 * i + 1] = std::min<u32>(deg[w], 255u) | (lpos[w] << 8);
-            }
-        {   // edge filter: 16 bits per undirected edge, two of them set
-            u64 bits = 1024;
-            while (bits < 8ull * n_adj) bits <<= 1;
-            std::vector<u32> words(bits / 32, 0u);
-            k3_bloom_build(V, offsets, nbrs, bits, words.data());
-            c->bloom_bits = bits;
-            GPE_CUDA(c, c->d_bloom.reserve(words.size() * sizeof(u32)));
-            GPE_CUDA(c, cudaMemcpy(c->d_bloom.p, words.data(), words.size() * sizeof(u32), cudaMemcpyHostToDevice));
-        }
-        GPE_CUDA(c, c->d_lclass.reserve(lclass.size() * sizeof(u32)));
-        GPE_CUDA(c, c->d_lpos.reserve(lpos.size() * sizeof(u32)));
-        GPE_CUDA(c, c->d_lcoff.reserve(lcoff.size() * sizeof(u32)));
-        GPE_CUDA(c, cudaMemcpyAsync(c->d_lclass.p, lclass.data(), lclass.size() * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
-        GPE_CUDA(c, cudaMemcpyAsync(c->d_lpos.p, lpos.data(), lpos.size() * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
-        GPE_CUDA(c, cudaMemcpyAsync(c->d_lcoff.p, lcoff.data(), lcoff.size() * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
-        GPE_CUDA(c, c->d_nbrL.reserve(nbrL.size() * sizeof(u32)));
-        GPE_CUDA(c, c->d_gtab.reserve(gtab.size() * sizeof(u32)));
-        GPE_CUDA(c, cudaMemcpyAsync(c->d_nbrL.p, nbrL.data(), nbrL.size() * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
-        GPE_CUDA(c, cudaMemcpyAsync(c->d_gtab.p, gtab.data(), gtab.size() * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
-        GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (dir_bytes > free_b / 3)
+            return c->fail(GPE_ERR_UNSUPPORTED, "group directory of %llu bytes (V x (labels+1) entries) does not fit; "
+                                                "a sparse directory is not built yet", (unsigned long long)dir_bytes);
     }
-    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    GPE_CUDA(c, c->d_lcoff.reserve(((size_t)nl + 2) * sizeof(u32)));
+    GPE_CUDA(c, c->d_lclass.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_lpos.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_newid.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_degJ.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_labelJ.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_offJ.reserve(((size_t)V + 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_nbrJ.reserve(std::max<size_t>(n_adj, 1) * (c->wide_adj ? 8 : 4)));
+    GPE_CUDA(c, c->d_nbrG.reserve(std::max<size_t>(n_adj, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_gtab.reserve(std::max<u64>(dir_bytes, 16)));
+    u64 bits = 1024;  // edge filter: 16 bits per undirected edge, two of them set
+    while (bits < 8ull * n_adj) bits <<= 1;
+    c->bloom_bits = bits;
+    GPE_CUDA(c, c->d_bloom.reserve(bits / 8));
+    DevBuf tmp;
+    u32 *max_class_dev = reinterpret_cast<u32 *>(c->d_counters.as<u64>() + 4);
+    cudaError_t e = k0_build_classes(V, nl, c->d_label.as<u32>(), c->d_deg.as<u32>(), c->d_lcoff.as<u32>(), c->d_lclass.as<u32>(),
+                                     c->d_lpos.as<u32>(), c->d_newid.as<u32>(), c->d_degJ.as<u32>(), c->d_labelJ.as<u32>(),
+                                     c->d_offJ.as<u32>(), max_class_dev, tmp, c->stream);
+    if (e == cudaSuccess)
+        e = k0_build_join_graph(V, n_adj, nl, c->d_off.as<u32>(), c->d_nbr.as<u32>(), c->d_lclass.as<u32>(), c->d_newid.as<u32>(),
+                                c->d_degJ.as<u32>(), c->d_offJ.as<u32>(), c->d_lcoff.as<u32>(), c->wide_adj, c->wide_dir,
+                                c->dir_row_bytes, c->d_nbrJ.as<u32>(), c->d_nbrG.as<u32>(), c->d_gtab.p, c->d_bloom.as<u64>(), bits,
+                                tmp, c->sm_count, c->stream);
+    u32 max_class = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&max_class, max_class_dev, sizeof(u32), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    tmp.release();
+    GPE_CUDA(c, e);
+    c->max_class = max_class;
+    c->stats.kernel_launches += 12;
     c->have_graph = true;
-    c->have_emb = c->have_enum = c->have_table = false;
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_set_graph", ex.what()) : GPE_ERR_INVALID;
 }
 
-int gpe_set_embeddings(gpe_ctx *c, uint32_t e, const double *vde) {
+int gpe_set_embeddings(gpe_ctx *c, uint32_t e, const double *vde) try {
     if (!c || !vde) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
     if (!c->have_graph) return c->fail(GPE_ERR_INVALID, "gpe_set_graph first");
     if (e == 0 || e > (u32)kMaxE) return c->fail(GPE_ERR_UNSUPPORTED, "embedding dimension %u not in 1..%d", e, kMaxE);
@@ -674,11 +634,13 @@ int gpe_set_embeddings(gpe_ctx *c, uint32_t e, const double *vde) {
     c->have_emb = true;
     c->have_table = false;
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_set_embeddings", ex.what()) : GPE_ERR_INVALID;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 int gpe_enumerate(gpe_ctx *c, uint32_t L, const uint32_t *sorted_nodes, const uint32_t *membership, uint32_t p,
-                  uint64_t *rows_per_partition, uint64_t *n_rows) {
+                  uint64_t *rows_per_partition, uint64_t *n_rows) try {
     if (!c || !sorted_nodes || !membership || p == 0) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
     if (!c->have_graph) return c->fail(GPE_ERR_INVALID, "gpe_set_graph first");
     if (L != 3 && L != 4)
@@ -736,17 +698,21 @@ int gpe_enumerate(gpe_ctx *c, uint32_t L, const uint32_t *sorted_nodes, const ui
     c->have_enum = true;
     c->have_table = false;
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_enumerate", ex.what()) : GPE_ERR_INVALID;
 }
 
-int gpe_start_rows(gpe_ctx *c, uint64_t *start_row) {
+int gpe_start_rows(gpe_ctx *c, uint64_t *start_row) try {
     if (!c || !start_row) return GPE_ERR_INVALID;
     if (!c->have_enum) return c->fail(GPE_ERR_INVALID, "gpe_enumerate first");
     GPE_CUDA(c, cudaSetDevice(c->device));
     GPE_CUDA(c, cudaMemcpy(start_row, c->d_start_rows.p, ((size_t)c->V + 1) * sizeof(u64), cudaMemcpyDeviceToHost));
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_start_rows", ex.what()) : GPE_ERR_INVALID;
 }
 
-int gpe_dump_paths(gpe_ctx *c, uint64_t first, uint64_t n, uint32_t *vids) {
+int gpe_dump_paths(gpe_ctx *c, uint64_t first, uint64_t n, uint32_t *vids) try {
     if (!c || (!vids && n)) return GPE_ERR_INVALID;
     if (!c->have_enum) return c->fail(GPE_ERR_INVALID, "gpe_enumerate first");
     if (first + n > c->n_rows) return c->fail(GPE_ERR_INVALID, "rows [%llu,%llu) outside the table of %llu rows",
@@ -767,10 +733,12 @@ int gpe_dump_paths(gpe_ctx *c, uint64_t first, uint64_t n, uint32_t *vids) {
     out.release();
     GPE_CUDA(c, e);
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_dump_paths", ex.what()) : GPE_ERR_INVALID;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-int gpe_build_table(gpe_ctx *c, const uint8_t *part_select, uint64_t *n_table_rows) {
+int gpe_build_table(gpe_ctx *c, const uint8_t *part_select, uint64_t *n_table_rows) try {
     if (!c) return GPE_ERR_INVALID;
     if (!c->have_enum || !c->have_emb) return c->fail(GPE_ERR_INVALID, "gpe_enumerate and gpe_set_embeddings first");
     if (!k2_supported(c->L, c->e))
@@ -856,9 +824,11 @@ int gpe_build_table(gpe_ctx *c, const uint8_t *part_select, uint64_t *n_table_ro
     c->have_table = true;
     if (n_table_rows) *n_table_rows = t.n_rows;
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_build_table", ex.what()) : GPE_ERR_INVALID;
 }
 
-int gpe_dump_table(gpe_ctx *c, uint64_t first, uint64_t n, uint32_t *vids, uint32_t *labels, uint32_t *degs, double *pde) {
+int gpe_dump_table(gpe_ctx *c, uint64_t first, uint64_t n, uint32_t *vids, uint32_t *labels, uint32_t *degs, double *pde) try {
     if (!c) return GPE_ERR_INVALID;
     if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
     if (first + n > c->tv.n_rows) return c->fail(GPE_ERR_INVALID, "row range outside the table");
@@ -882,11 +852,13 @@ int gpe_dump_table(gpe_ctx *c, uint64_t first, uint64_t n, uint32_t *vids, uint3
     dv.release(); dl.release(); dd.release(); dp.release();
     GPE_CUDA(c, e);
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_dump_table", ex.what()) : GPE_ERR_INVALID;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 int gpe_filter(gpe_ctx *c, uint32_t n_qpaths, const uint32_t *q_vids, const uint32_t *q_labels, const uint32_t *q_degs,
-               const double *q_pde, uint32_t nq, uint32_t flags, uint64_t *cand_offsets, uint64_t *survivors) {
+               const double *q_pde, uint32_t nq, uint32_t flags, uint64_t *cand_offsets, uint64_t *survivors) try {
     if (!c) return GPE_ERR_INVALID;
     if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
     if (n_qpaths && (!q_vids || !q_labels || !q_degs || !q_pde)) return c->fail(GPE_ERR_INVALID, "null plan arrays");
@@ -912,14 +884,17 @@ int gpe_filter(gpe_ctx *c, uint32_t n_qpaths, const uint32_t *q_vids, const uint
         GPE_CUDA(c, cudaMemcpyAsync(survivors, c->d_survivors.p, (size_t)n_qpaths * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_filter", ex.what()) : GPE_ERR_INVALID;
 }
 
-int gpe_get_candidates(gpe_ctx *c, uint32_t *cand) {
+int gpe_get_candidates(gpe_ctx *c, uint32_t *cand) try {
     if (!c || !cand) return GPE_ERR_INVALID;
     if (!c->b_filtered) return c->fail(GPE_ERR_INVALID, "no filter result");
     GPE_CUDA(c, cudaSetDevice(c->device));
-    if (c->b_n_cand) GPE_CUDA(c, cudaMemcpy(cand, c->d_cand.p, c->b_n_cand * sizeof(u32), cudaMemcpyDeviceToHost));
-    return GPE_OK;
+    return download_candidates(c, cand);
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_get_candidates", ex.what()) : GPE_ERR_INVALID;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -932,7 +907,7 @@ uint64_t gpe_clamp_answer(uint64_t raw_total, uint64_t limit) {
 
 int gpe_refine(gpe_ctx *c, uint32_t nq, const uint32_t *q_offsets, const uint32_t *q_nbrs, const uint32_t *q_labels,
                const uint64_t *cand_offsets, const uint32_t *cand, uint64_t limit, uint64_t *n_matches,
-               uint32_t *order_out, uint32_t *pivot_out, uint32_t *matches, uint64_t matches_cap) {
+               uint32_t *order_out, uint32_t *pivot_out, uint32_t *matches, uint64_t matches_cap) try {
     if (!c || !q_offsets || !q_labels || !cand_offsets) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
     if (!c->have_graph) return c->fail(GPE_ERR_INVALID, "gpe_set_graph first");
     GPE_CUDA(c, cudaSetDevice(c->device));
@@ -952,7 +927,15 @@ int gpe_refine(gpe_ctx *c, uint32_t nq, const uint32_t *q_offsets, const uint32_
     c->b_cand_clean = false;  // caller-supplied sets: the reference takes them as they are
     GPE_CUDA(c, c->d_cand.reserve(std::max<u64>(total, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_cand_off.reserve(((size_t)nq + 1) * sizeof(u64)));
-    if (total) GPE_CUDA(c, cudaMemcpyAsync(c->d_cand.p, cand, total * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    if (total) {  // the caller's ids -> class order (the join's id space)
+        DevBuf tmp;
+        GPE_CUDA(c, tmp.reserve(total * sizeof(u32)));
+        cudaError_t e = cudaMemcpyAsync(tmp.p, cand, total * sizeof(u32), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = k0_gather(total, c->d_newid.as<u32>(), tmp.as<u32>(), c->d_cand.as<u32>(), c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        tmp.release();
+        GPE_CUDA(c, e);
+    }
     GPE_CUDA(c, cudaMemcpyAsync(c->d_cand_off.p, cand_offsets, ((size_t)nq + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
     u32 *d_matches = nullptr;
     if (matches && matches_cap) {
@@ -975,10 +958,12 @@ int gpe_refine(gpe_ctx *c, uint32_t nq, const uint32_t *q_offsets, const uint32_
     if ((rc = read_join_stats(c))) return rc;
     c->b_filtered = false;
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_refine", ex.what()) : GPE_ERR_INVALID;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-int gpe_batch_upload(gpe_ctx *c, const gpe_batch *b, uint32_t flags) {
+int gpe_batch_upload(gpe_ctx *c, const gpe_batch *b, uint32_t flags) try {
     if (!c || !b || !b->q_vbase || !b->q_ebase || !b->q_offsets || !b->q_labels) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
     if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
     GPE_CUDA(c, cudaSetDevice(c->device));
@@ -1024,6 +1009,8 @@ int gpe_batch_upload(gpe_ctx *c, const gpe_batch *b, uint32_t flags) {
     if (rc) return rc;
     c->b_pge = false;
     return setup_filter(c, qp, b->q_vbase[b->n_queries], flags);
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_batch_upload", ex.what()) : GPE_ERR_INVALID;
 }
 
 int gpe_batch_filter(gpe_ctx *c) {
@@ -1041,7 +1028,7 @@ int gpe_batch_join(gpe_ctx *c, uint32_t rank, uint32_t world) {
     return run_join(c, rank, world, nullptr, 0);
 }
 
-int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) {
+int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) try {
     if (!c || !raw_counts) return GPE_ERR_INVALID;
     if (!c->b_joined) return c->fail(GPE_ERR_INVALID, "gpe_batch_join first");
     GPE_CUDA(c, cudaSetDevice(c->device));
@@ -1056,28 +1043,6 @@ int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) {
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
     // raw counts are exact below 2^44 and saturated beyond (k3_join.cu kSat); capped so that shards can still be summed
     for (size_t q = 0; q < nq; q++) pin[q] = std::min<u64>(pin[q], 1ull << 48);
-    if (c->b_bfs_used) {  // level-synchronous join: did every frontier fit?  (else recompute depth-first, once)
-        u32 cnt[72];
-        GPE_CUDA(c, cudaMemcpyAsync(cnt, c->d_bfs_cnt.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
-        GPE_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (cnt[64]) {
-            c->stats.join_fallbacks++;
-            int rc = run_join(c, c->b_rank, c->b_world, nullptr, 0, /*force_dfs=*/true);
-            if (rc) return rc;
-            return gpe_batch_download(c, raw_counts);
-        }
-        memcpy(raw_counts, pin, (size_t)c->b_nq * sizeof(u64));
-        JoinQueue jq;
-        memcpy(&jq, pin + c->b_nq, sizeof jq);
-        u64 steps;
-        memcpy(&steps, cnt + 66, sizeof steps);
-        c->stats.join_items = jq.n_init;
-        c->stats.join_exports = c->stats.join_donations = c->stats.join_idle_polls = 0;
-        c->stats.join_steps = steps;
-        c->stats.join_warp_iters = (steps + 31) / 32;
-        c->stats.d2h_bytes += (size_t)c->b_nq * sizeof(u64) + sizeof(JoinQueue) + sizeof cnt;
-        return GPE_OK;
-    }
     memcpy(raw_counts, pin, (size_t)c->b_nq * sizeof(u64));
     JoinQueue jq;
     memcpy(&jq, pin + c->b_nq, sizeof jq);
@@ -1110,9 +1075,11 @@ int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) {
     c->stats.join_idle_polls = jq.idle_polls;
     c->stats.d2h_bytes += (size_t)c->b_nq * sizeof(u64) + sizeof(JoinQueue);
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_batch_download", ex.what()) : GPE_ERR_INVALID;
 }
 
-int gpe_query_batch(gpe_ctx *c, const gpe_batch *b, uint32_t flags, uint64_t *answers) {
+int gpe_query_batch(gpe_ctx *c, const gpe_batch *b, uint32_t flags, uint64_t *answers) try {
     if (!c || !answers) return GPE_ERR_INVALID;
     int rc = gpe_batch_upload(c, b, flags);
     if (rc) return rc;
@@ -1121,6 +1088,8 @@ int gpe_query_batch(gpe_ctx *c, const gpe_batch *b, uint32_t flags, uint64_t *an
     if ((rc = gpe_batch_download(c, answers))) return rc;
     for (u32 q = 0; q < b->n_queries; q++) answers[q] = gpe_clamp_answer(answers[q], c->h_limits[q]);
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_query_batch", ex.what()) : GPE_ERR_INVALID;
 }
 
 int gpe_batch_cand_info(gpe_ctx *c, uint64_t *n_slots, uint64_t *n_cand_total) {
@@ -1148,8 +1117,9 @@ int gpe_batch_cand_merge(gpe_ctx *c, uint32_t world, const void *d_counts, const
     GPE_CUDA(c, cudaSetDevice(c->device));
     GPE_CUDA(c, cudaMemsetAsync(c->d_bitmap.p, 0, std::max<u64>((u64)c->b_slots * c->b_words, 1) * sizeof(u32), c->stream));
     GPE_CUDA(c, c->d_chunk_cnt.reserve(std::max<size_t>((size_t)world * c->b_slots, 1) * sizeof(u64)));
-    GPE_CUDA(c, k3_scatter((const u32 *)d_counts, (const u32 *)d_cand, stride, world, c->b_slots, c->d_lpos.as<u32>(),
-                           c->d_bitmap.as<u32>(), c->b_words, c->d_chunk_cnt.as<u64>(), c->stream));
+    GPE_CUDA(c, k3_scatter((const u32 *)d_counts, (const u32 *)d_cand, stride, world, c->b_slots, c->d_slot_label.as<u32>(),
+                           c->d_lcoff.as<u32>(), c->n_labels, c->d_bitmap.as<u32>(), c->b_words, c->d_chunk_cnt.as<u64>(),
+                           c->stream));
     int rc = compact_candidates(c);
     if (rc) return rc;
     c->b_filtered = true;
@@ -1185,13 +1155,15 @@ int gpe_batch_bitmap_merge(gpe_ctx *c, uint32_t world, const void *d_all) {
     return GPE_OK;
 }
 
-int gpe_batch_get_candidates(gpe_ctx *c, uint64_t *cand_offsets, uint32_t *cand) {
+int gpe_batch_get_candidates(gpe_ctx *c, uint64_t *cand_offsets, uint32_t *cand) try {
     if (!c || !cand_offsets) return GPE_ERR_INVALID;
     if (!c->b_filtered) return c->fail(GPE_ERR_INVALID, "no filter result");
     GPE_CUDA(c, cudaSetDevice(c->device));
     GPE_CUDA(c, cudaMemcpy(cand_offsets, c->d_cand_off.p, ((size_t)c->b_slots + 1) * sizeof(u64), cudaMemcpyDeviceToHost));
-    if (cand && c->b_n_cand) GPE_CUDA(c, cudaMemcpy(cand, c->d_cand.p, c->b_n_cand * sizeof(u32), cudaMemcpyDeviceToHost));
+    if (cand) return download_candidates(c, cand);
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_batch_get_candidates", ex.what()) : GPE_ERR_INVALID;
 }
 
 int gpe_batch_get_plan(gpe_ctx *c, uint32_t *order, uint32_t *pivot) {
@@ -1208,7 +1180,7 @@ int gpe_batch_get_plan(gpe_ctx *c, uint32_t *order, uint32_t *pivot) {
 // ---------------------------------------------------------------------------------------------------------------
 // GNN-PGE variant of seam S2 (see k4_pge.cu for its status).  Shares candidate bitmaps, compaction, matching order and
 // join with the path filter; only the table (one row per data vertex) and the scan differ.
-int gpe_pge_build(gpe_ctx *c, uint32_t pl, const double *x) {
+int gpe_pge_build(gpe_ctx *c, uint32_t pl, const double *x) try {
     if (!c || !x) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
     if (!c->have_graph || !c->have_emb) return c->fail(GPE_ERR_INVALID, "gpe_set_graph and gpe_set_embeddings first");
     if (pl < 1 || pl > (u32)kMaxL) return c->fail(GPE_ERR_UNSUPPORTED, "GNN-PGE path groups are built for 1..%d vertices per path", kMaxL);
@@ -1223,9 +1195,11 @@ int gpe_pge_build(gpe_ctx *c, uint32_t pl, const double *x) {
     c->pge_pl = pl;
     c->have_pge = true;
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_pge_build", ex.what()) : GPE_ERR_INVALID;
 }
 
-int gpe_pge_dump_groups(gpe_ctx *c, double *pg, double *plg, uint8_t *has) {
+int gpe_pge_dump_groups(gpe_ctx *c, double *pg, double *plg, uint8_t *has) try {
     if (!c || !pg || !plg || !has) return GPE_ERR_INVALID;
     if (!c->have_pge) return c->fail(GPE_ERR_INVALID, "gpe_pge_build first");
     GPE_CUDA(c, cudaSetDevice(c->device));
@@ -1243,9 +1217,11 @@ int gpe_pge_dump_groups(gpe_ctx *c, double *pg, double *plg, uint8_t *has) {
     a.release(); b.release(); h.release();
     GPE_CUDA(c, e);
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_pge_dump_groups", ex.what()) : GPE_ERR_INVALID;
 }
 
-int gpe_pge_batch_upload(gpe_ctx *c, const gpe_batch *b) {
+int gpe_pge_batch_upload(gpe_ctx *c, const gpe_batch *b) try {
     if (!c || !b || !b->q_vbase || !b->q_ebase || !b->q_offsets || !b->q_labels) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
     if (!c->have_pge) return c->fail(GPE_ERR_INVALID, "gpe_pge_build first");
     GPE_CUDA(c, cudaSetDevice(c->device));
@@ -1323,6 +1299,8 @@ int gpe_pge_batch_upload(gpe_ctx *c, const gpe_batch *b) {
     c->b_pge = true;
     c->stats.n_slots = n_slots;
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_pge_batch_upload", ex.what()) : GPE_ERR_INVALID;
 }
 
 int gpe_pge_batch_filter(gpe_ctx *c) {
@@ -1356,7 +1334,7 @@ int gpe_pge_batch_filter(gpe_ctx *c) {
     return GPE_OK;
 }
 
-int gpe_pge_query_batch(gpe_ctx *c, const gpe_batch *b, uint64_t *answers) {
+int gpe_pge_query_batch(gpe_ctx *c, const gpe_batch *b, uint64_t *answers) try {
     if (!c || !answers) return GPE_ERR_INVALID;
     int rc = gpe_pge_batch_upload(c, b);
     if (rc) return rc;
@@ -1365,6 +1343,8 @@ int gpe_pge_query_batch(gpe_ctx *c, const gpe_batch *b, uint64_t *answers) {
     if ((rc = gpe_batch_download(c, answers))) return rc;
     for (u32 q = 0; q < b->n_queries; q++) answers[q] = gpe_clamp_answer(answers[q], c->h_limits[q]);
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_pge_query_batch", ex.what()) : GPE_ERR_INVALID;
 }
 
 }  // extern "C"

@@ -27,6 +27,7 @@ constexpr int kMaxL = 4;         // path positions supported by the compiled ker
 constexpr int kMaxE = 8;
 constexpr u32 kKeyBudget = 1u << 22;  // max label-sequence buckets of the table directory
 constexpr double kEps = 1e-6;    // custom.h:43
+constexpr int kMaxDevices = 64;  // per-device caches of launch configurations
 
 // Grow-only device buffer.
 struct DevBuf {
@@ -76,8 +77,37 @@ struct GraphView {
     const u32 *lpos;   // V: position of a vertex inside its label class
     const u32 *lclass; // vertices by (label, id)
     const u32 *lcoff;  // labels + 1 class offsets
-    const uint2 *nbrL; // adjacency grouped by neighbour label: (neighbour, degree [| class position << 8]); same offsets as nbr
+    const u32 *nbrG;   // adjacency grouped by neighbour label (ascending id inside a group); same offsets as nbr
 };
+
+// The join's own copy of the data graph, in CLASS ORDER (built on the device by k0_graph.cu): vertex v has the id
+// v' = lcoff[label(v)] + lpos(v).  Sorted by v' an adjacency list is grouped by neighbour label with ids ascending inside
+// every group, and "the i-th vertex of label l" (candidate bitmaps, subtree tables) is v' - lcoff[l] without a lookup.
+struct JoinGraph {
+    u32 V, nl;
+    const u32 *nbrJ;            // adjacency entries, rows by v': narrow u32 (v' | min(degree,255) << 24) or wide uint2
+    const unsigned char *gtab;  // group directory, row v' at gtab + v' * dir_row_bytes: narrow u32 base | u16 rel[nl+1], wide u32 abs[nl+1]
+    u32 dir_row_bytes;
+    bool wide_adj, wide_dir;
+    const u32 *degJ, *labelJ;   // per vertex, class order
+    const u32 *lcoff;           // nl + 1: first v' of every label
+    const u32 *orig;            // v' -> the caller's vertex id (= lclass)
+    const u64 *tpool;           // subtree tables (k3_tree_tables); the walk's view is shifted down by V entries (see k3_order)
+    const u64 *bloom;           // edge filter: two bits per undirected edge, both inside one 64-bit word
+    u64 bloom_word_mask;
+};
+
+// Blocked edge filter hash: both bits of an edge live in ONE 64-bit word (one 8-byte load per test), a handful of
+// 32-bit multiplies (the r01k capture had 16 % of the join's instructions in two 64-bit mixers per test).
+__host__ __device__ __forceinline__ void join_edge_probe(u32 a, u32 b, u64 word_mask, u64 &word, u64 &bits) {
+    const u32 lo = a < b ? a : b, hi = a < b ? b : a;
+    u32 x = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
+    x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
+    u32 y = (lo ^ 0x68E31DA4u) * 0xB5297A4Du + hi * 0x1B56C4E9u;
+    y ^= y >> 16;
+    word = (u64)x & word_mask;
+    bits = (1ull << (y & 63)) | (1ull << (y >> 6 & 63));
+}
 
 // Physical layout of the path table: tile-major blocked structure-of-arrays.
 //   scan tile t (tile_bytes each): labels[L][R] u32 | degs[L][R] u32 | pde[L*e][R] f64
@@ -189,20 +219,19 @@ struct gpe_ctx {
     // graph
     u32 V = 0, n_adj = 0, n_labels = 0, max_degree = 0;
     gpe::DevBuf d_off, d_nbr, d_label, d_deg, d_rank, d_sorted, d_member, d_vde;
-    gpe::DevBuf d_nbrL, d_gtab;  // label-grouped adjacency + group directory (join)
+    gpe::DevBuf d_nbrJ, d_gtab, d_offJ, d_degJ, d_labelJ, d_newid;  // the join's class-ordered copy of the graph (k0_graph.cu)
+    gpe::DevBuf d_nbrG;  // adjacency grouped by neighbour label in the caller's ids (k1 histogram / fill)
     gpe::DevBuf d_lclass, d_lpos, d_lcoff;  // label classes: vertices by (label, id), position in class, class offsets
+    bool wide_adj = false, wide_dir = false;
+    u32 dir_row_bytes = 0;
     gpe::DevBuf d_tjobs, d_tchild, d_tpool, d_tcursor, d_tlist, d_qcur;  // subtree tables of the join (jobs, child lists, value pool, pool cursor)
     u32 max_class = 0;
-    bool lpos_packed = false;
     gpe::DevBuf d_bloom;  // edge filter of the join
     u64 bloom_bits = 0;
     gpe::DevBuf d_pge, d_pge_x, d_pge_q;  // GNN-PGE: path groups of the data vertices, label embeddings, query records
     u32 pge_pl = 0;
     bool have_pge = false, b_pge = false;
-    gpe::DevBuf d_bfs, d_bfs_cnt;  // level-synchronous join: frontiers + counters
-    bool b_bfs_used = false;
-    u64 bfs_cap_e = 0, bfs_cap_c = 0;
-    u32 bfs_max_nq = 0, b_rank = 0, b_world = 1;
+    u32 b_rank = 0, b_world = 1;
     gpe::DevBuf d_items, d_ready, d_jq, d_init, d_kids;  // exported join work items, their publication flags, the queue header, start tickets
     u32 join_epoch = 0;
     u32 b_max_nq = 0;
@@ -269,6 +298,18 @@ namespace gpe {
 cudaError_t exclusive_scan_u64(u64 *d_data, u64 n, DevBuf &tmp, cudaStream_t s);
 u64 exclusive_scan_launches(u64 n);
 
+// K0: device-side construction of what gpe_set_graph derives from the CSR (k0_graph.cu)
+// err3: {smallest (code << 32 | vertex) or ~0, max label, max degree}; codes 1 offsets, 2 id range, 3 self loop, 4 order
+cudaError_t k0_validate(u32 V, u32 n_adj, const u32 *off, const u32 *nbr, const u32 *label, u32 *deg, u64 *err3, cudaStream_t s);
+cudaError_t k0_build_classes(u32 V, u32 n_labels, const u32 *label, const u32 *deg, u32 *lcoff /*n_labels + 2*/, u32 *lclass,
+                             u32 *lpos, u32 *newid, u32 *degJ, u32 *labelJ, u32 *offJ /*V + 1*/, u32 *max_class_dev, DevBuf &tmp,
+                             cudaStream_t s);
+cudaError_t k0_build_join_graph(u32 V, u32 n_adj, u32 n_labels, const u32 *off, const u32 *nbr, const u32 *lclass,
+                                const u32 *newid, const u32 *degJ, const u32 *offJ, const u32 *lcoff, bool wide_adj,
+                                bool wide_dir, u32 dir_row_bytes, u32 *nbrJ, u32 *nbrG, void *gtab, u64 *bloom, u64 bloom_bits,
+                                DevBuf &tmp, int sm_count, cudaStream_t s);
+cudaError_t k0_gather(u64 n, const u32 *map, const u32 *in, u32 *out, cudaStream_t s);  // out[i] = map[in[i]]
+
 // K1
 cudaError_t k1_count(const GraphView &g, u32 L, const u32 *sorted, const u32 *offr, u64 *cnt_r, int sm_count,
                      cudaStream_t s);
@@ -305,11 +346,12 @@ cudaError_t k3_chunk_count(const u32 *bitmap, u64 words_per_slot, u64 chunks_per
 cudaError_t k3_merge_count(const u32 *all, u64 shard_words, u32 world, u32 *bitmap, u64 words_per_slot,
                            u64 chunks_per_slot, u32 n_slots, u64 *chunk_cnt, cudaStream_t s);
 // bit i of slot s stands for vertex lclass[lcoff[slot_label[s]] + i]
+// (candidate lists on the device hold class-order ids: first id of the slot's label + bit position)
 cudaError_t k3_compact(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slot, u32 n_slots, const u64 *chunk_off,
-                       const u32 *slot_label, const u32 *lclass, const u32 *lcoff, u32 n_labels, u32 *cand, u64 *cand_off,
+                       const u32 *slot_label, const u32 *lcoff, u32 n_labels, u32 *cand, u64 *cand_off, cudaStream_t s);
+cudaError_t k3_scatter(const u32 *counts, const u32 *cand, u64 stride, u32 world, u32 n_slots, const u32 *slot_label,
+                       const u32 *lcoff, u32 n_labels, u32 *bitmap, u64 words_per_slot, u64 *prefix_tmp /*world x n_slots*/,
                        cudaStream_t s);
-cudaError_t k3_scatter(const u32 *counts, const u32 *cand, u64 stride, u32 world, u32 n_slots, const u32 *lpos,
-                       u32 *bitmap, u64 words_per_slot, u64 *prefix_tmp /*world x n_slots*/, cudaStream_t s);
 cudaError_t k3_counts_from_offsets(const u64 *cand_off, u32 n_slots, u32 *counts, cudaStream_t s);
 cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebase, const u32 *q_offsets,
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
@@ -319,43 +361,23 @@ cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebas
                      u64 *tcursor, u32 *tcount /*kMaxTreeLevels, zeroed*/, u32 *tlist /*kMaxTreeLevels x 2 n_slots*/, u32 n_slots,
                      bool allow_weighted /*counted leaves may carry peeled subtrees (depth-first kernel only)*/,
                      const u32 *qmode /*per query or null: 0 as usual, 1 no weighted leaves, 2 leave the query out*/, cudaStream_t s);
-// label-grouped adjacency for the join (built on the host in gpe_set_graph)
-struct JoinView {
-    const u32 *label, *nbrL /* (neighbour, degree) pairs */, *gtab;
-    u32 V, nl;
-    const u32 *deg, *lclass, *lpos, *lcoff;
-    const u64 *tpool;
-    const u32 *bloom;
-    u64 bloom_mask;
-    bool lpos_packed;  // nbrL[.].y = min(degree, 255) | class position << 8 (else the plain degree)
-};
-// host: two bits per undirected edge into a table of n_bits (power of two) bits
-void k3_bloom_build(u32 V, const u32 *offsets, const u32 *nbrs, u64 n_bits, u32 *words);
 // tables of the peeled subtrees, levels 1..max_level (one launch each)
 constexpr u32 kMaxTreeLevels = GPE_MAX_QUERY_VERTICES;
-cudaError_t k3_tree_tables(const JoinView &jv, u32 n_slots, u32 max_class, u32 max_level, const TreeJob *tjobs,
+cudaError_t k3_tree_tables(const JoinGraph &jv, u32 n_slots, u32 max_class, u32 max_level, const TreeJob *tjobs,
                            const u32 *tchild, const u32 *tcount, const u32 *tlist, const u32 *bitmap, u64 words_per_slot,
                            u64 *tpool, int sm_count, cudaStream_t s);
 u32 k3_item_stride(u32 max_nq);  // u32 words per exported work item
 // one ticket (query, position in cand[]) per start candidate of this shard; init: 8 bytes per ticket
-cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
+cudaError_t k3_init_items(const JoinGraph &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
                           const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world,
                           u32 heavy_deg /*roots of at least this degree are ticketed first*/, u64 *cursors /*6 per query, zeroed*/,
                           void *init, JoinQueue *jq, bool use_tables /*subtree tables are valid: dead roots get no ticket*/,
                           int sm_count, cudaStream_t s);
 // one persistent launch: every thread runs work items (explicit-stack DFS) and exports subtrees when others starve
-cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
+cudaError_t k3_dfs(const JoinGraph &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
                    const void *init, const u64 *limits, u64 *answers, u32 *items, u64 export_cap, u32 *ready, u32 epoch,
                    JoinQueue *jq, u32 *matches, u64 matches_cap, u64 *match_cursor, u64 *inexact /*per query, zeroed: set when a
                    weighted count met a saturated operand*/, int sm_count, cudaStream_t s);
-
-// level-synchronous join (counting, no answer limits): frontier buffers in `buf` (k3_bfs_bytes), counters = 256 u32, zeroed;
-// counters[64] != 0 afterwards means a frontier outgrew its buffer and the result must be recomputed depth-first;
-// the u64 at counters + 66 counts the candidates tested
-size_t k3_bfs_bytes(u32 max_nq, u64 cap_e, u64 cap_c);
-cudaError_t k3_bfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
-                   const void *init, const JoinQueue *jq, u64 *answers, void *buf, u64 cap_e, u64 cap_c, u32 *counters,
-                   u32 levels, int sm_count, cudaStream_t s);
 
 // K4: GNN-PGE (per-vertex path groups), see k4_pge.cu.  Rows in class order (index = lcoff[label] + lpos), columns by
 // dimension: pg_lo/pg_hi/plg_lo/plg_hi [pde][V], deg [V], has [V].

@@ -11,6 +11,7 @@
 #include <numeric>
 #include <random>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "gpe.h"
@@ -95,13 +96,26 @@ void gen_vde(uint32_t V, const uint32_t *off, const uint32_t *nbr, const uint32_
     }
     uint32_t max_label = 0;
     for (uint32_t v = 0; v < V; v++) max_label = std::max(max_label, labels[v]);
-    std::vector<double> table;
-    std::vector<char> have;
-    if (V && !cache) { table.resize(((size_t)max_label + 1) * e); have.assign((size_t)max_label + 1, 0); }
-    for (uint32_t v = 0; v < V && !cache; v++) {
-        uint32_t lab = labels[v];
-        if (!have[lab]) { label_embedding(lab, e, &table[(size_t)lab * e]); have[lab] = 1; }
-        std::memcpy(x + (size_t)v * e, &table[(size_t)lab * e], sizeof(double) * e);
+    // gen_vde_x accepts any 32-bit label (it only seeds the generator with it): a dense table while the label
+    // alphabet is small, a hash map for sparse huge label ids (never an allocation proportional to the largest id)
+    if (V && !cache && max_label < (1u << 24)) {
+        std::vector<double> table(((size_t)max_label + 1) * e);
+        std::vector<char> have((size_t)max_label + 1, 0);
+        for (uint32_t v = 0; v < V; v++) {
+            uint32_t lab = labels[v];
+            if (!have[lab]) { label_embedding(lab, e, &table[(size_t)lab * e]); have[lab] = 1; }
+            std::memcpy(x + (size_t)v * e, &table[(size_t)lab * e], sizeof(double) * e);
+        }
+    } else if (V && !cache) {
+        std::unordered_map<uint32_t, std::vector<double>> table;
+        for (uint32_t v = 0; v < V; v++) {
+            auto it = table.find(labels[v]);
+            if (it == table.end()) {
+                it = table.emplace(labels[v], std::vector<double>(e)).first;
+                label_embedding(labels[v], e, it->second.data());
+            }
+            std::memcpy(x + (size_t)v * e, it->second.data(), sizeof(double) * e);
+        }
     }
     for (uint32_t v = 0; v < V; v++) {
         double *out = vde + (size_t)v * e;
@@ -258,7 +272,7 @@ static thread_local std::string g_host_err;
 const char *gpe_host_last_error_internal() { return g_host_err.c_str(); }
 
 extern "C" int gpe_host_load_graph(const char *path, uint32_t *V, uint32_t *E, uint32_t *offsets, uint32_t *nbrs,
-                                   uint32_t *labels) {
+                                   uint32_t *labels) try {
     gpe::HostGraph g;
     int rc = gpe::load_graph_file(path, g, g_host_err);
     if (rc) return rc;
@@ -268,18 +282,24 @@ extern "C" int gpe_host_load_graph(const char *path, uint32_t *V, uint32_t *E, u
     if (nbrs) std::copy(g.nbrs.begin(), g.nbrs.end(), nbrs);
     if (labels) std::copy(g.labels.begin(), g.labels.end(), labels);
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    g_host_err = ex.what();
+    return GPE_ERR_INVALID;
 }
 
 extern "C" int gpe_host_gen_vde(uint32_t V, const uint32_t *offsets, const uint32_t *nbrs, const uint32_t *labels,
-                                uint32_t e, double *x, double *vde) {
+                                uint32_t e, double *x, double *vde) try {
     if (!offsets || !labels || !x || !vde || e == 0) return GPE_ERR_INVALID;
     gpe::gen_vde(V, offsets, nbrs, labels, e, x, vde);
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    g_host_err = ex.what();
+    return GPE_ERR_INVALID;
 }
 
 extern "C" int gpe_host_query_plan(uint32_t nq, const uint32_t *q_offsets, const uint32_t *q_nbrs,
                                    const uint32_t *q_labels, uint32_t L, uint32_t e, uint32_t cap, uint32_t *vids,
-                                   uint32_t *labels, uint32_t *degs, double *pde, uint32_t *n) {
+                                   uint32_t *labels, uint32_t *degs, double *pde, uint32_t *n) try {
     if (nq > GPE_MAX_QUERY_VERTICES || L < 2 || L > GPE_MAX_QUERY_VERTICES || e == 0) return GPE_ERR_INVALID;
     gpe::QueryPlan plan;
     gpe::query_plan(nq, q_offsets, q_nbrs, q_labels, L, e, plan);
@@ -290,13 +310,19 @@ extern "C" int gpe_host_query_plan(uint32_t nq, const uint32_t *q_offsets, const
     if (pde) std::copy(plan.pde.begin(), plan.pde.begin() + (size_t)m * L * e, pde);
     if (n) *n = plan.n;
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    g_host_err = ex.what();
+    return GPE_ERR_INVALID;
 }
 
 extern "C" int gpe_host_pge_groups(uint32_t V, const uint32_t *offsets, const uint32_t *nbrs, const uint32_t *labels,
-                                   uint32_t pl, uint32_t e, double *pg, double *plg, uint8_t *has) {
+                                   uint32_t pl, uint32_t e, double *pg, double *plg, uint8_t *has) try {
     if (!offsets || !labels || !pg || !plg || !has || e == 0 || pl == 0 || pl > GPE_MAX_QUERY_VERTICES) return GPE_ERR_INVALID;
     std::vector<double> x((size_t)V * e), vde((size_t)V * e);
     gpe::gen_vde(V, offsets, nbrs, labels, e, x.data(), vde.data());
     gpe::pge_groups(V, offsets, nbrs, pl, e, x.data(), vde.data(), pg, plg, has);
     return GPE_OK;
+} catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
+    g_host_err = ex.what();
+    return GPE_ERR_INVALID;
 }

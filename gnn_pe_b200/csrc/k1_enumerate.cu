@@ -91,7 +91,7 @@ __global__ void scan_apply_kernel(u64 *data, u64 n, const u64 *block_offsets) {
 // ------------------------------------------------------------------------------------------------
 // The walk: one warp, one start vertex `a` (rank ra).  F is a functor with warp-uniform hooks.
 // ------------------------------------------------------------------------------------------------
-// GROUPED: the innermost adjacency list is read in label-grouped order (nbrL) instead of id order.  The set of rows
+// GROUPED: the innermost adjacency list is read in label-grouped order (nbrG) instead of id order.  The set of rows
 // is the same; consecutive lanes then mostly share a label, hence a table bucket, and the fill writes runs of
 // consecutive rows (full sectors) instead of one row per bucket.  Only for the order-insensitive passes (histogram,
 // fill): count and dump reproduce the reference's order and walk by id.
@@ -106,7 +106,7 @@ __device__ __forceinline__ void walk_start_vertex(const GraphView &g, u32 a, u32
             for (u32 j = b0; j < b1; j += 32) {
                 u32 jj = j + lane;
                 bool in = jj < b1;
-                u32 c = in ? (GROUPED ? g.nbrL[jj].x : g.nbr[jj]) : 0u;
+                u32 c = in ? (GROUPED ? g.nbrG[jj] : g.nbr[jj]) : 0u;
                 bool valid = in && g.rank[c] > ra;  // c != a follows from the strict rank test
                 f.chunk(b, c, 0u, valid);
             }
@@ -118,7 +118,7 @@ __device__ __forceinline__ void walk_start_vertex(const GraphView &g, u32 a, u32
                 for (u32 j = c0; j < c1; j += 32) {
                     u32 jj = j + lane;
                     bool in = jj < c1;
-                    u32 d = in ? (GROUPED ? g.nbrL[jj].x : g.nbr[jj]) : 0u;
+                    u32 d = in ? (GROUPED ? g.nbrG[jj] : g.nbr[jj]) : 0u;
                     bool valid = in && d != b && g.rank[d] > ra;  // d != a by rank, d != c: no loops
                     f.chunk(b, c, d, valid);
                 }

@@ -380,10 +380,17 @@ cudaError_t launch_scan_v(const TableView &t, const void *qblocks, const u64 *wo
     using G = ScanGeom<L, E, VIDS>;
     // Staging capacity: what two CTAs per SM leave next to the ring, in whole slots (at most one per (path, position)
     // of a block); when not even one slot fits (huge label classes) the kernel falls back to direct REDs.
-    static int ctas_per_sm = 0;
-    static u64 cfg_words = ~0ull;
-    static u32 stage_words = 0;
-    static size_t smem_bytes = 0;
+    // (cached per device: cudaFuncSetAttribute and the occupancy are per-device properties, and one process may hold
+    //  contexts on several GPUs)
+    struct Cfg { int ctas_per_sm = 0; u64 cfg_words = ~0ull; u32 stage_words = 0; size_t smem_bytes = 0; };
+    static Cfg cfgs[kMaxDevices];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Cfg &cf = cfgs[dev % kMaxDevices];
+    int &ctas_per_sm = cf.ctas_per_sm;
+    u64 &cfg_words = cf.cfg_words;
+    u32 &stage_words = cf.stage_words;
+    size_t &smem_bytes = cf.smem_bytes;
     if (ctas_per_sm == 0 || cfg_words != words_per_slot) {
         stage_words = 0;
         if (VIDS && words_per_slot > 0 && scan_stage_on()) {

@@ -106,7 +106,6 @@ __global__ void __launch_bounds__(256) k3_compact_kernel(const u32 *__restrict__
                                                          u64 chunks_per_slot, u64 n_chunks, u32 n_slots,
                                                          const u64 *__restrict__ chunk_off,
                                                          const u32 *__restrict__ slot_label,
-                                                         const u32 *__restrict__ lclass,
                                                          const u32 *__restrict__ lcoff, u32 n_labels,
                                                          u32 *__restrict__ cand, u64 *__restrict__ cand_off) {
     const int lane = threadIdx.x & 31;
@@ -121,9 +120,9 @@ __global__ void __launch_bounds__(256) k3_compact_kernel(const u32 *__restrict__
     if (chunk_off[w + 1] == out) return;
     const u32 *p = bitmap + slot * words_per_slot + c * kChunkWords;
     u32 vbase = (u32)(c * kChunkWords * 32);
-    // bit -> vertex: positions inside the slot's label class (ascending position = ascending id)
+    // bit -> vertex in class order: first id of the slot's label + the position (ascending position = ascending id)
     const u32 sl = slot_label[slot];
-    const u32 *cls = lclass + (sl < n_labels ? lcoff[sl] : 0);
+    const u32 cls = sl < n_labels ? lcoff[sl] : 0;
     for (int i = 0; i < (int)kChunkWords / 32; i++) {
         u32 word = p[i * 32 + lane];
         u32 n = __popc(word), inc = n;
@@ -137,7 +136,7 @@ __global__ void __launch_bounds__(256) k3_compact_kernel(const u32 *__restrict__
         while (word) {
             int b = __ffs(word) - 1;
             word &= word - 1;
-            cand[my++] = cls[v0 + b];
+            cand[my++] = cls + v0 + b;
         }
         out += __shfl_sync(kFull, inc, 31);
     }
@@ -156,14 +155,17 @@ __global__ void k3_scatter_prefix_kernel(const u32 *__restrict__ counts, u32 wor
 
 __global__ void __launch_bounds__(256) k3_scatter_kernel(const u32 *__restrict__ counts, const u32 *__restrict__ cand,
                                                          const u64 *__restrict__ prefix, u64 stride, u32 world,
-                                                         u32 n_slots, const u32 *__restrict__ lpos, u32 *bitmap,
+                                                         u32 n_slots, const u32 *__restrict__ slot_label,
+                                                         const u32 *__restrict__ lcoff, u32 n_labels, u32 *bitmap,
                                                          u64 words_per_slot) {
     for (u32 job = blockIdx.x; job < world * n_slots; job += gridDim.x) {
         u32 r = job / n_slots, slot = job % n_slots;
         u32 n = counts[(u64)r * n_slots + slot];
         const u32 *list = cand + (u64)r * stride + prefix[(u64)r * n_slots + slot];
+        const u32 sl = slot_label[slot];
+        const u32 first = sl < n_labels ? lcoff[sl] : 0;
         for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
-            u32 v = lpos[list[i]];  // candidates of a slot all carry the slot's label: the bit is the class position
+            u32 v = list[i] - first;  // candidates of a slot all carry the slot's label: the bit is the class position
             atomicOr(bitmap + (u64)slot * words_per_slot + (v >> 5), 1u << (v & 31));
         }
     }
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 const u32 sz = qlab[pv] < n_labels ? lcoff[qlab[pv] + 1] - lcoff[qlab[pv]] : 0;
                 sj.table_off = atomicAdd((unsigned long long *)tcursor, (unsigned long long)sz);
                 tlist[(u64)sj.level * n_slots + atomicAdd(&tcount[sj.level], 1u)] = ji;
-                stab[u] = sj.table_off;
+                stab[u] = sj.table_off + V - (qlab[pv] < n_labels ? lcoff[qlab[pv]] : 0);  // read as tpool[.. + v' of the pivot's image]
             }
             for (u32 u = 0; u < nq; u++) depth_of[u] = 0xffffffffu;
             for (u32 i = 0; i < n_exec; i++) { depth_of[xo[i]] = i; lab[i] = qlab[xo[i]]; }
@@ -429,7 +431,9 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 jd.deg = qdeg(u);
                 jd.pivot_depth = 0;
                 jd.bn_mask = 0;
-                jd.tree_off = tjobs[vb + u].level ? tjobs[vb + u].table_off : kNoTree;
+                // (tables are indexed by class position; the walk holds class-order ids v' = lcoff[label] + position and reads
+                //  tpool[tree_off + v'] from a pool pointer shifted down by V, so the offset stays non-negative)
+                jd.tree_off = tjobs[vb + u].level ? tjobs[vb + u].table_off + V - (qlab[u] < n_labels ? lcoff[qlab[u]] : 0) : kNoTree;
                 jd.tail_mask = 0;
                 jd.tail_k = 0;
                 jd.sure_used = 0;
@@ -562,20 +566,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
 //
 // Edge tests (checkEdgeExistence, graph.h:215-236) are binary searches too, but inside the label group of one
 // endpoint instead of its whole adjacency list: same answer, a fraction of the dependent loads.
-struct JoinGraph {
-    const u32 *label;
-    const uint2 *nbrL;  // adjacency grouped by neighbour label, ascending id inside a group: (neighbour, its degree)
-    const u32 *gtab;    // V x (nl+1): start of every label group of every vertex (absolute, into nbrL)
-    u32 V, nl;
-    const u32 *deg;     // V
-    const u32 *lclass;  // vertices by (label, id)
-    const u32 *lpos;    // position of a vertex inside its label class
-    const u32 *lcoff;   // nl + 1 class offsets into lclass
-    const u64 *tpool;   // subtree tables (k3_tree_tables), indexed [table offset + lpos]
-    const u32 *bloom;   // edge filter: two bits per undirected edge in a table of bloom_mask + 1 bits
-    u64 bloom_mask;
-    bool packed;        // nbrL[.].y = min(degree, 255) | class position << 8
-};
+// (JoinGraph -- the join's copy of the data graph in class order -- is declared in gpe_internal.h and built by k0_graph.cu)
 
 constexpr int kItemHdr = 8;  // q, level, lo, hi, prod (2 words), label of the start vertex, pad; then EMB | S0 | E0
 constexpr u32 kSplit = 8;
@@ -588,42 +579,65 @@ constexpr int kTailBatch = 8;    // parked lanes that trigger a joint evaluation
 
 __host__ __device__ constexpr u32 item_stride(u32 m) { return kItemHdr + 3 * m; }
 
-// gtab rows and binary-search probes are random reads without reuse inside an SM: they go around L1 (ld.global.cg) so
-// that the small, hot join plan stays resident in what the stack leaves of it
+// Directory rows and binary-search probes are random reads without reuse inside an SM: they go around L1
+// (ld.global.cg) so that the small, hot join plan stays resident in what the stack leaves of it.
+struct DirRow {  // the group directory row of one vertex
+    const unsigned char *p;
+    u32 base;  // narrow rows: start of the vertex's adjacency; the row holds 16-bit offsets from it
+};
+__device__ __forceinline__ DirRow dir_row(const JoinGraph &g, u32 v) {
+    DirRow r;
+    r.p = g.gtab + (u64)v * g.dir_row_bytes;
+    r.base = g.wide_dir ? 0u : __ldcg(reinterpret_cast<const u32 *>(r.p));
+    return r;
+}
+__device__ __forceinline__ void row_range(const JoinGraph &g, const DirRow &r, u32 label, u32 &lo, u32 &hi) {
+    if (g.wide_dir) {
+        lo = __ldcg(reinterpret_cast<const u32 *>(r.p) + label);
+        hi = __ldcg(reinterpret_cast<const u32 *>(r.p) + label + 1);
+    } else {
+        const unsigned short *h = reinterpret_cast<const unsigned short *>(r.p + 4) + label;
+        lo = r.base + __ldcg(h);
+        hi = r.base + __ldcg(h + 1);
+    }
+}
 __device__ __forceinline__ void group_range(const JoinGraph &g, u32 v, u32 label, u32 &lo, u32 &hi) {
     if (label >= g.nl) { lo = hi = 0; return; }
-    const u32 *row = g.gtab + (u64)v * (g.nl + 1) + label;
-    lo = __ldcg(row);
-    hi = __ldcg(row + 1);
+    row_range(g, dir_row(g, v), label, lo, hi);
+}
+// adjacency entry: neighbour (class-order id) and its degree saturated at 255 (query degrees are < 64, so every
+// `degree >= query degree` test is exact)
+__device__ __forceinline__ void adj_entry(const JoinGraph &g, u32 at, u32 &c, u32 &cdeg) {
+    if (g.wide_adj) {
+        const uint2 e = reinterpret_cast<const uint2 *>(g.nbrJ)[at];
+        c = e.x;
+        cdeg = e.y;
+    } else {
+        const u32 e = g.nbrJ[at];
+        c = e & 0xffffffu;
+        cdeg = e >> 24;
+    }
+}
+__device__ __forceinline__ u32 adj_id_cg(const JoinGraph &g, u32 at) {
+    return g.wide_adj ? __ldcg(g.nbrJ + 2 * (u64)at) : __ldcg(g.nbrJ + at) & 0xffffffu;
 }
 
 // Edge filter: "no" is exact, "maybe" has to be confirmed by a search.  Most membership / edge tests of the join
-// fail (a prefix vertex is rarely adjacent to the pivot), and a failed test costs two independent loads here
-// instead of a chain of binary-search probes.
-// Blocked: both bits of an edge live in ONE 64-bit word (one 8-byte load per test), and the hash is a handful of
-// 32-bit multiplies -- the r01k capture had 16 % of the kernel's instructions in two 64-bit mixers per test.
-__host__ __device__ __forceinline__ void edge_probe(u32 a, u32 b, u64 word_mask, u64 &word, u64 &bits) {
-    const u32 lo = a < b ? a : b, hi = a < b ? b : a;
-    u32 x = lo * 0x9E3779B1u + hi * 0x85EBCA77u;
-    x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
-    u32 y = (lo ^ 0x68E31DA4u) * 0xB5297A4Du + hi * 0x1B56C4E9u;
-    y ^= y >> 16;
-    word = (u64)x & word_mask;
-    bits = (1ull << (y & 63)) | (1ull << (y >> 6 & 63));
-}
+// fail (a prefix vertex is rarely adjacent to the pivot), and a failed test costs one 8-byte load here instead of a
+// chain of binary-search probes (join_edge_probe, gpe_internal.h: both bits of an edge live in ONE 64-bit word).
 template <bool CG>
 __device__ __forceinline__ bool edge_maybe(const JoinGraph &g, u32 a, u32 b) {
     u64 word, bits;
-    edge_probe(a, b, g.bloom_mask >> 6, word, bits);
-    const u64 *p = reinterpret_cast<const u64 *>(g.bloom) + word;
+    join_edge_probe(a, b, g.bloom_word_mask, word, bits);
+    const u64 *p = g.bloom + word;
     return ((CG ? __ldcg(p) : __ldg(p)) & bits) == bits;  // CG: around L1 (random, no reuse), which holds the plans
 }
 
-// is v a member of the group nbrL[s, e)?  (ids ascending)
+// is v a member of the group [s, e) of the adjacency?  (ids ascending)
 __device__ __forceinline__ bool in_group(const JoinGraph &g, u32 s, u32 e, u32 v) {
     while (s < e) {
         const u32 mid = s + ((e - s) >> 1);
-        const u32 x = __ldcg(&g.nbrL[mid].x);
+        const u32 x = adj_id_cg(g, mid);
         if (x == v) return true;
         if (x < v) s = mid + 1; else e = mid;
     }
@@ -654,9 +668,9 @@ struct RootItem { u32 q, pos; bool heavy, alive; };
 // vertex carries the candidate bitmap -- never gets a ticket: the test runs here, coalesced over the class, instead of
 // costing a ticket claim and a divergent first step in the walk.
 __device__ __forceinline__ RootItem root_item(u64 item, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
-                                              const u64 *cand_off, const u32 *cand, const u32 *lclass, const u32 *deg,
+                                              const u64 *cand_off, const u32 *cand, const u32 *deg /*class order*/,
                                               const u32 *lcoff, u32 n_labels, const u64 *item_base, u32 rank, u32 world,
-                                              u32 heavy_deg, const u32 *lpos, const u64 *tpool) {
+                                              u32 heavy_deg, const u64 *tpool /*shifted by -V*/) {
     u32 lo = 0, hi = n_queries;
     while (hi - lo > 1) {
         u32 mid = (lo + hi) >> 1;
@@ -669,11 +683,11 @@ __device__ __forceinline__ RootItem root_item(u64 item, u32 n_queries, const u32
     const JoinDepth &j0 = jplan[vb];
     const u64 first = j0.tail_mask ? (j0.label < n_labels ? lcoff[j0.label] : 0) : cand_off[vb + j0.u];
     r.pos = (u32)(first + idx);
-    const u32 c = j0.tail_mask ? lclass[r.pos] : cand[r.pos];
+    const u32 c = j0.tail_mask ? r.pos : cand[r.pos];  // a class position IS the class-order id
     const u32 dg = deg[c];
     r.heavy = dg >= heavy_deg;
     r.alive = !j0.tail_mask || dg >= j0.deg;
-    if (r.alive && tpool && j0.tree_off != kNoTree) r.alive = tpool[j0.tree_off + lpos[c]] != 0;
+    if (r.alive && tpool && j0.tree_off != kNoTree) r.alive = tpool[j0.tree_off + c] != 0;
     return r;
 }
 
@@ -683,19 +697,17 @@ __global__ void __launch_bounds__(256) k3_init_count_kernel(u32 n_queries, const
                                                             const JoinDepth *__restrict__ jplan,
                                                             const u64 *__restrict__ cand_off,
                                                             const u32 *__restrict__ cand,
-                                                            const u32 *__restrict__ lclass,
                                                             const u32 *__restrict__ deg,
                                                             const u32 *__restrict__ lcoff, u32 n_labels,
                                                             const u64 *__restrict__ item_base, u32 rank, u32 world,
-                                                            u32 heavy_deg, const u32 *__restrict__ lpos,
-                                                            const u64 *__restrict__ tpool, u64 *qcur) {
+                                                            u32 heavy_deg, const u64 *__restrict__ tpool, u64 *qcur) {
     const u64 n_items = item_base[n_queries], n_round = (n_items + 31) / 32 * 32;
     const int lane = threadIdx.x & 31;
     for (u64 item = (u64)blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += (u64)gridDim.x * blockDim.x) {
         RootItem r{0xffffffffu, 0, false, false};
         if (item < n_items)
-            r = root_item(item, n_queries, q_vbase, jplan, cand_off, cand, lclass, deg, lcoff, n_labels, item_base, rank, world,
-                          heavy_deg, lpos, tpool);
+            r = root_item(item, n_queries, q_vbase, jplan, cand_off, cand, deg, lcoff, n_labels, item_base, rank, world,
+                          heavy_deg, tpool);
         // one atomic per (warp, query, class): consecutive items belong to one query almost always
         const unsigned peers = __match_any_sync(kFull, r.alive ? (r.q << 1 | (r.heavy ? 1u : 0u)) : 0xffffffffu);
         if (r.alive && lane == __ffs(peers) - 1)
@@ -734,20 +746,19 @@ __global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const
                                                             const JoinDepth *__restrict__ jplan,
                                                             const u64 *__restrict__ cand_off,
                                                             const u32 *__restrict__ cand,
-                                                            const u32 *__restrict__ lclass,
                                                             const u32 *__restrict__ deg,
                                                             const u32 *__restrict__ lcoff, u32 n_labels,
                                                             const u64 *__restrict__ item_base, u32 rank, u32 world,
-                                                            u32 heavy_deg, const u32 *__restrict__ lpos,
-                                                            const u64 *__restrict__ tpool, u64 *qcur, uint2 *init) {
+                                                            u32 heavy_deg, const u64 *__restrict__ tpool, u64 *qcur,
+                                                            uint2 *init) {
     const u64 n_items = item_base[n_queries], n_round = (n_items + 31) / 32 * 32;
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
     for (u64 item = (u64)blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += (u64)gridDim.x * blockDim.x) {
         RootItem r{0xffffffffu, 0, false, false};
         if (item < n_items)
-            r = root_item(item, n_queries, q_vbase, jplan, cand_off, cand, lclass, deg, lcoff, n_labels, item_base, rank, world,
-                          heavy_deg, lpos, tpool);
+            r = root_item(item, n_queries, q_vbase, jplan, cand_off, cand, deg, lcoff, n_labels, item_base, rank, world,
+                          heavy_deg, tpool);
         const bool valid = r.alive;
         // one atomic per (warp, query, class)
         const unsigned peers = __match_any_sync(kFull, valid ? (r.q << 1 | (r.heavy ? 1u : 0u)) : 0xffffffffu);
@@ -783,22 +794,24 @@ __global__ void __launch_bounds__(256) k3_tree_tables_kernel(JoinGraph g, const 
     if (job.label >= g.nl) continue;
     const u32 c0 = g.lcoff[job.label], n = g.lcoff[job.label + 1] - c0;
     for (u32 pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
-        const u32 x = g.lclass[c0 + pos];
-        const u32 *row = g.gtab + (u64)x * (g.nl + 1);
+        const DirRow row = dir_row(g, c0 + pos);  // class-order id of the class's pos-th vertex: rows are contiguous
         u64 val = 1;
         for (u32 k = 0; k < job.n_child && val; k++) {
             const TreeJob cj = tjobs[tchild[job.child_begin + k]];
             u64 sum = 0;
             if (cj.label < g.nl) {
-                const u32 s = row[cj.label], e = row[cj.label + 1];
+                u32 s, e;
+                row_range(g, row, cj.label, s, e);
                 if (cj.level == 0 && cj.start_slot == 0xffffffffu) {
                     sum = e - s;  // a plain leaf: every neighbour of the label (its degree is >= 1)
                 } else {
                     const u32 *bm = cj.start_slot == 0xffffffffu ? nullptr : bitmap + (u64)cj.start_slot * words_per_slot;
+                    const u32 cfirst = g.lcoff[cj.label];
                     for (u32 at = s; at < e; at++) {
-                        const uint2 yd = g.nbrL[at];
-                        if ((g.packed ? yd.y & 255u : yd.y) < cj.qdeg) continue;
-                        const u32 yp = g.packed ? yd.y >> 8 : g.lpos[yd.x];
+                        u32 y, ydeg;
+                        adj_entry(g, at, y, ydeg);
+                        if (ydeg < cj.qdeg) continue;
+                        const u32 yp = y - cfirst;
                         if (bm && !(bm[yp >> 5] >> (yp & 31) & 1)) continue;
                         sum = sat_add(sum, cj.level ? tpool[cj.table_off + yp] : 1);
                     }
@@ -1066,22 +1079,19 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             const u32 at = CUR(d);
             CUR(d) = at + 1;
             const JoinDepth *jd = jplan + vb + d;
-            u32 c, cdeg, cpos = 0;
+            u32 c, cdeg;
             if (d == 0) {
                 if (jd->tail_mask) {  // the walk starts from the root's label class (the start vertex was peeled)
-                    c = g.lclass[at];
-                    cdeg = g.deg[c];
+                    c = at;           // a position in the class-ordered vertex list is the id itself
+                    cdeg = g.degJ[c];
                     lab0 = jd->label;
                 } else {  // start candidates are taken as they are (the reference never checks them, custom.h:827-830)
                     c = cand[at];
                     cdeg = 0xffffffffu;
-                    lab0 = g.label[c];
+                    lab0 = g.labelJ[c];
                 }
             } else {
-                const uint2 cd = g.nbrL[at];
-                c = cd.x;
-                cdeg = g.packed ? cd.y & 255u : cd.y;
-                cpos = cd.y >> 8;
+                adj_entry(g, at, c, cdeg);
             }
             // (bit scans -- ffs/popc -- run on the quarter-rate XU pipe, which a first version of this loop saturated:
             //  the masks of the plan are walked with shifts instead)
@@ -1090,8 +1100,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             const u64 tree_off = matches ? kNoTree : jd->tree_off;
             u64 tree_f = 1;
             if (ok && tree_off != kNoTree) {
-                const u32 pos = (g.packed && d) ? cpos : (cgl ? __ldcg(g.lpos + c) : g.lpos[c]);
-                tree_f = __ldcg(g.tpool + tree_off + pos);
+                tree_f = __ldcg(g.tpool + tree_off + c);
                 ok = tree_f != 0;
             }
             // injective: only earlier depths of the same label could collide (k3_order); enumeration mode also walks the
@@ -1099,7 +1108,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             u64 sm = d ? (matches ? (1ull << d) - 1 : jd->tail_mask) : 0;
             for (u32 t = 0; sm; t++, sm >>= 1)
                 if (sm & 1) ok = ok && EMB(t) != c;
-            const u32 *row = g.gtab + (u64)c * (g.nl + 1);
+            const DirRow row = dir_row(g, c);
             u64 bn = d ? jd->bn_mask : 0;
             for (u32 t = 0; ok && bn; t++, bn >>= 1) {  // the other backward neighbours: edge (c, EMB(t)) must exist
                 if (!(bn & 1)) continue;
@@ -1107,7 +1116,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 if (!(cgl ? edge_maybe<true>(g, c, EMB(t)) : edge_maybe<false>(g, c, EMB(t)))) {
                     ok = false;
                 } else if (cdeg <= 64) {  // search c's (short) group of label(EMB(t))
-                    ok = lt_ < g.nl && in_group(g, __ldcg(row + lt_), __ldcg(row + lt_ + 1), EMB(t));
+                    u32 s = 0, e = 0;
+                    if (lt_ < g.nl) row_range(g, row, lt_, s, e);
+                    ok = in_group(g, s, e, EMB(t));
                 } else {           // search EMB(t)'s group of c's label
                     u32 s, e;
                     group_range(g, EMB(t), jd->label, s, e);
@@ -1123,8 +1134,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                     const uint2 k0 = kl[k], k1 = kl[min(k + 1, kn - 1)];  // (depth, label)
                     const u32 i0 = k0.x, l0 = k0.y, i1 = k1.x, l1 = k1.y;
                     u32 a0 = 0, b0 = 0, a1 = 0, b1 = 0;
-                    if (l0 < g.nl) { a0 = __ldcg(row + l0); b0 = __ldcg(row + l0 + 1); }
-                    if (l1 < g.nl) { a1 = __ldcg(row + l1); b1 = __ldcg(row + l1 + 1); }
+                    if (l0 < g.nl) row_range(g, row, l0, a0, b0);
+                    if (l1 < g.nl) row_range(g, row, l1, a1, b1);
                     S0(i0) = a0; E0(i0) = b0;
                     S0(i1) = a1; E0(i1) = b1;
                     if (a0 >= b0 || a1 >= b1) { ok = false; break; }  // nothing to draw from: no match below c
@@ -1160,7 +1171,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                                     in_group(g, s, e, EMB(t))) used++;
                             return (u64)((e - s) - used);
                         }
-                        u64 wsum = __ldcg(g.tpool + lf->units_mask + __ldcg(g.lpos + pvx));
+                        u64 wsum = __ldcg(g.tpool + lf->units_mask + pvx);
                         if (wsum >= kSat) inexact[q] = 1;  // saturated minuend: the difference below is unknown
                         const u64 sure = lf->bn_mask;
                         u64 m = lf->tail_mask | sure;
@@ -1170,18 +1181,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                             const bool in = (sure >> t & 1) ||
                                             ((t != 0 || lab0 == llab) &&
                                              (cgl ? edge_maybe<true>(g, pvx, y) : edge_maybe<false>(g, pvx, y)) && in_group(g, s, e, y));
-                            if (in && g.deg[y] >= lf->deg)
-                                wsum -= lf->tree_off != kNoTree ? __ldcg(g.tpool + lf->tree_off + __ldcg(g.lpos + y)) : 1ull;
+                            if (in && g.degJ[y] >= lf->deg)
+                                wsum -= lf->tree_off != kNoTree ? __ldcg(g.tpool + lf->tree_off + y) : 1ull;
                         }
                         return wsum;
                     };
                     // weight of one group member (entry of nbrL) as image of a counted leaf
-                    auto leaf_weight = [&](const JoinDepth *lf, uint2 ent) -> u64 {
+                    auto leaf_weight = [&](const JoinDepth *lf, u32 id, u32 dg) -> u64 {
                         if (!(lf->tail_k & kTailW)) return 1ull;
-                        const u32 dg = g.packed ? ent.y & 255u : ent.y;
                         if (dg < lf->deg) return 0ull;
                         if (lf->tree_off == kNoTree) return 1ull;
-                        return __ldcg(g.tpool + lf->tree_off + (g.packed ? ent.y >> 8 : __ldcg(g.lpos + ent.x)));
+                        return __ldcg(g.tpool + lf->tree_off + id);
                     };
                     const u32 s = S0(i), e = E0(i);
                     const u64 n_free = leaf_free(ld, s, e);
@@ -1202,14 +1212,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                         u64 inter = 0;
                         u32 x = s, y = s2;
                         while (x < e && y < e2) {
-                            const uint2 ex = g.nbrL[x], ey = g.nbrL[y];
-                            if (ex.x == ey.x) {
+                            u32 idx, dgx, idy, dgy;
+                            adj_entry(g, x, idx, dgx);
+                            adj_entry(g, y, idy, dgy);
+                            if (idx == idy) {
                                 bool is_used = false;
-                                for (u32 t = 0; t <= d; t++) is_used = is_used || EMB(t) == ex.x;
-                                if (!is_used) inter += leaf_weight(ld, ex) * leaf_weight(lb, ey);
+                                for (u32 t = 0; t <= d; t++) is_used = is_used || EMB(t) == idx;
+                                if (!is_used) inter += leaf_weight(ld, idx, dgx) * leaf_weight(lb, idy, dgy);
                                 x++;
                                 y++;
-                            } else if (ex.x < ey.x) {
+                            } else if (idx < idy) {
                                 x++;
                             } else {
                                 y++;
@@ -1238,7 +1250,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                             u64 pos = atomicAdd((unsigned long long *)match_cursor, 1ull);
                             if (pos < matches_cap) {
                                 u32 *out = matches + pos * nq;
-                                for (u32 t = 0; t <= d; t++) out[jplan[vb + t].u] = EMB(t);
+                                for (u32 t = 0; t <= d; t++) out[jplan[vb + t].u] = g.orig[EMB(t)];  // back to the caller's ids
                             }
                         }
                     } else {
@@ -1322,292 +1334,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
 #undef E0
 }
 
-// ---- the level-synchronous join ----------------------------------------------------------------------------------
-//
-// Counting without an answer limit needs no early exit, so the walk can run one depth at a time over ALL partial
-// embeddings of ALL queries instead of one depth-first stack per thread: a frontier entry is (query, matched vertices
-// 0..L, running product); a level turns entries into candidates (one per member of the pivot's label group), tests
-// every candidate with one thread, and appends the survivors as the next frontier.  Same plan, same tests, same
-// counted-tail factors and subtree tables as the depth-first kernel -- only the schedule differs: every thread of the
-// GPU has a candidate of its own, there is no stack, no ticket queue and no work stealing, and the random gathers
-// (adjacency, tables, group directory, edge filter) are in flight by the million instead of one chain per lane.
-// The depth-first kernel remains for answer limits (`-n N` stops early), enumeration (matches wanted), caller-
-// supplied candidate sets, and as the fallback when a frontier outgrows its buffer (overflow flag, checked on download).
-struct BfsView {
-    u32 cap_e, cap_c;     // entries per frontier buffer, candidates per level
-    u32 *fq[2];           // query of every entry (two frontiers: current / next)
-    u64 *fprod[2];        // running product
-    u32 *femb[2];         // matched vertices, [depth][cap_e]
-    u32 *fS, *foff;       // per current entry: start of its candidate group in nbrL, first candidate slot
-    u32 *parent;          // per candidate slot: the entry it extends
-    u32 *n_entries;       // [depth]: entries with depths 0..depth matched
-    unsigned long long *n_cands;  // [depth]: candidates for that depth
-    u32 *overflow;
-    unsigned long long *steps;
-};
-
-// everything a freshly matched depth D decides (emb[D] = c is set): empty label groups for later depths reject it;
-// the counted-tail factors that close at D multiply into p.  Returns the new product (0 = no match below).
-template <int M, int T>
-__device__ u64 bfs_close(const JoinGraph &g, const JoinDepth *plan, const uint2 *kids_q, u32 n_exec, u32 tail_at, u32 D,
-                         const u32 *emb /*[t * T]*/, u32 lab0, u64 p) {
-#define BE(t) emb[(t) * T]
-    const JoinDepth *jd = plan + D;
-    const u32 c = BE(D);
-    const uint2 *kl = kids_q + jd->kid_begin;
-    const u32 *row = g.gtab + (u64)c * (g.nl + 1);
-    for (u32 k = 0; k < jd->kid_count; k++) {
-        const u32 l = kl[k].y;
-        if (l >= g.nl) return 0;
-        if (__ldcg(row + l) >= __ldcg(row + l + 1)) return 0;  // nothing to draw from: no match below c
-    }
-    u64 um = tail_at < n_exec ? jd->units_mask >> tail_at : 0;
-    for (u32 i = tail_at; um && p; i++, um >>= 1) {
-        if (!(um & 1)) continue;
-        const JoinDepth *ld = plan + i;
-        u32 s, e, used = ld->sure_used;
-        group_range(g, BE(ld->pivot_depth), ld->label, s, e);
-        {
-            const u32 llab = ld->label, pvx = BE(ld->pivot_depth);
-            u64 m = ld->tail_mask;
-            for (u32 t = 0; m; t++, m >>= 1)
-                if ((m & 1) && (t != 0 || lab0 == llab) && edge_maybe<true>(g, pvx, BE(t)) && in_group(g, s, e, BE(t))) used++;
-        }
-        const u32 n_free = (e - s) - used;
-        if (ld->tail_k == kTailMul) {
-            u64 f = n_free;
-            u32 n_run = n_free;
-            for (u32 k = i + 1; k < n_exec && plan[k].tail_k == kTailFall; k++) {
-                n_run = n_run ? n_run - 1 : 0;
-                f = sat_mul(f, n_run);
-            }
-            p = sat_mul(p, f);
-        } else {  // kTailPairA: leaf i and leaf i+1, same label, different pivots
-            const JoinDepth *lb = ld + 1;
-            u32 s2, e2, used2 = lb->sure_used;
-            group_range(g, BE(lb->pivot_depth), lb->label, s2, e2);
-            {
-                const u32 llab = lb->label, pvx = BE(lb->pivot_depth);
-                u64 m = lb->tail_mask;
-                for (u32 t = 0; m; t++, m >>= 1)
-                    if ((m & 1) && (t != 0 || lab0 == llab) && edge_maybe<true>(g, pvx, BE(t)) && in_group(g, s2, e2, BE(t))) used2++;
-            }
-            const u32 n_free2 = (e2 - s2) - used2;
-            u64 inter = 0;
-            u32 x = s, y = s2;
-            while (x < e && y < e2) {
-                const u32 vx = __ldcg(&g.nbrL[x].x), vy = __ldcg(&g.nbrL[y].x);
-                if (vx == vy) {
-                    bool is_used = false;
-                    for (u32 t = 0; t <= D; t++) is_used = is_used || BE(t) == vx;
-                    inter += is_used ? 0 : 1;
-                    x++;
-                    y++;
-                } else if (vx < vy) {
-                    x++;
-                } else {
-                    y++;
-                }
-            }
-            p = sat_mul(p, (u64)n_free * n_free2 - inter);
-        }
-    }
-    return p;
-#undef BE
-}
-
-// bank a finished product / append a surviving entry; called by all 32 lanes
-__device__ __forceinline__ void bfs_bank(u64 *answers, u32 q, u64 p, bool fin) {
-    const unsigned m = __ballot_sync(kFull, fin);
-    if (!m) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    const u32 q0 = __shfl_sync(kFull, q, leader);
-    if (__all_sync(kFull, !fin || q == q0)) {
-        u64 v = fin ? p : 0;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v = sat_add(v, __shfl_xor_sync(kFull, v, o));
-        if (lane == leader) flush_answer(answers, q0, v);
-    } else if (fin) {
-        flush_answer(answers, q, p);
-    }
-}
-__device__ __forceinline__ u32 bfs_append_slot(u32 *counter, bool app) {
-    const unsigned m = __ballot_sync(kFull, app);
-    if (!m) return 0xffffffffu;
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    u32 base = 0;
-    if (lane == leader) base = atomicAdd(counter, (u32)__popc(m));
-    base = __shfl_sync(kFull, base, leader);
-    return app ? base + __popc(m & lanemask_lt()) : 0xffffffffu;
-}
-
-// depth 0: one thread per live root (the ticket list of k3_init_items)
-template <int M, int T>
-__global__ void __launch_bounds__(T) k3_bfs_root_kernel(JoinGraph g, BfsView b, const u32 *__restrict__ q_vbase,
-                                                        const JoinDepth *__restrict__ jplan,
-                                                        const uint2 *__restrict__ kids, const u32 *__restrict__ cand,
-                                                        const uint2 *__restrict__ init, const JoinQueue *jq, u64 *answers) {
-    extern __shared__ u32 s_emb[];  // [M][T]
-    u32 *emb = s_emb + threadIdx.x;
-    const u64 n = jq->n_init, n_round = (n + 31) / 32 * 32;
-    u64 my_steps = 0;
-    for (u64 i = (u64)blockIdx.x * T + threadIdx.x; i < n_round; i += (u64)gridDim.x * T) {
-        bool fin = false, app = false;
-        u32 q = 0, c = 0;
-        u64 p = 0;
-        if (i < n) {
-            const uint2 it = init[i];
-            q = it.x;
-            const u32 vb = q_vbase[q];
-            const JoinDepth *plan = jplan + vb;
-            const u32 n_exec = plan->sure_used, tail_at = n_exec - plan->tail_k;
-            c = plan->tail_mask ? g.lclass[it.y] : cand[it.y];
-            my_steps++;
-            u64 tree_f = 1;
-            if (plan->tree_off != kNoTree) tree_f = __ldcg(g.tpool + plan->tree_off + __ldcg(g.lpos + c));
-            if (tree_f) {
-                emb[0] = c;
-                p = bfs_close<M, T>(g, plan, kids + vb, n_exec, tail_at, 0, emb, plan->label, tree_f);
-                fin = p != 0 && tail_at == 1;
-                app = p != 0 && tail_at > 1;
-            }
-        }
-        bfs_bank(answers, q, p, fin);
-        const u32 slot = bfs_append_slot(b.n_entries, app);
-        if (app) {
-            if (slot < b.cap_e) {
-                b.fq[0][slot] = q;
-                b.fprod[0][slot] = p;
-                b.femb[0][slot] = c;
-            } else {
-                *b.overflow = 1;
-            }
-        }
-    }
-    for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(kFull, my_steps, o);
-    if ((threadIdx.x & 31) == 0 && my_steps) atomicAdd(b.steps, (unsigned long long)my_steps);
-}
-
-// entries with depths 0..D-1 matched -> candidate slots for depth D (one per member of the pivot's label group)
-__global__ void __launch_bounds__(256) k3_bfs_count_kernel(JoinGraph g, BfsView b, u32 D, const u32 *__restrict__ q_vbase,
-                                                           const JoinDepth *__restrict__ jplan) {
-    const int cur = (D - 1) & 1, lane = threadIdx.x & 31;
-    if (*b.overflow) return;  // the result is recomputed depth-first anyway
-    const u32 n = min(b.n_entries[D - 1], b.cap_e), n_round = (n + 31) / 32 * 32;
-    for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n_round; e += gridDim.x * blockDim.x) {
-        u32 S = 0, cnt = 0;
-        if (e < n) {
-            const JoinDepth *jd = jplan + q_vbase[b.fq[cur][e]] + D;
-            u32 E;
-            group_range(g, b.femb[cur][(u64)jd->pivot_depth * b.cap_e + e], jd->label, S, E);
-            cnt = E - S;
-        }
-        u32 inc = cnt;  // inclusive warp scan
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u32 t = __shfl_up_sync(kFull, inc, o);
-            if (lane >= o) inc += t;
-        }
-        const u32 total = __shfl_sync(kFull, inc, 31);
-        u64 base = 0;
-        if (lane == 31 && total) base = atomicAdd(&b.n_cands[D], (unsigned long long)total);
-        base = __shfl_sync(kFull, base, 31) + inc - cnt;
-        const bool fits = base + cnt <= b.cap_c;
-        if (e < n) {
-            b.fS[e] = S;
-            b.foff[e] = (u32)base;
-            if (cnt && !fits) *b.overflow = 1;
-        }
-        // parent ids: short groups by their own thread, long ones by the whole warp
-        if (fits && cnt <= 8)
-            for (u32 k = 0; k < cnt; k++) b.parent[(u32)base + k] = e;
-        unsigned big = __ballot_sync(kFull, fits && cnt > 8);
-        while (big) {
-            const int src = __ffs(big) - 1;
-            big &= big - 1;
-            const u32 bb = __shfl_sync(kFull, (u32)base, src), cc = __shfl_sync(kFull, cnt, src), ee = __shfl_sync(kFull, e, src);
-            for (u32 k = lane; k < cc; k += 32) b.parent[bb + k] = ee;
-        }
-    }
-}
-
-// one thread per candidate of depth D
-template <int M, int T>
-__global__ void __launch_bounds__(T) k3_bfs_expand_kernel(JoinGraph g, BfsView b, u32 D, const u32 *__restrict__ q_vbase,
-                                                          const JoinDepth *__restrict__ jplan,
-                                                          const uint2 *__restrict__ kids, u64 *answers) {
-    extern __shared__ u32 s_emb[];  // [M][T]
-    u32 *emb = s_emb + threadIdx.x;
-#define BE(t) emb[(t) * T]
-    const int cur = (D - 1) & 1, nxt = D & 1;
-    if (*b.overflow) return;
-    const u32 n = (u32)min(b.n_cands[D], (unsigned long long)b.cap_c), n_round = (n + 31) / 32 * 32;
-    u64 my_steps = 0;
-    for (u32 sidx = blockIdx.x * T + threadIdx.x; sidx < n_round; sidx += gridDim.x * T) {
-        bool fin = false, app = false;
-        u32 q = 0, c = 0, e = 0;
-        u64 p = 0;
-        if (sidx < n) {
-            e = b.parent[sidx];
-            q = b.fq[cur][e];
-            const u32 vb = q_vbase[q];
-            const JoinDepth *plan = jplan + vb, *jd = plan + D;
-            const u32 n_exec = plan->sure_used, tail_at = n_exec - plan->tail_k, lab0 = plan->label;
-            const uint2 cd = g.nbrL[b.fS[e] + (sidx - b.foff[e])];
-            c = cd.x;
-            const u32 cdeg = g.packed ? cd.y & 255u : cd.y;
-            my_steps++;
-            bool ok = cdeg >= jd->deg;
-            u64 tree_f = 1;
-            if (ok && jd->tree_off != kNoTree) {
-                tree_f = __ldcg(g.tpool + jd->tree_off + (g.packed ? cd.y >> 8 : __ldcg(g.lpos + c)));
-                ok = tree_f != 0;
-            }
-            if (ok) {
-                for (u32 t = 0; t < D; t++) BE(t) = b.femb[cur][(u64)t * b.cap_e + e];
-                u64 sm = jd->tail_mask;  // earlier depths of the same label (k3_order)
-                for (u32 t = 0; sm; t++, sm >>= 1)
-                    if (sm & 1) ok = ok && BE(t) != c;
-                const u32 *row = g.gtab + (u64)c * (g.nl + 1);
-                u64 bn = jd->bn_mask;
-                for (u32 t = 0; ok && bn; t++, bn >>= 1) {  // the other backward neighbours: edge (c, emb[t]) must exist
-                    if (!(bn & 1)) continue;
-                    const u32 lt_ = t ? plan[t].label : lab0;
-                    if (!edge_maybe<true>(g, c, BE(t))) {
-                        ok = false;
-                    } else if (cdeg <= 64) {
-                        ok = lt_ < g.nl && in_group(g, __ldcg(row + lt_), __ldcg(row + lt_ + 1), BE(t));
-                    } else {
-                        u32 s2, e2;
-                        group_range(g, BE(t), jd->label, s2, e2);
-                        ok = in_group(g, s2, e2, c);
-                    }
-                }
-            }
-            if (ok) {
-                BE(D) = c;
-                p = bfs_close<M, T>(g, plan, kids + vb, n_exec, tail_at, D, emb, lab0, sat_mul(b.fprod[cur][e], tree_f));
-                fin = p != 0 && D + 1 == tail_at;
-                app = p != 0 && D + 1 < tail_at;
-            }
-        }
-        bfs_bank(answers, q, p, fin);
-        const u32 slot = bfs_append_slot(&b.n_entries[D], app);
-        if (app) {
-            if (slot < b.cap_e) {
-                b.fq[nxt][slot] = q;
-                b.fprod[nxt][slot] = p;
-                for (u32 t = 0; t <= D; t++) b.femb[nxt][(u64)t * b.cap_e + slot] = BE(t);
-            } else {
-                *b.overflow = 1;
-            }
-        }
-    }
-    for (int o = 16; o; o >>= 1) my_steps += __shfl_xor_sync(kFull, my_steps, o);
-    if ((threadIdx.x & 31) == 0 && my_steps) atomicAdd(b.steps, (unsigned long long)my_steps);
-#undef BE
-}
-
 }  // namespace
 
 cudaError_t k3_chunk_count(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slot, u32 n_slots, u64 *chunk_cnt,
@@ -1629,22 +1355,22 @@ cudaError_t k3_merge_count(const u32 *all, u64 shard_words, u32 world, u32 *bitm
 }
 
 cudaError_t k3_compact(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slot, u32 n_slots, const u64 *chunk_off,
-                       const u32 *slot_label, const u32 *lclass, const u32 *lcoff, u32 n_labels, u32 *cand, u64 *cand_off,
-                       cudaStream_t s) {
+                       const u32 *slot_label, const u32 *lcoff, u32 n_labels, u32 *cand, u64 *cand_off, cudaStream_t s) {
     u64 n_chunks = chunks_per_slot * n_slots;
     if (n_chunks == 0) return cudaSuccess;
     k3_compact_kernel<<<(unsigned)((n_chunks * 32 + 255) / 256), 256, 0, s>>>(bitmap, words_per_slot, chunks_per_slot,
                                                                              n_chunks, n_slots, chunk_off, slot_label,
-                                                                             lclass, lcoff, n_labels, cand, cand_off);
+                                                                             lcoff, n_labels, cand, cand_off);
     return cudaGetLastError();
 }
 
-cudaError_t k3_scatter(const u32 *counts, const u32 *cand, u64 stride, u32 world, u32 n_slots, const u32 *lpos,
-                       u32 *bitmap, u64 words_per_slot, u64 *prefix_tmp, cudaStream_t s) {
+cudaError_t k3_scatter(const u32 *counts, const u32 *cand, u64 stride, u32 world, u32 n_slots, const u32 *slot_label,
+                       const u32 *lcoff, u32 n_labels, u32 *bitmap, u64 words_per_slot, u64 *prefix_tmp, cudaStream_t s) {
     if (world * n_slots == 0) return cudaSuccess;
     k3_scatter_prefix_kernel<<<(world + 31) / 32, 32, 0, s>>>(counts, world, n_slots, prefix_tmp);
     unsigned blocks = std::min<unsigned>(world * n_slots, 148 * 8);
-    k3_scatter_kernel<<<blocks, 256, 0, s>>>(counts, cand, prefix_tmp, stride, world, n_slots, lpos, bitmap, words_per_slot);
+    k3_scatter_kernel<<<blocks, 256, 0, s>>>(counts, cand, prefix_tmp, stride, world, n_slots, slot_label, lcoff, n_labels, bitmap,
+                                             words_per_slot);
     return cudaGetLastError();
 }
 
@@ -1672,30 +1398,24 @@ static u32 join_m(u32 max_nq) { return max_nq <= 8 ? 8 : max_nq <= 16 ? 16 : max
 
 u32 k3_item_stride(u32 max_nq) { return item_stride(join_m(max_nq)); }
 
-static JoinGraph join_graph(const JoinView &jv) {
-    return JoinGraph{jv.label, reinterpret_cast<const uint2 *>(jv.nbrL), jv.gtab, jv.V, jv.nl, jv.deg, jv.lclass, jv.lpos,
-                     jv.lcoff, jv.tpool, jv.bloom, jv.bloom_mask, jv.lpos_packed};
-}
-
-cudaError_t k3_init_items(const JoinView &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
+cudaError_t k3_init_items(const JoinGraph &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
                           const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world, u32 heavy_deg,
                           u64 *cursors, void *init, JoinQueue *jq, bool use_tables, int sm_count, cudaStream_t s) {
     // (enumeration mode walks every vertex and ignores the tables: roots are then only filtered by degree)
     const u64 *tp = use_tables ? jv.tpool : nullptr;
-    k3_init_count_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, cand, jv.lclass, jv.deg, jv.lcoff,
-                                                     jv.nl, item_base, rank, world, heavy_deg, jv.lpos, tp, cursors);
+    k3_init_count_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, cand, jv.degJ, jv.lcoff,
+                                                     jv.nl, item_base, rank, world, heavy_deg, tp, cursors);
     k3_init_prefix_kernel<<<1, 32, 0, s>>>(n_queries, cursors, jq);
-    k3_init_items_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, cand, jv.lclass, jv.deg, jv.lcoff,
-                                                     jv.nl, item_base, rank, world, heavy_deg, jv.lpos, tp, cursors,
+    k3_init_items_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, cand, jv.degJ, jv.lcoff,
+                                                     jv.nl, item_base, rank, world, heavy_deg, tp, cursors,
                                                      reinterpret_cast<uint2 *>(init));
     return cudaGetLastError();
 }
 
-cudaError_t k3_tree_tables(const JoinView &jv, u32 n_slots, u32 max_class, u32 max_level, const TreeJob *tjobs,
+cudaError_t k3_tree_tables(const JoinGraph &g, u32 n_slots, u32 max_class, u32 max_level, const TreeJob *tjobs,
                            const u32 *tchild, const u32 *tcount, const u32 *tlist, const u32 *bitmap, u64 words_per_slot,
                            u64 *tpool, int sm_count, cudaStream_t s) {
     if (n_slots == 0 || max_class == 0) return cudaSuccess;
-    JoinGraph g = join_graph(jv);
     // a level may hold a handful of tables only (chains are peeled one level at a time), so a table gets up to 64
     // blocks of its own; rows of the grid beyond the level's job count exit at once
     const u32 gy = std::min<u32>(n_slots, (u32)sm_count * 2);
@@ -1707,13 +1427,16 @@ cudaError_t k3_tree_tables(const JoinView &jv, u32 n_slots, u32 max_class, u32 m
     return cudaGetLastError();
 }
 
-cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
+cudaError_t k3_dfs(const JoinGraph &g, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
                    const void *init, const u64 *limits, u64 *answers, u32 *items, u64 export_cap, u32 *ready, u32 epoch,
                    JoinQueue *jq, u32 *matches, u64 matches_cap, u64 *match_cursor, u64 *inexact, int sm_count, cudaStream_t s) {
-    JoinGraph g = join_graph(jv);
     // stack bytes per thread: M x (8 + 5 x 4); threads per CTA chosen so that ~30 warps fit in an SM's shared memory
+    // (launch configurations are cached per device: function attributes and occupancy are per-device properties)
+    int dev = 0;
+    cudaGetDevice(&dev);
 #define LAUNCH(M, T, B)                                                                                                \
-    static int per_sm_##M##_##B = 0;                                                                                        \
+    static int per_sm_arr_##M##_##B[kMaxDevices] = {};                                                                      \
+    int &per_sm_##M##_##B = per_sm_arr_##M##_##B[dev % kMaxDevices];                                                        \
     const size_t smem_##M##_##B = (size_t)M * T * 28 + T;                                                                       \
     if (!per_sm_##M##_##B) {                                                                                                \
         cudaFuncSetAttribute(k3_dfs_kernel<M, T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_##M##_##B);        \
@@ -1745,67 +1468,6 @@ cudaError_t k3_dfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const Joi
     else { LAUNCH(64, 128, 1); }
 #undef LAUNCH
     return cudaGetLastError();
-}
-
-// ---- level-synchronous join: buffers carved out of one allocation, 1 + 2 x (levels) launches, no host sync ---------
-size_t k3_bfs_bytes(u32 max_nq, u64 cap_e, u64 cap_c) {
-    const u64 m = join_m(max_nq);
-    return (size_t)(2 * cap_e * (4 + 8 + 4 * m) + cap_e * 8 + cap_c * 4 + 4096);
-}
-
-cudaError_t k3_bfs(const JoinView &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,
-                   const void *init, const JoinQueue *jq, u64 *answers, void *buf, u64 cap_e, u64 cap_c, u32 *counters /*256 u32, zeroed*/,
-                   u32 levels /*depths to run: the batch's largest query*/, int sm_count, cudaStream_t s) {
-    JoinGraph g = join_graph(jv);
-    const u64 m = join_m(max_nq);
-    BfsView b;
-    b.cap_e = (u32)cap_e;
-    b.cap_c = (u32)cap_c;
-    unsigned char *p = reinterpret_cast<unsigned char *>(buf);
-    for (int i = 0; i < 2; i++) { b.fprod[i] = reinterpret_cast<u64 *>(p); p += cap_e * 8; }
-    for (int i = 0; i < 2; i++) { b.fq[i] = reinterpret_cast<u32 *>(p); p += cap_e * 4; }
-    for (int i = 0; i < 2; i++) { b.femb[i] = reinterpret_cast<u32 *>(p); p += cap_e * 4 * m; }
-    b.fS = reinterpret_cast<u32 *>(p); p += cap_e * 4;
-    b.foff = reinterpret_cast<u32 *>(p); p += cap_e * 4;
-    b.parent = reinterpret_cast<u32 *>(p);
-    b.n_entries = counters;
-    b.overflow = counters + 64;
-    b.steps = reinterpret_cast<unsigned long long *>(counters + 66);
-    b.n_cands = reinterpret_cast<unsigned long long *>(counters + 68);
-    const unsigned grid = (unsigned)sm_count * 8;
-#define BFS_LAUNCH(M)                                                                                                         \
-    do {                                                                                                                      \
-        constexpr int T = (M) <= 16 ? 256 : 128;                                                                              \
-        const size_t smem = (size_t)(M) * T * 4;                                                                              \
-        cudaFuncSetAttribute(k3_bfs_root_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
-        cudaFuncSetAttribute(k3_bfs_expand_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
-        k3_bfs_root_kernel<M, T><<<grid, T, smem, s>>>(g, b, q_vbase, jplan, reinterpret_cast<const uint2 *>(kids), cand,     \
-                                                       reinterpret_cast<const uint2 *>(init), jq, answers);                   \
-        for (u32 D = 1; D < levels; D++) {                                                                                    \
-            k3_bfs_count_kernel<<<grid, 256, 0, s>>>(g, b, D, q_vbase, jplan);                                                \
-            k3_bfs_expand_kernel<M, T><<<grid, T, smem, s>>>(g, b, D, q_vbase, jplan, reinterpret_cast<const uint2 *>(kids),  \
-                                                             answers);                                                       \
-        }                                                                                                                     \
-    } while (0)
-    if (m == 8) BFS_LAUNCH(8);
-    else if (m == 16) BFS_LAUNCH(16);
-    else if (m == 32) BFS_LAUNCH(32);
-    else BFS_LAUNCH(64);
-#undef BFS_LAUNCH
-    return cudaGetLastError();
-}
-
-void k3_bloom_build(u32 V, const u32 *offsets, const u32 *nbrs, u64 n_bits /*power of two, >= 64*/, u32 *words) {
-    u64 *w64 = reinterpret_cast<u64 *>(words);
-    const u64 word_mask = (n_bits >> 6) - 1;
-    for (u32 v = 0; v < V; v++)
-        for (u32 j = offsets[v]; j < offsets[v + 1]; j++) {
-            const u32 w = nbrs[j];
-            if (w < v) continue;
-            u64 word, bits;
-            edge_probe(v, w, word_mask, word, bits);
-            w64[word] |= bits;
-        }
 }
 
 }  // namespace gpe

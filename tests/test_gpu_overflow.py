@@ -41,19 +41,22 @@ def test_answer_is_min_of_total_and_limit(name):
 
 def test_small_limit_stops_the_join_early():
     """`-n N` ends the enumeration (custom.h:851-854): far fewer DFS steps than the unlimited run."""
-    gold = load_case("quickstart")
-    g = graph_io.read_graph(gold["data_path"])
-    q = graph_io.read_graph(gold["query_paths_files"][0])
-    sorted_nodes, membership = graph_io.read_membership(gold["membership_path"], g.V)
+    from gnn_pe_b200 import synth
+    g = synth.uniform_graph(3000, 36000, 2, seed=7)
     eng = engine.Engine(0)
     try:
-        eng.offline(g, l=2, e=2, p=5, sorted_nodes=sorted_nodes, membership=membership)
-        assert eng.online(q) == 45426
-        full = eng.ctx.stats()["join_steps"]
-        assert eng.online(q, 10) == 10
+        eng.offline(g, l=2, e=2, p=4)
+        best, full, total = None, 0, 0
+        for q in synth.query_batch(g, 6, 7, seed=8):  # dense 7-vertex queries over 2 labels: cores with repeated labels
+            n = eng.online(q)
+            steps = eng.ctx.stats()["join_steps"]
+            if steps > full:
+                best, full, total = q, steps, n
+        assert full > 200_000 and total > 1000, (full, total)  # the case must be heavy for the comparison to mean something
+        assert eng.online(best, 10) == 10
         limited = eng.ctx.stats()["join_steps"]
         assert limited * 4 < full, (limited, full)
-        # several copies with different limits in one batch do not disturb each other
-        assert eng.online_batch([q, q, q], [5, gpe.LIMIT_MAX, 1000]).tolist() == [5, 45426, 1000]
+        # copies with different limits in one batch do not disturb each other
+        assert eng.online_batch([best, best, best], [5, gpe.LIMIT_MAX, 1000]).tolist() == [5, total, 1000]
     finally:
         eng.close()

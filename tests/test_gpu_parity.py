@@ -473,11 +473,11 @@ def test_factorised_join_equals_reference_enumeration(nl, seed):
     ctx.close()
 
 
-# The level-synchronous schedule of the join (GPE_JOIN_MODE=bfs: counting, no answer limit) against the oracle's
-# enumeration and against the depth-first kernel on the same batch; with a frontier buffer too small for the batch the
-# library must notice, recompute depth-first and still return the same counts.
+# Counted leaves that carry peeled subtrees (weighted sums and pairs, the default) against the same leaves walked
+# (GPE_JOIN_WEIGHTED=0, also what a query falls back to when a weighted count saturates) and against the oracle's
+# enumeration, on one batch of query shapes.
 @pytest.mark.parametrize("nl,seed", [(9, 31), (16, 32)])
-def test_level_synchronous_join_equals_depth_first_and_oracle(nl, seed, monkeypatch):
+def test_weighted_leaves_equal_walked_leaves_and_oracle(nl, seed, monkeypatch):
     from oracle import oracle
     g = synth.chung_lu_graph(1200, 7000, nl, gamma=2.4, degree_cap=60, seed=seed)
     og = oracle.OracleGraph.from_csr(g.offsets, g.nbrs, g.labels)
@@ -499,8 +499,7 @@ def test_level_synchronous_join_equals_depth_first_and_oracle(nl, seed, monkeypa
     assert len(queries) >= 20 and sum(1 for e in expect if e > 0) >= len(expect) // 4
 
     def run(env):
-        for k in ("GPE_JOIN_MODE", "GPE_BFS_CAP"):
-            monkeypatch.delenv(k, raising=False)
+        monkeypatch.delenv("GPE_JOIN_WEIGHTED", raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         ctx = gpe.GpeContext(0)
@@ -515,14 +514,10 @@ def test_level_synchronous_join_equals_depth_first_and_oracle(nl, seed, monkeypa
         ctx.close()
         return ans, st, one
 
-    bfs, st_b, one_b = run({"GPE_JOIN_MODE": "bfs"})
-    assert st_b["join_bfs"] == 1 and st_b["join_fallbacks"] == 0
-    bad = [(i, a, e) for i, (a, e) in enumerate(zip(bfs, expect)) if a != e]
+    weighted, st_w, one_w = run({})
+    bad = [(i, a, e) for i, (a, e) in enumerate(zip(weighted, expect)) if a != e]
     assert not bad, bad
-    assert one_b == expect[::7]
-    dfs, st_d, _ = run({})
-    assert st_d["join_bfs"] == 0 and dfs == expect
-    small, st_s, _ = run({"GPE_JOIN_MODE": "bfs", "GPE_BFS_CAP": "1024"})
-    assert small == expect
-    if nl == 9:  # (with 16 labels no frontier of this batch reaches the 1024-entry floor)
-        assert st_s["join_fallbacks"] >= 1
+    assert one_w == expect[::7]
+    walked, st_d, _ = run({"GPE_JOIN_WEIGHTED": "0"})
+    assert walked == expect
+    assert st_d["join_steps"] >= st_w["join_steps"]  # counting never walks more than walking
