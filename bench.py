@@ -33,24 +33,57 @@ WORKLOADS = {
     "small": dict(kind="chung_lu", V=100_000, E=1_000_000, labels=20, gamma=3.0, cap=1000, seed=2022,
                   l=2, e=2, n_queries=100, q_vertices=8, q_seed=2023, p=8,
                   desc="synthetic power-law 100K v / 1M e / 20 labels, l=2, e=2, 100 random-walk 8-vertex queries"),
+    # BASELINE.json configs[2]: sharded over 2/4/8 GPUs.  Poisson degrees (mean 20): 2.0 B table rows = 144 GB of scan
+    # tiles + 24 GB of ids, i.e. 84 / 42 / 21 GB per GPU at 2 / 4 / 8 (the power-law variant, 5.2 B rows, does not fit 2)
+    "config3": dict(kind="uniform_native", V=10_000_000, E=100_000_000, labels=50, seed=2024,
+                    l=2, e=2, n_queries=100, q_vertices=8, q_seed=2025, p=8, min_gpus=2,
+                    desc="synthetic Poisson-degree 10M v / 100M e / 50 labels, p=8, l=2, e=2, 100 random-walk 8-vertex queries"),
+    # BASELINE.json configs[4]: query-batch throughput on the config 3 graph, n = MAX answers
+    "config5": dict(kind="uniform_native", V=10_000_000, E=100_000_000, labels=50, seed=2024,
+                    l=2, e=2, n_queries=1000, q_vertices=(4, 16), q_mixed=True, q_seed=2026, p=8, min_gpus=2,
+                    desc="synthetic Poisson-degree 10M v / 100M e / 50 labels, p=8, l=2, e=2, 1000 mixed sparse/dense "
+                         "random-walk queries of 4-16 vertices, n=MAX"),
+    # down-scaled copies of configs 3 / 5 (same generator and query mix) for development runs and the CPU tests
+    "config3_small": dict(kind="uniform_native", V=200_000, E=2_000_000, labels=50, seed=2024,
+                          l=2, e=2, n_queries=100, q_vertices=8, q_seed=2025, p=8,
+                          desc="synthetic Poisson-degree 200K v / 2M e / 50 labels, p=8, l=2, e=2, 100 random-walk 8-vertex queries"),
+    "config5_small": dict(kind="uniform_native", V=200_000, E=2_000_000, labels=50, seed=2024,
+                          l=2, e=2, n_queries=200, q_vertices=(4, 16), q_mixed=True, q_seed=2026, p=8,
+                          desc="synthetic Poisson-degree 200K v / 2M e / 50 labels, p=8, l=2, e=2, 200 mixed sparse/dense "
+                               "random-walk queries of 4-16 vertices, n=MAX"),
 }
 
 
+def make_graph(w):
+    from gnn_pe_b200 import synth
+    if w["kind"] == "chung_lu":
+        return synth.chung_lu_graph(w["V"], w["E"], w["labels"], w["gamma"], w["cap"], w["seed"])
+    return synth.uniform_graph_native(w["V"], w["E"], w["labels"], w["seed"])
+
+
+def make_queries(w, g):
+    from gnn_pe_b200 import synth
+    return synth.query_batch(g, w["n_queries"], w["q_vertices"], seed=w["q_seed"], mixed=w.get("q_mixed", False))
+
+
 def load_workload(name, rank=0, world=1, barrier=None):
-    from gnn_pe_b200 import graph_io, synth
+    """Rank 0 generates the graph once and leaves it as raw arrays in shared memory; the other ranks map it."""
+    from gnn_pe_b200 import graph_io
     w = WORKLOADS[name]
-    cache = os.path.join(os.environ.get("GPE_BENCH_CACHE", "/tmp/gpe_bench_cache"), f"{name}.npz")
-    if rank == 0 and not os.path.exists(cache):
-        os.makedirs(os.path.dirname(cache), exist_ok=True)
-        g = synth.chung_lu_graph(w["V"], w["E"], w["labels"], w["gamma"], w["cap"], w["seed"])
-        np.savez(cache + ".tmp.npz", offsets=g.offsets, nbrs=g.nbrs, labels=g.labels)
-        os.replace(cache + ".tmp.npz", cache)
+    graph_key = f"{w['kind']}_{w['V']}_{w['E']}_{w['labels']}_{w['seed']}"
+    base = os.environ.get("GPE_BENCH_CACHE", "/dev/shm/gpe_bench_cache" if os.path.isdir("/dev/shm") else "/tmp/gpe_bench_cache")
+    paths = {k: os.path.join(base, f"{graph_key}.{k}.npy") for k in ("offsets", "nbrs", "labels")}
+    if rank == 0 and not all(os.path.exists(p) for p in paths.values()):
+        os.makedirs(base, exist_ok=True)
+        g = make_graph(w)
+        for k, p in paths.items():
+            np.save(p + ".tmp.npy", getattr(g, k))
+            os.replace(p + ".tmp.npy", p)
     if barrier:
         barrier()
-    z = np.load(cache)
-    g = graph_io.CSRGraph(z["offsets"], z["nbrs"], z["labels"])
-    queries = synth.query_batch(g, w["n_queries"], w["q_vertices"], seed=w["q_seed"])
-    return w, g, queries
+    g = graph_io.CSRGraph(*(np.load(paths[k], mmap_mode="r") for k in ("offsets", "nbrs", "labels")))
+    g = graph_io.CSRGraph(np.ascontiguousarray(g.offsets), np.ascontiguousarray(g.nbrs), np.ascontiguousarray(g.labels))
+    return w, g, make_queries(w, g)
 
 
 def peaks():
@@ -156,6 +189,23 @@ def run_reference(args):
     return 0
 
 
+def expected_answers(name):
+    """Oracle answers of sampled queries (tests/golden/config_answers.json, made by tests/golden/make_config_answers.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "config_answers.json")
+    try:
+        rec = json.load(open(path)).get(name)
+    except Exception:
+        rec = None
+    return {int(k): int(v) for k, v in rec["answers"].items()} if rec else {}
+
+
+def static_json(*parts):
+    try:
+        return json.load(open(os.path.join(ROOT, *parts)))
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,12 +215,13 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("GPE_BENCH_WORKLOAD", "config2"), choices=list(WORKLOADS))
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-streaming", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
+    import torch  # before libgpe: the process then carries ONE NCCL (PyTorch's bundled copy), which libgpe binds at run time
     import torch.distributed as dist
     from gnn_pe_b200 import gpe, graph_io
 
@@ -181,36 +232,65 @@ def main():
         raise SystemExit("bench.py needs a B200: libgpe has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # torch.distributed only carries the control plane (rendezvous, barriers, the max over ranks of the timings);
+        # the data path -- candidate all-gather, count all-reduce -- is NCCL inside libgpe (gpe_comm_init)
+        dist.init_process_group("gloo")
     barrier = (lambda: dist.barrier()) if world > 1 else None
 
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     w, g, queries = load_workload(args.workload, rank, world, barrier)
+    if world < w.get("min_gpus", 1):
+        raise SystemExit(f"workload {args.workload} needs at least {w['min_gpus']} GPUs (table size); got {world}")
     L, e, p = w["l"] + 1, w["e"], max(w["p"], world)
-    from gnn_pe_b200 import sharding
     ctx = gpe.GpeContext(local)
-    eng = sharding.ShardedEngine(ctx, rank, world)
+    nccl_version = 0
+    if world > 1:
+        ids = [gpe.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(rank, world, ids[0])
+        nccl_version = ctx.comm_info()[2]
     t0 = time.time()
     _, vde = gpe.host_gen_vde(g.offsets, g.nbrs, g.labels, e)
     sorted_nodes = graph_io.degree_order(g)
     membership = graph_io.block_membership(g.V, p)
+    t1 = time.time()
+    ctx.set_graph(g.offsets, g.nbrs, g.labels)
+    ctx.sync()
+    t_graph = time.time() - t1
+    ctx.set_embeddings(vde)
     ctx.set_timing(1)
-    n_rows, rows_pp, table_rows = eng.build(g, w["l"], e, p, sorted_nodes, membership, vde)
+    n_rows, rows_pp = ctx.enumerate(L, sorted_nodes, membership, p)
+    table_rows = ctx.build_table_shard()
     st = ctx.stats()
+    row_bytes = st["row_bytes"]
+    peak, peak_src = peaks()
+    # K1 (offline table build) against the HBM roofline, SURVEY.md 8(d): N x (4L + row_bytes) written + the CSR read once
+    k1_bytes = table_rows * (4 * L + row_bytes) + 4 * (g.V + 1 + 2 * g.E + g.V)
     build = dict(enumerate_ms=st["last_enumerate_ms"], build_table_ms=st["last_build_ms"], rows=n_rows,
-                 table_rows_this_rank=table_rows, setup_s=time.time() - t0)
+                 table_rows_this_rank=table_rows, table_gb_this_rank=table_rows * (row_bytes + 4 * L) / 1e9,
+                 set_graph_s=t_graph, setup_s=time.time() - t0,
+                 roofline_k1=dict(bound="hbm", kernels="k1_hist + k1_fill + k1_expand (whole table build)",
+                                  algorithmic_bytes=int(k1_bytes), ms=st["last_build_ms"],
+                                  achieved=k1_bytes / max(st["last_build_ms"], 1e-9) / 1e6, peak=peak, unit="GB/s",
+                                  frac=k1_bytes / max(st["last_build_ms"], 1e-9) / 1e6 / peak,
+                                  note="includes the first-touch cudaMalloc of the table; per-kernel times in profiles/"))
     ctx.set_timing(0)
 
     stream = torch.cuda.ExternalStream(ctx.stream)
     nq = len(queries)
     limits = [gpe.LIMIT_MAX] * nq
-    step_resident = eng.step
-    finish = lambda: eng.finish(limits)
 
     with torch.cuda.stream(stream):
         ctx.batch_upload(queries, limits)
         for _ in range(args.warmup):
-            step_resident()
-        answers = finish()
+            ctx.batch_step()
+        answers = ctx.batch_finish()
         launches0 = ctx.stats()["kernel_launches"]
         ctx.collect_timings()
         ctx.set_timing(2)
@@ -222,31 +302,27 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         for _ in range(args.steps):
-            step_resident()
+            ctx.batch_step()
         ev1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ms = ev0.elapsed_time(ev1)
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
         stages = ctx.collect_timings()
         ctx.set_timing(0)
+        answers2 = ctx.batch_finish()
         st_step = ctx.stats()
         launches = st_step["kernel_launches"] - launches0
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        answers2 = finish()
         assert np.array_equal(answers, answers2)
 
-        # ---- e2e: host buffers in, answers out.  1 GPU: one C-ABI call per step (gpe_query_batch).  N GPUs: the
-        # staged calls with the NCCL exchange between them.  Host planning, H2D and D2H are inside the timed region.
+        # ---- e2e: host buffers in, answers out, every step: host planning, H2D of the batch, kernels, the exchange,
+        # D2H of the answers -- all inside the timed region.  1 GPU: ONE C-ABI call per step (gpe_query_batch).
         def e2e_step():
             if world == 1:
                 return ctx.query_batch(queries, limits)
             ctx.batch_upload(queries, limits)
-            eng.step()
-            return eng.finish(limits)
+            ctx.batch_step()
+            return ctx.batch_finish()
 
         for _ in range(2):
             e2e_step()
@@ -257,24 +333,18 @@ def main():
         for _ in range(args.steps):
             a3 = e2e_step()
         torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t1
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        e2e_s = max_over_ranks(time.perf_counter() - t1)
         assert np.array_equal(a3, answers)
         s3 = ctx.stats()
         e2e = dict(value=nq * args.steps / e2e_s, unit="queries/s", h2d_bytes_per_step=int(s3["h2d_bytes"]),
                    d2h_bytes_per_step=int(s3["d2h_bytes"]), ms_per_step=1000.0 * e2e_s / args.steps,
                    api="gpe_query_batch (host plan + H2D + kernels + D2H)" if world == 1 else
-                       "gpe_batch_upload + filter + NCCL all-gather + merge + join + download + all-reduce")
+                       "gpe_batch_upload + gpe_batch_step (scan, NCCL all-gather, merge, join) + gpe_batch_finish (D2H, NCCL all-reduce)")
         clocks = sampler.stop()
 
-        # ---- streaming pass: pruning off, every row of the table against one query's plan paths ----
+        # ---- streaming pass: pruning off, every row of this rank's table against one query's plan paths ----
         streaming = None
-        peak, peak_src = peaks()
-        row_bytes = st_step["row_bytes"]
-        if world == 1:
+        if not args.no_streaming:
             q0 = queries[0]
             plan = gpe.host_query_plan(q0.offsets, q0.nbrs, q0.labels, L, e)
             ctx.set_timing(1)
@@ -289,45 +359,61 @@ def main():
             sbytes = s["scan_rows"] * row_bytes
             streaming = dict(rows=int(s["scan_rows"]), bytes=int(sbytes), ms_avg=tot_ms / reps, ms_best=best,
                              achieved=sbytes / (tot_ms / reps) / 1e6, unit="GB/s", frac=sbytes / (tot_ms / reps) / 1e6 / peak,
-                             plan_paths=int(len(plan["vids"])))
+                             plan_paths=int(len(plan["vids"])), rank=rank)
 
     scan = stages["scan"]
     scan_ms = scan["ms"] / max(scan["launches"], 1)
     scan_bytes = st_step["scan_rows"] * row_bytes
     achieved = scan_bytes / scan_ms / 1e6 if scan_ms > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "scan_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("in_step_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = dict(bound="hbm", kernel="k2_scan_kernel<3,2> (in-step, pruned work list)", achieved=achieved, peak=peak,
-                    unit="GB/s", frac=achieved / peak, traffic=traffic, peak_source=peak_src,
+    # physical DRAM bytes of the in-step scan launch: from the kept ncu capture of the SAME workload at 1 GPU, else null
+    traffic, traffic_src = None, None
+    tr = static_json("profiles", "scan_traffic.json")
+    if tr and world == 1 and tr.get("workload", "config2") == args.workload:
+        traffic, traffic_src = tr.get("in_step_dram_bytes_per_launch"), "profiles/scan_traffic.json (ncu --set full capture, not re-measured by this run)"
+    roofline = dict(bound="hbm", kernel=f"k2_scan_kernel<{L},{e}> (in-step, label-bucketed work list)", achieved=achieved, peak=peak,
+                    unit="GB/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
                     algorithmic_bytes_per_launch=int(scan_bytes), rows_per_launch=int(st_step["scan_rows"]),
                     row_bytes=int(row_bytes), ms_per_launch=scan_ms,
                     tiles_examined=int(st_step["scan_items"]), tiles_unpruned=int(st_step["scan_items_unpruned"]),
-                    share_of_step=scan["ms"] / ms if ms else None, streaming=streaming,
+                    share_of_step=scan["ms"] / max(stages["scan"]["ms"] + stages["select"]["ms"] + stages["compact"]["ms"] + stages["join"]["ms"], 1e-9),
+                    streaming=streaming, rank=rank,
                     stage_ms_per_step={k: v["ms"] / args.steps for k, v in stages.items()})
+    # the join is latency / divergence bound: candidate tests per second and what the kept ncu capture says about it
+    join_ms = stages["join"]["ms"] / args.steps
+    join = dict(ms_per_step=join_ms, candidate_tests_per_step=int(st_step["join_steps"]),
+                tests_per_s=st_step["join_steps"] / max(join_ms, 1e-9) * 1e3,
+                lane_utilisation=st_step["join_steps"] / max(32 * st_step["join_warp_iters"], 1),
+                exports=int(st_step["join_exports"]), donations=int(st_step["join_donations"]), rank=rank,
+                ncu=static_json("profiles", "join_ncu.json"))
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         r = cpu_reference_leg(w, g, queries, args.cpu_baseline_seconds, threads, expect=answers)
         cpu_baseline = dict(value=r["n"] / r["seconds"], unit="queries/s", cores=threads, kind="port",
+                            what="brute-force CPU port of the leaf compare (custom.h:407-435, all pairs, no index) + the "
+                                 "reference's refinement; the real binary's indexed path is in cpu_baseline_real",
                             sample=f"first {r['n']} of {nq} queries, full data graph, {r['seconds']:.1f} s",
                             parity_with_gpu_answers=r["parity_ok"])
+    if world > 1:
+        dist.barrier()
 
     if rank == 0:
+        exp = expected_answers(args.workload)
+        bad = {i: (int(answers[i]), v) for i, v in exp.items() if i < nq and int(answers[i]) != min(v, gpe.LIMIT_MAX)}
         out = dict(metric="online queries/sec", value=nq * args.steps / (ms / 1000.0), unit="queries/s", n_gpus=world,
                    steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True,
-                   scaling="strong" if world > 1 else "weak", vs_baseline=None, dtype="f64", data="synthetic",
+                   scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
                    config=dict(workload=w["desc"], name=args.workload, partitions=p,
-                               parallelism=f"path table sharded over {world} GPU(s) by partition" if world > 1 else "1 GPU",
+                               parallelism=f"path table sharded over {world} GPU(s) by partition, NCCL inside libgpe" if world > 1 else "1 GPU",
                                l2_policy=f"scan reads {scan_bytes / 1e6:.0f} MB per step from a "
                                          f"{table_rows * (row_bytes + 4 * L) / 1e9:.1f} GB table (> 126 MB L2), no flush"),
-                   gpu_launches=int(launches), clocks=clocks, e2e=e2e, roofline=roofline, cpu_baseline=cpu_baseline,
-                   build=build, answers_checksum=int(answers.sum()), answers_nonzero=int((answers > 0).sum()))
+                   gpu_launches=int(launches), clocks=clocks, e2e=e2e, roofline=roofline, join=join, cpu_baseline=cpu_baseline,
+                   cpu_baseline_real=static_json("profiles", "cpu_baseline_real.json"),
+                   build=build, nccl=dict(version=nccl_version, ranks=world, via="libgpe gpe_comm_init (ncclCommInitRank)") if world > 1 else None,
+                   answers_checksum=int(answers.sum()), answers_nonzero=int((answers > 0).sum()),
+                   oracle_parity=dict(checked=len([i for i in exp if i < nq]), mismatches=bad, ok=not bad,
+                                      source="tests/golden/config_answers.json (oracle.online_streaming on the CPU)"))
         print(json.dumps(out))
     ctx.close()
     if world > 1:

@@ -6,6 +6,7 @@
 #include <thread>
 
 #include "gpe_internal.h"
+#include "gpe_nccl.h"
 #include "host_ref.h"
 
 using namespace gpe;
@@ -85,6 +86,7 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
     c->b_flags = flags;
     c->b_slots = n_slots;
     c->b_qpaths = n;
+    std::vector<u32> slot_label_host;
 
     // group plan paths into blocks of <= kQB that read the same tiles
     std::vector<u32> order(n);
@@ -147,8 +149,7 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
         for (u32 i = 0; i < n; i++)
             for (u32 k = 0; k < L; k++) slot_label[qp.slots[(size_t)i * L + k]] = qp.labels[(size_t)i * L + k];
         GPE_CUDA(c, c->d_slot_label.reserve(slot_label.size() * sizeof(u32)));
-        GPE_CUDA(c, cudaMemcpyAsync(c->d_slot_label.p, slot_label.data(), slot_label.size() * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
-        GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+        slot_label_host.swap(slot_label);
     }
     c->b_chunks_per_slot = c->b_words / kChunkWords;
 
@@ -160,12 +161,16 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
     GPE_CUDA(c, c->d_survivors.reserve(std::max<u32>(n, 1) * sizeof(u64)));
     GPE_CUDA(c, c->d_bitmap.reserve(std::max<u64>((u64)n_slots * c->b_words, 1) * sizeof(u32)));
     // stage through pinned memory so the copies are asynchronous
-    size_t need = recs.size() + (nb + 1) * sizeof(u32) + (nb + 1) * sizeof(u64) + 64;
-    GPE_CUDA(c, c->h_pin.reserve(need));
-    unsigned char *pin = c->h_pin.as<unsigned char>();
+    const size_t sl_bytes = slot_label_host.size() * sizeof(u32);
     size_t o_rec = 0, o_t0 = (recs.size() + 15) / 16 * 16, o_pf = (o_t0 + (nb + 1) * sizeof(u32) + 15) / 16 * 16;
-    GPE_CUDA(c, c->h_pin.reserve(o_pf + (nb + 1) * sizeof(u64)));
-    pin = c->h_pin.as<unsigned char>();
+    const size_t o_sl = (o_pf + (nb + 1) * sizeof(u64) + 15) / 16 * 16;
+    if (c->h_pin.cap < o_sl + sl_bytes) {  // (growing frees the old block: wait for copies still reading it)
+        GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+        GPE_CUDA(c, c->h_pin.reserve(o_sl + sl_bytes));
+    }
+    unsigned char *pin = c->h_pin.as<unsigned char>();
+    memcpy(pin + o_sl, slot_label_host.data(), sl_bytes);
+    GPE_CUDA(c, cudaMemcpyAsync(c->d_slot_label.p, pin + o_sl, sl_bytes, cudaMemcpyHostToDevice, c->stream));
     memcpy(pin + o_rec, recs.data(), recs.size());
     memcpy(pin + o_t0, t0.data(), (nb + 1) * sizeof(u32));
     memcpy(pin + o_pf, prefix.data(), (nb + 1) * sizeof(u64));
@@ -173,7 +178,8 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
         GPE_CUDA(c, cudaMemcpyAsync(c->d_qblocks.p, pin + o_rec, recs.size(), cudaMemcpyHostToDevice, c->stream));
     GPE_CUDA(c, cudaMemcpyAsync(c->d_qb_t0.p, pin + o_t0, (nb + 1) * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
     GPE_CUDA(c, cudaMemcpyAsync(c->d_qb_prefix.p, pin + o_pf, (nb + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-    c->stats.h2d_bytes += recs.size() + (nb + 1) * (sizeof(u32) + sizeof(u64));
+    c->stats.h2d_bytes += recs.size() + (nb + 1) * (sizeof(u32) + sizeof(u64)) + sl_bytes;
+    GPE_CUDA(c, cudaEventRecord(c->ev_upload, c->stream));  // the staging block may be overwritten once this has passed
     c->b_scanned = false;
     c->b_filtered = false;
     c->b_joined = false;
@@ -184,8 +190,12 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
     return GPE_OK;
 }
 
-// bitmap -> sorted candidate lists (d_cand, d_cand_off); one host sync for the total.  With d_all != null the bitmaps
-// are first replaced by the union of `world` all-gathered shard bitmaps (same kernel as the popcount pass).
+// bitmap -> sorted candidate lists (d_cand, d_cand_off), entirely on the stream: NO host sync.  The total is only known on
+// the device, so d_cand is sized from what earlier batches needed (or a bound); the expand kernel drops what does not fit
+// and raises a flag that gpe_batch_download / cand_total() check once the stream has been waited for anyway -- the step
+// is then redone with the right size (first batches only).  With d_all != null the bitmaps are first replaced by the
+// union of `world` all-gathered shard bitmaps (same kernel as the popcount pass).
+// pinned h_pin3: [0] candidate total, [1..2] scan counters, [3] overflow flag -- valid after the next stream sync.
 int compact_candidates(gpe_ctx *c, const u32 *d_all = nullptr, u32 world = 0) {
     StageTimer tm(c, &c->stats.last_compact_ms, kStageCompact);
     const u64 n_chunks = c->b_chunks_per_slot * c->b_slots;
@@ -199,27 +209,76 @@ int compact_candidates(gpe_ctx *c, const u32 *d_all = nullptr, u32 world = 0) {
         GPE_CUDA(c, k3_chunk_count(c->d_bitmap.as<u32>(), c->b_words, c->b_chunks_per_slot, c->b_slots,
                                    c->d_chunk_off.as<u64>(), c->stream));
     GPE_CUDA(c, exclusive_scan_u64(c->d_chunk_off.as<u64>(), n_chunks + 1, c->d_scan_tmp, c->stream));
-    GPE_CUDA(c, c->h_pin2.reserve(16 * sizeof(u64)));
-    u64 *pin = c->h_pin2.as<u64>();
-    GPE_CUDA(c, cudaMemcpyAsync(pin, c->d_chunk_off.as<u64>() + n_chunks, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-    GPE_CUDA(c, cudaMemcpyAsync(pin + 1, c->d_counters.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->b_n_cand = pin[0];
-    c->stats.n_candidates = pin[0];
-    c->stats.scan_items = pin[1];
-    c->stats.scan_rows = pin[1] * kTileRows;
-    GPE_CUDA(c, c->d_cand.reserve(std::max<u64>(c->b_n_cand, 1) * sizeof(u32)));
+    // capacity: twice the largest total seen so far, at least 4 M entries, never more than every slot's whole class
+    const u64 bound = std::max<u64>((u64)c->b_slots * c->max_class, 1);
+    const u64 want = std::min<u64>(bound, std::max<u64>(2 * c->cand_seen_max, 4ull << 20));
+    if (c->d_cand.cap / sizeof(u32) < want) GPE_CUDA(c, c->d_cand.reserve(want * sizeof(u32)));
+    c->b_cand_cap = c->d_cand.cap / sizeof(u32);
+    if (const char *e = getenv("GPE_CAND_CAP")) c->b_cand_cap = std::min<u64>(c->b_cand_cap, strtoull(e, nullptr, 10));  // tests: force the repair path
+    u64 *flag = c->d_counters.as<u64>() + 5;
+    GPE_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(u64), c->stream));
     if (n_chunks == 0) {
         GPE_CUDA(c, cudaMemsetAsync(c->d_cand_off.p, 0, sizeof(u64), c->stream));
     } else {
         GPE_CUDA(c, k3_compact(c->d_bitmap.as<u32>(), c->b_words, c->b_chunks_per_slot, c->b_slots,
                                c->d_chunk_off.as<u64>(), c->d_slot_label.as<u32>(), c->d_lcoff.as<u32>(), c->n_labels,
-                               c->d_cand.as<u32>(), c->d_cand_off.as<u64>(), c->stream));
+                               c->d_cand.as<u32>(), c->d_cand_off.as<u64>(), c->b_cand_cap, flag, c->stream));
     }
+    GPE_CUDA(c, c->h_pin3.reserve(8 * sizeof(u64)));
+    u64 *pin = c->h_pin3.as<u64>();
+    GPE_CUDA(c, cudaMemcpyAsync(pin, c->d_chunk_off.as<u64>() + n_chunks, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(pin + 1, c->d_counters.p, 2 * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    GPE_CUDA(c, cudaMemcpyAsync(pin + 3, flag, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    c->b_cand_known = false;
+    c->b_cand_external_lists = false;
     c->stats.compact_launches += 3;
     c->stats.kernel_launches += 1 + exclusive_scan_launches(n_chunks + 1) + (n_chunks ? 1 : 0);
-    c->stats.d2h_bytes += 3 * sizeof(u64);
+    c->stats.d2h_bytes += 4 * sizeof(u64);
     return GPE_OK;
+}
+
+// Wait for the stream and take over what the compaction left in pinned memory.  Returns 1 when the candidate lists did
+// not fit d_cand (the caller redoes compaction + join; the capacity has been raised), 0 otherwise, < 0 never.
+int cand_total(gpe_ctx *c, bool *overflow) {
+    if (overflow) *overflow = false;
+    if (c->b_cand_known) return GPE_OK;
+    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    const u64 *pin = c->h_pin3.as<u64>();
+    c->b_n_cand = pin[0];
+    c->cand_seen_max = std::max(c->cand_seen_max, pin[0]);
+    c->stats.n_candidates = pin[0];
+    c->stats.scan_items = pin[1];
+    c->stats.scan_rows = pin[1] * kTileRows;
+    c->b_cand_known = true;
+    if (pin[3] && overflow) *overflow = true;
+    return GPE_OK;
+}
+
+int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, bool force_dfs = false,
+             const u32 *d_qmode = nullptr);
+
+// the lists did not fit: expand them again into a buffer of the right size (chunk offsets are still on the device)
+int recompact(gpe_ctx *c) {
+    GPE_CUDA(c, c->d_cand.reserve(std::max<u64>(c->b_n_cand, 1) * sizeof(u32)));
+    c->b_cand_cap = c->d_cand.cap / sizeof(u32);
+    u64 *flag = c->d_counters.as<u64>() + 5;
+    GPE_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(u64), c->stream));
+    GPE_CUDA(c, k3_compact(c->d_bitmap.as<u32>(), c->b_words, c->b_chunks_per_slot, c->b_slots, c->d_chunk_off.as<u64>(),
+                           c->d_slot_label.as<u32>(), c->d_lcoff.as<u32>(), c->n_labels, c->d_cand.as<u32>(),
+                           c->d_cand_off.as<u64>(), c->b_cand_cap, flag, c->stream));
+    c->stats.kernel_launches++;
+    return GPE_OK;
+}
+
+// Candidate total known on the host and the lists complete; a join that already ran on truncated lists (it found the
+// overflow flag and did nothing) is run again.
+int settle_candidates(gpe_ctx *c) {
+    bool overflow = false;
+    int rc = cand_total(c, &overflow);
+    if (rc || !overflow) return rc;
+    if ((rc = recompact(c))) return rc;
+    if (c->b_joined) rc = run_join(c, c->b_rank, c->b_world, nullptr, 0, false, nullptr);
+    return rc;
 }
 
 // select + scan: the candidate bitmaps of this GPU's table (shard) are on the device afterwards
@@ -281,12 +340,26 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
     GPE_CUDA(c, c->d_q_nbrs.reserve(sz[3]));
     GPE_CUDA(c, c->d_q_labels.reserve(sz[4]));
     GPE_CUDA(c, c->d_limits.reserve(std::max<size_t>(sz[5], 8)));
-    GPE_CUDA(c, cudaMemcpyAsync(c->d_q_vbase.p, q_vbase, sz[0], cudaMemcpyHostToDevice, c->stream));
-    GPE_CUDA(c, cudaMemcpyAsync(c->d_q_ebase.p, q_ebase, sz[1], cudaMemcpyHostToDevice, c->stream));
-    GPE_CUDA(c, cudaMemcpyAsync(c->d_q_offsets.p, q_offsets, sz[2], cudaMemcpyHostToDevice, c->stream));
-    if (n_adj) GPE_CUDA(c, cudaMemcpyAsync(c->d_q_nbrs.p, q_nbrs, n_adj * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
-    if (n_slots) GPE_CUDA(c, cudaMemcpyAsync(c->d_q_labels.p, q_labels, n_slots * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
-    if (n_queries) GPE_CUDA(c, cudaMemcpyAsync(c->d_limits.p, c->h_limits.data(), sz[5], cudaMemcpyHostToDevice, c->stream));
+    {   // staged through pinned memory: the copies are asynchronous and the caller's buffers are free on return
+        size_t off[7];
+        const size_t bytes[6] = {sz[0], sz[1], sz[2], (size_t)n_adj * sizeof(u32), (size_t)n_slots * sizeof(u32), sz[5]};
+        off[0] = 0;
+        for (int i = 0; i < 6; i++) off[i + 1] = (off[i] + bytes[i] + 15) / 16 * 16;
+        GPE_CUDA(c, cudaEventSynchronize(c->ev_upload));  // the previous batch's copies out of the staging blocks are done
+        if (c->h_pin_q.cap < off[6]) {
+            GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+            GPE_CUDA(c, c->h_pin_q.reserve(off[6]));
+        }
+        unsigned char *pin = c->h_pin_q.as<unsigned char>();
+        const void *src[6] = {q_vbase, q_ebase, q_offsets, q_nbrs, q_labels, c->h_limits.data()};
+        void *dst[6] = {c->d_q_vbase.p, c->d_q_ebase.p, c->d_q_offsets.p, c->d_q_nbrs.p, c->d_q_labels.p, c->d_limits.p};
+        for (int i = 0; i < 6; i++) {
+            if (!bytes[i]) continue;
+            memcpy(pin + off[i], src[i], bytes[i]);
+            GPE_CUDA(c, cudaMemcpyAsync(dst[i], pin + off[i], bytes[i], cudaMemcpyHostToDevice, c->stream));
+        }
+        GPE_CUDA(c, cudaEventRecord(c->ev_upload, c->stream));
+    }
     GPE_CUDA(c, c->d_order.reserve(std::max<size_t>(n_slots, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_pivot.reserve(std::max<size_t>(n_slots, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_jplan.reserve(std::max<size_t>(n_slots, 1) * sizeof(JoinDepth)));
@@ -295,16 +368,13 @@ int upload_queries(gpe_ctx *c, u32 n_queries, const u32 *q_vbase, const u32 *q_e
     GPE_CUDA(c, c->d_answers.reserve((2 * (size_t)n_queries + 8) * sizeof(u64)));
     GPE_CUDA(c, c->d_match_cursor.reserve(2 * sizeof(u64)));
     c->stats.h2d_bytes += sz[0] + sz[1] + sz[2] + (size_t)n_adj * sizeof(u32) + (size_t)n_slots * sizeof(u32) + sz[5];
-    // pageable sources: make sure the copies are done before the caller's buffers go away
-    GPE_CUDA(c, cudaStreamSynchronize(c->stream));
     return GPE_OK;
 }
 
 constexpr u64 kJoinExportBytes = 256ull << 20;  // room for exported work items
 
 // d_answers: [0, nq + 8) raw counts, [nq + 8, 2 nq + 8) per-query "inexact" flags (see kSat in k3_join.cu)
-int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, bool force_dfs = false,
-             const u32 *d_qmode = nullptr) {
+int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, bool force_dfs, const u32 *d_qmode) {
     StageTimer tm(c, &c->stats.last_join_ms, kStageJoin);
     c->b_rank = rank;
     c->b_world = world;
@@ -347,11 +417,11 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
                                    tcount, tlist, clean_start ? c->d_bitmap.as<u32>() : nullptr, c->b_words,
                                    c->d_tpool.as<u64>(), c->sm_count, c->stream));
     }
-    // tickets [0, n_init) are the root candidates of this shard (b_n_cand + V bounds their number from above);
+    // tickets [0, n_init) are the root candidates of this shard (the candidate capacity + one label class per query bounds them);
     // later tickets are subtrees exported by busy threads
     const u32 stride = k3_item_stride(c->b_max_nq);
     const u64 cap = kJoinExportBytes / (stride * sizeof(u32));
-    GPE_CUDA(c, c->d_init.reserve((std::max<u64>(c->b_n_cand, 1) + (u64)nq * c->max_class) * 2 * sizeof(u32)));
+    GPE_CUDA(c, c->d_init.reserve((std::max<u64>(c->b_cand_cap, 1) + (u64)nq * c->max_class) * 2 * sizeof(u32)));
     GPE_CUDA(c, c->d_items.reserve(cap * stride * sizeof(u32)));
     if (c->d_ready.cap < cap * sizeof(u32) || c->join_epoch == 0xffffffffu) {
         GPE_CUDA(c, c->d_ready.reserve(cap * sizeof(u32)));
@@ -365,7 +435,8 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
     GPE_CUDA(c, cudaMemsetAsync(c->d_qcur.p, 0, ((size_t)nq + 1) * 6 * sizeof(u64), c->stream));
     GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
                               c->d_cand.as<u32>(), c->d_item_base.as<u64>(), rank, world, heavy_deg,
-                              c->d_qcur.as<u64>(), c->d_init.p, jq, tree_launches > 0, c->sm_count, c->stream));
+                              c->d_qcur.as<u64>(), c->d_init.p, jq, tree_launches > 0,
+                              c->b_cand_external_lists ? nullptr : c->d_counters.as<u64>() + 5, c->sm_count, c->stream));
     GPE_CUDA(c, k3_dfs(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_cand.as<u32>(),
                        c->d_init.p, c->d_limits.as<u64>(), answers, c->d_items.as<u32>(), cap, c->d_ready.as<u32>(), epoch,
                        jq, d_matches, matches_cap, c->d_match_cursor.as<u64>(), answers + nq + 8, c->sm_count, c->stream));
@@ -462,7 +533,8 @@ int gpe_create(int device, gpe_ctx **out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+        (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming)) != cudaSuccess) {
         g_create_err = cudaGetErrorString(e);
         delete c;
         return GPE_ERR_CUDA;
@@ -475,6 +547,9 @@ void gpe_destroy(gpe_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->comm) nccl_api().CommDestroy((ncclComm_t)c->comm);
+    c->d_all_bitmaps.release();
+    c->d_reduce.release();
     DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrJ, &c->d_gtab, &c->d_offJ, &c->d_degJ, &c->d_labelJ, &c->d_newid, &c->d_nbrG, &c->d_lclass, &c->d_lpos, &c->d_lcoff, &c->d_bloom, &c->d_tjobs, &c->d_tchild, &c->d_tpool, &c->d_tcursor, &c->d_tlist, &c->d_qcur, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
                       &c->d_offr, &c->d_ebase, &c->d_start_rows, &c->d_scan_tmp, &c->d_tiles, &c->d_vids, &c->d_sum_u32, &c->d_sum_f64,
                       &c->d_bucket, &c->d_cursor, &c->d_qblocks, &c->d_qb_t0, &c->d_qb_prefix, &c->d_worklist,
@@ -485,6 +560,9 @@ void gpe_destroy(gpe_ctx *c) {
     for (DevBuf *b : bufs) b->release();
     c->h_pin.release();
     c->h_pin2.release();
+    c->h_pin3.release();
+    c->h_pin_q.release();
+    if (c->ev_upload) cudaEventDestroy(c->ev_upload);
     for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
@@ -878,6 +956,7 @@ int gpe_filter(gpe_ctx *c, uint32_t n_qpaths, const uint32_t *q_vids, const uint
     if (rc) return rc;
     rc = run_filter(c);
     if (rc) return rc;
+    if ((rc = settle_candidates(c))) return rc;
     if (cand_offsets)
         GPE_CUDA(c, cudaMemcpyAsync(cand_offsets, c->d_cand_off.p, ((size_t)nq + 1) * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     if (survivors && n_qpaths)
@@ -892,6 +971,7 @@ int gpe_get_candidates(gpe_ctx *c, uint32_t *cand) try {
     if (!c || !cand) return GPE_ERR_INVALID;
     if (!c->b_filtered) return c->fail(GPE_ERR_INVALID, "no filter result");
     GPE_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = settle_candidates(c)) return rc;
     return download_candidates(c, cand);
 } catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
     return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_get_candidates", ex.what()) : GPE_ERR_INVALID;
@@ -924,6 +1004,8 @@ int gpe_refine(gpe_ctx *c, uint32_t nq, const uint32_t *q_offsets, const uint32_
     }
     c->b_slots = nq;
     c->b_n_cand = total;
+    c->b_cand_known = true;
+    c->b_cand_external_lists = true;  // no compaction ran: nothing to settle
     c->b_cand_clean = false;  // caller-supplied sets: the reference takes them as they are
     GPE_CUDA(c, c->d_cand.reserve(std::max<u64>(total, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_cand_off.reserve(((size_t)nq + 1) * sizeof(u64)));
@@ -963,28 +1045,33 @@ int gpe_refine(gpe_ctx *c, uint32_t nq, const uint32_t *q_offsets, const uint32_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-int gpe_batch_upload(gpe_ctx *c, const gpe_batch *b, uint32_t flags) try {
-    if (!c || !b || !b->q_vbase || !b->q_ebase || !b->q_offsets || !b->q_labels) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
-    if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
-    GPE_CUDA(c, cudaSetDevice(c->device));
-    const u32 L = c->tv.L, E = c->tv.E, D = c->tv.D;
-    QPathSet qp;
-    qp.L = L;
-    qp.D = D;
+// Host planning of a batch (dfs_query + gen_vde(query) + gen_query_pde per query, main.cpp:142-158): independent of the
+// GPU, so one plan serves every context of a multi-GPU run, and it can be computed while a previous batch is in flight.
+struct gpe_plan {
+    u32 L = 0, E = 0;
+    std::vector<QueryPlan> plans;
+    std::string err;
+};
+
+static int plan_batch(const gpe_batch *b, u32 L, u32 E, LabelTable &table, gpe_plan &out) {
+    out.L = L;
+    out.E = E;
     std::string why;
     for (u32 q = 0; q < b->n_queries; q++) {
         const u32 vb = b->q_vbase[q], nq = b->q_vbase[q + 1] - vb;
-        if (!check_query(c, nq, b->q_offsets + vb + q, b->q_nbrs + b->q_ebase[q], why))
-            return c->fail(GPE_ERR_INVALID, "query %u: %s", q, why.c_str());
+        if (!check_query(nullptr, nq, b->q_offsets + vb + q, b->q_nbrs + b->q_ebase[q], why)) {
+            out.err = "query " + std::to_string(q) + ": " + why;
+            return GPE_ERR_INVALID;
+        }
     }
-    // the reference plans one query at a time (main.cpp:142-158); here the queries of a batch are planned by a few
-    // host threads, label embeddings come from a table filled once per batch
-    c->label_table.fill(b->q_labels, b->q_vbase[b->n_queries], E);
-    std::vector<QueryPlan> plans(b->n_queries);
+    // the reference plans one query at a time; here the queries of a batch are planned by a few host threads, label
+    // embeddings come from a table filled once per batch
+    table.fill(b->q_labels, b->q_vbase[b->n_queries], E);
+    out.plans.assign(b->n_queries, QueryPlan());
     auto plan_range = [&](u32 q0, u32 q1) {
         for (u32 q = q0; q < q1; q++) {
             const u32 vb = b->q_vbase[q], nq = b->q_vbase[q + 1] - vb;
-            query_plan(nq, b->q_offsets + vb + q, b->q_nbrs + b->q_ebase[q], b->q_labels + vb, L, E, plans[q], &c->label_table);
+            query_plan(nq, b->q_offsets + vb + q, b->q_nbrs + b->q_ebase[q], b->q_labels + vb, L, E, out.plans[q], &table);
         }
     };
     const u32 n_thr = b->n_queries >= 64 ? std::min<u32>(8, std::max<u32>(1, std::thread::hardware_concurrency() / 2)) : 1;
@@ -997,8 +1084,17 @@ int gpe_batch_upload(gpe_ctx *c, const gpe_batch *b, uint32_t flags) try {
         plan_range(0, std::min(per, b->n_queries));
         for (auto &th : pool) th.join();
     }
+    return GPE_OK;
+}
+
+static int upload_planned(gpe_ctx *c, const gpe_batch *b, const gpe_plan &pl, uint32_t flags) {
+    const u32 L = c->tv.L, D = c->tv.D;
+    if (pl.L != L || pl.E != c->tv.E || pl.plans.size() != b->n_queries) return c->fail(GPE_ERR_INVALID, "plan does not belong to this batch / table");
+    QPathSet qp;
+    qp.L = L;
+    qp.D = D;
     for (u32 q = 0; q < b->n_queries; q++) {
-        const QueryPlan &plan = plans[q];
+        const QueryPlan &plan = pl.plans[q];
         const u32 vb = b->q_vbase[q];
         for (u32 i = 0; i < plan.n * L; i++) qp.slots.push_back(vb + plan.vids[i]);
         qp.labels.insert(qp.labels.end(), plan.labels.begin(), plan.labels.end());
@@ -1009,6 +1105,15 @@ int gpe_batch_upload(gpe_ctx *c, const gpe_batch *b, uint32_t flags) try {
     if (rc) return rc;
     c->b_pge = false;
     return setup_filter(c, qp, b->q_vbase[b->n_queries], flags);
+}
+
+int gpe_batch_upload(gpe_ctx *c, const gpe_batch *b, uint32_t flags) try {
+    if (!c || !b || !b->q_vbase || !b->q_ebase || !b->q_offsets || !b->q_labels) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
+    if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    gpe_plan pl;
+    if (int rc = plan_batch(b, c->tv.L, c->tv.E, c->label_table, pl)) return c->fail(rc, "%s", pl.err.c_str());
+    return upload_planned(c, b, pl, flags);
 } catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
     return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_batch_upload", ex.what()) : GPE_ERR_INVALID;
 }
@@ -1041,6 +1146,15 @@ int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) try {
     static_assert(sizeof(JoinQueue) <= 16 * sizeof(u64), "pinned layout");
     if (nq) GPE_CUDA(c, cudaMemcpyAsync(pin_flags, c->d_answers.as<u64>() + nq + 8, nq * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!c->b_cand_known) {  // first look at what the compaction reported: did the candidate lists fit their buffer?
+        bool overflow = false;
+        if (int rc = cand_total(c, &overflow)) return rc;
+        if (overflow) {  // the join saw the flag and did nothing: expand the lists again, join again, read again
+            if (int rc = recompact(c)) return rc;
+            if (int rc = run_join(c, c->b_rank, c->b_world, nullptr, 0)) return rc;
+            return gpe_batch_download(c, raw_counts);
+        }
+    }
     // raw counts are exact below 2^44 and saturated beyond (k3_join.cu kSat); capped so that shards can still be summed
     for (size_t q = 0; q < nq; q++) pin[q] = std::min<u64>(pin[q], 1ull << 48);
     memcpy(raw_counts, pin, (size_t)c->b_nq * sizeof(u64));
@@ -1095,6 +1209,8 @@ int gpe_query_batch(gpe_ctx *c, const gpe_batch *b, uint32_t flags, uint64_t *an
 int gpe_batch_cand_info(gpe_ctx *c, uint64_t *n_slots, uint64_t *n_cand_total) {
     if (!c) return GPE_ERR_INVALID;
     if (!c->b_filtered) return c->fail(GPE_ERR_INVALID, "no filter result");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = settle_candidates(c)) return rc;
     if (n_slots) *n_slots = c->b_slots;
     if (n_cand_total) *n_cand_total = c->b_n_cand;
     return GPE_OK;
@@ -1104,6 +1220,7 @@ int gpe_batch_cand_export(gpe_ctx *c, void *d_counts_u32, void *d_cand_u32) {
     if (!c || !d_counts_u32) return GPE_ERR_INVALID;
     if (!c->b_filtered) return c->fail(GPE_ERR_INVALID, "no filter result");
     GPE_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = settle_candidates(c)) return rc;
     GPE_CUDA(c, k3_counts_from_offsets(c->d_cand_off.as<u64>(), c->b_slots, (u32 *)d_counts_u32, c->stream));
     if (c->b_n_cand && d_cand_u32)
         GPE_CUDA(c, cudaMemcpyAsync(d_cand_u32, c->d_cand.p, c->b_n_cand * sizeof(u32), cudaMemcpyDeviceToDevice, c->stream));
@@ -1159,6 +1276,7 @@ int gpe_batch_get_candidates(gpe_ctx *c, uint64_t *cand_offsets, uint32_t *cand)
     if (!c || !cand_offsets) return GPE_ERR_INVALID;
     if (!c->b_filtered) return c->fail(GPE_ERR_INVALID, "no filter result");
     GPE_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = settle_candidates(c)) return rc;
     GPE_CUDA(c, cudaMemcpy(cand_offsets, c->d_cand_off.p, ((size_t)c->b_slots + 1) * sizeof(u64), cudaMemcpyDeviceToHost));
     if (cand) return download_candidates(c, cand);
     return GPE_OK;
@@ -1345,6 +1463,208 @@ int gpe_pge_query_batch(gpe_ctx *c, const gpe_batch *b, uint64_t *answers) try {
     return GPE_OK;
 } catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
     return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_pge_query_batch", ex.what()) : GPE_ERR_INVALID;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-GPU: the path table sharded by the reference's partitions (a path belongs to the partition of its first
+// vertex, custom.h:74; GPU r of N holds partitions i % N == r), one candidate exchange per batch in place of the serial
+// merge (main.cpp:166-172), the join split by start candidate.  NCCL inside the library, no PyTorch.
+#define GPE_NCCL(ctx, expr)                                                                                       \
+    do {                                                                                                          \
+        ncclResult_t r__ = (expr);                                                                                \
+        if (r__ != ncclSuccess)                                                                                   \
+            return (ctx)->fail(GPE_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, nccl_api().GetErrorString(r__)); \
+    } while (0)
+
+int gpe_comm_unique_id(void *id_out) {
+    if (!id_out) return GPE_ERR_INVALID;
+    static_assert(sizeof(ncclUniqueId) == GPE_COMM_ID_BYTES, "ncclUniqueId size");
+    NcclApi &n = nccl_api();
+    if (!n.ok) { g_create_err = n.err; return GPE_ERR_UNSUPPORTED; }
+    ncclUniqueId id;
+    if (n.GetUniqueId(&id) != ncclSuccess) { g_create_err = "ncclGetUniqueId failed"; return GPE_ERR_CUDA; }
+    memcpy(id_out, &id, sizeof id);
+    return GPE_OK;
+}
+
+int gpe_comm_init(gpe_ctx *c, int rank, int world, const void *id_in) {
+    if (!c || !id_in || world < 1 || rank < 0 || rank >= world) return c ? c->fail(GPE_ERR_INVALID, "bad rank/world/id") : GPE_ERR_INVALID;
+    NcclApi &n = nccl_api();
+    if (!n.ok) return c->fail(GPE_ERR_UNSUPPORTED, "%s", n.err.c_str());
+    if (c->comm) return c->fail(GPE_ERR_INVALID, "context already has a communicator");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, id_in, sizeof id);
+    ncclComm_t comm = nullptr;
+    GPE_NCCL(c, n.CommInitRank(&comm, world, id, rank));
+    c->comm = comm;
+    c->comm_rank = rank;
+    c->comm_world = world;
+    return GPE_OK;
+}
+
+int gpe_comm_init_all(gpe_ctx **ctxs, int n_ctx) {
+    if (!ctxs || n_ctx < 1 || n_ctx > kMaxDevices) return GPE_ERR_INVALID;
+    NcclApi &n = nccl_api();
+    if (!n.ok) return ctxs[0] ? ctxs[0]->fail(GPE_ERR_UNSUPPORTED, "%s", n.err.c_str()) : GPE_ERR_UNSUPPORTED;
+    int devs[kMaxDevices];
+    ncclComm_t comms[kMaxDevices];
+    for (int i = 0; i < n_ctx; i++) {
+        if (!ctxs[i] || ctxs[i]->comm) return GPE_ERR_INVALID;
+        devs[i] = ctxs[i]->device;
+    }
+    GPE_NCCL(ctxs[0], n.CommInitAll(comms, n_ctx, devs));
+    for (int i = 0; i < n_ctx; i++) {
+        ctxs[i]->comm = comms[i];
+        ctxs[i]->comm_rank = i;
+        ctxs[i]->comm_world = n_ctx;
+    }
+    return GPE_OK;
+}
+
+int gpe_comm_destroy(gpe_ctx *c) {
+    if (!c) return GPE_ERR_INVALID;
+    if (c->comm) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        nccl_api().CommDestroy((ncclComm_t)c->comm);
+        c->comm = nullptr;
+    }
+    c->comm_rank = 0;
+    c->comm_world = 1;
+    return GPE_OK;
+}
+
+int gpe_comm_info(gpe_ctx *c, int *rank, int *world, int *nccl_version) {
+    if (!c) return GPE_ERR_INVALID;
+    if (rank) *rank = c->comm_rank;
+    if (world) *world = c->comm_world;
+    if (nccl_version) {
+        *nccl_version = 0;
+        if (nccl_api().ok) nccl_api().GetVersion(nccl_version);
+    }
+    return GPE_OK;
+}
+
+int gpe_build_table_shard(gpe_ctx *c, uint64_t *n_table_rows) {
+    if (!c) return GPE_ERR_INVALID;
+    if (!c->have_enum) return c->fail(GPE_ERR_INVALID, "gpe_enumerate first");
+    if (c->comm_world <= 1) return gpe_build_table(c, nullptr, n_table_rows);
+    if (c->p < (u32)c->comm_world) return c->fail(GPE_ERR_INVALID, "%u partitions for %d GPUs: enumerate with p >= the number of GPUs", c->p, c->comm_world);
+    std::vector<uint8_t> sel(c->p);
+    for (u32 i = 0; i < c->p; i++) sel[i] = (int)(i % (u32)c->comm_world) == c->comm_rank;
+    return gpe_build_table(c, sel.data(), n_table_rows);
+}
+
+namespace {
+// stage 2 + 3 of one context up to the exchange / after it (everything asynchronous on the context's stream)
+int sharded_exchange_enqueue(gpe_ctx *c) {  // between ncclGroupStart/End when one thread drives several contexts
+    const u64 bytes = (u64)c->b_slots * c->b_words * sizeof(u32);
+    GPE_CUDA(c, c->d_all_bitmaps.reserve(std::max<u64>(bytes * c->comm_world, 16)));
+    if (bytes) GPE_NCCL(c, nccl_api().AllGather(c->d_bitmap.p, c->d_all_bitmaps.p, bytes, ncclUint8, (ncclComm_t)c->comm, c->stream));
+    return GPE_OK;
+}
+int sharded_after_exchange(gpe_ctx *c) {
+    int rc = compact_candidates(c, c->d_all_bitmaps.as<u32>(), (u32)c->comm_world);
+    if (rc) return rc;
+    c->b_filtered = true;
+    c->b_cand_external = true;
+    c->b_cand_clean = true;  // a union of filter outputs
+    return run_join(c, (u32)c->comm_rank, (u32)c->comm_world, nullptr, 0);
+}
+}  // namespace
+
+int gpe_batch_step(gpe_ctx *c) {
+    if (!c) return GPE_ERR_INVALID;
+    if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    if (!c->comm) {
+        if (int rc = run_filter(c)) return rc;
+        return run_join(c, 0, 1, nullptr, 0);
+    }
+    // (a communicator of one rank takes the same route: the exchange is then a copy)
+    if (int rc = run_scan(c)) return rc;
+    if (int rc = sharded_exchange_enqueue(c)) return rc;
+    return sharded_after_exchange(c);
+}
+
+int gpe_batch_finish(gpe_ctx *c, uint64_t *answers) {
+    if (!c || !answers) return GPE_ERR_INVALID;
+    if (int rc = gpe_batch_download(c, answers)) return rc;  // this shard's raw counts (repaired locally if need be)
+    const u32 nq = c->b_nq;
+    if (c->comm && nq) {  // C2: sum of the shards' counts (each at most 2^48: no wrap)
+        GPE_CUDA(c, c->d_reduce.reserve((size_t)nq * sizeof(u64)));
+        GPE_CUDA(c, c->h_pin2.reserve((2 * std::max<size_t>(nq, 16) + 32) * sizeof(u64)));
+        u64 *pin = c->h_pin2.as<u64>();
+        memcpy(pin, answers, (size_t)nq * sizeof(u64));
+        GPE_CUDA(c, cudaMemcpyAsync(c->d_reduce.p, pin, (size_t)nq * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+        GPE_NCCL(c, nccl_api().AllReduce(c->d_reduce.p, c->d_reduce.p, nq, ncclUint64, ncclSum, (ncclComm_t)c->comm, c->stream));
+        GPE_CUDA(c, cudaMemcpyAsync(pin, c->d_reduce.p, (size_t)nq * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+        memcpy(answers, pin, (size_t)nq * sizeof(u64));
+        c->stats.h2d_bytes += (size_t)nq * sizeof(u64);
+        c->stats.d2h_bytes += (size_t)nq * sizeof(u64);
+    }
+    for (u32 q = 0; q < nq; q++) answers[q] = gpe_clamp_answer(answers[q], c->h_limits[q]);
+    return GPE_OK;
+}
+
+// ---- one process, several contexts (host/main -g N): one thread enqueues every GPU's work, NCCL calls grouped --------
+int gpe_multi_batch_upload(gpe_ctx **ctxs, int n, const gpe_batch *b, uint32_t flags) try {
+    if (!ctxs || n < 1 || !b || !ctxs[0]) return GPE_ERR_INVALID;
+    gpe_ctx *c0 = ctxs[0];
+    if (!c0->have_table) return c0->fail(GPE_ERR_INVALID, "gpe_build_table first");
+    gpe_plan pl;
+    if (int rc = plan_batch(b, c0->tv.L, c0->tv.E, c0->label_table, pl)) return c0->fail(rc, "%s", pl.err.c_str());
+    for (int i = 0; i < n; i++) {
+        GPE_CUDA(ctxs[i], cudaSetDevice(ctxs[i]->device));
+        if (int rc = upload_planned(ctxs[i], b, pl, flags)) return rc;
+    }
+    return GPE_OK;
+} catch (const std::exception &ex) {
+    return ctxs && ctxs[0] ? ctxs[0]->fail(GPE_ERR_INVALID, "gpe_multi_batch_upload: %s", ex.what()) : GPE_ERR_INVALID;
+}
+
+int gpe_multi_batch_step(gpe_ctx **ctxs, int n) {
+    if (!ctxs || n < 1) return GPE_ERR_INVALID;
+    if (n == 1) return gpe_batch_step(ctxs[0]);
+    for (int i = 0; i < n; i++) {
+        GPE_CUDA(ctxs[i], cudaSetDevice(ctxs[i]->device));
+        if (int rc = run_scan(ctxs[i])) return rc;
+    }
+    GPE_NCCL(ctxs[0], nccl_api().GroupStart());
+    for (int i = 0; i < n; i++) {
+        GPE_CUDA(ctxs[i], cudaSetDevice(ctxs[i]->device));
+        if (int rc = sharded_exchange_enqueue(ctxs[i])) { nccl_api().GroupEnd(); return rc; }
+    }
+    GPE_NCCL(ctxs[0], nccl_api().GroupEnd());
+    for (int i = 0; i < n; i++) {
+        GPE_CUDA(ctxs[i], cudaSetDevice(ctxs[i]->device));
+        if (int rc = sharded_after_exchange(ctxs[i])) return rc;
+    }
+    return GPE_OK;
+}
+
+int gpe_multi_batch_finish(gpe_ctx **ctxs, int n, uint64_t *answers) try {
+    if (!ctxs || n < 1 || !answers) return GPE_ERR_INVALID;
+    const u32 nq = ctxs[0]->b_nq;
+    std::vector<u64> part(nq);
+    for (u32 q = 0; q < nq; q++) answers[q] = 0;
+    for (int i = 0; i < n; i++) {  // the GPUs ran concurrently; the host sum replaces the all-reduce (one process)
+        if (int rc = gpe_batch_download(ctxs[i], part.data())) return rc;
+        for (u32 q = 0; q < nq; q++) answers[q] += part[q];
+    }
+    for (u32 q = 0; q < nq; q++) answers[q] = gpe_clamp_answer(answers[q], ctxs[0]->h_limits[q]);
+    return GPE_OK;
+} catch (const std::exception &ex) {
+    return ctxs && ctxs[0] ? ctxs[0]->fail(GPE_ERR_INVALID, "gpe_multi_batch_finish: %s", ex.what()) : GPE_ERR_INVALID;
+}
+
+int gpe_multi_query_batch(gpe_ctx **ctxs, int n, const gpe_batch *b, uint32_t flags, uint64_t *answers) {
+    if (int rc = gpe_multi_batch_upload(ctxs, n, b, flags)) return rc;
+    if (int rc = gpe_multi_batch_step(ctxs, n)) return rc;
+    return gpe_multi_batch_finish(ctxs, n, answers);
 }
 
 }  // extern "C"

@@ -268,7 +268,15 @@ struct gpe_ctx {
     gpe::DevBuf d_chunk_cnt, d_chunk_off, d_cand, d_cand_off;
     gpe::DevBuf d_q_vbase, d_q_ebase, d_q_offsets, d_q_nbrs, d_q_labels, d_limits;
     gpe::DevBuf d_order, d_pivot, d_jplan, d_item_base, d_answers, d_matches, d_match_cursor, d_qmode;
-    gpe::PinnedBuf h_pin, h_pin2;
+    gpe::PinnedBuf h_pin, h_pin2, h_pin3, h_pin_q;  // staging: query-path blocks, answers, compaction results, query arrays
+    cudaEvent_t ev_upload = nullptr;                // the last upload's copies out of h_pin / h_pin_q are done
+    u64 b_cand_cap = 0, cand_seen_max = 0;          // entries d_cand holds; largest candidate total of any batch so far
+    bool b_cand_external_lists = false;             // candidate lists were supplied by the caller (gpe_refine): no compaction ran
+    bool b_cand_known = false;                      // b_n_cand / scan counters have been read back for this batch
+    // multi-GPU (gpe_comm_*): NCCL communicator of this context, its rank, the all-gathered shard bitmaps
+    void *comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    gpe::DevBuf d_all_bitmaps, d_reduce;
     gpe::LabelTable label_table;  // label embeddings of the queries seen so far (host planning)
     u64 b_chunks_per_slot = 0;
 
@@ -347,8 +355,10 @@ cudaError_t k3_merge_count(const u32 *all, u64 shard_words, u32 world, u32 *bitm
                            u64 chunks_per_slot, u32 n_slots, u64 *chunk_cnt, cudaStream_t s);
 // bit i of slot s stands for vertex lclass[lcoff[slot_label[s]] + i]
 // (candidate lists on the device hold class-order ids: first id of the slot's label + bit position)
+// cap: entries `cand` holds; a chunk that would write beyond it is dropped and *overflow set
 cudaError_t k3_compact(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slot, u32 n_slots, const u64 *chunk_off,
-                       const u32 *slot_label, const u32 *lcoff, u32 n_labels, u32 *cand, u64 *cand_off, cudaStream_t s);
+                       const u32 *slot_label, const u32 *lcoff, u32 n_labels, u32 *cand, u64 *cand_off, u64 cap,
+                       u64 *overflow, cudaStream_t s);
 cudaError_t k3_scatter(const u32 *counts, const u32 *cand, u64 stride, u32 world, u32 n_slots, const u32 *slot_label,
                        const u32 *lcoff, u32 n_labels, u32 *bitmap, u64 words_per_slot, u64 *prefix_tmp /*world x n_slots*/,
                        cudaStream_t s);
@@ -372,6 +382,7 @@ cudaError_t k3_init_items(const JoinGraph &jv, u32 n_queries, const u32 *q_vbase
                           const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world,
                           u32 heavy_deg /*roots of at least this degree are ticketed first*/, u64 *cursors /*6 per query, zeroed*/,
                           void *init, JoinQueue *jq, bool use_tables /*subtree tables are valid: dead roots get no ticket*/,
+                          const u64 *cand_overflow /*device flag or null: set => the candidate lists are truncated, no tickets*/,
                           int sm_count, cudaStream_t s);
 // one persistent launch: every thread runs work items (explicit-stack DFS) and exports subtrees when others starve
 cudaError_t k3_dfs(const JoinGraph &jv, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,

@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) k3_compact_kernel(const u32 *__restrict__
                                                          const u64 *__restrict__ chunk_off,
                                                          const u32 *__restrict__ slot_label,
                                                          const u32 *__restrict__ lcoff, u32 n_labels,
-                                                         u32 *__restrict__ cand, u64 *__restrict__ cand_off) {
+                                                         u32 *__restrict__ cand, u64 *__restrict__ cand_off, u64 cap,
+                                                         u64 *overflow) {
     const int lane = threadIdx.x & 31;
     u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n_chunks) return;
@@ -118,6 +119,10 @@ __global__ void __launch_bounds__(256) k3_compact_kernel(const u32 *__restrict__
         if (slot == 0) cand_off[n_slots] = chunk_off[n_chunks];
     }
     if (chunk_off[w + 1] == out) return;
+    if (chunk_off[w + 1] > cap) {  // the list buffer was sized before the total was known: the host redoes this step
+        if (lane == 0) *overflow = 1;
+        return;
+    }
     const u32 *p = bitmap + slot * words_per_slot + c * kChunkWords;
     u32 vbase = (u32)(c * kChunkWords * 32);
     // bit -> vertex in class order: first id of the slot's label + the position (ascending position = ascending id)
@@ -700,7 +705,9 @@ __global__ void __launch_bounds__(256) k3_init_count_kernel(u32 n_queries, const
                                                             const u32 *__restrict__ deg,
                                                             const u32 *__restrict__ lcoff, u32 n_labels,
                                                             const u64 *__restrict__ item_base, u32 rank, u32 world,
-                                                            u32 heavy_deg, const u64 *__restrict__ tpool, u64 *qcur) {
+                                                            u32 heavy_deg, const u64 *__restrict__ tpool, u64 *qcur,
+                                                            const u64 *__restrict__ cand_overflow) {
+    if (cand_overflow && *cand_overflow) return;  // truncated candidate lists: the host redoes the step
     const u64 n_items = item_base[n_queries], n_round = (n_items + 31) / 32 * 32;
     const int lane = threadIdx.x & 31;
     for (u64 item = (u64)blockIdx.x * blockDim.x + threadIdx.x; item < n_round; item += (u64)gridDim.x * blockDim.x) {
@@ -750,7 +757,8 @@ __global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const
                                                             const u32 *__restrict__ lcoff, u32 n_labels,
                                                             const u64 *__restrict__ item_base, u32 rank, u32 world,
                                                             u32 heavy_deg, const u64 *__restrict__ tpool, u64 *qcur,
-                                                            uint2 *init) {
+                                                            uint2 *init, const u64 *__restrict__ cand_overflow) {
+    if (cand_overflow && *cand_overflow) return;
     const u64 n_items = item_base[n_queries], n_round = (n_items + 31) / 32 * 32;
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
@@ -1355,12 +1363,13 @@ cudaError_t k3_merge_count(const u32 *all, u64 shard_words, u32 world, u32 *bitm
 }
 
 cudaError_t k3_compact(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slot, u32 n_slots, const u64 *chunk_off,
-                       const u32 *slot_label, const u32 *lcoff, u32 n_labels, u32 *cand, u64 *cand_off, cudaStream_t s) {
+                       const u32 *slot_label, const u32 *lcoff, u32 n_labels, u32 *cand, u64 *cand_off, u64 cap, u64 *overflow,
+                       cudaStream_t s) {
     u64 n_chunks = chunks_per_slot * n_slots;
     if (n_chunks == 0) return cudaSuccess;
     k3_compact_kernel<<<(unsigned)((n_chunks * 32 + 255) / 256), 256, 0, s>>>(bitmap, words_per_slot, chunks_per_slot,
                                                                              n_chunks, n_slots, chunk_off, slot_label,
-                                                                             lcoff, n_labels, cand, cand_off);
+                                                                             lcoff, n_labels, cand, cand_off, cap, overflow);
     return cudaGetLastError();
 }
 
@@ -1400,15 +1409,16 @@ u32 k3_item_stride(u32 max_nq) { return item_stride(join_m(max_nq)); }
 
 cudaError_t k3_init_items(const JoinGraph &jv, u32 n_queries, const u32 *q_vbase, const JoinDepth *jplan,
                           const u64 *cand_off, const u32 *cand, const u64 *item_base, u32 rank, u32 world, u32 heavy_deg,
-                          u64 *cursors, void *init, JoinQueue *jq, bool use_tables, int sm_count, cudaStream_t s) {
+                          u64 *cursors, void *init, JoinQueue *jq, bool use_tables, const u64 *cand_overflow, int sm_count,
+                          cudaStream_t s) {
     // (enumeration mode walks every vertex and ignores the tables: roots are then only filtered by degree)
     const u64 *tp = use_tables ? jv.tpool : nullptr;
     k3_init_count_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, cand, jv.degJ, jv.lcoff,
-                                                     jv.nl, item_base, rank, world, heavy_deg, tp, cursors);
+                                                     jv.nl, item_base, rank, world, heavy_deg, tp, cursors, cand_overflow);
     k3_init_prefix_kernel<<<1, 32, 0, s>>>(n_queries, cursors, jq);
     k3_init_items_kernel<<<sm_count * 4, 256, 0, s>>>(n_queries, q_vbase, jplan, cand_off, cand, jv.degJ, jv.lcoff,
                                                      jv.nl, item_base, rank, world, heavy_deg, tp, cursors,
-                                                     reinterpret_cast<uint2 *>(init));
+                                                     reinterpret_cast<uint2 *>(init), cand_overflow);
     return cudaGetLastError();
 }
 

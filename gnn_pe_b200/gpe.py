@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpe.so")
 LIMIT_MAX = 0xFFFFFFFF
 FILTER_NO_PRUNE = 1
+COMM_ID_BYTES = 128
 
 _LIB = None
 
@@ -66,7 +67,9 @@ SYMBOLS = [
     "gpe_batch_scan", "gpe_batch_bitmap", "gpe_batch_bitmap_merge",
     "gpe_batch_get_candidates", "gpe_batch_get_plan", "gpe_pge_build", "gpe_host_pge_groups", "gpe_pge_dump_groups", "gpe_pge_batch_upload",
     "gpe_pge_batch_filter", "gpe_pge_query_batch", "gpe_get_stats", "gpe_stream", "gpe_sync", "gpe_set_timing",
-    "gpe_collect_timings",
+    "gpe_collect_timings", "gpe_comm_unique_id", "gpe_comm_init", "gpe_comm_init_all", "gpe_comm_destroy", "gpe_comm_info",
+    "gpe_build_table_shard", "gpe_batch_step", "gpe_batch_finish", "gpe_multi_batch_upload", "gpe_multi_batch_step",
+    "gpe_multi_batch_finish", "gpe_multi_query_batch",
 ]
 
 
@@ -116,6 +119,18 @@ def lib():
         L.gpe_pge_batch_upload.argtypes = [vp, C.POINTER(Batch)]
         L.gpe_pge_batch_filter.argtypes = [vp]
         L.gpe_pge_query_batch.argtypes = [vp, C.POINTER(Batch), vp]
+        L.gpe_comm_unique_id.argtypes = [vp]
+        L.gpe_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.gpe_comm_init_all.argtypes = [vp, C.c_int]
+        L.gpe_comm_destroy.argtypes = [vp]
+        L.gpe_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.gpe_build_table_shard.argtypes = [vp, C.POINTER(u64)]
+        L.gpe_batch_step.argtypes = [vp]
+        L.gpe_batch_finish.argtypes = [vp, vp]
+        L.gpe_multi_batch_upload.argtypes = [vp, C.c_int, C.POINTER(Batch), u32]
+        L.gpe_multi_batch_step.argtypes = [vp, C.c_int]
+        L.gpe_multi_batch_finish.argtypes = [vp, C.c_int, vp]
+        L.gpe_multi_query_batch.argtypes = [vp, C.c_int, C.POINTER(Batch), u32, vp]
         L.gpe_batch_get_candidates.argtypes = [vp, vp, vp]
         L.gpe_batch_get_plan.argtypes = [vp, vp, vp]
         L.gpe_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -203,6 +218,49 @@ def pack_queries(queries):
         labs.append(_u32(q.labels))
     cat = lambda xs: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0, np.uint32), dtype=np.uint32)
     return vbase, ebase, cat(offs), cat(nbrs + [np.zeros(1, np.uint32)]), cat(labs)
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through libgpe (rank 0 calls it and hands the bytes to the other ranks)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    if lib().gpe_comm_unique_id(buf):
+        raise GpeError(lib().gpe_last_error(None).decode())
+    return buf.raw
+
+
+class MultiGpu:
+    """One process, several GPUs: contexts in rank order sharing one NCCL communicator (gpe_comm_init_all)."""
+
+    def __init__(self, devices):
+        self.ctxs = [GpeContext(d) for d in devices]
+        self._L = lib()
+        self._arr = (C.c_void_p * len(self.ctxs))(*[c._h for c in self.ctxs])
+        if len(self.ctxs) > 1 and self._L.gpe_comm_init_all(self._arr, len(self.ctxs)):
+            raise GpeError(self._L.gpe_last_error(self.ctxs[0]._h).decode())
+
+    def _ck(self, rc):
+        if rc:
+            msgs = [self._L.gpe_last_error(c._h).decode() for c in self.ctxs]
+            raise GpeError("; ".join(m for m in msgs if m))
+
+    def build(self, g, L, e, p, sorted_nodes, membership, vde):
+        rows = []
+        for c in self.ctxs:
+            c.set_graph(g.offsets, g.nbrs, g.labels)
+            c.set_embeddings(vde)
+            n_rows, _ = c.enumerate(L, sorted_nodes, membership, p)
+            rows.append(c.build_table_shard())
+        return n_rows, rows
+
+    def query_batch(self, queries, limits=None, flags: int = 0) -> np.ndarray:
+        b = self.ctxs[0]._batch_struct(queries, limits)
+        ans = np.zeros(max(len(queries), 1), dtype=np.uint64)
+        self._ck(self._L.gpe_multi_query_batch(self._arr, len(self.ctxs), C.byref(b), flags, _ptr(ans)))
+        return ans[: len(queries)]
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
 
 
 class GpeContext:
@@ -349,6 +407,29 @@ class GpeContext:
     def batch_download(self) -> np.ndarray:
         out = np.zeros(max(self._n_queries, 1), dtype=np.uint64)
         self._ck(self._L.gpe_batch_download(self._h, _ptr(out)))
+        return out[: self._n_queries]
+
+    # ---- multi-GPU with NCCL inside the library (one process per GPU) ----
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self._ck(self._L.gpe_comm_init(self._h, rank, world, buf))
+
+    def comm_info(self):
+        r, w, v = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self._L.gpe_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        return r.value, w.value, v.value
+
+    def build_table_shard(self) -> int:
+        n = C.c_uint64(0)
+        self._ck(self._L.gpe_build_table_shard(self._h, C.byref(n)))
+        return int(n.value)
+
+    def batch_step(self):
+        self._ck(self._L.gpe_batch_step(self._h))
+
+    def batch_finish(self) -> np.ndarray:
+        out = np.zeros(max(self._n_queries, 1), dtype=np.uint64)
+        self._ck(self._L.gpe_batch_finish(self._h, _ptr(out)))
         return out[: self._n_queries]
 
     def batch_cand_info(self):

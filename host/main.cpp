@@ -17,6 +17,9 @@
 //     (custom.h:218-258);
 //   * missing input files are errors (the reference reads zeros silently, main.cpp:80-85);
 //   * -l other than 2 follows the patched-oracle semantics of SURVEY.md F5 (only l=2 and l=3 are built);
+//   * -g N (--gpus N) shards the online stage over N GPUs of this machine, one process: GPU r holds the path table of
+//     the partitions i % N == r (needs -p >= N), the candidate sets are exchanged with NCCL inside libgpe and the join
+//     is split by start candidate (gpe_comm_init_all / gpe_multi_query_batch).  Answers are those of -g 1;
 //   * -q may name a DIRECTORY: every *.graph file in it (sorted by name) is answered in one batch -- one
 //     `<file>: Answer Number: N` line per query, then the batch's total time and queries/s (BASELINE.json config 5).
 #include <algorithm>
@@ -31,6 +34,7 @@
 #include <fstream>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -41,14 +45,14 @@ namespace {
 struct Options {
     std::string file = "../Test/", data = "../Test/data_graph.graph", query = "../Test/query_graph.graph";
     std::string mode = "offline", answers = "MAX";
-    uint32_t partitions = 5, length = 2, embedding = 2;
+    uint32_t partitions = 5, length = 2, embedding = 2, gpus = 1;
 };
 
 bool parse(int argc, char **argv, Options &o) {
     struct Opt { const char *s, *l; int id; };
     static const Opt opts[] = {{"-f", "--file", 0}, {"-d", "--data", 1}, {"-q", "--query", 2}, {"-m", "--mode", 3},
                                {"-p", "--partition", 4}, {"-l", "--length", 5}, {"-e", "--embedding", 6},
-                               {"-n", "--answers", 7}};
+                               {"-n", "--answers", 7}, {"-g", "--gpus", 8}};
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i], val;
         int id = -1;
@@ -59,7 +63,7 @@ bool parse(int argc, char **argv, Options &o) {
             if (a.rfind(s, 0) == 0 && a.size() > 2 && a[1] != '-') { id = op.id; val = a.substr(a[2] == '=' ? 3 : 2); break; }
         }
         if (a == "-h" || a == "--help") {
-            std::puts("usage: main [-f dir/] [-d data.graph] [-q query.graph] [-m offline|online] [-p N] [-l N] [-e N] [-n MAX|N]");
+            std::puts("usage: main [-f dir/] [-d data.graph] [-q query.graph] [-m offline|online] [-p N] [-l N] [-e N] [-n MAX|N] [-g GPUS]");
             std::exit(0);
         }
         if (id < 0) { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return false; }
@@ -72,6 +76,7 @@ bool parse(int argc, char **argv, Options &o) {
             case 5: o.length = (uint32_t)std::stoul(val); break;
             case 6: o.embedding = (uint32_t)std::stoul(val); break;
             case 7: o.answers = val; break;
+            case 8: o.gpus = (uint32_t)std::stoul(val); break;
         }
     }
     return true;
@@ -249,9 +254,46 @@ int main(int argc, char **argv) {
         }
         std::vector<double> x((size_t)G.V * o.embedding), vde((size_t)G.V * o.embedding);
         CK(ctx, gpe_host_gen_vde(G.V, G.off.data(), G.nbr.data(), G.lab.data(), o.embedding, x.data(), vde.data()));
-        CK(ctx, gpe_set_embeddings(ctx, o.embedding, vde.data()));
-        uint64_t table_rows = 0;
-        CK(ctx, gpe_build_table(ctx, nullptr, &table_rows));
+        // -g N: one context per GPU (context 0 is the one that enumerated above), one communicator, sharded tables
+        const int n_gpu = (int)std::max<uint32_t>(o.gpus, 1);
+        if ((uint32_t)n_gpu > o.partitions) { std::fprintf(stderr, "-g %d needs -p >= %d (GPU r holds the partitions i %% %d == r)\n", n_gpu, n_gpu, n_gpu); return 1; }
+        std::vector<gpe_ctx *> ctxs(1, ctx);
+        for (int d = 1; d < n_gpu; d++) {
+            gpe_ctx *cd = nullptr;
+            if (gpe_create(d, &cd) != GPE_OK) { std::fprintf(stderr, "libgpe: GPU %d: %s\n", d, gpe_last_error(nullptr)); return 1; }
+            ctxs.push_back(cd);
+        }
+        if (n_gpu > 1) CK(ctx, gpe_comm_init_all(ctxs.data(), n_gpu));
+        {
+            std::vector<int> rcs(n_gpu, GPE_OK);
+            std::vector<std::thread> pool;
+            for (int d = 0; d < n_gpu; d++)
+                pool.emplace_back([&, d] {
+                    gpe_ctx *cd = ctxs[d];
+                    int rc = GPE_OK;
+                    if (d > 0) {
+                        rc = gpe_set_graph(cd, G.V, G.off.data(), G.nbr.data(), G.lab.data());
+                        if (!rc) rc = gpe_enumerate(cd, L, sorted.data(), member.data(), o.partitions, nullptr, nullptr);
+                    }
+                    if (!rc) rc = gpe_set_embeddings(cd, o.embedding, vde.data());
+                    uint64_t table_rows = 0;
+                    if (!rc) rc = gpe_build_table_shard(cd, &table_rows);
+                    rcs[d] = rc;
+                });
+            for (auto &t : pool) t.join();
+            for (int d = 0; d < n_gpu; d++)
+                if (rcs[d] != GPE_OK) { std::fprintf(stderr, "libgpe: GPU %d: %s\n", d, gpe_last_error(ctxs[d])); return 1; }
+        }
+        auto run_batch = [&](const gpe_batch *b, uint64_t *out) {
+            return n_gpu == 1 ? gpe_query_batch(ctx, b, 0, out) : gpe_multi_query_batch(ctxs.data(), n_gpu, b, 0, out);
+        };
+        auto report = [&](int rc) {
+            if (rc == GPE_OK) return false;
+            for (gpe_ctx *cd : ctxs)
+                if (gpe_last_error(cd)[0]) std::fprintf(stderr, "libgpe: %s\n", gpe_last_error(cd));
+            return true;
+        };
+        auto destroy_all = [&] { for (gpe_ctx *cd : ctxs) gpe_destroy(cd); };
 
         struct stat st_q{};
         if (stat(o.query.c_str(), &st_q) == 0 && S_ISDIR(st_q.st_mode)) {  // a directory of queries: one batch
@@ -279,13 +321,13 @@ int main(int argc, char **argv) {
             std::vector<uint64_t> limits(files.size(), limit), answers(files.size(), 0);
             gpe_batch batch{(uint32_t)files.size(), vbase.data(), ebase.data(), offs.data(), nbrs.data(), labs.data(), limits.data()};
             auto t0 = std::chrono::high_resolution_clock::now();
-            CK(ctx, gpe_query_batch(ctx, &batch, 0, answers.data()));
+            if (report(run_batch(&batch, answers.data()))) return 1;
             auto t1 = std::chrono::high_resolution_clock::now();
             double ms = std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count() / 1e6;
             for (size_t i = 0; i < files.size(); i++)
                 std::cout << files[i] << ": Answer Number: " << (uint32_t)answers[i] << std::endl;
             std::cout << "Queries: " << files.size() << " Query Time (ms): " << ms << " Queries/s: " << files.size() / (ms / 1e3) << std::endl;
-            gpe_destroy(ctx);
+            destroy_all();
             return 0;
         }
         Graph Q;
@@ -298,10 +340,12 @@ int main(int argc, char **argv) {
         std::cout << plan_size << std::endl;  // custom.h:630
         uint64_t answer = 0;
         auto t0 = std::chrono::high_resolution_clock::now();  // plan + filter + refinement, as main.cpp:148-179 sums
-        CK(ctx, gpe_query_batch(ctx, &batch, 0, &answer));
+        if (report(run_batch(&batch, &answer))) return 1;
         auto t1 = std::chrono::high_resolution_clock::now();
         double ms = std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count() / 1e6;
         std::cout << "Answer Number: " << (uint32_t)answer << " Query Time (ms): " << ms << std::endl;  // main.cpp:179
+        destroy_all();
+        return 0;
     }
     gpe_destroy(ctx);
     return 0;

@@ -148,7 +148,9 @@ int gpe_query_batch(gpe_ctx *ctx, const gpe_batch *batch, uint32_t flags, uint64
 int gpe_batch_cand_info(gpe_ctx *ctx, uint64_t *n_slots, uint64_t *n_cand_total);
 int gpe_batch_cand_export(gpe_ctx *ctx, void *d_counts_u32 /*n_slots*/, void *d_cand_u32 /*n_cand_total*/);
 /* Replace the batch's candidate sets by the union of `world` shards' lists.  d_counts: world x n_slots
- * (u32), d_cand: world x stride (u32), shard r's lists concatenated at d_cand + r*stride. */
+ * (u32), d_cand: world x stride (u32), shard r's lists concatenated at d_cand + r*stride.  The lists that
+ * gpe_batch_cand_export writes are in the library's device-side id space (vertices numbered by (label, id): the same
+ * numbering on every GPU that loaded the same graph), ascending inside a slot; they are meant for this call. */
 int gpe_batch_cand_merge(gpe_ctx *ctx, uint32_t world, const void *d_counts, const void *d_cand, uint64_t stride);
 /* The same exchange in bitmap form, the one the multi-GPU engine uses: fixed size (no count exchange, no host
  * sync), one all-gather, and the union is fused into the compaction's popcount pass.
@@ -157,7 +159,8 @@ int gpe_batch_cand_merge(gpe_ctx *ctx, uint32_t world, const void *d_counts, con
  *                          = the i-th vertex (ascending id) of the slot's label -- identical layout on every shard;
  *   gpe_batch_bitmap_merge d_all = `world` such bitmaps one after the other (the all-gather's output, device memory);
  *                          replaces the local bitmaps by their OR and builds the sorted candidate lists.
- * All three are asynchronous on the context's stream up to the one host read of the candidate total. */
+ * All three are asynchronous on the context's stream: no host sync (the candidate total stays on the device until
+ * gpe_batch_download or a candidate getter needs it). */
 int gpe_batch_scan(gpe_ctx *ctx);
 int gpe_batch_bitmap(gpe_ctx *ctx, void **d_bitmap, uint64_t *n_bytes);
 int gpe_batch_bitmap_merge(gpe_ctx *ctx, uint32_t world, const void *d_all);
@@ -165,12 +168,43 @@ int gpe_batch_bitmap_merge(gpe_ctx *ctx, uint32_t world, const void *d_all);
 int gpe_batch_get_candidates(gpe_ctx *ctx, uint64_t *cand_offsets /*n_slots+1*/, uint32_t *cand /*or NULL*/);
 int gpe_batch_get_plan(gpe_ctx *ctx, uint32_t *order /*n_slots*/, uint32_t *pivot /*n_slots*/);
 
+/* ---- multi-GPU (replaces the per-partition OpenMP loop + serial merge, main.cpp:160-172) -----------------------------
+ * The path table is sharded by the reference's own partitions: a path belongs to the partition of its FIRST vertex
+ * (custom.h:74), GPU r of N holds the partitions i % N == r (enumerate with p >= N).  Per batch there is ONE exchange --
+ * an all-gather of the shards' candidate bitmaps, whose union is fused into the compaction -- then every GPU joins the
+ * start candidates idx % N == r and the match counts are summed.  NCCL is bound at run time (libnccl.so.2); a
+ * single-GPU user never loads it.  Two ways to run it:
+ *   one process per GPU:  rank 0 calls gpe_comm_unique_id and hands the 128 bytes to the others (any transport);
+ *                         every rank: gpe_comm_init, gpe_build_table_shard, then per batch gpe_batch_upload,
+ *                         gpe_batch_step, gpe_batch_finish (collective calls: same order on every rank);
+ *   one process, N GPUs:  N contexts, gpe_comm_init_all, gpe_build_table_shard on each, then gpe_multi_query_batch
+ *                         (or its three stages) -- what `host/main -g N` does. */
+#define GPE_COMM_ID_BYTES 128
+int gpe_comm_unique_id(void *id_out /*GPE_COMM_ID_BYTES*/);
+int gpe_comm_init(gpe_ctx *ctx, int rank, int world, const void *id /*GPE_COMM_ID_BYTES*/);
+int gpe_comm_init_all(gpe_ctx **ctxs, int n);
+int gpe_comm_destroy(gpe_ctx *ctx); /* also done by gpe_destroy */
+int gpe_comm_info(gpe_ctx *ctx, int *rank, int *world, int *nccl_version /*e.g. 22703, 0 if NCCL is not loaded*/);
+/* gpe_build_table for the partitions of this context's rank (all of them without a communicator). */
+int gpe_build_table_shard(gpe_ctx *ctx, uint64_t *n_table_rows);
+/* Stages 2 + 3 of an uploaded batch, asynchronous on the context's stream: scan of the local shard, candidate
+ * exchange, compaction, join of this rank's start candidates.  Without a communicator: gpe_batch_filter + gpe_batch_join. */
+int gpe_batch_step(gpe_ctx *ctx);
+/* Stage 4: wait, sum the shards' counts (all-reduce), apply the limit rule: answers as gpe_query_batch returns them. */
+int gpe_batch_finish(gpe_ctx *ctx, uint64_t *answers /*n_queries*/);
+/* One thread driving N contexts (contexts of gpe_comm_init_all, in rank order): the batch is planned once on the host
+ * and uploaded to every GPU; the GPUs run concurrently, NCCL calls are grouped. */
+int gpe_multi_batch_upload(gpe_ctx **ctxs, int n, const gpe_batch *batch, uint32_t flags);
+int gpe_multi_batch_step(gpe_ctx **ctxs, int n);
+int gpe_multi_batch_finish(gpe_ctx **ctxs, int n, uint64_t *answers);
+int gpe_multi_query_batch(gpe_ctx **ctxs, int n, const gpe_batch *batch, uint32_t flags, uint64_t *answers);
+
 /* ---- GNN-PGE: the reference's sibling variant of the filter (GNN-PGE/src/main.cpp, GNN-PGE/include/custom.h) --------
  * One row per data VERTEX: the bounding box of the embeddings of all simple paths of `pl` vertices that start at it
  * ("path group", src/main.cpp:91-176), over the dominance embeddings and over the label embeddings.  A data vertex v
  * is a candidate of a query vertex u iff label and degree fit, the label boxes overlap and v's upper corner is not
  * below u's lower corner (include/custom.h:332-367).  Matching order and join are shared with the path filter.
- * STATUS: compiled, NOT yet verified on a GPU (written after round 1's GPU budget was spent); its oracle is pinned. */
+ * Verified on B200 against the golden vectors of the unmodified GNN-PGE binary (tests/test_gpu_pge.py). */
 /* x: the label embeddings per vertex (V x e) as gpe_host_gen_vde returns them; needs gpe_set_graph + gpe_set_embeddings.
  * pl = vertices per path (GNN-PGE's -l, default 2; 1..4 here). */
 int gpe_pge_build(gpe_ctx *ctx, uint32_t pl, const double *x);
