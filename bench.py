@@ -189,6 +189,96 @@ def run_reference(args):
     return 0
 
 
+def run_pge(args):
+    """The GNN-PGE variant of the filter on one GPU: per-vertex path groups built on the device, the
+    label classes the batch asks for scanned (k4_pge_scan), then the shared compaction / order / join.  Same metric."""
+    import torch
+    from gnn_pe_b200 import gpe
+    from oracle import oracle
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("--filter pge runs on one GPU (one row per data vertex: the table is small; replicas only)")
+    w, g, queries = load_workload(args.workload)
+    e, pl = w["e"], 2  # GNN-PGE's default path length: 2 vertices per path
+    ctx = gpe.GpeContext(0)
+    x, vde = gpe.host_gen_vde(g.offsets, g.nbrs, g.labels, e)
+    ctx.set_graph(g.offsets, g.nbrs, g.labels)
+    ctx.set_embeddings(vde)
+    t0 = time.perf_counter()
+    ctx.pge_build(pl, x)
+    build_ms = (time.perf_counter() - t0) * 1e3
+    nq = len(queries)
+    ctx.pge_batch_upload(queries)
+    for _ in range(max(args.warmup, 3)):
+        ctx.pge_batch_filter()
+        ctx.batch_join()
+    answers = ctx.batch_download()
+    ctx.collect_timings()
+    ctx.set_timing(2)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    sampler = ClockSampler(0)
+    sampler.start()
+    with torch.cuda.stream(stream):
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            ctx.pge_batch_filter()
+            ctx.batch_join()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+    stages = ctx.collect_timings()
+    ctx.set_timing(0)
+    assert np.array_equal(answers, ctx.batch_download())
+    st = ctx.stats()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        a3 = ctx.pge_query_batch(queries)
+    e2e_s = time.perf_counter() - t1
+    assert np.array_equal(a3, np.minimum(answers, gpe.LIMIT_MAX))
+    s3 = ctx.stats()
+    clocks = sampler.stop()
+    peak, peak_src = peaks()
+    pde = pl * e
+    row_bytes = 3 * pde * 8 + 4  # what the leaf test reads: label box lo/hi, upper corner of the embedding box, degree
+    scan_ms = stages["scan"]["ms"] / max(stages["scan"]["launches"], 1)
+    scan_bytes = st["scan_rows"] * row_bytes
+    cpu = None
+    if not args.no_cpu_baseline:
+        og = oracle.OracleGraph.from_csr(g.offsets, g.nbrs, g.labels)
+        t0, n, ok = time.time(), 0, True
+        oracle.pge_groups(og, pl, e)
+        t_groups = time.time() - t0
+        t0 = time.time()
+        for i, q in enumerate(queries):
+            oq = oracle.OracleGraph.from_csr(q.offsets, q.nbrs, q.labels)
+            ok = ok and oracle.pge_online(og, oq, pl, e) == int(min(answers[i], gpe.LIMIT_MAX))
+            n += 1
+            if time.time() - t0 > args.cpu_baseline_seconds:
+                break
+        cpu = dict(value=n / (time.time() - t0), unit="queries/s", cores=1, kind="port",
+                   sample=f"first {n} of {nq} queries (orc_pge_online: groups recomputed per call), data-side groups {t_groups:.1f} s",
+                   parity_with_gpu_answers=ok)
+    out = dict(metric="online queries/sec", value=nq * args.steps / (ms / 1e3), unit="queries/s", n_gpus=1, steps=args.steps,
+               warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+               dtype="f64", data="synthetic", filter="gnn-pge",
+               config=dict(workload=w["desc"], name=args.workload, filter=f"GNN-PGE path groups, pl={pl}, e={e}"),
+               gpu_launches=int(st["kernel_launches"]), clocks=clocks,
+               e2e=dict(value=nq * args.steps / e2e_s, unit="queries/s", h2d_bytes_per_step=int(s3["h2d_bytes"]),
+                        d2h_bytes_per_step=int(s3["d2h_bytes"]), ms_per_step=1e3 * e2e_s / args.steps, api="gpe_pge_query_batch"),
+               roofline=dict(bound="hbm", kernel=f"k4_pge_scan_kernel<{pde}>", achieved=scan_bytes / max(scan_ms, 1e-9) / 1e6, peak=peak,
+                             unit="GB/s", frac=scan_bytes / max(scan_ms, 1e-9) / 1e6 / peak, traffic=None, peak_source=peak_src,
+                             algorithmic_bytes_per_launch=int(scan_bytes), rows_per_launch=int(st["scan_rows"]), row_bytes=row_bytes,
+                             ms_per_launch=scan_ms, stage_ms_per_step={k: v["ms"] / args.steps for k, v in stages.items()},
+                             note="one row per data vertex of the label classes the batch asks for; at 1 M vertices the launch is "
+                                  "tens of microseconds: latency, not bandwidth"),
+               cpu_baseline=cpu, build=dict(pge_build_ms=build_ms), answers_checksum=int(np.minimum(answers, gpe.LIMIT_MAX).sum()),
+               n_candidates=int(st["n_candidates"]))
+    print(json.dumps(out))
+    ctx.close()
+    return 0
+
+
 def expected_answers(name):
     """Oracle answers of sampled queries (tests/golden/config_answers.json, made by tests/golden/make_config_answers.py)."""
     path = os.path.join(ROOT, "tests", "golden", "config_answers.json")
@@ -216,10 +306,14 @@ def main():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-streaming", action="store_true")
+    ap.add_argument("--filter", default="path", choices=["path", "pge"],
+                    help="path: GNN-PE's path-table dominance scan (the headline); pge: the GNN-PGE per-vertex path-group filter")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.filter == "pge":
+        return run_pge(args)
 
     import torch  # before libgpe: the process then carries ONE NCCL (PyTorch's bundled copy), which libgpe binds at run time
     import torch.distributed as dist
@@ -395,7 +489,13 @@ def main():
                                  "reference's refinement; the real binary's indexed path is in cpu_baseline_real",
                             sample=f"first {r['n']} of {nq} queries, full data graph, {r['seconds']:.1f} s",
                             parity_with_gpu_answers=r["parity_ok"])
+    per_rank = None
     if world > 1:
+        mine = dict(rank=rank, table_rows=int(table_rows), stage_ms_per_step=roofline["stage_ms_per_step"],
+                    join_tests=int(st_step["join_steps"]), scan_rows=int(st_step["scan_rows"]))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
         dist.barrier()
 
     if rank == 0:
@@ -410,7 +510,7 @@ def main():
                                          f"{table_rows * (row_bytes + 4 * L) / 1e9:.1f} GB table (> 126 MB L2), no flush"),
                    gpu_launches=int(launches), clocks=clocks, e2e=e2e, roofline=roofline, join=join, cpu_baseline=cpu_baseline,
                    cpu_baseline_real=static_json("profiles", "cpu_baseline_real.json"),
-                   build=build, nccl=dict(version=nccl_version, ranks=world, via="libgpe gpe_comm_init (ncclCommInitRank)") if world > 1 else None,
+                   per_rank=per_rank, build=build, nccl=dict(version=nccl_version, ranks=world, via="libgpe gpe_comm_init (ncclCommInitRank)") if world > 1 else None,
                    answers_checksum=int(answers.sum()), answers_nonzero=int((answers > 0).sum()),
                    oracle_parity=dict(checked=len([i for i in exp if i < nq]), mismatches=bad, ok=not bad,
                                       source="tests/golden/config_answers.json (oracle.online_streaming on the CPU)"))

@@ -249,6 +249,11 @@ int cand_total(gpe_ctx *c, bool *overflow) {
     c->stats.n_candidates = pin[0];
     c->stats.scan_items = pin[1];
     c->stats.scan_rows = pin[1] * kTileRows;
+    if (c->b_pge_rows_pending) {  // GNN-PGE scan: rows = data vertices of the label classes some query vertex asked for
+        c->stats.scan_rows = pin[4];
+        c->stats.scan_items = (pin[4] + 255) / 256;
+        c->b_pge_rows_pending = false;
+    }
     c->b_cand_known = true;
     if (pin[3] && overflow) *overflow = true;
     return GPE_OK;
@@ -311,6 +316,7 @@ int run_scan(gpe_ctx *c) {
 }
 
 int run_filter(gpe_ctx *c) {
+    c->b_sparse_used = false;
     int rc = run_scan(c);
     if (rc) return rc;
     if ((rc = compact_candidates(c))) return rc;
@@ -1146,6 +1152,17 @@ int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) try {
     static_assert(sizeof(JoinQueue) <= 16 * sizeof(u64), "pinned layout");
     if (nq) GPE_CUDA(c, cudaMemcpyAsync(pin_flags, c->d_answers.as<u64>() + nq + 8, nq * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->b_sparse_used) {  // sparse exchange: did every shard's non-zero words fit the buffer?  (same numbers on every rank)
+        const u64 *h = c->h_pin4.as<u64>();
+        u64 mx = 0;
+        for (int r = 0; r < c->comm_world; r++) mx = std::max(mx, h[2 * r]);
+        c->sparse_seen_max = std::max(c->sparse_seen_max, mx);
+        c->need_dense_redo = mx > c->sparse_cap;  // gpe_batch_finish / gpe_multi_batch_finish redo the step (a collective)
+        if (c->need_dense_redo) {
+            for (u32 q = 0; q < c->b_nq; q++) raw_counts[q] = 0;
+            return GPE_OK;
+        }
+    }
     if (!c->b_cand_known) {  // first look at what the compaction reported: did the candidate lists fit their buffer?
         bool overflow = false;
         if (int rc = cand_total(c, &overflow)) return rc;
@@ -1304,6 +1321,7 @@ int gpe_pge_build(gpe_ctx *c, uint32_t pl, const double *x) try {
     if (pl < 1 || pl > (u32)kMaxL) return c->fail(GPE_ERR_UNSUPPORTED, "GNN-PGE path groups are built for 1..%d vertices per path", kMaxL);
     GPE_CUDA(c, cudaSetDevice(c->device));
     const u32 pde = pl * c->e;
+    if (!k4_pge_supported(pde)) return c->fail(GPE_ERR_UNSUPPORTED, "no GNN-PGE scan kernel compiled for pl*e = %u", pde);
     GPE_CUDA(c, c->d_pge_x.reserve(std::max<size_t>((size_t)c->V * c->e, 1) * sizeof(double)));
     GPE_CUDA(c, c->d_pge.reserve(k4_pge_bytes(c->V, pde)));
     if (c->V) GPE_CUDA(c, cudaMemcpyAsync(c->d_pge_x.p, x, (size_t)c->V * c->e * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1440,12 +1458,15 @@ int gpe_pge_batch_filter(gpe_ctx *c) {
                                 reinterpret_cast<const u32 *>(base + o_deg), reinterpret_cast<const double *>(base + o_d0),
                                 reinterpret_cast<const double *>(base + o_d0 + dsz),
                                 reinterpret_cast<const double *>(base + o_d0 + 2 * dsz), c->d_bitmap.as<u32>(), c->b_words,
-                                c->d_survivors.as<u64>(), c->sm_count, c->stream));
+                                c->d_survivors.as<u64>(), c->d_survivors.as<u64>() + 1, c->sm_count, c->stream));
         c->stats.scan_launches++;
         c->stats.kernel_launches++;
     }
+    GPE_CUDA(c, c->h_pin3.reserve(8 * sizeof(u64)));
+    GPE_CUDA(c, cudaMemcpyAsync(c->h_pin3.as<u64>() + 4, c->d_survivors.as<u64>() + 1, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     int rc = compact_candidates(c);
     if (rc) return rc;
+    c->b_pge_rows_pending = true;  // cand_total() turns h_pin3[4] into stats.scan_rows (rows of the classes asked for)
     c->b_filtered = true;
     c->b_cand_external = false;
     c->b_cand_clean = true;  // label equal and degree >= hold for every candidate; the bitmaps are on the device
@@ -1559,14 +1580,58 @@ int gpe_build_table_shard(gpe_ctx *c, uint64_t *n_table_rows) {
 
 namespace {
 // stage 2 + 3 of one context up to the exchange / after it (everything asynchronous on the context's stream)
+// The exchange has two forms (both ONE fixed-size all-gather, no size exchange, no host sync):
+//   dense:  the bitmaps as they are; the union is fused into the compaction's popcount pass;
+//   sparse: the non-zero words as (index, word) pairs in a buffer whose capacity follows what earlier batches needed --
+//           chosen when that is at most a quarter of the dense size (large label alphabets: config 3 / 5).  A shard that
+//           outgrows the capacity is noticed after the step (gpe_batch_download) and the step is redone dense.
+bool sparse_choice(gpe_ctx *c, u64 &cap) {
+    const u64 words = (u64)c->b_slots * c->b_words;
+    cap = std::max<u64>(2 * c->sparse_seen_max, 1ull << 16);
+    if (const char *e = getenv("GPE_SPARSE_CAP")) cap = std::max<u64>(strtoull(e, nullptr, 10), 1);  // tests: force the dense redo
+    if (const char *e = getenv("GPE_EXCHANGE")) {
+        if (!strcmp(e, "dense")) return false;
+        if (!strcmp(e, "sparse")) return !c->force_dense && words < (1ull << 32);
+    }
+    return !c->force_dense && words < (1ull << 32) && cap * 8 + 16 <= words * 4 / 4;
+}
+int sharded_before_exchange(gpe_ctx *c) {  // after the scan: pack the local bitmaps when the exchange is sparse
+    u64 cap = 0;
+    c->b_sparse_used = sparse_choice(c, cap);
+    if (!c->b_sparse_used) return GPE_OK;
+    c->sparse_cap = cap;
+    const u64 stride = 16 + cap * 8;
+    GPE_CUDA(c, c->d_sparse.reserve(stride));
+    GPE_CUDA(c, c->d_all_bitmaps.reserve(stride * c->comm_world));
+    GPE_CUDA(c, k3_sparse_pack(c->d_bitmap.as<u32>(), (u64)c->b_slots * c->b_words, cap, c->d_sparse.p, c->sm_count, c->stream));
+    c->stats.kernel_launches++;
+    return GPE_OK;
+}
 int sharded_exchange_enqueue(gpe_ctx *c) {  // between ncclGroupStart/End when one thread drives several contexts
+    if (c->b_sparse_used) {
+        GPE_NCCL(c, nccl_api().AllGather(c->d_sparse.p, c->d_all_bitmaps.p, 16 + c->sparse_cap * 8, ncclUint8, (ncclComm_t)c->comm, c->stream));
+        c->stats.exchange_bytes = (16 + c->sparse_cap * 8) * (u64)c->comm_world;
+        return GPE_OK;
+    }
     const u64 bytes = (u64)c->b_slots * c->b_words * sizeof(u32);
     GPE_CUDA(c, c->d_all_bitmaps.reserve(std::max<u64>(bytes * c->comm_world, 16)));
     if (bytes) GPE_NCCL(c, nccl_api().AllGather(c->d_bitmap.p, c->d_all_bitmaps.p, bytes, ncclUint8, (ncclComm_t)c->comm, c->stream));
+    c->stats.exchange_bytes = bytes * (u64)c->comm_world;
     return GPE_OK;
 }
 int sharded_after_exchange(gpe_ctx *c) {
-    int rc = compact_candidates(c, c->d_all_bitmaps.as<u32>(), (u32)c->comm_world);
+    int rc;
+    if (c->b_sparse_used) {
+        const u64 stride = 16 + c->sparse_cap * 8;
+        GPE_CUDA(c, k3_sparse_merge(c->d_all_bitmaps.p, stride, (u32)c->comm_world, (u32)c->comm_rank, c->sparse_cap,
+                                    c->d_bitmap.as<u32>(), c->sm_count, c->stream));
+        c->stats.kernel_launches++;
+        GPE_CUDA(c, c->h_pin4.reserve((size_t)kMaxDevices * 2 * sizeof(u64)));
+        GPE_CUDA(c, cudaMemcpy2DAsync(c->h_pin4.p, 16, c->d_all_bitmaps.p, stride, 16, (size_t)c->comm_world, cudaMemcpyDeviceToHost, c->stream));
+        rc = compact_candidates(c);
+    } else {
+        rc = compact_candidates(c, c->d_all_bitmaps.as<u32>(), (u32)c->comm_world);
+    }
     if (rc) return rc;
     c->b_filtered = true;
     c->b_cand_external = true;
@@ -1585,6 +1650,7 @@ int gpe_batch_step(gpe_ctx *c) {
     }
     // (a communicator of one rank takes the same route: the exchange is then a copy)
     if (int rc = run_scan(c)) return rc;
+    if (int rc = sharded_before_exchange(c)) return rc;
     if (int rc = sharded_exchange_enqueue(c)) return rc;
     return sharded_after_exchange(c);
 }
@@ -1592,6 +1658,14 @@ int gpe_batch_step(gpe_ctx *c) {
 int gpe_batch_finish(gpe_ctx *c, uint64_t *answers) {
     if (!c || !answers) return GPE_ERR_INVALID;
     if (int rc = gpe_batch_download(c, answers)) return rc;  // this shard's raw counts (repaired locally if need be)
+    if (c->need_dense_redo) {  // a shard outgrew the sparse exchange buffer (every rank sees that): once more, dense
+        c->force_dense = true;
+        int rc = gpe_batch_step(c);
+        c->force_dense = false;
+        if (rc) return rc;
+        if ((rc = gpe_batch_download(c, answers))) return rc;
+        c->stats.exchange_redos++;
+    }
     const u32 nq = c->b_nq;
     if (c->comm && nq) {  // C2: sum of the shards' counts (each at most 2^48: no wrap)
         GPE_CUDA(c, c->d_reduce.reserve((size_t)nq * sizeof(u64)));
@@ -1632,6 +1706,7 @@ int gpe_multi_batch_step(gpe_ctx **ctxs, int n) {
     for (int i = 0; i < n; i++) {
         GPE_CUDA(ctxs[i], cudaSetDevice(ctxs[i]->device));
         if (int rc = run_scan(ctxs[i])) return rc;
+        if (int rc = sharded_before_exchange(ctxs[i])) return rc;
     }
     GPE_NCCL(ctxs[0], nccl_api().GroupStart());
     for (int i = 0; i < n; i++) {
@@ -1650,10 +1725,20 @@ int gpe_multi_batch_finish(gpe_ctx **ctxs, int n, uint64_t *answers) try {
     if (!ctxs || n < 1 || !answers) return GPE_ERR_INVALID;
     const u32 nq = ctxs[0]->b_nq;
     std::vector<u64> part(nq);
-    for (u32 q = 0; q < nq; q++) answers[q] = 0;
-    for (int i = 0; i < n; i++) {  // the GPUs ran concurrently; the host sum replaces the all-reduce (one process)
-        if (int rc = gpe_batch_download(ctxs[i], part.data())) return rc;
-        for (u32 q = 0; q < nq; q++) answers[q] += part[q];
+    for (int attempt = 0; attempt < 2; attempt++) {
+        for (u32 q = 0; q < nq; q++) answers[q] = 0;
+        bool redo = false;
+        for (int i = 0; i < n; i++) {  // the GPUs ran concurrently; the host sum replaces the all-reduce (one process)
+            if (int rc = gpe_batch_download(ctxs[i], part.data())) return rc;
+            redo = redo || ctxs[i]->need_dense_redo;
+            for (u32 q = 0; q < nq; q++) answers[q] += part[q];
+        }
+        if (!redo) break;
+        // a shard outgrew the sparse exchange buffer: the step once more with the dense exchange, on every GPU
+        for (int i = 0; i < n; i++) ctxs[i]->force_dense = true;
+        int rc = gpe_multi_batch_step(ctxs, n);
+        for (int i = 0; i < n; i++) { ctxs[i]->force_dense = false; ctxs[i]->stats.exchange_redos++; }
+        if (rc) return rc;
     }
     for (u32 q = 0; q < nq; q++) answers[q] = gpe_clamp_answer(answers[q], ctxs[0]->h_limits[q]);
     return GPE_OK;

@@ -230,7 +230,7 @@ struct gpe_ctx {
     u64 bloom_bits = 0;
     gpe::DevBuf d_pge, d_pge_x, d_pge_q;  // GNN-PGE: path groups of the data vertices, label embeddings, query records
     u32 pge_pl = 0;
-    bool have_pge = false, b_pge = false;
+    bool have_pge = false, b_pge = false, b_pge_rows_pending = false;
     u32 b_rank = 0, b_world = 1;
     gpe::DevBuf d_items, d_ready, d_jq, d_init, d_kids;  // exported join work items, their publication flags, the queue header, start tickets
     u32 join_epoch = 0;
@@ -276,7 +276,10 @@ struct gpe_ctx {
     // multi-GPU (gpe_comm_*): NCCL communicator of this context, its rank, the all-gathered shard bitmaps
     void *comm = nullptr;
     int comm_rank = 0, comm_world = 1;
-    gpe::DevBuf d_all_bitmaps, d_reduce;
+    gpe::DevBuf d_all_bitmaps, d_reduce, d_sparse;
+    u64 sparse_cap = 0, sparse_seen_max = 0;  // pairs per shard buffer of the sparse exchange; most non-zero words a shard ever had
+    bool b_sparse_used = false, force_dense = false, need_dense_redo = false;
+    gpe::PinnedBuf h_pin4;                    // the shards' non-zero word counts of the last sparse exchange
     gpe::LabelTable label_table;  // label embeddings of the queries seen so far (host planning)
     u64 b_chunks_per_slot = 0;
 
@@ -362,6 +365,10 @@ cudaError_t k3_compact(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slo
 cudaError_t k3_scatter(const u32 *counts, const u32 *cand, u64 stride, u32 world, u32 n_slots, const u32 *slot_label,
                        const u32 *lcoff, u32 n_labels, u32 *bitmap, u64 words_per_slot, u64 *prefix_tmp /*world x n_slots*/,
                        cudaStream_t s);
+// sparse candidate exchange: non-zero bitmap words as (index, word) pairs in a fixed-capacity buffer (u64 count | u64 | pairs)
+cudaError_t k3_sparse_pack(const u32 *bitmap, u64 n_words, u64 cap, void *buf, int sm_count, cudaStream_t s);
+cudaError_t k3_sparse_merge(const void *all, u64 stride_bytes, u32 world, u32 my_rank, u64 cap, u32 *bitmap, int sm_count,
+                            cudaStream_t s);
 cudaError_t k3_counts_from_offsets(const u64 *cand_off, u32 n_slots, u32 *counts, cudaStream_t s);
 cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebase, const u32 *q_offsets,
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
@@ -402,7 +409,9 @@ PgeView k4_pge_view(void *buf, u32 V, u32 pde);
 cudaError_t k4_pge_groups(const GraphView &g, u32 pl, const double *d_x, const PgeView &p, int sm_count, cudaStream_t s);
 cudaError_t k4_pge_scan(const PgeView &p, u32 V, u32 pde, u32 n_labels, const u32 *lcoff, const u32 *label_slot_off,
                         const u32 *slot_list, const u32 *q_deg, const double *q_pg_lo, const double *q_plg_lo,
-                        const double *q_plg_hi, u32 *bitmap, u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s);
+                        const double *q_plg_hi, u32 *bitmap, u64 words_per_slot, u64 *survivors, u64 *rows_examined /*rows of the
+                        label classes some query vertex asks for*/, int sm_count, cudaStream_t s);
+bool k4_pge_supported(u32 pde);
 cudaError_t k4_pge_dump(const PgeView &p, const GraphView &g, u32 pde, double *pg, double *plg, unsigned char *has,
                         cudaStream_t s);
 

@@ -147,6 +147,43 @@ __global__ void __launch_bounds__(256) k3_compact_kernel(const u32 *__restrict__
     }
 }
 
+// ---- sparse form of the candidate exchange ---------------------------------------------------------------------
+// On large label alphabets the class-local bitmaps are almost empty (config 5: 10^4 slots x 25 KB, a few hundred
+// candidates each), and all-gathering them dense would dominate the step.  A shard packs its non-zero words as
+// (word index, word) pairs into a buffer of fixed capacity -- the all-gather stays ONE fixed-size collective without a
+// size exchange -- and every GPU ORs the other shards' pairs into its own bitmaps.  header[0] counts the non-zero
+// words; more than the capacity means the step is redone with the dense exchange (checked on the host after the step).
+__global__ void __launch_bounds__(256) k3_sparse_pack_kernel(const u32 *__restrict__ bitmap, u64 n_words, u64 cap,
+                                                             unsigned long long *header, uint2 *pairs) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = lanemask_lt();
+    const u64 n_round = (n_words + 31) / 32 * 32;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (u64)gridDim.x * blockDim.x) {
+        const u32 w = i < n_words ? __ldcs(bitmap + i) : 0u;
+        const unsigned m = __ballot_sync(kFull, w != 0);
+        if (!m) continue;
+        u64 base = 0;
+        if (lane == 0) base = atomicAdd(header, (unsigned long long)__popc(m));
+        base = __shfl_sync(kFull, base, 0) + __popc(m & lt);
+        if (w && base < cap) pairs[base] = make_uint2((u32)i, w);
+    }
+}
+
+// all: `world` exchange buffers one after the other (stride_bytes apart): u64 count | u64 | cap x (index, word)
+__global__ void __launch_bounds__(256) k3_sparse_merge_kernel(const unsigned char *__restrict__ all, u64 stride_bytes,
+                                                              u32 world, u32 my_rank, u64 cap, u32 *bitmap) {
+    for (u32 r = blockIdx.y; r < world; r += gridDim.y) {
+        if (r == my_rank) continue;  // my own bits are already in place
+        const unsigned char *buf = all + (u64)r * stride_bytes;
+        const u64 n = min(*reinterpret_cast<const u64 *>(buf), cap);
+        const uint2 *pairs = reinterpret_cast<const uint2 *>(buf + 16);
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+            const uint2 pw = pairs[i];
+            atomicOr(bitmap + pw.x, pw.y);
+        }
+    }
+}
+
 // ---- union of several shards' candidate lists into the bitmaps (multi-GPU merge) ---------------------------
 __global__ void k3_scatter_prefix_kernel(const u32 *__restrict__ counts, u32 world, u32 n_slots, u64 *prefix) {
     u32 r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1370,6 +1407,24 @@ cudaError_t k3_compact(const u32 *bitmap, u64 words_per_slot, u64 chunks_per_slo
     k3_compact_kernel<<<(unsigned)((n_chunks * 32 + 255) / 256), 256, 0, s>>>(bitmap, words_per_slot, chunks_per_slot,
                                                                              n_chunks, n_slots, chunk_off, slot_label,
                                                                              lcoff, n_labels, cand, cand_off, cap, overflow);
+    return cudaGetLastError();
+}
+
+cudaError_t k3_sparse_pack(const u32 *bitmap, u64 n_words, u64 cap, void *buf /*16 + cap x 8 bytes*/, int sm_count, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(buf, 0, 16, s);
+    if (e != cudaSuccess) return e;
+    if (n_words == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<u64>((n_words + 255) / 256, (u64)sm_count * 16);
+    k3_sparse_pack_kernel<<<blocks, 256, 0, s>>>(bitmap, n_words, cap, reinterpret_cast<unsigned long long *>(buf),
+                                                 reinterpret_cast<uint2 *>(reinterpret_cast<unsigned char *>(buf) + 16));
+    return cudaGetLastError();
+}
+
+cudaError_t k3_sparse_merge(const void *all, u64 stride_bytes, u32 world, u32 my_rank, u64 cap, u32 *bitmap, int sm_count,
+                            cudaStream_t s) {
+    if (world <= 1) return cudaSuccess;
+    dim3 grid((unsigned)sm_count * 2, world);
+    k3_sparse_merge_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const unsigned char *>(all), stride_bytes, world, my_rank, cap, bitmap);
     return cudaGetLastError();
 }
 

@@ -51,7 +51,7 @@ class Stats(C.Structure):
                 ("last_scan_ms", "last_select_ms", "last_compact_ms", "last_join_ms", "last_build_ms",
                  "last_enumerate_ms")] + \
                [(n, C.c_uint64) for n in ("n_qpaths", "n_qblocks", "n_slots", "n_candidates", "join_items",
-                                        "kernel_launches", "h2d_bytes", "d2h_bytes", "join_exports", "join_donations", "join_steps", "join_warp_iters", "join_idle_polls", "join_bfs", "join_fallbacks", "join_reruns")]
+                                        "kernel_launches", "h2d_bytes", "d2h_bytes", "join_exports", "join_donations", "join_steps", "join_warp_iters", "join_idle_polls", "join_bfs", "join_fallbacks", "join_reruns", "exchange_bytes", "exchange_redos")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

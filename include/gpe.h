@@ -238,6 +238,8 @@ typedef struct gpe_stats {
     uint64_t join_fallbacks;  /* level-synchronous joins recomputed depth-first because a frontier outgrew its buffer */
     uint64_t join_reruns;     /* batches some of whose queries were joined a second time with their weighted counted leaves
                                  walked, because a weighted count met a saturated (>= 2^62) table entry */
+    uint64_t exchange_bytes;  /* multi-GPU: bytes this GPU received in the last candidate exchange (dense bitmaps or sparse pairs) */
+    uint64_t exchange_redos;  /* steps redone with the dense exchange because a shard outgrew the sparse buffer */
 } gpe_stats;
 int gpe_get_stats(gpe_ctx *ctx, gpe_stats *out);
 /* The context's CUDA stream (cudaStream_t) so callers can bracket calls with their own events. */

@@ -69,3 +69,31 @@ def test_candidate_buffer_overflow_is_repaired():
             del os.environ["GPE_CAND_CAP"]
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("mode,cap", [("sparse", None), ("sparse", "8"), ("dense", None)])
+def test_exchange_forms_agree(mode, cap, monkeypatch):
+    """Dense bitmaps, sparse (index, word) pairs, and a sparse buffer that is too small (the step is then redone with the
+    dense exchange): same answers.  One rank here; tests/test_multigpu.py runs two."""
+    gold = load_case("uniform300")
+    g = graph_io.read_graph(gold["data_path"])
+    sorted_nodes, membership = graph_io.read_membership(gold["membership_path"], g.V)
+    monkeypatch.setenv("GPE_EXCHANGE", mode)
+    if cap:
+        monkeypatch.setenv("GPE_SPARSE_CAP", cap)
+    ctx = gpe.GpeContext(0)
+    try:
+        ctx.comm_init(0, 1, gpe.comm_unique_id())
+        ctx.set_graph(g.offsets, g.nbrs, g.labels)
+        _, vde = gpe.host_gen_vde(g.offsets, g.nbrs, g.labels, gold["e"])
+        ctx.set_embeddings(vde)
+        ctx.enumerate(gold["l"] + 1, sorted_nodes, membership, gold["p"])
+        ctx.build_table_shard()
+        queries = [graph_io.read_graph(qf) for qf in gold["query_paths_files"]]
+        limits = [r["limit"] if r["limit"] is not None else gpe.LIMIT_MAX for r in gold["queries"]]
+        ctx.batch_upload(queries, limits)
+        ctx.batch_step()
+        assert ctx.batch_finish().tolist() == [r["answer"] for r in gold["queries"]]
+        assert ctx.stats()["exchange_redos"] == (1 if cap else 0)
+    finally:
+        ctx.close()

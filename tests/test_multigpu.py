@@ -35,9 +35,13 @@ def test_bench_two_gpus_matches_one_gpu():
     assert a["oracle_parity"]["ok"] and b["oracle_parity"]["ok"] and b["oracle_parity"]["checked"] >= 5
 
 
-@pytest.mark.parametrize("name", ["quickstart", "uniform300"])
-def test_one_process_two_contexts_gives_the_golden_answers(name):
+@pytest.mark.parametrize("name,exchange,cap", [("quickstart", "dense", None), ("uniform300", "dense", None),
+                                               ("quickstart", "sparse", None), ("uniform300", "sparse", "8")])
+def test_one_process_two_contexts_gives_the_golden_answers(name, exchange, cap, monkeypatch):
     _two_gpus()
+    monkeypatch.setenv("GPE_EXCHANGE", exchange)  # both forms of the candidate exchange; cap 8: sparse buffer too small, redone dense
+    if cap:
+        monkeypatch.setenv("GPE_SPARSE_CAP", cap)
     from gnn_pe_b200 import gpe, graph_io
     gold = load_case(name)
     g = graph_io.read_graph(gold["data_path"])
