@@ -55,6 +55,7 @@ GraphView graph_view(const gpe_ctx *c) {
     g.label = c->d_label.as<u32>();
     g.deg = c->d_deg.as<u32>();
     g.rank = c->d_rank.as<u32>();
+    g.ranklab = c->d_ranklab.as<u64>();
     g.vde = c->d_vde.as<double>();
     g.e = c->e;
     g.lpos = c->d_lpos.as<u32>();
@@ -556,7 +557,7 @@ void gpe_destroy(gpe_ctx *c) {
     if (c->comm) nccl_api().CommDestroy((ncclComm_t)c->comm);
     c->d_all_bitmaps.release();
     c->d_reduce.release();
-    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrJ, &c->d_gtab, &c->d_offJ, &c->d_degJ, &c->d_labelJ, &c->d_newid, &c->d_nbrG, &c->d_lclass, &c->d_lpos, &c->d_lcoff, &c->d_bloom, &c->d_tjobs, &c->d_tchild, &c->d_tpool, &c->d_tcursor, &c->d_tlist, &c->d_qcur, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde,
+    DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrJ, &c->d_gtab, &c->d_offJ, &c->d_degJ, &c->d_labelJ, &c->d_newid, &c->d_nbrG, &c->d_lclass, &c->d_lpos, &c->d_lcoff, &c->d_bloom, &c->d_tjobs, &c->d_tchild, &c->d_tpool, &c->d_tcursor, &c->d_tlist, &c->d_qcur, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde, &c->d_vrec, &c->d_ranklab,
                       &c->d_offr, &c->d_ebase, &c->d_start_rows, &c->d_scan_tmp, &c->d_tiles, &c->d_vids, &c->d_sum_u32, &c->d_sum_f64,
                       &c->d_bucket, &c->d_cursor, &c->d_qblocks, &c->d_qb_t0, &c->d_qb_prefix, &c->d_worklist,
                       &c->d_counters, &c->d_bitmap, &c->d_survivors, &c->d_slot_label, &c->d_chunk_cnt, &c->d_chunk_off, &c->d_cand,
@@ -714,7 +715,10 @@ int gpe_set_embeddings(gpe_ctx *c, uint32_t e, const double *vde) try {
     c->e = e;
     GPE_CUDA(c, c->d_vde.reserve(std::max<size_t>((size_t)c->V * e, 1) * sizeof(double)));
     if (c->V) GPE_CUDA(c, cudaMemcpyAsync(c->d_vde.p, vde, (size_t)c->V * e * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, c->d_vrec.reserve(k1_vertex_record_bytes(c->V, e)));
+    GPE_CUDA(c, k1_vertex_records(graph_view(c), c->d_vrec.p, c->stream));
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stats.kernel_launches++;
     c->have_emb = true;
     c->have_table = false;
     return GPE_OK;
@@ -745,6 +749,7 @@ int gpe_enumerate(gpe_ctx *c, uint32_t L, const uint32_t *sorted_nodes, const ui
     c->p = p;
     c->h_member.assign(membership, membership + V);
     GPE_CUDA(c, c->d_rank.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
+    GPE_CUDA(c, c->d_ranklab.reserve(std::max<size_t>(V, 1) * sizeof(u64)));
     GPE_CUDA(c, c->d_sorted.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_member.reserve(std::max<size_t>(V, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_offr.reserve(((size_t)V + 1) * sizeof(u32)));
@@ -756,6 +761,7 @@ int gpe_enumerate(gpe_ctx *c, uint32_t L, const uint32_t *sorted_nodes, const ui
         GPE_CUDA(c, cudaMemcpyAsync(c->d_member.p, membership, (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
     }
     GPE_CUDA(c, cudaMemcpyAsync(c->d_offr.p, offr.data(), ((size_t)V + 1) * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
+    GPE_CUDA(c, k1_rank_labels(V, c->d_rank.as<u32>(), c->d_label.as<u32>(), c->d_ranklab.as<u64>(), c->stream));
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
 
     u64 *ebase = c->d_ebase.as<u64>();
@@ -895,7 +901,7 @@ int gpe_build_table(gpe_ctx *c, const uint8_t *part_select, uint64_t *n_table_ro
     }
     GPE_CUDA(c, cudaMemcpyAsync(c->d_cursor.p, bucket, ((size_t)t.n_keys + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
     GPE_CUDA(c, k1_fill(g, t, c->d_sorted.as<u32>(), c->d_member.as<u32>(), sel, c->d_cursor.as<u64>(), c->sm_count, c->stream));
-    GPE_CUDA(c, k1_expand(t, g, c->sm_count, c->stream));
+    GPE_CUDA(c, k1_expand(t, c->d_vrec.p, c->sm_count, c->stream));
     cudaEventRecord(b1, c->stream);
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaEventElapsedTime(&c->stats.last_build_ms, b0, b1);

@@ -72,6 +72,7 @@ struct GraphView {
     const u32 *label;  // V
     const u32 *deg;    // V
     const u32 *rank;   // V: position in membership.txt
+    const u64 *ranklab;  // V: rank | label << 32 (the enumeration walks gather both with one load)
     const double *vde; // V x e
     u32 e;
     const u32 *lpos;   // V: position of a vertex inside its label class
@@ -218,7 +219,7 @@ struct gpe_ctx {
 
     // graph
     u32 V = 0, n_adj = 0, n_labels = 0, max_degree = 0;
-    gpe::DevBuf d_off, d_nbr, d_label, d_deg, d_rank, d_sorted, d_member, d_vde;
+    gpe::DevBuf d_off, d_nbr, d_label, d_deg, d_rank, d_sorted, d_member, d_vde, d_vrec, d_ranklab;
     gpe::DevBuf d_nbrJ, d_gtab, d_offJ, d_degJ, d_labelJ, d_newid;  // the join's class-ordered copy of the graph (k0_graph.cu)
     gpe::DevBuf d_nbrG;  // adjacency grouped by neighbour label in the caller's ids (k1 histogram / fill)
     gpe::DevBuf d_lclass, d_lpos, d_lcoff;  // label classes: vertices by (label, id), position in class, class offsets
@@ -322,6 +323,7 @@ cudaError_t k0_build_join_graph(u32 V, u32 n_adj, u32 n_labels, const u32 *off, 
 cudaError_t k0_gather(u64 n, const u32 *map, const u32 *in, u32 *out, cudaStream_t s);  // out[i] = map[in[i]]
 
 // K1
+cudaError_t k1_rank_labels(u32 V, const u32 *rank, const u32 *label, u64 *ranklab, cudaStream_t s);
 cudaError_t k1_count(const GraphView &g, u32 L, const u32 *sorted, const u32 *offr, u64 *cnt_r, int sm_count,
                      cudaStream_t s);
 cudaError_t k1_rows_per_partition(u32 V, const u32 *sorted, const u32 *offr, const u64 *ebase, const u32 *member,
@@ -333,7 +335,10 @@ cudaError_t k1_histogram(const GraphView &g, const TableView &t, const u32 *sort
 cudaError_t k1_fill(const GraphView &g, const TableView &t, const u32 *sorted, const u32 *member,
                     const unsigned char *part_sel, u64 *cursor, int sm_count, cudaStream_t s);
 // vertex ids (written by k1_fill) -> scan tiles + class positions + per-tile summaries
-cudaError_t k1_expand(const TableView &t, const GraphView &g, int sm_count, cudaStream_t s);
+// packed per-vertex records (label, degree, class position | embedding) that k1_expand gathers from
+size_t k1_vertex_record_bytes(u32 V, u32 e);
+cudaError_t k1_vertex_records(const GraphView &g, void *vrec, cudaStream_t s);
+cudaError_t k1_expand(const TableView &t, const void *vrec, int sm_count, cudaStream_t s);
 cudaError_t k1_dump_table(const TableView &t, const GraphView &g, u64 first, u64 n, u32 *vids, u32 *labels, u32 *degs,
                           double *pde, cudaStream_t s);
 

@@ -107,8 +107,9 @@ __device__ __forceinline__ void walk_start_vertex(const GraphView &g, u32 a, u32
                 u32 jj = j + lane;
                 bool in = jj < b1;
                 u32 c = in ? (GROUPED ? g.nbrG[jj] : g.nbr[jj]) : 0u;
-                bool valid = in && g.rank[c] > ra;  // c != a follows from the strict rank test
-                f.chunk(b, c, 0u, valid);
+                const u64 rl = in ? g.ranklab[c] : 0ull;  // rank | label << 32: one gather for both
+                bool valid = in && (u32)rl > ra;  // c != a follows from the strict rank test
+                f.chunk(b, c, 0u, valid, (u32)(rl >> 32));
             }
         } else {
             for (u32 t = b0; t < b1; ++t) {
@@ -119,8 +120,9 @@ __device__ __forceinline__ void walk_start_vertex(const GraphView &g, u32 a, u32
                     u32 jj = j + lane;
                     bool in = jj < c1;
                     u32 d = in ? (GROUPED ? g.nbrG[jj] : g.nbr[jj]) : 0u;
-                    bool valid = in && d != b && g.rank[d] > ra;  // d != a by rank, d != c: no loops
-                    f.chunk(b, c, d, valid);
+                    const u64 rl = in ? g.ranklab[d] : 0ull;
+                    bool valid = in && d != b && (u32)rl > ra;  // d != a by rank, d != c: no loops
+                    f.chunk(b, c, d, valid, (u32)(rl >> 32));
                 }
             }
         }
@@ -134,7 +136,7 @@ struct CountF {
     u64 cnt;
     int lane;
     __device__ void begin_slot(u32, u32) { cnt = 0; }
-    __device__ void chunk(u32, u32, u32, bool valid) { cnt += __popc(__ballot_sync(kFull, valid)); }
+    __device__ void chunk(u32, u32, u32, bool valid, u32) { cnt += __popc(__ballot_sync(kFull, valid)); }
     __device__ void end_slot(u32 si) { if (lane == 0) out[si] = cnt; }
 };
 
@@ -174,7 +176,7 @@ struct DumpF {
     u64 id;
     int lane;
     __device__ void begin_slot(u32 si, u32) { id = ebase[si]; }
-    __device__ void chunk(u32 b, u32 c, u32 d, bool valid) {
+    __device__ void chunk(u32 b, u32 c, u32 d, bool valid, u32) {
         unsigned m = __ballot_sync(kFull, valid);
         u64 my = id + __popc(m & lanemask_lt());
         if (valid && my >= first && my < first + n) {
@@ -219,11 +221,10 @@ struct HistF {
     u32 key_a;
     u32 key_ab;
     __device__ void begin_slot(u32, u32 b) { key_ab = key_a + key_term(kp, 1, g.label[b]); }
-    __device__ void chunk(u32, u32 c, u32 d, bool valid) {
+    __device__ void chunk(u32, u32 c, u32 d, bool valid, u32 last_label) {  // last_label: label of the path's last vertex
         unsigned act = __ballot_sync(kFull, valid);
         if (!valid) return;
-        u32 key = key_ab + key_term(kp, 2, g.label[c]);
-        if (L == 4) key += key_term(kp, 3, g.label[d]);
+        u32 key = key_ab + (L == 4 ? key_term(kp, 2, g.label[c]) + key_term(kp, 3, last_label) : key_term(kp, 2, last_label));
         unsigned peers = __match_any_sync(act, key);
         if ((peers & lanemask_lt()) == 0)
             atomicAdd((unsigned long long *)&hist[key], (unsigned long long)__popc(peers));
@@ -260,11 +261,10 @@ struct FillF {
     __device__ void put(u64 row, int k, u32 v) const {
         t.vids[((row / kTileRows) * L + k) * kTileRows + (u32)(row % kTileRows)] = v;
     }
-    __device__ void chunk(u32 b, u32 c, u32 d, bool valid) {
+    __device__ void chunk(u32 b, u32 c, u32 d, bool valid, u32 last_label) {
         unsigned act = __ballot_sync(kFull, valid);
         if (!valid) return;
-        u32 key = key_ab + key_term(kp, 2, g.label[c]);
-        if (L == 4) key += key_term(kp, 3, g.label[d]);
+        u32 key = key_ab + (L == 4 ? key_term(kp, 2, g.label[c]) + key_term(kp, 3, last_label) : key_term(kp, 2, last_label));
         unsigned peers = __match_any_sync(act, key);
         int leader = __ffs(peers) - 1;
         u64 base = 0;
@@ -301,11 +301,15 @@ __global__ void __launch_bounds__(256) k1_fill_kernel(GraphView g, KeyParams kp,
 // structure-of-arrays columns with full-line stores, replaces the ids by class positions (the bit index of the
 // candidate bitmaps), and reduces the tile's label range, max degrees and max-corner.  HBM-write bound:
 // (8L + 8Le + 4L) bytes per row.
-template <int L>
-__global__ void __launch_bounds__(kTileRows) k1_expand_kernel(TableView t, GraphView g) {
+// The per-vertex gathers come from ONE packed record per vertex (label, degree, class position, pad | embedding: 16 + 8e
+// bytes, built by k1_vertex_records): one or two 32-byte sectors per vertex instead of one each from four arrays -- the
+// kernel was bound by L2 sector requests (6 G four-byte gathers for 515 M rows), not by its stores.
+template <int L, int E>
+__global__ void __launch_bounds__(kTileRows) k1_expand_kernel(TableView t, const uint4 *__restrict__ vrec) {
     constexpr int W = kTileRows / 32;
+    constexpr int RQ = 1 + (E + 1) / 2;         // 16-byte words per record
     __shared__ u32 s_u[2][3 * L][W];            // per-warp partials: label min, label max, max degree per position
-    __shared__ double s_d[2][kMaxL * kMaxE][W]; // per-warp partials of the max-corner; double-buffered by tile parity,
+    __shared__ double s_d[2][L * E][W];         // per-warp partials of the max-corner; double-buffered by tile parity,
     const u32 r = threadIdx.x;                  // so one barrier per tile is enough
     const int lane = r & 31, warp = r >> 5;
     int buf = 0;
@@ -316,37 +320,43 @@ __global__ void __launch_bounds__(kTileRows) k1_expand_kernel(TableView t, Graph
         u32 *dg = reinterpret_cast<u32 *>(base + 4u * L * kTileRows);
         double *pde = reinterpret_cast<double *>(base + 8u * L * kTileRows);
         u32 *vid = t.vids + tile * L * kTileRows;
-        // all of a row's loads are issued before anything depends on them: ids first, then the per-vertex gathers
-        u32 v[L], l[L], d[L], ps[L];
+        // all of a row's loads are issued before anything depends on them: ids first, then the records
+        u32 v[L];
 #pragma unroll
         for (int k = 0; k < L; k++) v[k] = valid ? __ldcs(vid + k * kTileRows + r) : 0u;  // streaming: the table is touched once,
-#pragma unroll                                                                          // the per-vertex arrays stay in L2
+        uint4 head[L];                                                                  // the vertex records stay in L2
+        double emb[L][E];
+#pragma unroll
         for (int k = 0; k < L; k++) {
-            l[k] = valid ? g.label[v[k]] : 0xffffffffu;
-            d[k] = valid ? g.deg[v[k]] : 0u;
-            ps[k] = valid ? g.lpos[v[k]] : 0u;
+            const uint4 *rec = vrec + (u64)v[k] * RQ;
+            head[k] = valid ? __ldg(rec) : make_uint4(0xffffffffu, 0u, 0u, 0u);
+#pragma unroll
+            for (int x = 0; x < E; x += 2) {
+                const uint4 q = valid ? __ldg(rec + 1 + x / 2) : make_uint4(0u, 0u, 0xbff00000u, 0u);
+                emb[k][x] = valid ? __hiloint2double((int)q.y, (int)q.x) : -1.0;
+                if (x + 1 < E) emb[k][x + 1] = valid ? __hiloint2double((int)q.w, (int)q.z) : -1.0;
+            }
         }
 #pragma unroll
         for (int k = 0; k < L; k++) {
-            for (u32 x = 0; x < t.E; x++) {
-                double e = -1.0;
-                if (valid) {
-                    e = g.vde[(u64)v[k] * t.E + x];
-                    __stcs(pde + (k * t.E + x) * kTileRows + r, e);
-                }
+#pragma unroll
+            for (int x = 0; x < E; x++) {
+                double e = emb[k][x];
+                if (valid) __stcs(pde + (k * E + x) * kTileRows + r, e);
 #pragma unroll
                 for (int o = 16; o; o >>= 1) e = fmax(e, __shfl_xor_sync(kFull, e, o));
-                if (lane == 0) s_d[buf][k * t.E + x][warp] = e;
+                if (lane == 0) s_d[buf][k * E + x][warp] = e;
             }
         }
 #pragma unroll
         for (int k = 0; k < L; k++) {
+            const u32 lk = head[k].x, dk = head[k].y;
             if (valid) {
-                __stcs(lab + k * kTileRows + r, l[k]);
-                __stcs(dg + k * kTileRows + r, d[k]);
-                __stcs(vid + k * kTileRows + r, ps[k]);
+                __stcs(lab + k * kTileRows + r, lk);
+                __stcs(dg + k * kTileRows + r, dk);
+                __stcs(vid + k * kTileRows + r, head[k].z);
             }
-            u32 mn = l[k], mx = valid ? l[k] : 0u, dm = d[k];
+            u32 mn = lk, mx = valid ? lk : 0u, dm = dk;
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
                 mn = min(mn, __shfl_xor_sync(kFull, mn, o));
@@ -368,6 +378,18 @@ __global__ void __launch_bounds__(kTileRows) k1_expand_kernel(TableView t, Graph
             for (int w = 1; w < W; w++) acc = fmax(acc, s_d[buf][dd][w]);
             t.pde_max[dd * t.n_tiles + tile] = acc;
         }
+    }
+}
+
+// label | degree | class position | 0, then the embedding padded to an even number of doubles
+__global__ void __launch_bounds__(256) k1_vertex_records_kernel(GraphView g, u32 rq, uint4 *vrec) {
+    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= g.V) return;
+    uint4 *rec = vrec + (u64)v * rq;
+    rec[0] = make_uint4(g.label[v], g.deg[v], g.lpos[v], 0u);
+    for (u32 x = 0; x < g.e; x += 2) {
+        const double a = g.vde[(u64)v * g.e + x], b = x + 1 < g.e ? g.vde[(u64)v * g.e + x + 1] : 0.0;
+        rec[1 + x / 2] = make_uint4((u32)__double2loint(a), (u32)__double2hiint(a), (u32)__double2loint(b), (u32)__double2hiint(b));
     }
 }
 
@@ -443,6 +465,18 @@ cudaError_t exclusive_scan_u64(u64 *d_data, u64 n, DevBuf &tmp, cudaStream_t s) 
     return cudaGetLastError();
 }
 
+namespace {
+__global__ void __launch_bounds__(256) k1_rank_labels_kernel(u32 V, const u32 *__restrict__ rank, const u32 *__restrict__ label, u64 *out) {
+    const u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < V) out[v] = (u64)rank[v] | ((u64)label[v] << 32);
+}
+}  // namespace
+
+cudaError_t k1_rank_labels(u32 V, const u32 *rank, const u32 *label, u64 *ranklab, cudaStream_t s) {
+    if (V) k1_rank_labels_kernel<<<(V + 255) / 256, 256, 0, s>>>(V, rank, label, ranklab);
+    return cudaGetLastError();
+}
+
 cudaError_t k1_count(const GraphView &g, u32 L, const u32 *sorted, const u32 *offr, u64 *cnt_r, int sm_count,
                      cudaStream_t s) {
     if (L == 3) k1_count_kernel<3><<<walk_grid(sm_count), 256, 0, s>>>(g, sorted, offr, cnt_r);
@@ -481,11 +515,27 @@ cudaError_t k1_fill(const GraphView &g, const TableView &t, const u32 *sorted, c
     return cudaGetLastError();
 }
 
-cudaError_t k1_expand(const TableView &t, const GraphView &g, int sm_count, cudaStream_t s) {
+size_t k1_vertex_record_bytes(u32 V, u32 e) { return (size_t)std::max<u32>(V, 1) * (1 + (e + 1) / 2) * sizeof(uint4); }
+
+cudaError_t k1_vertex_records(const GraphView &g, void *vrec, cudaStream_t s) {
+    if (g.V == 0) return cudaSuccess;
+    k1_vertex_records_kernel<<<(g.V + 255) / 256, 256, 0, s>>>(g, 1 + (g.e + 1) / 2, reinterpret_cast<uint4 *>(vrec));
+    return cudaGetLastError();
+}
+
+cudaError_t k1_expand(const TableView &t, const void *vrec, int sm_count, cudaStream_t s) {
     if (t.n_tiles == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)std::min<u64>(t.n_tiles, (u64)sm_count * 8 * 16);
-    if (t.L == 3) k1_expand_kernel<3><<<blocks, kTileRows, 0, s>>>(t, g);
-    else k1_expand_kernel<4><<<blocks, kTileRows, 0, s>>>(t, g);
+    const uint4 *vr = reinterpret_cast<const uint4 *>(vrec);
+#define EXPAND(L_, E_) k1_expand_kernel<L_, E_><<<blocks, kTileRows, 0, s>>>(t, vr)
+    if (t.L == 3) {
+        switch (t.E) { case 1: EXPAND(3, 1); break; case 2: EXPAND(3, 2); break; case 3: EXPAND(3, 3); break;
+                       case 4: EXPAND(3, 4); break; case 8: EXPAND(3, 8); break; default: return cudaErrorInvalidValue; }
+    } else {
+        switch (t.E) { case 1: EXPAND(4, 1); break; case 2: EXPAND(4, 2); break; case 3: EXPAND(4, 3); break;
+                       case 4: EXPAND(4, 4); break; case 8: EXPAND(4, 8); break; default: return cudaErrorInvalidValue; }
+    }
+#undef EXPAND
     return cudaGetLastError();
 }
 

@@ -137,3 +137,23 @@ def test_config2_full_size_properties():
     n, _ = oracle.online_streaming(og, oq, L, e, sorted_nodes, vde)
     assert n == int(full[qi])
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["config3_small", "config5_small", "small"])
+def test_bench_workloads_match_the_oracle_fixture(name):
+    """Down-scaled copies of bench.py's config 3 / 5 workloads (same generator, labels and query mix) and of config 2:
+    the sampled queries of tests/golden/config_answers.json (oracle.online_streaming on the CPU) through the batch path."""
+    import json
+    import os
+    import bench
+    from tests.golden_util import ROOT
+    rec = json.load(open(os.path.join(ROOT, "tests", "golden", "config_answers.json")))[name]
+    w, g, queries = bench.load_workload(name)
+    assert (g.V, g.E, len(queries)) == (rec["V"], rec["E"], rec["n_queries"])  # the generators are deterministic
+    ctx, vde, sorted_nodes, n_rows, _ = _engine(g, w["l"], w["e"], p=w["p"])
+    try:
+        ans = ctx.query_batch(queries)
+        got = {i: int(ans[int(i)]) for i in rec["answers"]}
+        assert got == {i: min(v, gpe.LIMIT_MAX) for i, v in rec["answers"].items()}
+    finally:
+        ctx.close()
