@@ -1690,6 +1690,37 @@ int gpe_batch_finish(gpe_ctx *c, uint64_t *answers) {
     return GPE_OK;
 }
 
+// Several batches, pipelined on one host thread: while the GPU works on batch i (everything up to the download is
+// asynchronous), the host plans batch i+1 (dfs_query + gen_vde + gen_query_pde of every query, custom.h:94-119, :574-633
+// -- what the reference does serially per query before it touches its index, main.cpp:142-158).  With a communicator
+// the collective calls happen in the same order on every rank.
+int gpe_query_batches(gpe_ctx *c, uint32_t n_batches, const gpe_batch *batches, uint32_t flags, uint64_t *const *answers) try {
+    if (!c || (n_batches && (!batches || !answers))) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
+    if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
+    GPE_CUDA(c, cudaSetDevice(c->device));
+    gpe_plan cur, next;
+    if (n_batches)
+        if (int rc = plan_batch(&batches[0], c->tv.L, c->tv.E, c->label_table, cur)) return c->fail(rc, "batch 0: %s", cur.err.c_str());
+    u64 h2d = 0, d2h = 0;
+    for (uint32_t i = 0; i < n_batches; i++) {
+        if (int rc = upload_planned(c, &batches[i], cur, flags)) return rc;
+        if (int rc = gpe_batch_step(c)) return rc;
+        if (i + 1 < n_batches) {
+            next = gpe_plan();
+            if (int rc = plan_batch(&batches[i + 1], c->tv.L, c->tv.E, c->label_table, next)) return c->fail(rc, "batch %u: %s", i + 1, next.err.c_str());
+        }
+        if (int rc = gpe_batch_finish(c, answers[i])) return rc;
+        h2d += c->stats.h2d_bytes;
+        d2h += c->stats.d2h_bytes;
+        std::swap(cur, next);
+    }
+    c->stats.h2d_bytes = h2d;  // of all the batches of this call
+    c->stats.d2h_bytes = d2h;
+    return GPE_OK;
+} catch (const std::exception &ex) {
+    return c ? c->fail(GPE_ERR_INVALID, "gpe_query_batches: %s", ex.what()) : GPE_ERR_INVALID;
+}
+
 // ---- one process, several contexts (host/main -g N): one thread enqueues every GPU's work, NCCL calls grouped --------
 int gpe_multi_batch_upload(gpe_ctx **ctxs, int n, const gpe_batch *b, uint32_t flags) try {
     if (!ctxs || n < 1 || !b || !ctxs[0]) return GPE_ERR_INVALID;

@@ -236,7 +236,11 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                                                        u32 *tchild, u64 *tcursor, u32 *tcount, u32 *tlist,
                                                        u32 n_slots /*stride of tlist: 2 x slots*/, u32 sjob_base /*slots*/,
                                                        bool allow_weighted_all, const u32 *__restrict__ qmode) {
-    for (u32 q = threadIdx.x; q < n_queries; q += blockDim.x) {
+    // One query per WARP, lane 0 only: the plan is serial, branchy code -- 32 different queries in the lanes of one warp
+    // execute it 32 times over (the r01y launch list had this kernel at 94 us for 100 queries in a single CTA) -- and
+    // spread over the SMs 1000 queries take as long as 100.
+    const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q < n_queries && (threadIdx.x & 31) == 0) {
         // qmode (second pass of a batch some of whose weighted counts saturated, see kSat): 0 as usual, 1 plan this query
         // without weighted counted leaves, 2 leave this query out (no tickets, no tables)
         const u32 mode = qmode ? qmode[q] : 0;
@@ -558,17 +562,26 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
             else total = qlab[root] < n_labels ? lcoff[qlab[root] + 1] - lcoff[qlab[root]] : 0;
             items = total > rank ? (total - rank + world - 1) / world : 0;
         }
-        item_base[q + 1] = (items + per_ticket - 1) / per_ticket;  // tickets of this query; turned into a prefix below
+        item_base[q + 1] = (items + per_ticket - 1) / per_ticket;  // tickets of this query; turned into a prefix by the next kernel
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u64 run = 0;
-        item_base[0] = 0;
-        for (u32 q = 0; q < n_queries; q++) {
-            run += item_base[q + 1];
-            item_base[q + 1] = run;
+}
+
+// item_base[q + 1] (tickets of query q) -> inclusive prefix, item_base[0] = 0; one warp, chunks of 32 queries
+__global__ void k3_order_prefix_kernel(u32 n_queries, u64 *item_base) {
+    const int lane = threadIdx.x;
+    u64 run = 0;
+    for (u32 q0 = 0; q0 < n_queries; q0 += 32) {
+        const u32 q = q0 + lane;
+        u64 v = q < n_queries ? item_base[q + 1] : 0, inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += t;
         }
+        if (q < n_queries) item_base[q + 1] = run + inc;
+        run += __shfl_sync(kFull, inc, 31);
     }
+    if (lane == 0) item_base[0] = 0;
 }
 
 // ---- the join ------------------------------------------------------------------------------------------------
@@ -759,19 +772,24 @@ __global__ void __launch_bounds__(256) k3_init_count_kernel(u32 n_queries, const
     }
 }
 
-__global__ void k3_init_prefix_kernel(u32 n_queries, u64 *qcur, JoinQueue *jq) {
-    if (threadIdx.x || blockIdx.x) return;
-    u64 heavy = 0;
-    for (u32 q = 0; q < n_queries; q++) {
-        qcur[kQCur * (u64)q + 1] = heavy;
-        heavy += qcur[kQCur * (u64)q];
-    }
-    u64 light = heavy;
-    for (u32 q = 0; q < n_queries; q++) {
-        qcur[kQCur * (u64)q + 2] = light;
-        light += qcur[kQCur * (u64)q + 5];
-    }
-    const u64 n_items = light;  // live roots = tickets
+__global__ void k3_init_prefix_kernel(u32 n_queries, u64 *qcur, JoinQueue *jq) {  // one warp
+    const int lane = threadIdx.x;
+    u64 run = 0;
+    for (int pass = 0; pass < 2; pass++)  // heavy roots of query 0, 1, ... then the light ones
+        for (u32 q0 = 0; q0 < n_queries; q0 += 32) {
+            const u32 q = q0 + lane;
+            const u64 v = q < n_queries ? qcur[kQCur * (u64)q + (pass ? 5 : 0)] : 0;
+            u64 inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u64 t = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (q < n_queries) qcur[kQCur * (u64)q + (pass ? 2 : 1)] = run + inc - v;
+            run += __shfl_sync(kFull, inc, 31);
+        }
+    if (lane != 0) return;
+    const u64 n_items = run;  // live roots = tickets
     jq->head = 0;
     jq->tail = n_items;
     jq->pending = (long long)n_items;
@@ -832,13 +850,16 @@ __global__ void __launch_bounds__(256) k3_tree_tables_kernel(JoinGraph g, const 
                                                              const u32 *__restrict__ tcount,
                                                              const u32 *__restrict__ tlist, u32 n_slots,
                                                              const u32 *__restrict__ bitmap, u64 words_per_slot,
-                                                             u64 *tpool) {
+                                                             u64 *tpool, u32 max_class) {
+  // work unit = (table of this level, block of 256 class positions); a level without tables costs one look at tcount
   const u32 n_jobs = tcount[level];
-  for (u32 ji = blockIdx.y; ji < n_jobs; ji += gridDim.y) {
+  const u32 chunks = (max_class + 255) / 256;
+  for (u64 unit = blockIdx.x; unit < (u64)n_jobs * chunks; unit += gridDim.x) {
+    const u32 ji = (u32)(unit / chunks), chunk = (u32)(unit % chunks);
     const TreeJob job = tjobs[tlist[(u64)level * n_slots + ji]];
     if (job.label >= g.nl) continue;
     const u32 c0 = g.lcoff[job.label], n = g.lcoff[job.label + 1] - c0;
-    for (u32 pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += gridDim.x * blockDim.x) {
+    for (u32 pos = chunk * 256 + threadIdx.x; pos < min(n, (chunk + 1) * 256); pos += blockDim.x) {
         const DirRow row = dir_row(g, c0 + pos);  // class-order id of the class's pos-th vertex: rows are contiguous
         u64 val = 1;
         for (u32 k = 0; k < job.n_child && val; k++) {
@@ -1451,10 +1472,11 @@ cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebas
                      u32 n_slots, bool allow_weighted, const u32 *qmode, cudaStream_t s) {
     // jobs / child lists / per-level job lists hold 2 x n_slots entries: [0, n_slots) the tables N_v of vertices with
     // peeled children, [n_slots, 2 n_slots) the tables S_u of weighted counted leaves
-    k3_order_kernel<<<1, 256, 0, s>>>(n_queries, V, q_vbase, q_ebase, q_offsets, q_nbrs, q_labels, cand_off, order,
+    k3_order_kernel<<<(n_queries * 32 + 127) / 128 + 1, 128, 0, s>>>(n_queries, V, q_vbase, q_ebase, q_offsets, q_nbrs, q_labels, cand_off, order,
                                       pivot, jplan, reinterpret_cast<uint2 *>(kids), item_base, rank, world, 1, enumerate,
                                       clean_start, n_labels, lcoff, tjobs, tchild, tcursor, tcount, tlist, 2 * n_slots,
                                       n_slots, allow_weighted, qmode);
+    k3_order_prefix_kernel<<<1, 32, 0, s>>>(n_queries, item_base);
     return cudaGetLastError();
 }
 
@@ -1481,14 +1503,12 @@ cudaError_t k3_tree_tables(const JoinGraph &g, u32 n_slots, u32 max_class, u32 m
                            const u32 *tchild, const u32 *tcount, const u32 *tlist, const u32 *bitmap, u64 words_per_slot,
                            u64 *tpool, int sm_count, cudaStream_t s) {
     if (n_slots == 0 || max_class == 0) return cudaSuccess;
-    // a level may hold a handful of tables only (chains are peeled one level at a time), so a table gets up to 64
-    // blocks of its own; rows of the grid beyond the level's job count exit at once
-    const u32 gy = std::min<u32>(n_slots, (u32)sm_count * 2);
-    const u32 gx = std::max<u32>(1, std::min<u32>((max_class + 255) / 256, 64));
-    dim3 grid(gx, gy);
+    // one persistent 1-D grid per level over (table, block of 256 class positions) units: a level with a handful of tables
+    // still fills the GPU, and a level without any costs a launch of blocks that read one counter and exit
+    const u32 grid = (u32)sm_count * 8;
     for (u32 level = 1; level <= max_level; level++)
         k3_tree_tables_kernel<<<grid, 256, 0, s>>>(g, tjobs, tchild, level, tcount, tlist, 2 * n_slots /*list stride*/, bitmap,
-                                                   words_per_slot, tpool);
+                                                   words_per_slot, tpool, max_class);
     return cudaGetLastError();
 }
 

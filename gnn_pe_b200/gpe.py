@@ -69,7 +69,7 @@ SYMBOLS = [
     "gpe_pge_batch_filter", "gpe_pge_query_batch", "gpe_get_stats", "gpe_stream", "gpe_sync", "gpe_set_timing",
     "gpe_collect_timings", "gpe_comm_unique_id", "gpe_comm_init", "gpe_comm_init_all", "gpe_comm_destroy", "gpe_comm_info",
     "gpe_build_table_shard", "gpe_batch_step", "gpe_batch_finish", "gpe_multi_batch_upload", "gpe_multi_batch_step",
-    "gpe_multi_batch_finish", "gpe_multi_query_batch",
+    "gpe_multi_batch_finish", "gpe_multi_query_batch", "gpe_query_batches",
 ]
 
 
@@ -119,6 +119,7 @@ def lib():
         L.gpe_pge_batch_upload.argtypes = [vp, C.POINTER(Batch)]
         L.gpe_pge_batch_filter.argtypes = [vp]
         L.gpe_pge_query_batch.argtypes = [vp, C.POINTER(Batch), vp]
+        L.gpe_query_batches.argtypes = [vp, u32, vp, u32, vp]
         L.gpe_comm_unique_id.argtypes = [vp]
         L.gpe_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
         L.gpe_comm_init_all.argtypes = [vp, C.c_int]
@@ -392,6 +393,27 @@ class GpeContext:
         ans = np.zeros(max(len(queries), 1), dtype=np.uint64)
         self._ck(self._L.gpe_query_batch(self._h, C.byref(b), flags, _ptr(ans)))
         return ans[: len(queries)]
+
+    def prepare_batches(self, batches, limits=None):
+        """Pack several batches (lists of query graphs) into gpe_batch structs: the host buffers gpe_query_batches takes."""
+        n = len(batches)
+        structs = (Batch * max(n, 1))()
+        keep, outs = [], []
+        for i, qs in enumerate(batches):
+            structs[i] = self._batch_struct(qs, None if limits is None else limits[i])
+            keep.append(self._keep)
+            outs.append(np.zeros(max(len(qs), 1), dtype=np.uint64))
+        ptrs = (C.c_void_p * max(n, 1))(*[o.ctypes.data for o in outs])
+        return dict(n=n, structs=structs, keep=keep, outs=outs, ptrs=ptrs, sizes=[len(qs) for qs in batches])
+
+    def run_batches(self, prepared, flags: int = 0):
+        """gpe_query_batches: all the batches in ONE call, host planning of batch i+1 overlapped with the GPU work of batch i."""
+        self._ck(self._L.gpe_query_batches(self._h, prepared["n"], prepared["structs"], flags, prepared["ptrs"]))
+        self._n_queries = prepared["sizes"][-1] if prepared["n"] else 0
+        return [o[:k] for o, k in zip(prepared["outs"], prepared["sizes"])]
+
+    def query_batches(self, batches, limits=None, flags: int = 0):
+        return self.run_batches(self.prepare_batches(batches, limits), flags)
 
     def batch_upload(self, queries, limits=None, flags: int = 0):
         b = self._batch_struct(queries, limits)

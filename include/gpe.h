@@ -143,6 +143,12 @@ uint64_t gpe_clamp_answer(uint64_t raw_total, uint64_t limit);
 /* All four stages for one GPU, host buffers in, answers out: the end-to-end call. */
 int gpe_query_batch(gpe_ctx *ctx, const gpe_batch *batch, uint32_t flags, uint64_t *answers);
 
+/* Several batches in one call, pipelined: the host plans batch i+1 while the GPU works on batch i (a context holds one
+ * batch at a time, so nothing is double-buffered on the device).  answers[i] (n_queries of batch i) as gpe_query_batch.
+ * Works with or without a communicator (gpe_comm_init): with one, every rank makes the same call.  gpe_stats.h2d_bytes /
+ * d2h_bytes afterwards hold the totals over all the batches. */
+int gpe_query_batches(gpe_ctx *ctx, uint32_t n_batches, const gpe_batch *batches, uint32_t flags, uint64_t *const *answers);
+
 /* Candidate exchange between shards (replaces the serial merge main.cpp:166-172 when the table is
  * sharded over GPUs).  Device pointers: the caller moves them with NCCL. */
 int gpe_batch_cand_info(gpe_ctx *ctx, uint64_t *n_slots, uint64_t *n_cand_total);

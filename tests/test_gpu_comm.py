@@ -97,3 +97,31 @@ def test_exchange_forms_agree(mode, cap, monkeypatch):
         assert ctx.stats()["exchange_redos"] == (1 if cap else 0)
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("with_comm", [False, True])
+def test_pipelined_batches_equal_single_calls(with_comm):
+    """gpe_query_batches (host planning of batch i+1 behind the GPU work of batch i) returns what gpe_query_batch returns
+    batch by batch -- batches of different composition, with limits, with and without a (one-rank) communicator."""
+    gold = load_case("uniform300")
+    g = graph_io.read_graph(gold["data_path"])
+    sorted_nodes, membership = graph_io.read_membership(gold["membership_path"], g.V)
+    ctx = gpe.GpeContext(0)
+    try:
+        if with_comm:
+            ctx.comm_init(0, 1, gpe.comm_unique_id())
+        ctx.set_graph(g.offsets, g.nbrs, g.labels)
+        _, vde = gpe.host_gen_vde(g.offsets, g.nbrs, g.labels, gold["e"])
+        ctx.set_embeddings(vde)
+        ctx.enumerate(gold["l"] + 1, sorted_nodes, membership, gold["p"])
+        ctx.build_table_shard()
+        queries = [graph_io.read_graph(qf) for qf in gold["query_paths_files"]]
+        limits = [r["limit"] if r["limit"] is not None else gpe.LIMIT_MAX for r in gold["queries"]]
+        want = [r["answer"] for r in gold["queries"]]
+        batches = [queries, queries[:3], queries[::-1], queries[2:]]
+        lims = [limits, limits[:3], limits[::-1], limits[2:]]
+        got = ctx.query_batches(batches, lims)
+        assert [a.tolist() for a in got] == [want, want[:3], want[::-1], want[2:]]
+        assert ctx.query_batches([]) == []
+    finally:
+        ctx.close()
