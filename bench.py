@@ -421,6 +421,7 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        s2 = ctx.stats()
         t1 = time.perf_counter()
         outs = ctx.run_batches(prepared)
         torch.cuda.synchronize()
@@ -429,6 +430,9 @@ def main():
         s3 = ctx.stats()
         e2e = dict(value=nq * args.steps / e2e_s, unit="queries/s", h2d_bytes_per_step=int(s3["h2d_bytes"] // args.steps),
                    d2h_bytes_per_step=int(s3["d2h_bytes"] // args.steps), ms_per_step=1000.0 * e2e_s / args.steps,
+                   launches_per_step=(s3["kernel_launches"] - s2["kernel_launches"]) / args.steps,
+                   join_reruns=int(s3["join_reruns"] - s2["join_reruns"]), exchange_redos=int(s3["exchange_redos"] - s2["exchange_redos"]),
+                   n_candidates=int(s3["n_candidates"]), exchange_bytes=int(s3["exchange_bytes"]),
                    api=f"gpe_query_batches: {args.steps} batches in one call (host plan of batch i+1 overlapped with the GPU work of batch i; "
                        "per batch: plan + H2D + kernels" + (" + NCCL all-gather + all-reduce" if world > 1 else "") + " + D2H)")
         if world == 1:

@@ -411,7 +411,8 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
                          c->d_q_nbrs.as<u32>(), c->d_q_labels.as<u32>(), c->d_cand_off.as<u64>(), c->d_order.as<u32>(),
                          c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_item_base.as<u64>(), rank, world,
                          enumerate, clean_start, c->n_labels, c->d_lcoff.as<u32>(), c->d_tjobs.as<TreeJob>(),
-                         c->d_tchild.as<u32>(), c->d_tcursor.as<u64>(), tcount, tlist, n_slots, allow_weighted, d_qmode, c->stream));
+                         c->d_tchild.as<u32>(), c->d_tcursor.as<u64>(), tcount, tlist, n_slots, allow_weighted, d_qmode,
+                         (float)(getenv("GPE_JOIN_PEEL") ? (atoi(getenv("GPE_JOIN_PEEL")) ? 1e9 : 0.0) : c->branching), c->stream));
     // (the kernels that walk read tpool[tree_off + v'] with tree_off = table offset + V - lcoff[label]: pointer shifted by -V;
     //  k3_tree_tables writes through the unshifted pointer it is given separately)
     JoinGraph jv{c->V, c->n_labels, c->d_nbrJ.as<u32>(), c->d_gtab.as<unsigned char>(), c->dir_row_bytes, c->wide_adj,
@@ -636,7 +637,7 @@ int gpe_set_graph(gpe_ctx *c, uint32_t V, const uint32_t *offsets, const uint32_
     if (V) GPE_CUDA(c, cudaMemcpyAsync(c->d_label.p, labels, (size_t)V * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
     GPE_CUDA(c, k0_validate(V, n_adj, c->d_off.as<u32>(), c->d_nbr.as<u32>(), c->d_label.as<u32>(), c->d_deg.as<u32>(),
                             c->d_counters.as<u64>(), c->stream));
-    u64 err3[3];
+    u64 err3[4];
     GPE_CUDA(c, cudaMemcpyAsync(err3, c->d_counters.p, sizeof err3, cudaMemcpyDeviceToHost, c->stream));
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
     if (err3[0] != ~0ull) {
@@ -657,6 +658,9 @@ int gpe_set_graph(gpe_ctx *c, uint32_t V, const uint32_t *offsets, const uint32_
     c->n_labels = V ? max_label + 1 : 0;
     c->max_degree = max_deg;
     const u32 nl = c->n_labels;
+    // expected number of neighbours of ONE given label of a vertex reached over an edge: (sum d^2 / sum d) / labels.  Above ~1
+    // a walk over unique-label query vertices grows (power-law graphs), below it dies out (the join's plan uses it)
+    c->branching = n_adj && nl ? (double)err3[3] / (double)n_adj / (double)nl : 0.0;
     // group directory: one row per vertex with the start of every label group of its adjacency; 16-bit offsets from the
     // row's base while degrees allow it (46 bytes per vertex at 20 labels instead of 84)
     c->wide_adj = V > (1u << 24);

@@ -219,6 +219,7 @@ struct gpe_ctx {
 
     // graph
     u32 V = 0, n_adj = 0, n_labels = 0, max_degree = 0;
+    double branching = 0.0;  // (sum d^2 / sum d) / labels: growth factor of a walk over unique-label query vertices
     gpe::DevBuf d_off, d_nbr, d_label, d_deg, d_rank, d_sorted, d_member, d_vde, d_vrec, d_ranklab;
     gpe::DevBuf d_nbrJ, d_gtab, d_offJ, d_degJ, d_labelJ, d_newid;  // the join's class-ordered copy of the graph (k0_graph.cu)
     gpe::DevBuf d_nbrG;  // adjacency grouped by neighbour label in the caller's ids (k1 histogram / fill)
@@ -311,7 +312,7 @@ cudaError_t exclusive_scan_u64(u64 *d_data, u64 n, DevBuf &tmp, cudaStream_t s);
 u64 exclusive_scan_launches(u64 n);
 
 // K0: device-side construction of what gpe_set_graph derives from the CSR (k0_graph.cu)
-// err3: {smallest (code << 32 | vertex) or ~0, max label, max degree}; codes 1 offsets, 2 id range, 3 self loop, 4 order
+// err3 (4 words): {smallest (code << 32 | vertex) or ~0, max label, max degree, sum of squared degrees}; codes 1 offsets, 2 id range, 3 self loop, 4 order
 cudaError_t k0_validate(u32 V, u32 n_adj, const u32 *off, const u32 *nbr, const u32 *label, u32 *deg, u64 *err3, cudaStream_t s);
 cudaError_t k0_build_classes(u32 V, u32 n_labels, const u32 *label, const u32 *deg, u32 *lcoff /*n_labels + 2*/, u32 *lclass,
                              u32 *lpos, u32 *newid, u32 *degJ, u32 *labelJ, u32 *offJ /*V + 1*/, u32 *max_class_dev, DevBuf &tmp,
@@ -382,7 +383,9 @@ cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebas
                      query label (they come from the filter)*/, u32 n_labels, const u32 *lcoff, TreeJob *tjobs, u32 *tchild,
                      u64 *tcursor, u32 *tcount /*kMaxTreeLevels, zeroed*/, u32 *tlist /*kMaxTreeLevels x 2 n_slots*/, u32 n_slots,
                      bool allow_weighted /*counted leaves may carry peeled subtrees (depth-first kernel only)*/,
-                     const u32 *qmode /*per query or null: 0 as usual, 1 no weighted leaves, 2 leave the query out*/, cudaStream_t s);
+                     const u32 *qmode /*per query or null: 0 as usual, 1 no weighted leaves, 2 leave the query out*/,
+                     float branching /*growth factor of a walk per depth (graph statistic): decides whether tabulating peeled
+                     subtrees over whole label classes pays for a query*/, cudaStream_t s);
 // tables of the peeled subtrees, levels 1..max_level (one launch each)
 constexpr u32 kMaxTreeLevels = GPE_MAX_QUERY_VERTICES;
 cudaError_t k3_tree_tables(const JoinGraph &jv, u32 n_slots, u32 max_class, u32 max_level, const TreeJob *tjobs,

@@ -21,7 +21,7 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// err[0]: smallest (code << 32 | vertex) seen, err[1]: max label, err[2]: max degree
+// err[0]: smallest (code << 32 | vertex) seen, err[1]: max label, err[2]: max degree, err[3]: sum of squared degrees
 __global__ void __launch_bounds__(256) k0_validate_kernel(u32 V, u32 n_adj, const u32 *__restrict__ off,
                                                           const u32 *__restrict__ nbr, const u32 *__restrict__ label,
                                                           u32 *__restrict__ deg, unsigned long long *err) {
@@ -47,13 +47,16 @@ __global__ void __launch_bounds__(256) k0_validate_kernel(u32 V, u32 n_adj, cons
         my_label = label[v];
         if (bad != ~0ull) atomicMin(err, bad);
     }
+    unsigned long long sq = (unsigned long long)my_deg * my_deg;
     for (int o = 16; o; o >>= 1) {
         my_label = max(my_label, __shfl_xor_sync(kFull, my_label, o));
         my_deg = max(my_deg, __shfl_xor_sync(kFull, my_deg, o));
+        sq += __shfl_xor_sync(kFull, sq, o);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMax(err + 1, (unsigned long long)my_label);
         atomicMax(err + 2, (unsigned long long)my_deg);
+        atomicAdd(err + 3, sq);
     }
 }
 
@@ -165,7 +168,7 @@ cudaError_t k0_gather(u64 n, const u32 *map, const u32 *in, u32 *out, cudaStream
 }
 
 cudaError_t k0_validate(u32 V, u32 n_adj, const u32 *off, const u32 *nbr, const u32 *label, u32 *deg, u64 *err3, cudaStream_t s) {
-    const u64 init[3] = {~0ull, 0, 0};
+    const u64 init[4] = {~0ull, 0, 0, 0};
     cudaError_t e = cudaMemcpyAsync(err3, init, sizeof init, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
     if (V) k0_validate_kernel<<<(V + 255) / 256, 256, 0, s>>>(V, n_adj, off, nbr, label, deg, reinterpret_cast<unsigned long long *>(err3));

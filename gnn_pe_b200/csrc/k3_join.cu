@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                                                        u32 n_labels, const u32 *__restrict__ lcoff, TreeJob *tjobs,
                                                        u32 *tchild, u64 *tcursor, u32 *tcount, u32 *tlist,
                                                        u32 n_slots /*stride of tlist: 2 x slots*/, u32 sjob_base /*slots*/,
-                                                       bool allow_weighted_all, const u32 *__restrict__ qmode) {
+                                                       bool allow_weighted_all, const u32 *__restrict__ qmode,
+                                                       float branching) {
     // One query per WARP, lane 0 only: the plan is serial, branchy code -- 32 different queries in the lanes of one warp
     // execute it 32 times over (the r01y launch list had this kernel at 94 us for 100 queries in a single CTA) -- and
     // spread over the SMs 1000 queries take as long as 100.
@@ -321,6 +322,27 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                             changed = true;
                         }
                     }
+                }
+            }
+            // Does tabulating pay?  A table costs one entry per vertex of a whole label class; walking the peeled vertices
+            // instead costs about roots x (b + b^2 + ...) steps, b = the graph's growth factor per depth.  With a selective
+            // filter on a large label alphabet (BASELINE.json configs 3 / 5: a few hundred start candidates, classes of
+            // 200 K vertices, b = 0.4) the walk is thousands of times cheaper; on a power-law graph (b > 1) it explodes.
+            // Tables are dropped only when the walk is estimated at least 16 times cheaper.
+            if (n_peel) {
+                double table_cost = 0.0;
+                for (u32 u = 0; u < nq; u++) {
+                    bool has_child = false;
+                    for (u32 k = 0; k < n_peel; k++) has_child = has_child || par[peel[k]] == u;
+                    if (has_child && qlab[u] < n_labels) table_cost += (double)(lcoff[qlab[u] + 1] - lcoff[qlab[u]]);
+                }
+                double g = 0.0, bp = 1.0;
+                for (u32 i = 1; i < nq; i++) { bp *= (double)branching; g += bp; if (g > 1e18) break; }
+                const double walk_cost = (double)count(start) * (1.0 + g);
+                if (walk_cost * 16.0 < table_cost) {
+                    n_peel = 0;
+                    alive = nq >= 64 ? ~0ull : (1ull << nq) - 1;
+                    for (u32 u = 0; u < nq; u++) { remdeg[u] = qdeg(u); par[u] = 0xffffffffu; }
                 }
             }
             const u32 nK = nq - n_peel;
@@ -1469,13 +1491,13 @@ cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebas
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
                      JoinDepth *jplan, void *kids, u64 *item_base, u32 rank, u32 world, bool enumerate, bool clean_start,
                      u32 n_labels, const u32 *lcoff, TreeJob *tjobs, u32 *tchild, u64 *tcursor, u32 *tcount, u32 *tlist,
-                     u32 n_slots, bool allow_weighted, const u32 *qmode, cudaStream_t s) {
+                     u32 n_slots, bool allow_weighted, const u32 *qmode, float branching, cudaStream_t s) {
     // jobs / child lists / per-level job lists hold 2 x n_slots entries: [0, n_slots) the tables N_v of vertices with
     // peeled children, [n_slots, 2 n_slots) the tables S_u of weighted counted leaves
     k3_order_kernel<<<(n_queries * 32 + 127) / 128 + 1, 128, 0, s>>>(n_queries, V, q_vbase, q_ebase, q_offsets, q_nbrs, q_labels, cand_off, order,
                                       pivot, jplan, reinterpret_cast<uint2 *>(kids), item_base, rank, world, 1, enumerate,
                                       clean_start, n_labels, lcoff, tjobs, tchild, tcursor, tcount, tlist, 2 * n_slots,
-                                      n_slots, allow_weighted, qmode);
+                                      n_slots, allow_weighted, qmode, branching);
     k3_order_prefix_kernel<<<1, 32, 0, s>>>(n_queries, item_base);
     return cudaGetLastError();
 }

@@ -19,3 +19,10 @@ except Exception as e: print("no json", e)
 PY
   tail -3 gpurun_out/${TAG}_bench_${WL}.err
 done
+if [ -n "$GPE_LAUNCH_LIST" ]; then
+  for WL in $GPE_LAUNCH_LIST; do
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${TAG}_launches_${WL}.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-streaming --workload $WL > gpurun_out/${TAG}_ncu_bench_${WL}.log 2>&1
+    echo "ncu $WL rc=$?"
+  done
+fi
