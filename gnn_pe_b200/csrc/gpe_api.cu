@@ -77,7 +77,27 @@ struct QPathSet {
     u32 L = 0, D = 0;
     std::vector<u32> slots, labels, degs;  // n x L
     std::vector<double> pde;               // n x D
+    std::vector<u32> sid;                  // survivor counter of every path (empty: its own index)
     u32 n() const { return L ? (u32)(labels.size() / L) : 0; }
+    // GPE_FILTER_BOTH_ORIENTATIONS: every plan path once more with its positions reversed -- comparing the reversed plan
+    // path with a stored row is comparing the plan path with the row's other orientation, which the reference never
+    // stored (custom.h:68-79) and never compares (:407-435).  Survivors of both count for the original path.
+    void add_reversed() {
+        const u32 n0 = n(), E = D / L;
+        sid.resize(n0);
+        for (u32 i = 0; i < n0; i++) sid[i] = i;
+        for (u32 i = 0; i < n0; i++) {
+            for (u32 k = 0; k < L; k++) {
+                const size_t src = (size_t)i * L + (L - 1 - k);
+                slots.push_back(slots[src]);
+                labels.push_back(labels[src]);
+                degs.push_back(degs[src]);
+            }
+            for (u32 k = 0; k < L; k++)
+                for (u32 x = 0; x < E; x++) pde.push_back(pde[(size_t)i * D + (size_t)(L - 1 - k) * E + x]);
+            sid.push_back(i);
+        }
+    }
 };
 
 int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
@@ -107,7 +127,7 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
         while (j < n && j - i < (u32)kQB && (!prune || keys[order[j]] == keys[order[i]])) j++;
         QBlockHost hb;
         hb.n = j - i;
-        hb.first_qpath = order[i];
+        hb.first_qpath = qp.sid.empty() ? order[i] : qp.sid[order[i]];
         if (prune) {
             u64 r0 = c->h_bucket_start[keys[order[i]]], r1 = c->h_bucket_start[keys[order[i]] + 1];
             hb.t0 = (u32)(r0 / kTileRows);
@@ -118,7 +138,7 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
         }
         for (u32 m = 0; m < hb.n; m++) {
             u32 q = order[i + m];
-            ids[m] = q;
+            ids[m] = qp.sid.empty() ? q : qp.sid[q];
             for (u32 k = 0; k < L; k++) {
                 bl[m * L + k] = qp.labels[(size_t)q * L + k];
                 bd[m * L + k] = qp.degs[(size_t)q * L + k];
@@ -968,6 +988,7 @@ int gpe_filter(gpe_ctx *c, uint32_t n_qpaths, const uint32_t *q_vids, const uint
     qp.degs.assign(q_degs, q_degs + (size_t)n_qpaths * L);
     qp.pde.assign(q_pde, q_pde + (size_t)n_qpaths * D);
     c->b_nq = 1;
+    if (flags & GPE_FILTER_BOTH_ORIENTATIONS) qp.add_reversed();
     int rc = setup_filter(c, qp, nq, flags);
     if (rc) return rc;
     rc = run_filter(c);
@@ -1117,6 +1138,7 @@ static int upload_planned(gpe_ctx *c, const gpe_batch *b, const gpe_plan &pl, ui
         qp.degs.insert(qp.degs.end(), plan.degs.begin(), plan.degs.end());
         qp.pde.insert(qp.pde.end(), plan.pde.begin(), plan.pde.end());
     }
+    if (flags & GPE_FILTER_BOTH_ORIENTATIONS) qp.add_reversed();
     int rc = upload_queries(c, b->n_queries, b->q_vbase, b->q_ebase, b->q_offsets, b->q_nbrs, b->q_labels, b->limits);
     if (rc) return rc;
     c->b_pge = false;

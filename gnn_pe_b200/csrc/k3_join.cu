@@ -998,7 +998,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
         //      header is good enough; near the end only a fresh one is trusted)
         if (free_m && h_head < h_tail && (fresh || h_head + 65536 < h_tail)) {
             const u64 avail = h_tail - h_head;
-            const u32 n_want = (u32)min((u64)__popc(free_m), avail);
+            // scarce work (fewer tickets than lanes on the GPU: small batches, selective filters) is spread one ticket per
+            // warp -- 32 different roots in the lanes of one warp run 32 divergent walks one after the other while
+            // thousands of warps sit idle; the lanes of the claiming warp are fed by donation instead
+            const u64 n_warps = (u64)gridDim.x * (THREADS / 32);
+            const u32 share = (u32)min((avail + n_warps - 1) / n_warps, (u64)32);
+            const u32 n_want = (u32)min((u64)min((u32)__popc(free_m), share), avail);
             u64 b0 = 0;
             if (lane == 0) b0 = atomicAdd(&jq->head, (unsigned long long)n_want);
             b0 = __shfl_sync(kFull, b0, 0);

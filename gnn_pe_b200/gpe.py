@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpe.so")
 LIMIT_MAX = 0xFFFFFFFF
 FILTER_NO_PRUNE = 1
+FILTER_BOTH_ORIENTATIONS = 2  # exact mode: the true number of embeddings, not the reference's under-count
 COMM_ID_BYTES = 128
 
 _LIB = None

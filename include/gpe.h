@@ -91,6 +91,12 @@ int gpe_dump_table(gpe_ctx *ctx, uint64_t first, uint64_t n, uint32_t *vids /*n 
                    uint32_t *degs /*n x L*/, double *pde /*n x L*e*/);
 
 #define GPE_FILTER_NO_PRUNE 1u /* streaming mode: every plan path is compared with every table row */
+/* Exact mode (off by default because it changes results relative to the reference): every plan path is
+ * also compared with the OTHER orientation of every stored row.  The reference stores one orientation per path
+ * (custom.h:68-79) and never compares the reverse (:407-435), which loses candidates and under-counts (its quick start
+ * prints 45,426 of 221,832 embeddings); with both orientations the candidate sets are complete and the answer is the
+ * true number of embeddings.  Accepted by gpe_filter, gpe_batch_upload, gpe_query_batch(es) and the multi-GPU calls. */
+#define GPE_FILTER_BOTH_ORIENTATIONS 2u
 
 /* One query: the plan paths (Query_Plan Q of Partition::query) against the whole table.  The candidate
  * sets stay on the device; cand_offsets (nq+1) gives their sizes, survivors (n_qpaths, may be NULL) the
