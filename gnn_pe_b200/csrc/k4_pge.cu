@@ -171,7 +171,6 @@ __global__ void __launch_bounds__(256) k4_pge_scan_kernel(PgeView p, u32 V, u32 
         for (u32 l = l_first; l <= l_last; l++) {
             const u32 c0 = lcoff[l], c1 = lcoff[l + 1];
             const bool mine = in && idx >= c0 && idx < c1;
-            const u32 pos = idx - c0;
             if (mine) my_rows++;
             for (u32 i0 = label_slot_off[l]; i0 < label_slot_off[l + 1]; i0 += kPgeChunk) {
                 const u32 n = min((u32)kPgeChunk, label_slot_off[l + 1] - i0);
@@ -191,12 +190,17 @@ __global__ void __launch_bounds__(256) k4_pge_scan_kernel(PgeView p, u32 V, u32 
                     const unsigned m = __ballot_sync(kFull, ok);
                     if (!m) continue;
                     my += ok ? 1 : 0;
-                    // the warp's rows of this class are consecutive positions: everything that shares my word, written once
-                    const unsigned peers = __match_any_sync(kFull, mine ? pos >> 5 : 0xffffffffu);
-                    if (mine && (peers & ((1u << lane) - 1)) == 0) {
-                        u32 word = 0;
-                        for (unsigned r = m & peers; r; r &= r - 1) word |= 1u << ((pos + (__ffs(r) - 1 - lane)) & 31);
-                        if (word) atomicOr(bitmap + (u64)s_slot[j] * words_per_slot + (pos >> 5), word);
+                    // the warp's 32 rows are consecutive bit positions base_pos .. base_pos + 31 of the slot's class-local
+                    // bitmap (negative / beyond the class for rows of a neighbouring class, whose `ok` is false): they fall
+                    // into at most two words, written by lane 0 -- no per-survivor atomics, no match instruction
+                    if (lane == 0) {
+                        const int base_pos = (int)(idx) - (int)c0;  // lane 0's position
+                        const int sh = ((base_pos % 32) + 32) % 32;
+                        const int w_first = (base_pos - sh) / 32;   // floor(base_pos / 32)
+                        const unsigned m0 = sh ? m & ((1u << (32 - sh)) - 1) : m, m1 = sh ? m >> (32 - sh) : 0u;
+                        u32 *dst = bitmap + (u64)s_slot[j] * words_per_slot;
+                        if (m0) atomicOr(dst + w_first, m0 << sh);
+                        if (m1) atomicOr(dst + w_first + 1, m1);
                     }
                 }
             }
