@@ -324,6 +324,10 @@ int run_scan(gpe_ctx *c) {
         }
         {
             StageTimer tm(c, &c->stats.last_scan_ms, kStageScan);
+            if (c->tv.ids_only)
+                GPE_CUDA(c, k2_scan_ids(c->tv, c->d_vrec.p, c->d_qblocks.p, c->d_worklist.as<u64>(), c->d_counters.as<u64>(),
+                                        c->d_bitmap.as<u32>(), c->b_words, c->d_survivors.as<u64>(), c->sm_count, c->stream));
+            else
             GPE_CUDA(c, k2_scan(c->tv, c->d_qblocks.p, c->d_worklist.as<u64>(), c->d_counters.as<u64>(),
                                 c->d_bitmap.as<u32>(), c->b_words, c->d_survivors.as<u64>(),
                                 !(c->b_flags & GPE_FILTER_NO_PRUNE), c->sm_count, c->stream));
@@ -635,6 +639,8 @@ int gpe_get_stats(gpe_ctx *c, gpe_stats *out) {
     c->stats.table_tiles = c->tv.n_tiles;
     c->stats.tile_rows = kTileRows;
     c->stats.row_bytes = c->tv.L ? (u64)c->tv.L * 8 + (u64)c->tv.D * 8 : 0;
+    c->stats.table_ids_only = c->tv.ids_only ? 1 : 0;
+    c->stats.stored_row_bytes = c->tv.L ? (c->tv.ids_only ? (u64)c->tv.L * 4 : (u64)c->tv.L * 12 + (u64)c->tv.D * 8) : 0;
     *out = c->stats;
     return GPE_OK;
 }
@@ -900,17 +906,34 @@ int gpe_build_table(gpe_ctx *c, const uint8_t *part_select, uint64_t *n_table_ro
     t.n_rows = c->h_bucket_start[t.n_keys];
     t.n_tiles = (t.n_rows + kTileRows - 1) / kTileRows;
     if (t.n_tiles >= 0xffffffffull) return c->fail(GPE_ERR_UNSUPPORTED, "table has more than 2^32 tiles");
-    const size_t tile_bytes_total = std::max<u64>(t.n_tiles, 1) * t.tile_bytes;
+    size_t tile_bytes_total = std::max<u64>(t.n_tiles, 1) * t.tile_bytes;
     const size_t vids_bytes = std::max<u64>(t.n_tiles, 1) * t.L * kTileRows * sizeof(u32);
-    cudaError_t e1 = c->d_tiles.reserve(tile_bytes_total);
+    // Layout: materialised scan rows (8L + 8Le bytes each, what k2_scan streams) next to the ids, or the ids alone
+    // (4L bytes per row, everything else gathered by k2_scan_ids) when the rows would not fit -- config 4's l=3, e=4 table
+    // is 160 bytes x 2 x 10^10 rows materialised.  Auto: materialise while table + ids stay below 70 % of the free HBM.
+    {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        free_b += c->d_tiles.cap + c->d_vids.cap + c->d_sum_u32.cap + c->d_sum_f64.cap;  // what a rebuild would reuse
+        t.ids_only = c->table_layout == 2 || (c->table_layout == 0 && (double)(tile_bytes_total + vids_bytes) > 0.7 * (double)free_b);
+    }
+    if (t.ids_only) {
+        c->d_tiles.release();
+        c->d_sum_u32.release();
+        c->d_sum_f64.release();
+        tile_bytes_total = 0;
+    }
+    cudaError_t e1 = t.ids_only ? cudaSuccess : c->d_tiles.reserve(tile_bytes_total);
     cudaError_t e2 = e1 == cudaSuccess ? c->d_vids.reserve(vids_bytes) : e1;
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         cudaGetLastError();
         return c->fail(GPE_ERR_CUDA, "path table of %llu rows needs %.1f GB of HBM: %s", (unsigned long long)t.n_rows,
                        (tile_bytes_total + vids_bytes) / 1e9, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     }
-    GPE_CUDA(c, c->d_sum_u32.reserve(std::max<u64>(t.n_tiles, 1) * 3 * t.L * sizeof(u32)));
-    GPE_CUDA(c, c->d_sum_f64.reserve(std::max<u64>(t.n_tiles, 1) * t.D * sizeof(double)));
+    if (!t.ids_only) {
+        GPE_CUDA(c, c->d_sum_u32.reserve(std::max<u64>(t.n_tiles, 1) * 3 * t.L * sizeof(u32)));
+        GPE_CUDA(c, c->d_sum_f64.reserve(std::max<u64>(t.n_tiles, 1) * t.D * sizeof(double)));
+    }
     t.tiles = c->d_tiles.as<unsigned char>();
     t.vids = c->d_vids.as<u32>();
     t.lab_min = c->d_sum_u32.as<u32>();
@@ -920,12 +943,12 @@ int gpe_build_table(gpe_ctx *c, const uint8_t *part_select, uint64_t *n_table_ro
     t.bucket_start = bucket;
     if (t.n_tiles) {
         // only the tail of the last tile is never written
-        GPE_CUDA(c, cudaMemsetAsync(t.tiles + (t.n_tiles - 1) * t.tile_bytes, 0, t.tile_bytes, c->stream));
+        if (!t.ids_only) GPE_CUDA(c, cudaMemsetAsync(t.tiles + (t.n_tiles - 1) * t.tile_bytes, 0, t.tile_bytes, c->stream));
         GPE_CUDA(c, cudaMemsetAsync(t.vids + (t.n_tiles - 1) * t.L * kTileRows, 0, t.L * kTileRows * sizeof(u32), c->stream));
     }
     GPE_CUDA(c, cudaMemcpyAsync(c->d_cursor.p, bucket, ((size_t)t.n_keys + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
     GPE_CUDA(c, k1_fill(g, t, c->d_sorted.as<u32>(), c->d_member.as<u32>(), sel, c->d_cursor.as<u64>(), c->sm_count, c->stream));
-    GPE_CUDA(c, k1_expand(t, c->d_vrec.p, c->sm_count, c->stream));
+    if (!t.ids_only) GPE_CUDA(c, k1_expand(t, c->d_vrec.p, c->sm_count, c->stream));
     cudaEventRecord(b1, c->stream);
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaEventElapsedTime(&c->stats.last_build_ms, b0, b1);
@@ -942,6 +965,12 @@ int gpe_build_table(gpe_ctx *c, const uint8_t *part_select, uint64_t *n_table_ro
     return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_build_table", ex.what()) : GPE_ERR_INVALID;
 }
 
+int gpe_set_table_layout(gpe_ctx *c, int layout) {
+    if (!c || layout < 0 || layout > 2) return c ? c->fail(GPE_ERR_INVALID, "layout must be 0 (auto), 1 (rows) or 2 (ids only)") : GPE_ERR_INVALID;
+    c->table_layout = layout;
+    return GPE_OK;
+}
+
 int gpe_dump_table(gpe_ctx *c, uint64_t first, uint64_t n, uint32_t *vids, uint32_t *labels, uint32_t *degs, double *pde) try {
     if (!c) return GPE_ERR_INVALID;
     if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
@@ -956,7 +985,7 @@ int gpe_dump_table(gpe_ctx *c, uint64_t first, uint64_t n, uint32_t *vids, uint3
     if (degs && e == cudaSuccess) e = dd.reserve(n * L * sizeof(u32));
     if (pde && e == cudaSuccess) e = dp.reserve(n * D * sizeof(double));
     if (e == cudaSuccess)
-        e = k1_dump_table(c->tv, graph_view(c), first, n, vids ? dv.as<u32>() : nullptr, labels ? dl.as<u32>() : nullptr,
+        e = k1_dump_table(c->tv, graph_view(c), c->d_vrec.p, first, n, vids ? dv.as<u32>() : nullptr, labels ? dl.as<u32>() : nullptr,
                           degs ? dd.as<u32>() : nullptr, pde ? dp.as<double>() : nullptr, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (vids && e == cudaSuccess) e = cudaMemcpy(vids, dv.p, n * L * sizeof(u32), cudaMemcpyDeviceToHost);

@@ -119,6 +119,7 @@ struct TableView {
     u32 L, E, D;
     u64 n_rows, n_tiles;
     u32 tile_bytes;
+    bool ids_only;  // no scan tiles and no summaries: `vids` holds the rows' vertex ids, everything else is gathered (k2_scan_ids)
     unsigned char *tiles;
     u32 *vids;
     // per-tile summaries (the analogue of Partition::build_auxiliary_index, custom.h:268-364)
@@ -251,6 +252,7 @@ struct gpe_ctx {
 
     // table
     gpe::TableView tv{};
+    int table_layout = 0;  // gpe_set_table_layout: 0 auto, 1 materialised rows, 2 ids only
     gpe::DevBuf d_tiles, d_vids, d_sum_u32, d_sum_f64, d_bucket, d_cursor;
     std::vector<u64> h_bucket_start;
 
@@ -340,8 +342,8 @@ cudaError_t k1_fill(const GraphView &g, const TableView &t, const u32 *sorted, c
 size_t k1_vertex_record_bytes(u32 V, u32 e);
 cudaError_t k1_vertex_records(const GraphView &g, void *vrec, cudaStream_t s);
 cudaError_t k1_expand(const TableView &t, const void *vrec, int sm_count, cudaStream_t s);
-cudaError_t k1_dump_table(const TableView &t, const GraphView &g, u64 first, u64 n, u32 *vids, u32 *labels, u32 *degs,
-                          double *pde, cudaStream_t s);
+cudaError_t k1_dump_table(const TableView &t, const GraphView &g, const void *vrec, u64 first, u64 n, u32 *vids, u32 *labels,
+                          u32 *degs, double *pde, cudaStream_t s);
 
 // K2
 size_t qblock_rec_bytes(u32 L, u32 E);
@@ -353,6 +355,9 @@ cudaError_t k2_select(const TableView &t, const void *qblocks, const u32 *qb_t0,
 // with_vids: the tiles' vertex ids travel with them through the TMA ring (pruned work lists, survivors common)
 cudaError_t k2_scan(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters, u32 *bitmap,
                     u64 words_per_slot, u64 *survivors, bool with_vids, int sm_count, cudaStream_t s);
+// the same scan over an ids-only table: rows are gathered from the packed vertex records (k1_vertex_records)
+cudaError_t k2_scan_ids(const TableView &t, const void *vrec, const void *qblocks, const u64 *worklist, const u64 *counters,
+                        u32 *bitmap, u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s);
 bool k2_supported(u32 L, u32 E);
 
 // K3 (candidate compaction, matching order, join)

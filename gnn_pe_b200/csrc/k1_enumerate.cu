@@ -393,13 +393,26 @@ __global__ void __launch_bounds__(256) k1_vertex_records_kernel(GraphView g, u32
     }
 }
 
-__global__ void k1_dump_table_kernel(TableView t, GraphView g, u64 first, u64 n, u32 *vids, u32 *labels, u32 *degs,
-                                     double *pde) {
+__global__ void k1_dump_table_kernel(TableView t, GraphView g, const uint4 *__restrict__ vrec, u64 first, u64 n, u32 *vids,
+                                     u32 *labels, u32 *degs, double *pde) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u64 row = first + i;
     u64 tile = row / kTileRows;
     u32 r = (u32)(row % kTileRows);
+    if (t.ids_only) {  // the row is its vertex ids; the columns are what the scan gathers
+        const u32 rq = 1 + (t.E + 1) / 2;
+        for (u32 k = 0; k < t.L; k++) {
+            const u32 v = t.vids[(tile * t.L + k) * kTileRows + r];
+            const uint4 h = vrec[(u64)v * rq];
+            if (vids) vids[i * t.L + k] = v;
+            if (labels) labels[i * t.L + k] = h.x;
+            if (degs) degs[i * t.L + k] = h.y;
+            if (pde)
+                for (u32 x = 0; x < t.E; x++) pde[i * t.D + k * t.E + x] = g.vde[(u64)v * t.E + x];
+        }
+        return;
+    }
     const unsigned char *base = t.tiles + tile * t.tile_bytes;
     const u32 *lab = reinterpret_cast<const u32 *>(base);
     const u32 *dg = reinterpret_cast<const u32 *>(base + 4u * t.L * kTileRows);
@@ -539,10 +552,11 @@ cudaError_t k1_expand(const TableView &t, const void *vrec, int sm_count, cudaSt
     return cudaGetLastError();
 }
 
-cudaError_t k1_dump_table(const TableView &t, const GraphView &g, u64 first, u64 n, u32 *vids, u32 *labels, u32 *degs,
-                          double *pde, cudaStream_t s) {
+cudaError_t k1_dump_table(const TableView &t, const GraphView &g, const void *vrec, u64 first, u64 n, u32 *vids, u32 *labels,
+                          u32 *degs, double *pde, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    k1_dump_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t, g, first, n, vids, labels, degs, pde);
+    k1_dump_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(t, g, reinterpret_cast<const uint4 *>(vrec), first, n, vids,
+                                                                    labels, degs, pde);
     return cudaGetLastError();
 }
 

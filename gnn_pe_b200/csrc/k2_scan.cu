@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) k2_select_kernel(TableView t, const QBloc
             }
             b = lo;
             tile = qb_t0[b] + (u32)(idx - qb_prefix[b]);
-            if (!prune) {
+            if (!prune || t.ids_only) {  // (an ids-only table keeps no per-tile summaries: the bucket directory is the pruning)
                 pass = true;
             } else {
                 const QBlockRec<L, E> &rec = qblocks[b];
@@ -352,6 +352,92 @@ k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u
     }
 }
 
+// ---- the scan of an ids-only table ---------------------------------------------------------------------------
+// Layout for tables that do not fit materialised (BASELINE.json config 4: l=3, e=4 -> 160-byte rows, ~2 x 10^10 of them):
+// a row is its L vertex ids (4L bytes); label, degree, class position and embedding of every vertex come from the packed
+// per-vertex records k1_expand gathers from (16 + 8e bytes each, L2-resident up to a few million vertices).  The
+// row-level test is the same; what streams from HBM is 4L bytes per row plus the gathers that miss L2, and neighbouring
+// rows of a bucket share all but their last vertex, so most gathers of a warp are one broadcast line.
+// One row per thread, a contiguous chunk of the work list per CTA, the query-path block of the chunk in shared memory.
+template <int L, int E>
+__global__ void __launch_bounds__(kTileRows) k2_scan_ids_kernel(TableView t, const uint4 *__restrict__ vrec,
+                                                                const QBlockRec<L, E> *__restrict__ qblocks,
+                                                                const u64 *__restrict__ worklist,
+                                                                const u64 *__restrict__ counters, u32 *__restrict__ bitmap,
+                                                                u64 words_per_slot, u64 *__restrict__ survivors) {
+    constexpr int D = L * E;
+    constexpr int RQ = 1 + (E + 1) / 2;
+    __shared__ QBlockRec<L, E> s_rec;
+    const int lane = threadIdx.x & 31;
+    const u32 r = threadIdx.x;
+    const u64 n_items = counters[0];
+    const u64 per = (n_items + gridDim.x - 1) / gridDim.x;
+    const u64 first = min((u64)blockIdx.x * per, n_items), n_my = min(per, n_items - first);
+    u32 cur_b = 0xffffffffu, my_cnt = 0, my_qpath = 0;
+    for (u64 k = 0; k < n_my; k++) {
+        const u64 item = worklist[first + k];
+        const u32 tile = (u32)item, b = (u32)(item >> 32);
+        if (b != cur_b) {  // block-uniform
+            if (my_cnt) atomicAdd((unsigned long long *)&survivors[my_qpath], (unsigned long long)my_cnt);
+            my_cnt = 0;
+            cur_b = b;
+            __syncthreads();  // everybody is done with the previous block's record
+            const u32 *src = reinterpret_cast<const u32 *>(&qblocks[b]);
+            u32 *dst = reinterpret_cast<u32 *>(&s_rec);
+            for (u32 i = threadIdx.x; i < sizeof(QBlockRec<L, E>) / 4; i += blockDim.x) dst[i] = src[i];
+            __syncthreads();
+            my_qpath = lane < kQB ? s_rec.qpath[lane] : 0;
+        }
+        const bool valid = (u64)tile * kTileRows + r < t.n_rows;
+        u32 v[L];
+#pragma unroll
+        for (int kk = 0; kk < L; kk++) v[kk] = valid ? __ldcs(t.vids + ((u64)tile * L + kk) * kTileRows + r) : 0u;
+        uint4 head[L];
+        double pde[D];
+#pragma unroll
+        for (int kk = 0; kk < L; kk++) {
+            const uint4 *rec = vrec + (u64)v[kk] * RQ;
+            head[kk] = __ldg(rec);
+#pragma unroll
+            for (int x = 0; x < E; x += 2) {
+                const uint4 q = __ldg(rec + 1 + x / 2);
+                pde[kk * E + x] = __hiloint2double((int)q.y, (int)q.x);
+                if (x + 1 < E) pde[kk * E + x + 1] = __hiloint2double((int)q.w, (int)q.z);
+            }
+        }
+        const u32 nq = s_rec.n;
+        u32 okm = 0;
+        for (u32 j = 0; j < nq; j++) {
+            bool ok = valid;
+#pragma unroll
+            for (int kk = 0; kk < L; kk++) ok &= (s_rec.labels[j][kk] == head[kk].x) & (s_rec.degs[j][kk] <= head[kk].y);
+            if (ok) {
+#pragma unroll
+                for (int d = 0; d < D; d++) ok &= !(s_rec.pde[j][d] - pde[d] > kEps);
+            }
+            const unsigned m = __ballot_sync(kFull, ok);
+            if (lane == (int)j) my_cnt += __popc(m);
+            okm |= (u32)ok << j;
+        }
+        if (__any_sync(kFull, okm != 0)) {
+            const u32 okm_left = __shfl_up_sync(kFull, okm, 1);
+#pragma unroll
+            for (int kk = 0; kk < L; kk++) {
+                const u32 pos = okm ? head[kk].z : 0xffffffffu, lab = head[kk].x;  // class position: the bit index
+                const u32 pos_left = __shfl_up_sync(kFull, pos, 1), lab_left = __shfl_up_sync(kFull, lab, 1);
+                u32 todo = okm;
+                if (lane > 0 && pos_left == pos && lab_left == lab) todo &= ~okm_left;  // the left neighbour sets the same bits
+                while (todo) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    atomicOr(bitmap + (u64)s_rec.slot[j][kk] * words_per_slot + (pos >> 5), 1u << (pos & 31));
+                }
+            }
+        }
+    }
+    if (my_cnt) atomicAdd((unsigned long long *)&survivors[my_qpath], (unsigned long long)my_cnt);
+}
+
 template <int L, int E>
 cudaError_t launch_select(const TableView &t, const void *qblocks, const u32 *qb_t0, const u64 *qb_prefix,
                           u32 n_qblocks, u64 n_items, bool prune, u64 *worklist, u64 *counters, cudaStream_t s) {
@@ -482,6 +568,24 @@ cudaError_t k2_select(const TableView &t, const void *qblocks, const u32 *qb_t0,
                       u64 n_items, bool prune, u64 *worklist, u64 *counters, cudaStream_t s) {
     cudaError_t e = cudaErrorInvalidValue;
 #define CALL(l, e_) e = launch_select<l, e_>(t, qblocks, qb_t0, qb_prefix, n_qblocks, n_items, prune, worklist, counters, s)
+    GPE_DISPATCH_LE(t.L, t.E, CALL);
+#undef CALL
+    return e;
+}
+
+template <int L, int E>
+cudaError_t launch_scan_ids(const TableView &t, const void *vrec, const void *qblocks, const u64 *worklist, const u64 *counters,
+                            u32 *bitmap, u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s) {
+    k2_scan_ids_kernel<L, E><<<(unsigned)sm_count * 8, kTileRows, 0, s>>>(t, reinterpret_cast<const uint4 *>(vrec),
+                                                                        reinterpret_cast<const QBlockRec<L, E> *>(qblocks), worklist,
+                                                                        counters, bitmap, words_per_slot, survivors);
+    return cudaGetLastError();
+}
+
+cudaError_t k2_scan_ids(const TableView &t, const void *vrec, const void *qblocks, const u64 *worklist, const u64 *counters,
+                        u32 *bitmap, u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s) {
+    cudaError_t e = cudaErrorInvalidValue;
+#define CALL(l, e_) e = launch_scan_ids<l, e_>(t, vrec, qblocks, worklist, counters, bitmap, words_per_slot, survivors, sm_count, s)
     GPE_DISPATCH_LE(t.L, t.E, CALL);
 #undef CALL
     return e;

@@ -52,7 +52,7 @@ class Stats(C.Structure):
                 ("last_scan_ms", "last_select_ms", "last_compact_ms", "last_join_ms", "last_build_ms",
                  "last_enumerate_ms")] + \
                [(n, C.c_uint64) for n in ("n_qpaths", "n_qblocks", "n_slots", "n_candidates", "join_items",
-                                        "kernel_launches", "h2d_bytes", "d2h_bytes", "join_exports", "join_donations", "join_steps", "join_warp_iters", "join_idle_polls", "join_bfs", "join_fallbacks", "join_reruns", "exchange_bytes", "exchange_redos")]
+                                        "kernel_launches", "h2d_bytes", "d2h_bytes", "join_exports", "join_donations", "join_steps", "join_warp_iters", "join_idle_polls", "join_bfs", "join_fallbacks", "join_reruns", "table_ids_only", "stored_row_bytes", "exchange_bytes", "exchange_redos")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -70,7 +70,7 @@ SYMBOLS = [
     "gpe_pge_batch_filter", "gpe_pge_query_batch", "gpe_get_stats", "gpe_stream", "gpe_sync", "gpe_set_timing",
     "gpe_collect_timings", "gpe_comm_unique_id", "gpe_comm_init", "gpe_comm_init_all", "gpe_comm_destroy", "gpe_comm_info",
     "gpe_build_table_shard", "gpe_batch_step", "gpe_batch_finish", "gpe_multi_batch_upload", "gpe_multi_batch_step",
-    "gpe_multi_batch_finish", "gpe_multi_query_batch", "gpe_query_batches",
+    "gpe_multi_batch_finish", "gpe_multi_query_batch", "gpe_query_batches", "gpe_set_table_layout",
 ]
 
 
@@ -121,6 +121,7 @@ def lib():
         L.gpe_pge_batch_filter.argtypes = [vp]
         L.gpe_pge_query_batch.argtypes = [vp, C.POINTER(Batch), vp]
         L.gpe_query_batches.argtypes = [vp, u32, vp, u32, vp]
+        L.gpe_set_table_layout.argtypes = [vp, C.c_int]
         L.gpe_comm_unique_id.argtypes = [vp]
         L.gpe_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
         L.gpe_comm_init_all.argtypes = [vp, C.c_int]
@@ -329,6 +330,10 @@ class GpeContext:
         return out
 
     # ---- S2 ----
+    def set_table_layout(self, layout: int):
+        """0 auto, 1 materialised rows, 2 vertex ids only (rows gathered by the scan)."""
+        self._ck(self._L.gpe_set_table_layout(self._h, layout))
+
     def build_table(self, part_select=None) -> int:
         sel = None if part_select is None else np.ascontiguousarray(part_select, dtype=np.uint8)
         n = C.c_uint64(0)

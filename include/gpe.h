@@ -86,6 +86,15 @@ int gpe_start_rows(gpe_ctx *ctx, uint64_t *start_row /*V+1*/);
 /* Materialise the structure-of-arrays path table (labels, degrees, path embeddings; vertex ids beside
  * it) for the partitions with part_select[i] != 0 (NULL = all).  Needs gpe_enumerate + gpe_set_embeddings. */
 int gpe_build_table(gpe_ctx *ctx, const uint8_t *part_select /*p or NULL*/, uint64_t *n_table_rows);
+/* How the next gpe_build_table stores the rows.  GPE_TABLE_ROWS: labels, degrees and path embeddings materialised
+ * (8L + 8Le bytes per row, 72 at l=2,e=2: what the TMA scan streams) next to the vertex ids (4L).  GPE_TABLE_IDS: the
+ * vertex ids only; the scan gathers everything else from packed per-vertex records -- for tables that do not fit
+ * materialised (l=3, e=4: 160-byte rows).  GPE_TABLE_AUTO (default): rows while they fit in 70 % of the free HBM.
+ * Candidate sets and answers do not depend on the layout. */
+#define GPE_TABLE_AUTO 0
+#define GPE_TABLE_ROWS 1
+#define GPE_TABLE_IDS 2
+int gpe_set_table_layout(gpe_ctx *ctx, int layout);
 /* Copy the table back in its physical (label-bucketed) row order, for parity checks: any may be NULL. */
 int gpe_dump_table(gpe_ctx *ctx, uint64_t first, uint64_t n, uint32_t *vids /*n x L*/, uint32_t *labels /*n x L*/,
                    uint32_t *degs /*n x L*/, double *pde /*n x L*e*/);
@@ -250,6 +259,8 @@ typedef struct gpe_stats {
     uint64_t join_fallbacks;  /* level-synchronous joins recomputed depth-first because a frontier outgrew its buffer */
     uint64_t join_reruns;     /* batches some of whose queries were joined a second time with their weighted counted leaves
                                  walked, because a weighted count met a saturated (>= 2^62) table entry */
+    uint64_t table_ids_only;  /* 1: the table holds vertex ids only (GPE_TABLE_IDS) */
+    uint64_t stored_row_bytes; /* bytes per row actually held in HBM: 4L + row_bytes, or 4L for an ids-only table */
     uint64_t exchange_bytes;  /* multi-GPU: bytes this GPU received in the last candidate exchange (dense bitmaps or sparse pairs) */
     uint64_t exchange_redos;  /* steps redone with the dense exchange because a shard outgrew the sparse buffer */
 } gpe_stats;
