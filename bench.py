@@ -43,6 +43,15 @@ WORKLOADS = {
                     l=2, e=2, n_queries=1000, q_vertices=(4, 16), q_mixed=True, q_seed=2026, p=8, min_gpus=2,
                     desc="synthetic Poisson-degree 10M v / 100M e / 50 labels, p=8, l=2, e=2, 1000 mixed sparse/dense "
                          "random-walk queries of 4-16 vertices, n=MAX"),
+    # BASELINE.json configs[3]: longer paths.  Poisson degrees (mean 20), 20 labels: ~1.8 x 10^10 four-vertex paths; 160-byte
+    # rows materialised would be 2.9 TB, so the table is held as vertex ids only (16 bytes per row: 290 GB, 36 GB per GPU
+    # at 8) and the scan gathers the rest (GPE_TABLE_IDS, chosen automatically).  Patched-oracle semantics for l=3
+    "config4": dict(kind="uniform_native", V=5_000_000, E=50_000_000, labels=20, seed=2027,
+                    l=3, e=4, n_queries=100, q_vertices=12, q_seed=2028, p=8, min_gpus=2,
+                    desc="synthetic Poisson-degree 5M v / 50M e / 20 labels, p=8, l=3, e=4, 100 dense (induced) random-walk 12-vertex queries"),
+    "config4_small": dict(kind="uniform_native", V=100_000, E=1_000_000, labels=20, seed=2027,
+                          l=3, e=4, n_queries=50, q_vertices=12, q_seed=2028, p=8,
+                          desc="synthetic Poisson-degree 100K v / 1M e / 20 labels, p=8, l=3, e=4, 50 dense (induced) random-walk 12-vertex queries"),
     # down-scaled copies of configs 3 / 5 (same generator and query mix) for development runs and the CPU tests
     "config3_small": dict(kind="uniform_native", V=200_000, E=2_000_000, labels=50, seed=2024,
                           l=2, e=2, n_queries=100, q_vertices=8, q_seed=2025, p=8,
@@ -306,6 +315,8 @@ def main():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-streaming", action="store_true")
+    ap.add_argument("--table-layout", type=int, default=0, choices=[0, 1, 2],
+                    help="0 auto (rows while they fit), 1 materialised rows, 2 vertex ids only (rows gathered by the scan)")
     ap.add_argument("--filter", default="path", choices=["path", "pge"],
                     help="path: GNN-PE's path-table dominance scan (the headline); pge: the GNN-PGE per-vertex path-group filter")
     args = ap.parse_args()
@@ -360,14 +371,17 @@ def main():
     ctx.set_embeddings(vde)
     ctx.set_timing(1)
     n_rows, rows_pp = ctx.enumerate(L, sorted_nodes, membership, p)
+    ctx.set_table_layout(args.table_layout)
     table_rows = ctx.build_table_shard()
     st = ctx.stats()
     row_bytes = st["row_bytes"]
     peak, peak_src = peaks()
     # K1 (offline table build) against the HBM roofline, SURVEY.md 8(d): N x (4L + row_bytes) written + the CSR read once
-    k1_bytes = table_rows * (4 * L + row_bytes) + 4 * (g.V + 1 + 2 * g.E + g.V)
+    k1_bytes = table_rows * st["stored_row_bytes"] + 4 * (g.V + 1 + 2 * g.E + g.V)
     build = dict(enumerate_ms=st["last_enumerate_ms"], build_table_ms=st["last_build_ms"], rows=n_rows,
-                 table_rows_this_rank=table_rows, table_gb_this_rank=table_rows * (row_bytes + 4 * L) / 1e9,
+                 table_rows_this_rank=table_rows, table_gb_this_rank=table_rows * st["stored_row_bytes"] / 1e9,
+                 table_layout="ids only (rows gathered by the scan)" if st["table_ids_only"] else "materialised rows + ids",
+                 stored_row_bytes=int(st["stored_row_bytes"]),
                  set_graph_s=t_graph, setup_s=time.time() - t0,
                  roofline_k1=dict(bound="hbm", kernels="k1_hist + k1_fill + k1_expand (whole table build)",
                                   algorithmic_bytes=int(k1_bytes), ms=st["last_build_ms"],
@@ -474,7 +488,9 @@ def main():
     tr = static_json("profiles", "scan_traffic.json")
     if tr and world == 1 and tr.get("workload", "config2") == args.workload:
         traffic, traffic_src = tr.get("in_step_dram_bytes_per_launch"), "profiles/scan_traffic.json (ncu --set full capture, not re-measured by this run)"
-    roofline = dict(bound="hbm", kernel=f"k2_scan_kernel<{L},{e}> (in-step, label-bucketed work list)", achieved=achieved, peak=peak,
+    roofline = dict(bound="hbm", kernel=(f"k2_scan_ids_kernel<{L},{e}> (ids-only table: {4 * L} B/row streamed, the rest gathered)"
+                                         if st_step["table_ids_only"] else f"k2_scan_kernel<{L},{e}>") + " (in-step, label-bucketed work list)",
+                    achieved=achieved, peak=peak,
                     unit="GB/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
                     algorithmic_bytes_per_launch=int(scan_bytes), rows_per_launch=int(st_step["scan_rows"]),
                     row_bytes=int(row_bytes), ms_per_launch=scan_ms,
@@ -517,7 +533,7 @@ def main():
                    config=dict(workload=w["desc"], name=args.workload, partitions=p,
                                parallelism=f"path table sharded over {world} GPU(s) by partition, NCCL inside libgpe" if world > 1 else "1 GPU",
                                l2_policy=f"scan reads {scan_bytes / 1e6:.0f} MB per step from a "
-                                         f"{table_rows * (row_bytes + 4 * L) / 1e9:.1f} GB table (> 126 MB L2), no flush"),
+                                         f"{table_rows * st_step['stored_row_bytes'] / 1e9:.1f} GB table (> 126 MB L2), no flush"),
                    gpu_launches=int(launches), clocks=clocks, e2e=e2e, roofline=roofline, join=join, cpu_baseline=cpu_baseline,
                    cpu_baseline_real=static_json("profiles", "cpu_baseline_real.json"),
                    per_rank=per_rank, build=build, nccl=dict(version=nccl_version, ranks=world, via="libgpe gpe_comm_init (ncclCommInitRank)") if world > 1 else None,

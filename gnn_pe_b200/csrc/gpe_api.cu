@@ -691,6 +691,8 @@ int gpe_set_graph(gpe_ctx *c, uint32_t V, const uint32_t *offsets, const uint32_
     // row's base while degrees allow it (46 bytes per vertex at 20 labels instead of 84)
     c->wide_adj = V > (1u << 24);
     c->wide_dir = max_deg >= 65536u;
+    if (const char *e = getenv("GPE_JOIN_DIR")) c->wide_dir = c->wide_dir || !strcmp(e, "wide");  // measurement switches
+    if (const char *e = getenv("GPE_JOIN_ADJ")) c->wide_adj = c->wide_adj || !strcmp(e, "wide");
     c->dir_row_bytes = c->wide_dir ? (nl + 1) * 4 : (4 + (nl + 1) * 2 + 3) / 4 * 4;
     const u64 dir_bytes = (u64)V * c->dir_row_bytes;
     {
@@ -1213,6 +1215,7 @@ int gpe_batch_download(gpe_ctx *c, uint64_t *raw_counts) try {
     static_assert(sizeof(JoinQueue) <= 16 * sizeof(u64), "pinned layout");
     if (nq) GPE_CUDA(c, cudaMemcpyAsync(pin_flags, c->d_answers.as<u64>() + nq + 8, nq * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     GPE_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->need_dense_redo = false;
     if (c->b_sparse_used) {  // sparse exchange: did every shard's non-zero words fit the buffer?  (same numbers on every rank)
         const u64 *h = c->h_pin4.as<u64>();
         u64 mx = 0;

@@ -1001,8 +1001,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
             // scarce work (fewer tickets than lanes on the GPU: small batches, selective filters) is spread one ticket per
             // warp -- 32 different roots in the lanes of one warp run 32 divergent walks one after the other while
             // thousands of warps sit idle; the lanes of the claiming warp are fed by donation instead
+            // (decided once per launch from the number of start tickets: the tail of a long queue is still claimed 32 at a time)
             const u64 n_warps = (u64)gridDim.x * (THREADS / 32);
-            const u32 share = (u32)min((avail + n_warps - 1) / n_warps, (u64)32);
+            const u32 share = n_init >= n_warps * 32 ? 32u : (u32)max((n_init + n_warps - 1) / n_warps, (u64)1);
             const u32 n_want = (u32)min((u64)min((u32)__popc(free_m), share), avail);
             u64 b0 = 0;
             if (lane == 0) b0 = atomicAdd(&jq->head, (unsigned long long)n_want);

@@ -20,6 +20,7 @@ from oracle import oracle  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "config_answers.json")
 SAMPLES = {"config2": [0, 17, 38, 59, 80, 99], "config3": [0, 21, 42, 63, 84], "config5": [0, 201, 402, 603, 804, 999],
+           "config4": [0, 33, 66], "config4_small": list(range(0, 50, 7)),
            "config3_small": list(range(0, 100, 9)), "config5_small": list(range(0, 200, 13)), "small": list(range(0, 100, 11))}
 
 
