@@ -310,8 +310,12 @@ int settle_candidates(gpe_ctx *c) {
 // select + scan: the candidate bitmaps of this GPU's table (shard) are on the device afterwards
 int run_scan(gpe_ctx *c) {
     const u64 n_items = c->b_items_unpruned;
-    GPE_CUDA(c, cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(u64), c->stream));
-    GPE_CUDA(c, cudaMemsetAsync(c->d_survivors.p, 0, std::max<u32>(c->b_qpaths, 1) * sizeof(u64), c->stream));
+    {
+        ZeroList z;
+        z.add(c->d_counters.p, 8 * sizeof(u64));
+        z.add(c->d_survivors.p, std::max<u32>(c->b_qpaths, 1) * sizeof(u64));
+        GPE_CUDA(c, k0_zero(z, c->stream));
+    }
     GPE_CUDA(c, cudaMemsetAsync(c->d_bitmap.p, 0, std::max<u64>((u64)c->b_slots * c->b_words, 1) * sizeof(u32), c->stream));
     if (n_items > 0 && c->b_qblocks > 0) {
         {
@@ -411,8 +415,9 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
     c->b_world = world;
     const u32 nq = c->b_nq;
     u64 *answers = c->d_answers.as<u64>();
-    GPE_CUDA(c, cudaMemsetAsync(c->d_answers.p, 0, (2 * (size_t)nq + 8) * sizeof(u64), c->stream));
-    GPE_CUDA(c, cudaMemsetAsync(c->d_match_cursor.p, 0, 2 * sizeof(u64), c->stream));
+    ZeroList zl;  // everything the join wants zeroed, one launch (filled below)
+    zl.add(c->d_answers.p, (2 * (size_t)nq + 8) * sizeof(u64));
+    zl.add(c->d_match_cursor.p, 2 * sizeof(u64));
     GPE_CUDA(c, c->d_jq.reserve(sizeof(JoinQueue)));
     // Subtree tables are only sound when the start vertex's candidates carry its label; that holds for the
     // filter's own candidate sets (their bitmaps are on the device), not for caller-supplied ones (gpe_refine).
@@ -423,20 +428,35 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
     GPE_CUDA(c, c->d_tjobs.reserve(2 * std::max<size_t>(n_slots, 1) * sizeof(TreeJob)));
     GPE_CUDA(c, c->d_tchild.reserve(2 * std::max<size_t>(n_slots, 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_tcursor.reserve(4 * sizeof(u64)));
-    GPE_CUDA(c, c->d_tpool.reserve(2 * std::max<u64>((u64)n_slots * c->max_class, 1) * sizeof(u64)));
-    GPE_CUDA(c, cudaMemsetAsync(c->d_tcursor.p, 0, 4 * sizeof(u64), c->stream));
+    // table pool: room for a table per slot and a sum table per slot at most, capped at 1 Gi entries (8 GB) and a quarter
+    // of the free memory -- a query whose tables do not fit walks instead (k3_order reserves per query)
+    u64 pool_cap = 2 * std::max<u64>((u64)n_slots * c->max_class, 1);
+    if (c->d_tpool.cap / sizeof(u64) < pool_cap) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        pool_cap = std::min<u64>(pool_cap, std::max<u64>(std::min<u64>(1ull << 30, (free_b + c->d_tpool.cap) / 4 / sizeof(u64)), c->d_tpool.cap / sizeof(u64)));
+        if (const char *e = getenv("GPE_JOIN_POOL")) pool_cap = std::min<u64>(pool_cap, std::max<u64>(strtoull(e, nullptr, 10), 1));  // tests
+        GPE_CUDA(c, c->d_tpool.reserve(pool_cap * sizeof(u64)));
+    }
+    pool_cap = std::min<u64>(pool_cap, c->d_tpool.cap / sizeof(u64));
+    if (const char *e = getenv("GPE_JOIN_POOL")) pool_cap = std::min<u64>(pool_cap, std::max<u64>(strtoull(e, nullptr, 10), 1));
+    zl.add(c->d_tcursor.p, 4 * sizeof(u64));
     GPE_CUDA(c, c->d_tlist.reserve(((size_t)kMaxTreeLevels * 2 * std::max<u32>(n_slots, 1) + kMaxTreeLevels) * sizeof(u32)));
     bool allow_weighted = true;  // counted leaves may carry peeled subtrees
     if (const char *e = getenv("GPE_JOIN_WEIGHTED")) allow_weighted = atoi(e) != 0;
     (void)force_dfs;
     u32 *tcount = c->d_tlist.as<u32>(), *tlist = tcount + kMaxTreeLevels;
-    GPE_CUDA(c, cudaMemsetAsync(tcount, 0, kMaxTreeLevels * sizeof(u32), c->stream));
+    zl.add(tcount, kMaxTreeLevels * sizeof(u32));
+    GPE_CUDA(c, c->d_qcur.reserve(((size_t)nq + 1) * 6 * sizeof(u64)));
+    zl.add(c->d_qcur.p, ((size_t)nq + 1) * 6 * sizeof(u64));
+    GPE_CUDA(c, k0_zero(zl, c->stream));
     GPE_CUDA(c, k3_order(nq, c->V, c->d_q_vbase.as<u32>(), c->d_q_ebase.as<u32>(), c->d_q_offsets.as<u32>(),
                          c->d_q_nbrs.as<u32>(), c->d_q_labels.as<u32>(), c->d_cand_off.as<u64>(), c->d_order.as<u32>(),
                          c->d_pivot.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_item_base.as<u64>(), rank, world,
                          enumerate, clean_start, c->n_labels, c->d_lcoff.as<u32>(), c->d_tjobs.as<TreeJob>(),
                          c->d_tchild.as<u32>(), c->d_tcursor.as<u64>(), tcount, tlist, n_slots, allow_weighted, d_qmode,
-                         (float)(getenv("GPE_JOIN_PEEL") ? (atoi(getenv("GPE_JOIN_PEEL")) ? 1e9 : 0.0) : c->branching), c->stream));
+                         (float)(getenv("GPE_JOIN_PEEL") ? (atoi(getenv("GPE_JOIN_PEEL")) ? 1e9 : 0.0) : c->branching), pool_cap,
+                         c->stream));
     // (the kernels that walk read tpool[tree_off + v'] with tree_off = table offset + V - lcoff[label]: pointer shifted by -V;
     //  k3_tree_tables writes through the unshifted pointer it is given separately)
     JoinGraph jv{c->V, c->n_labels, c->d_nbrJ.as<u32>(), c->d_gtab.as<unsigned char>(), c->dir_row_bytes, c->wide_adj,
@@ -463,8 +483,6 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
     const u32 epoch = ++c->join_epoch;
     JoinQueue *jq = c->d_jq.as<JoinQueue>();
     const u32 heavy_deg = std::max<u32>(32, c->V ? (u32)(4ull * c->n_adj / c->V) : 32);  // 4 x the mean degree
-    GPE_CUDA(c, c->d_qcur.reserve(((size_t)nq + 1) * 6 * sizeof(u64)));
-    GPE_CUDA(c, cudaMemsetAsync(c->d_qcur.p, 0, ((size_t)nq + 1) * 6 * sizeof(u64), c->stream));
     GPE_CUDA(c, k3_init_items(jv, nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_cand_off.as<u64>(),
                               c->d_cand.as<u32>(), c->d_item_base.as<u64>(), rank, world, heavy_deg,
                               c->d_qcur.as<u64>(), c->d_init.p, jq, tree_launches > 0,
@@ -472,8 +490,8 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
     GPE_CUDA(c, k3_dfs(jv, c->b_max_nq, c->d_q_vbase.as<u32>(), c->d_jplan.as<JoinDepth>(), c->d_kids.p, c->d_cand.as<u32>(),
                        c->d_init.p, c->d_limits.as<u64>(), answers, c->d_items.as<u32>(), cap, c->d_ready.as<u32>(), epoch,
                        jq, d_matches, matches_cap, c->d_match_cursor.as<u64>(), answers + nq + 8, c->sm_count, c->stream));
-    c->stats.kernel_launches += tree_launches;
-    c->stats.join_launches += tree_launches;
+    c->stats.kernel_launches += tree_launches ? 1 : 0;  // all table levels in one cooperative launch
+    c->stats.join_launches += tree_launches ? 1 : 0;
     c->stats.kernel_launches += 5;
     c->stats.join_launches += 5;
     c->b_joined = true;

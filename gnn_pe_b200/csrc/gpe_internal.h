@@ -324,6 +324,13 @@ cudaError_t k0_build_join_graph(u32 V, u32 n_adj, u32 n_labels, const u32 *off, 
                                 bool wide_dir, u32 dir_row_bytes, u32 *nbrJ, u32 *nbrG, void *gtab, u64 *bloom, u64 bloom_bits,
                                 DevBuf &tmp, int sm_count, cudaStream_t s);
 cudaError_t k0_gather(u64 n, const u32 *map, const u32 *in, u32 *out, cudaStream_t s);  // out[i] = map[in[i]]
+struct ZeroList {  // up to 8 small regions (32-bit words) zeroed by one launch
+    u32 *p[8];
+    u64 words[8];
+    int n = 0;
+    void add(void *ptr, size_t bytes) { p[n] = reinterpret_cast<u32 *>(ptr); words[n] = bytes / 4; n++; }
+};
+cudaError_t k0_zero(const ZeroList &z, cudaStream_t s);
 
 // K1
 cudaError_t k1_rank_labels(u32 V, const u32 *rank, const u32 *label, u64 *ranklab, cudaStream_t s);
@@ -390,7 +397,8 @@ cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebas
                      bool allow_weighted /*counted leaves may carry peeled subtrees (depth-first kernel only)*/,
                      const u32 *qmode /*per query or null: 0 as usual, 1 no weighted leaves, 2 leave the query out*/,
                      float branching /*growth factor of a walk per depth (graph statistic): decides whether tabulating peeled
-                     subtrees over whole label classes pays for a query*/, cudaStream_t s);
+                     subtrees over whole label classes pays for a query*/,
+                     u64 pool_cap /*entries of the table pool: a query whose tables do not fit walks instead*/, cudaStream_t s);
 // tables of the peeled subtrees, levels 1..max_level (one launch each)
 constexpr u32 kMaxTreeLevels = GPE_MAX_QUERY_VERTICES;
 cudaError_t k3_tree_tables(const JoinGraph &jv, u32 n_slots, u32 max_class, u32 max_level, const TreeJob *tjobs,

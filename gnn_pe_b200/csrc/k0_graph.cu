@@ -161,6 +161,22 @@ __global__ void __launch_bounds__(256) k0_gather_kernel(u64 n, const u32 *__rest
 
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) k0_zero_kernel(ZeroList z) {
+    for (int r = 0; r < z.n; r++)
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < z.words[r]; i += (u64)gridDim.x * blockDim.x) z.p[r][i] = 0;
+}
+}  // namespace
+
+// several small regions zeroed by ONE launch (a step of a small batch is bound by its launch count)
+cudaError_t k0_zero(const ZeroList &z, cudaStream_t s) {
+    u64 most = 0;
+    for (int r = 0; r < z.n; r++) most = std::max(most, z.words[r]);
+    if (z.n == 0 || most == 0) return cudaSuccess;
+    k0_zero_kernel<<<(unsigned)std::min<u64>((most + 255) / 256, 64), 256, 0, s>>>(z);
+    return cudaGetLastError();
+}
+
 cudaError_t k0_gather(u64 n, const u32 *map, const u32 *in, u32 *out, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     k0_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, map, in, out);

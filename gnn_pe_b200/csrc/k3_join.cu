@@ -14,6 +14,8 @@
 //     candidate sets are only used for the start vertex and for ordering.
 //
 // Latency / divergence bound (L2-resident CSR gathers), no bandwidth roofline, no tensor cores.
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "gpe_internal.h"
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                                                        u32 *tchild, u64 *tcursor, u32 *tcount, u32 *tlist,
                                                        u32 n_slots /*stride of tlist: 2 x slots*/, u32 sjob_base /*slots*/,
                                                        bool allow_weighted_all, const u32 *__restrict__ qmode,
-                                                       float branching) {
+                                                       float branching, u64 pool_cap) {
     // One query per WARP, lane 0 only: the plan is serial, branchy code -- 32 different queries in the lanes of one warp
     // execute it 32 times over (the r01y launch list had this kernel at 94 us for 100 queries in a single CTA) -- and
     // spread over the SMs 1000 queries take as long as 100.
@@ -329,6 +331,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
             // filter on a large label alphabet (BASELINE.json configs 3 / 5: a few hundred start candidates, classes of
             // 200 K vertices, b = 0.4) the walk is thousands of times cheaper; on a power-law graph (b > 1) it explodes.
             // Tables are dropped only when the walk is estimated at least 16 times cheaper.
+            u64 pool_at = 0;  // this query's slice of the table pool (sub-allocated below without atomics)
             if (n_peel) {
                 double table_cost = 0.0;
                 for (u32 u = 0; u < nq; u++) {
@@ -339,7 +342,28 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 double g = 0.0, bp = 1.0;
                 for (u32 i = 1; i < nq; i++) { bp *= (double)branching; g += bp; if (g > 1e18) break; }
                 const double walk_cost = (double)count(start) * (1.0 + g);
-                if (walk_cost * 16.0 < table_cost) {
+                // room in the table pool for everything this query may tabulate, reserved with ONE atomic: a table per
+                // vertex with peeled children plus, at most, a sum table per core leaf that carries peeled subtrees (sized by
+                // the largest class a pivot could have).  No room (the pool is capped) -> this query walks instead.
+                u64 need = 0, biggest = 0;
+                u32 n_sum = 0;
+                for (u32 u = 0; u < nq; u++) {
+                    const u64 cls = qlab[u] < n_labels ? lcoff[qlab[u] + 1] - lcoff[qlab[u]] : 0;
+                    bool has_child = false;
+                    for (u32 k = 0; k < n_peel; k++) has_child = has_child || par[peel[k]] == u;
+                    if (has_child) need += cls;
+                    if (alive >> u & 1) {
+                        biggest = max(biggest, cls);
+                        if (remdeg[u] == 1 && qdeg(u) != 1) n_sum++;
+                    }
+                }
+                need += (u64)n_sum * biggest;
+                bool keep = !(walk_cost * 16.0 < table_cost);
+                if (keep) {
+                    pool_at = atomicAdd((unsigned long long *)tcursor, (unsigned long long)need);
+                    keep = pool_at + need <= pool_cap;
+                }
+                if (!keep) {
                     n_peel = 0;
                     alive = nq >= 64 ? ~0ull : (1ull << nq) - 1;
                     for (u32 u = 0; u < nq; u++) { remdeg[u] = qdeg(u); par[u] = 0xffffffffu; }
@@ -462,7 +486,8 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 tlevel[v] = lvl;
                 tj.level = lvl;
                 const u32 sz = qlab[v] < n_labels ? lcoff[qlab[v] + 1] - lcoff[qlab[v]] : 0;
-                tj.table_off = atomicAdd((unsigned long long *)tcursor, (unsigned long long)sz);
+                tj.table_off = pool_at;
+                pool_at += sz;
                 tlist[(u64)lvl * n_slots + atomicAdd(&tcount[lvl], 1u)] = vb + v;  // this level's launch works on it
             };
             for (u32 k = 0; k < n_peel; k++) make_table(peel[k]);
@@ -485,7 +510,8 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 sj.qdeg = qdeg(pv);
                 sj.start_slot = 0xffffffffu;
                 const u32 sz = qlab[pv] < n_labels ? lcoff[qlab[pv] + 1] - lcoff[qlab[pv]] : 0;
-                sj.table_off = atomicAdd((unsigned long long *)tcursor, (unsigned long long)sz);
+                sj.table_off = pool_at;
+                pool_at += sz;
                 tlist[(u64)sj.level * n_slots + atomicAdd(&tcount[sj.level], 1u)] = ji;
                 stab[u] = sj.table_off + V - (qlab[pv] < n_labels ? lcoff[qlab[pv]] : 0);  // read as tpool[.. + v' of the pivot's image]
             }
@@ -865,16 +891,22 @@ __global__ void __launch_bounds__(256) k3_init_items_kernel(u32 n_queries, const
 //     N_v[x] = prod over peeled children c of v ( sum over y in N(x), label(y) = label(c), deg(y) >= deg(c)
 //                                                  [, y in C(start) when c is the start vertex] of N_c[y] ),
 // with N_c = 1 for a child without children.  All labels of a peeled subtree are unique in the query, so these maps
-// are injective and disjoint from the rest by construction.  One launch per table level (children before parents);
-// blockIdx.y = query vertex slot.
+// are injective and disjoint from the rest by construction.  ONE cooperative launch for all levels (children before
+// parents, a grid-wide barrier between two levels): a batch without any table -- large label alphabets, where the plan
+// walks instead (k3_order) -- costs one launch that reads one counter, not one launch per possible level.
 __global__ void __launch_bounds__(256) k3_tree_tables_kernel(JoinGraph g, const TreeJob *__restrict__ tjobs,
-                                                             const u32 *__restrict__ tchild, u32 level,
+                                                             const u32 *__restrict__ tchild, u32 max_level,
                                                              const u32 *__restrict__ tcount,
                                                              const u32 *__restrict__ tlist, u32 n_slots,
                                                              const u32 *__restrict__ bitmap, u64 words_per_slot,
                                                              u64 *tpool, u32 max_class) {
-  // work unit = (table of this level, block of 256 class positions); a level without tables costs one look at tcount
+ cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+ for (u32 level = 1; level <= max_level; level++) {
+  // work unit = (table of this level, block of 256 class positions).  Levels are filled bottom-up: a table of level k has
+  // a child table of level k-1, so the first empty level ends the kernel (every block reads the same counter)
   const u32 n_jobs = tcount[level];
+  if (n_jobs == 0) break;
+  if (level > 1) grid.sync();  // the tables of the level below are complete
   const u32 chunks = (max_class + 255) / 256;
   for (u64 unit = blockIdx.x; unit < (u64)n_jobs * chunks; unit += gridDim.x) {
     const u32 ji = (u32)(unit / chunks), chunk = (u32)(unit % chunks);
@@ -910,6 +942,7 @@ __global__ void __launch_bounds__(256) k3_tree_tables_kernel(JoinGraph g, const 
         tpool[job.table_off + pos] = val;
     }
   }
+ }
 }
 
 template <int M, int THREADS, int MINB>
@@ -1497,13 +1530,13 @@ cudaError_t k3_order(u32 n_queries, u32 V, const u32 *q_vbase, const u32 *q_ebas
                      const u32 *q_nbrs, const u32 *q_labels, const u64 *cand_off, u32 *order, u32 *pivot,
                      JoinDepth *jplan, void *kids, u64 *item_base, u32 rank, u32 world, bool enumerate, bool clean_start,
                      u32 n_labels, const u32 *lcoff, TreeJob *tjobs, u32 *tchild, u64 *tcursor, u32 *tcount, u32 *tlist,
-                     u32 n_slots, bool allow_weighted, const u32 *qmode, float branching, cudaStream_t s) {
+                     u32 n_slots, bool allow_weighted, const u32 *qmode, float branching, u64 pool_cap, cudaStream_t s) {
     // jobs / child lists / per-level job lists hold 2 x n_slots entries: [0, n_slots) the tables N_v of vertices with
     // peeled children, [n_slots, 2 n_slots) the tables S_u of weighted counted leaves
     k3_order_kernel<<<(n_queries * 32 + 127) / 128 + 1, 128, 0, s>>>(n_queries, V, q_vbase, q_ebase, q_offsets, q_nbrs, q_labels, cand_off, order,
                                       pivot, jplan, reinterpret_cast<uint2 *>(kids), item_base, rank, world, 1, enumerate,
                                       clean_start, n_labels, lcoff, tjobs, tchild, tcursor, tcount, tlist, 2 * n_slots,
-                                      n_slots, allow_weighted, qmode, branching);
+                                      n_slots, allow_weighted, qmode, branching, pool_cap);
     k3_order_prefix_kernel<<<1, 32, 0, s>>>(n_queries, item_base);
     return cudaGetLastError();
 }
@@ -1533,11 +1566,20 @@ cudaError_t k3_tree_tables(const JoinGraph &g, u32 n_slots, u32 max_class, u32 m
     if (n_slots == 0 || max_class == 0) return cudaSuccess;
     // one persistent 1-D grid per level over (table, block of 256 class positions) units: a level with a handful of tables
     // still fills the GPU, and a level without any costs a launch of blocks that read one counter and exit
-    const u32 grid = (u32)sm_count * 8;
-    for (u32 level = 1; level <= max_level; level++)
-        k3_tree_tables_kernel<<<grid, 256, 0, s>>>(g, tjobs, tchild, level, tcount, tlist, 2 * n_slots /*list stride*/, bitmap,
-                                                   words_per_slot, tpool, max_class);
-    return cudaGetLastError();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static int per_sm[kMaxDevices] = {};
+    if (!per_sm[dev % kMaxDevices]) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k3_tree_tables_kernel, 256, 0) != cudaSuccess || n < 1) n = 1;
+        per_sm[dev % kMaxDevices] = std::min(n, 8);
+    }
+    const u32 grid = (u32)sm_count * per_sm[dev % kMaxDevices];  // all blocks resident: the kernel synchronises grid-wide
+    JoinGraph gg = g;
+    u32 list_stride = 2 * n_slots;
+    void *args[] = {&gg, (void *)&tjobs, (void *)&tchild, &max_level, (void *)&tcount, (void *)&tlist, &list_stride, (void *)&bitmap,
+                    &words_per_slot, &tpool, &max_class};
+    return cudaLaunchCooperativeKernel((const void *)k3_tree_tables_kernel, dim3(grid), dim3(256), args, 0, s);
 }
 
 cudaError_t k3_dfs(const JoinGraph &g, u32 max_nq, const u32 *q_vbase, const JoinDepth *jplan, const void *kids, const u32 *cand,

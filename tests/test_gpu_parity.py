@@ -499,7 +499,8 @@ def test_weighted_leaves_equal_walked_leaves_and_oracle(nl, seed, monkeypatch):
     assert len(queries) >= 20 and sum(1 for e in expect if e > 0) >= len(expect) // 4
 
     def run(env):
-        monkeypatch.delenv("GPE_JOIN_WEIGHTED", raising=False)
+        for k in ("GPE_JOIN_WEIGHTED", "GPE_JOIN_POOL", "GPE_JOIN_PEEL"):
+            monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         ctx = gpe.GpeContext(0)
@@ -521,3 +522,8 @@ def test_weighted_leaves_equal_walked_leaves_and_oracle(nl, seed, monkeypatch):
     walked, st_d, _ = run({"GPE_JOIN_WEIGHTED": "0"})
     assert walked == expect
     assert st_d["join_steps"] >= st_w["join_steps"]  # counting never walks more than walking
+    # a table pool too small for any table (a query whose tables do not fit walks instead) and no tables at all
+    tiny, st_t, _ = run({"GPE_JOIN_POOL": "64"})
+    assert tiny == expect and st_t["join_steps"] >= st_w["join_steps"]
+    none, _, _ = run({"GPE_JOIN_PEEL": "0"})
+    assert none == expect
