@@ -221,12 +221,6 @@ __global__ void k3_counts_kernel(const u64 *__restrict__ cand_off, u32 n_slots, 
 }
 
 // ---- matching order: generateGQLQueryPlan (custom.h:670-722) + generateBN (:724-755) -----------------------
-__device__ bool q_edge(const u32 *off, const u32 *nbr, u32 u, u32 v) {
-    for (u32 j = off[u]; j < off[u + 1]; j++)
-        if (nbr[j] == v) return true;
-    return false;
-}
-
 __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, const u32 *__restrict__ q_vbase,
                                                        const u32 *__restrict__ q_ebase,
                                                        const u32 *__restrict__ q_offsets,
@@ -254,8 +248,19 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
         const u32 *qlab = q_labels + vb;
         const u64 *co = cand_off + vb;
         u32 *ord = order + vb, *piv = pivot + vb;
-        auto count = [&](u32 u) { return (u32)(co[u + 1] - co[u]); };
-        auto qdeg = [&](u32 u) { return off[u + 1] - off[u]; };
+        // per-vertex candidate counts, degrees and adjacency masks once, up front (independent loads); the selection loops
+        // below ask for them O(nq^2) times
+        u32 cnt_[kMaxNQ], qd_[kMaxNQ];
+        u64 adjm[kMaxNQ];
+        for (u32 u = 0; u < nq; u++) {
+            cnt_[u] = (u32)(co[u + 1] - co[u]);
+            qd_[u] = off[u + 1] - off[u];
+            u64 m = 0;
+            for (u32 j = off[u]; j < off[u + 1]; j++) m |= 1ull << nbr[j];
+            adjm[u] = m;
+        }
+        auto count = [&](u32 u) { return cnt_[u]; };
+        auto qdeg = [&](u32 u) { return qd_[u]; };
         u64 items = 0;
         if (nq > 0) {
             // ---- the reference's plan (reported through gpe_refine / gpe_batch_get_plan) ----
@@ -267,7 +272,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
             u64 visited = 0, adjacent = 0;
             auto mark = [&](u32 u) {
                 visited |= 1ull << u;
-                for (u32 j = off[u]; j < off[u + 1]; j++) adjacent |= 1ull << nbr[j];
+                adjacent |= adjm[u];
             };
             ord[0] = start;
             piv[0] = 0xffffffffu;
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                 ord[i] = next;
                 u32 pv = 0xffffffffu;
                 for (u32 j = 0; j < i; j++)
-                    if (q_edge(off, nbr, next, ord[j])) { pv = ord[j]; break; }
+                    if (adjm[next] >> ord[j] & 1) { pv = ord[j]; break; }
                 piv[i] = pv;
             }
 
@@ -563,7 +568,7 @@ __global__ void __launch_bounds__(256) k3_order_kernel(u32 n_queries, u32 V, con
                         if (t == jd.pivot_depth) continue;
                         if (t == 0 && root_is_start && !clean_start) { jd.tail_mask |= 1ull; continue; }  // its data label is only known at run time
                         if (lab[t] != jd.label) continue;
-                        if (q_edge(off, nbr, xo[t], pvu)) { jd.sure_used++; sure_mask |= 1ull << t; } else jd.tail_mask |= 1ull << t;
+                        if (adjm[xo[t]] >> pvu & 1) { jd.sure_used++; sure_mask |= 1ull << t; } else jd.tail_mask |= 1ull << t;
                     }
                     if (wu) {  // (a core leaf has no backward neighbour besides its pivot: both words are free)
                         jd.bn_mask = sure_mask;   // WHICH prefix vertices surely sit in the group: their weights are subtracted
