@@ -681,9 +681,13 @@ constexpr u32 kSplit = 8;
 constexpr int kExportEveryLog2 = 1;  // log2 of the rounds between two looks at the queue header (config 2, ms per batch:
                                      // every 8 rounds 15.60, 4: 15.28, 2: 15.22, 1: 15.71 -- the end of the join is a few
                                      // generations of subtree hand-overs, each waiting for a busy warp's next look)
-constexpr int kStepsPerRound = 2;   // DFS steps of a lane between two rounds of scheduling (tickets, donation, export)
-constexpr int kExportLanes = 4;  // lanes of a warp that may hand work over in one round
-constexpr int kTailBatch = 8;    // parked lanes that trigger a joint evaluation of their counted-tail factors
+// (round 2, measured with tools/join_split_bench.py -- the join of one rank of an N-way split on one GPU, config 2, ms for
+//  N = 1 / 2 / 4 / 8: steps per round 2 -> 1: 13.9 / 8.2 / 5.4 / 4.1 -> 14.0 / 8.3 / 5.2 / 3.5; tail batch 8 -> 16 on top:
+//  13.7 / 8.0 / 5.1 / 3.5; export lanes 4 -> 8: 3.4-3.6 at N = 8.  Shorter rounds shorten the hand-over generations at
+//  the end of a launch, which is most of a small share's time)
+constexpr int kStepsPerRound = 1;   // DFS steps of a lane between two rounds of scheduling (tickets, donation, export)
+constexpr int kExportLanes = 8;  // lanes of a warp that may hand work over in one round
+constexpr int kTailBatch = 16;   // parked lanes that trigger a joint evaluation of their counted-tail factors
 
 __host__ __device__ constexpr u32 item_stride(u32 m) { return kItemHdr + 3 * m; }
 
@@ -912,40 +916,60 @@ __global__ void __launch_bounds__(256) k3_tree_tables_kernel(JoinGraph g, const 
   const u32 n_jobs = tcount[level];
   if (n_jobs == 0) break;
   if (level > 1) grid.sync();  // the tables of the level below are complete
+  // (the table's description and its children's are block-uniform loads that stay in L1; no shared memory, no block
+  //  barrier: warps of a block run ahead of each other -- a capture with per-table barriers spent half its samples in them)
   const u32 chunks = (max_class + 255) / 256;
+  const int lane = threadIdx.x & 31;
   for (u64 unit = blockIdx.x; unit < (u64)n_jobs * chunks; unit += gridDim.x) {
     const u32 ji = (u32)(unit / chunks), chunk = (u32)(unit % chunks);
     const TreeJob job = tjobs[tlist[(u64)level * n_slots + ji]];
     if (job.label >= g.nl) continue;
     const u32 c0 = g.lcoff[job.label], n = g.lcoff[job.label + 1] - c0;
-    for (u32 pos = chunk * 256 + threadIdx.x; pos < min(n, (chunk + 1) * 256); pos += blockDim.x) {
-        const DirRow row = dir_row(g, c0 + pos);  // class-order id of the class's pos-th vertex: rows are contiguous
-        u64 val = 1;
-        for (u32 k = 0; k < job.n_child && val; k++) {
-            const TreeJob cj = tjobs[tchild[job.child_begin + k]];
-            u64 sum = 0;
-            if (cj.label < g.nl) {
-                u32 s, e;
-                row_range(g, row, cj.label, s, e);
-                if (cj.level == 0 && cj.start_slot == 0xffffffffu) {
-                    sum = e - s;  // a plain leaf: every neighbour of the label (its degree is >= 1)
-                } else {
-                    const u32 *bm = cj.start_slot == 0xffffffffu ? nullptr : bitmap + (u64)cj.start_slot * words_per_slot;
-                    const u32 cfirst = g.lcoff[cj.label];
-                    for (u32 at = s; at < e; at++) {
-                        u32 y, ydeg;
-                        adj_entry(g, at, y, ydeg);
-                        if (ydeg < cj.qdeg) continue;
-                        const u32 yp = y - cfirst;
-                        if (bm && !(bm[yp >> 5] >> (yp & 31) & 1)) continue;
-                        sum = sat_add(sum, cj.level ? tpool[cj.table_off + yp] : 1);
-                    }
-                }
+    const u32 pos = chunk * 256 + threadIdx.x;
+    if (chunk * 256 + (threadIdx.x & ~31u) >= n) continue;  // warp-uniform: nothing of this warp's 32 positions is in the class
+    const bool valid = pos < n;
+    DirRow row{};
+    if (valid) row = dir_row(g, c0 + pos);  // class-order id of the class's pos-th vertex: rows are contiguous
+    u64 val = valid ? 1 : 0;
+    for (u32 k = 0; k < job.n_child; k++) {  // warp-uniform loop: a lane whose product is already 0 just idles
+        const TreeJob cj = tjobs[tchild[job.child_begin + k]];
+        u32 s = 0, e = 0;
+        if (val && cj.label < g.nl) row_range(g, row, cj.label, s, e);
+        u64 sum;
+        if (cj.level == 0 && cj.start_slot == 0xffffffffu) {
+            sum = e - s;  // a plain leaf: every neighbour of the label (its degree is >= 1)
+        } else {
+            const u32 *bm = cj.start_slot == 0xffffffffu ? nullptr : bitmap + (u64)cj.start_slot * words_per_slot;
+            const u32 cfirst = cj.label < g.nl ? g.lcoff[cj.label] : 0;
+            auto weight = [&](u32 at) -> u64 {
+                u32 y, ydeg;
+                adj_entry(g, at, y, ydeg);
+                if (ydeg < cj.qdeg) return 0;
+                const u32 yp = y - cfirst;
+                if (bm && !(bm[yp >> 5] >> (yp & 31) & 1)) return 0;
+                return cj.level ? tpool[cj.table_off + yp] : 1;
+            };
+            // Group sizes are heavy-tailed (a hub has 50 neighbours of one label where the average vertex has one): a lane
+            // sums a short group itself, a long one is summed by the whole warp -- otherwise one hub row holds up 31 lanes
+            constexpr u32 kLong = 8;
+            sum = 0;
+            if (e - s <= kLong)
+                for (u32 at = s; at < e; at++) sum = sat_add(sum, weight(at));
+            unsigned big = __ballot_sync(kFull, e - s > kLong);
+            while (big) {
+                const int src = __ffs(big) - 1;
+                big &= big - 1;
+                const u32 ss = __shfl_sync(kFull, s, src), ee = __shfl_sync(kFull, e, src);
+                u64 part = 0;
+                for (u32 at = ss + lane; at < ee; at += 32) part = sat_add(part, weight(at));
+#pragma unroll
+                for (int o = 16; o; o >>= 1) part = sat_add(part, __shfl_xor_sync(kFull, part, o));
+                if (lane == src) sum = part;
             }
-            val = sat_mul(val, sum);
         }
-        tpool[job.table_off + pos] = val;
+        val = sat_mul(val, sum);
     }
+    if (valid) tpool[job.table_off + pos] = val;
   }
  }
 }
@@ -964,6 +988,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
     const u32 exp_mask = (1u << (flags >> 4 & 7u)) - 1;  // rounds between two looks at the queue header, minus one (kExportEvery)
     const int tail_batch = (int)(flags >> 8 & 0xffu);  // parked lanes that trigger a joint evaluation (kTailBatch)
     const int spr = (int)(flags >> 16 & 0xffu);        // DFS steps of a lane between two rounds of scheduling (kStepsPerRound)
+    const u32 split = flags >> 24 & 0xfu;              // pieces an exported sibling range is cut into (kSplit)
+    const int export_lanes = (int)(flags >> 28 & 0xfu);  // lanes of a warp that may hand work over in one round (kExportLanes)
     extern __shared__ u64 s_stack64[];  // prod [M][THREADS] u64 | emb | cur | end | s0 | e0, each [M][THREADS] u32
     u64 *prod = s_stack64 + threadIdx.x;
     u32 *emb = reinterpret_cast<u32 *>(s_stack64 + M * THREADS) + threadIdx.x;
@@ -1408,12 +1434,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 for (l = base; l <= d; l++)
                     if (CUR(l) < END(l)) { key = (l << 5) | (u32)lane; break; }
             }
-            for (int round = 0; round < kExportLanes; round++) {
+            for (int round = 0; round < export_lanes; round++) {
                 const u32 best = __reduce_min_sync(kFull, key);
                 if (best == 0xffffffffu) break;
                 if (key != best) continue;
                 key = 0xffffffffu;
-                const u32 c0 = CUR(l), len = END(l) - c0, np = min(len, kSplit);
+                const u32 c0 = CUR(l), len = END(l) - c0, np = min(len, split);
                 const u64 o = atomicAdd(&jq->tail, (unsigned long long)np) - n_init;
                 if (o + np > export_cap) {
                     can_export = false;  // those tickets are never published; their holders idle until the end
@@ -1615,11 +1641,16 @@ cudaError_t k3_dfs(const JoinGraph &g, u32 max_nq, const u32 *q_vbase, const Joi
     if (env_cg < 0) { const char *e = getenv("GPE_JOIN_CG"); env_cg = e ? atoi(e) : 1; }
     static int env_exp = -1;
     if (env_exp < 0) { const char *e = getenv("GPE_JOIN_EXPORT_LOG2"); env_exp = e ? atoi(e) : kExportEveryLog2; if (env_exp < 0 || env_exp > 7) env_exp = kExportEveryLog2; }
-    const u32 flags = (env_cg ? 2u : 0u) | ((u32)env_exp << 4) | ((u32)env_tb << 8) | ((u32)env_spr << 16);
+    static int env_split = -1;
+    if (env_split < 0) { const char *e = getenv("GPE_JOIN_SPLIT"); env_split = e ? atoi(e) : (int)kSplit; if (env_split < 1 || env_split > 15) env_split = (int)kSplit; }
+    static int env_xl = -1;
+    if (env_xl < 0) { const char *e = getenv("GPE_JOIN_EXPORT_LANES"); env_xl = e ? atoi(e) : kExportLanes; if (env_xl < 1 || env_xl > 15) env_xl = kExportLanes; }
+    const u32 flags = (env_cg ? 2u : 0u) | ((u32)env_exp << 4) | ((u32)env_tb << 8) | ((u32)env_spr << 16) | ((u32)env_split << 24) |
+                      ((u32)env_xl << 28);
     // 8-vertex stacks, CTAs of 128 threads per SM (config 2, ms per batch): 5 (96 registers) 15.97, 6 (80 registers, 92 bytes of
     // spills) 15.61, 7 (72 registers) 19.9 -- beyond 6 the stacks leave too little of the SM's memory to L1, which holds the plans
     static int env_blocks = -1;
-    if (env_blocks < 0) { const char *e = getenv("GPE_JOIN_BLOCKS"); env_blocks = e ? atoi(e) : 6; }
+    if (env_blocks < 0) { const char *e = getenv("GPE_JOIN_BLOCKS"); env_blocks = e ? atoi(e) : 5; }  // (round 2, one step per round: 5 <= 6)
     if (max_nq <= 8 && env_blocks == 7) { LAUNCH(8, 128, 7); }
     else if (max_nq <= 8 && env_blocks == 6) { LAUNCH(8, 128, 6); }
     else if (max_nq <= 8) { LAUNCH(8, 128, 5); }
