@@ -285,7 +285,9 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
 
 // the lists did not fit: expand them again into a buffer of the right size (chunk offsets are still on the device)
 int recompact(gpe_ctx *c) {
-    GPE_CUDA(c, c->d_cand.reserve(std::max<u64>(c->b_n_cand, 1) * sizeof(u32)));
+    // (sized as the next batches will ask for -- twice the largest total seen -- so that no later step reallocates)
+    const u64 bound = std::max<u64>((u64)c->b_slots * c->max_class, 1);
+    GPE_CUDA(c, c->d_cand.reserve(std::min<u64>(bound, std::max<u64>(2 * c->cand_seen_max, 4ull << 20)) * sizeof(u32)));
     c->b_cand_cap = c->d_cand.cap / sizeof(u32);
     u64 *flag = c->d_counters.as<u64>() + 5;
     GPE_CUDA(c, cudaMemsetAsync(flag, 0, sizeof(u64), c->stream));
