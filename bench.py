@@ -447,6 +447,8 @@ def main():
                    launches_per_step=(s3["kernel_launches"] - s2["kernel_launches"]) / args.steps,
                    join_reruns=int(s3["join_reruns"] - s2["join_reruns"]), exchange_redos=int(s3["exchange_redos"] - s2["exchange_redos"]),
                    n_candidates=int(s3["n_candidates"]), exchange_bytes=int(s3["exchange_bytes"]),
+                   host_ms_per_step=dict(upload=s3["host_upload_ms"] / args.steps, enqueue=s3["host_enqueue_ms"] / args.steps,
+                                         plan_next=s3["host_plan_ms"] / args.steps, finish_wait=s3["host_finish_ms"] / args.steps),
                    api=f"gpe_query_batches: {args.steps} batches in one call (host plan of batch i+1 overlapped with the GPU work of batch i; "
                        "per batch: plan + H2D + kernels" + (" + NCCL all-gather + all-reduce" if world > 1 else "") + " + D2H)")
         if world == 1:

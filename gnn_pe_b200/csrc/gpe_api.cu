@@ -1,6 +1,7 @@
 // gpe_api.cu -- the C ABI (include/gpe.h) and the host orchestration of the three kernel groups.
 // Product code: no CPU fallback, nothing from oracle/.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <numeric>
 #include <thread>
@@ -1772,6 +1773,10 @@ int gpe_batch_finish(gpe_ctx *c, uint64_t *answers) {
 // asynchronous), the host plans batch i+1 (dfs_query + gen_vde + gen_query_pde of every query, custom.h:94-119, :574-633
 // -- what the reference does serially per query before it touches its index, main.cpp:142-158).  With a communicator
 // the collective calls happen in the same order on every rank.
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int gpe_query_batches(gpe_ctx *c, uint32_t n_batches, const gpe_batch *batches, uint32_t flags, uint64_t *const *answers) try {
     if (!c || (n_batches && (!batches || !answers))) return c ? c->fail(GPE_ERR_INVALID, "null argument") : GPE_ERR_INVALID;
     if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
@@ -1780,20 +1785,30 @@ int gpe_query_batches(gpe_ctx *c, uint32_t n_batches, const gpe_batch *batches, 
     if (n_batches)
         if (int rc = plan_batch(&batches[0], c->tv.L, c->tv.E, c->label_table, cur)) return c->fail(rc, "batch 0: %s", cur.err.c_str());
     u64 h2d = 0, d2h = 0;
+    double t_plan = 0, t_upload = 0, t_enqueue = 0, t_finish = 0;  // host wall clock per phase, summed over the batches
     for (uint32_t i = 0; i < n_batches; i++) {
+        double t0 = now_ms();
         if (int rc = upload_planned(c, &batches[i], cur, flags)) return rc;
+        double t1 = now_ms();
         if (int rc = gpe_batch_step(c)) return rc;
+        double t2 = now_ms();
         if (i + 1 < n_batches) {
             next = gpe_plan();
             if (int rc = plan_batch(&batches[i + 1], c->tv.L, c->tv.E, c->label_table, next)) return c->fail(rc, "batch %u: %s", i + 1, next.err.c_str());
         }
+        double t3 = now_ms();
         if (int rc = gpe_batch_finish(c, answers[i])) return rc;
+        t_upload += t1 - t0; t_enqueue += t2 - t1; t_plan += t3 - t2; t_finish += now_ms() - t3;
         h2d += c->stats.h2d_bytes;
         d2h += c->stats.d2h_bytes;
         std::swap(cur, next);
     }
     c->stats.h2d_bytes = h2d;  // of all the batches of this call
     c->stats.d2h_bytes = d2h;
+    c->stats.host_upload_ms = (float)t_upload;
+    c->stats.host_enqueue_ms = (float)t_enqueue;
+    c->stats.host_plan_ms = (float)t_plan;
+    c->stats.host_finish_ms = (float)t_finish;
     return GPE_OK;
 } catch (const std::exception &ex) {
     return c ? c->fail(GPE_ERR_INVALID, "gpe_query_batches: %s", ex.what()) : GPE_ERR_INVALID;

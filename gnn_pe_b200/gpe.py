@@ -52,7 +52,8 @@ class Stats(C.Structure):
                 ("last_scan_ms", "last_select_ms", "last_compact_ms", "last_join_ms", "last_build_ms",
                  "last_enumerate_ms")] + \
                [(n, C.c_uint64) for n in ("n_qpaths", "n_qblocks", "n_slots", "n_candidates", "join_items",
-                                        "kernel_launches", "h2d_bytes", "d2h_bytes", "join_exports", "join_donations", "join_steps", "join_warp_iters", "join_idle_polls", "join_bfs", "join_fallbacks", "join_reruns", "table_ids_only", "stored_row_bytes", "exchange_bytes", "exchange_redos")]
+                                        "kernel_launches", "h2d_bytes", "d2h_bytes", "join_exports", "join_donations", "join_steps", "join_warp_iters", "join_idle_polls", "join_bfs", "join_fallbacks", "join_reruns", "table_ids_only", "stored_row_bytes", "exchange_bytes", "exchange_redos")] + \
+               [(n, C.c_float) for n in ("host_upload_ms", "host_enqueue_ms", "host_plan_ms", "host_finish_ms")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

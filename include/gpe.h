@@ -263,6 +263,9 @@ typedef struct gpe_stats {
     uint64_t stored_row_bytes; /* bytes per row actually held in HBM: 4L + row_bytes, or 4L for an ids-only table */
     uint64_t exchange_bytes;  /* multi-GPU: bytes this GPU received in the last candidate exchange (dense bitmaps or sparse pairs) */
     uint64_t exchange_redos;  /* steps redone with the dense exchange because a shard outgrew the sparse buffer */
+    /* last gpe_query_batches call, host wall clock summed over its batches: staging + H2D enqueue of a planned batch, kernel /
+     * collective enqueue, planning of the NEXT batch (overlaps the GPU), waiting for the GPU + D2H + all-reduce */
+    float host_upload_ms, host_enqueue_ms, host_plan_ms, host_finish_ms;
 } gpe_stats;
 int gpe_get_stats(gpe_ctx *ctx, gpe_stats *out);
 /* The context's CUDA stream (cudaStream_t) so callers can bracket calls with their own events. */
