@@ -101,15 +101,23 @@ struct QPathSet {
     }
 };
 
-int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
+// The host half of setting a batch up for the scan: plan paths grouped into query-path blocks by table bucket, the blocks'
+// records packed, their tile ranges from the bucket directory, the label of every slot.  Reads the context (table
+// directory), changes nothing: gpe_query_batches stages batch i+1 while the GPU works on batch i.
+struct FilterStage {
+    u32 n = 0, nb = 0, n_slots = 0, flags = 0;
+    std::vector<unsigned char> recs;
+    std::vector<u32> t0, slot_label;
+    std::vector<u64> prefix;
+};
+
+void stage_filter(const gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags, FilterStage &st) {
     const TableView &t = c->tv;
     const u32 L = t.L, D = t.D, n = qp.n();
     const bool prune = !(flags & GPE_FILTER_NO_PRUNE);
-    c->b_flags = flags;
-    c->b_slots = n_slots;
-    c->b_qpaths = n;
-    std::vector<u32> slot_label_host;
-
+    st.n = n;
+    st.n_slots = n_slots;
+    st.flags = flags;
     // group plan paths into blocks of <= kQB that read the same tiles
     std::vector<u32> order(n);
     std::iota(order.begin(), order.end(), 0u);
@@ -120,7 +128,8 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
     }
     const size_t rec_bytes = qblock_rec_bytes(L, t.E);
     std::vector<QBlockHost> blocks;
-    std::vector<unsigned char> recs;
+    st.recs.clear();
+    st.recs.reserve(((size_t)n / kQB + 64) * rec_bytes);
     std::vector<u32> ids(kQB), bl(kQB * kMaxL), bd(kQB * kMaxL), bs(kQB * kMaxL);
     std::vector<double> bp((size_t)kQB * kMaxL * kMaxE);
     for (u32 i = 0; i < n;) {
@@ -147,60 +156,66 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
             }
             for (u32 d = 0; d < D; d++) bp[(size_t)m * D + d] = qp.pde[(size_t)q * D + d];
         }
-        recs.resize(recs.size() + rec_bytes);
-        qblock_pack(L, t.E, recs.data() + recs.size() - rec_bytes, hb.n, hb.first_qpath, ids.data(), bl.data(),
+        st.recs.resize(st.recs.size() + rec_bytes);
+        qblock_pack(L, t.E, st.recs.data() + st.recs.size() - rec_bytes, hb.n, hb.first_qpath, ids.data(), bl.data(),
                     bd.data(), bs.data(), bp.data());
         blocks.push_back(hb);
         i = j;
     }
     const u32 nb = (u32)blocks.size();
-    c->b_qblocks = nb;
-    std::vector<u32> t0(nb + 1, 0);
-    std::vector<u64> prefix(nb + 1, 0);
+    st.nb = nb;
+    st.t0.assign(nb + 1, 0);
+    st.prefix.assign(nb + 1, 0);
     for (u32 b = 0; b < nb; b++) {
-        t0[b] = blocks[b].t0;
-        prefix[b + 1] = prefix[b] + (blocks[b].t1 - blocks[b].t0);
+        st.t0[b] = blocks[b].t0;
+        st.prefix[b + 1] = st.prefix[b] + (blocks[b].t1 - blocks[b].t0);
     }
-    c->b_items_unpruned = prefix[nb];
+    // label of every slot, from the plan paths that cover it (an uncovered slot stays empty)
+    st.slot_label.assign(std::max<u32>(n_slots, 1), 0xffffffffu);
+    for (u32 i = 0; i < n; i++)
+        for (u32 k = 0; k < L; k++) st.slot_label[qp.slots[(size_t)i * L + k]] = qp.labels[(size_t)i * L + k];
+}
+
+// The device half: buffers, the copies (through pinned memory, asynchronous), the batch state of the context.
+int commit_filter(gpe_ctx *c, const FilterStage &st) {
+    const u32 n = st.n, nb = st.nb, n_slots = st.n_slots;
+    c->b_flags = st.flags;
+    c->b_slots = n_slots;
+    c->b_qpaths = n;
+    c->b_qblocks = nb;
+    c->b_items_unpruned = st.prefix[nb];
     // candidate bitmaps are local to the slot's label class: bit i of slot s = the i-th vertex (by id) of label(s).
     // 20x smaller than one bit per data vertex at 20 labels, so they stay in L2 while the table streams through
     c->b_words = ((u64)(c->max_class + 31) / 32 + kChunkWords - 1) / kChunkWords * kChunkWords;
     if (c->b_words == 0) c->b_words = kChunkWords;
-    {   // label of every slot, from the plan paths that cover it (an uncovered slot stays empty)
-        std::vector<u32> slot_label(std::max<u32>(n_slots, 1), 0xffffffffu);
-        for (u32 i = 0; i < n; i++)
-            for (u32 k = 0; k < L; k++) slot_label[qp.slots[(size_t)i * L + k]] = qp.labels[(size_t)i * L + k];
-        GPE_CUDA(c, c->d_slot_label.reserve(slot_label.size() * sizeof(u32)));
-        slot_label_host.swap(slot_label);
-    }
     c->b_chunks_per_slot = c->b_words / kChunkWords;
-
-    GPE_CUDA(c, c->d_qblocks.reserve(std::max<size_t>(recs.size(), 16)));
+    GPE_CUDA(c, c->d_slot_label.reserve(st.slot_label.size() * sizeof(u32)));
+    GPE_CUDA(c, c->d_qblocks.reserve(std::max<size_t>(st.recs.size(), 16)));
     GPE_CUDA(c, c->d_qb_t0.reserve((nb + 1) * sizeof(u32)));
     GPE_CUDA(c, c->d_qb_prefix.reserve((nb + 1) * sizeof(u64)));
-    GPE_CUDA(c, c->d_worklist.reserve(std::max<u64>(prefix[nb], 1) * sizeof(u64)));
+    GPE_CUDA(c, c->d_worklist.reserve(std::max<u64>(st.prefix[nb], 1) * sizeof(u64)));
     GPE_CUDA(c, c->d_counters.reserve(8 * sizeof(u64)));
     GPE_CUDA(c, c->d_survivors.reserve(std::max<u32>(n, 1) * sizeof(u64)));
     GPE_CUDA(c, c->d_bitmap.reserve(std::max<u64>((u64)n_slots * c->b_words, 1) * sizeof(u32)));
     // stage through pinned memory so the copies are asynchronous
-    const size_t sl_bytes = slot_label_host.size() * sizeof(u32);
-    size_t o_rec = 0, o_t0 = (recs.size() + 15) / 16 * 16, o_pf = (o_t0 + (nb + 1) * sizeof(u32) + 15) / 16 * 16;
+    const size_t sl_bytes = st.slot_label.size() * sizeof(u32);
+    size_t o_rec = 0, o_t0 = (st.recs.size() + 15) / 16 * 16, o_pf = (o_t0 + (nb + 1) * sizeof(u32) + 15) / 16 * 16;
     const size_t o_sl = (o_pf + (nb + 1) * sizeof(u64) + 15) / 16 * 16;
     if (c->h_pin.cap < o_sl + sl_bytes) {  // (growing frees the old block: wait for copies still reading it)
         GPE_CUDA(c, cudaStreamSynchronize(c->stream));
         GPE_CUDA(c, c->h_pin.reserve(o_sl + sl_bytes));
     }
     unsigned char *pin = c->h_pin.as<unsigned char>();
-    memcpy(pin + o_sl, slot_label_host.data(), sl_bytes);
+    memcpy(pin + o_sl, st.slot_label.data(), sl_bytes);
     GPE_CUDA(c, cudaMemcpyAsync(c->d_slot_label.p, pin + o_sl, sl_bytes, cudaMemcpyHostToDevice, c->stream));
-    memcpy(pin + o_rec, recs.data(), recs.size());
-    memcpy(pin + o_t0, t0.data(), (nb + 1) * sizeof(u32));
-    memcpy(pin + o_pf, prefix.data(), (nb + 1) * sizeof(u64));
-    if (!recs.empty())
-        GPE_CUDA(c, cudaMemcpyAsync(c->d_qblocks.p, pin + o_rec, recs.size(), cudaMemcpyHostToDevice, c->stream));
+    memcpy(pin + o_rec, st.recs.data(), st.recs.size());
+    memcpy(pin + o_t0, st.t0.data(), (nb + 1) * sizeof(u32));
+    memcpy(pin + o_pf, st.prefix.data(), (nb + 1) * sizeof(u64));
+    if (!st.recs.empty())
+        GPE_CUDA(c, cudaMemcpyAsync(c->d_qblocks.p, pin + o_rec, st.recs.size(), cudaMemcpyHostToDevice, c->stream));
     GPE_CUDA(c, cudaMemcpyAsync(c->d_qb_t0.p, pin + o_t0, (nb + 1) * sizeof(u32), cudaMemcpyHostToDevice, c->stream));
     GPE_CUDA(c, cudaMemcpyAsync(c->d_qb_prefix.p, pin + o_pf, (nb + 1) * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-    c->stats.h2d_bytes += recs.size() + (nb + 1) * (sizeof(u32) + sizeof(u64)) + sl_bytes;
+    c->stats.h2d_bytes += st.recs.size() + (nb + 1) * (sizeof(u32) + sizeof(u64)) + sl_bytes;
     GPE_CUDA(c, cudaEventRecord(c->ev_upload, c->stream));  // the staging block may be overwritten once this has passed
     c->b_scanned = false;
     c->b_filtered = false;
@@ -208,8 +223,14 @@ int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
     c->stats.n_qpaths = n;
     c->stats.n_qblocks = nb;
     c->stats.n_slots = n_slots;
-    c->stats.scan_items_unpruned = prefix[nb];
+    c->stats.scan_items_unpruned = st.prefix[nb];
     return GPE_OK;
+}
+
+int setup_filter(gpe_ctx *c, const QPathSet &qp, u32 n_slots, u32 flags) {
+    FilterStage st;
+    stage_filter(c, qp, n_slots, flags, st);
+    return commit_filter(c, st);
 }
 
 // bitmap -> sorted candidate lists (d_cand, d_cand_off), entirely on the stream: NO host sync.  The total is only known on
@@ -1140,9 +1161,11 @@ struct gpe_plan {
     u32 L = 0, E = 0;
     std::vector<QueryPlan> plans;
     std::string err;
+    FilterStage stage;            // the batch staged for the scan of `staged_for` (stage_planned), or nothing
+    const gpe_ctx *staged_for = nullptr;
 };
 
-static int plan_batch(const gpe_batch *b, u32 L, u32 E, LabelTable &table, gpe_plan &out) {
+static int plan_batch(const gpe_batch *b, u32 L, u32 E, LabelTable &table, gpe_plan &out, int ranks_on_host = 1) {
     out.L = L;
     out.E = E;
     std::string why;
@@ -1163,7 +1186,9 @@ static int plan_batch(const gpe_batch *b, u32 L, u32 E, LabelTable &table, gpe_p
             query_plan(nq, b->q_offsets + vb + q, b->q_nbrs + b->q_ebase[q], b->q_labels + vb, L, E, out.plans[q], &table);
         }
     };
-    const u32 n_thr = b->n_queries >= 64 ? std::min<u32>(8, std::max<u32>(1, std::thread::hardware_concurrency() / 2)) : 1;
+    // (with one process per GPU every rank plans the whole batch: the ranks share the host's cores)
+    const u32 hw = std::max<u32>(1, std::thread::hardware_concurrency());
+    const u32 n_thr = b->n_queries >= 64 ? std::min<u32>(8, std::max<u32>(1, ranks_on_host > 1 ? hw / (u32)ranks_on_host : hw / 2)) : 1;
     if (n_thr <= 1) {
         plan_range(0, b->n_queries);
     } else {
@@ -1176,9 +1201,37 @@ static int plan_batch(const gpe_batch *b, u32 L, u32 E, LabelTable &table, gpe_p
     return GPE_OK;
 }
 
+// plans -> plan-path arrays -> staged filter, host only (the part of an upload that can run while the GPU is busy)
+static void stage_planned(const gpe_ctx *c, const gpe_batch *b, gpe_plan &pl, uint32_t flags) {
+    const u32 L = c->tv.L, D = c->tv.D;
+    QPathSet qp;
+    qp.L = L;
+    qp.D = D;
+    size_t total = 0;
+    for (const QueryPlan &plan : pl.plans) total += plan.n;
+    qp.slots.reserve(total * L * 2); qp.labels.reserve(total * L * 2); qp.degs.reserve(total * L * 2); qp.pde.reserve(total * D * 2);
+    for (u32 q = 0; q < b->n_queries; q++) {
+        const QueryPlan &plan = pl.plans[q];
+        const u32 vb = b->q_vbase[q];
+        for (u32 i = 0; i < plan.n * L; i++) qp.slots.push_back(vb + plan.vids[i]);
+        qp.labels.insert(qp.labels.end(), plan.labels.begin(), plan.labels.end());
+        qp.degs.insert(qp.degs.end(), plan.degs.begin(), plan.degs.end());
+        qp.pde.insert(qp.pde.end(), plan.pde.begin(), plan.pde.end());
+    }
+    if (flags & GPE_FILTER_BOTH_ORIENTATIONS) qp.add_reversed();
+    stage_filter(c, qp, b->q_vbase[b->n_queries], flags, pl.stage);
+    pl.staged_for = c;
+}
+
 static int upload_planned(gpe_ctx *c, const gpe_batch *b, const gpe_plan &pl, uint32_t flags) {
     const u32 L = c->tv.L, D = c->tv.D;
     if (pl.L != L || pl.E != c->tv.E || pl.plans.size() != b->n_queries) return c->fail(GPE_ERR_INVALID, "plan does not belong to this batch / table");
+    if (pl.staged_for == c && pl.stage.flags == flags) {  // staged ahead: only the copies are left
+        int rc = upload_queries(c, b->n_queries, b->q_vbase, b->q_ebase, b->q_offsets, b->q_nbrs, b->q_labels, b->limits);
+        if (rc) return rc;
+        c->b_pge = false;
+        return commit_filter(c, pl.stage);
+    }
     QPathSet qp;
     qp.L = L;
     qp.D = D;
@@ -1202,7 +1255,7 @@ int gpe_batch_upload(gpe_ctx *c, const gpe_batch *b, uint32_t flags) try {
     if (!c->have_table) return c->fail(GPE_ERR_INVALID, "gpe_build_table first");
     GPE_CUDA(c, cudaSetDevice(c->device));
     gpe_plan pl;
-    if (int rc = plan_batch(b, c->tv.L, c->tv.E, c->label_table, pl)) return c->fail(rc, "%s", pl.err.c_str());
+    if (int rc = plan_batch(b, c->tv.L, c->tv.E, c->label_table, pl, c->comm_world)) return c->fail(rc, "%s", pl.err.c_str());
     return upload_planned(c, b, pl, flags);
 } catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
     return c ? c->fail(GPE_ERR_INVALID, "%s: %s", "gpe_batch_upload", ex.what()) : GPE_ERR_INVALID;
@@ -1783,7 +1836,7 @@ int gpe_query_batches(gpe_ctx *c, uint32_t n_batches, const gpe_batch *batches, 
     GPE_CUDA(c, cudaSetDevice(c->device));
     gpe_plan cur, next;
     if (n_batches)
-        if (int rc = plan_batch(&batches[0], c->tv.L, c->tv.E, c->label_table, cur)) return c->fail(rc, "batch 0: %s", cur.err.c_str());
+        if (int rc = plan_batch(&batches[0], c->tv.L, c->tv.E, c->label_table, cur, c->comm_world)) return c->fail(rc, "batch 0: %s", cur.err.c_str());
     u64 h2d = 0, d2h = 0;
     double t_plan = 0, t_upload = 0, t_enqueue = 0, t_finish = 0;  // host wall clock per phase, summed over the batches
     for (uint32_t i = 0; i < n_batches; i++) {
@@ -1794,7 +1847,8 @@ int gpe_query_batches(gpe_ctx *c, uint32_t n_batches, const gpe_batch *batches, 
         double t2 = now_ms();
         if (i + 1 < n_batches) {
             next = gpe_plan();
-            if (int rc = plan_batch(&batches[i + 1], c->tv.L, c->tv.E, c->label_table, next)) return c->fail(rc, "batch %u: %s", i + 1, next.err.c_str());
+            if (int rc = plan_batch(&batches[i + 1], c->tv.L, c->tv.E, c->label_table, next, c->comm_world)) return c->fail(rc, "batch %u: %s", i + 1, next.err.c_str());
+            stage_planned(c, &batches[i + 1], next, flags);
         }
         double t3 = now_ms();
         if (int rc = gpe_batch_finish(c, answers[i])) return rc;
