@@ -44,10 +44,10 @@ WORKLOADS = {
                     desc="synthetic Poisson-degree 10M v / 100M e / 50 labels, p=8, l=2, e=2, 1000 mixed sparse/dense "
                          "random-walk queries of 4-16 vertices, n=MAX"),
     # BASELINE.json configs[3]: longer paths.  Poisson degrees (mean 20), 20 labels: ~1.8 x 10^10 four-vertex paths; 160-byte
-    # rows materialised would be 2.9 TB, so the table is held as vertex ids only (16 bytes per row: 290 GB, 36 GB per GPU
-    # at 8) and the scan gathers the rest (GPE_TABLE_IDS, chosen automatically).  Patched-oracle semantics for l=3
+    # rows materialised would be 3.2 TB, so the table is held as vertex ids only (16 bytes per row: 320 GB, 42 GB per GPU
+    # at 8, 80 at 4; 2 GPUs are not enough) and the scan gathers the rest (GPE_TABLE_IDS, chosen automatically).  Patched-oracle semantics for l=3
     "config4": dict(kind="uniform_native", V=5_000_000, E=50_000_000, labels=20, seed=2027,
-                    l=3, e=4, n_queries=100, q_vertices=12, q_seed=2028, p=8, min_gpus=2,
+                    l=3, e=4, n_queries=100, q_vertices=12, q_seed=2028, p=8, min_gpus=4,
                     desc="synthetic Poisson-degree 5M v / 50M e / 20 labels, p=8, l=3, e=4, 100 dense (induced) random-walk 12-vertex queries"),
     "config4_small": dict(kind="uniform_native", V=100_000, E=1_000_000, labels=20, seed=2027,
                           l=3, e=4, n_queries=50, q_vertices=12, q_seed=2028, p=8,
@@ -550,4 +550,14 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    try:
+        rc = main()
+    except BaseException:  # noqa: BLE001
+        # A rank that fails must not linger: its peers are (or will be) waiting inside a collective, and destructors that
+        # synchronise with the GPU would wait for them in turn.  Print, then leave without running any.
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)
+    sys.exit(rc)

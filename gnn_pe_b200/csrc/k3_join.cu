@@ -990,6 +990,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
     const int spr = (int)(flags >> 16 & 0xffu);        // DFS steps of a lane between two rounds of scheduling (kStepsPerRound)
     const u32 split = flags >> 24 & 0xfu;              // pieces an exported sibling range is cut into (kSplit)
     const int export_lanes = (int)(flags >> 28 & 0xfu);  // lanes of a warp that may hand work over in one round (kExportLanes)
+    const u32 backoff_max = 512u << (flags >> 2 & 3u);   // longest sleep of a warp without work between two looks at the queue (ns)
     extern __shared__ u64 s_stack64[];  // prod [M][THREADS] u64 | emb | cur | end | s0 | e0, each [M][THREADS] u32
     u64 *prod = s_stack64 + threadIdx.x;
     u32 *emb = reinterpret_cast<u32 *>(s_stack64 + M * THREADS) + threadIdx.x;
@@ -1149,7 +1150,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k3_dfs_kernel(JoinGraph g, cons
                 if (lane == 0) atomicAdd(&jq->idle, 1ull);
             }
             __nanosleep(backoff);
-            if (backoff < 4096) backoff <<= 1;
+            if (backoff < backoff_max) backoff <<= 1;
             w_polls++;
             continue;
         }
@@ -1645,7 +1646,9 @@ cudaError_t k3_dfs(const JoinGraph &g, u32 max_nq, const u32 *q_vbase, const Joi
     if (env_split < 0) { const char *e = getenv("GPE_JOIN_SPLIT"); env_split = e ? atoi(e) : (int)kSplit; if (env_split < 1 || env_split > 15) env_split = (int)kSplit; }
     static int env_xl = -1;
     if (env_xl < 0) { const char *e = getenv("GPE_JOIN_EXPORT_LANES"); env_xl = e ? atoi(e) : kExportLanes; if (env_xl < 1 || env_xl > 15) env_xl = kExportLanes; }
-    const u32 flags = (env_cg ? 2u : 0u) | ((u32)env_exp << 4) | ((u32)env_tb << 8) | ((u32)env_spr << 16) | ((u32)env_split << 24) |
+    static int env_bo = -1;  // 0..3: idle warps sleep at most 512 / 1024 / 2048 / 4096 ns between polls
+    if (env_bo < 0) { const char *e = getenv("GPE_JOIN_BACKOFF"); env_bo = e ? atoi(e) : 3; if (env_bo < 0 || env_bo > 3) env_bo = 3; }
+    const u32 flags = (env_cg ? 2u : 0u) | ((u32)env_bo << 2) | ((u32)env_exp << 4) | ((u32)env_tb << 8) | ((u32)env_spr << 16) | ((u32)env_split << 24) |
                       ((u32)env_xl << 28);
     // 8-vertex stacks, CTAs of 128 threads per SM (config 2, ms per batch): 5 (96 registers) 15.97, 6 (80 registers, 92 bytes of
     // spills) 15.61, 7 (72 registers) 19.9 -- beyond 6 the stacks leave too little of the SM's memory to L1, which holds the plans

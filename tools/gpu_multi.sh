@@ -12,7 +12,7 @@ if [ "$N" = "2" ]; then
   tail -5 gpurun_out/${TAG}_pytest_multigpu.log
 fi
 for WL in $WLS; do
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
+  timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
      bench.py --gpus $N --steps 10 --warmup 3 --workload $WL --no-cpu-baseline > gpurun_out/${TAG}_bench_${WL}_${N}gpu.json 2> gpurun_out/${TAG}_bench_${WL}_${N}gpu.err
   echo "bench $WL x$N rc=$?"
   python - <<PY
