@@ -17,6 +17,9 @@ ctx.set_embeddings(vde)
 ctx.enumerate(w["l"] + 1, graph_io.degree_order(g), graph_io.block_membership(g.V, w["p"]), w["p"])
 ctx.build_table()
 ctx.batch_upload(queries)
+ctx.batch_filter()
+ctx.batch_join()
+ctx.batch_download()  # settles the candidate buffer (sized before the first total is known): later steps are the steady state
 for _ in range(steps):
     ctx.batch_filter()
     ctx.batch_join()
