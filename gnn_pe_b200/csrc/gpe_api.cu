@@ -455,15 +455,17 @@ int run_join(gpe_ctx *c, u32 rank, u32 world, u32 *d_matches, u64 matches_cap, b
     // table pool: room for a table per slot and a sum table per slot at most, capped at 1 Gi entries (8 GB) and a quarter
     // of the free memory -- a query whose tables do not fit walks instead (k3_order reserves per query)
     u64 pool_cap = 2 * std::max<u64>((u64)n_slots * c->max_class, 1);
-    if (c->d_tpool.cap / sizeof(u64) < pool_cap) {
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        pool_cap = std::min<u64>(pool_cap, std::max<u64>(std::min<u64>(1ull << 30, (free_b + c->d_tpool.cap) / 4 / sizeof(u64)), c->d_tpool.cap / sizeof(u64)));
+    {
+        const u64 have = c->d_tpool.cap / sizeof(u64), hard_cap = 1ull << 30;
+        if (have < pool_cap && have < hard_cap) {  // batches are still getting bigger: grow, but never thrash -- the target
+            size_t free_b = 0, total_b = 0;        // depends on the free memory of the moment, so only a clear gain counts
+            cudaMemGetInfo(&free_b, &total_b);
+            const u64 target = std::min<u64>(pool_cap, std::min<u64>(hard_cap, (free_b + c->d_tpool.cap) / 4 / sizeof(u64)));
+            if (target > have + have / 4) GPE_CUDA(c, c->d_tpool.reserve(target * sizeof(u64)));
+        }
+        pool_cap = std::min<u64>(pool_cap, c->d_tpool.cap / sizeof(u64));
         if (const char *e = getenv("GPE_JOIN_POOL")) pool_cap = std::min<u64>(pool_cap, std::max<u64>(strtoull(e, nullptr, 10), 1));  // tests
-        GPE_CUDA(c, c->d_tpool.reserve(pool_cap * sizeof(u64)));
     }
-    pool_cap = std::min<u64>(pool_cap, c->d_tpool.cap / sizeof(u64));
-    if (const char *e = getenv("GPE_JOIN_POOL")) pool_cap = std::min<u64>(pool_cap, std::max<u64>(strtoull(e, nullptr, 10), 1));
     zl.add(c->d_tcursor.p, 4 * sizeof(u64));
     GPE_CUDA(c, c->d_tlist.reserve(((size_t)kMaxTreeLevels * 2 * std::max<u32>(n_slots, 1) + kMaxTreeLevels) * sizeof(u32)));
     bool allow_weighted = true;  // counted leaves may carry peeled subtrees
