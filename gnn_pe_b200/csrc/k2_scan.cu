@@ -79,14 +79,14 @@ __device__ __forceinline__ void bulk_load_nohint(void *dst, const void *src, u32
                  : "memory");
 }
 
-template <int L, int E, bool VIDS>
+template <int L, int E, bool VIDS, int NSREQ = kStages>
 struct ScanGeom {
     static constexpr int D = L * E;
     static constexpr int kTileBytes = kTileRows * (8 * L + 8 * D);
     static constexpr int kVidBytes = VIDS ? kTileRows * 4 * L : 0;  // the tile's vertex ids ride along when survivors are the rule
     static constexpr int kRecBytes = (int)sizeof(QBlockRec<L, E>);
     static constexpr int kStageBytes = ((kTileBytes + kVidBytes + kRecBytes + 127) / 128) * 128;
-    static constexpr int kNumStages = (kStages * kStageBytes <= 200 * 1024) ? kStages
+    static constexpr int kNumStages = (NSREQ * kStageBytes <= 200 * 1024) ? NSREQ
                                        : ((200 * 1024) / kStageBytes >= 2 ? (200 * 1024) / kStageBytes : 2);
     static constexpr int kSmemBytes = kNumStages * kStageBytes + 1024;  // ring + barriers/meta + alignment slack
 };
@@ -150,12 +150,12 @@ __global__ void __launch_bounds__(256) k2_select_kernel(TableView t, const QBloc
 // VIDS = false (streaming, every row against every plan path: survivors are rare): vertex ids are fetched from
 //               global memory by the few rows that need them.
 // Survivors set their bits with fire-and-forget reductions (RED.OR): nothing in the consumer loop waits on L2.
-template <int L, int E, bool VIDS>
+template <int L, int E, bool VIDS, int NSREQ = kStages>
 __global__ void __launch_bounds__(kTileRows + 32, 1)
 k2_scan_kernel(TableView t, const QBlockRec<L, E> *__restrict__ qblocks, const u64 *__restrict__ worklist,
                const u64 *__restrict__ counters, u32 *__restrict__ bitmap, u64 words_per_slot,
                u64 *__restrict__ survivors, int red_mode, u32 stage_words) {
-    using G = ScanGeom<L, E, VIDS>;
+    using G = ScanGeom<L, E, VIDS, NSREQ>;
     constexpr int D = G::D;
     constexpr int NS = G::kNumStages;
     // (no manual re-alignment through an integer cast: it would hide the shared address space from the compiler and
@@ -460,11 +460,17 @@ inline bool scan_stage_on() {
     return on != 0;
 }
 
-template <int L, int E, bool VIDS>
-cudaError_t launch_scan_v(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters,
-                          u32 *bitmap, u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s) {
-    using G = ScanGeom<L, E, VIDS>;
-    // Staging capacity: what two CTAs per SM leave next to the ring, in whole slots (at most one per (path, position)
+inline int scan_env(const char *name, int dflt, int lo, int hi) {
+    const char *e = getenv(name);
+    const int v = e ? atoi(e) : dflt;
+    return v < lo || v > hi ? dflt : v;
+}
+
+template <int L, int E, bool VIDS, int NSREQ>
+cudaError_t launch_scan_ns(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters,
+                           u32 *bitmap, u64 words_per_slot, u64 *survivors, int sm_count, int want_ctas, cudaStream_t s) {
+    using G = ScanGeom<L, E, VIDS, NSREQ>;
+    // Staging capacity: what `want_ctas` CTAs per SM leave next to the ring, in whole slots (at most one per (path, position)
     // of a block); when not even one slot fits (huge label classes) the kernel falls back to direct REDs.
     // (cached per device: cudaFuncSetAttribute and the occupancy are per-device properties, and one process may hold
     //  contexts on several GPUs)
@@ -480,27 +486,40 @@ cudaError_t launch_scan_v(const TableView &t, const void *qblocks, const u64 *wo
     if (ctas_per_sm == 0 || cfg_words != words_per_slot) {
         stage_words = 0;
         if (VIDS && words_per_slot > 0 && scan_stage_on()) {
-            const size_t budget = (size_t)(227 * 1024) / 2 - 1024;  // per CTA, two CTAs per SM (1 KB reserved each)
+            const size_t budget = (size_t)(227 * 1024) / want_ctas - 1024;  // per CTA (1 KB reserved each)
             if (budget > (size_t)G::kSmemBytes) {
                 const u64 slots = std::min<u64>((budget - G::kSmemBytes) / 4 / words_per_slot, (u64)kQB * L);
                 stage_words = (u32)(slots * words_per_slot);
             }
         }
         smem_bytes = (size_t)G::kSmemBytes + (size_t)stage_words * 4;
-        cudaError_t e = cudaFuncSetAttribute(k2_scan_kernel<L, E, VIDS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k2_scan_kernel<L, E, VIDS, NSREQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem_bytes);
         if (e != cudaSuccess) return e;
         int n = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k2_scan_kernel<L, E, VIDS>, kTileRows + 32, smem_bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k2_scan_kernel<L, E, VIDS, NSREQ>, kTileRows + 32, smem_bytes);
         if (e != cudaSuccess) return e;
         ctas_per_sm = n < 1 ? 1 : n;
         cfg_words = words_per_slot;
     }
     unsigned blocks = (unsigned)(sm_count * ctas_per_sm);
-    k2_scan_kernel<L, E, VIDS><<<blocks, kTileRows + 32, smem_bytes, s>>>(
+    k2_scan_kernel<L, E, VIDS, NSREQ><<<blocks, kTileRows + 32, smem_bytes, s>>>(
         t, reinterpret_cast<const QBlockRec<L, E> *>(qblocks), worklist, counters, bitmap, words_per_slot, survivors,
         scan_red_mode(), stage_words);
     return cudaGetLastError();
+}
+
+template <int L, int E, bool VIDS>
+cudaError_t launch_scan_v(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters,
+                          u32 *bitmap, u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s) {
+    // measurement switches (the headline geometry only): ring depth and CTAs per SM the staging budget is sized for
+    if constexpr (L == 3 && E == 2 && VIDS) {
+        static const int ns = scan_env("GPE_SCAN_STAGES", kStages, 2, 4), ctas = scan_env("GPE_SCAN_CTAS", 2, 1, 4);
+        if (ns == 2) return launch_scan_ns<L, E, VIDS, 2>(t, qblocks, worklist, counters, bitmap, words_per_slot, survivors, sm_count, ctas, s);
+        if (ns == 3) return launch_scan_ns<L, E, VIDS, 3>(t, qblocks, worklist, counters, bitmap, words_per_slot, survivors, sm_count, ctas, s);
+        return launch_scan_ns<L, E, VIDS, kStages>(t, qblocks, worklist, counters, bitmap, words_per_slot, survivors, sm_count, ctas, s);
+    }
+    return launch_scan_ns<L, E, VIDS, kStages>(t, qblocks, worklist, counters, bitmap, words_per_slot, survivors, sm_count, 2, s);
 }
 
 template <int L, int E>
