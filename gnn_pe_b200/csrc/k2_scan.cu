@@ -512,11 +512,16 @@ cudaError_t launch_scan_ns(const TableView &t, const void *qblocks, const u64 *w
 template <int L, int E, bool VIDS>
 cudaError_t launch_scan_v(const TableView &t, const void *qblocks, const u64 *worklist, const u64 *counters,
                           u32 *bitmap, u64 words_per_slot, u64 *survivors, int sm_count, cudaStream_t s) {
-    // measurement switches (the headline geometry only): ring depth and CTAs per SM the staging budget is sized for
-    if constexpr (L == 3 && E == 2 && VIDS) {
-        static const int ns = scan_env("GPE_SCAN_STAGES", kStages, 2, 4), ctas = scan_env("GPE_SCAN_CTAS", 2, 1, 4);
+    // Bucketed work lists (VIDS): a 2-deep ring and as many CTAs per SM as fit (3 at l=2, e=2) instead of a 4-deep ring and
+    // 2 CTAs -- the consumers' FP64 compare chains were latency bound at 27 % occupancy: in-step scan 0.670 -> 0.558 ms on
+    // config 2 = 0.61 -> 0.73 of the HBM peak (gpurun_out/r02y_ab*: 3 stages x 2 CTAs 0.674, 2 x 2 0.696).  The streaming mode
+    // (every row against every plan path, 0.97 of the peak) keeps the deep ring.  GPE_SCAN_STAGES / GPE_SCAN_CTAS override.
+    if constexpr (VIDS) {
+        using G2 = ScanGeom<L, E, VIDS, 2>;
+        static const int ns = scan_env("GPE_SCAN_STAGES", 2, 2, 4);
+        static const int fit = (int)std::max<size_t>(1, std::min<size_t>(3, (size_t)(227 * 1024) / ((size_t)G2::kSmemBytes + 4096)));
+        static const int ctas = scan_env("GPE_SCAN_CTAS", ns == 2 ? fit : 2, 1, 4);
         if (ns == 2) return launch_scan_ns<L, E, VIDS, 2>(t, qblocks, worklist, counters, bitmap, words_per_slot, survivors, sm_count, ctas, s);
-        if (ns == 3) return launch_scan_ns<L, E, VIDS, 3>(t, qblocks, worklist, counters, bitmap, words_per_slot, survivors, sm_count, ctas, s);
         return launch_scan_ns<L, E, VIDS, kStages>(t, qblocks, worklist, counters, bitmap, words_per_slot, survivors, sm_count, ctas, s);
     }
     return launch_scan_ns<L, E, VIDS, kStages>(t, qblocks, worklist, counters, bitmap, words_per_slot, survivors, sm_count, 2, s);
