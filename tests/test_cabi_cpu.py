@@ -98,3 +98,20 @@ def test_host_pge_groups_against_reference_golden(lib, name):
     pg, plg, has = gpe.host_pge_groups(off, nbr, lab, pge["pl"], pge["e"])
     assert hashlib.md5(pg.tobytes()).hexdigest() == pge["pg_md5"]
     assert hashlib.md5(plg.tobytes()).hexdigest() == pge["plg_md5"]
+
+
+def test_host_mirror_accepts_any_32_bit_label():
+    """gen_vde_x only seeds a generator with the label (custom.h:492-511), so any 32-bit label is legal: the host mirror
+    must not size a table by the largest label id (an allocation of tens of GB, or std::bad_alloc through the C ABI)."""
+    import numpy as np
+    from gnn_pe_b200 import gpe
+    from oracle import oracle
+    off = np.array([0, 1, 3, 4], dtype=np.uint32)
+    nbr = np.array([1, 0, 2, 1], dtype=np.uint32)
+    lab = np.array([0x80000000, 7, 0xFFFFFFF0], dtype=np.uint32)
+    x, vde = gpe.host_gen_vde(off, nbr, lab, 3)
+    for v in range(3):
+        assert x[v].tobytes() == oracle.label_embedding(int(lab[v]), 3).tobytes()
+    assert vde[1].tobytes() == (x[1] + (x[0] + x[2])).tobytes()
+    plan = gpe.host_query_plan(off, nbr, lab, 3, 3)
+    assert len(plan["vids"]) >= 1 and set(plan["labels"].ravel().tolist()) <= set(lab.tolist())
