@@ -29,7 +29,9 @@ def build(force: bool = False) -> str:
     csrc = os.path.join(_HERE, "csrc")
     srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cpp", ".h"))]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "gpe.h"))
-    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    synth = os.path.join(_HERE, "libgpe_synth.so")  # the seeded generator of the large synthetic graphs (same Makefile)
+    stale = (not os.path.exists(LIB_PATH)) or (not os.path.exists(synth)) or \
+        any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
         if not os.path.exists("/usr/local/cuda/bin/nvcc") and os.path.exists(LIB_PATH) and not force:
             return LIB_PATH
