@@ -619,6 +619,7 @@ u32 orc_query_plan(void *qv, u32 L, u32 e, int literal, u32 cap, u32 *vids, u32 
 }
 
 // Brute-force filter of the handle's enumerated table (all rows) for query `qv`.
+// literal_plan: bit 0 = the literal dfs enumeration of the query paths, bit 1 = both orientations (exact mode).
 // cand_off: nq+1 offsets into cand (sorted ascending per query vertex); returns total size
 // (call with cand == NULL first to size the buffer).  survivors: per plan path, may be NULL.
 u64 orc_filter(void *gv, void *qv, u32 e, int literal_plan, u64 *cand_off, u32 *cand, u64 cand_cap,
@@ -627,12 +628,32 @@ u64 orc_filter(void *gv, void *qv, u32 e, int literal_plan, u64 *cand_off, u32 *
     OGraph &q = ((Handle *)qv)->g;
     u32 L = h->L;
     std::vector<QPath> plan;
-    query_plan(q, L, e, literal_plan != 0, plan, nullptr);
+    query_plan(q, L, e, (literal_plan & 1) != 0, plan, nullptr);
+    const size_t n_plan = plan.size();
+    if (literal_plan & 2) {
+        // Exact mode (not the reference's behaviour): the reference stores one orientation of every data
+        // path (custom.h:68-79) and compares plan paths with that one only (:407-435).  Comparing the reversed plan path
+        // with the stored row is comparing the plan path with the row's other orientation.
+        for (size_t j = 0; j < n_plan; j++) {
+            QPath r = plan[j];
+            std::reverse(r.vids.begin(), r.vids.end());
+            std::reverse(r.labels.begin(), r.labels.end());
+            std::reverse(r.degrees.begin(), r.degrees.end());
+            for (u32 k = 0; k < L; k++)
+                for (u32 d = 0; d < e; d++) r.pde[k * e + d] = plan[j].pde[(L - 1 - k) * e + d];
+            plan.push_back(r);
+        }
+    }
     std::vector<double> x((size_t)h->g.V * e), vde((size_t)h->g.V * e);
     vertex_embeddings(h->g, e, x.data(), vde.data());
     std::vector<std::set<u32>> cs(q.V);
     std::vector<u64> surv(plan.size(), 0);
     filter_rows(h->g, vde.data(), e, L, plan, h->rows.data(), h->rows.size() / L, cs, surv.data());
+    if (literal_plan & 2) {  // survivors of both orientations count for the plan path
+        for (size_t j = 0; j < n_plan; j++) surv[j] += surv[n_plan + j];
+        surv.resize(n_plan);
+        plan.resize(n_plan);
+    }
     u64 total = 0;
     for (u32 u = 0; u < q.V; u++) {
         cand_off[u] = total;

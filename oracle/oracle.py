@@ -169,14 +169,17 @@ def query_plan(q: OracleGraph, L: int, e: int, literal: bool = False):
                 n_query_paths=int(nqp.value))
 
 
-def filter_candidates(g: OracleGraph, q: OracleGraph, e: int, literal_plan: bool = False):
+def filter_candidates(g: OracleGraph, q: OracleGraph, e: int, literal_plan: bool = False,
+                      both_orientations: bool = False):
     """Brute-force dominance filter over g's enumerated table.  Returns (list of sorted
-    candidate arrays per query vertex, survivors per plan path)."""
+    candidate arrays per query vertex, survivors per plan path).  both_orientations: the exact mode of
+    SURVEY.md 8f-4 (every plan path against both orientations of every stored row) -- not the reference's rule."""
+    mode = int(bool(literal_plan)) | (2 if both_orientations else 0)
     off = np.zeros(q.V + 1, dtype=np.uint64)
-    total = int(lib().orc_filter(g._h, q._h, e, int(literal_plan), off, None, 0, None, 0))
+    total = int(lib().orc_filter(g._h, q._h, e, mode, off, None, 0, None, 0))
     cand = np.zeros(max(total, 1), dtype=np.uint32)
     surv = np.zeros(4096, dtype=np.uint64)
-    lib().orc_filter(g._h, q._h, e, int(literal_plan), off, cand.ctypes.data_as(C.c_void_p), total,
+    lib().orc_filter(g._h, q._h, e, mode, off, cand.ctypes.data_as(C.c_void_p), total,
                      surv.ctypes.data_as(C.c_void_p), len(surv))
     n_plan = len(query_plan(q, g.L, e, literal_plan)["weight"])
     sets = [cand[int(off[u]): int(off[u + 1])].copy() for u in range(q.V)]

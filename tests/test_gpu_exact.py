@@ -49,3 +49,26 @@ def test_random_queries_true_count(seed, nl):
         assert eng.ctx.query_batch(queries, flags=gpe.FILTER_BOTH_ORIENTATIONS | gpe.FILTER_NO_PRUNE).tolist() == exact
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("seed,nl,l,e", [(6, 4, 2, 2), (7, 3, 3, 2)])
+def test_exact_candidate_sets_match_oracle(seed, nl, l, e):
+    """gpe_filter with the flag: candidate lists and survivors equal to the oracle's exact mode (itself pinned against
+    the filter-free count in tests/test_exact_oracle_cpu.py), bucketed and streaming scans."""
+    from oracle import oracle
+    g = synth.chung_lu_graph(600, 2600, nl, gamma=2.6, degree_cap=40, seed=seed)
+    eng = engine.Engine(0)
+    try:
+        eng.offline(g, l=l, e=e, p=3)
+        og = oracle.OracleGraph.from_csr(g.offsets, g.nbrs, g.labels)
+        og.enumerate(l + 1, graph_io.degree_order(g))
+        for q in synth.query_batch(g, 6, (4, 8), seed=seed + 30, mixed=True):
+            oq = oracle.OracleGraph.from_csr(q.offsets, q.nbrs, q.labels)
+            sets, surv = oracle.filter_candidates(og, oq, e, both_orientations=True)
+            plan = gpe.host_query_plan(q.offsets, q.nbrs, q.labels, l + 1, e)
+            for flags in (gpe.FILTER_BOTH_ORIENTATIONS, gpe.FILTER_BOTH_ORIENTATIONS | gpe.FILTER_NO_PRUNE):
+                gsets, gsurv = eng.ctx.filter(plan, q.V, flags)
+                assert [s.tolist() for s in gsets] == [s.tolist() for s in sets]
+                assert gsurv.tolist() == surv.tolist()
+    finally:
+        eng.close()
