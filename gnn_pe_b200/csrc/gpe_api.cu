@@ -626,6 +626,7 @@ void gpe_destroy(gpe_ctx *c) {
     if (c->comm) nccl_api().CommDestroy((ncclComm_t)c->comm);
     c->d_all_bitmaps.release();
     c->d_reduce.release();
+    c->d_sparse.release();
     DevBuf *bufs[] = {&c->d_off, &c->d_nbr, &c->d_label, &c->d_deg, &c->d_nbrJ, &c->d_gtab, &c->d_offJ, &c->d_degJ, &c->d_labelJ, &c->d_newid, &c->d_nbrG, &c->d_lclass, &c->d_lpos, &c->d_lcoff, &c->d_bloom, &c->d_tjobs, &c->d_tchild, &c->d_tpool, &c->d_tcursor, &c->d_tlist, &c->d_qcur, &c->d_items, &c->d_ready, &c->d_jq, &c->d_init, &c->d_kids, &c->d_rank, &c->d_sorted, &c->d_member, &c->d_vde, &c->d_vrec, &c->d_ranklab,
                       &c->d_offr, &c->d_ebase, &c->d_start_rows, &c->d_scan_tmp, &c->d_tiles, &c->d_vids, &c->d_sum_u32, &c->d_sum_f64,
                       &c->d_bucket, &c->d_cursor, &c->d_qblocks, &c->d_qb_t0, &c->d_qb_prefix, &c->d_worklist,
@@ -637,6 +638,7 @@ void gpe_destroy(gpe_ctx *c) {
     c->h_pin.release();
     c->h_pin2.release();
     c->h_pin3.release();
+    c->h_pin4.release();
     c->h_pin_q.release();
     if (c->ev_upload) cudaEventDestroy(c->ev_upload);
     for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
