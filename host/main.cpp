@@ -20,6 +20,9 @@
 //   * -g N (--gpus N) shards the online stage over N GPUs of this machine, one process: GPU r holds the path table of
 //     the partitions i % N == r (needs -p >= N), the candidate sets are exchanged with NCCL inside libgpe and the join
 //     is split by start candidate (gpe_comm_init_all / gpe_multi_query_batch).  Answers are those of -g 1;
+//   * --filter pge (-F pge) runs the sibling variant GNN-PGE instead (GNN-PGE/src/main.cpp:38-363: same flags, -l is
+//     the number of VERTICES per path there, files under gnn-pge/): offline writes gnn-pge/data_vertices.bin byte for
+//     byte as the reference does (:179-194), online prints its `Answer Num:` line (:361).  One GPU;
 //   * -q may name a DIRECTORY: every *.graph file in it (sorted by name) is answered in one batch -- one
 //     `<file>: Answer Number: N` line per query, then the batch's total time and queries/s (BASELINE.json config 5).
 #include <algorithm>
@@ -44,7 +47,7 @@ namespace {
 
 struct Options {
     std::string file = "../Test/", data = "../Test/data_graph.graph", query = "../Test/query_graph.graph";
-    std::string mode = "offline", answers = "MAX";
+    std::string mode = "offline", answers = "MAX", filter = "pe";
     uint32_t partitions = 5, length = 2, embedding = 2, gpus = 1;
 };
 
@@ -52,7 +55,7 @@ bool parse(int argc, char **argv, Options &o) {
     struct Opt { const char *s, *l; int id; };
     static const Opt opts[] = {{"-f", "--file", 0}, {"-d", "--data", 1}, {"-q", "--query", 2}, {"-m", "--mode", 3},
                                {"-p", "--partition", 4}, {"-l", "--length", 5}, {"-e", "--embedding", 6},
-                               {"-n", "--answers", 7}, {"-g", "--gpus", 8}};
+                               {"-n", "--answers", 7}, {"-g", "--gpus", 8}, {"-F", "--filter", 9}};
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i], val;
         int id = -1;
@@ -63,7 +66,7 @@ bool parse(int argc, char **argv, Options &o) {
             if (a.rfind(s, 0) == 0 && a.size() > 2 && a[1] != '-') { id = op.id; val = a.substr(a[2] == '=' ? 3 : 2); break; }
         }
         if (a == "-h" || a == "--help") {
-            std::puts("usage: main [-f dir/] [-d data.graph] [-q query.graph] [-m offline|online] [-p N] [-l N] [-e N] [-n MAX|N] [-g GPUS]");
+            std::puts("usage: main [-f dir/] [-d data.graph] [-q query.graph] [-m offline|online] [-p N] [-l N] [-e N] [-n MAX|N] [-g GPUS] [-F pe|pge]");
             std::exit(0);
         }
         if (id < 0) { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return false; }
@@ -77,6 +80,7 @@ bool parse(int argc, char **argv, Options &o) {
             case 6: o.embedding = (uint32_t)std::stoul(val); break;
             case 7: o.answers = val; break;
             case 8: o.gpus = (uint32_t)std::stoul(val); break;
+            case 9: o.filter = val; break;
         }
     }
     return true;
@@ -171,6 +175,46 @@ int check_manifest(const std::string &path, const Manifest &now, const std::vect
     return 0;
 }
 
+// A directory of query graphs as one batch (every *.graph file, sorted by name).
+struct QueryDir {
+    std::vector<std::string> files;
+    std::vector<uint32_t> vbase{0}, ebase{0}, offs, nbrs, labs;
+    std::vector<uint64_t> limits;
+    gpe_batch batch{};
+};
+
+// 0 = loaded, 1 = no query files, -1 = a file could not be read (message printed)
+int load_query_dir(const std::string &path, uint64_t limit, QueryDir &qd) {
+    if (DIR *dir = opendir(path.c_str())) {
+        while (dirent *e = readdir(dir)) {
+            std::string n = e->d_name;
+            if (n.size() > 6 && n.compare(n.size() - 6, 6, ".graph") == 0) qd.files.push_back(n);
+        }
+        closedir(dir);
+    }
+    std::sort(qd.files.begin(), qd.files.end());
+    if (qd.files.empty()) { std::fprintf(stderr, "no *.graph files in %s\n", path.c_str()); return 1; }
+    for (const std::string &n : qd.files) {
+        Graph Qi;
+        if (!load(path + "/" + n, Qi)) return -1;
+        qd.offs.insert(qd.offs.end(), Qi.off.begin(), Qi.off.end());
+        qd.nbrs.insert(qd.nbrs.end(), Qi.nbr.begin(), Qi.nbr.begin() + Qi.off[Qi.V]);
+        qd.labs.insert(qd.labs.end(), Qi.lab.begin(), Qi.lab.begin() + Qi.V);
+        qd.vbase.push_back(qd.vbase.back() + Qi.V);
+        qd.ebase.push_back(qd.ebase.back() + Qi.off[Qi.V]);
+    }
+    qd.nbrs.push_back(0);
+    qd.limits.assign(qd.files.size(), limit);
+    qd.batch = gpe_batch{(uint32_t)qd.files.size(), qd.vbase.data(), qd.ebase.data(), qd.offs.data(), qd.nbrs.data(),
+                         qd.labs.data(), qd.limits.data()};
+    return 0;
+}
+
+bool is_dir(const std::string &path) {
+    struct stat st{};
+    return stat(path.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+
 #define CK(ctx, call)                                                                  \
     do {                                                                               \
         if ((call) != GPE_OK) {                                                        \
@@ -178,6 +222,74 @@ int check_manifest(const std::string &path, const Manifest &now, const std::vect
             return 1;                                                                  \
         }                                                                              \
     } while (0)
+
+// ---- GNN-PGE (GNN-PGE/src/main.cpp:38-363) ------------------------------------------------------------------------
+// The reference also reads gnn-pge/membership.txt (:77-88), but only to deal the vertices to its per-partition R*-trees;
+// there is one row per data vertex here and one scan over all of them, so the file is not needed.
+int run_pge(const Options &o, uint64_t limit) {
+    if (o.gpus > 1) { std::fprintf(stderr, "--filter pge runs on one GPU (one row per data vertex: nothing to shard)\n"); return 1; }
+    const uint32_t pl = o.length, e = o.embedding;  // GNN-PGE's -l counts vertices (custom.h:47, main.cpp:58)
+    Graph G;
+    if (!load(o.data, G)) return -1;
+    gpe_ctx *ctx = nullptr;
+    if (gpe_create(0, &ctx) != GPE_OK) { std::fprintf(stderr, "libgpe: %s\n", gpe_last_error(nullptr)); return 1; }
+    std::vector<double> x((size_t)G.V * e), vde((size_t)G.V * e);
+    CK(ctx, gpe_host_gen_vde(G.V, G.off.data(), G.nbr.data(), G.lab.data(), e, x.data(), vde.data()));
+    CK(ctx, gpe_set_graph(ctx, G.V, G.off.data(), G.nbr.data(), G.lab.data()));
+    CK(ctx, gpe_set_embeddings(ctx, e, vde.data()));
+    CK(ctx, gpe_pge_build(ctx, pl, x.data()));  // main.cpp:91-176 for every data vertex
+
+    if (o.mode == "offline") {  // gnn-pge/data_vertices.bin, main.cpp:179-194
+        const size_t W = (size_t)2 * pl * e;
+        std::vector<double> pg((size_t)G.V * W), plg((size_t)G.V * W), nx(e);
+        std::vector<uint8_t> has(std::max<size_t>(G.V, 1));
+        CK(ctx, gpe_pge_dump_groups(ctx, pg.data(), plg.data(), has.data()));
+        const std::string name = o.file + "gnn-pge/data_vertices.bin";
+        FILE *f = std::fopen(name.c_str(), "wb");
+        if (!f) { std::fprintf(stderr, "cannot write %s\n", name.c_str()); return 1; }
+        bool ok = std::fwrite(&G.V, 4, 1, f) == 1;
+        for (uint32_t v = 0; v < G.V && ok; v++) {
+            const uint32_t head[3] = {v, G.lab[v], G.off[v + 1] - G.off[v]};
+            const double key = 0;  // never set for data vertices: the value-initialised field (custom.h:73-88)
+            std::fill(nx.begin(), nx.end(), 0.0);  // the neighbours' label embeddings, custom.h:460-471
+            for (uint32_t j = G.off[v]; j < G.off[v + 1]; j++)
+                for (uint32_t k = 0; k < e; k++) nx[k] += x[(size_t)G.nbr[j] * e + k];
+            ok = std::fwrite(head, 4, 3, f) == 3 && std::fwrite(&key, 8, 1, f) == 1 &&
+                 std::fwrite(&x[(size_t)v * e], 8, e, f) == e && std::fwrite(nx.data(), 8, e, f) == e &&
+                 std::fwrite(&vde[(size_t)v * e], 8, e, f) == e && std::fwrite(&pg[v * W], 8, W, f) == W &&
+                 std::fwrite(&plg[v * W], 8, W, f) == W;
+        }
+        if (std::fclose(f) != 0 || !ok) { std::fprintf(stderr, "cannot write %s\n", name.c_str()); return 1; }
+    }
+
+    if (o.mode == "online") {
+        if (is_dir(o.query)) {
+            QueryDir qd;
+            if (int rc = load_query_dir(o.query, limit, qd)) return rc;
+            std::vector<uint64_t> answers(qd.files.size(), 0);
+            auto t0 = std::chrono::high_resolution_clock::now();
+            CK(ctx, gpe_pge_query_batch(ctx, &qd.batch, answers.data()));
+            auto t1 = std::chrono::high_resolution_clock::now();
+            double ms = std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count() / 1e6;
+            for (size_t i = 0; i < qd.files.size(); i++)
+                std::cout << qd.files[i] << ": Answer Num: " << (uint32_t)answers[i] << std::endl;
+            std::cout << "Queries: " << qd.files.size() << " Query Time (ms): " << ms << " Queries/s: " << qd.files.size() / (ms / 1e3) << std::endl;
+        } else {
+            Graph Q;
+            if (!load(o.query, Q)) return -1;
+            uint32_t vbase[2] = {0, Q.V}, ebase[2] = {0, Q.off[Q.V]};
+            gpe_batch batch{1, vbase, ebase, Q.off.data(), Q.nbr.data(), Q.lab.data(), &limit};
+            uint64_t answer = 0;
+            auto t0 = std::chrono::high_resolution_clock::now();  // query groups + filter + refinement, main.cpp:251-361
+            CK(ctx, gpe_pge_query_batch(ctx, &batch, &answer));
+            auto t1 = std::chrono::high_resolution_clock::now();
+            double ms = std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count() / 1e6;
+            std::cout << "Answer Num: " << (uint32_t)answer << " Query Time (ms): " << ms << std::endl;  // main.cpp:361
+        }
+    }
+    gpe_destroy(ctx);
+    return 0;
+}
 
 }  // namespace
 
@@ -187,6 +299,8 @@ int main(int argc, char **argv) {
     const uint32_t L = o.length + 1;  // main.cpp:58
     uint64_t limit = GPE_LIMIT_MAX;   // main.cpp:62-69
     if (o.answers != "MAX") limit = (uint64_t)(uint32_t)std::stoi(o.answers);
+    if (o.filter == "pge") return run_pge(o, limit);
+    if (o.filter != "pe") { std::fprintf(stderr, "--filter is pe or pge\n"); return 2; }
     const std::string partitions_path = o.file + "gnn-pe/partitions/";
 
     Graph G;
@@ -295,38 +409,17 @@ int main(int argc, char **argv) {
         };
         auto destroy_all = [&] { for (gpe_ctx *cd : ctxs) gpe_destroy(cd); };
 
-        struct stat st_q{};
-        if (stat(o.query.c_str(), &st_q) == 0 && S_ISDIR(st_q.st_mode)) {  // a directory of queries: one batch
-            std::vector<std::string> files;
-            if (DIR *dir = opendir(o.query.c_str())) {
-                while (dirent *e = readdir(dir)) {
-                    std::string n = e->d_name;
-                    if (n.size() > 6 && n.compare(n.size() - 6, 6, ".graph") == 0) files.push_back(n);
-                }
-                closedir(dir);
-            }
-            std::sort(files.begin(), files.end());
-            if (files.empty()) { std::fprintf(stderr, "no *.graph files in %s\n", o.query.c_str()); return 1; }
-            std::vector<uint32_t> vbase(1, 0), ebase(1, 0), offs, nbrs, labs;
-            for (const std::string &n : files) {
-                Graph Qi;
-                if (!load(o.query + "/" + n, Qi)) return -1;
-                offs.insert(offs.end(), Qi.off.begin(), Qi.off.end());
-                nbrs.insert(nbrs.end(), Qi.nbr.begin(), Qi.nbr.begin() + Qi.off[Qi.V]);
-                labs.insert(labs.end(), Qi.lab.begin(), Qi.lab.begin() + Qi.V);
-                vbase.push_back(vbase.back() + Qi.V);
-                ebase.push_back(ebase.back() + Qi.off[Qi.V]);
-            }
-            nbrs.push_back(0);
-            std::vector<uint64_t> limits(files.size(), limit), answers(files.size(), 0);
-            gpe_batch batch{(uint32_t)files.size(), vbase.data(), ebase.data(), offs.data(), nbrs.data(), labs.data(), limits.data()};
+        if (is_dir(o.query)) {  // a directory of queries: one batch
+            QueryDir qd;
+            if (int rc = load_query_dir(o.query, limit, qd)) return rc;
+            std::vector<uint64_t> answers(qd.files.size(), 0);
             auto t0 = std::chrono::high_resolution_clock::now();
-            if (report(run_batch(&batch, answers.data()))) return 1;
+            if (report(run_batch(&qd.batch, answers.data()))) return 1;
             auto t1 = std::chrono::high_resolution_clock::now();
             double ms = std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count() / 1e6;
-            for (size_t i = 0; i < files.size(); i++)
-                std::cout << files[i] << ": Answer Number: " << (uint32_t)answers[i] << std::endl;
-            std::cout << "Queries: " << files.size() << " Query Time (ms): " << ms << " Queries/s: " << files.size() / (ms / 1e3) << std::endl;
+            for (size_t i = 0; i < qd.files.size(); i++)
+                std::cout << qd.files[i] << ": Answer Number: " << (uint32_t)answers[i] << std::endl;
+            std::cout << "Queries: " << qd.files.size() << " Query Time (ms): " << ms << " Queries/s: " << qd.files.size() / (ms / 1e3) << std::endl;
             destroy_all();
             return 0;
         }
