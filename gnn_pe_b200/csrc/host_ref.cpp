@@ -30,6 +30,14 @@ int load_graph_file(const char *path, HostGraph &g, std::string &err) {
     char tag;
     uint32_t V = 0, E = 0;
     in >> tag >> V >> E;
+    if (!in || tag != 't') { err = std::string(path) + " does not start with a 't V E' line"; return GPE_ERR_INVALID; }
+    {   // a 'v' line takes at least 7 bytes and an 'e' line 5: refuse a header the file cannot back before allocating for it
+        const std::streampos here = in.tellg();
+        in.seekg(0, std::ios::end);
+        const uint64_t bytes = (uint64_t)in.tellg();
+        in.seekg(here);
+        if ((uint64_t)V * 7 + (uint64_t)E * 5 > bytes) { err = "the header promises more vertices and edges than the file holds"; return GPE_ERR_INVALID; }
+    }
     g.offsets.assign((size_t)V + 1, 0);
     g.nbrs.assign((size_t)E * 2, 0);
     g.labels.assign(V, 0);
@@ -37,13 +45,13 @@ int load_graph_file(const char *path, HostGraph &g, std::string &err) {
     while (in >> tag) {
         if (tag == 'v') {
             uint32_t id, label, degree;
-            in >> id >> label >> degree;
+            if (!(in >> id >> label >> degree)) { err = "truncated 'v' line"; return GPE_ERR_INVALID; }
             if (id >= V) { err = "vertex id out of range"; return GPE_ERR_INVALID; }
             g.labels[id] = label;
             g.offsets[id + 1] = g.offsets[id] + degree;
         } else if (tag == 'e') {
             uint32_t u, v;
-            in >> u >> v;
+            if (!(in >> u >> v)) { err = "truncated 'e' line"; return GPE_ERR_INVALID; }
             if (u >= V || v >= V) { err = "edge endpoint out of range"; return GPE_ERR_INVALID; }
             size_t pu = (size_t)g.offsets[u] + used[u], pv = (size_t)g.offsets[v] + used[v];
             if (pu >= g.nbrs.size() || pv >= g.nbrs.size() || used[u] >= g.offsets[u + 1] - g.offsets[u] ||
@@ -57,6 +65,14 @@ int load_graph_file(const char *path, HostGraph &g, std::string &err) {
             used[v]++;
         }
     }
+    // The reference trusts the header and the declared degrees (graph.cpp:176-229) and reads or writes out of bounds when
+    // they disagree with the edge list; here that is an error.
+    for (uint32_t v = 0; v < V; v++)
+        if (g.offsets[v + 1] < g.offsets[v] || used[v] != g.offsets[v + 1] - g.offsets[v]) {
+            err = "declared vertex degrees do not match the edge list";
+            return GPE_ERR_INVALID;
+        }
+    if (g.offsets[V] != g.nbrs.size()) { err = "the header's edge count does not match the vertex degrees"; return GPE_ERR_INVALID; }
     for (uint32_t v = 0; v < V; v++) std::sort(g.nbrs.begin() + g.offsets[v], g.nbrs.begin() + g.offsets[v + 1]);
     return GPE_OK;
 }
