@@ -555,15 +555,7 @@ int download_candidates(gpe_ctx *c, u32 *cand) {
 bool check_query(gpe_ctx *c, u32 nq, const u32 *off, const u32 *nbr, std::string &why) {
     if (nq > GPE_MAX_QUERY_VERTICES) { why = "query has more than GPE_MAX_QUERY_VERTICES vertices"; return false; }
     if (nq == 0) { why = "empty query graph"; return false; }
-    if (off[0] != 0) { why = "query offsets must start at 0"; return false; }
-    for (u32 u = 0; u < nq; u++) {
-        if (off[u + 1] < off[u]) { why = "query offsets not monotone"; return false; }
-        for (u32 j = off[u]; j < off[u + 1]; j++) {
-            if (nbr[j] >= nq) { why = "query neighbour id out of range"; return false; }
-            if (nbr[j] == u) { why = "self loop in query graph"; return false; }
-            if (j > off[u] && nbr[j - 1] >= nbr[j]) { why = "query adjacency must be strictly ascending (simple graph)"; return false; }
-        }
-    }
+    if (!query_csr_ok(nq, off, nbr, why)) return false;
     if (!query_connected(nq, off, nbr)) {
         // custom.h:684-704 reads an uninitialised `next_vertex` for a disconnected query
         why = "disconnected query graph (undefined behaviour in the reference)";

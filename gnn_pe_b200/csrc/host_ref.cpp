@@ -144,6 +144,29 @@ void gen_vde(uint32_t V, const uint32_t *off, const uint32_t *nbr, const uint32_
     }
 }
 
+// A query graph as the C ABI takes it: CSR offsets from 0, adjacency strictly ascending (simple), ids in range, no self
+// loops, every edge listed from both ends.  The reference builds its CSR from a file and never checks (graph.cpp:163-242).
+bool query_csr_ok(uint32_t nq, const uint32_t *off, const uint32_t *nbr, std::string &why) {
+    if (!off || (nq && off[nq] && !nbr)) { why = "null query arrays"; return false; }
+    if (off[0] != 0) { why = "query offsets must start at 0"; return false; }
+    for (uint32_t u = 0; u < nq; u++) {
+        if (off[u + 1] < off[u]) { why = "query offsets not monotone"; return false; }
+        if (off[u + 1] - off[u] >= nq) { why = "query degree out of range"; return false; }
+    }
+    for (uint32_t u = 0; u < nq; u++)
+        for (uint32_t j = off[u]; j < off[u + 1]; j++) {
+            if (nbr[j] >= nq) { why = "query neighbour id out of range"; return false; }
+            if (nbr[j] == u) { why = "self loop in query graph"; return false; }
+            if (j > off[u] && nbr[j - 1] >= nbr[j]) { why = "query adjacency must be strictly ascending (simple graph)"; return false; }
+        }
+    for (uint32_t u = 0; u < nq; u++)
+        for (uint32_t j = off[u]; j < off[u + 1]; j++) {
+            const uint32_t v = nbr[j];
+            if (!std::binary_search(nbr + off[v], nbr + off[v + 1], u)) { why = "query adjacency is not symmetric"; return false; }
+        }
+    return true;
+}
+
 bool query_connected(uint32_t nq, const uint32_t *off, const uint32_t *nbr) {
     if (nq == 0) return true;
     std::vector<char> seen(nq, 0);
@@ -316,7 +339,8 @@ extern "C" int gpe_host_gen_vde(uint32_t V, const uint32_t *offsets, const uint3
 extern "C" int gpe_host_query_plan(uint32_t nq, const uint32_t *q_offsets, const uint32_t *q_nbrs,
                                    const uint32_t *q_labels, uint32_t L, uint32_t e, uint32_t cap, uint32_t *vids,
                                    uint32_t *labels, uint32_t *degs, double *pde, uint32_t *n) try {
-    if (nq > GPE_MAX_QUERY_VERTICES || L < 2 || L > GPE_MAX_QUERY_VERTICES || e == 0) return GPE_ERR_INVALID;
+    if (nq > GPE_MAX_QUERY_VERTICES || L < 2 || L > GPE_MAX_QUERY_VERTICES || e == 0 || !q_offsets || !q_labels) return GPE_ERR_INVALID;
+    if (!gpe::query_csr_ok(nq, q_offsets, q_nbrs, g_host_err)) return GPE_ERR_INVALID;
     gpe::QueryPlan plan;
     gpe::query_plan(nq, q_offsets, q_nbrs, q_labels, L, e, plan);
     uint32_t m = std::min(plan.n, cap);

@@ -30,6 +30,7 @@ struct LabelTable {
 int load_graph_file(const char *path, HostGraph &g, std::string &err);
 void gen_vde(uint32_t V, const uint32_t *off, const uint32_t *nbr, const uint32_t *labels, uint32_t e, double *x,
              double *vde, const LabelTable *table = nullptr);
+bool query_csr_ok(uint32_t nq, const uint32_t *off, const uint32_t *nbr, std::string &why);
 bool query_connected(uint32_t nq, const uint32_t *off, const uint32_t *nbr);
 void query_plan(uint32_t nq, const uint32_t *off, const uint32_t *nbr, const uint32_t *labels, uint32_t L, uint32_t e,
                 QueryPlan &plan, const LabelTable *table = nullptr);

@@ -169,6 +169,11 @@ def test_edge_cases():
     qd = graph_io.csr_from_edges(4, np.array([[0, 1], [2, 3]]), np.array([0, 1, 2, 3]))
     with pytest.raises(gpe.GpeError, match="disconnected"):
         ctx.query_batch([qd])
+    # an edge listed from one end only
+    qa = graph_io.csr_from_edges(3, np.array([[0, 1], [1, 2]]), np.array([0, 1, 2]))
+    qa.nbrs[-1] = 0          # 2 lists 0, 0 does not list 2
+    with pytest.raises(gpe.GpeError, match="symmetric"):
+        ctx.query_batch([qa])
     # empty batch
     assert ctx.query_batch([]).tolist() == []
     # errors: wrong call order and unsupported shapes

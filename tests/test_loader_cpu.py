@@ -68,3 +68,28 @@ def test_random_token_soup_never_crashes(tmp_path_factory, lines):
     # accepted: then it is a consistent CSR
     assert off[0] == 0 and (np.diff(off.astype(np.int64)) >= 0).all() and off[-1] == len(nbr)
     assert (nbr < max(len(lab), 1)).all()
+
+
+# ---- query graphs handed over as arrays (gpe_host_query_plan; the batch calls run the same check) ------------------
+TRIANGLE_TAIL = ([0, 2, 4, 7, 8], [1, 2, 0, 2, 0, 1, 3, 2], [1, 0, 1, 2])
+
+
+def test_query_arrays_well_formed():
+    off, nbr, lab = TRIANGLE_TAIL
+    plan = gpe.host_query_plan(off, nbr, lab, 3, 2)
+    assert len(plan["vids"]) >= 1 and set(plan["vids"].ravel().tolist()) == {0, 1, 2, 3}
+
+
+@pytest.mark.parametrize("off,nbr", [
+    ([1, 2, 4, 7, 8], TRIANGLE_TAIL[1]),                 # offsets do not start at 0
+    ([0, 4, 2, 7, 8], TRIANGLE_TAIL[1]),                 # not monotone
+    ([0, 2, 4, 7, 4000000000], TRIANGLE_TAIL[1]),        # a degree beyond the query
+    (TRIANGLE_TAIL[0], [1, 2, 0, 2, 0, 1, 9, 2]),        # neighbour id out of range
+    (TRIANGLE_TAIL[0], [0, 2, 0, 2, 0, 1, 3, 2]),        # self loop
+    (TRIANGLE_TAIL[0], [2, 1, 0, 2, 0, 1, 3, 2]),        # adjacency not ascending
+    (TRIANGLE_TAIL[0], [1, 1, 0, 2, 0, 1, 3, 2]),        # duplicate edge
+    (TRIANGLE_TAIL[0], [1, 2, 0, 2, 0, 1, 3, 1]),        # 3 lists 1, but 1 does not list 3
+])
+def test_query_arrays_malformed(off, nbr):
+    with pytest.raises(gpe.GpeError):
+        gpe.host_query_plan(off, nbr, TRIANGLE_TAIL[2], 3, 2)
