@@ -326,9 +326,22 @@ extern "C" int gpe_host_load_graph(const char *path, uint32_t *V, uint32_t *E, u
     return GPE_ERR_INVALID;
 }
 
+// Memory safety of a caller's CSR before host code walks it (gpe_set_graph checks the rest -- order, symmetry, simple --
+// on the device).
+static bool data_csr_in_bounds(uint32_t V, const uint32_t *off, const uint32_t *nbr, std::string &why) {
+    if (off[0] != 0) { why = "offsets must start at 0"; return false; }
+    for (uint32_t v = 0; v < V; v++)
+        if (off[v + 1] < off[v]) { why = "offsets not monotone"; return false; }
+    if (off[V] && !nbr) { why = "null neighbour array"; return false; }
+    for (size_t j = 0; j < off[V]; j++)
+        if (nbr[j] >= V) { why = "neighbour id out of range"; return false; }
+    return true;
+}
+
 extern "C" int gpe_host_gen_vde(uint32_t V, const uint32_t *offsets, const uint32_t *nbrs, const uint32_t *labels,
                                 uint32_t e, double *x, double *vde) try {
     if (!offsets || !labels || !x || !vde || e == 0) return GPE_ERR_INVALID;
+    if (!data_csr_in_bounds(V, offsets, nbrs, g_host_err)) return GPE_ERR_INVALID;
     gpe::gen_vde(V, offsets, nbrs, labels, e, x, vde);
     return GPE_OK;
 } catch (const std::exception &ex) {  // e.g. std::bad_alloc: an error code, never an abort through the C ABI
@@ -358,6 +371,7 @@ extern "C" int gpe_host_query_plan(uint32_t nq, const uint32_t *q_offsets, const
 extern "C" int gpe_host_pge_groups(uint32_t V, const uint32_t *offsets, const uint32_t *nbrs, const uint32_t *labels,
                                    uint32_t pl, uint32_t e, double *pg, double *plg, uint8_t *has) try {
     if (!offsets || !labels || !pg || !plg || !has || e == 0 || pl == 0 || pl > GPE_MAX_QUERY_VERTICES) return GPE_ERR_INVALID;
+    if (!data_csr_in_bounds(V, offsets, nbrs, g_host_err)) return GPE_ERR_INVALID;
     std::vector<double> x((size_t)V * e), vde((size_t)V * e);
     gpe::gen_vde(V, offsets, nbrs, labels, e, x.data(), vde.data());
     gpe::pge_groups(V, offsets, nbrs, pl, e, x.data(), vde.data(), pg, plg, has);

@@ -93,3 +93,16 @@ def test_query_arrays_well_formed():
 def test_query_arrays_malformed(off, nbr):
     with pytest.raises(gpe.GpeError):
         gpe.host_query_plan(off, nbr, TRIANGLE_TAIL[2], 3, 2)
+
+
+@pytest.mark.parametrize("off,nbr", [
+    ([1, 2, 4, 7, 8], TRIANGLE_TAIL[1]),
+    ([0, 4, 2, 7, 8], TRIANGLE_TAIL[1]),
+    (TRIANGLE_TAIL[0], [1, 2, 0, 2, 0, 1, 4000000000, 2]),
+])
+def test_data_arrays_out_of_bounds(off, nbr):
+    """Host code that walks a caller's CSR (embeddings, GNN-PGE groups) checks it is memory-safe first."""
+    with pytest.raises(gpe.GpeError):
+        gpe.host_gen_vde(off, nbr, TRIANGLE_TAIL[2], 2)
+    with pytest.raises(gpe.GpeError):
+        gpe.host_pge_groups(off, nbr, TRIANGLE_TAIL[2], 2, 2)
