@@ -23,13 +23,17 @@ from . import graph_io
 
 
 def _read_any(path: str) -> graph_io.CSRGraph:
-    if path.endswith((".gpickle", ".gpickle.gz", ".pkl", ".pickle")):
+    with open(path, "rb") as f:
+        magic = f.read(2)
+    if magic == b"\x1f\x8b" or magic[:1] == b"\x80":   # gzip or a bare pickle (the reference's Test/*.gpickle.gz is the latter)
         import gzip
         import pickle
-        with (gzip.open(path, "rb") if path.endswith(".gz") else open(path, "rb")) as f:
-            G = pickle.load(f)                     # a networkx graph with integer nodes 0..V-1 and a 'label' attribute
+        with (gzip.open(path, "rb") if magic == b"\x1f\x8b" else open(path, "rb")) as f:
+            G = pickle.load(f)                          # a networkx graph with integer nodes 0..V-1 (gnnpe.py:52-53)
         nodes = sorted(G.nodes())
-        labels = np.array([G.nodes[v].get("label", 0) for v in nodes], dtype=np.uint32)
+        if nodes != list(range(len(nodes))):
+            raise ValueError("the pickled graph's nodes are not 0..V-1")
+        labels = np.array([G.nodes[v].get("label", 0) for v in nodes], dtype=np.uint32)   # only the topology is used here
         edges = np.array([(u, v) for u, v in G.edges() if u != v], dtype=np.int64).reshape(-1, 2)
         return graph_io.csr_from_edges(len(nodes), edges, labels)
     return graph_io.read_graph(path)

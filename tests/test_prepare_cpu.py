@@ -49,3 +49,16 @@ def test_pge_variant_and_errors(tmp_path):
     assert os.path.isfile(str(tmp_path / "gnn-pge" / "membership.txt"))
     with pytest.raises(ValueError):
         prepare.partition(g, 0)
+
+
+REF_TEST = "/root/reference/Test/"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TEST + "data_graph.gpickle.gz"), reason="the reference tree is not on this machine")
+def test_reads_the_reference_pickle(tmp_path):
+    """The reference's script takes the networkx pickle of the data graph; the same topology comes out of either file."""
+    pytest.importorskip("networkx")
+    a, b = str(tmp_path / "a") + "/", str(tmp_path / "b") + "/"
+    prepare.main(["--f", a, "--d", REF_TEST + "data_graph.gpickle.gz", "--p", "5", "--partitioner", "rcm"])
+    prepare.main(["--f", b, "--d", REF_TEST + "data_graph.graph", "--p", "5", "--partitioner", "rcm"])
+    assert open(a + "gnn-pe/membership.txt").read() == open(b + "gnn-pe/membership.txt").read()
