@@ -115,3 +115,20 @@ def test_host_mirror_accepts_any_32_bit_label():
     assert vde[1].tobytes() == (x[1] + (x[0] + x[2])).tobytes()
     plan = gpe.host_query_plan(off, nbr, lab, 3, 3)
     assert len(plan["vids"]) >= 1 and set(plan["labels"].ravel().tolist()) <= set(lab.tolist())
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/gpe.h must compile as C99 (no C++ in the signatures) and a C program must link
+    against libgpe.so with nothing but -lgpe (the cgo / JNI / ctypes situation of INTEGRATION.md)."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "gpe.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '    gpe_stats st; gpe_batch b; (void)st; (void)b;\n'
+                   '    printf("%d %llu\\n", gpe_abi_version(), (unsigned long long)gpe_clamp_answer(7, 3));\n'
+                   '    return 0;\n}\n')
+    exe = tmp_path / "t"
+    libdir = os.path.join(ROOT, "gnn_pe_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lgpe", f"-Wl,-rpath,{libdir}"])
+    assert subprocess.check_output([str(exe)]).decode().split() == ["1", "3"]
