@@ -46,14 +46,17 @@ int gpe_abi_version(void);
 /* ---- host-side mirror of the reference's cheap serial steps (pure host code, no GPU) --- */
 
 /* Static_Graph::loadGraphFromFile, libsrc/graph/graph.cpp:163-242.  Two-call pattern: with
- * offsets == NULL only V, E are returned.  nbrs come back sorted ascending per vertex (:231-233). */
+ * offsets == NULL only V, E are returned.  nbrs come back sorted ascending per vertex (:231-233).  A file whose header,
+ * declared degrees and edge list disagree is an error here (the reference reads or writes out of bounds). */
 int gpe_host_load_graph(const char *path, uint32_t *V, uint32_t *E, uint32_t *offsets /*V+1*/,
                         uint32_t *nbrs /*2E*/, uint32_t *labels /*V*/);
 /* gen_vde_x + gen_vde, custom.h:492-544.  x, vde: V x e, row-major. */
 int gpe_host_gen_vde(uint32_t V, const uint32_t *offsets, const uint32_t *nbrs, const uint32_t *labels,
                      uint32_t e, double *x, double *vde);
 /* dfs_query (custom.h:94-119, main.cpp:142-146) + gen_vde(query) + gen_query_pde (custom.h:574-633).
- * Writes at most cap plan paths (vids/labels/degs: n x L, pde: n x L*e) and returns the plan size in *n. */
+ * Writes at most cap plan paths (vids/labels/degs: n x L, pde: n x L*e) and returns the plan size in *n.  The query arrays
+ * are checked first (offsets from 0 and monotone, ids in range, adjacency strictly ascending and symmetric), as in every
+ * batch call. */
 int gpe_host_query_plan(uint32_t nq, const uint32_t *q_offsets, const uint32_t *q_nbrs, const uint32_t *q_labels,
                         uint32_t L, uint32_t e, uint32_t cap, uint32_t *vids, uint32_t *labels, uint32_t *degs,
                         double *pde, uint32_t *n);
