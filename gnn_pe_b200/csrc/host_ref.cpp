@@ -312,6 +312,7 @@ const char *gpe_host_last_error_internal() { return g_host_err.c_str(); }
 
 extern "C" int gpe_host_load_graph(const char *path, uint32_t *V, uint32_t *E, uint32_t *offsets, uint32_t *nbrs,
                                    uint32_t *labels) try {
+    if (!path) { g_host_err = "null path"; return GPE_ERR_INVALID; }
     gpe::HostGraph g;
     int rc = gpe::load_graph_file(path, g, g_host_err);
     if (rc) return rc;

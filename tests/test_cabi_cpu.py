@@ -132,3 +132,26 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
                            str(src), "-o", str(exe), "-L", libdir, "-lgpe", f"-Wl,-rpath,{libdir}"])
     assert subprocess.check_output([str(exe)]).decode().split() == ["1", "3"]
+
+
+def test_null_arguments_never_crash():
+    """Every entry point of include/gpe.h called with all-NULL / zero arguments (no context can exist without a GPU, so
+    this is also what a caller that ignored a failed gpe_create would do): an error code or a harmless value, never a
+    crash.  Runs in a child process so that a crash is a test failure with the function's name, not a dead test run."""
+    import subprocess
+    import sys
+    header = open(os.path.join(ROOT, "include", "gpe.h")).read()
+    protos = re.findall(r"\n(int|uint64_t|void \*|const char \*|void)\s*(gpe_[a-z_0-9]+)\s*\(([^;]*?)\);", header)
+    assert len(protos) == len(gpe.SYMBOLS)
+    calls = [(ret, name, 0 if args.strip() in ("", "void") else args.count(",") + 1) for ret, name, args in protos]
+    child = (
+        "import ctypes as C, sys\n"
+        f"L = C.CDLL({os.path.join(ROOT, 'gnn_pe_b200', 'libgpe.so')!r})\n"
+        f"for ret, name, n in {calls!r}:\n"
+        "    print(name, flush=True)\n"
+        "    f = getattr(L, name); f.restype = C.c_uint64\n"
+        "    r = f(*([C.c_void_p(0)] * n))\n"
+        "    if ret == 'int' and name != 'gpe_abi_version' and (r & 0xffffffff) == 0: sys.exit('accepted NULLs: ' + name)\n"
+        "print('done')\n")
+    r = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("done"), (r.returncode, r.stdout.strip().splitlines()[-1:], r.stderr[-300:])
